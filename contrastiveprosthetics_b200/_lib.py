@@ -1,0 +1,133 @@
+"""ctypes binding of libcpros.so (include/cpros.h) -- the only way the package computes anything.
+
+There is NO CPU fallback: if the shared library is missing or a tensor is not a CUDA tensor the
+call raises.  The library is built in-tree by `build()` (nvcc, sm_100a) so that it travels with
+the repository snapshot to the GPU box.
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG, "csrc")
+SO_PATH = os.path.join(_PKG, "libcpros.so")
+SOURCES = ["version.cu", "gather.cu", "encoder.cu", "head.cu", "vote.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+N_BN, N_FC = 9, 7
+BN_BATCH, BN_BATCH_UPDATE, BN_RUNNING = 0, 1, 2
+ENGINE_SIMT, ENGINE_TC = 0, 1
+
+
+def _stale():
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)] + \
+           [os.path.join(os.path.dirname(_PKG), "include", "cpros.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a into contrastiveprosthetics_b200/libcpros.so."""
+    if not force and not _stale():
+        return SO_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", SO_PATH] + [os.path.join(_CSRC, s) for s in SOURCES]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return SO_PATH
+
+
+class EncoderTensors(ctypes.Structure):
+    _fields_ = [("conv1_w", ctypes.c_void_p), ("conv1_b", ctypes.c_void_p),
+                ("conv2_w", ctypes.c_void_p), ("conv2_b", ctypes.c_void_p),
+                ("fc_w", ctypes.c_void_p * N_FC), ("fc_b", ctypes.c_void_p * N_FC),
+                ("proj_w", ctypes.c_void_p),
+                ("bn_w", ctypes.c_void_p * N_BN), ("bn_b", ctypes.c_void_p * N_BN),
+                ("bn_rm", ctypes.c_void_p * N_BN), ("bn_rv", ctypes.c_void_p * N_BN)]
+
+
+class EncoderOpts(ctypes.Structure):
+    _fields_ = [("bn_mode", ctypes.c_int32), ("engine", ctypes.c_int32),
+                ("bn_momentum", ctypes.c_float), ("bn_eps", ctypes.c_float),
+                ("dropout_p", ctypes.c_float), ("save_for_backward", ctypes.c_int32),
+                ("dropout_seed", ctypes.c_uint64), ("ext_masks", ctypes.c_void_p)]
+
+
+_lib = None
+_vp, _i64, _i32, _sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_size_t
+
+
+def lib():
+    """Load libcpros.so; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(
+            f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). contrastiveprosthetics_b200 has no CPU or PyTorch fallback.")
+    L = ctypes.CDLL(SO_PATH)
+    L.cp_version.restype = ctypes.c_int
+    L.cp_status_string.restype = ctypes.c_char_p
+    L.cp_status_string.argtypes = [ctypes.c_int]
+    L.cp_gather_norm.argtypes = [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp]
+    L.cp_encoder_workspace_bytes.restype = _sz
+    L.cp_encoder_workspace_bytes.argtypes = [_i64, ctypes.POINTER(EncoderOpts)]
+    L.cp_encoder_forward.argtypes = [ctypes.POINTER(EncoderTensors), _vp, _i64, _vp, _vp, _sz,
+                                     ctypes.POINTER(EncoderOpts), _vp]
+    L.cp_encoder_backward.argtypes = [ctypes.POINTER(EncoderTensors), _vp, _i64,
+                                      ctypes.POINTER(EncoderTensors), _vp, _sz,
+                                      ctypes.POINTER(EncoderOpts), _vp]
+    L.cp_linear_workspace_bytes.restype = _sz
+    L.cp_linear_workspace_bytes.argtypes = [_i64, _i32, _i32]
+    L.cp_linear_forward.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _i32, _vp]
+    L.cp_linear_backward.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz, _i32, _vp]
+    L.cp_head_workspace_bytes.restype = _sz
+    L.cp_head_workspace_bytes.argtypes = [_i64]
+    L.cp_head_forward_backward.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                           _vp, _sz, _vp]
+    L.cp_logits_loss.argtypes = [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
+    L.cp_vote_eval.argtypes = [_vp, _i64, _i32, _i32, _vp, _vp, _vp]
+    L.cp_rank_rows.argtypes = [_vp, _i64, _vp, _vp]
+    L.cp_subset_eval.argtypes = [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp]
+    for name in ("cp_gather_norm", "cp_encoder_forward", "cp_encoder_backward", "cp_linear_forward",
+                 "cp_linear_backward", "cp_head_forward_backward", "cp_logits_loss", "cp_vote_eval",
+                 "cp_rank_rows", "cp_subset_eval"):
+        getattr(L, name).restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+EXPORTS = ["cp_version", "cp_status_string", "cp_gather_norm", "cp_encoder_workspace_bytes",
+           "cp_encoder_forward", "cp_encoder_backward", "cp_linear_workspace_bytes",
+           "cp_linear_forward", "cp_linear_backward", "cp_head_workspace_bytes",
+           "cp_head_forward_backward", "cp_logits_loss", "cp_vote_eval", "cp_rank_rows",
+           "cp_subset_eval"]
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = lib().cp_status_string(status).decode()
+        raise RuntimeError(f"libcpros {what}: status {status}: {msg}")
+
+
+def ptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL).  Refuses CPU tensors."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("libcpros takes CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("libcpros needs contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"expected {dtype}, got {t.dtype}")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

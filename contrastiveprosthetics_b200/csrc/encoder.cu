@@ -1,0 +1,357 @@
+// K2: EMG encoder forward / backward orchestration (EMGNet, models.py:230-342).
+//
+//   x (n,12) -> conv k3 (1->64) -> ReLU -> BN2d -> conv k3 (64->64) -> ReLU -> BN2d -> flatten
+//            -> 7 x [Linear -> ReLU -> BN1d (-> Dropout after blocks 4..7)] -> Linear 512->16
+//
+// HBM layout (fp32, all inside the caller's workspace):
+//   conv stages   [n*12, 64]   position-major, channel-contiguous: the k=3 convolution becomes an
+//                              implicit GEMM whose A row (n,p) is the 192 contiguous floats that
+//                              start at row (n,p-1); the flatten is index p*64+c, so fc1 runs on a
+//                              column-permuted copy of its weight (prep_weights_kernel).
+//   linear stages [n, 512]
+//   per stage: Y (post-ReLU, pre-BN; kept for backward) and A (post-BN/dropout = next GEMM input).
+// BatchNorm statistics are produced by the GEMM / conv epilogues as per-CTA partial column sums
+// (no second pass over the activation) and finalised in double precision.
+#include <algorithm>
+#include "gemm_simt.cuh"
+#include "encoder_kernels.cuh"
+
+namespace {
+
+constexpr int F_CONV = 64;
+constexpr int F_FC = 512;
+constexpr int K_FC1 = 768;
+constexpr int WGRAD_SPLITS_MAX = 32;                       // at the largest (512x768) weight
+constexpr size_t WPART_ELEMS = (size_t)WGRAD_SPLITS_MAX * F_FC * K_FC1;
+
+struct Ws {
+    float *X0, *Y1, *A1, *Y2, *A2;
+    float *Y[CP_N_FC], *A[CP_N_FC];
+    uint8_t* keep[4];
+    float *G0, *G1;
+    float *mean[CP_N_BN], *istd[CP_N_BN], *scale[CP_N_BN], *shift[CP_N_BN];
+    float *pa, *pb;            // per-CTA column partials
+    float *m1, *m2;
+    float *wpart;              // split-K weight-gradient partials
+    float *Wc2, *Wc2d, *W1p;
+    float *ppart;              // projection / conv1 weight-gradient partials
+    size_t bytes;
+};
+
+struct Carver {
+    char* base;
+    size_t off = 0;
+    template <typename Tp> Tp* take(size_t n) {
+        Tp* p = reinterpret_cast<Tp*>(base + off);
+        off += cp_align(n * sizeof(Tp));
+        return p;
+    }
+};
+
+int64_t partial_rows(int64_t n) {
+    // the largest number of per-CTA partial rows any stage produces
+    return cp_cdiv(n * 12, 128) + cp_cdiv(n, 128) + 8;
+}
+
+Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
+    Ws w;
+    Carver c{reinterpret_cast<char*>(base)};
+    const bool save = o->save_for_backward != 0;
+    const size_t conv_elems = (size_t)n * 12 * F_CONV, fc_elems = (size_t)n * F_FC;
+    w.X0 = c.take<float>((size_t)n * 12);
+    if (save) {
+        w.Y1 = c.take<float>(conv_elems); w.A1 = c.take<float>(conv_elems);
+        w.Y2 = c.take<float>(conv_elems); w.A2 = c.take<float>(conv_elems);
+        for (int l = 0; l < CP_N_FC; ++l) { w.Y[l] = c.take<float>(fc_elems); w.A[l] = c.take<float>(fc_elems); }
+        w.G0 = c.take<float>(conv_elems);
+        w.G1 = c.take<float>(conv_elems);
+    } else {
+        // inference: every stage reuses one Y and two alternating A buffers
+        float* y = c.take<float>(conv_elems);
+        float* a0 = c.take<float>(conv_elems);
+        float* a1 = c.take<float>(conv_elems);
+        w.Y1 = w.Y2 = y; w.A1 = a0; w.A2 = a1;
+        for (int l = 0; l < CP_N_FC; ++l) { w.Y[l] = y; w.A[l] = (l & 1) ? a1 : a0; }
+        w.G0 = w.G1 = nullptr;
+    }
+    for (int d = 0; d < 4; ++d) w.keep[d] = (o->dropout_p > 0.f) ? c.take<uint8_t>(fc_elems) : nullptr;
+    for (int l = 0; l < CP_N_BN; ++l) {
+        w.mean[l] = c.take<float>(F_FC); w.istd[l] = c.take<float>(F_FC);
+        w.scale[l] = c.take<float>(F_FC); w.shift[l] = c.take<float>(F_FC);
+    }
+    const size_t pr = (size_t)partial_rows(n);
+    w.pa = c.take<float>(pr * F_FC);
+    w.pb = c.take<float>(pr * F_FC);
+    w.m1 = c.take<float>(F_FC);
+    w.m2 = c.take<float>(F_FC);
+    w.wpart = save ? c.take<float>(WPART_ELEMS) : nullptr;
+    w.Wc2 = c.take<float>(64 * 192);
+    w.Wc2d = c.take<float>(64 * 192);
+    w.W1p = c.take<float>(F_FC * K_FC1);
+    w.ppart = save ? c.take<float>((size_t)cp_cdiv(n, PROJ_W_ROWS) * CP_EMB_DIM * 512 +
+                                   (size_t)cp_cdiv(n * 12, 1024) * 3 * 64)
+                   : nullptr;
+    w.bytes = c.off;
+    return w;
+}
+
+inline unsigned ew_grid(int64_t n_vec) {
+    int64_t b = cp_cdiv(n_vec, 256);
+    const int64_t cap = (int64_t)CP_NUM_SMS * 16;
+    return (unsigned)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+// C = act(A . B^T + bias) (+ column statistics partials)
+template <int BM, int BN, int BMODE, bool ACONV>
+int launch_nt(const float* A, int64_t M, int K, int lda, const float* B, int N, int ldb, const float* bias,
+              float* C, int ldc, float* psum, float* psq, int relu, cudaStream_t st) {
+    if (K % GEMM_BK != 0 || N % BN != 0) return CP_ERR_ARG;
+    GemmNT g{A, M, K, lda, B, N, ldb, bias, C, ldc, psum, psq, relu};
+    const int64_t tiles = cp_cdiv(M, BM) * (N / BN);
+    gemm_nt_kernel<BM, BN, BMODE, ACONV><<<(unsigned)tiles, 256, 0, st>>>(g);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+// dW[Mo,No] = G^T . A, split over row slabs; out written through wgrad_reduce (mode = re-layout)
+template <int BM, int BN, bool ACONV>
+int launch_wgrad(const float* G, int ldg, int Mo, const float* A, int lda, int No, int64_t R, float* wpart,
+                 float* out, int mode, cudaStream_t st) {
+    if (Mo % BM != 0 || No % BN != 0) return CP_ERR_ARG;
+    const int tiles = (Mo / BM) * (No / BN);
+    constexpr int resident = BM * BN >= 128 * 128 ? 2 : 4;      // CTAs per SM the tile shape allows
+    int S = (resident * CP_NUM_SMS + tiles - 1) / tiles;        // one full wave of 148 SMs
+    const int64_t max_s = cp_cdiv(R, 8 * GEMM_BK);
+    if (S > max_s) S = (int)max_s;
+    const int64_t cap = (int64_t)(WPART_ELEMS / ((size_t)Mo * No));
+    if (S > cap) S = (int)cap;
+    if (S < 1) S = 1;
+    int64_t rps = cp_cdiv(cp_cdiv(R, S), GEMM_BK) * GEMM_BK;
+    S = (int)cp_cdiv(R, rps);
+    GemmTN g{G, ldg, Mo, A, lda, No, R, rps, wpart};
+    dim3 grid(No / BN, Mo / BM, S);
+    gemm_tn_kernel<BM, BN, ACONV><<<grid, 256, 0, st>>>(g);
+    CP_CHECK_LAUNCH();
+    wgrad_reduce_kernel<<<(unsigned)cp_cdiv((int64_t)Mo * No, 256), 256, 0, st>>>(wpart, S, Mo, No, out, mode);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+int bn_finalize(const Ws& w, int l, int F, int P, int64_t R, const cp_encoder_tensors* p,
+                const cp_encoder_opts* o, cudaStream_t st) {
+    if (o->bn_mode != CP_BN_BATCH && (!p->bn_rm[l] || !p->bn_rv[l])) return CP_ERR_ARG;
+    bn_finalize_kernel<<<F / 32, 1024, 0, st>>>(w.pa, w.pb, P, F, R, p->bn_w[l], p->bn_b[l], p->bn_rm[l],
+                                                p->bn_rv[l], o->bn_mode, o->bn_momentum, o->bn_eps,
+                                                w.mean[l], w.istd[l], w.scale[l], w.shift[l]);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+template <int F>
+int bn_apply(const float* y, float* a, int64_t R, const Ws& w, int l, const uint8_t* keep, float inv_keep,
+             cudaStream_t st) {
+    bn_apply_kernel<F><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, R, w.scale[l], w.shift[l], keep, inv_keep);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+// BN backward + ReLU backward of stage l:  g (grad w.r.t. stage output A) -> gz (grad w.r.t. the
+// pre-activation), d_gamma, d_beta, d_bias
+template <int F>
+int bn_backward(const float* g, const float* y, float* gz, int64_t R, const Ws& w, int l,
+                const uint8_t* keep, float inv_keep, const float* gamma, float* d_gamma, float* d_beta,
+                float* d_bias, cudaStream_t st) {
+    const int P = (int)cp_cdiv(R, ColMap<F>::ROWS);
+    bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb);
+    CP_CHECK_LAUNCH();
+    bn_bwd_finalize_kernel<<<F / 32, 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta);
+    CP_CHECK_LAUNCH();
+    bn_bwd_apply_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], gamma, w.m1, w.m2,
+                                              gz, w.pa);
+    CP_CHECK_LAUNCH();
+    colsum_finalize_kernel<<<F / 32, 1024, 0, st>>>(w.pa, P, F, d_bias, 0);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+#define CP_TRY(expr)                 \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ != CP_OK) return rc__; \
+    } while (0)
+
+bool opts_ok(const cp_encoder_opts* o) {
+    return o && o->bn_mode >= 0 && o->bn_mode <= 2 && o->dropout_p >= 0.f && o->dropout_p < 1.f;
+}
+
+}  // namespace
+
+extern "C" size_t cp_encoder_workspace_bytes(int64_t n, const cp_encoder_opts* opts) {
+    if (n <= 0 || !opts_ok(opts)) return 0;
+    return carve(nullptr, n, opts).bytes;
+}
+
+extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, int64_t n, float* emb,
+                                  void* workspace, size_t workspace_bytes, const cp_encoder_opts* o,
+                                  void* stream) {
+    if (!p || !x || !emb || !workspace || n <= 0 || !opts_ok(o)) return CP_ERR_ARG;
+    if (o->engine != CP_ENGINE_SIMT) return CP_ERR_UNSUPPORTED;
+    if (((uintptr_t)workspace) % 256 != 0) return CP_ERR_ARG;
+    const Ws w = carve(workspace, n, o);
+    if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t R12 = n * 12;
+
+    prep_weights_kernel<<<(F_FC * K_FC1 + 255) / 256, 256, 0, st>>>(p->conv2_w, p->fc_w[0], w.Wc2, w.Wc2d, w.W1p);
+    CP_CHECK_LAUNCH();
+    CP_CUDA(cudaMemcpyAsync(w.X0, x, sizeof(float) * R12, cudaMemcpyDeviceToDevice, st));
+
+    // conv1 -> ReLU (+stats) -> BN
+    const int P1 = (int)cp_cdiv(R12, ColMap<F_CONV>::ROWS);
+    conv1_fwd_kernel<<<P1, 256, 0, st>>>(w.X0, R12, p->conv1_w, p->conv1_b, w.Y1, w.pa, w.pb);
+    CP_CHECK_LAUNCH();
+    CP_TRY(bn_finalize(w, 0, F_CONV, P1, R12, p, o, st));
+    CP_TRY(bn_apply<F_CONV>(w.Y1, w.A1, R12, w, 0, nullptr, 1.f, st));
+
+    // conv2 as implicit GEMM [n*12, 192] x [64, 192]^T
+    CP_TRY((launch_nt<128, 64, 0, true>(w.A1, R12, 192, 64, w.Wc2, 64, 192, p->conv2_b, w.Y2, 64, w.pa, w.pb, 1, st)));
+    CP_TRY(bn_finalize(w, 1, F_CONV, (int)cp_cdiv(R12, 128), R12, p, o, st));
+    CP_TRY(bn_apply<F_CONV>(w.Y2, w.A2, R12, w, 1, nullptr, 1.f, st));
+
+    // 7 x Linear -> ReLU -> BN (-> Dropout)
+    const float inv_keep = o->dropout_p > 0.f ? 1.f / (1.f - o->dropout_p) : 1.f;
+    for (int l = 0; l < CP_N_FC; ++l) {
+        const float* in = l == 0 ? w.A2 : w.A[l - 1];
+        const int K = l == 0 ? K_FC1 : F_FC;
+        const float* W = l == 0 ? w.W1p : p->fc_w[l];
+        CP_TRY((launch_nt<128, 128, 0, false>(in, n, K, K, W, F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb, 1, st)));
+        CP_TRY(bn_finalize(w, 2 + l, F_FC, (int)cp_cdiv(n, 128), n, p, o, st));
+        const uint8_t* keep = nullptr;
+        if (l >= 3 && o->dropout_p > 0.f) {
+            const int d = l - 3;
+            if (o->ext_masks) {
+                CP_CUDA(cudaMemcpyAsync(w.keep[d], o->ext_masks + (size_t)d * n * F_FC, (size_t)n * F_FC,
+                                        cudaMemcpyDeviceToDevice, st));
+            } else {
+                dropout_mask_kernel<<<ew_grid(n * (F_FC / 4)), 256, 0, st>>>(w.keep[d], n * (F_FC / 4), o->dropout_p,
+                                                                          o->dropout_seed, (uint64_t)d);
+                CP_CHECK_LAUNCH();
+            }
+            keep = w.keep[d];
+        }
+        CP_TRY(bn_apply<F_FC>(w.Y[l], w.A[l], n, w, 2 + l, keep, inv_keep, st));
+    }
+    // projection 512 -> 16
+    proj_fwd_kernel<<<(unsigned)std::min<int64_t>(cp_cdiv(n, 8), (int64_t)CP_NUM_SMS * 4), 256, 0, st>>>(
+        w.A[CP_N_FC - 1], p->proj_w, emb, n);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_emb, int64_t n,
+                                   const cp_encoder_tensors* gr, void* workspace, size_t workspace_bytes,
+                                   const cp_encoder_opts* o, void* stream) {
+    if (!p || !d_emb || !gr || !workspace || n <= 0 || !opts_ok(o)) return CP_ERR_ARG;
+    if (o->engine != CP_ENGINE_SIMT) return CP_ERR_UNSUPPORTED;
+    if (!o->save_for_backward || o->bn_mode == CP_BN_RUNNING) return CP_ERR_UNSUPPORTED;
+    const Ws w = carve(workspace, n, o);
+    if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t R12 = n * 12;
+    const float inv_keep = o->dropout_p > 0.f ? 1.f / (1.f - o->dropout_p) : 1.f;
+
+    // projection
+    const int Pp = (int)cp_cdiv(n, PROJ_W_ROWS);
+    proj_bwd_weight_kernel<<<Pp, 256, 0, st>>>(d_emb, w.A[CP_N_FC - 1], n, w.ppart);
+    CP_CHECK_LAUNCH();
+    colsum_finalize_kernel<<<CP_EMB_DIM * 512 / 32, 1024, 0, st>>>(w.ppart, Pp, CP_EMB_DIM * 512, gr->proj_w, 0);
+    CP_CHECK_LAUNCH();
+    proj_bwd_data_kernel<<<(unsigned)std::min<int64_t>(cp_cdiv(n, 2), (int64_t)CP_NUM_SMS * 8), 256, 0, st>>>(
+        d_emb, p->proj_w, w.G0, n);
+    CP_CHECK_LAUNCH();
+
+    // linear blocks, last to first.  G0 = grad w.r.t. block output, G1 = grad w.r.t. pre-activation
+    for (int l = CP_N_FC - 1; l >= 0; --l) {
+        const uint8_t* keep = (l >= 3 && o->dropout_p > 0.f) ? w.keep[l - 3] : nullptr;
+        CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], w.G1, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l], gr->bn_w[2 + l],
+                                 gr->bn_b[2 + l], gr->fc_b[l], st));
+        if (l > 0) {
+            CP_TRY((launch_wgrad<128, 128, false>(w.G1, F_FC, F_FC, w.A[l - 1], F_FC, F_FC, n, w.wpart, gr->fc_w[l], 0, st)));
+            CP_TRY((launch_nt<128, 128, 1, false>(w.G1, n, F_FC, F_FC, p->fc_w[l], F_FC, F_FC, nullptr, w.G0, F_FC,
+                                                  nullptr, nullptr, 0, st)));
+        } else {
+            CP_TRY((launch_wgrad<128, 128, false>(w.G1, F_FC, F_FC, w.A2, K_FC1, K_FC1, n, w.wpart, gr->fc_w[0], 1, st)));
+            CP_TRY((launch_nt<128, 128, 1, false>(w.G1, n, F_FC, F_FC, w.W1p, K_FC1, K_FC1, nullptr, w.G0, K_FC1,
+                                                  nullptr, nullptr, 0, st)));
+        }
+    }
+    // conv2 block: G0 is [n*12, 64] (same memory order as the [n,768] position-major flatten)
+    CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, w.G1, R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1], gr->bn_b[1],
+                               gr->conv2_b, st));
+    CP_CUDA(cudaMemsetAsync(gr->conv2_w, 0, sizeof(float) * 64 * 64 * 9, st));
+    CP_TRY((launch_wgrad<64, 64, true>(w.G1, 64, 64, w.A1, 64, 192, R12, w.wpart, gr->conv2_w, 2, st)));
+    CP_TRY((launch_nt<128, 64, 0, true>(w.G1, R12, 192, 64, w.Wc2d, 64, 192, nullptr, w.G0, 64, nullptr, nullptr, 0, st)));
+    // conv1 block
+    CP_TRY(bn_backward<F_CONV>(w.G0, w.Y1, w.G1, R12, w, 0, nullptr, 1.f, p->bn_w[0], gr->bn_w[0], gr->bn_b[0],
+                               gr->conv1_b, st));
+    const int P1 = (int)cp_cdiv(R12, ColMap<F_CONV>::ROWS);
+    float* c1part = w.ppart + (size_t)Pp * CP_EMB_DIM * 512;
+    conv1_bwd_kernel<<<P1, 256, 0, st>>>(w.G1, w.X0, R12, c1part);
+    CP_CHECK_LAUNCH();
+    CP_CUDA(cudaMemsetAsync(gr->conv1_w, 0, sizeof(float) * 64 * 9, st));
+    colsum_finalize_kernel<<<3 * 64 / 32, 1024, 0, st>>>(c1part, P1, 3 * 64, gr->conv1_w, 1);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+// ------------------------------------------------------------------- layer-level entry points
+extern "C" size_t cp_linear_workspace_bytes(int64_t M, int N, int K) {
+    const size_t part = cp_align((size_t)cp_cdiv(M, 128) * N * sizeof(float));
+    return 2 * part + cp_align(WPART_ELEMS * sizeof(float));
+}
+
+extern "C" int cp_linear_forward(const float* A, const float* W, const float* bias, float* Y, int64_t M,
+                                 int N, int K, int relu, float* col_sum, float* col_sqsum, void* workspace,
+                                 size_t workspace_bytes, int engine, void* stream) {
+    if (!A || !W || !Y || M <= 0 || N <= 0 || K <= 0) return CP_ERR_ARG;
+    if (engine != CP_ENGINE_SIMT) return CP_ERR_UNSUPPORTED;
+    if ((col_sum || col_sqsum) && (!col_sum || !col_sqsum || !workspace)) return CP_ERR_ARG;
+    if (col_sum && workspace_bytes < cp_linear_workspace_bytes(M, N, K)) return CP_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t part = cp_align((size_t)cp_cdiv(M, 128) * N * sizeof(float));
+    float* pa = col_sum ? reinterpret_cast<float*>(workspace) : nullptr;
+    float* pb = col_sum ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + part) : nullptr;
+    if (N % 128 == 0) CP_TRY((launch_nt<128, 128, 0, false>(A, M, K, K, W, N, K, bias, Y, N, pa, pb, relu, st)));
+    else CP_TRY((launch_nt<128, 64, 0, false>(A, M, K, K, W, N, K, bias, Y, N, pa, pb, relu, st)));
+    if (col_sum) {
+        const int P = (int)cp_cdiv(M, 128);
+        colsum_finalize_kernel<<<(N + 31) / 32, 1024, 0, st>>>(pa, P, N, col_sum, 0);
+        CP_CHECK_LAUNCH();
+        colsum_finalize_kernel<<<(N + 31) / 32, 1024, 0, st>>>(pb, P, N, col_sqsum, 0);
+        CP_CHECK_LAUNCH();
+    }
+    return CP_OK;
+}
+
+extern "C" int cp_linear_backward(const float* G, const float* A, const float* W, float* dA, float* dW,
+                                  float* db, int64_t M, int N, int K, void* workspace, size_t workspace_bytes,
+                                  int engine, void* stream) {
+    if (!G || !A || !W || !workspace || M <= 0 || N % 128 != 0 || K % 128 != 0) return CP_ERR_ARG;
+    if ((size_t)N * K > WPART_ELEMS) return CP_ERR_ARG;
+    if (engine != CP_ENGINE_SIMT) return CP_ERR_UNSUPPORTED;
+    if (workspace_bytes < cp_linear_workspace_bytes(M, N, K)) return CP_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t part = cp_align((size_t)cp_cdiv(M, 128) * N * sizeof(float));
+    float* wpart = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 2 * part);
+    if (dA) CP_TRY((launch_nt<128, 128, 1, false>(G, M, N, N, W, K, K, nullptr, dA, K, nullptr, nullptr, 0, st)));
+    if (dW) CP_TRY((launch_wgrad<128, 128, false>(G, N, N, A, K, K, M, wpart, dW, 0, st)));
+    if (db) {
+        float* pa = reinterpret_cast<float*>(workspace);
+        const int P = (int)cp_cdiv(M, 128);
+        colsum_rows_kernel<<<dim3((N + 31) / 32, P), 256, 0, st>>>(G, M, N, pa);
+        CP_CHECK_LAUNCH();
+        colsum_finalize_kernel<<<(N + 31) / 32, 1024, 0, st>>>(pa, P, N, db, 0);
+        CP_CHECK_LAUNCH();
+    }
+    return CP_OK;
+}

@@ -1,0 +1,468 @@
+// Non-GEMM kernels of the EMG encoder: k=3 conv on 1 input channel, BatchNorm/AdaBN statistics
+// finalisation, BN apply (+dropout), BN backward (reduce / apply fused with the ReLU mask and the
+// bias gradient), the 512->16 projection, weight re-layouts.  All fp32; all HBM-bound: each
+// activation is read/written in 16-byte lanes, per-column reductions use register accumulators
+// + one shared-memory step and leave deterministic per-CTA partials (no float atomics).
+//
+// Activation layout: [rows, F] row-major, F = 64 (conv stages, rows = windows*12, channel
+// contiguous) or F = 512 (linear stages, rows = windows).
+#pragma once
+#include "common.cuh"
+#include <curand_kernel.h>
+
+template <int F> struct ColMap {
+    static constexpr int QX = F / 4;            // float4 column groups
+    static constexpr int RY = 256 / QX;         // row lanes per CTA
+    static constexpr int ROWS = F == 512 ? 128 : 1024;   // rows per CTA (64 per thread)
+};
+
+// sum over the RY row lanes of a CTA; result for column c valid in threads with ry == 0
+template <int F>
+__device__ __forceinline__ void block_col_reduce(float (&v)[4], float* red /*[RY][F]*/, int qx, int ry) {
+    constexpr int RY = ColMap<F>::RY;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[ry * F + qx * 4 + j] = v[j];
+    __syncthreads();
+    if (ry == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float s = 0.f;
+            for (int y = 0; y < RY; ++y) s += red[y * F + qx * 4 + j];
+            v[j] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ conv1
+// y1[(n,p), c] = relu(b[c] + sum_tap w[c,tap] * x[n, p+tap-1])   (models.py:255-256; a 3x3 conv
+// with padding 1 on a 1x12 image only ever sees the middle kernel row)
+__global__ void __launch_bounds__(256)
+conv1_fwd_kernel(const float* __restrict__ x, int64_t R /* = n*12 */, const float* __restrict__ w9,
+                 const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ psum,
+                 float* __restrict__ psq) {
+    constexpr int F = 64;
+    __shared__ float red[ColMap<F>::RY * F];
+    const int qx = threadIdx.x % 16, ry = threadIdx.x / 16;
+    float w[4][3], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = qx * 4 + j;
+        b[j] = __ldg(bias + c);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) w[j][t] = __ldg(w9 + c * 9 + 3 + t);
+    }
+    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    const int64_t r0 = (int64_t)blockIdx.x * ColMap<F>::ROWS;
+    for (int k = ry; k < ColMap<F>::ROWS; k += ColMap<F>::RY) {
+        const int64_t r = r0 + k;
+        if (r >= R) break;
+        const int p = (int)(r % 12);
+        const float xm = p > 0 ? __ldg(x + r - 1) : 0.f;
+        const float x0 = __ldg(x + r);
+        const float xp = p < 11 ? __ldg(x + r + 1) : 0.f;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = b[j];
+            a = fmaf(w[j][0], xm, a);
+            a = fmaf(w[j][1], x0, a);
+            a = fmaf(w[j][2], xp, a);
+            v[j] = fmaxf(a, 0.f);
+            s[j] += v[j];
+            q[j] = fmaf(v[j], v[j], q[j]);
+        }
+        *reinterpret_cast<float4*>(y + r * F + qx * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    block_col_reduce<F>(s, red, qx, ry);
+    block_col_reduce<F>(q, red, qx, ry);
+    if (ry == 0) {
+        *reinterpret_cast<float4*>(psum + (int64_t)blockIdx.x * F + qx * 4) = make_float4(s[0], s[1], s[2], s[3]);
+        *reinterpret_cast<float4*>(psq + (int64_t)blockIdx.x * F + qx * 4) = make_float4(q[0], q[1], q[2], q[3]);
+    }
+}
+
+// dW1[c,tap] = sum_r gz[r,c] * x[r+tap-1]; partial[blk][tap][64]
+__global__ void __launch_bounds__(256)
+conv1_bwd_kernel(const float* __restrict__ gz, const float* __restrict__ x, int64_t R,
+                 float* __restrict__ partial) {
+    constexpr int F = 64;
+    __shared__ float red[ColMap<F>::RY * F];
+    const int qx = threadIdx.x % 16, ry = threadIdx.x / 16;
+    float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+    const int64_t r0 = (int64_t)blockIdx.x * ColMap<F>::ROWS;
+    for (int k = ry; k < ColMap<F>::ROWS; k += ColMap<F>::RY) {
+        const int64_t r = r0 + k;
+        if (r >= R) break;
+        const int p = (int)(r % 12);
+        const float xm = p > 0 ? __ldg(x + r - 1) : 0.f;
+        const float x0 = __ldg(x + r);
+        const float xp = p < 11 ? __ldg(x + r + 1) : 0.f;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gz + r * F + qx * 4));
+        const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            a0[j] = fmaf(gv[j], xm, a0[j]);
+            a1[j] = fmaf(gv[j], x0, a1[j]);
+            a2[j] = fmaf(gv[j], xp, a2[j]);
+        }
+    }
+    block_col_reduce<F>(a0, red, qx, ry);
+    block_col_reduce<F>(a1, red, qx, ry);
+    block_col_reduce<F>(a2, red, qx, ry);
+    if (ry == 0) {
+        float* o = partial + (int64_t)blockIdx.x * 3 * F;
+        *reinterpret_cast<float4*>(o + 0 * F + qx * 4) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+        *reinterpret_cast<float4*>(o + 1 * F + qx * 4) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+        *reinterpret_cast<float4*>(o + 2 * F + qx * 4) = make_float4(a2[0], a2[1], a2[2], a2[3]);
+    }
+}
+
+// ------------------------------------------------------------------------ partial reductions
+// Sum P per-CTA partial rows of width `width` in double.  CTA = 32 columns x 32 partial lanes.
+__device__ __forceinline__ double reduce_partials(const float* __restrict__ part, int P, int width,
+                                                  int col, int lane, double* sm /*[32][33]*/) {
+    double s = 0.0;
+    if (col < width)
+        for (int p = lane; p < P; p += 32) s += (double)__ldg(part + (int64_t)p * width + col);
+    const int cx = threadIdx.x % 32;
+    sm[lane * 33 + cx] = s;
+    __syncthreads();
+    double t = 0.0;
+    if (lane == 0)
+        for (int l = 0; l < 32; ++l) t += sm[l * 33 + cx];
+    __syncthreads();
+    return t;      // valid for lane == 0
+}
+
+// BatchNorm statistics -> mean, inv-std, and the affine (scale, shift) the apply kernels use:
+// y_bn = x*scale + shift with scale = gamma*istd, shift = beta - mean*scale (same arrangement as
+// torch's CPU batch-norm transform).  mode: CP_BN_BATCH / _BATCH_UPDATE / _RUNNING.
+__global__ void __launch_bounds__(1024)
+bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int P, int F,
+                   int64_t R, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ run_mean, float* __restrict__ run_var, int mode, float momentum,
+                   float eps, float* __restrict__ mean_o, float* __restrict__ istd_o,
+                   float* __restrict__ scale_o, float* __restrict__ shift_o) {
+    __shared__ double sm[32 * 33];
+    const int col = blockIdx.x * 32 + threadIdx.x % 32, lane = threadIdx.x / 32;
+    double mean, var;
+    if (mode == CP_BN_RUNNING) {
+        if (lane != 0 || col >= F) return;
+        mean = (double)run_mean[col];
+        var = (double)run_var[col];
+    } else {
+        const double s = reduce_partials(psum, P, F, col, lane, sm);
+        const double q = reduce_partials(psq, P, F, col, lane, sm);
+        if (lane != 0 || col >= F) return;
+        mean = s / (double)R;
+        var = q / (double)R - mean * mean;          // biased variance (normalisation)
+        if (var < 0.0) var = 0.0;
+        if (mode == CP_BN_BATCH_UPDATE) {
+            const double unbiased = R > 1 ? var * (double)R / (double)(R - 1) : var;
+            run_mean[col] = (float)((1.0 - (double)momentum) * (double)run_mean[col] + (double)momentum * mean);
+            run_var[col] = (float)((1.0 - (double)momentum) * (double)run_var[col] + (double)momentum * unbiased);
+        }
+    }
+    const float istd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[col] * istd;
+    mean_o[col] = (float)mean;
+    istd_o[col] = istd;
+    scale_o[col] = sc;
+    shift_o[col] = beta[col] - (float)mean * sc;
+}
+
+// ---------------------------------------------------------------------------------- BN apply
+// a = y*scale + shift, then (linear blocks 4..7) dropout: a * keep / (1-p)   (models.py:282-297)
+template <int F>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, int64_t R,
+                const float* __restrict__ scale, const float* __restrict__ shift,
+                const uint8_t* __restrict__ keep, float inv_keep) {
+    const int64_t total = R * (F / 4);
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < total;
+         v += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(v % (F / 4)) * 4;
+        const float4 x = __ldg(reinterpret_cast<const float4*>(y) + v);
+        const float4 s = __ldg(reinterpret_cast<const float4*>(scale + c));
+        const float4 t = __ldg(reinterpret_cast<const float4*>(shift + c));
+        float4 o = make_float4(fmaf(x.x, s.x, t.x), fmaf(x.y, s.y, t.y), fmaf(x.z, s.z, t.z), fmaf(x.w, s.w, t.w));
+        if (keep) {
+            const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(keep) + v);
+            o.x = m.x ? o.x * inv_keep : 0.f; o.y = m.y ? o.y * inv_keep : 0.f;
+            o.z = m.z ? o.z * inv_keep : 0.f; o.w = m.w ? o.w * inv_keep : 0.f;
+        }
+        reinterpret_cast<float4*>(a)[v] = o;
+    }
+}
+
+// keep mask ~ Bernoulli(1-p), Philox4x32-10 keyed by (seed, layer), counter = element/4
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(uint8_t* __restrict__ keep, int64_t n4, float p, uint64_t seed, uint64_t layer) {
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n4;
+         v += (int64_t)gridDim.x * blockDim.x) {
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, /*subsequence=*/(unsigned long long)v, /*offset=*/layer * 4ull, &st);
+        const float4 u = curand_uniform4(&st);          // (0,1]
+        uchar4 m;
+        m.x = u.x > p; m.y = u.y > p; m.z = u.z > p; m.w = u.w > p;
+        reinterpret_cast<uchar4*>(keep)[v] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------- BN backward
+// g' = g * keep/(1-p);  xh = (y - mean)*istd;  partials: sum g', sum g'*xh
+template <int F>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t R,
+                     const uint8_t* __restrict__ keep, float inv_keep, const float* __restrict__ mean,
+                     const float* __restrict__ istd, float* __restrict__ p1, float* __restrict__ p2) {
+    __shared__ float red[ColMap<F>::RY * F];
+    const int qx = threadIdx.x % ColMap<F>::QX, ry = threadIdx.x / ColMap<F>::QX;
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + qx * 4));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(istd + qx * 4));
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    const int64_t r0 = (int64_t)blockIdx.x * ColMap<F>::ROWS;
+    for (int k = ry; k < ColMap<F>::ROWS; k += ColMap<F>::RY) {
+        const int64_t r = r0 + k;
+        if (r >= R) break;
+        const int64_t v = r * (F / 4) + qx;
+        float4 gv = __ldg(reinterpret_cast<const float4*>(g) + v);
+        const float4 yv = __ldg(reinterpret_cast<const float4*>(y) + v);
+        if (keep) {
+            const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(keep) + v);
+            gv.x = m.x ? gv.x * inv_keep : 0.f; gv.y = m.y ? gv.y * inv_keep : 0.f;
+            gv.z = m.z ? gv.z * inv_keep : 0.f; gv.w = m.w ? gv.w * inv_keep : 0.f;
+        }
+        s1[0] += gv.x; s1[1] += gv.y; s1[2] += gv.z; s1[3] += gv.w;
+        s2[0] = fmaf(gv.x, (yv.x - mu.x) * is.x, s2[0]);
+        s2[1] = fmaf(gv.y, (yv.y - mu.y) * is.y, s2[1]);
+        s2[2] = fmaf(gv.z, (yv.z - mu.z) * is.z, s2[2]);
+        s2[3] = fmaf(gv.w, (yv.w - mu.w) * is.w, s2[3]);
+    }
+    block_col_reduce<F>(s1, red, qx, ry);
+    block_col_reduce<F>(s2, red, qx, ry);
+    if (ry == 0) {
+        *reinterpret_cast<float4*>(p1 + (int64_t)blockIdx.x * F + qx * 4) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+        *reinterpret_cast<float4*>(p2 + (int64_t)blockIdx.x * F + qx * 4) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+    }
+}
+
+// d_gamma = sum g'*xh, d_beta = sum g';  m1 = d_beta/R, m2 = d_gamma/R
+__global__ void __launch_bounds__(1024)
+bn_bwd_finalize_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int P, int F, int64_t R,
+                       float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ d_gamma,
+                       float* __restrict__ d_beta) {
+    __shared__ double sm[32 * 33];
+    const int col = blockIdx.x * 32 + threadIdx.x % 32, lane = threadIdx.x / 32;
+    const double a = reduce_partials(p1, P, F, col, lane, sm);
+    const double b = reduce_partials(p2, P, F, col, lane, sm);
+    if (lane != 0 || col >= F) return;
+    m1[col] = (float)(a / (double)R);
+    m2[col] = (float)(b / (double)R);
+    if (d_beta) d_beta[col] = (float)a;
+    if (d_gamma) d_gamma[col] = (float)b;
+}
+
+// gz = 1[y>0] * gamma*istd * (g' - m1 - xh*m2)     (BN backward, then ReLU backward);
+// partial column sums of gz = bias gradient of the preceding Linear / Conv.
+template <int F>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t R,
+                    const uint8_t* __restrict__ keep, float inv_keep, const float* __restrict__ mean,
+                    const float* __restrict__ istd, const float* __restrict__ gamma,
+                    const float* __restrict__ m1, const float* __restrict__ m2, float* __restrict__ gz,
+                    float* __restrict__ pdb) {
+    __shared__ float red[ColMap<F>::RY * F];
+    const int qx = threadIdx.x % ColMap<F>::QX, ry = threadIdx.x / ColMap<F>::QX;
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + qx * 4));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(istd + qx * 4));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + qx * 4));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(m1 + qx * 4));
+    const float4 a2 = __ldg(reinterpret_cast<const float4*>(m2 + qx * 4));
+    const float k0 = ga.x * is.x, k1 = ga.y * is.y, k2 = ga.z * is.z, k3 = ga.w * is.w;
+    float sb[4] = {0, 0, 0, 0};
+    const int64_t r0 = (int64_t)blockIdx.x * ColMap<F>::ROWS;
+    for (int k = ry; k < ColMap<F>::ROWS; k += ColMap<F>::RY) {
+        const int64_t r = r0 + k;
+        if (r >= R) break;
+        const int64_t v = r * (F / 4) + qx;
+        float4 gv = __ldg(reinterpret_cast<const float4*>(g) + v);
+        const float4 yv = __ldg(reinterpret_cast<const float4*>(y) + v);
+        if (keep) {
+            const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(keep) + v);
+            gv.x = m.x ? gv.x * inv_keep : 0.f; gv.y = m.y ? gv.y * inv_keep : 0.f;
+            gv.z = m.z ? gv.z * inv_keep : 0.f; gv.w = m.w ? gv.w * inv_keep : 0.f;
+        }
+        float4 o;
+        o.x = yv.x > 0.f ? k0 * (gv.x - a1.x - (yv.x - mu.x) * is.x * a2.x) : 0.f;
+        o.y = yv.y > 0.f ? k1 * (gv.y - a1.y - (yv.y - mu.y) * is.y * a2.y) : 0.f;
+        o.z = yv.z > 0.f ? k2 * (gv.z - a1.z - (yv.z - mu.z) * is.z * a2.z) : 0.f;
+        o.w = yv.w > 0.f ? k3 * (gv.w - a1.w - (yv.w - mu.w) * is.w * a2.w) : 0.f;
+        reinterpret_cast<float4*>(gz)[v] = o;
+        sb[0] += o.x; sb[1] += o.y; sb[2] += o.z; sb[3] += o.w;
+    }
+    block_col_reduce<F>(sb, red, qx, ry);
+    if (ry == 0)
+        *reinterpret_cast<float4*>(pdb + (int64_t)blockIdx.x * F + qx * 4) = make_float4(sb[0], sb[1], sb[2], sb[3]);
+}
+
+// out[c] = sum_p partial[p][c]   (bias gradients, projection / conv1 weight gradients)
+// remap: 0 identity; 1 conv1 weight: partial col = tap*64 + c -> out[c*9 + 3 + tap]
+__global__ void __launch_bounds__(1024)
+colsum_finalize_kernel(const float* __restrict__ part, int P, int width, float* __restrict__ out, int remap) {
+    __shared__ double sm[32 * 33];
+    const int col = blockIdx.x * 32 + threadIdx.x % 32, lane = threadIdx.x / 32;
+    const double s = reduce_partials(part, P, width, col, lane, sm);
+    if (lane != 0 || col >= width) return;
+    if (remap == 1) out[(col % 64) * 9 + 3 + col / 64] = (float)s;
+    else out[col] = (float)s;
+}
+
+// partial[blockIdx.y][c] = sum of G[r, c] over the 128-row slab blockIdx.y (layer-level bias grad)
+__global__ void __launch_bounds__(256)
+colsum_rows_kernel(const float* __restrict__ G, int64_t M, int N, float* __restrict__ partial) {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x % 32, lane = threadIdx.x / 32;
+    const int col = blockIdx.x * 32 + cx;
+    const int64_t r0 = (int64_t)blockIdx.y * 128;
+    float s = 0.f;
+    if (col < N)
+        for (int k = lane; k < 128 && r0 + k < M; k += 8) s += __ldg(G + (r0 + k) * N + col);
+    red[lane][cx] = s;
+    __syncthreads();
+    if (lane == 0 && col < N) {
+        float t = 0.f;
+        for (int l = 0; l < 8; ++l) t += red[l][cx];
+        partial[(int64_t)blockIdx.y * N + col] = t;
+    }
+}
+
+// --------------------------------------------------------------------------------- projection
+// emb[r, o] = sum_k a[r,k] * Wp[o,k]    (models.py:314, bias-free 512 -> 16)
+__global__ void __launch_bounds__(256)
+proj_fwd_kernel(const float* __restrict__ a, const float* __restrict__ Wp, float* __restrict__ emb, int64_t R) {
+    __shared__ __align__(16) float W[CP_EMB_DIM][512];
+    for (int e = threadIdx.x; e < CP_EMB_DIM * 512 / 4; e += 256)
+        reinterpret_cast<float4*>(&W[0][0])[e] = __ldg(reinterpret_cast<const float4*>(Wp) + e);
+    __syncthreads();
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < R; r += (int64_t)gridDim.x * 8) {
+        float4 x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = __ldg(reinterpret_cast<const float4*>(a + r * 512) + lane + 32 * j);
+        float out = 0.f;
+#pragma unroll
+        for (int o = 0; o < CP_EMB_DIM; ++o) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 w = *reinterpret_cast<const float4*>(&W[o][(lane + 32 * j) * 4]);
+                s = fmaf(x[j].x, w.x, s); s = fmaf(x[j].y, w.y, s);
+                s = fmaf(x[j].z, w.z, s); s = fmaf(x[j].w, w.w, s);
+            }
+            s = warp_sum(s);
+            if (lane == o) out = s;
+        }
+        if (lane < CP_EMB_DIM) emb[r * CP_EMB_DIM + lane] = out;
+    }
+}
+
+// ga[r,k] = sum_o d[r,o] * Wp[o,k]
+__global__ void __launch_bounds__(256)
+proj_bwd_data_kernel(const float* __restrict__ d, const float* __restrict__ Wp, float* __restrict__ ga, int64_t R) {
+    const int q = threadIdx.x % 128, rl = threadIdx.x / 128;
+    float4 w[CP_EMB_DIM];
+#pragma unroll
+    for (int o = 0; o < CP_EMB_DIM; ++o) w[o] = __ldg(reinterpret_cast<const float4*>(Wp + o * 512) + q);
+    for (int64_t r = (int64_t)blockIdx.x * 2 + rl; r < R; r += (int64_t)gridDim.x * 2) {
+        float dv[CP_EMB_DIM];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(d + r * CP_EMB_DIM) + j);
+            dv[j * 4 + 0] = t.x; dv[j * 4 + 1] = t.y; dv[j * 4 + 2] = t.z; dv[j * 4 + 3] = t.w;
+        }
+        float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int o = 0; o < CP_EMB_DIM; ++o) {
+            o4.x = fmaf(dv[o], w[o].x, o4.x); o4.y = fmaf(dv[o], w[o].y, o4.y);
+            o4.z = fmaf(dv[o], w[o].z, o4.z); o4.w = fmaf(dv[o], w[o].w, o4.w);
+        }
+        reinterpret_cast<float4*>(ga + r * 512)[q] = o4;
+    }
+}
+
+// dWp[o,k] partial over a slab of rows: partial[blk][o*512 + k]
+#define PROJ_W_ROWS 256
+__global__ void __launch_bounds__(256)
+proj_bwd_weight_kernel(const float* __restrict__ d, const float* __restrict__ a, int64_t R,
+                       float* __restrict__ partial) {
+    __shared__ float4 red[128];
+    const int q = threadIdx.x % 128, rl = threadIdx.x / 128;
+    float4 acc[CP_EMB_DIM];
+#pragma unroll
+    for (int o = 0; o < CP_EMB_DIM; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t r0 = (int64_t)blockIdx.x * PROJ_W_ROWS;
+    for (int k = rl; k < PROJ_W_ROWS; k += 2) {
+        const int64_t r = r0 + k;
+        if (r >= R) break;
+        const float4 x = __ldg(reinterpret_cast<const float4*>(a + r * 512) + q);
+        float dv[CP_EMB_DIM];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(d + r * CP_EMB_DIM) + j);
+            dv[j * 4 + 0] = t.x; dv[j * 4 + 1] = t.y; dv[j * 4 + 2] = t.z; dv[j * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int o = 0; o < CP_EMB_DIM; ++o) {
+            acc[o].x = fmaf(dv[o], x.x, acc[o].x); acc[o].y = fmaf(dv[o], x.y, acc[o].y);
+            acc[o].z = fmaf(dv[o], x.z, acc[o].z); acc[o].w = fmaf(dv[o], x.w, acc[o].w);
+        }
+    }
+    float* out = partial + (int64_t)blockIdx.x * CP_EMB_DIM * 512;
+#pragma unroll
+    for (int o = 0; o < CP_EMB_DIM; ++o) {
+        __syncthreads();
+        if (rl == 1) red[q] = acc[o];
+        __syncthreads();
+        if (rl == 0) {
+            const float4 t = red[q];
+            reinterpret_cast<float4*>(out + o * 512)[q] =
+                make_float4(acc[o].x + t.x, acc[o].y + t.y, acc[o].z + t.z, acc[o].w + t.w);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ weight layouts
+// Wc2 [o][tap*64+c]  = conv2_w[o][c][1][tap]         conv2 forward  (B operand, [N=64,K=192])
+// Wc2d[c][tap*64+o]  = conv2_w[o][c][1][2-tap]       conv2 data-gradient
+// W1p [o][p*64+c]    = fc1_w[o][c*12+p]              fc1 on the position-major flatten
+__global__ void __launch_bounds__(256)
+prep_weights_kernel(const float* __restrict__ conv2_w, const float* __restrict__ fc1_w,
+                    float* __restrict__ Wc2, float* __restrict__ Wc2d, float* __restrict__ W1p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 64 * 192) {
+        const int o = i / 192, k = i % 192, tap = k / 64, c = k % 64;
+        Wc2[i] = __ldg(conv2_w + (o * 64 + c) * 9 + 3 + tap);
+        // same flat index read as [c'][tap*64 + o'] with c' = o, o' = c
+        Wc2d[i] = __ldg(conv2_w + (c * 64 + o) * 9 + 3 + (2 - tap));
+    }
+    if (i < 512 * 768) {
+        const int o = i / 768, k = i % 768, p = k / 64, c = k % 64;
+        W1p[i] = __ldg(fc1_w + o * 768 + c * 12 + p);
+    }
+}
+
+// dW = sum_z P[z]  with the inverse re-layouts.  mode 0: identity; 1: fc1 (cols p*64+c -> c*12+p);
+// 2: conv2 (cols tap*64+c -> [o][c][1][tap] of a zero-initialised (64,64,3,3) tensor)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ P, int S, int Mo, int No, float* __restrict__ out, int mode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Mo * No) return;
+    double s = 0.0;
+    for (int z = 0; z < S; ++z) s += (double)__ldg(P + (int64_t)z * Mo * No + i);
+    const int o = i / No, k = i % No;
+    if (mode == 0) out[i] = (float)s;
+    else if (mode == 1) out[o * 768 + (k % 64) * 12 + k / 64] = (float)s;
+    else out[(o * 64 + k % 64) * 9 + 3 + k / 64] = (float)s;
+}

@@ -1,0 +1,13 @@
+#include "common.cuh"
+
+extern "C" int cp_version(void) { return 100; }   // 0.1.0
+
+extern "C" const char* cp_status_string(int status) {
+    switch (status) {
+        case CP_OK: return "ok";
+        case CP_ERR_ARG: return "invalid argument (null pointer, bad size or misaligned workspace)";
+        case CP_ERR_WORKSPACE: return "workspace too small";
+        case CP_ERR_UNSUPPORTED: return "unsupported mode for this entry point";
+        default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown libcpros status";
+    }
+}

@@ -1,0 +1,163 @@
+// K4 / K4': windowed majority vote and class-subset evaluator.  Integer / indexing kernels.
+//
+// K4  replaces the per-group Python loop of 249 `pred[:win].mode(0)` launches + host syncs
+//     (models.py:151-163) by one launch: one CTA per item, one thread per class row, an
+//     incremental prefix-mode with torch's CPU tie rule (smallest label among the most frequent).
+// K4' implements the README-only subset evaluator (README.md:11,15).  Instead of re-running a
+//     masked argmax over |S|^2 logits per (trial, window), every logit row is ranked ONCE
+//     (cp_rank_rows, uint8 order); the restricted argmax of any subset is then "first label of
+//     the ranked row that is in the subset" -- ~41/|S| byte probes.  Logits are read from HBM
+//     once for all trials (164 B/window).
+#include "common.cuh"
+
+#define T CP_TASKS
+#define MAXW 32
+
+// ------------------------------------------------------------------------------------- K4 vote
+__global__ void __launch_bounds__(64)
+vote_kernel(const int32_t* __restrict__ pred, int W, int n_votes, int32_t* __restrict__ votes,
+            int64_t* __restrict__ y_pred) {
+    __shared__ uint8_t cnt[T][T + 3];
+    __shared__ int correct_at[MAXW * 8];
+    const int64_t b = blockIdx.x;
+    const int i = threadIdx.x;
+    for (int k = threadIdx.x; k < W; k += blockDim.x) correct_at[k] = 0;
+    if (i < T)
+        for (int j = 0; j < T; ++j) cnt[i][j] = 0;
+    __syncthreads();
+    int best = 0, best_c = 0;
+    if (i < T) {
+        for (int w = 0; w < W; ++w) {
+            const int l = pred[(b * W + w) * T + i];
+            const int c = ++cnt[i][l];
+            // prefix mode, ties -> smallest label: the incremented label wins iff it now has
+            // strictly more votes, or as many votes and a smaller label
+            if (c > best_c || (c == best_c && l < best)) { best = l; best_c = c; }
+            if (best == i) atomicAdd(&correct_at[w], 1);
+        }
+        y_pred[b * T + i] = best;
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < n_votes; v += blockDim.x) {
+        const int w = (v + 1 < W ? v + 1 : W) - 1;           // pred[:win] clamps at W rows
+        votes[b * n_votes + v] = correct_at[w];
+    }
+}
+
+extern "C" int cp_vote_eval(const int32_t* pred, int64_t B, int W, int n_votes, int32_t* votes,
+                            int64_t* y_pred, void* stream) {
+    if (B == 0) return CP_OK;
+    if (!pred || !votes || !y_pred || B < 0 || W <= 0 || W > MAXW * 8 || n_votes <= 0) return CP_ERR_ARG;
+    vote_kernel<<<(unsigned)B, 64, 0, (cudaStream_t)stream>>>(pred, W, n_votes, votes, y_pred);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+// ------------------------------------------------------------------------------- K4' rank rows
+// 64 rows per CTA staged in shared memory; thread (row, j) counts the entries that beat entry j:
+// rank_j = #{k : v_k > v_j or (v_k == v_j and k < j)}  ->  order[rank_j] = j.
+#define RR_ROWS 64
+__global__ void __launch_bounds__(256)
+rank_rows_kernel(const float* __restrict__ logits, int64_t n_rows, uint8_t* __restrict__ order) {
+    __shared__ float v[RR_ROWS][T + 1];
+    __shared__ uint8_t ord[RR_ROWS][T + 3];
+    const int64_t r0 = (int64_t)blockIdx.x * RR_ROWS;
+    const int nr = (int)min((int64_t)RR_ROWS, n_rows - r0);
+    for (int e = threadIdx.x; e < nr * T; e += blockDim.x) v[e / T][e % T] = __ldg(logits + r0 * T + e);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nr * T; e += blockDim.x) {
+        const int r = e / T, j = e % T;
+        const float x = v[r][j];
+        int rank = 0;
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            const float y = v[r][k];
+            rank += (y > x) || (y == x && k < j);
+        }
+        ord[r][rank] = (uint8_t)j;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nr * T; e += blockDim.x) order[r0 * T + e] = ord[e / T][e % T];
+}
+
+extern "C" int cp_rank_rows(const float* logits, int64_t n_rows, uint8_t* order, void* stream) {
+    if (n_rows == 0) return CP_OK;
+    if (!logits || !order || n_rows < 0) return CP_ERR_ARG;
+    rank_rows_kernel<<<(unsigned)cp_cdiv(n_rows, RR_ROWS), 256, 0, (cudaStream_t)stream>>>(logits, n_rows, order);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+// ----------------------------------------------------------------------------- K4' subset eval
+// grid = (item b, trial chunk).  The CTA stages the ranked rows of its item (W*41*41 bytes = 42 KB
+// at W=25) in shared memory once; each thread owns one trial of the chunk and walks the rows of
+// its subset.  Per-thread label counters live in shared memory (byte lanes, column = thread).
+#define SE_THREADS 128
+__global__ void __launch_bounds__(SE_THREADS)
+subset_eval_kernel(const uint8_t* __restrict__ order, int W, const uint8_t* __restrict__ masks,
+                   int64_t n_trials, unsigned long long* __restrict__ correct) {
+    extern __shared__ uint8_t smem[];
+    uint8_t* ord = smem;                                   // [W][T][T]
+    uint8_t* cnt = smem + ((W * T * T + 15) / 16) * 16;    // [T][SE_THREADS]
+    const int64_t b = blockIdx.x;
+    const uint8_t* src = order + b * (int64_t)W * T * T;
+    for (int e = threadIdx.x; e < W * T * T; e += SE_THREADS) ord[e] = __ldg(src + e);
+    for (int e = threadIdx.x; e < T * SE_THREADS; e += SE_THREADS) cnt[e] = 0;
+    __syncthreads();
+    const int tid = threadIdx.x;
+    for (int64_t t = (int64_t)blockIdx.y * SE_THREADS + tid; t < n_trials;
+         t += (int64_t)gridDim.y * SE_THREADS) {
+        unsigned long long m = 0;
+        for (int j = 0; j < T; ++j) m |= (unsigned long long)(__ldg(masks + t * T + j) != 0) << j;
+        int n_ok = 0;
+        for (int i = 0; i < T; ++i) {
+            if (!((m >> i) & 1ull)) continue;
+            int best = 0, best_c = 0;
+            uint8_t seen[MAXW];
+            for (int w = 0; w < W; ++w) {
+                const uint8_t* row = ord + (w * T + i) * T;
+                int k = 0;
+                int l = row[0];
+                while (!((m >> l) & 1ull)) l = row[++k];     // subset contains i, so this terminates
+                seen[w] = (uint8_t)l;
+                const int c = ++cnt[l * SE_THREADS + tid];
+                if (c > best_c || (c == best_c && l < best)) { best = l; best_c = c; }
+            }
+            for (int w = 0; w < W; ++w) cnt[seen[w] * SE_THREADS + tid] = 0;
+            n_ok += (best == i);
+        }
+        if (n_ok) atomicAdd(correct + t, (unsigned long long)n_ok);
+    }
+}
+
+__global__ void subset_total_kernel(const uint8_t* __restrict__ masks, int64_t n_trials, int64_t B,
+                                    int64_t* __restrict__ total) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_trials) return;
+    int s = 0;
+    for (int j = 0; j < T; ++j) s += masks[t * T + j] != 0;
+    total[t] = B * s;
+}
+
+extern "C" int cp_subset_eval(const uint8_t* order, int64_t B, int W, const uint8_t* masks,
+                              int64_t n_trials, int64_t* correct, int64_t* total, void* stream) {
+    if (n_trials == 0) return CP_OK;
+    if (!order || !masks || !correct || !total || B < 0 || W <= 0 || W > MAXW || n_trials < 0)
+        return CP_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    CP_CUDA(cudaMemsetAsync(correct, 0, sizeof(int64_t) * n_trials, st));
+    subset_total_kernel<<<(unsigned)cp_cdiv(n_trials, 256), 256, 0, st>>>(masks, n_trials, B, total);
+    CP_CHECK_LAUNCH();
+    if (B == 0) return CP_OK;
+    const size_t smem = ((size_t)(W * T * T + 15) / 16) * 16 + (size_t)T * SE_THREADS;
+    CP_CUDA(cudaFuncSetAttribute(subset_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // trial chunks: enough CTAs for >= 2 waves of 148 SMs x 4 resident CTAs when B is small
+    int64_t chunks = cp_cdiv(n_trials, SE_THREADS);
+    int64_t want = cp_cdiv((int64_t)CP_NUM_SMS * 8, B);
+    if (chunks > want) chunks = want < 1 ? 1 : want;
+    dim3 grid((unsigned)B, (unsigned)chunks);
+    subset_eval_kernel<<<grid, SE_THREADS, smem, st>>>(order, W, masks, n_trials,
+                                                       reinterpret_cast<unsigned long long*>(correct));
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}

@@ -1,0 +1,488 @@
+"""Drop-in `Model` / `EMGNet` / `GLOVENet` / `AdaBatchNorm{1,2}d` (reference: code/models.py).
+
+Same constructor signatures, attributes, method names, argument meaning and state-dict keys as
+the reference, so train.py-style callers and checkpoints keep working -- but no
+layer is ever *called*: the nn.Modules below are parameter containers, and every forward /
+backward goes through libcpros.so (hand-written sm_100a CUDA, see include/cpros.h):
+
+    EMGNet.forward            -> cp_encoder_forward / cp_encoder_backward      (models.py:319-342)
+    Model.forward + .loss     -> cp_head_forward_backward (one fused launch)    (models.py:112-208)
+    vote loop in .loss (eval) -> cp_vote_eval                                   (models.py:149-163)
+
+There is no PyTorch/CPU fallback: CPU tensors raise.  `--prediction` and `--glove` modes are out
+of scope (broken in the reference) and raise NotImplementedError.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .constants import (EMG_DIM, GLOVE_DIM, MAX_TASKS_TRAIN, PREDICTION_WINDOW,
+                        PREDICTION_WINDOW_SIZE, VOTE)
+
+N_VOTES = PREDICTION_WINDOW - 1      # `for win in range(1, PREDICTION_WINDOW)`  (models.py:153)
+
+
+class AdaBatchNorm1d(nn.Module):
+    """models.py:17-25 -- BatchNorm with batch statistics in train AND eval (momentum 0, no running
+    stats).  Parameter container only; statistics are computed by the encoder kernels."""
+
+    def __init__(self, num_features, device="cuda"):
+        super().__init__()
+        self.device = torch.device(device)
+        self.bn = nn.BatchNorm1d(num_features=num_features, momentum=0, track_running_stats=False)
+        self.to(self.device)
+
+    def forward(self, X):
+        raise RuntimeError("AdaBatchNorm1d is fused into cp_encoder_forward; call EMGNet.forward")
+
+
+class AdaBatchNorm2d(nn.Module):
+    """models.py:27-35."""
+
+    def __init__(self, num_features, device="cuda"):
+        super().__init__()
+        self.device = torch.device(device)
+        self.bn = nn.BatchNorm2d(num_features=num_features, momentum=0, track_running_stats=False)
+        self.to(self.device)
+
+    def forward(self, X):
+        raise RuntimeError("AdaBatchNorm2d is fused into cp_encoder_forward; call EMGNet.forward")
+
+
+def _bn_leaf(m):
+    return m.bn if isinstance(m, (AdaBatchNorm1d, AdaBatchNorm2d)) else m
+
+
+# ------------------------------------------------------------------------------ autograd glue
+def _fill_tensors(struct, conv1_w, conv1_b, conv2_w, conv2_b, fc_w, fc_b, proj_w, bn_w, bn_b,
+                  bn_rm=None, bn_rv=None):
+    P = _lib.ptr
+    struct.conv1_w, struct.conv1_b = P(conv1_w), P(conv1_b)
+    struct.conv2_w, struct.conv2_b = P(conv2_w), P(conv2_b)
+    for i in range(_lib.N_FC):
+        struct.fc_w[i], struct.fc_b[i] = P(fc_w[i]), P(fc_b[i])
+    struct.proj_w = P(proj_w)
+    for i in range(_lib.N_BN):
+        struct.bn_w[i], struct.bn_b[i] = P(bn_w[i]), P(bn_b[i])
+        struct.bn_rm[i] = P(bn_rm[i]) if bn_rm is not None else None
+        struct.bn_rv[i] = P(bn_rv[i]) if bn_rv is not None else None
+    return struct
+
+
+def _split(params):
+    """flat list of 37 tensors -> named groups (order = EMGNet.kernel_params())."""
+    conv1_w, conv1_b, conv2_w, conv2_b = params[0:4]
+    fc_w, fc_b = params[4:11], params[11:18]
+    proj_w = params[18]
+    bn_w, bn_b = params[19:28], params[28:37]
+    return conv1_w, conv1_b, conv2_w, conv2_b, fc_w, fc_b, proj_w, bn_w, bn_b
+
+
+class _EncoderFn(torch.autograd.Function):
+    """x (N,12) -> emb (N,16) through cp_encoder_forward; backward through cp_encoder_backward."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, *params):
+        L = _lib.lib()
+        if x.dtype != torch.float32:
+            raise RuntimeError("encoder input must be float32")
+        x = x.contiguous()
+        n = x.shape[0]
+        need_bwd = cfg["need_bwd"]
+        opts = _lib.EncoderOpts(bn_mode=cfg["bn_mode"], engine=cfg["engine"], bn_momentum=0.1, bn_eps=1e-5,
+                                dropout_p=float(cfg["dropout_p"]), save_for_backward=int(need_bwd),
+                                dropout_seed=int(cfg["seed"]),
+                                ext_masks=_lib.ptr(cfg["ext_masks"], torch.uint8))
+        nbytes = L.cp_encoder_workspace_bytes(n, ctypes.byref(opts))
+        if nbytes == 0:
+            raise RuntimeError("cp_encoder_workspace_bytes rejected the configuration")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        emb = torch.empty((n, 16), dtype=torch.float32, device=x.device)
+        tens = _fill_tensors(_lib.EncoderTensors(), *_split(params), bn_rm=cfg["bn_rm"], bn_rv=cfg["bn_rv"])
+        _lib.check(L.cp_encoder_forward(ctypes.byref(tens), _lib.ptr(x), n, _lib.ptr(emb), _lib.ptr(ws),
+                                        nbytes, ctypes.byref(opts), _lib.stream()), "cp_encoder_forward")
+        if need_bwd:
+            ctx.ws, ctx.opts, ctx.tens, ctx.n = ws, opts, tens, n
+            ctx.params = params            # keeps the storages (and pointers in `tens`) alive
+            ctx.cfg = cfg
+        return emb
+
+    @staticmethod
+    def backward(ctx, d_emb):
+        L = _lib.lib()
+        d_emb = d_emb.contiguous()
+        grads = [torch.empty_like(p) for p in ctx.params]
+        gt = _fill_tensors(_lib.EncoderTensors(), *_split(grads))
+        _lib.check(L.cp_encoder_backward(ctypes.byref(ctx.tens), _lib.ptr(d_emb), ctx.n, ctypes.byref(gt),
+                                         _lib.ptr(ctx.ws), ctx.ws.numel(), ctypes.byref(ctx.opts),
+                                         _lib.stream()), "cp_encoder_backward")
+        ctx.ws = None
+        return (None, None) + tuple(grads)
+
+
+class _HeadFn(torch.autograd.Function):
+    """Fused head: emb (N,16) [+ class table] -> loss; gradients are produced by the SAME launch
+    and only scaled by grad_output in backward."""
+
+    @staticmethod
+    def forward(ctx, emb, table_w, table_b, B, W, want_grad, want_logits):
+        L = _lib.lib()
+        dev = emb.device
+        G = B * W
+        emb = emb.contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        pred = torch.empty((G, MAX_TASKS_TRAIN), dtype=torch.int32, device=dev)
+        ncor = torch.empty((G,), dtype=torch.int32, device=dev)
+        logits = torch.empty((G, MAX_TASKS_TRAIN, MAX_TASKS_TRAIN), dtype=torch.float32, device=dev) \
+            if want_logits else None
+        d_emb = torch.empty_like(emb) if want_grad else None
+        d_w = torch.empty_like(table_w) if want_grad else None
+        d_b = torch.empty_like(table_b) if want_grad else None
+        nbytes = L.cp_head_workspace_bytes(G)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        P = _lib.ptr
+        _lib.check(L.cp_head_forward_backward(P(emb), B, W, P(table_w.contiguous()), P(table_b.contiguous()),
+                                              P(loss), P(d_emb), P(d_w), P(d_b), P(pred), P(ncor), P(logits),
+                                              P(ws), nbytes, _lib.stream()), "cp_head_forward_backward")
+        ctx.saved = (d_emb, d_w, d_b)
+        ctx.mark_non_differentiable(pred, ncor)
+        if logits is None:
+            logits = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(logits)
+        return loss, pred, ncor, logits
+
+    @staticmethod
+    def backward(ctx, g_loss, _gp, _gn, _gl):
+        d_emb, d_w, d_b = ctx.saved
+        if d_emb is None:
+            raise RuntimeError("head was run without gradients")
+        return d_emb * g_loss, d_w * g_loss, d_b * g_loss, None, None, None, None
+
+
+class _LogitsLossFn(torch.autograd.Function):
+    """Loss / argmax from materialised logits (callers that kept only the logits tensor)."""
+
+    @staticmethod
+    def forward(ctx, logits, want_grad):
+        L = _lib.lib()
+        logits = logits.contiguous()
+        G = logits.shape[0]
+        dev = logits.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        pred = torch.empty((G, MAX_TASKS_TRAIN), dtype=torch.int32, device=dev)
+        ncor = torch.empty((G,), dtype=torch.int32, device=dev)
+        d_logits = torch.empty_like(logits) if want_grad else None
+        nbytes = L.cp_head_workspace_bytes(G)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        P = _lib.ptr
+        _lib.check(L.cp_logits_loss(P(logits), G, P(loss), P(d_logits), P(pred), P(ncor), P(ws), nbytes,
+                                    _lib.stream()), "cp_logits_loss")
+        ctx.saved = d_logits
+        ctx.mark_non_differentiable(pred, ncor)
+        return loss, pred, ncor
+
+    @staticmethod
+    def backward(ctx, g_loss, _gp, _gn):
+        return ctx.saved * g_loss, None
+
+
+class FusedLogits:
+    """What `Model.forward` returns in training: a handle to the fused head's results.  The 41x41
+    similarity tiles never leave shared memory; `.materialize()` re-runs the head with a logits
+    output for callers that really want the tensor."""
+
+    def __init__(self, model, emb, B, W, loss, pred, ncor):
+        self._model, self._emb, self.B, self.W = model, emb, B, W
+        self.loss, self.pred, self.ncor = loss, pred, ncor
+        self.shape = (B * W, MAX_TASKS_TRAIN, MAX_TASKS_TRAIN)
+
+    def materialize(self):
+        w, b = self._model.glove_net.table_params()
+        with torch.no_grad():
+            return _HeadFn.apply(self._emb.detach(), w, b, self.B, self.W, False, True)[3]
+
+
+# ------------------------------------------------------------------------------------ Model
+class Model(nn.Module):
+    """CLIP-style contrastive classifier over 41 grasp classes (models.py:66-228)."""
+
+    def __init__(self, params, adabn=True, train_model=True, prediction=False, glove=False, device="cuda"):
+        super().__init__()
+        if prediction or glove:
+            raise NotImplementedError("--prediction / --glove modes are out of scope (broken in the "
+                                      "reference: models.py:178 vs 337, 417 vs 451)")
+        self.params = params
+        self.train_model = train_model
+        self.adabn = adabn
+        self.prediction = prediction
+        self.glove = glove
+        self.device = torch.device(device)
+
+        self.emg_net = EMGNet(d_e=params['d_e'], dp=params['dp_emg'], adabn=adabn, prediction=prediction,
+                              device=device)
+        self.glove_net = GLOVENet(d_e=params['d_e'], dp=params['dp_glove'], adabn=adabn, prediction=prediction,
+                                  device=device)
+        self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1) / 0.07)   # never applied (models.py:129)
+        self.to(self.device)
+
+        self.correct_tr = []
+        self.correct_v = []
+        self.materialize_logits = False     # training: return a real logits tensor from forward()
+        self.reset()
+
+    # -- mode switches (models.py:87-104)
+    def set_train(self):
+        self.train_model = True
+        self.train()
+        self.reset()
+
+    def set_test(self):
+        self.train_model = False
+        self.eval()
+        self.reset()
+
+    def set_val(self):
+        self.set_test()
+
+    def reset(self):
+        self._pending = []          # per-loss() device results, resolved lazily (no per-step host sync)
+        self._corrects = []
+        self.voting = []
+        self.y_pred = []
+        self.y_true = []
+
+    def encode_emg(self, EMG):
+        return self.emg_net(EMG)
+
+    def encode_glove(self, GLOVE, labels):
+        return self.glove_net(GLOVE, labels)
+
+    # -- forward (models.py:112-130)
+    def forward(self, EMG, GLOVE, labels):
+        B, T = EMG.shape[0], EMG.shape[1]
+        W = EMG.shape[2]
+        if T != MAX_TASKS_TRAIN:
+            raise RuntimeError(f"expected {MAX_TASKS_TRAIN} class rows per group, got {T}")
+        emb = self.emg_net.encode_flat(EMG)                       # (B*41*W, 16), order (b, class, w)
+        w, b = self.glove_net.table_params()
+        want_grad = torch.is_grad_enabled() and self.training
+        want_logits = (not self.training) or self.materialize_logits
+        loss, pred, ncor, logits = _HeadFn.apply(emb, w, b, B, W, want_grad, want_logits)
+        handle = FusedLogits(self, emb, B, W, loss, pred, ncor)
+        if want_logits:
+            logits._cp_handle = handle
+            return logits
+        return handle
+
+    # -- loss + accuracy (+ vote) (models.py:132-208)
+    def loss(self, logits, labels):
+        handle = logits if isinstance(logits, FusedLogits) else getattr(logits, "_cp_handle", None)
+        if handle is not None:
+            loss, pred, ncor, B, W = handle.loss, handle.pred, handle.ncor, handle.B, handle.W
+        else:
+            # foreign logits tensor: same loss from the materialised values
+            W = self.emg_net.shape[2] if (not self.training and VOTE) else 1
+            B = logits.shape[0] // W
+            want_grad = torch.is_grad_enabled() and logits.requires_grad
+            loss, pred, ncor = _LogitsLossFn.apply(logits, want_grad)
+        if not self.training and VOTE:
+            L = _lib.lib()
+            votes = torch.empty((B, N_VOTES), dtype=torch.int32, device=pred.device)
+            y_pred = torch.empty((B, MAX_TASKS_TRAIN), dtype=torch.int64, device=pred.device)
+            _lib.check(L.cp_vote_eval(_lib.ptr(pred), B, W, N_VOTES, _lib.ptr(votes), _lib.ptr(y_pred),
+                                      _lib.stream()), "cp_vote_eval")
+            self._pending.append(("vote", votes, y_pred))
+        else:
+            self._pending.append(("train", ncor, None))
+        return loss
+
+    # -- accumulators.  The kernels return INTEGER counts; the float arithmetic of the reference
+    #    (float32 running sum of count/41 per batch, models.py:134,166,170-172) is reproduced here.
+    def _resolve(self):
+        T = MAX_TASKS_TRAIN
+        for kind, a, b in self._pending:
+            if kind == "train":
+                counts = a.cpu().numpy().astype(np.float64)
+            else:
+                votes = a.cpu().numpy()
+                y_pred = b.cpu().numpy()
+                for g in range(votes.shape[0]):
+                    self.voting.append(list(votes[g].astype(np.float64) / T))
+                    self.y_pred.append(y_pred[g])
+                    self.y_true.append(np.arange(T, dtype=np.int64))
+                counts = votes[:, -1].astype(np.float64)
+            per_group = (counts / T).astype(np.float32)
+            acc = np.cumsum(per_group, dtype=np.float32)[-1]         # sequential float32 adds
+            self._corrects.append(float(np.float32(acc / np.float32(len(per_group)))))
+        self._pending = []
+
+    @property
+    def corrects(self):
+        self._resolve()
+        return self._corrects
+
+    def correct(self):
+        return np.array(self.corrects).mean()
+
+    def correct_raw(self):
+        return np.array(self.corrects)
+
+    def voting_raw(self):
+        self._resolve()
+        return np.array(self.voting)
+
+    def y_pred_raw(self):
+        self._resolve()
+        return np.array(self.y_pred)
+
+    def y_true_raw(self):
+        self._resolve()
+        return np.array(self.y_true)
+
+    def l2(self):
+        """models.py:225-228: reg * sum of un-squared Frobenius norms (tiny; plain torch ops)."""
+        return self.glove_net.l2() * self.params['reg_glove'] + self.emg_net.l2() * self.params['reg_emg']
+
+
+def _l2_of(module):
+    """models.py:344-349 / 467-472: parameters whose name has neither 'bn' nor 'bias'."""
+    reg = 0
+    for name, p in module.named_parameters():
+        if 'bn' not in name and 'bias' not in name:
+            reg = reg + torch.norm(p)
+    return reg
+
+
+class EMGNet(nn.Module):
+    """12-channel instantaneous sEMG -> d_e embedding (models.py:230-349)."""
+
+    def __init__(self, d_e, dp=.5, adabn=True, train=True, prediction=False, device="cuda"):
+        super().__init__()
+        if prediction:
+            raise NotImplementedError("prediction head is out of scope")
+        if d_e != 16:
+            raise NotImplementedError("libcpros is built for d_e = 16 (train.py:182 des=[16])")
+        self.device = torch.device(device)
+        self.d_e = d_e
+        self.dp = dp
+        self.prediction = prediction
+        self.adabn = adabn
+        if adabn:
+            self.bn1d_func, self.bn2d_func = AdaBatchNorm1d, AdaBatchNorm2d
+            bn1 = lambda f: AdaBatchNorm1d(f, device=device)     # noqa: E731
+            bn2 = lambda f: AdaBatchNorm2d(f, device=device)     # noqa: E731
+        else:
+            self.bn1d_func, self.bn2d_func = nn.BatchNorm1d, nn.BatchNorm2d
+            bn1, bn2 = nn.BatchNorm1d, nn.BatchNorm2d
+
+        # Same module tree (and therefore the same state-dict keys and RNG consumption at init)
+        # as models.py:248-315.
+        self.conv_emg = nn.Sequential(
+            nn.Conv2d(1, 64, (3, 3), padding=(1, 1)), nn.ReLU(), bn2(64),
+            nn.Conv2d(64, 64, (3, 3), padding=(1, 1)), nn.ReLU(), bn2(64),
+            nn.Flatten())
+        blocks = [nn.Linear(EMG_DIM * 64, 512), nn.ReLU(), bn1(512)]
+        for i in range(6):
+            blocks += [nn.Linear(512, 512), nn.ReLU(), bn1(512)]
+            if i >= 2:
+                blocks.append(nn.Dropout(self.dp))
+        self.linear = nn.Sequential(*blocks)
+        self.bits = self.d_e
+        self.last = nn.Sequential(nn.Linear(512, self.d_e, bias=False))
+        self.to(self.device)
+
+        self.engine = _lib.ENGINE_SIMT
+        self.dropout_seed = 0x5EED
+        self._step = 0
+        self.ext_dropout_masks = None        # (4, N, 512) uint8 keep masks injected by parity tests
+        self.shape = None
+
+    # ordered views of the module tree for the kernels
+    def _convs(self):
+        return [self.conv_emg[0], self.conv_emg[3]]
+
+    def _linears(self):
+        return [m for m in self.linear if isinstance(m, nn.Linear)]
+
+    def _bns(self):
+        out = [_bn_leaf(self.conv_emg[2]), _bn_leaf(self.conv_emg[5])]
+        out += [_bn_leaf(m) for m in self.linear
+                if isinstance(m, (AdaBatchNorm1d, nn.BatchNorm1d))]
+        return out
+
+    def kernel_params(self):
+        c, l, b = self._convs(), self._linears(), self._bns()
+        return ([c[0].weight, c[0].bias, c[1].weight, c[1].bias] + [m.weight for m in l] +
+                [m.bias for m in l] + [self.last[0].weight] + [m.weight for m in b] + [m.bias for m in b])
+
+    def encode_flat(self, EMG):
+        """(B,41,W,1,12) or anything reshapeable to (-1,12) -> (N,16) embeddings, row order unchanged."""
+        self.shape = EMG.shape
+        x = EMG.reshape(-1, EMG_DIM)
+        bns = self._bns()
+        if self.adabn:
+            bn_mode, rm, rv = _lib.BN_BATCH, None, None
+        else:
+            bn_mode = _lib.BN_BATCH_UPDATE if self.training else _lib.BN_RUNNING
+            rm, rv = [m.running_mean for m in bns], [m.running_var for m in bns]
+            if self.training:
+                for m in bns:
+                    m.num_batches_tracked += 1
+        dp = float(self.dp) if self.training else 0.0
+        self._step += 1
+        cfg = {"bn_mode": bn_mode, "engine": self.engine, "dropout_p": dp,
+               "seed": (self.dropout_seed * 1000003 + self._step) & 0xFFFFFFFFFFFFFFFF,
+               "ext_masks": self.ext_dropout_masks if dp > 0 else None,
+               "bn_rm": rm, "bn_rv": rv,
+               "need_bwd": torch.is_grad_enabled() and self.training}
+        return _EncoderFn.apply(x, cfg, *self.kernel_params())
+
+    def forward(self, EMG):
+        """models.py:319-342 incl. the (B,41,W) -> (B*W,41) regrouping."""
+        out = self.encode_flat(EMG)
+        shape = self.shape
+        out = out.reshape((shape[0], shape[1], shape[2], self.bits)).transpose(1, 2)
+        return out.reshape((-1, shape[1], self.bits))
+
+    def l2(self):
+        return _l2_of(self)
+
+
+class GLOVENet(nn.Module):
+    """Class tower.  Default branch of the reference (models.py:457-458): a learnable 41 x d_e table,
+    `Linear(41->d_e)(one_hot(label))`; the glove angles themselves are unused."""
+
+    def __init__(self, d_e, dp=.5, adabn=True, train=True, prediction=False, device="cuda"):
+        super().__init__()
+        if prediction:
+            raise NotImplementedError("prediction head is out of scope")
+        self.device = torch.device(device)
+        self.d_e = d_e
+        self.dp = dp
+        self.prediction = prediction
+        self.conv_glove = nn.Sequential(nn.Flatten())
+        self.linear = nn.Sequential(nn.Flatten())
+        self.bits = self.d_e
+        self.easy = nn.Sequential(nn.Linear(MAX_TASKS_TRAIN, self.d_e))
+        self.last = nn.Sequential(nn.Linear(512 // 2, self.bits, bias=False))   # unused in forward, still regularised
+        self.to(self.device)
+
+    def table_params(self):
+        return self.easy[0].weight, self.easy[0].bias
+
+    def forward(self, GLOVE, labels):
+        """models.py:432-465.  Returns the class embeddings (B or B*25, 41, d_e); Model.forward does
+        not call this (the table is read directly by the fused head)."""
+        w, b = self.table_params()
+        shape = GLOVE.shape
+        out = (w.t() + b)[labels.reshape(-1)].reshape((shape[0], -1, self.bits))
+        if not self.training and VOTE:
+            out = out.reshape((shape[0], 1, shape[1], self.bits)).expand(-1, PREDICTION_WINDOW_SIZE, -1, -1)
+            out = out.reshape(-1, shape[1], self.bits)
+        return out
+
+    def l2(self):
+        return _l2_of(self)

@@ -1,0 +1,153 @@
+/* libcpros -- B200 (sm_100a) kernels for the ContrastiveProsthetics hot path.  C ABI.
+ *
+ * Every entry point takes raw DEVICE pointers, explicit sizes and a CUDA stream (void* =
+ * cudaStream_t), returns an int status (0 ok, <0 argument error, >0 cudaError_t), never
+ * allocates or frees caller memory, never throws, never synchronises the device, and is
+ * re-entrant per stream.  There is no CPU implementation behind any symbol.
+ *
+ * The reference (FibonacciDude/ContrastiveProsthetics) is pure Python and has no FFI; each
+ * symbol below cites the reference Python code it replaces (paths under /root/reference/code).
+ * The reference-side binding (a ctypes stub + torch.autograd.Function) is in INTEGRATION.md and
+ * shipped in contrastiveprosthetics_b200/_lib.py.
+ */
+#ifndef CPROS_H
+#define CPROS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CP_OK 0
+#define CP_ERR_ARG (-1)        /* null pointer / bad size */
+#define CP_ERR_WORKSPACE (-2)  /* workspace too small */
+#define CP_ERR_UNSUPPORTED (-3)
+
+#define CP_TASKS 41            /* constants.py:46  MAX_TASKS  */
+#define CP_EMG_DIM 12          /* constants.py:97  EMG_DIM    */
+#define CP_EMB_DIM 16          /* d_e (train.py:182 des=[16]) */
+#define CP_N_BN 9              /* 2 BatchNorm2d + 7 BatchNorm1d (models.py:248-298) */
+#define CP_N_FC 7
+
+int cp_version(void);
+/* static string for a status returned by any entry point */
+const char *cp_status_string(int status);
+
+/* ---------------------------------------------------------------- K1: gather (+ normalise)
+ * Replaces TaskWrapper.__getitem__ -> DB23.__getitem__/slice_batch (utils.py:51-64,
+ * load.py:256-273) + default_collate, and RunningStats.normalize (utils.py:129-130).
+ *   dst[r, :] = (src[idx[r], :] - mean[c]) / std[c]          (true divide)
+ * src: (src_rows, row_len) fp32 (EMG_use: row_len 12; tensor: row_len 25*12), idx: n_rows int64,
+ * channel c = column % n_ch; mean/std: stat_len in {0 (no normalisation), 1 (scalar), n_ch}.
+ * Out-of-range indices are reported through *err_flag (device int, may be NULL) and read row 0. */
+int cp_gather_norm(const float *src, int64_t src_rows, int row_len, const int64_t *idx,
+                   int64_t n_rows, float *dst, const float *mean, const float *std, int stat_len,
+                   int n_ch, int *err_flag, void *stream);
+
+/* ---------------------------------------------------------------- K2: EMG encoder
+ * Replaces EMGNet.forward up to the projection (models.py:319-323; layers 248-315; BN types
+ * 17-35, 238-243) and its autograd backward.  All tensors fp32, PyTorch state-dict layouts. */
+typedef struct cp_encoder_tensors {
+    float *conv1_w;            /* (64,1,3,3)  emg_net.conv_emg.0.weight */
+    float *conv1_b;            /* (64)                                   */
+    float *conv2_w;            /* (64,64,3,3) emg_net.conv_emg.3.weight */
+    float *conv2_b;            /* (64)                                   */
+    float *fc_w[CP_N_FC];      /* (512,768), 6 x (512,512)  emg_net.linear.{0,3,6,9,13,17,21} */
+    float *fc_b[CP_N_FC];      /* (512)                                  */
+    float *proj_w;             /* (16,512)    emg_net.last.0.weight      */
+    float *bn_w[CP_N_BN];      /* gamma: 64,64,512 x 7                   */
+    float *bn_b[CP_N_BN];      /* beta                                   */
+    float *bn_rm[CP_N_BN];     /* running_mean (stock BN only, else NULL) */
+    float *bn_rv[CP_N_BN];     /* running_var                             */
+} cp_encoder_tensors;
+
+#define CP_BN_BATCH 0          /* batch statistics (AdaBN always; models.py:22,32) */
+#define CP_BN_BATCH_UPDATE 1   /* batch statistics + running-stat update (nn.BatchNorm train) */
+#define CP_BN_RUNNING 2        /* running statistics (nn.BatchNorm eval) */
+
+#define CP_ENGINE_SIMT 0       /* fp32 FFMA GEMMs */
+#define CP_ENGINE_TC 1         /* tcgen05 3xTF32 GEMMs (fp32-level accuracy) */
+
+typedef struct cp_encoder_opts {
+    int32_t bn_mode;
+    int32_t engine;
+    float bn_momentum;         /* 0.1 for nn.BatchNorm */
+    float bn_eps;              /* 1e-5 */
+    float dropout_p;           /* dropout after linear blocks 4..7 (models.py:282-297); 0 = off */
+    int32_t save_for_backward; /* keep activations in the workspace for cp_encoder_backward */
+    uint64_t dropout_seed;     /* Philox key; element stream = (layer, flat index) */
+    const uint8_t *ext_masks;  /* optional 4 x (n,512) {0,1} keep masks (parity tests), else NULL */
+} cp_encoder_opts;
+
+size_t cp_encoder_workspace_bytes(int64_t n_windows, const cp_encoder_opts *opts);
+
+/* x: (n,12) windows -> emb: (n,16).  params: weights (read-only except bn_rm/bn_rv in mode 1). */
+int cp_encoder_forward(const cp_encoder_tensors *params, const float *x, int64_t n, float *emb,
+                       void *workspace, size_t workspace_bytes, const cp_encoder_opts *opts,
+                       void *stream);
+
+/* d_emb: (n,16) -> grads (same layouts as params; bn_rm/bn_rv ignored; every grad tensor is
+ * OVERWRITTEN).  Must follow a cp_encoder_forward with save_for_backward on the same workspace. */
+int cp_encoder_backward(const cp_encoder_tensors *params, const float *d_emb, int64_t n,
+                        const cp_encoder_tensors *grads, void *workspace, size_t workspace_bytes,
+                        const cp_encoder_opts *opts, void *stream);
+
+/* Layer-level entry points (unit parity tests; the encoder calls the same kernels).
+ * Y = relu?(A[M,K] @ W[N,K]^T + bias) with per-column sum / sum-of-squares (BN statistics). */
+int cp_linear_forward(const float *A, const float *W, const float *bias, float *Y, int64_t M, int N,
+                      int K, int relu, float *col_sum, float *col_sqsum, void *workspace,
+                      size_t workspace_bytes, int engine, void *stream);
+/* dA[M,K] = G[M,N] @ W[N,K];  dW[N,K] = G^T @ A;  db[N] = colsum(G) */
+int cp_linear_backward(const float *G, const float *A, const float *W, float *dA, float *dW,
+                       float *db, int64_t M, int N, int K, void *workspace, size_t workspace_bytes,
+                       int engine, void *stream);
+size_t cp_linear_workspace_bytes(int64_t M, int N, int K);
+
+/* ---------------------------------------------------------------- K3: fused contrastive head
+ * Replaces Model.forward's contrastive branch (models.py:121-130), GLOVENet.forward's default
+ * branch (models.py:457-465) and Model.loss -> contrastive_loopy_loss x2 (models.py:198-208,
+ * 132-173, float part).  Group g = (b, w): rows emb[((b*41 + i)*W + w)*16 ...], i = class.
+ *   loss = 1/2 (mean row-CE + mean column-CE) of S_g = normalise(emb_g) normalise(table)^T
+ * table[j,:] = table_w[:,j] + table_b  (glove_net.easy.0: weight (16,41), bias (16)).
+ * Outputs (each may be NULL): loss (1 float), d_emb (same layout as emb), d_table_w (16,41),
+ * d_table_b (16) -- gradients of `loss` w.r.t. the un-normalised inputs; pred (B*W,41) int32 =
+ * first-max argmax per row; n_correct (B*W) int32 = #(pred == row); logits (B*W,41,41). */
+size_t cp_head_workspace_bytes(int64_t n_groups);
+int cp_head_forward_backward(const float *emb, int64_t B, int W, const float *table_w,
+                             const float *table_b, float *loss, float *d_emb, float *d_table_w,
+                             float *d_table_b, int32_t *pred, int32_t *n_correct, float *logits,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
+/* Same loss / gradient / argmax from MATERIALISED logits (G,41,41) (a caller that kept only the
+ * logits, e.g. results.py:40): d_logits (G,41,41) may be NULL. */
+int cp_logits_loss(const float *logits, int64_t G, float *loss, float *d_logits, int32_t *pred,
+                   int32_t *n_correct, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------- K4: windowed majority vote
+ * Replaces the vote loop of contrastive_loopy_loss (models.py:149-163, constants.py:74-78).
+ * pred: (B,W,41) int32.  votes: (B,n_votes) int32 = #rows whose prefix-mode over the first
+ * min(v+1,W) samples equals the row label (mode ties -> smallest label).  y_pred: (B,41) int64 =
+ * full-window mode. */
+int cp_vote_eval(const int32_t *pred, int64_t B, int W, int n_votes, int32_t *votes,
+                 int64_t *y_pred, void *stream);
+
+/* ---------------------------------------------------------------- K4': class-subset evaluator
+ * Implements the README-only test-time evaluator (README.md:11,15; inputs = the logits dumped by
+ * results.py:42-61).  Two steps:
+ *  cp_rank_rows:   order[r, k] = label with the k-th largest logit of row r (ties -> smaller
+ *                  label first), uint8, for r over (B*W*41) rows of 41 logits.
+ *  cp_subset_eval: for trial t with class mask masks[t, 0..40], every group b and every row
+ *                  i in the subset: pred_w = first label in order[(b,w,i), :] that is in the
+ *                  subset; decision = mode over the W window (ties -> smallest label);
+ *                  correct[t] += decision == i; total[t] = B * |subset|.  int64 outputs are
+ *                  OVERWRITTEN. */
+int cp_rank_rows(const float *logits, int64_t n_rows, uint8_t *order, void *stream);
+int cp_subset_eval(const uint8_t *order, int64_t B, int W, const uint8_t *masks, int64_t n_trials,
+                   int64_t *correct, int64_t *total, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPROS_H */

@@ -1,0 +1,173 @@
+"""K2 parity: encoder forward / backward through the C-ABI vs the CPU oracle (torch fp32, pinned to
+the reference by tests/test_oracle_golden.py).  Tolerance: 1e-5 relative (norm-wise per tensor,
+SURVEY.md section 7) for forward values; gradients are additionally put in context with the fp64
+oracle, because fp32-vs-fp32 gradient differences through 9 BatchNorm layers are dominated by the
+oracle's own rounding."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from contrastiveprosthetics_b200 import _lib
+from contrastiveprosthetics_b200.models import Model
+from oracle import model as OM
+from gpu_util import load_sd, perturbed_state, rel_err
+
+pytestmark = pytest.mark.gpu
+PARAMS = {'d_e': 16, 'dp_emg': 0.0, 'dp_glove': 0.0, 'reg_emg': 0.0, 'reg_glove': 0.0}
+FWD_TOL = 1e-5
+GRAD_TOL = 1e-4          # vs fp32 oracle; see test_backward_error_in_fp64_context for the 1e-5 context
+
+
+@pytest.mark.parametrize("M,N,K,relu", [(300, 512, 512, 1), (128, 512, 768, 1), (1000, 64, 192, 0), (1, 512, 512, 1)])
+def test_linear_layer_forward(M, N, K, relu):
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    ref = F.linear(A, W, b)
+    if relu:
+        ref = F.relu(ref)
+    L = _lib.lib()
+    Ad, Wd, bd = A.cuda(), W.cuda(), b.cuda()
+    Y = torch.empty(M, N, device="cuda")
+    cs, cq = torch.empty(N, device="cuda"), torch.empty(N, device="cuda")
+    nb = L.cp_linear_workspace_bytes(M, N, K)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    P = _lib.ptr
+    _lib.check(L.cp_linear_forward(P(Ad), P(Wd), P(bd), P(Y), M, N, K, relu, P(cs), P(cq), P(ws), nb, 0, _lib.stream()))
+    assert rel_err(Y, ref) < 2e-6
+    assert rel_err(cs, ref.double().sum(0)) < 1e-5
+    assert rel_err(cq, (ref.double() ** 2).sum(0)) < 1e-5
+
+
+def test_linear_layer_backward():
+    M, N, K = 700, 512, 768
+    g = torch.Generator().manual_seed(1)
+    A, W, G = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(M, N, generator=g)
+    L = _lib.lib()
+    P = _lib.ptr
+    Ad, Wd, Gd = A.cuda(), W.cuda(), G.cuda()
+    dA, dW, db = torch.empty(M, K, device="cuda"), torch.empty(N, K, device="cuda"), torch.empty(N, device="cuda")
+    nb = L.cp_linear_workspace_bytes(M, N, K)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    _lib.check(L.cp_linear_backward(P(Gd), P(Ad), P(Wd), P(dA), P(dW), P(db), M, N, K, P(ws), nb, 0, _lib.stream()))
+    assert rel_err(dA, G.double() @ W.double()) < 2e-6
+    assert rel_err(dW, G.double().t() @ A.double()) < 2e-6
+    assert rel_err(db, G.double().sum(0)) < 2e-6
+
+
+def _model(sd, adabn, dp=0.0):
+    params = dict(PARAMS)
+    params['dp_emg'] = dp
+    m = Model(params, adabn=adabn, device="cuda")
+    load_sd(m, sd)
+    return m
+
+
+@pytest.mark.parametrize("adabn,training", [(True, True), (True, False), (False, True), (False, False)])
+@pytest.mark.parametrize("n", [41 * 3, 1000])
+def test_encoder_forward(adabn, training, n):
+    sd = perturbed_state(7, adabn)
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, 12, generator=g)
+    new_stats = {}
+    with torch.no_grad():
+        ref = OM.encoder_forward(sd, x, adabn, training, new_stats=new_stats)
+    m = _model(sd, adabn)
+    m.train(training)
+    with torch.no_grad():
+        emb = m.emg_net.encode_flat(x.cuda())
+    assert rel_err(emb, ref) < FWD_TOL
+    if not adabn and training:       # running statistics updated like nn.BatchNorm (momentum 0.1, unbiased var)
+        got = m.state_dict()
+        for k, v in new_stats.items():
+            if v.is_floating_point():
+                assert rel_err(got[k], v) < 1e-5, k
+            else:
+                assert int(got[k]) == int(v), k
+
+
+def _grads_cuda(sd, adabn, x, d_emb, dp=0.0, masks=None):
+    m = _model(sd, adabn, dp)
+    m.train(True)
+    if masks is not None:
+        m.emg_net.ext_dropout_masks = torch.stack(masks).to(torch.uint8).cuda().contiguous()
+    emb = m.emg_net.encode_flat(x.cuda())
+    emb.backward(d_emb.cuda())
+    return emb.detach().cpu(), {"emg_net." + k: p.grad.detach().cpu() for k, p in m.emg_net.named_parameters()}
+
+
+def _grads_oracle(sd, adabn, x, d_emb, dtype, dp=0.0, masks=None):
+    p = {}
+    for k, v in sd.items():
+        if v.is_floating_point():
+            p[k] = v.to(dtype).clone().requires_grad_(k in OM.trainable_keys(sd))
+        else:
+            p[k] = v.clone()
+    emb = OM.encoder_forward(p, x.to(dtype), adabn, True, masks, dp)
+    emb.backward(d_emb.to(dtype))
+    return emb.detach(), {k: p[k].grad for k in p if k.startswith("emg_net.") and getattr(p[k], "grad", None) is not None}
+
+
+@pytest.mark.parametrize("adabn", [True, False])
+@pytest.mark.parametrize("n", [41 * 8, 777])
+def test_encoder_backward(adabn, n):
+    sd = perturbed_state(11, adabn)
+    g = torch.Generator().manual_seed(n + 1)
+    x, d_emb = torch.randn(n, 12, generator=g), torch.randn(n, 16, generator=g)
+    emb, got = _grads_cuda(sd, adabn, x, d_emb)
+    ref_emb, ref = _grads_oracle(sd, adabn, x, d_emb, torch.float32)
+    assert rel_err(emb, ref_emb) < FWD_TOL
+    assert set(got) == set(ref)
+    worst = max((rel_err(got[k], ref[k]), k) for k in ref)
+    assert worst[0] < GRAD_TOL, worst
+    # the structurally-zero rows of the 3x3 kernels get exactly zero data gradient
+    for k in ("emg_net.conv_emg.0.weight", "emg_net.conv_emg.3.weight"):
+        assert torch.count_nonzero(got[k][:, :, 0, :]) == 0 and torch.count_nonzero(got[k][:, :, 2, :]) == 0
+
+
+def test_backward_error_in_fp64_context():
+    """fp32 CUDA gradients are as close to the fp64 truth as the fp32 oracle (reference arithmetic) is."""
+    adabn, n = True, 41 * 16
+    sd = perturbed_state(13, adabn)
+    g = torch.Generator().manual_seed(5)
+    x, d_emb = torch.randn(n, 12, generator=g), torch.randn(n, 16, generator=g)
+    _, got = _grads_cuda(sd, adabn, x, d_emb)
+    _, ref32 = _grads_oracle(sd, adabn, x, d_emb, torch.float32)
+    _, ref64 = _grads_oracle(sd, adabn, x, d_emb, torch.float64)
+    for k in ref64:
+        e_cuda, e_ref = rel_err(got[k], ref64[k]), rel_err(ref32[k], ref64[k])
+        assert e_cuda < max(3 * e_ref, 1e-5), (k, e_cuda, e_ref)
+
+
+def test_dropout_with_injected_masks():
+    """models.py:282-297: dropout after linear blocks 4..7, keep/(1-p) scaling, same masks both sides."""
+    adabn, n, dp = True, 41 * 6, 0.5
+    sd = perturbed_state(17, adabn)
+    g = torch.Generator().manual_seed(9)
+    x, d_emb = torch.randn(n, 12, generator=g), torch.randn(n, 16, generator=g)
+    masks = [torch.empty(n, 512).bernoulli_(0.5, generator=g) for _ in range(4)]
+    emb, got = _grads_cuda(sd, adabn, x, d_emb, dp, masks)
+    ref_emb, ref = _grads_oracle(sd, adabn, x, d_emb, torch.float32, dp, masks)
+    assert rel_err(emb, ref_emb) < FWD_TOL
+    worst = max((rel_err(got[k], ref[k]), k) for k in ref)
+    assert worst[0] < GRAD_TOL, worst
+
+
+def test_inkernel_dropout_statistics():
+    """Philox keep masks: keep rate ~ 1-p, different per layer / per step, eval is deterministic."""
+    sd = perturbed_state(19, True)
+    m = _model(sd, True, dp=0.5)
+    x = torch.randn(41 * 20, 12, generator=torch.Generator().manual_seed(2)).cuda()
+    m.train(True)
+    with torch.no_grad():
+        a = m.emg_net.encode_flat(x)
+        b = m.emg_net.encode_flat(x)
+    assert not torch.equal(a, b)
+    m.train(False)
+    with torch.no_grad():
+        assert torch.equal(m.emg_net.encode_flat(x), m.emg_net.encode_flat(x))

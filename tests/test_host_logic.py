@@ -1,0 +1,145 @@
+"""Host-side logic that runs without a GPU: split masks / D / len of DB23, trial generation and
+sharding, the C-ABI surface, loud failure without CUDA, world_size-2 gloo paths."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from contrastiveprosthetics_b200 import _lib, subset
+from contrastiveprosthetics_b200.load import DB23
+from contrastiveprosthetics_b200.synthetic import synth_emg
+from contrastiveprosthetics_b200.utils import TaskWrapper
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def gd(golden_dir):
+    return np.load(os.path.join(golden_dir, "dataset.npz"))
+
+
+@pytest.fixture(scope="module")
+def emg():
+    return synth_emg()
+
+
+@pytest.mark.parametrize("db2", [False, True])
+def test_db23_splits_match_reference(gd, emg, db2):
+    ds = DB23(db2=db2, device="cpu")
+    ds.load_tensors(emg)
+    for split in ("train", "val", "test"):
+        getattr(ds, "set_" + split)()
+        tag = f"db2{int(db2)}_{split}"
+        assert ds.D == int(gd[tag + "_D"])
+        assert len(ds) == int(gd[tag + "_len"])
+        assert len(TaskWrapper(ds)) == int(gd[tag + "_twlen"])
+        assert np.array_equal(ds.tasks_mask.numpy(), gd[tag + "_tasks"])
+        assert np.array_equal(ds.people_mask.numpy(), gd[tag + "_people"])
+        assert np.array_equal(ds.rep_mask.numpy(), gd[tag + "_reps"])
+        assert np.array_equal(ds.EMG_use[gd[tag + "_rows"]].numpy(), gd[tag + "_EMG_use"])
+        assert np.array_equal(ds.tensor[gd[tag + "_trows"]].numpy(), gd[tag + "_tensor"])
+
+
+def test_no_cpu_fallback(emg):
+    """Indexing is the CUDA gather; on CPU tensors it must raise, not silently index with torch."""
+    ds = DB23(db2=False, device="cpu")
+    ds.load_tensors(emg)
+    ds.set_train()
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ds[torch.arange(41)]
+    from contrastiveprosthetics_b200.models import Model
+    m = Model({'d_e': 16, 'dp_emg': 0., 'dp_glove': 0., 'reg_emg': 0., 'reg_glove': 0.}, device="cpu")
+    with pytest.raises(RuntimeError):
+        m.forward(torch.zeros(2, 41, 1, 1, 12), torch.zeros(2, 41, 20), torch.arange(41).repeat(2))
+
+
+def test_cabi_exports_every_declared_symbol():
+    """libcpros.so loads and exports exactly what include/cpros.h declares."""
+    _lib.build()
+    hdr = open(os.path.join(ROOT, "include", "cpros.h")).read()
+    declared = set(re.findall(r"\b(cp_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"cp_encoder_tensors", "cp_encoder_opts"}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = ctypes.CDLL(_lib.SO_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _lib.lib().cp_version() >= 100
+    # struct mirrors: 4 + 7 + 7 + 1 + 4*9 pointers; opts 40 bytes
+    assert ctypes.sizeof(_lib.EncoderTensors) == 8 * (4 + 14 + 1 + 36)
+    assert ctypes.sizeof(_lib.EncoderOpts) == 40
+
+
+def test_missing_library_raises(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "SO_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()
+
+
+def test_make_trials_and_sharding():
+    masks, sizes = subset.make_trials(sizes=range(1, 41), trials_per_size=144, seed=0)
+    assert masks.shape == (40 * 144, 41) and masks[:, 40].all()
+    assert np.array_equal(masks.sum(1), sizes + 1)
+    # size 40 == the full 41-class set (data/min_grasp.xlsx: min == max at size 40)
+    assert masks[sizes == 40].all()
+    cover = []
+    for r in range(8):
+        lo, hi = subset.shard_trials(144, r, 8)
+        assert hi - lo == 18
+        cover += list(range(lo, hi))
+    assert cover == list(range(144))
+    lo, hi = subset.shard_trials(5, 7, 8)
+    assert lo == hi
+
+
+def test_batches_cover_every_item_once_per_rank_split(emg):
+    ds = DB23(db2=False, device="cpu")
+    ds.load_tensors(emg)
+    tw = TaskWrapper(ds, with_glove=False)
+    tw.set_val()
+    seen = []
+    tw.get_batch = lambda items: seen.append(items.clone())          # host logic only
+    for w in range(2):
+        g = torch.Generator().manual_seed(3)
+        list(tw.batches(5, shuffle=True, generator=g, rank=w, world_size=2))
+    allitems = torch.cat(seen).sort().values
+    assert torch.equal(allitems, torch.arange(ds.D))
+
+
+_GLOO_WORKER = r'''
+import os, sys, torch, numpy as np
+sys.path.insert(0, os.environ["CP_ROOT"])
+from contrastiveprosthetics_b200 import dist as cpdist, subset
+rank, world, dev = cpdist.init_from_env("gloo")
+assert world == 2 and dev.type == "cpu"
+# flat-bucket gradient averaging
+torch.manual_seed(0)
+ps = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7))]
+for i, p in enumerate(ps):
+    p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+cpdist.FlatGradAllReduce(ps)()
+assert torch.allclose(ps[0].grad, torch.full((5, 3), 1.5)) and torch.allclose(ps[1].grad, torch.full((7,), 3.0))
+# trial sharding + exact integer reduction
+masks, _ = subset.make_trials(sizes=[3], trials_per_size=9, seed=1)
+lo, hi = subset.shard_trials(len(masks), rank, world)
+correct = torch.zeros(len(masks), dtype=torch.int64); correct[lo:hi] = torch.arange(lo, hi) + 1
+cpdist.sum_counts(correct)
+assert torch.equal(correct, torch.arange(len(masks)) + 1)
+print("rank", rank, "ok")
+'''
+
+
+def test_gloo_world_size_2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, CP_ROOT=ROOT, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
