@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- train sEMG windows/s (+ subset-eval preds/s) of the B200 hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU oracle port
+
+A "step" is one full train_loop iteration (train.py:95-108) on one batch of synthetic DB2-shaped
+data: gather -> encoder forward -> fused head/loss (+ l2) -> backward -> [gradient all-reduce]
+-> Adam x2.  Workload at every N: config C2 of BASELINE.json per GPU -- batch_size 4096 groups =
+167,936 windows per step per GPU, AdaBN on, fp32 (weak scaling; BatchNorm statistics stay local
+to the rank).  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T = 41
+PARAMS = {'d_e': 16, 'dp_emg': 0.5, 'dp_glove': 0.5, 'reg_emg': 1e-5, 'reg_glove': 1e-5,
+          'lr_emg': 1e-3, 'lr_glove': 1e-3, 'epochs': 1}
+FLOP_PER_WINDOW_TRAIN = 2 * 6_369_792          # fwd 2.124 M MAC, train 3x minus conv1 dX
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons during the timed region (NVML, 100 ms period)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU oracle arm
+def cpu_oracle_steps(n_steps, warmup, groups=256, seed=0):
+    """The reference's CPU path as restated by oracle/ (torch CPU, all host threads): forward, loss,
+    l2, backward, two Adams on `groups` x 41 windows per step.  Returns (windows/s, ms/step, cores)."""
+    from oracle import model as OM
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = OM.init_state(42, True)
+    g = torch.Generator().manual_seed(seed)
+    tk = OM.trainable_keys(sd)
+    m = {k: torch.zeros_like(sd[k]) for k in tk}
+    v = {k: torch.zeros_like(sd[k]) for k in tk}
+    N = groups * T
+    times = []
+    for s in range(warmup + n_steps):
+        EMG = torch.randn(groups, T, 1, 1, 12, generator=g)
+        masks = [torch.empty(N, 512).bernoulli_(0.5, generator=g) for _ in range(4)]
+        t0 = time.perf_counter()
+        res, grads, _ = OM.train_step_grads(sd, EMG, True, dp=0.5, dropout_masks=masks, reg_emg=1e-5, reg_glove=1e-5)
+        for k in tk:
+            OM.adam_update(sd[k], grads[k], m[k], v[k], s + 1, 1e-3)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    return N / (ms / 1e3), ms, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    groups = 256
+    wps, ms, cores = cpu_oracle_steps(args.steps, args.warmup, groups)
+    line = {
+        "impl": "reference", "metric": "train sEMG windows/s", "value": wps, "unit": "windows/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: train step, batch_size 4096 groups x 41 windows, AdaBN on, fp32",
+                   "note": f"CPU arm times a bounded sample of the workload: {groups} groups "
+                           f"({groups * T} windows) per step, same per-window work"},
+        "cpu_baseline": {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {groups * T} windows (oracle/ torch-CPU port of "
+                                   "train.py:95-108; the Python reference cannot travel to the GPU box)"},
+        "e2e": {"value": wps, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- CUDA arm
+def run_cuda(args):
+    import torch.distributed as dist
+    from contrastiveprosthetics_b200 import _lib, dist as cpdist, subset as cps
+    from contrastiveprosthetics_b200.load import DB23
+    from contrastiveprosthetics_b200.models import Model
+    from contrastiveprosthetics_b200.utils import TaskWrapper
+
+    rank, world, dev = cpdist.init_from_env()
+    assert dev.type == "cuda", "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
+    L = _lib.lib()
+    B = args.batch_size
+    N = B * T
+    torch.manual_seed(42)
+    model = Model(dict(PARAMS), adabn=True, device=str(dev))
+    opt_e = torch.optim.Adam(model.emg_net.parameters(), lr=PARAMS['lr_emg'], weight_decay=0)
+    opt_g = torch.optim.Adam(model.glove_net.parameters(), lr=PARAMS['lr_glove'], weight_decay=0)
+    sync_grads = cpdist.FlatGradAllReduce(list(model.emg_net.parameters()) + list(model.glove_net.parameters()))
+    ds = DB23(db2=True, device=dev)
+    ds.load_synthetic(with_glove=False)
+    tw = TaskWrapper(ds, with_glove=False)
+    tw.set_train()
+    model.set_train()
+    gen = torch.Generator().manual_seed(1234)
+
+    def step_resident(items):
+        EMG, GLOVE, label = tw.get_batch(items)
+        label = label.reshape(-1)
+        logits = model.forward(EMG, GLOVE, label)
+        loss = model.loss(logits, label) + model.l2()
+        opt_e.zero_grad(set_to_none=True)
+        opt_g.zero_grad(set_to_none=True)
+        loss.backward()
+        sync_grads()
+        opt_e.step()
+        opt_g.step()
+        return loss
+
+    def draw_items():
+        # every rank draws the same global batch and takes its slice (sample sharding)
+        order = torch.randperm(tw.D, generator=gen)[:min(B * world, tw.D)]
+        per = order.numel() // world
+        return order[rank * per:(rank + 1) * per].to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.cp_launch_count()
+        with ClockSampler(dev.index or 0) as cs:
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            barrier()
+        ms = e0.elapsed_time(e1) / steps
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), cs.summary(), L.cp_launch_count() - l0
+
+    # ---- device-resident metric
+    items_ring = [draw_items() for _ in range(8)]
+    it = {"i": 0}
+
+    def resident_step():
+        it["i"] += 1
+        step_resident(items_ring[it["i"] % len(items_ring)])
+
+    ms, clocks, launches = timed(resident_step, args.steps, args.warmup)
+    value = N * world / (ms / 1e3)
+
+    # ---- e2e: host batches (pinned) -> H2D every step, loss + correct counts -> host every step
+    host_batches = []
+    for i in range(4):
+        EMG, _, label = tw.get_batch(items_ring[i])
+        host_batches.append((EMG.cpu().pin_memory(), label.cpu().pin_memory()))
+    h2d = host_batches[0][0].numel() * 4 + host_batches[0][1].numel() * 8
+    sink = {"loss": 0.0}
+
+    def e2e_step():
+        it["i"] += 1
+        hE, hl = host_batches[it["i"] % len(host_batches)]
+        EMG = hE.to(dev, non_blocking=True)
+        label = hl.to(dev, non_blocking=True).reshape(-1)
+        logits = model.forward(EMG, None, label)
+        loss = model.loss(logits, label)
+        total = loss + model.l2()
+        opt_e.zero_grad(set_to_none=True)
+        opt_g.zero_grad(set_to_none=True)
+        total.backward()
+        sync_grads()
+        opt_e.step()
+        opt_g.step()
+        sink["loss"] = loss.item()                       # device -> host read of the step's result
+        sink["acc"] = model.corrects[-1]                 # per-group correct counts (B int32) -> host
+
+    ms_e2e, _, _ = timed(e2e_step, max(3, args.steps // 2), 2)
+    e2e_value = N * world / (ms_e2e / 1e3)
+    d2h = 4 + B * 4
+
+    # ---- dominant kernel alone: fc forward GEMM at the step's shape (CUDA events on its stream)
+    roof = None
+    sub = None
+    cpu = None
+    if rank == 0:
+        peaks = measured_peaks()
+        M, Nn, K = N, 512, 512
+        A = torch.randn(M, K, device=dev)
+        Wt = torch.randn(Nn, K, device=dev)
+        bias = torch.randn(Nn, device=dev)
+        Y = torch.empty(M, Nn, device=dev)
+        cs_, cq_ = torch.empty(Nn, device=dev), torch.empty(Nn, device=dev)
+        nb = L.cp_linear_workspace_bytes(M, Nn, K)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        P = _lib.ptr
+
+        def gemm():
+            _lib.check(L.cp_linear_forward(P(A), P(Wt), P(bias), P(Y), M, Nn, K, 1, P(cs_), P(cq_), P(ws), nb,
+                                           model.emg_net.engine, _lib.stream()))
+        for _ in range(3):
+            gemm()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            gemm()
+        e1.record()
+        torch.cuda.synchronize()
+        gms = e0.elapsed_time(e1) / reps
+        ach = 2.0 * M * Nn * K / (gms * 1e-3) / 1e12
+        roof = {"kernel": "gemm_nt_kernel<128,128> (Linear 512->512 + bias + ReLU + BN-stat partials), "
+                          "7 fwd + 7 dgrad + 7 wgrad launches of this family per step",
+                "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                "ms_per_launch": gms,
+                "note": "fp32 FFMA engine measured against the bf16 tensor peak; step-level: "
+                        f"{FLOP_PER_WINDOW_TRAIN * N / (ms * 1e-3) / 1e12:.2f} TFLOP/s algorithmic"}
+        del A, Wt, Y, ws
+
+    # ---- subset evaluator (C4): 160 test items x 25 x 41 windows, 144 trials x 40 sizes, trials sharded
+    items_eval, Wv = 160, 25
+    lg = torch.randn(items_eval * Wv, T, T, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    masks, sizes = cps.make_trials(sizes=range(1, 41), trials_per_size=144, seed=0)
+    lo, hi = cps.shard_trials(len(masks), rank, world)
+    mdev = torch.from_numpy(masks[lo:hi]).to(dev)
+
+    def subset_run():
+        ev = cps.SubsetEvaluator(lg, Wv)
+        return ev.evaluate(mdev)
+
+    for _ in range(2):
+        subset_run()
+    ms_sub, _, _ = timed(subset_run, 5, 1)
+    preds_per_s = items_eval * Wv * T * len(masks) / (ms_sub / 1e3)
+
+    if rank == 0:
+        wps, cms, cores = cpu_oracle_steps(n_steps=3, warmup=1, groups=256)
+        cpu = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
+               "sample": f"3 steps x {256 * T} windows of the same train step (oracle/ torch-CPU port), "
+                         f"{cms:.0f} ms/step"}
+        line = {
+            "metric": "train sEMG windows/s", "value": value, "unit": "windows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: train step, batch_size 4096 groups x 41 windows = 167,936 windows "
+                                   "per GPU per step, AdaBN on, dropout 0.5, fp32, DB2-shaped synthetic sEMG",
+                       "batch_size_groups_per_gpu": B, "windows_per_step": N * world,
+                       "engine": "simt-fp32" if model.emg_net.engine == 0 else "tcgen05-3xtf32",
+                       "parallelism": f"dp{world} (sample-sharded, local BatchNorm, one flat grad all-reduce)",
+                       "l2_policy": "per-step working set ~8 GB of activations >> 126 MB L2; no explicit flush"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
+            "roofline": roof, "cpu_baseline": cpu,
+            "subset_eval": {"value": preds_per_s, "unit": "preds/s", "ms": ms_sub,
+                            "workload": "C4: 160 items x 25 x 41 test windows x 5760 trials (144 x 40 sizes), "
+                                        "rank + vote + count; trials sharded over ranks"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch_size", type=int, default=4096, help="groups of 41 windows per GPU per step")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,7 @@ def lib():
             "(nvcc, sm_100a). contrastiveprosthetics_b200 has no CPU or PyTorch fallback.")
     L = ctypes.CDLL(SO_PATH)
     L.cp_version.restype = ctypes.c_int
+    L.cp_launch_count.restype = ctypes.c_ulonglong
     L.cp_status_string.restype = ctypes.c_char_p
     L.cp_status_string.argtypes = [ctypes.c_int]
     L.cp_gather_norm.argtypes = [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp]
@@ -83,6 +84,8 @@ def lib():
     L.cp_encoder_backward.argtypes = [ctypes.POINTER(EncoderTensors), _vp, _i64,
                                       ctypes.POINTER(EncoderTensors), _vp, _sz,
                                       ctypes.POINTER(EncoderOpts), _vp]
+    L.cp_encoder_read_activation.argtypes = [_vp, _sz, _i64, ctypes.POINTER(EncoderOpts), _i32, _i32, _vp, _vp]
+    L.cp_encoder_read_activation.restype = ctypes.c_int
     L.cp_linear_workspace_bytes.restype = _sz
     L.cp_linear_workspace_bytes.argtypes = [_i64, _i32, _i32]
     L.cp_linear_forward.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _i32, _vp]
@@ -103,8 +106,8 @@ def lib():
     return L
 
 
-EXPORTS = ["cp_version", "cp_status_string", "cp_gather_norm", "cp_encoder_workspace_bytes",
-           "cp_encoder_forward", "cp_encoder_backward", "cp_linear_workspace_bytes",
+EXPORTS = ["cp_version", "cp_launch_count", "cp_status_string", "cp_gather_norm", "cp_encoder_workspace_bytes",
+           "cp_encoder_forward", "cp_encoder_backward", "cp_encoder_read_activation", "cp_linear_workspace_bytes",
            "cp_linear_forward", "cp_linear_backward", "cp_head_workspace_bytes",
            "cp_head_forward_backward", "cp_logits_loss", "cp_vote_eval", "cp_rank_rows",
            "cp_subset_eval"]

@@ -6,10 +6,13 @@
 
 #define CP_NUM_SMS 148   // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
+// every kernel launch of the library goes through this macro: it also feeds cp_launch_count()
+extern unsigned long long g_cp_launches;
 #define CP_CHECK_LAUNCH()                                  \
     do {                                                   \
         cudaError_t e__ = cudaGetLastError();              \
         if (e__ != cudaSuccess) return (int)e__;           \
+        ++g_cp_launches;                                   \
     } while (0)
 
 #define CP_CUDA(call)                                      \

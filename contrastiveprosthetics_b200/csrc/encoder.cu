@@ -304,6 +304,28 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     return CP_OK;
 }
 
+// Debug / parity tap: copy a saved activation out of the workspace.
+extern "C" int cp_encoder_read_activation(const void* workspace, size_t workspace_bytes, int64_t n,
+                                          const cp_encoder_opts* o, int stage, int which, float* dst,
+                                          void* stream) {
+    if (!workspace || !dst || n <= 0 || !opts_ok(o) || stage < 0 || stage >= CP_N_BN || which < 0 || which > 1)
+        return CP_ERR_ARG;
+    if (!o->save_for_backward) return CP_ERR_UNSUPPORTED;
+    const Ws w = carve(const_cast<void*>(workspace), n, o);
+    if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
+    const float* src;
+    size_t elems;
+    if (stage < 2) {
+        src = which == 0 ? (stage == 0 ? w.Y1 : w.Y2) : (stage == 0 ? w.A1 : w.A2);
+        elems = (size_t)n * 12 * F_CONV;
+    } else {
+        src = which == 0 ? w.Y[stage - 2] : w.A[stage - 2];
+        elems = (size_t)n * F_FC;
+    }
+    CP_CUDA(cudaMemcpyAsync(dst, src, elems * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return CP_OK;
+}
+
 // ------------------------------------------------------------------- layer-level entry points
 extern "C" size_t cp_linear_workspace_bytes(int64_t M, int N, int K) {
     const size_t part = cp_align((size_t)cp_cdiv(M, 128) * N * sizeof(float));

@@ -1,6 +1,12 @@
 #include "common.cuh"
 
+unsigned long long g_cp_launches = 0;
+
 extern "C" int cp_version(void) { return 100; }   // 0.1.0
+
+// number of kernels this library has launched in this process (host-side counter, not thread-safe
+// across concurrent callers; used by bench.py's gpu_launches)
+extern "C" unsigned long long cp_launch_count(void) { return g_cp_launches; }
 
 extern "C" const char* cp_status_string(int status) {
     switch (status) {

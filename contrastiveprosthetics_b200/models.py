@@ -108,6 +108,8 @@ class _EncoderFn(torch.autograd.Function):
             ctx.ws, ctx.opts, ctx.tens, ctx.n = ws, opts, tens, n
             ctx.params = params            # keeps the storages (and pointers in `tens`) alive
             ctx.cfg = cfg
+            if cfg.get("tap") is not None:
+                cfg["tap"].update(ws=ws, opts=opts, n=n)
         return emb
 
     @staticmethod
@@ -398,6 +400,7 @@ class EMGNet(nn.Module):
         self.dropout_seed = 0x5EED
         self._step = 0
         self.ext_dropout_masks = None        # (4, N, 512) uint8 keep masks injected by parity tests
+        self.debug_tap = None                # set to {} to keep the workspace for read_activation()
         self.shape = None
 
     # ordered views of the module tree for the kernels
@@ -437,8 +440,24 @@ class EMGNet(nn.Module):
                "seed": (self.dropout_seed * 1000003 + self._step) & 0xFFFFFFFFFFFFFFFF,
                "ext_masks": self.ext_dropout_masks if dp > 0 else None,
                "bn_rm": rm, "bn_rv": rv,
-               "need_bwd": torch.is_grad_enabled() and self.training}
+               "need_bwd": torch.is_grad_enabled() and self.training,
+               "tap": self.debug_tap}
         return _EncoderFn.apply(x, cfg, *self.kernel_params())
+
+    def read_activation(self, stage, which=0):
+        """Parity tap (tests): saved activation of BN stage 0..8 of the last training forward, in the
+        reference's layout ((N,64,1,12) for the conv stages, (N,512) for the linear ones).  Needs
+        `self.debug_tap = {}` before the forward."""
+        t = self.debug_tap
+        n = t["n"]
+        shape = (n * 12, 64) if stage < 2 else (n, 512)
+        dst = torch.empty(shape, dtype=torch.float32, device=t["ws"].device)
+        _lib.check(_lib.lib().cp_encoder_read_activation(_lib.ptr(t["ws"]), t["ws"].numel(), n, ctypes.byref(t["opts"]),
+                                                         stage, which, _lib.ptr(dst), _lib.stream()),
+                   "cp_encoder_read_activation")
+        if stage < 2:
+            return dst.reshape(n, 12, 64).permute(0, 2, 1).reshape(n, 64, 1, 12)
+        return dst
 
     def forward(self, EMG):
         """models.py:319-342 incl. the (B,41,W) -> (B*W,41) regrouping."""

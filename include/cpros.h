@@ -32,6 +32,8 @@ extern "C" {
 #define CP_N_FC 7
 
 int cp_version(void);
+/* kernels launched by this library in this process so far (host-side counter) */
+unsigned long long cp_launch_count(void);
 /* static string for a status returned by any entry point */
 const char *cp_status_string(int status);
 
@@ -93,6 +95,13 @@ int cp_encoder_forward(const cp_encoder_tensors *params, const float *x, int64_t
 int cp_encoder_backward(const cp_encoder_tensors *params, const float *d_emb, int64_t n,
                         const cp_encoder_tensors *grads, void *workspace, size_t workspace_bytes,
                         const cp_encoder_opts *opts, void *stream);
+
+/* Parity tap: copy the saved activation of BN stage `stage` (0,1: conv stages, layout (n*12,64)
+ * position-major/channel-contiguous; 2..8: linear stages, (n,512)) out of a workspace written by
+ * cp_encoder_forward(save_for_backward=1).  which = 0: post-ReLU pre-BN, 1: post-BN(/dropout). */
+int cp_encoder_read_activation(const void *workspace, size_t workspace_bytes, int64_t n,
+                               const cp_encoder_opts *opts, int stage, int which, float *dst,
+                               void *stream);
 
 /* Layer-level entry points (unit parity tests; the encoder calls the same kernels).
  * Y = relu?(A[M,K] @ W[N,K]^T + bias) with per-column sum / sum-of-squares (BN statistics). */

@@ -78,28 +78,45 @@ def _batch_norm(sd, prefix, x, adabn, training, new_stats):
     return y
 
 
+def _relu(out, relu_masks, i):
+    """ReLU, or -- for kink-controlled gradient parity -- multiplication by an injected 0/1 mask (the
+    ReLU pattern another implementation took: pre-activations within float noise of 0 otherwise
+    flip between any two fp32 evaluations and change the gradient by O(1/sqrt(#elements)))."""
+    if relu_masks is None:
+        return F.relu(out)
+    return out * relu_masks[i].to(out.dtype)
+
+
 def encoder_forward(sd, x, adabn=True, training=True, dropout_masks=None, dp=0.0, new_stats=None,
-                    taps=None):
+                    taps=None, relu_masks=None):
     """EMGNet.forward up to the projection (models.py:319-323): x (N,12) -> emb (N,d_e).
 
     dropout_masks: optional list of 4 {0,1} tensors (N,512) for the dropout after linear blocks
     4..7 (models.py:282-297); applied as mask/(1-dp) in training.  None and dp==0 -> identity.
-    taps: optional dict that receives intermediate activations (for layer-level parity tests)."""
+    taps: optional dict that receives intermediate activations (for layer-level parity tests).
+    relu_masks: optional list of 9 0/1 tensors (2 conv stages (N,64,1,12), 7 linear stages (N,512))."""
     out = x.reshape(-1, 1, 1, EMG_DIM)
+    stage = 0
     for ci, bi in CONV_BLOCKS:
         out = F.conv2d(out, sd[f"emg_net.conv_emg.{ci}.weight"], sd[f"emg_net.conv_emg.{ci}.bias"],
                        padding=(1, 1))
-        out = F.relu(out)
         if taps is not None:
-            taps[f"conv{ci}_relu"] = out
+            taps[f"pre{stage}"] = out
+        out = _relu(out, relu_masks, stage)
+        if taps is not None:
+            taps[f"relu{stage}"] = out
+        stage += 1
         out = _batch_norm(sd, bn_prefix(adabn, "conv_emg", bi), out, adabn, training, new_stats)
     out = out.flatten(1)
     d = 0
     for li, bi, has_dp in LINEAR_BLOCKS:
         out = F.linear(out, sd[f"emg_net.linear.{li}.weight"], sd[f"emg_net.linear.{li}.bias"])
-        out = F.relu(out)
         if taps is not None:
-            taps[f"linear{li}_relu"] = out
+            taps[f"pre{stage}"] = out
+        out = _relu(out, relu_masks, stage)
+        if taps is not None:
+            taps[f"relu{stage}"] = out
+        stage += 1
         out = _batch_norm(sd, bn_prefix(adabn, "linear", bi), out, adabn, training, new_stats)
         if has_dp:
             if training and dropout_masks is not None and dp > 0:

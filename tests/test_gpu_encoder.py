@@ -19,7 +19,14 @@ from gpu_util import load_sd, perturbed_state, rel_err
 pytestmark = pytest.mark.gpu
 PARAMS = {'d_e': 16, 'dp_emg': 0.0, 'dp_glove': 0.0, 'reg_emg': 0.0, 'reg_glove': 0.0}
 FWD_TOL = 1e-5
-GRAD_TOL = 1e-4          # vs fp32 oracle; see test_backward_error_in_fp64_context for the 1e-5 context
+# Gradients: 1e-5-level agreement holds once both sides take the SAME ReLU branches.  Any two fp32
+# evaluations (the reference on CPU vs on GPU included) flip the pre-activations that lie within
+# rounding noise of 0 (~2e-6 of all elements per layer), and each flip moves a gradient tensor by
+# ~1/sqrt(#elements) of its norm (measured: 2.4e-3 at 328 windows; the fp32 ORACLE itself is 1e-3
+# away from the fp64 oracle).  So the tight test injects the kernel's ReLU pattern into the oracle
+# (oracle.model._relu) and the un-conditioned test only bounds the flip noise.
+GRAD_TOL = 2e-5
+GRAD_TOL_UNCONDITIONED = 2e-2
 
 
 @pytest.mark.parametrize("M,N,K,relu", [(300, 512, 512, 1), (128, 512, 768, 1), (1000, 64, 192, 0), (1, 512, 512, 1)])
@@ -91,54 +98,79 @@ def test_encoder_forward(adabn, training, n):
                 assert int(got[k]) == int(v), k
 
 
-def _grads_cuda(sd, adabn, x, d_emb, dp=0.0, masks=None):
+def _grads_cuda(sd, adabn, x, d_emb, dp=0.0, masks=None, taps=None):
     m = _model(sd, adabn, dp)
     m.train(True)
+    m.emg_net.debug_tap = {}
     if masks is not None:
         m.emg_net.ext_dropout_masks = torch.stack(masks).to(torch.uint8).cuda().contiguous()
     emb = m.emg_net.encode_flat(x.cuda())
     emb.backward(d_emb.cuda())
+    if taps is not None:
+        for stage in range(9):
+            taps[f"relu{stage}"] = m.emg_net.read_activation(stage, 0).cpu()
+            taps[f"bn{stage}"] = m.emg_net.read_activation(stage, 1).cpu()
     return emb.detach().cpu(), {"emg_net." + k: p.grad.detach().cpu() for k, p in m.emg_net.named_parameters()}
 
 
-def _grads_oracle(sd, adabn, x, d_emb, dtype, dp=0.0, masks=None):
+def _relu_pattern(taps):
+    return [(taps[f"relu{s}"] > 0) for s in range(9)]
+
+
+def _grads_oracle(sd, adabn, x, d_emb, dtype, dp=0.0, masks=None, relu_masks=None, taps=None):
     p = {}
     for k, v in sd.items():
         if v.is_floating_point():
             p[k] = v.to(dtype).clone().requires_grad_(k in OM.trainable_keys(sd))
         else:
             p[k] = v.clone()
-    emb = OM.encoder_forward(p, x.to(dtype), adabn, True, masks, dp)
+    emb = OM.encoder_forward(p, x.to(dtype), adabn, True, masks, dp, taps=taps, relu_masks=relu_masks)
     emb.backward(d_emb.to(dtype))
     return emb.detach(), {k: p[k].grad for k in p if k.startswith("emg_net.") and getattr(p[k], "grad", None) is not None}
 
 
 @pytest.mark.parametrize("adabn", [True, False])
-@pytest.mark.parametrize("n", [41 * 8, 777])
+@pytest.mark.parametrize("n", [41 * 8, 777, 41 * 100])
 def test_encoder_backward(adabn, n):
     sd = perturbed_state(11, adabn)
     g = torch.Generator().manual_seed(n + 1)
     x, d_emb = torch.randn(n, 12, generator=g), torch.randn(n, 16, generator=g)
-    emb, got = _grads_cuda(sd, adabn, x, d_emb)
-    ref_emb, ref = _grads_oracle(sd, adabn, x, d_emb, torch.float32)
+    taps = {}
+    emb, got = _grads_cuda(sd, adabn, x, d_emb, taps=taps)
+    # every stage's activation (post-ReLU) agrees with the oracle's
+    otaps = {}
+    ref_emb, ref_free = _grads_oracle(sd, adabn, x, d_emb, torch.float32, taps=otaps)
     assert rel_err(emb, ref_emb) < FWD_TOL
+    for stage in range(9):
+        assert rel_err(taps[f"relu{stage}"], otaps[f"relu{stage}"].detach()) < FWD_TOL, stage
+    # tight: same ReLU pattern on both sides
+    _, ref = _grads_oracle(sd, adabn, x, d_emb, torch.float32, relu_masks=_relu_pattern(taps))
     assert set(got) == set(ref)
     worst = max((rel_err(got[k], ref[k]), k) for k in ref)
     assert worst[0] < GRAD_TOL, worst
+    # un-conditioned: only ReLU-flip noise separates the two fp32 evaluations
+    worst = max((rel_err(got[k], ref_free[k]), k) for k in ref_free)
+    assert worst[0] < GRAD_TOL_UNCONDITIONED, worst
+    flips = sum(int(((taps[f"relu{s}"] > 0) != (otaps[f"relu{s}"] > 0)).sum()) for s in range(9))
+    total = sum(taps[f"relu{s}"].numel() for s in range(9))
+    assert flips / total < 1e-4, (flips, total)
     # the structurally-zero rows of the 3x3 kernels get exactly zero data gradient
     for k in ("emg_net.conv_emg.0.weight", "emg_net.conv_emg.3.weight"):
         assert torch.count_nonzero(got[k][:, :, 0, :]) == 0 and torch.count_nonzero(got[k][:, :, 2, :]) == 0
 
 
 def test_backward_error_in_fp64_context():
-    """fp32 CUDA gradients are as close to the fp64 truth as the fp32 oracle (reference arithmetic) is."""
+    """With the ReLU pattern fixed, fp32 CUDA gradients are as close to the fp64 truth as the fp32
+    oracle (the reference's own arithmetic) is."""
     adabn, n = True, 41 * 16
     sd = perturbed_state(13, adabn)
     g = torch.Generator().manual_seed(5)
     x, d_emb = torch.randn(n, 12, generator=g), torch.randn(n, 16, generator=g)
-    _, got = _grads_cuda(sd, adabn, x, d_emb)
-    _, ref32 = _grads_oracle(sd, adabn, x, d_emb, torch.float32)
-    _, ref64 = _grads_oracle(sd, adabn, x, d_emb, torch.float64)
+    taps = {}
+    _, got = _grads_cuda(sd, adabn, x, d_emb, taps=taps)
+    pat = _relu_pattern(taps)
+    _, ref32 = _grads_oracle(sd, adabn, x, d_emb, torch.float32, relu_masks=pat)
+    _, ref64 = _grads_oracle(sd, adabn, x, d_emb, torch.float64, relu_masks=pat)
     for k in ref64:
         e_cuda, e_ref = rel_err(got[k], ref64[k]), rel_err(ref32[k], ref64[k])
         assert e_cuda < max(3 * e_ref, 1e-5), (k, e_cuda, e_ref)
@@ -151,8 +183,9 @@ def test_dropout_with_injected_masks():
     g = torch.Generator().manual_seed(9)
     x, d_emb = torch.randn(n, 12, generator=g), torch.randn(n, 16, generator=g)
     masks = [torch.empty(n, 512).bernoulli_(0.5, generator=g) for _ in range(4)]
-    emb, got = _grads_cuda(sd, adabn, x, d_emb, dp, masks)
-    ref_emb, ref = _grads_oracle(sd, adabn, x, d_emb, torch.float32, dp, masks)
+    taps = {}
+    emb, got = _grads_cuda(sd, adabn, x, d_emb, dp, masks, taps=taps)
+    ref_emb, ref = _grads_oracle(sd, adabn, x, d_emb, torch.float32, dp, masks, relu_masks=_relu_pattern(taps))
     assert rel_err(emb, ref_emb) < FWD_TOL
     worst = max((rel_err(got[k], ref[k]), k) for k in ref)
     assert worst[0] < GRAD_TOL, worst

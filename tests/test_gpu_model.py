@@ -59,6 +59,7 @@ def test_first_train_step_matches_reference_fixture(gm, tw, adabn):
     assert np.array_equal(EMG.cpu().numpy(), gm[f"{tag}|EMG0"])
     model.set_train()
     model.materialize_logits = True
+    model.emg_net.debug_tap = {}
     logits = model.forward(EMG, GLOVE, label.reshape(-1))
     loss = model.loss(logits, label.reshape(-1))
     l2 = model.l2()
@@ -68,7 +69,23 @@ def test_first_train_step_matches_reference_fixture(gm, tw, adabn):
     assert float((logits.detach().cpu() - torch.from_numpy(gm[f"{tag}|logits0"])).abs().max()) < 1e-5
     grads = {n: p.grad.detach().cpu() for n, p in model.named_parameters() if p.grad is not None}
     assert "logit_scale" not in grads
-    _check_grads(gm, tag, grads, 1e-4)
+    # vs the stored reference gradients: bounded by ReLU-flip noise between two fp32 evaluations
+    # (tests/test_gpu_encoder.py explains; 123-window batch -> ~1/sqrt(63k) per flip)
+    _check_grads(gm, tag, grads, 3e-2)
+    # vs the oracle (pinned to the reference at 2e-5 by tests/test_oracle_golden.py) with the
+    # kernel's ReLU pattern injected: rounding-level agreement
+    sd = OM.init_state(42, adabn)
+    pat = [(model.emg_net.read_activation(s, 0).cpu() > 0) for s in range(9)]
+    p = {k: (v.clone().requires_grad_(True) if k in OM.trainable_keys(sd) else v.clone()) for k, v in sd.items()}
+    emb = OM.encoder_forward(p, EMG.cpu().reshape(-1, 12), adabn, True, relu_masks=pat)
+    emb = emb.reshape(3, 41, 1, 16).transpose(1, 2).reshape(3, 41, 16)
+    emb = emb / emb.norm(dim=-1, keepdim=True)
+    tab = OM.class_table(p)
+    tab = tab / tab.norm(dim=-1, keepdim=True)
+    res = OM.contrastive_loss(torch.matmul(emb, tab.t()), True)
+    (res["loss"] + OM.l2_penalty(p, PARAMS['reg_emg'], PARAMS['reg_glove'])).backward()
+    for k in OM.trainable_keys(sd):
+        assert rel_err(grads[k], p[k].grad) < 2e-5, k
     assert model.corrects[0] == gm[f"{tag}|train_corrects"][0]
     if not adabn:
         sd = model.state_dict()
