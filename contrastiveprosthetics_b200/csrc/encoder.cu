@@ -12,8 +12,14 @@
 //   per stage: Y (post-ReLU, pre-BN; kept for backward) and A (post-BN/dropout = next GEMM input).
 // BatchNorm statistics are produced by the GEMM / conv epilogues as per-CTA partial column sums
 // (no second pass over the activation) and finalised in double precision.
+//
+// Engines (cp_encoder_opts.engine): CP_ENGINE_SIMT runs every GEMM as fp32 FFMA; CP_ENGINE_TC runs the
+// seven linear layers (97 % of the MACs outside conv2) on tcgen05 with the 3xTF32 split: the BN-apply
+// and BN-backward kernels then write their outputs as two tf32 planes (hi, lo) that the TMA-fed GEMMs
+// consume directly, and the weights are split (and transposed for the data gradient) once per call.
 #include <algorithm>
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "encoder_kernels.cuh"
 
 namespace {
@@ -35,6 +41,9 @@ struct Ws {
     float *wpart;              // split-K weight-gradient partials
     float *Wc2, *Wc2d, *W1p;
     float *ppart;              // projection / conv1 weight-gradient partials
+    // tensor-core engine: low planes (the high plane reuses the fp32 slot) and split weights
+    float *A2_lo, *A_lo[CP_N_FC], *G1_lo;
+    float *Wh[CP_N_FC], *Wl[CP_N_FC], *Wth[CP_N_FC], *Wtl[CP_N_FC];
     size_t bytes;
 };
 
@@ -91,6 +100,25 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     w.ppart = save ? c.take<float>((size_t)cp_cdiv(n, PROJ_W_ROWS) * CP_EMB_DIM * 512 +
                                    (size_t)cp_cdiv(n * 12, 1024) * 3 * 64)
                    : nullptr;
+    w.A2_lo = w.G1_lo = nullptr;
+    for (int l = 0; l < CP_N_FC; ++l) w.A_lo[l] = w.Wh[l] = w.Wl[l] = w.Wth[l] = w.Wtl[l] = nullptr;
+    if (o->engine == CP_ENGINE_TC) {
+        if (save) {
+            w.A2_lo = c.take<float>(conv_elems);
+            for (int l = 0; l + 1 < CP_N_FC; ++l) w.A_lo[l] = c.take<float>(fc_elems);
+            w.G1_lo = c.take<float>(conv_elems);
+        } else {
+            float* l0 = c.take<float>(conv_elems);
+            float* l1 = c.take<float>(conv_elems);
+            w.A2_lo = l1;                                   // pairs with A2 = a1
+            for (int l = 0; l + 1 < CP_N_FC; ++l) w.A_lo[l] = (l & 1) ? l1 : l0;
+        }
+        for (int l = 0; l < CP_N_FC; ++l) {
+            const size_t we = (size_t)F_FC * (l == 0 ? K_FC1 : F_FC);
+            w.Wh[l] = c.take<float>(we); w.Wl[l] = c.take<float>(we);
+            w.Wth[l] = c.take<float>(we); w.Wtl[l] = c.take<float>(we);
+        }
+    }
     w.bytes = c.off;
     return w;
 }
@@ -147,10 +175,14 @@ int bn_finalize(const Ws& w, int l, int F, int P, int64_t R, const cp_encoder_te
     return CP_OK;
 }
 
+// a_lo != null: write (hi, lo) tf32 planes instead of the fp32 value
 template <int F>
-int bn_apply(const float* y, float* a, int64_t R, const Ws& w, int l, const uint8_t* keep, float inv_keep,
-             cudaStream_t st) {
-    bn_apply_kernel<F><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, R, w.scale[l], w.shift[l], keep, inv_keep);
+int bn_apply(const float* y, float* a, float* a_lo, int64_t R, const Ws& w, int l, const uint8_t* keep,
+             float inv_keep, cudaStream_t st) {
+    if (a_lo)
+        bn_apply_kernel<F, true><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, a_lo, R, w.scale[l], w.shift[l], keep, inv_keep);
+    else
+        bn_apply_kernel<F, false><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, nullptr, R, w.scale[l], w.shift[l], keep, inv_keep);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
@@ -158,7 +190,7 @@ int bn_apply(const float* y, float* a, int64_t R, const Ws& w, int l, const uint
 // BN backward + ReLU backward of stage l:  g (grad w.r.t. stage output A) -> gz (grad w.r.t. the
 // pre-activation), d_gamma, d_beta, d_bias
 template <int F>
-int bn_backward(const float* g, const float* y, float* gz, int64_t R, const Ws& w, int l,
+int bn_backward(const float* g, const float* y, float* gz, float* gz_lo, int64_t R, const Ws& w, int l,
                 const uint8_t* keep, float inv_keep, const float* gamma, float* d_gamma, float* d_beta,
                 float* d_bias, cudaStream_t st) {
     const int P = (int)cp_cdiv(R, ColMap<F>::ROWS);
@@ -166,8 +198,12 @@ int bn_backward(const float* g, const float* y, float* gz, int64_t R, const Ws& 
     CP_CHECK_LAUNCH();
     bn_bwd_finalize_kernel<<<F / 32, 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta);
     CP_CHECK_LAUNCH();
-    bn_bwd_apply_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], gamma, w.m1, w.m2,
-                                              gz, w.pa);
+    if (gz_lo)
+        bn_bwd_apply_kernel<F, true><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], gamma, w.m1,
+                                                        w.m2, gz, gz_lo, w.pa);
+    else
+        bn_bwd_apply_kernel<F, false><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], gamma, w.m1,
+                                                         w.m2, gz, nullptr, w.pa);
     CP_CHECK_LAUNCH();
     colsum_finalize_kernel<<<F / 32, 1024, 0, st>>>(w.pa, P, F, d_bias, 0);
     CP_CHECK_LAUNCH();
@@ -181,7 +217,18 @@ int bn_backward(const float* g, const float* y, float* gz, int64_t R, const Ws& 
     } while (0)
 
 bool opts_ok(const cp_encoder_opts* o) {
-    return o && o->bn_mode >= 0 && o->bn_mode <= 2 && o->dropout_p >= 0.f && o->dropout_p < 1.f;
+    return o && o->bn_mode >= 0 && o->bn_mode <= 2 && o->dropout_p >= 0.f && o->dropout_p < 1.f &&
+           (o->engine == CP_ENGINE_SIMT || o->engine == CP_ENGINE_TC);
+}
+
+// weight-gradient through the tensor-core split-K kernel + the shared re-layout / reduce kernel
+int tc_wgrad(const float* Gh, const float* Gl, int Mo, const float* Ah, const float* Al, int No, int64_t R,
+             float* wpart, float* out, int mode, cudaStream_t st) {
+    int S = 0;
+    CP_TRY(tcg::launch_tn(Gh, Gl, Mo, Mo, Ah, Al, No, No, R, wpart, WPART_ELEMS, &S, st));
+    wgrad_reduce_kernel<<<(unsigned)cp_cdiv((int64_t)Mo * No, 256), 256, 0, st>>>(wpart, S, Mo, No, out, mode);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
 }
 
 }  // namespace
@@ -195,8 +242,8 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
                                   void* workspace, size_t workspace_bytes, const cp_encoder_opts* o,
                                   void* stream) {
     if (!p || !x || !emb || !workspace || n <= 0 || !opts_ok(o)) return CP_ERR_ARG;
-    if (o->engine != CP_ENGINE_SIMT) return CP_ERR_UNSUPPORTED;
     if (((uintptr_t)workspace) % 256 != 0) return CP_ERR_ARG;
+    const bool tcE = o->engine == CP_ENGINE_TC;
     const Ws w = carve(workspace, n, o);
     if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -204,6 +251,14 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
 
     prep_weights_kernel<<<(F_FC * K_FC1 + 255) / 256, 256, 0, st>>>(p->conv2_w, p->fc_w[0], w.Wc2, w.Wc2d, w.W1p);
     CP_CHECK_LAUNCH();
+    if (tcE) {
+        for (int l = 0; l < CP_N_FC; ++l) {
+            const int K = l == 0 ? K_FC1 : F_FC;
+            prep_weights_tc_kernel<<<(F_FC * K + 255) / 256, 256, 0, st>>>(p->fc_w[l], K, l == 0, w.Wh[l], w.Wl[l],
+                                                                         w.Wth[l], w.Wtl[l]);
+            CP_CHECK_LAUNCH();
+        }
+    }
     CP_CUDA(cudaMemcpyAsync(w.X0, x, sizeof(float) * R12, cudaMemcpyDeviceToDevice, st));
 
     // conv1 -> ReLU (+stats) -> BN
@@ -211,12 +266,12 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     conv1_fwd_kernel<<<P1, 256, 0, st>>>(w.X0, R12, p->conv1_w, p->conv1_b, w.Y1, w.pa, w.pb);
     CP_CHECK_LAUNCH();
     CP_TRY(bn_finalize(w, 0, F_CONV, P1, R12, p, o, st));
-    CP_TRY(bn_apply<F_CONV>(w.Y1, w.A1, R12, w, 0, nullptr, 1.f, st));
+    CP_TRY(bn_apply<F_CONV>(w.Y1, w.A1, nullptr, R12, w, 0, nullptr, 1.f, st));
 
     // conv2 as implicit GEMM [n*12, 192] x [64, 192]^T
     CP_TRY((launch_nt<128, 64, 0, true>(w.A1, R12, 192, 64, w.Wc2, 64, 192, p->conv2_b, w.Y2, 64, w.pa, w.pb, 1, st)));
     CP_TRY(bn_finalize(w, 1, F_CONV, (int)cp_cdiv(R12, 128), R12, p, o, st));
-    CP_TRY(bn_apply<F_CONV>(w.Y2, w.A2, R12, w, 1, nullptr, 1.f, st));
+    CP_TRY(bn_apply<F_CONV>(w.Y2, w.A2, w.A2_lo, R12, w, 1, nullptr, 1.f, st));
 
     // 7 x Linear -> ReLU -> BN (-> Dropout)
     const float inv_keep = o->dropout_p > 0.f ? 1.f / (1.f - o->dropout_p) : 1.f;
@@ -224,7 +279,13 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
         const float* in = l == 0 ? w.A2 : w.A[l - 1];
         const int K = l == 0 ? K_FC1 : F_FC;
         const float* W = l == 0 ? w.W1p : p->fc_w[l];
-        CP_TRY((launch_nt<128, 128, 0, false>(in, n, K, K, W, F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb, 1, st)));
+        if (tcE) {
+            const float* in_lo = l == 0 ? w.A2_lo : w.A_lo[l - 1];
+            CP_TRY(tcg::launch_nt(in, in_lo, n, K, K, w.Wh[l], w.Wl[l], F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb,
+                                  1, st));
+        } else {
+            CP_TRY((launch_nt<128, 128, 0, false>(in, n, K, K, W, F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb, 1, st)));
+        }
         CP_TRY(bn_finalize(w, 2 + l, F_FC, (int)cp_cdiv(n, 128), n, p, o, st));
         const uint8_t* keep = nullptr;
         if (l >= 3 && o->dropout_p > 0.f) {
@@ -239,7 +300,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
             }
             keep = w.keep[d];
         }
-        CP_TRY(bn_apply<F_FC>(w.Y[l], w.A[l], n, w, 2 + l, keep, inv_keep, st));
+        CP_TRY(bn_apply<F_FC>(w.Y[l], w.A[l], w.A_lo[l], n, w, 2 + l, keep, inv_keep, st));
     }
     // projection 512 -> 16
     proj_fwd_kernel<<<(unsigned)std::min<int64_t>(cp_cdiv(n, 8), (int64_t)CP_NUM_SMS * 4), 256, 0, st>>>(
@@ -252,8 +313,8 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
                                    const cp_encoder_tensors* gr, void* workspace, size_t workspace_bytes,
                                    const cp_encoder_opts* o, void* stream) {
     if (!p || !d_emb || !gr || !workspace || n <= 0 || !opts_ok(o)) return CP_ERR_ARG;
-    if (o->engine != CP_ENGINE_SIMT) return CP_ERR_UNSUPPORTED;
     if (!o->save_for_backward || o->bn_mode == CP_BN_RUNNING) return CP_ERR_UNSUPPORTED;
+    const bool tcE = o->engine == CP_ENGINE_TC;
     const Ws w = carve(workspace, n, o);
     if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -273,9 +334,16 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     // linear blocks, last to first.  G0 = grad w.r.t. block output, G1 = grad w.r.t. pre-activation
     for (int l = CP_N_FC - 1; l >= 0; --l) {
         const uint8_t* keep = (l >= 3 && o->dropout_p > 0.f) ? w.keep[l - 3] : nullptr;
-        CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], w.G1, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l], gr->bn_w[2 + l],
-                                 gr->bn_b[2 + l], gr->fc_b[l], st));
-        if (l > 0) {
+        CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], w.G1, w.G1_lo, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
+                                 gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st));
+        if (tcE) {
+            const int K = l == 0 ? K_FC1 : F_FC;
+            const float* ah = l == 0 ? w.A2 : w.A[l - 1];
+            const float* al = l == 0 ? w.A2_lo : w.A_lo[l - 1];
+            CP_TRY(tc_wgrad(w.G1, w.G1_lo, F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, st));
+            CP_TRY(tcg::launch_nt(w.G1, w.G1_lo, n, F_FC, F_FC, w.Wth[l], w.Wtl[l], K, F_FC, nullptr, w.G0, K, nullptr,
+                                  nullptr, 0, st));
+        } else if (l > 0) {
             CP_TRY((launch_wgrad<128, 128, false>(w.G1, F_FC, F_FC, w.A[l - 1], F_FC, F_FC, n, w.wpart, gr->fc_w[l], 0, st)));
             CP_TRY((launch_nt<128, 128, 1, false>(w.G1, n, F_FC, F_FC, p->fc_w[l], F_FC, F_FC, nullptr, w.G0, F_FC,
                                                   nullptr, nullptr, 0, st)));
@@ -286,13 +354,14 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
         }
     }
     // conv2 block: G0 is [n*12, 64] (same memory order as the [n,768] position-major flatten)
-    CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, w.G1, R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1], gr->bn_b[1],
+    // (tensor-core engine: A2 holds only the hi plane; conv2's gradients need neither A2 nor a split G1)
+    CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, w.G1, nullptr, R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1], gr->bn_b[1],
                                gr->conv2_b, st));
     CP_CUDA(cudaMemsetAsync(gr->conv2_w, 0, sizeof(float) * 64 * 64 * 9, st));
     CP_TRY((launch_wgrad<64, 64, true>(w.G1, 64, 64, w.A1, 64, 192, R12, w.wpart, gr->conv2_w, 2, st)));
     CP_TRY((launch_nt<128, 64, 0, true>(w.G1, R12, 192, 64, w.Wc2d, 64, 192, nullptr, w.G0, 64, nullptr, nullptr, 0, st)));
     // conv1 block
-    CP_TRY(bn_backward<F_CONV>(w.G0, w.Y1, w.G1, R12, w, 0, nullptr, 1.f, p->bn_w[0], gr->bn_w[0], gr->bn_b[0],
+    CP_TRY(bn_backward<F_CONV>(w.G0, w.Y1, w.G1, nullptr, R12, w, 0, nullptr, 1.f, p->bn_w[0], gr->bn_w[0], gr->bn_b[0],
                                gr->conv1_b, st));
     const int P1 = (int)cp_cdiv(R12, ColMap<F_CONV>::ROWS);
     float* c1part = w.ppart + (size_t)Pp * CP_EMB_DIM * 512;
@@ -327,24 +396,67 @@ extern "C" int cp_encoder_read_activation(const void* workspace, size_t workspac
 }
 
 // ------------------------------------------------------------------- layer-level entry points
+namespace {
+struct LinWs {
+    float *pa, *pb, *wpart, *Ah, *Al, *Gh, *Gl, *Wh, *Wl;
+    size_t bytes;
+};
+LinWs carve_linear(void* base, int64_t M, int N, int K) {
+    LinWs w;
+    Carver c{reinterpret_cast<char*>(base)};
+    const size_t part = (size_t)cp_cdiv(M, 128) * N;
+    w.pa = c.take<float>(part);
+    w.pb = c.take<float>(part);
+    w.wpart = c.take<float>(WPART_ELEMS);
+    w.Ah = c.take<float>((size_t)M * K); w.Al = c.take<float>((size_t)M * K);
+    w.Gh = c.take<float>((size_t)M * N); w.Gl = c.take<float>((size_t)M * N);
+    w.Wh = c.take<float>((size_t)N * K); w.Wl = c.take<float>((size_t)N * K);
+    w.bytes = c.off;
+    return w;
+}
+int split_planes(const float* x, float* hi, float* lo, size_t elems, cudaStream_t st) {
+    if (elems % 4 != 0) return CP_ERR_ARG;
+    split_tf32_kernel<<<ew_grid((int64_t)(elems / 4)), 256, 0, st>>>(x, hi, lo, (int64_t)(elems / 4));
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+__global__ void __launch_bounds__(256)
+transpose_split_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ th, float* __restrict__ tl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * K) return;
+    float h, l;
+    split_tf32(__ldg(W + i), h, l);
+    const int n = i / K, k = i % K;
+    th[(size_t)k * N + n] = h; tl[(size_t)k * N + n] = l;
+}
+}  // namespace
+
 extern "C" size_t cp_linear_workspace_bytes(int64_t M, int N, int K) {
-    const size_t part = cp_align((size_t)cp_cdiv(M, 128) * N * sizeof(float));
-    return 2 * part + cp_align(WPART_ELEMS * sizeof(float));
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return carve_linear(nullptr, M, N, K).bytes;
 }
 
 extern "C" int cp_linear_forward(const float* A, const float* W, const float* bias, float* Y, int64_t M,
                                  int N, int K, int relu, float* col_sum, float* col_sqsum, void* workspace,
                                  size_t workspace_bytes, int engine, void* stream) {
     if (!A || !W || !Y || M <= 0 || N <= 0 || K <= 0) return CP_ERR_ARG;
-    if (engine != CP_ENGINE_SIMT) return CP_ERR_UNSUPPORTED;
-    if ((col_sum || col_sqsum) && (!col_sum || !col_sqsum || !workspace)) return CP_ERR_ARG;
-    if (col_sum && workspace_bytes < cp_linear_workspace_bytes(M, N, K)) return CP_ERR_WORKSPACE;
+    if (engine != CP_ENGINE_SIMT && engine != CP_ENGINE_TC) return CP_ERR_UNSUPPORTED;
+    if ((col_sum || col_sqsum) && (!col_sum || !col_sqsum)) return CP_ERR_ARG;
+    if ((col_sum || engine == CP_ENGINE_TC) && !workspace) return CP_ERR_ARG;
+    const LinWs w = carve_linear(workspace, M, N, K);
+    if (workspace && workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t part = cp_align((size_t)cp_cdiv(M, 128) * N * sizeof(float));
-    float* pa = col_sum ? reinterpret_cast<float*>(workspace) : nullptr;
-    float* pb = col_sum ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + part) : nullptr;
-    if (N % 128 == 0) CP_TRY((launch_nt<128, 128, 0, false>(A, M, K, K, W, N, K, bias, Y, N, pa, pb, relu, st)));
-    else CP_TRY((launch_nt<128, 64, 0, false>(A, M, K, K, W, N, K, bias, Y, N, pa, pb, relu, st)));
+    float* pa = col_sum ? w.pa : nullptr;
+    float* pb = col_sum ? w.pb : nullptr;
+    if (engine == CP_ENGINE_TC) {
+        CP_TRY(split_planes(A, w.Ah, w.Al, (size_t)M * K, st));
+        CP_TRY(split_planes(W, w.Wh, w.Wl, (size_t)N * K, st));
+        CP_TRY(tcg::launch_nt(w.Ah, w.Al, M, K, K, w.Wh, w.Wl, N, K, bias, Y, N, pa, pb, relu, st));
+    } else if (N % 128 == 0) {
+        CP_TRY((launch_nt<128, 128, 0, false>(A, M, K, K, W, N, K, bias, Y, N, pa, pb, relu, st)));
+    } else {
+        CP_TRY((launch_nt<128, 64, 0, false>(A, M, K, K, W, N, K, bias, Y, N, pa, pb, relu, st)));
+    }
     if (col_sum) {
         const int P = (int)cp_cdiv(M, 128);
         colsum_finalize_kernel<<<(N + 31) / 32, 1024, 0, st>>>(pa, P, N, col_sum, 0);
@@ -360,19 +472,30 @@ extern "C" int cp_linear_backward(const float* G, const float* A, const float* W
                                   int engine, void* stream) {
     if (!G || !A || !W || !workspace || M <= 0 || N % 128 != 0 || K % 128 != 0) return CP_ERR_ARG;
     if ((size_t)N * K > WPART_ELEMS) return CP_ERR_ARG;
-    if (engine != CP_ENGINE_SIMT) return CP_ERR_UNSUPPORTED;
-    if (workspace_bytes < cp_linear_workspace_bytes(M, N, K)) return CP_ERR_WORKSPACE;
+    if (engine != CP_ENGINE_SIMT && engine != CP_ENGINE_TC) return CP_ERR_UNSUPPORTED;
+    const LinWs w = carve_linear(workspace, M, N, K);
+    if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t part = cp_align((size_t)cp_cdiv(M, 128) * N * sizeof(float));
-    float* wpart = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 2 * part);
-    if (dA) CP_TRY((launch_nt<128, 128, 1, false>(G, M, N, N, W, K, K, nullptr, dA, K, nullptr, nullptr, 0, st)));
-    if (dW) CP_TRY((launch_wgrad<128, 128, false>(G, N, N, A, K, K, M, wpart, dW, 0, st)));
+    if (engine == CP_ENGINE_TC) {
+        CP_TRY(split_planes(G, w.Gh, w.Gl, (size_t)M * N, st));
+        if (dA) {
+            transpose_split_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(W, N, K, w.Wh, w.Wl);
+            CP_CHECK_LAUNCH();
+            CP_TRY(tcg::launch_nt(w.Gh, w.Gl, M, N, N, w.Wh, w.Wl, K, N, nullptr, dA, K, nullptr, nullptr, 0, st));
+        }
+        if (dW) {
+            CP_TRY(split_planes(A, w.Ah, w.Al, (size_t)M * K, st));
+            CP_TRY(tc_wgrad(w.Gh, w.Gl, N, w.Ah, w.Al, K, M, w.wpart, dW, 0, st));
+        }
+    } else {
+        if (dA) CP_TRY((launch_nt<128, 128, 1, false>(G, M, N, N, W, K, K, nullptr, dA, K, nullptr, nullptr, 0, st)));
+        if (dW) CP_TRY((launch_wgrad<128, 128, false>(G, N, N, A, K, K, M, w.wpart, dW, 0, st)));
+    }
     if (db) {
-        float* pa = reinterpret_cast<float*>(workspace);
         const int P = (int)cp_cdiv(M, 128);
-        colsum_rows_kernel<<<dim3((N + 31) / 32, P), 256, 0, st>>>(G, M, N, pa);
+        colsum_rows_kernel<<<dim3((N + 31) / 32, P), 256, 0, st>>>(G, M, N, w.pa);
         CP_CHECK_LAUNCH();
-        colsum_finalize_kernel<<<(N + 31) / 32, 1024, 0, st>>>(pa, P, N, db, 0);
+        colsum_finalize_kernel<<<(N + 31) / 32, 1024, 0, st>>>(w.pa, P, N, db, 0);
         CP_CHECK_LAUNCH();
     }
     return CP_OK;

@@ -174,9 +174,10 @@ bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq
 
 // ---------------------------------------------------------------------------------- BN apply
 // a = y*scale + shift, then (linear blocks 4..7) dropout: a * keep / (1-p)   (models.py:282-297)
-template <int F>
+// SPLIT: write the result as the two tf32 planes (hi -> a, lo -> a_lo) the tensor-core GEMMs consume
+template <int F, bool SPLIT>
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, int64_t R,
+bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, float* __restrict__ a_lo, int64_t R,
                 const float* __restrict__ scale, const float* __restrict__ shift,
                 const uint8_t* __restrict__ keep, float inv_keep) {
     const int64_t total = R * (F / 4);
@@ -192,7 +193,14 @@ bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, int64_t R,
             o.x = m.x ? o.x * inv_keep : 0.f; o.y = m.y ? o.y * inv_keep : 0.f;
             o.z = m.z ? o.z * inv_keep : 0.f; o.w = m.w ? o.w * inv_keep : 0.f;
         }
-        reinterpret_cast<float4*>(a)[v] = o;
+        if (SPLIT) {
+            float4 h, l;
+            split_tf32(o, h, l);
+            reinterpret_cast<float4*>(a)[v] = h;
+            reinterpret_cast<float4*>(a_lo)[v] = l;
+        } else {
+            reinterpret_cast<float4*>(a)[v] = o;
+        }
     }
 }
 
@@ -266,13 +274,13 @@ bn_bwd_finalize_kernel(const float* __restrict__ p1, const float* __restrict__ p
 
 // gz = 1[y>0] * gamma*istd * (g' - m1 - xh*m2)     (BN backward, then ReLU backward);
 // partial column sums of gz = bias gradient of the preceding Linear / Conv.
-template <int F>
+template <int F, bool SPLIT>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t R,
                     const uint8_t* __restrict__ keep, float inv_keep, const float* __restrict__ mean,
                     const float* __restrict__ istd, const float* __restrict__ gamma,
                     const float* __restrict__ m1, const float* __restrict__ m2, float* __restrict__ gz,
-                    float* __restrict__ pdb) {
+                    float* __restrict__ gz_lo, float* __restrict__ pdb) {
     __shared__ float red[ColMap<F>::RY * F];
     const int qx = threadIdx.x % ColMap<F>::QX, ry = threadIdx.x / ColMap<F>::QX;
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + qx * 4));
@@ -299,7 +307,14 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, in
         o.y = yv.y > 0.f ? k1 * (gv.y - a1.y - (yv.y - mu.y) * is.y * a2.y) : 0.f;
         o.z = yv.z > 0.f ? k2 * (gv.z - a1.z - (yv.z - mu.z) * is.z * a2.z) : 0.f;
         o.w = yv.w > 0.f ? k3 * (gv.w - a1.w - (yv.w - mu.w) * is.w * a2.w) : 0.f;
-        reinterpret_cast<float4*>(gz)[v] = o;
+        if (SPLIT) {
+            float4 h, l;
+            split_tf32(o, h, l);
+            reinterpret_cast<float4*>(gz)[v] = h;
+            reinterpret_cast<float4*>(gz_lo)[v] = l;
+        } else {
+            reinterpret_cast<float4*>(gz)[v] = o;
+        }
         sb[0] += o.x; sb[1] += o.y; sb[2] += o.z; sb[3] += o.w;
     }
     block_col_reduce<F>(sb, red, qx, ry);
@@ -451,6 +466,22 @@ prep_weights_kernel(const float* __restrict__ conv2_w, const float* __restrict__
         const int o = i / 768, k = i % 768, p = k / 64, c = k % 64;
         W1p[i] = __ldg(fc1_w + o * 768 + c * 12 + p);
     }
+}
+
+// Tensor-core engine weight planes, per linear layer l (K = 768 for l = 0 on the permuted flatten):
+//   fwd  Wh/Wl [512][K]   = split(W (l = 0: W1p))          B operand of Y = A . W^T      (K-major)
+//   dgrad Wth/Wtl [K][512] = split(transpose)                B operand of dA = G . W       (K-major)
+__global__ void __launch_bounds__(256)
+prep_weights_tc_kernel(const float* __restrict__ W, int K, int permute_fc1, float* __restrict__ Wh,
+                       float* __restrict__ Wl, float* __restrict__ Wth, float* __restrict__ Wtl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 512 * K) return;
+    const int o = i / K, k = i % K;
+    const float w = permute_fc1 ? __ldg(W + o * 768 + (k % 64) * 12 + k / 64) : __ldg(W + i);
+    float h, l;
+    split_tf32(w, h, l);
+    Wh[i] = h; Wl[i] = l;
+    Wth[(size_t)k * 512 + o] = h; Wtl[(size_t)k * 512 + o] = l;
 }
 
 // dW = sum_z P[z]  with the inverse re-layouts.  mode 0: identity; 1: fc1 (cols p*64+c -> c*12+p);

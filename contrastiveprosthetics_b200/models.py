@@ -396,7 +396,7 @@ class EMGNet(nn.Module):
         self.last = nn.Sequential(nn.Linear(512, self.d_e, bias=False))
         self.to(self.device)
 
-        self.engine = _lib.ENGINE_SIMT
+        self.engine = _lib.ENGINE_TC         # tcgen05 3xTF32 GEMMs (fp32-level accuracy); ENGINE_SIMT = fp32 FFMA
         self.dropout_seed = 0x5EED
         self._step = 0
         self.ext_dropout_masks = None        # (4, N, 512) uint8 keep masks injected by parity tests

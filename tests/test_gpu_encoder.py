@@ -29,8 +29,16 @@ GRAD_TOL = 2e-5
 GRAD_TOL_UNCONDITIONED = 2e-2
 
 
+ENGINES = [_lib.ENGINE_SIMT, _lib.ENGINE_TC]
+# per-GEMM relative error: fp32 FFMA ~2e-7; tcgen05 3xTF32 ~1e-6 (the TMEM accumulator rounds toward zero)
+GEMM_TOL = {_lib.ENGINE_SIMT: 2e-6, _lib.ENGINE_TC: 5e-6}
+
+
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("M,N,K,relu", [(300, 512, 512, 1), (128, 512, 768, 1), (1000, 64, 192, 0), (1, 512, 512, 1)])
-def test_linear_layer_forward(M, N, K, relu):
+def test_linear_layer_forward(M, N, K, relu, engine):
+    if engine == _lib.ENGINE_TC and N % 128 != 0:
+        pytest.skip("tensor-core tiles are 128 wide; the 64-channel conv stage stays on the FFMA engine")
     g = torch.Generator().manual_seed(0)
     A = torch.randn(M, K, generator=g)
     W = torch.randn(N, K, generator=g) / K ** 0.5
@@ -45,13 +53,17 @@ def test_linear_layer_forward(M, N, K, relu):
     nb = L.cp_linear_workspace_bytes(M, N, K)
     ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
     P = _lib.ptr
-    _lib.check(L.cp_linear_forward(P(Ad), P(Wd), P(bd), P(Y), M, N, K, relu, P(cs), P(cq), P(ws), nb, 0, _lib.stream()))
-    assert rel_err(Y, ref) < 2e-6
-    assert rel_err(cs, ref.double().sum(0)) < 1e-5
-    assert rel_err(cq, (ref.double() ** 2).sum(0)) < 1e-5
+    _lib.check(L.cp_linear_forward(P(Ad), P(Wd), P(bd), P(Y), M, N, K, relu, P(cs), P(cq), P(ws), nb, engine, _lib.stream()))
+    ref64 = F.linear(A.double(), W.double(), b.double())
+    if relu:
+        ref64 = F.relu(ref64)
+    assert rel_err(Y, ref64) < GEMM_TOL[engine]
+    assert rel_err(cs, ref64.sum(0)) < 1e-5
+    assert rel_err(cq, (ref64 ** 2).sum(0)) < 1e-5
 
 
-def test_linear_layer_backward():
+@pytest.mark.parametrize("engine", ENGINES)
+def test_linear_layer_backward(engine):
     M, N, K = 700, 512, 768
     g = torch.Generator().manual_seed(1)
     A, W, G = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(M, N, generator=g)
@@ -61,30 +73,32 @@ def test_linear_layer_backward():
     dA, dW, db = torch.empty(M, K, device="cuda"), torch.empty(N, K, device="cuda"), torch.empty(N, device="cuda")
     nb = L.cp_linear_workspace_bytes(M, N, K)
     ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
-    _lib.check(L.cp_linear_backward(P(Gd), P(Ad), P(Wd), P(dA), P(dW), P(db), M, N, K, P(ws), nb, 0, _lib.stream()))
-    assert rel_err(dA, G.double() @ W.double()) < 2e-6
-    assert rel_err(dW, G.double().t() @ A.double()) < 2e-6
+    _lib.check(L.cp_linear_backward(P(Gd), P(Ad), P(Wd), P(dA), P(dW), P(db), M, N, K, P(ws), nb, engine, _lib.stream()))
+    assert rel_err(dA, G.double() @ W.double()) < GEMM_TOL[engine]
+    assert rel_err(dW, G.double().t() @ A.double()) < GEMM_TOL[engine]
     assert rel_err(db, G.double().sum(0)) < 2e-6
 
 
-def _model(sd, adabn, dp=0.0):
+def _model(sd, adabn, dp=0.0, engine=_lib.ENGINE_SIMT):
     params = dict(PARAMS)
     params['dp_emg'] = dp
     m = Model(params, adabn=adabn, device="cuda")
     load_sd(m, sd)
+    m.emg_net.engine = engine
     return m
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("adabn,training", [(True, True), (True, False), (False, True), (False, False)])
 @pytest.mark.parametrize("n", [41 * 3, 1000])
-def test_encoder_forward(adabn, training, n):
+def test_encoder_forward(adabn, training, n, engine):
     sd = perturbed_state(7, adabn)
     g = torch.Generator().manual_seed(n)
     x = torch.randn(n, 12, generator=g)
     new_stats = {}
     with torch.no_grad():
         ref = OM.encoder_forward(sd, x, adabn, training, new_stats=new_stats)
-    m = _model(sd, adabn)
+    m = _model(sd, adabn, engine=engine)
     m.train(training)
     with torch.no_grad():
         emb = m.emg_net.encode_flat(x.cuda())
@@ -98,8 +112,8 @@ def test_encoder_forward(adabn, training, n):
                 assert int(got[k]) == int(v), k
 
 
-def _grads_cuda(sd, adabn, x, d_emb, dp=0.0, masks=None, taps=None):
-    m = _model(sd, adabn, dp)
+def _grads_cuda(sd, adabn, x, d_emb, dp=0.0, masks=None, taps=None, engine=_lib.ENGINE_SIMT):
+    m = _model(sd, adabn, dp, engine)
     m.train(True)
     m.emg_net.debug_tap = {}
     if masks is not None:
@@ -109,7 +123,6 @@ def _grads_cuda(sd, adabn, x, d_emb, dp=0.0, masks=None, taps=None):
     if taps is not None:
         for stage in range(9):
             taps[f"relu{stage}"] = m.emg_net.read_activation(stage, 0).cpu()
-            taps[f"bn{stage}"] = m.emg_net.read_activation(stage, 1).cpu()
     return emb.detach().cpu(), {"emg_net." + k: p.grad.detach().cpu() for k, p in m.emg_net.named_parameters()}
 
 
@@ -129,14 +142,15 @@ def _grads_oracle(sd, adabn, x, d_emb, dtype, dp=0.0, masks=None, relu_masks=Non
     return emb.detach(), {k: p[k].grad for k in p if k.startswith("emg_net.") and getattr(p[k], "grad", None) is not None}
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("adabn", [True, False])
 @pytest.mark.parametrize("n", [41 * 8, 777, 41 * 100])
-def test_encoder_backward(adabn, n):
+def test_encoder_backward(adabn, n, engine):
     sd = perturbed_state(11, adabn)
     g = torch.Generator().manual_seed(n + 1)
     x, d_emb = torch.randn(n, 12, generator=g), torch.randn(n, 16, generator=g)
     taps = {}
-    emb, got = _grads_cuda(sd, adabn, x, d_emb, taps=taps)
+    emb, got = _grads_cuda(sd, adabn, x, d_emb, taps=taps, engine=engine)
     # every stage's activation (post-ReLU) agrees with the oracle's
     otaps = {}
     ref_emb, ref_free = _grads_oracle(sd, adabn, x, d_emb, torch.float32, taps=otaps)
@@ -159,15 +173,16 @@ def test_encoder_backward(adabn, n):
         assert torch.count_nonzero(got[k][:, :, 0, :]) == 0 and torch.count_nonzero(got[k][:, :, 2, :]) == 0
 
 
-def test_backward_error_in_fp64_context():
+@pytest.mark.parametrize("engine", ENGINES)
+def test_backward_error_in_fp64_context(engine):
     """With the ReLU pattern fixed, fp32 CUDA gradients are as close to the fp64 truth as the fp32
-    oracle (the reference's own arithmetic) is."""
+    oracle (the reference's own arithmetic) is (FFMA engine), or within the 1e-5 budget (3xTF32)."""
     adabn, n = True, 41 * 16
     sd = perturbed_state(13, adabn)
     g = torch.Generator().manual_seed(5)
     x, d_emb = torch.randn(n, 12, generator=g), torch.randn(n, 16, generator=g)
     taps = {}
-    _, got = _grads_cuda(sd, adabn, x, d_emb, taps=taps)
+    _, got = _grads_cuda(sd, adabn, x, d_emb, taps=taps, engine=engine)
     pat = _relu_pattern(taps)
     _, ref32 = _grads_oracle(sd, adabn, x, d_emb, torch.float32, relu_masks=pat)
     _, ref64 = _grads_oracle(sd, adabn, x, d_emb, torch.float64, relu_masks=pat)
@@ -176,7 +191,8 @@ def test_backward_error_in_fp64_context():
         assert e_cuda < max(3 * e_ref, 1e-5), (k, e_cuda, e_ref)
 
 
-def test_dropout_with_injected_masks():
+@pytest.mark.parametrize("engine", ENGINES)
+def test_dropout_with_injected_masks(engine):
     """models.py:282-297: dropout after linear blocks 4..7, keep/(1-p) scaling, same masks both sides."""
     adabn, n, dp = True, 41 * 6, 0.5
     sd = perturbed_state(17, adabn)
@@ -184,7 +200,7 @@ def test_dropout_with_injected_masks():
     x, d_emb = torch.randn(n, 12, generator=g), torch.randn(n, 16, generator=g)
     masks = [torch.empty(n, 512).bernoulli_(0.5, generator=g) for _ in range(4)]
     taps = {}
-    emb, got = _grads_cuda(sd, adabn, x, d_emb, dp, masks, taps=taps)
+    emb, got = _grads_cuda(sd, adabn, x, d_emb, dp, masks, taps=taps, engine=engine)
     ref_emb, ref = _grads_oracle(sd, adabn, x, d_emb, torch.float32, dp, masks, relu_masks=_relu_pattern(taps))
     assert rel_err(emb, ref_emb) < FWD_TOL
     worst = max((rel_err(got[k], ref[k]), k) for k in ref)
