@@ -217,6 +217,10 @@ def run_cuda(args):
 
     ms, clocks, launches = timed(resident_step, args.steps, args.warmup)
     value = N * world / (ms / 1e3)
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "value": value, "ms_per_step": ms, "gpu_launches": int(launches)}))
+        return
 
     # ---- e2e: host batches (pinned) -> H2D every step, loss + correct counts -> host every step
     host_batches = []
@@ -343,6 +347,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch_size", type=int, default=4096, help="groups of 41 windows per GPU per step")
+    ap.add_argument("--profile", action="store_true",
+                    help="only the device-resident train steps (for ncu launch lists); prints a reduced line")
     ap.add_argument("--engine", default="tc", choices=["tc", "simt"],
                     help="tc: tcgen05 3xTF32 GEMMs (default); simt: fp32 FFMA GEMMs")
     args = ap.parse_args()

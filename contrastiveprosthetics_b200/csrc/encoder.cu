@@ -42,7 +42,7 @@ struct Ws {
     float *Wc2, *Wc2d, *W1p;
     float *ppart;              // projection / conv1 weight-gradient partials
     // tensor-core engine: low planes (the high plane reuses the fp32 slot) and split weights
-    float *A2_lo, *A_lo[CP_N_FC], *G1_lo;
+    float *A1_lo, *A2_lo, *A_lo[CP_N_FC], *G1_lo, *Wc2_lo, *Wc2d_lo;
     float *Wh[CP_N_FC], *Wl[CP_N_FC], *Wth[CP_N_FC], *Wtl[CP_N_FC];
     size_t bytes;
 };
@@ -100,16 +100,20 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     w.ppart = save ? c.take<float>((size_t)cp_cdiv(n, PROJ_W_ROWS) * CP_EMB_DIM * 512 +
                                    (size_t)cp_cdiv(n * 12, 1024) * 3 * 64)
                    : nullptr;
-    w.A2_lo = w.G1_lo = nullptr;
+    w.A1_lo = w.A2_lo = w.G1_lo = w.Wc2_lo = w.Wc2d_lo = nullptr;
     for (int l = 0; l < CP_N_FC; ++l) w.A_lo[l] = w.Wh[l] = w.Wl[l] = w.Wth[l] = w.Wtl[l] = nullptr;
     if (o->engine == CP_ENGINE_TC) {
+        w.Wc2_lo = c.take<float>(64 * 192);
+        w.Wc2d_lo = c.take<float>(64 * 192);
         if (save) {
+            w.A1_lo = c.take<float>(conv_elems);
             w.A2_lo = c.take<float>(conv_elems);
             for (int l = 0; l + 1 < CP_N_FC; ++l) w.A_lo[l] = c.take<float>(fc_elems);
             w.G1_lo = c.take<float>(conv_elems);
         } else {
             float* l0 = c.take<float>(conv_elems);
             float* l1 = c.take<float>(conv_elems);
+            w.A1_lo = l0;                                   // pairs with A1 = a0
             w.A2_lo = l1;                                   // pairs with A2 = a1
             for (int l = 0; l + 1 < CP_N_FC; ++l) w.A_lo[l] = (l & 1) ? l1 : l0;
         }
@@ -144,7 +148,7 @@ int launch_nt(const float* A, int64_t M, int K, int lda, const float* B, int N, 
 // dW[Mo,No] = G^T . A, split over row slabs; out written through wgrad_reduce (mode = re-layout)
 template <int BM, int BN, bool ACONV>
 int launch_wgrad(const float* G, int ldg, int Mo, const float* A, int lda, int No, int64_t R, float* wpart,
-                 float* out, int mode, cudaStream_t st) {
+                 float* out, int mode, cudaStream_t st, const float* G_lo = nullptr, const float* A_lo = nullptr) {
     if (Mo % BM != 0 || No % BN != 0) return CP_ERR_ARG;
     const int tiles = (Mo / BM) * (No / BN);
     constexpr int resident = BM * BN >= 128 * 128 ? 2 : 4;      // CTAs per SM the tile shape allows
@@ -156,7 +160,7 @@ int launch_wgrad(const float* G, int ldg, int Mo, const float* A, int lda, int N
     if (S < 1) S = 1;
     int64_t rps = cp_cdiv(cp_cdiv(R, S), GEMM_BK) * GEMM_BK;
     S = (int)cp_cdiv(R, rps);
-    GemmTN g{G, ldg, Mo, A, lda, No, R, rps, wpart};
+    GemmTN g{G, ldg, Mo, A, lda, No, R, rps, wpart, G_lo, A_lo};
     dim3 grid(No / BN, Mo / BM, S);
     gemm_tn_kernel<BM, BN, ACONV><<<grid, 256, 0, st>>>(g);
     CP_CHECK_LAUNCH();
@@ -249,7 +253,8 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t R12 = n * 12;
 
-    prep_weights_kernel<<<(F_FC * K_FC1 + 255) / 256, 256, 0, st>>>(p->conv2_w, p->fc_w[0], w.Wc2, w.Wc2d, w.W1p);
+    prep_weights_kernel<<<(F_FC * K_FC1 + 255) / 256, 256, 0, st>>>(p->conv2_w, p->fc_w[0], w.Wc2, w.Wc2d, w.W1p,
+                                                                    w.Wc2_lo, w.Wc2d_lo);
     CP_CHECK_LAUNCH();
     if (tcE) {
         for (int l = 0; l < CP_N_FC; ++l) {
@@ -266,11 +271,16 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     conv1_fwd_kernel<<<P1, 256, 0, st>>>(w.X0, R12, p->conv1_w, p->conv1_b, w.Y1, w.pa, w.pb);
     CP_CHECK_LAUNCH();
     CP_TRY(bn_finalize(w, 0, F_CONV, P1, R12, p, o, st));
-    CP_TRY(bn_apply<F_CONV>(w.Y1, w.A1, nullptr, R12, w, 0, nullptr, 1.f, st));
+    CP_TRY(bn_apply<F_CONV>(w.Y1, w.A1, w.A1_lo, R12, w, 0, nullptr, 1.f, st));
 
     // conv2 as implicit GEMM [n*12, 192] x [64, 192]^T
-    CP_TRY((launch_nt<128, 64, 0, true>(w.A1, R12, 192, 64, w.Wc2, 64, 192, p->conv2_b, w.Y2, 64, w.pa, w.pb, 1, st)));
-    CP_TRY(bn_finalize(w, 1, F_CONV, (int)cp_cdiv(R12, 128), R12, p, o, st));
+    if (tcE) {
+        CP_TRY(tcg::launch_conv_nt(w.A1, w.A1_lo, n, w.Wc2, w.Wc2_lo, p->conv2_b, w.Y2, w.pa, w.pb, 1, st));
+        CP_TRY(bn_finalize(w, 1, F_CONV, (int)cp_cdiv(n, tcg::CONV_WIN), R12, p, o, st));
+    } else {
+        CP_TRY((launch_nt<128, 64, 0, true>(w.A1, R12, 192, 64, w.Wc2, 64, 192, p->conv2_b, w.Y2, 64, w.pa, w.pb, 1, st)));
+        CP_TRY(bn_finalize(w, 1, F_CONV, (int)cp_cdiv(R12, 128), R12, p, o, st));
+    }
     CP_TRY(bn_apply<F_CONV>(w.Y2, w.A2, w.A2_lo, R12, w, 1, nullptr, 1.f, st));
 
     // 7 x Linear -> ReLU -> BN (-> Dropout)
@@ -354,12 +364,20 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
         }
     }
     // conv2 block: G0 is [n*12, 64] (same memory order as the [n,768] position-major flatten)
-    // (tensor-core engine: A2 holds only the hi plane; conv2's gradients need neither A2 nor a split G1)
-    CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, w.G1, nullptr, R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1], gr->bn_b[1],
-                               gr->conv2_b, st));
+    // tensor-core engine: G1 and A1 are (hi, lo) planes; the FFMA weight-gradient kernel adds them back
+    CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, w.G1, w.G1_lo, R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1],
+                               gr->bn_b[1], gr->conv2_b, st));
     CP_CUDA(cudaMemsetAsync(gr->conv2_w, 0, sizeof(float) * 64 * 64 * 9, st));
-    CP_TRY((launch_wgrad<64, 64, true>(w.G1, 64, 64, w.A1, 64, 192, R12, w.wpart, gr->conv2_w, 2, st)));
-    CP_TRY((launch_nt<128, 64, 0, true>(w.G1, R12, 192, 64, w.Wc2d, 64, 192, nullptr, w.G0, 64, nullptr, nullptr, 0, st)));
+    if (tcE) {
+        int S = 0;
+        CP_TRY(tcg::launch_conv_tn(w.A1, w.A1_lo, w.G1, w.G1_lo, n, w.wpart, WPART_ELEMS, &S, st));
+        wgrad_reduce_kernel<<<(192 * 64 + 255) / 256, 256, 0, st>>>(w.wpart, S, 192, 64, gr->conv2_w, 3);
+        CP_CHECK_LAUNCH();
+        CP_TRY(tcg::launch_conv_nt(w.G1, w.G1_lo, n, w.Wc2d, w.Wc2d_lo, nullptr, w.G0, nullptr, nullptr, 0, st));
+    } else {
+        CP_TRY((launch_wgrad<64, 64, true>(w.G1, 64, 64, w.A1, 64, 192, R12, w.wpart, gr->conv2_w, 2, st)));
+        CP_TRY((launch_nt<128, 64, 0, true>(w.G1, R12, 192, 64, w.Wc2d, 64, 192, nullptr, w.G0, 64, nullptr, nullptr, 0, st)));
+    }
     // conv1 block
     CP_TRY(bn_backward<F_CONV>(w.G0, w.Y1, w.G1, nullptr, R12, w, 0, nullptr, 1.f, p->bn_w[0], gr->bn_w[0], gr->bn_b[0],
                                gr->conv1_b, st));

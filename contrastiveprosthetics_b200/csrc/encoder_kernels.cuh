@@ -452,15 +452,24 @@ proj_bwd_weight_kernel(const float* __restrict__ d, const float* __restrict__ a,
 // Wc2 [o][tap*64+c]  = conv2_w[o][c][1][tap]         conv2 forward  (B operand, [N=64,K=192])
 // Wc2d[c][tap*64+o]  = conv2_w[o][c][1][2-tap]       conv2 data-gradient
 // W1p [o][p*64+c]    = fc1_w[o][c*12+p]              fc1 on the position-major flatten
+// Wc2_lo / Wc2d_lo non-null: write the tf32 (hi, lo) planes (tensor-core engine) instead of fp32
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(const float* __restrict__ conv2_w, const float* __restrict__ fc1_w,
-                    float* __restrict__ Wc2, float* __restrict__ Wc2d, float* __restrict__ W1p) {
+                    float* __restrict__ Wc2, float* __restrict__ Wc2d, float* __restrict__ W1p,
+                    float* __restrict__ Wc2_lo, float* __restrict__ Wc2d_lo) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 64 * 192) {
         const int o = i / 192, k = i % 192, tap = k / 64, c = k % 64;
-        Wc2[i] = __ldg(conv2_w + (o * 64 + c) * 9 + 3 + tap);
+        const float a = __ldg(conv2_w + (o * 64 + c) * 9 + 3 + tap);
         // same flat index read as [c'][tap*64 + o'] with c' = o, o' = c
-        Wc2d[i] = __ldg(conv2_w + (c * 64 + o) * 9 + 3 + (2 - tap));
+        const float b = __ldg(conv2_w + (c * 64 + o) * 9 + 3 + (2 - tap));
+        if (Wc2_lo) {
+            split_tf32(a, Wc2[i], Wc2_lo[i]);
+            split_tf32(b, Wc2d[i], Wc2d_lo[i]);
+        } else {
+            Wc2[i] = a;
+            Wc2d[i] = b;
+        }
     }
     if (i < 512 * 768) {
         const int o = i / 768, k = i % 768, p = k / 64, c = k % 64;
@@ -485,11 +494,19 @@ prep_weights_tc_kernel(const float* __restrict__ W, int K, int permute_fc1, floa
 }
 
 // dW = sum_z P[z]  with the inverse re-layouts.  mode 0: identity; 1: fc1 (cols p*64+c -> c*12+p);
-// 2: conv2 (cols tap*64+c -> [o][c][1][tap] of a zero-initialised (64,64,3,3) tensor)
+// 2: conv2 (cols tap*64+c -> [o][c][1][tap] of a zero-initialised (64,64,3,3) tensor);
+// 3: conv2 from the transposed tensor-core partials P[z][256][64] (row tap*64+c, column o)
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ P, int S, int Mo, int No, float* __restrict__ out, int mode) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Mo * No) return;
+    if (mode == 3) {
+        const int m = i / 64, o = i % 64;                 // Mo = 192 rows used of 256, No = 64
+        double s = 0.0;
+        for (int z = 0; z < S; ++z) s += (double)__ldg(P + ((int64_t)z * 256 + m) * 64 + o);
+        out[(o * 64 + m % 64) * 9 + 3 + m / 64] = (float)s;
+        return;
+    }
     double s = 0.0;
     for (int z = 0; z < S; ++z) s += (double)__ldg(P + (int64_t)z * Mo * No + i);
     const int o = i / No, k = i % No;

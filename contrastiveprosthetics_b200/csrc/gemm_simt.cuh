@@ -194,7 +194,17 @@ struct GemmTN {
     const float* A; int lda; int No;      // [R, lda] (or conv-view base [R,64], No = 192)
     int64_t R; int64_t rows_per_split;
     float* P;                             // [gridDim.z][Mo][No]
+    const float* G_lo; const float* A_lo; // optional low planes (operands stored split as hi + lo)
 };
+
+__device__ __forceinline__ float4 ld_planes(const float* hi, const float* lo, int64_t off) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(hi + off));
+    if (lo) {
+        const float4 l = __ldg(reinterpret_cast<const float4*>(lo + off));
+        v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
+    }
+    return v;
+}
 
 template <int BM, int BN, bool ACONV>
 __global__ void __launch_bounds__(256, 2)
@@ -217,8 +227,7 @@ gemm_tn_kernel(const GemmTN g) {
         for (int q = 0; q < G_LD; ++q) {
             const int f = tid + q * 256, kr = f / (BM / 4), cq = (f % (BM / 4)) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kr < GEMM_BK && rb + kr < r_end)
-                v = __ldg(reinterpret_cast<const float4*>(g.G + (rb + kr) * g.ldg + o0 + cq));
+            if (kr < GEMM_BK && rb + kr < r_end) v = ld_planes(g.G, g.G_lo, (rb + kr) * g.ldg + o0 + cq);
             rg[q] = v;
         }
 #pragma unroll
@@ -228,10 +237,9 @@ gemm_tn_kernel(const GemmTN g) {
             const int64_t r = rb + kr;
             if (kr < GEMM_BK && r < r_end) {
                 if (ACONV) {
-                    if (conv_valid(r, c0 + cq))
-                        v = __ldg(reinterpret_cast<const float4*>(g.A + (r - 1) * CONV_CH + c0 + cq));
+                    if (conv_valid(r, c0 + cq)) v = ld_planes(g.A, g.A_lo, (r - 1) * CONV_CH + c0 + cq);
                 } else {
-                    v = __ldg(reinterpret_cast<const float4*>(g.A + r * g.lda + c0 + cq));
+                    v = ld_planes(g.A, g.A_lo, r * g.lda + c0 + cq);
                 }
             }
             ra[q] = v;

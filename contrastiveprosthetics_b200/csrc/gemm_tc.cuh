@@ -21,6 +21,7 @@ namespace tcg {
 
 constexpr int BM = 128, BN = 128, BK = 32;        // BK floats = 128 bytes = one swizzle row
 constexpr int STAGES = 3;
+constexpr int MAX_STAGES = 4;
 constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB per operand plane per stage
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi, A_lo, B_hi, B_lo
 constexpr int UMMA_K = 8;                         // tf32: 32 bytes of K per instruction
@@ -28,15 +29,27 @@ constexpr int THREADS = 192;
 constexpr int EPI_THREADS = 128;
 constexpr int TMEM_COLS = 512;                    // 2 buffers x (main + correction accumulator) x 128 fp32 columns
 constexpr int ACC_COLS = 2 * BN;                  // columns per buffer
+// conv-view tiles: 10 windows x 12 positions = 120 of the 128 MMA rows carry data
+constexpr int CONV_WIN = 10, CONV_ROWS = 120;
 
 struct Smem {
-    uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+    uint64_t full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
     float csum[4][BN];
     float csq[4][BN];
 };
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + (int)sizeof(Smem);
+
+// geometry of the K-major kernel as a function of the N tile
+template <int BN_> struct NtCfg {
+    static constexpr int B_TILE = BN_ * BK * 4;
+    static constexpr int STAGE = 2 * TILE_BYTES + 2 * B_TILE;
+    static constexpr int NSTAGES = BN_ == 128 ? 3 : 4;
+    static constexpr int ACC = 2 * BN_;               // main + correction accumulator
+    static constexpr int TMEM = 4 * BN_;              // double buffered
+    static constexpr int SMEM = NSTAGES * STAGE + 1024 + (int)sizeof(Smem);
+};
 
 struct NtArgs {
     float* C; int ldc;
@@ -60,29 +73,37 @@ __device__ __forceinline__ void warp_col_reduce32(float (&v)[32], int lane) {
     }
 }
 
+// CONV: the A operand is the conv-view of a [windows][12][64] activation (k = 3 convolution as an
+// implicit GEMM, K = 3 taps x 64 channels = 6 k-blocks of 32): tm_a_* are 3-D maps (32 ch, 12 pos,
+// windows) and k-block kb loads the box at (channel half, tap-1, window0) -- positions -1 and 12 are
+// out of range and arrive as zeros, which is exactly the padding of models.py:255,259.
+template <int BN_, bool CONV>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                   const NtArgs g) {
+    using Cfg = NtCfg<BN_>;
+    constexpr int ROWS = CONV ? CONV_ROWS : BM;                 // data rows per tile
+    constexpr uint32_t A_BYTES = ROWS * BK * 4;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    Smem* sm = reinterpret_cast<Smem*>(tiles + STAGES * STAGE_BYTES);
+    Smem* sm = reinterpret_cast<Smem*>(tiles + Cfg::NSTAGES * Cfg::STAGE);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const int tiles_n = g.N / BN;
-    const int64_t tiles_m = (g.M + BM - 1) / BM;
+    const int tiles_n = g.N / BN_;
+    const int64_t tiles_m = (g.M + ROWS - 1) / ROWS;
     const int64_t n_tiles = tiles_m * tiles_n;
     const int kblocks = g.K / BK;
 
     if (warp == 0 && tc::elect_one()) {
         tc::prefetch_tmap(&tm_a_hi); tc::prefetch_tmap(&tm_a_lo);
         tc::prefetch_tmap(&tm_b_hi); tc::prefetch_tmap(&tm_b_lo);
-        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&sm->full[s], 1); tc::mbar_init(&sm->empty[s], 1); }
+        for (int s = 0; s < Cfg::NSTAGES; ++s) { tc::mbar_init(&sm->full[s], 1); tc::mbar_init(&sm->empty[s], 1); }
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&sm->tmem_full[a], 1); tc::mbar_init(&sm->tmem_empty[a], 4); }
         tc::fence_barrier_init();
     }
     if (warp == 1) {
-        tc::tmem_alloc(&sm->tmem_base, TMEM_COLS);
+        tc::tmem_alloc(&sm->tmem_base, Cfg::TMEM);
         tc::tmem_relinquish();
     }
     tc::tc_fence_before();
@@ -95,23 +116,30 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         if (tc::elect_one()) {
             int s = 0; uint32_t ph = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int m0 = (int)(t / tiles_n) * BM, n0 = (int)(t % tiles_n) * BN;
+                const int64_t tile_m = t / tiles_n;
+                const int n0 = (int)(t % tiles_n) * BN_;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     tc::mbar_wait(&sm->empty[s], ph ^ 1);
-                    uint8_t* st = tiles + s * STAGE_BYTES;
-                    tc::mbar_expect_tx(&sm->full[s], STAGE_BYTES);
-                    tc::tma_load_2d(st + 0 * TILE_BYTES, &tm_a_hi, &sm->full[s], kb * BK, m0);
-                    tc::tma_load_2d(st + 1 * TILE_BYTES, &tm_a_lo, &sm->full[s], kb * BK, m0);
+                    uint8_t* st = tiles + s * Cfg::STAGE;
+                    tc::mbar_expect_tx(&sm->full[s], 2 * A_BYTES + 2 * Cfg::B_TILE);
+                    if (CONV) {
+                        const int c0 = (kb & 1) * 32, p0 = (kb >> 1) - 1, w0 = (int)tile_m * CONV_WIN;
+                        tc::tma_load_3d(st, &tm_a_hi, &sm->full[s], c0, p0, w0);
+                        tc::tma_load_3d(st + TILE_BYTES, &tm_a_lo, &sm->full[s], c0, p0, w0);
+                    } else {
+                        tc::tma_load_2d(st, &tm_a_hi, &sm->full[s], kb * BK, (int)tile_m * BM);
+                        tc::tma_load_2d(st + TILE_BYTES, &tm_a_lo, &sm->full[s], kb * BK, (int)tile_m * BM);
+                    }
                     tc::tma_load_2d(st + 2 * TILE_BYTES, &tm_b_hi, &sm->full[s], kb * BK, n0);
-                    tc::tma_load_2d(st + 3 * TILE_BYTES, &tm_b_lo, &sm->full[s], kb * BK, n0);
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                    tc::tma_load_2d(st + 2 * TILE_BYTES + Cfg::B_TILE, &tm_b_lo, &sm->full[s], kb * BK, n0);
+                    if (++s == Cfg::NSTAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::idesc_tf32(BM, BN, 0, 0);
+            constexpr uint32_t idesc = tc::idesc_tf32(BM, BN_, 0, 0);
             int s = 0; uint32_t ph = 0;
             int it = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
@@ -120,25 +148,25 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 tc::tc_fence_after();
                 // two accumulators per tile: the hi.hi chain and the (small) correction chain are kept
                 // apart so that the accumulator's round-toward-zero steps on the big chain are 1/3 as many
-                const uint32_t d = tmem_base + acc * ACC_COLS;
-                const uint32_t dc = d + BN;
+                const uint32_t d = tmem_base + acc * Cfg::ACC;
+                const uint32_t dc = d + BN_;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     tc::mbar_wait(&sm->full[s], ph);
                     tc::tc_fence_after();
-                    const uint32_t base = tc::smem_u32(tiles + s * STAGE_BYTES);
+                    const uint32_t base = tc::smem_u32(tiles + s * Cfg::STAGE);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint32_t ko = k * UMMA_K * 4;                       // bytes along K inside the swizzle row
-                        const uint64_t a_hi = tc::smem_desc_sw128(base + 0 * TILE_BYTES + ko, 16, 1024);
-                        const uint64_t a_lo = tc::smem_desc_sw128(base + 1 * TILE_BYTES + ko, 16, 1024);
+                        const uint64_t a_hi = tc::smem_desc_sw128(base + ko, 16, 1024);
+                        const uint64_t a_lo = tc::smem_desc_sw128(base + TILE_BYTES + ko, 16, 1024);
                         const uint64_t b_hi = tc::smem_desc_sw128(base + 2 * TILE_BYTES + ko, 16, 1024);
-                        const uint64_t b_lo = tc::smem_desc_sw128(base + 3 * TILE_BYTES + ko, 16, 1024);
+                        const uint64_t b_lo = tc::smem_desc_sw128(base + 2 * TILE_BYTES + Cfg::B_TILE + ko, 16, 1024);
                         tc::mma_tf32(dc, a_lo, b_hi, idesc, (kb | k) != 0);
                         tc::mma_tf32(dc, a_hi, b_lo, idesc, 1);
                         tc::mma_tf32(d, a_hi, b_hi, idesc, (kb | k) != 0);
                     }
                     tc::mma_commit(&sm->empty[s]);                                // frees the stage when the MMAs retire
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                    if (++s == Cfg::NSTAGES) { s = 0; ph ^= 1; }
                 }
                 tc::mma_commit(&sm->tmem_full[acc]);
             }
@@ -151,17 +179,18 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             const int64_t tile_m = t / tiles_n;
-            const int n0 = (int)(t % tiles_n) * BN;
-            const int64_t row = tile_m * BM + q * 32 + lane;
-            const bool row_ok = row < g.M;
+            const int n0 = (int)(t % tiles_n) * BN_;
+            const int rl = q * 32 + lane;
+            const int64_t row = tile_m * ROWS + rl;
+            const bool row_ok = rl < ROWS && row < g.M;
             tc::mbar_wait(&sm->tmem_full[acc], (it >> 1) & 1);
             tc::tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < BN_ / 32; ++c) {
                 float v[32], vc[32];
-                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + c * 32;
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC + c * 32;
                 tc::tmem_ld32(ta, v);
-                tc::tmem_ld32(ta + BN, vc);
+                tc::tmem_ld32(ta + BN_, vc);
                 tc::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] += vc[j];
@@ -201,17 +230,19 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             if (lane == 0) tc::mbar_arrive(&sm->tmem_empty[acc]);
             if (g.psum) {
                 tc::named_bar_sync(1, EPI_THREADS);
-                const float s = sm->csum[0][et] + sm->csum[1][et] + sm->csum[2][et] + sm->csum[3][et];
-                const float qq = sm->csq[0][et] + sm->csq[1][et] + sm->csq[2][et] + sm->csq[3][et];
-                g.psum[tile_m * g.N + n0 + et] = s;
-                g.psq[tile_m * g.N + n0 + et] = qq;
+                if (et < BN_) {
+                    const float s = sm->csum[0][et] + sm->csum[1][et] + sm->csum[2][et] + sm->csum[3][et];
+                    const float qq = sm->csq[0][et] + sm->csq[1][et] + sm->csq[2][et] + sm->csq[3][et];
+                    g.psum[tile_m * g.N + n0 + et] = s;
+                    g.psq[tile_m * g.N + n0 + et] = qq;
+                }
                 tc::named_bar_sync(1, EPI_THREADS);
             }
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM);
 }
 
 // ---------------------------------------------------------------------------- weight gradient
@@ -344,6 +375,147 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_cons
     if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------- conv2 weight gradient
+// P[z][tap*64 + c][o] = sum over the windows of slab z, positions p, of X[w, p+tap-1, c] * G[(w,p), o]
+// (the transposed weight gradient of the k = 3 convolution).  M side = conv-view of X (192 columns,
+// padded to two 128-row MMA tiles: tile 0 = taps 0,1, tile 1 = tap 2 + 64 unused rows), N side = the
+// 64 output channels of G.  A k-block is 4 windows = 48 rows: per plane the M side is up to four
+// [48 rows][32 ch] boxes of the 3-D conv map shifted by tap-1 (zero padded by TMA), the N side two
+// [48][32] boxes of G.  Same MN-major 32B-atom swizzle / register-side chain cutting as gemm_tc_tn.
+constexpr int CW_WIN = 4, CW_ROWS = 48;                   // windows / rows per k-block
+constexpr int CW_BLOCK = CW_ROWS * 128;                   // bytes of one [48][32 floats] block
+constexpr int CW_STAGE = (4 + 2) * 2 * CW_BLOCK;          // (X: 4 blocks, G: 2 blocks) x (hi, lo)
+constexpr int CW_STAGES = 3;
+constexpr int CW_CHUNK_KB = 11;                           // 528 rows per accumulation chain
+constexpr int CW_SMEM = CW_STAGES * CW_STAGE + 1024 + (int)sizeof(Smem);
+
+struct CwArgs {
+    float* P;                    // [splits][256][64]
+    int64_t windows;
+    int64_t win_per_split;       // multiple of CW_WIN
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_tn_conv_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+                       const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant__ CUtensorMap tm_g_lo,
+                       const CwArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    Smem* sm = reinterpret_cast<Smem*>(tiles + CW_STAGES * CW_STAGE);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int mt = blockIdx.x;                               // 0: taps 0,1   1: tap 2
+    const int n_blocks = mt == 0 ? 4 : 2;                    // 32-channel blocks that carry data
+    const int64_t w_begin = (int64_t)blockIdx.y * g.win_per_split;
+    const int64_t w_end = min(g.windows, w_begin + g.win_per_split);
+    const int kblocks = (int)((w_end - w_begin + CW_WIN - 1) / CW_WIN);
+    const int chunks = (kblocks + CW_CHUNK_KB - 1) / CW_CHUNK_KB;
+
+    if (warp == 0 && tc::elect_one()) {
+        tc::prefetch_tmap(&tm_x_hi); tc::prefetch_tmap(&tm_x_lo);
+        tc::prefetch_tmap(&tm_g_hi); tc::prefetch_tmap(&tm_g_lo);
+        for (int s = 0; s < CW_STAGES; ++s) { tc::mbar_init(&sm->full[s], 1); tc::mbar_init(&sm->empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&sm->tmem_full[a], 1); tc::mbar_init(&sm->tmem_empty[a], 4); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(&sm->tmem_base, 256);                 // 2 buffers x (main + correction) x 64 columns
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = sm->tmem_base;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            int s = 0; uint32_t ph = 0;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                tc::mbar_wait(&sm->empty[s], ph ^ 1);
+                uint8_t* st = tiles + s * CW_STAGE;
+                const int w0 = (int)(w_begin + (int64_t)kb * CW_WIN);
+                tc::mbar_expect_tx(&sm->full[s], (uint32_t)(2 * n_blocks + 4) * CW_BLOCK);
+                for (int b = 0; b < n_blocks; ++b) {
+                    const int tap = mt * 2 + b / 2, c0 = (b & 1) * 32;
+                    tc::tma_load_3d(st + b * CW_BLOCK, &tm_x_hi, &sm->full[s], c0, tap - 1, w0);
+                    tc::tma_load_3d(st + (4 + b) * CW_BLOCK, &tm_x_lo, &sm->full[s], c0, tap - 1, w0);
+                }
+                // G: [rows][64] as (32 ch, row, 2 halves) -> two [48][32] blocks per plane
+                tc::tma_load_3d(st + 8 * CW_BLOCK, &tm_g_hi, &sm->full[s], 0, w0 * 12, 0);
+                tc::tma_load_3d(st + 10 * CW_BLOCK, &tm_g_lo, &sm->full[s], 0, w0 * 12, 0);
+                if (++s == CW_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::idesc_tf32(BM, 64, 1, 1);
+            int s = 0; uint32_t ph = 0;
+            int kb = 0;
+            for (int ch = 0; ch < chunks; ++ch) {
+                const int acc = ch & 1;
+                tc::mbar_wait(&sm->tmem_empty[acc], ((ch >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d = tmem_base + acc * 128;
+                const uint32_t dc = d + 64;
+                const int kb_end = min(kblocks, kb + CW_CHUNK_KB);
+                for (bool first = true; kb < kb_end; ++kb) {
+                    tc::mbar_wait(&sm->full[s], ph);
+                    tc::tc_fence_after();
+                    const uint32_t base = tc::smem_u32(tiles + s * CW_STAGE);
+#pragma unroll
+                    for (int k = 0; k < CW_ROWS / UMMA_K; ++k) {
+                        const uint32_t ko = k * 1024;
+                        const uint64_t x_hi = tc::smem_desc(base + 0 * CW_BLOCK + ko, CW_BLOCK, 512, 1);
+                        const uint64_t x_lo = tc::smem_desc(base + 4 * CW_BLOCK + ko, CW_BLOCK, 512, 1);
+                        const uint64_t g_hi = tc::smem_desc(base + 8 * CW_BLOCK + ko, CW_BLOCK, 512, 1);
+                        const uint64_t g_lo = tc::smem_desc(base + 10 * CW_BLOCK + ko, CW_BLOCK, 512, 1);
+                        const uint32_t accum = (first && k == 0) ? 0u : 1u;
+                        tc::mma_tf32(dc, x_lo, g_hi, idesc, accum);
+                        tc::mma_tf32(dc, x_hi, g_lo, idesc, 1);
+                        tc::mma_tf32(d, x_hi, g_hi, idesc, accum);
+                    }
+                    first = false;
+                    tc::mma_commit(&sm->empty[s]);
+                    if (++s == CW_STAGES) { s = 0; ph ^= 1; }
+                }
+                tc::mma_commit(&sm->tmem_full[acc]);
+            }
+        }
+    } else {
+        const int q = warp % 4;
+        float sum[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) sum[j] = 0.f;
+        for (int ch = 0; ch < chunks; ++ch) {
+            const int acc = ch & 1;
+            tc::mbar_wait(&sm->tmem_full[acc], (ch >> 1) & 1);
+            tc::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float v[32], vc[32];
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + c * 32;
+                tc::tmem_ld32(ta, v);
+                tc::tmem_ld32(ta + 64, vc);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[c * 32 + j] += v[j] + vc[j];
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&sm->tmem_empty[acc]);
+        }
+        const int m = mt * 128 + q * 32 + lane;
+        if (m < 192) {
+            float* dst = g.P + ((int64_t)blockIdx.y * 256 + m) * 64;
+#pragma unroll
+            for (int j = 0; j < 64; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, 256);
+}
+
 // ---------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -423,6 +595,36 @@ inline int launch_tn(const float* G_hi, const float* G_lo, int ldg, int Mo, cons
     return CP_OK;
 }
 
+// [windows][12][64] fp32 activation as (32-channel half, position, window) boxes {32, 12, 10}
+inline int make_tmap_conv(CUtensorMap* m, const float* base, int64_t windows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return CP_ERR_UNSUPPORTED;
+    cuuint64_t dims[3] = {64, 12, (cuuint64_t)windows};
+    cuuint64_t strides[2] = {64 * 4, 12 * 64 * 4};
+    cuuint32_t box[3] = {32, 12, CONV_WIN};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? CP_OK : CP_ERR_ARG;
+}
+
+template <int BN_, bool CONV>
+inline int launch_nt_cfg(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
+                         const CUtensorMap& tb_lo, const NtArgs& g, int64_t tiles_m, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_kernel<BN_, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     NtCfg<BN_>::SMEM));
+        attr_set = true;
+    }
+    const int64_t n_tiles = tiles_m * (g.N / BN_);
+    const int grid = (int)(n_tiles < CP_NUM_SMS ? n_tiles : CP_NUM_SMS);
+    gemm_tc_nt_kernel<BN_, CONV><<<grid, THREADS, NtCfg<BN_>::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
 inline int launch_nt(const float* A_hi, const float* A_lo, int64_t M, int K, int lda, const float* B_hi,
                      const float* B_lo, int N, int ldb, const float* bias, float* C, int ldc, float* psum,
                      float* psq, int relu, cudaStream_t st) {
@@ -433,16 +635,67 @@ inline int launch_nt(const float* A_hi, const float* A_lo, int64_t M, int K, int
     if ((rc = make_tmap_2d(&ta_lo, A_lo, M, K, lda, BM)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi, B_hi, N, K, ldb, BN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, N, K, ldb, BN)) != CP_OK) return rc;
+    NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu};
+    return launch_nt_cfg<128, false>(ta_hi, ta_lo, tb_hi, tb_lo, g, cp_cdiv(M, BM), st);
+}
+
+// conv2 as implicit GEMM: C[(w,p), o] = act(sum_{tap,c} X[w, p+tap-1, c] * B[o, tap*64+c] + bias[o]);
+// X planes are [windows][12][64], B planes [64][192]; partial statistics rows = ceil(windows/10)
+inline int launch_conv_nt(const float* X_hi, const float* X_lo, int64_t windows, const float* B_hi,
+                          const float* B_lo, const float* bias, float* C, float* psum, float* psq, int relu,
+                          cudaStream_t st) {
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    int rc;
+    if ((rc = make_tmap_conv(&ta_hi, X_hi, windows)) != CP_OK) return rc;
+    if ((rc = make_tmap_conv(&ta_lo, X_lo, windows)) != CP_OK) return rc;
+    if ((rc = make_tmap_2d(&tb_hi, B_hi, 64, 192, 192, 64)) != CP_OK) return rc;
+    if ((rc = make_tmap_2d(&tb_lo, B_lo, 64, 192, 192, 64)) != CP_OK) return rc;
+    NtArgs g{C, 64, bias, psum, psq, windows * 12, 64, 192, relu};
+    return launch_nt_cfg<64, true>(ta_hi, ta_lo, tb_hi, tb_lo, g, cp_cdiv(windows, CONV_WIN), st);
+}
+
+// conv2 weight gradient; P capacity >= splits*256*64 floats; *splits_out = number of slabs written
+inline int launch_conv_tn(const float* X_hi, const float* X_lo, const float* G_hi, const float* G_lo,
+                          int64_t windows, float* P, size_t p_capacity_elems, int* splits_out, cudaStream_t st) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return CP_ERR_UNSUPPORTED;
+    CUtensorMap tx_hi, tx_lo, tg_hi, tg_lo;
+    auto mk_x = [&](CUtensorMap* m, const float* base) {
+        cuuint64_t dims[3] = {64, 12, (cuuint64_t)windows};
+        cuuint64_t strides[2] = {64 * 4, 12 * 64 * 4};
+        cuuint32_t box[3] = {32, 12, CW_WIN};
+        cuuint32_t estr[3] = {1, 1, 1};
+        return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    auto mk_g = [&](CUtensorMap* m, const float* base) {
+        cuuint64_t dims[3] = {32, (cuuint64_t)(windows * 12), 2};
+        cuuint64_t strides[2] = {64 * 4, 128};
+        cuuint32_t box[3] = {32, CW_ROWS, 2};
+        cuuint32_t estr[3] = {1, 1, 1};
+        return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    if (!mk_x(&tx_hi, X_hi) || !mk_x(&tx_lo, X_lo) || !mk_g(&tg_hi, G_hi) || !mk_g(&tg_lo, G_lo)) return CP_ERR_ARG;
     static bool attr_set = false;
     if (!attr_set) {
-        CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_tn_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM));
         attr_set = true;
     }
-    NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu};
-    const int64_t n_tiles = cp_cdiv(M, BM) * (N / BN);
-    const int grid = (int)(n_tiles < CP_NUM_SMS ? n_tiles : CP_NUM_SMS);
-    gemm_tc_nt_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g);
+    int S = CP_NUM_SMS / 2;
+    const int64_t max_s = cp_cdiv(windows, (int64_t)CW_WIN * CW_CHUNK_KB);
+    if (S > max_s) S = (int)max_s;
+    const int64_t cap = (int64_t)(p_capacity_elems / (256 * 64));
+    if (S > cap) S = (int)cap;
+    if (S < 1) S = 1;
+    const int64_t wps = cp_cdiv(cp_cdiv(windows, S), CW_WIN) * CW_WIN;
+    S = (int)cp_cdiv(windows, wps);
+    CwArgs g{P, windows, wps};
+    gemm_tc_tn_conv_kernel<<<dim3(2, S), THREADS, CW_SMEM, st>>>(tx_hi, tx_lo, tg_hi, tg_lo, g);
     CP_CHECK_LAUNCH();
+    *splits_out = S;
     return CP_OK;
 }
 
