@@ -43,6 +43,7 @@ struct Ws {
     float *ppart;              // projection / conv1 weight-gradient partials
     // tensor-core engine: low planes (the high plane reuses the fp32 slot) and split weights
     float *A1_lo, *A2_lo, *A_lo[CP_N_FC], *G1_lo, *Wc2_lo, *Wc2d_lo;
+    float *G1b, *G1b_lo;      // second pre-activation-gradient buffer (weight-gradient GEMMs run on a side stream)
     float *Wh[CP_N_FC], *Wl[CP_N_FC], *Wth[CP_N_FC], *Wtl[CP_N_FC];
     size_t bytes;
 };
@@ -100,7 +101,7 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     w.ppart = save ? c.take<float>((size_t)cp_cdiv(n, PROJ_W_ROWS) * CP_EMB_DIM * 512 +
                                    (size_t)cp_cdiv(n * 12, 1024) * 3 * 64)
                    : nullptr;
-    w.A1_lo = w.A2_lo = w.G1_lo = w.Wc2_lo = w.Wc2d_lo = nullptr;
+    w.A1_lo = w.A2_lo = w.G1_lo = w.Wc2_lo = w.Wc2d_lo = w.G1b = w.G1b_lo = nullptr;
     for (int l = 0; l < CP_N_FC; ++l) w.A_lo[l] = w.Wh[l] = w.Wl[l] = w.Wth[l] = w.Wtl[l] = nullptr;
     if (o->engine == CP_ENGINE_TC) {
         w.Wc2_lo = c.take<float>(64 * 192);
@@ -110,6 +111,8 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
             w.A2_lo = c.take<float>(conv_elems);
             for (int l = 0; l + 1 < CP_N_FC; ++l) w.A_lo[l] = c.take<float>(fc_elems);
             w.G1_lo = c.take<float>(conv_elems);
+            w.G1b = c.take<float>(conv_elems);
+            w.G1b_lo = c.take<float>(conv_elems);
         } else {
             float* l0 = c.take<float>(conv_elems);
             float* l1 = c.take<float>(conv_elems);
@@ -219,6 +222,28 @@ int bn_backward(const float* g, const float* y, float* gz, float* gz_lo, int64_t
         int rc__ = (expr);           \
         if (rc__ != CP_OK) return rc__; \
     } while (0)
+
+// Side stream for the weight-gradient GEMMs of the tensor-core engine: they are off the critical
+// path (dgrad -> BN backward -> dgrad ...) and, being tensor-pipe bound, overlap with the HBM-bound
+// BN-backward kernels of the next layer.  Fork/join is by events, so the caller's stream semantics
+// (and CUDA-graph capture) are preserved.  Created once per process.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr};     // main -> side: G1 buffer b has been written
+    cudaEvent_t done[2] = {nullptr, nullptr};      // side -> main: G1 buffer b has been consumed
+    bool ok = false;
+    int init() {
+        if (ok) return CP_OK;
+        CP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CP_CUDA(cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming));
+            CP_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        }
+        ok = true;
+        return CP_OK;
+    }
+};
+SideStream g_side;
 
 bool opts_ok(const cp_encoder_opts* o) {
     return o && o->bn_mode >= 0 && o->bn_mode <= 2 && o->dropout_p >= 0.f && o->dropout_p < 1.f &&
@@ -342,52 +367,86 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     CP_CHECK_LAUNCH();
 
     // linear blocks, last to first.  G0 = grad w.r.t. block output, G1 = grad w.r.t. pre-activation
-    for (int l = CP_N_FC - 1; l >= 0; --l) {
-        const uint8_t* keep = (l >= 3 && o->dropout_p > 0.f) ? w.keep[l - 3] : nullptr;
-        CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], w.G1, w.G1_lo, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
-                                 gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st));
-        if (tcE) {
+    float* g1_conv1 = w.G1;
+    cudaEvent_t join_event = nullptr;
+    if (tcE) {
+        CP_TRY(g_side.init());
+        cudaStream_t ss = g_side.stream;
+        int nb = 0;                                    // stages processed so far -> G1 buffer parity
+        bool used[2] = {false, false};
+        auto g1 = [&](int b) { return b ? w.G1b : w.G1; };
+        auto g1lo = [&](int b) { return b ? w.G1b_lo : w.G1_lo; };
+        for (int l = CP_N_FC - 1; l >= 0; --l, ++nb) {
+            const int b = nb & 1;
+            const uint8_t* keep = (l >= 3 && o->dropout_p > 0.f) ? w.keep[l - 3] : nullptr;
+            if (used[b]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b], 0));     // WAR on the G1 buffer
+            CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], g1(b), g1lo(b), n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
+                                     gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st));
+            CP_CUDA(cudaEventRecord(g_side.ready[b], st));
             const int K = l == 0 ? K_FC1 : F_FC;
             const float* ah = l == 0 ? w.A2 : w.A[l - 1];
             const float* al = l == 0 ? w.A2_lo : w.A_lo[l - 1];
-            CP_TRY(tc_wgrad(w.G1, w.G1_lo, F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, st));
-            CP_TRY(tcg::launch_nt(w.G1, w.G1_lo, n, F_FC, F_FC, w.Wth[l], w.Wtl[l], K, F_FC, nullptr, w.G0, K, nullptr,
+            // side stream: dW_l = G1^T . A_{l-1}
+            CP_CUDA(cudaStreamWaitEvent(ss, g_side.ready[b], 0));
+            CP_TRY(tc_wgrad(g1(b), g1lo(b), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, ss));
+            CP_CUDA(cudaEventRecord(g_side.done[b], ss));
+            used[b] = true;
+            // main stream: G0 = G1 . W_l
+            CP_TRY(tcg::launch_nt(g1(b), g1lo(b), n, F_FC, F_FC, w.Wth[l], w.Wtl[l], K, F_FC, nullptr, w.G0, K, nullptr,
                                   nullptr, 0, st));
-        } else if (l > 0) {
-            CP_TRY((launch_wgrad<128, 128, false>(w.G1, F_FC, F_FC, w.A[l - 1], F_FC, F_FC, n, w.wpart, gr->fc_w[l], 0, st)));
-            CP_TRY((launch_nt<128, 128, 1, false>(w.G1, n, F_FC, F_FC, p->fc_w[l], F_FC, F_FC, nullptr, w.G0, F_FC,
-                                                  nullptr, nullptr, 0, st)));
-        } else {
-            CP_TRY((launch_wgrad<128, 128, false>(w.G1, F_FC, F_FC, w.A2, K_FC1, K_FC1, n, w.wpart, gr->fc_w[0], 1, st)));
-            CP_TRY((launch_nt<128, 128, 1, false>(w.G1, n, F_FC, F_FC, w.W1p, K_FC1, K_FC1, nullptr, w.G0, K_FC1,
-                                                  nullptr, nullptr, 0, st)));
         }
-    }
-    // conv2 block: G0 is [n*12, 64] (same memory order as the [n,768] position-major flatten)
-    // tensor-core engine: G1 and A1 are (hi, lo) planes; the FFMA weight-gradient kernel adds them back
-    CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, w.G1, w.G1_lo, R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1],
-                               gr->bn_b[1], gr->conv2_b, st));
-    CP_CUDA(cudaMemsetAsync(gr->conv2_w, 0, sizeof(float) * 64 * 64 * 9, st));
-    if (tcE) {
+        // conv2 block: G0 is [n*12, 64] (same memory order as the [n,768] position-major flatten)
+        const int b = nb & 1;
+        if (used[b]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b], 0));
+        CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, g1(b), g1lo(b), R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1],
+                                   gr->bn_b[1], gr->conv2_b, st));
+        CP_CUDA(cudaEventRecord(g_side.ready[b], st));
+        CP_CUDA(cudaStreamWaitEvent(ss, g_side.ready[b], 0));
+        CP_CUDA(cudaMemsetAsync(gr->conv2_w, 0, sizeof(float) * 64 * 64 * 9, ss));
         int S = 0;
-        CP_TRY(tcg::launch_conv_tn(w.A1, w.A1_lo, w.G1, w.G1_lo, n, w.wpart, WPART_ELEMS, &S, st));
-        wgrad_reduce_kernel<<<(192 * 64 + 255) / 256, 256, 0, st>>>(w.wpart, S, 192, 64, gr->conv2_w, 3);
+        CP_TRY(tcg::launch_conv_tn(w.A1, w.A1_lo, g1(b), g1lo(b), n, w.wpart, WPART_ELEMS, &S, ss));
+        wgrad_reduce_kernel<<<(192 * 64 + 255) / 256, 256, 0, ss>>>(w.wpart, S, 192, 64, gr->conv2_w, 3);
         CP_CHECK_LAUNCH();
-        CP_TRY(tcg::launch_conv_nt(w.G1, w.G1_lo, n, w.Wc2d, w.Wc2d_lo, nullptr, w.G0, nullptr, nullptr, 0, st));
+        CP_CUDA(cudaEventRecord(g_side.done[b], ss));
+        CP_TRY(tcg::launch_conv_nt(g1(b), g1lo(b), n, w.Wc2d, w.Wc2d_lo, nullptr, w.G0, nullptr, nullptr, 0, st));
+        // conv1's pre-activation gradient goes to the other buffer (its last reader is two stages back)
+        if (used[b ^ 1]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b ^ 1], 0));
+        g1_conv1 = g1(b ^ 1);
+        join_event = g_side.done[b];
     } else {
+        for (int l = CP_N_FC - 1; l >= 0; --l) {
+            const uint8_t* keep = (l >= 3 && o->dropout_p > 0.f) ? w.keep[l - 3] : nullptr;
+            CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], w.G1, nullptr, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
+                                     gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st));
+            if (l > 0) {
+                CP_TRY((launch_wgrad<128, 128, false>(w.G1, F_FC, F_FC, w.A[l - 1], F_FC, F_FC, n, w.wpart, gr->fc_w[l], 0, st)));
+                CP_TRY((launch_nt<128, 128, 1, false>(w.G1, n, F_FC, F_FC, p->fc_w[l], F_FC, F_FC, nullptr, w.G0, F_FC,
+                                                      nullptr, nullptr, 0, st)));
+            } else {
+                CP_TRY((launch_wgrad<128, 128, false>(w.G1, F_FC, F_FC, w.A2, K_FC1, K_FC1, n, w.wpart, gr->fc_w[0], 1, st)));
+                CP_TRY((launch_nt<128, 128, 1, false>(w.G1, n, F_FC, F_FC, w.W1p, K_FC1, K_FC1, nullptr, w.G0, K_FC1,
+                                                      nullptr, nullptr, 0, st)));
+            }
+        }
+        // conv2 block: G0 is [n*12, 64] (same memory order as the [n,768] position-major flatten)
+        CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, w.G1, nullptr, R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1],
+                                   gr->bn_b[1], gr->conv2_b, st));
+        CP_CUDA(cudaMemsetAsync(gr->conv2_w, 0, sizeof(float) * 64 * 64 * 9, st));
         CP_TRY((launch_wgrad<64, 64, true>(w.G1, 64, 64, w.A1, 64, 192, R12, w.wpart, gr->conv2_w, 2, st)));
         CP_TRY((launch_nt<128, 64, 0, true>(w.G1, R12, 192, 64, w.Wc2d, 64, 192, nullptr, w.G0, 64, nullptr, nullptr, 0, st)));
     }
     // conv1 block
-    CP_TRY(bn_backward<F_CONV>(w.G0, w.Y1, w.G1, nullptr, R12, w, 0, nullptr, 1.f, p->bn_w[0], gr->bn_w[0], gr->bn_b[0],
-                               gr->conv1_b, st));
+    CP_TRY(bn_backward<F_CONV>(w.G0, w.Y1, g1_conv1, nullptr, R12, w, 0, nullptr, 1.f, p->bn_w[0], gr->bn_w[0],
+                               gr->bn_b[0], gr->conv1_b, st));
     const int P1 = (int)cp_cdiv(R12, ColMap<F_CONV>::ROWS);
     float* c1part = w.ppart + (size_t)Pp * CP_EMB_DIM * 512;
-    conv1_bwd_kernel<<<P1, 256, 0, st>>>(w.G1, w.X0, R12, c1part);
+    conv1_bwd_kernel<<<P1, 256, 0, st>>>(g1_conv1, w.X0, R12, c1part);
     CP_CHECK_LAUNCH();
     CP_CUDA(cudaMemsetAsync(gr->conv1_w, 0, sizeof(float) * 64 * 9, st));
     colsum_finalize_kernel<<<3 * 64 / 32, 1024, 0, st>>>(c1part, P1, 3 * 64, gr->conv1_w, 1);
     CP_CHECK_LAUNCH();
+    // join: every weight gradient is complete before the caller's stream continues
+    if (join_event) CP_CUDA(cudaStreamWaitEvent(st, join_event, 0));
     return CP_OK;
 }
 
