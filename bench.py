@@ -262,14 +262,23 @@ def run_cuda(args):
         Wt = torch.randn(Nn, K, device=dev)
         bias = torch.randn(Nn, device=dev)
         Y = torch.empty(M, Nn, device=dev)
-        cs_, cq_ = torch.empty(Nn, device=dev), torch.empty(Nn, device=dev)
         nb = L.cp_linear_workspace_bytes(M, Nn, K)
         ws = torch.empty(nb, dtype=torch.uint8, device=dev)
         P = _lib.ptr
 
+        use_tc = model.emg_net.engine == _lib.ENGINE_TC
+        if use_tc:      # operands pre-split, as they are inside the encoder (the producing kernels write planes)
+            Ah, Al, Wh, Wl = (torch.empty_like(A), torch.empty_like(A), torch.empty_like(Wt), torch.empty_like(Wt))
+            _lib.check(L.cp_split_tf32(P(A), P(Ah), P(Al), A.numel(), _lib.stream()))
+            _lib.check(L.cp_split_tf32(P(Wt), P(Wh), P(Wl), Wt.numel(), _lib.stream()))
+
         def gemm():
-            _lib.check(L.cp_linear_forward(P(A), P(Wt), P(bias), P(Y), M, Nn, K, 1, P(cs_), P(cq_), P(ws), nb,
-                                           model.emg_net.engine, _lib.stream()))
+            if use_tc:
+                _lib.check(L.cp_linear_forward_planes(P(Ah), P(Al), P(Wh), P(Wl), P(bias), P(Y), M, Nn, K, 1, None, None,
+                                                      P(ws), nb, _lib.stream()))
+            else:
+                _lib.check(L.cp_linear_forward(P(A), P(Wt), P(bias), P(Y), M, Nn, K, 1, None, None, P(ws), nb,
+                                               _lib.ENGINE_SIMT, _lib.stream()))
         for _ in range(3):
             gemm()
         torch.cuda.synchronize()

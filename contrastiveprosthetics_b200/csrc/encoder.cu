@@ -38,6 +38,8 @@ struct Ws {
     float *mean[CP_N_BN], *istd[CP_N_BN], *scale[CP_N_BN], *shift[CP_N_BN];
     float *pa, *pb;            // per-CTA column partials
     float *m1, *m2;
+    double* rscratch;          // [RP_SLABS][2][512] slab sums of the two-level partial reductions
+    unsigned int* tickets;     // [16] last-CTA tickets (zero-initialised once per workspace)
     float *wpart;              // split-K weight-gradient partials
     float *Wc2, *Wc2d, *W1p;
     float *ppart;              // projection / conv1 weight-gradient partials
@@ -94,6 +96,8 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     w.pb = c.take<float>(pr * F_FC);
     w.m1 = c.take<float>(F_FC);
     w.m2 = c.take<float>(F_FC);
+    w.rscratch = c.take<double>((size_t)RP_SLABS * 2 * F_FC);
+    w.tickets = c.take<unsigned int>(64);
     w.wpart = save ? c.take<float>(WPART_ELEMS) : nullptr;
     w.Wc2 = c.take<float>(64 * 192);
     w.Wc2d = c.take<float>(64 * 192);
@@ -175,21 +179,23 @@ int launch_wgrad(const float* G, int ldg, int Mo, const float* A, int lda, int N
 int bn_finalize(const Ws& w, int l, int F, int P, int64_t R, const cp_encoder_tensors* p,
                 const cp_encoder_opts* o, cudaStream_t st) {
     if (o->bn_mode != CP_BN_BATCH && (!p->bn_rm[l] || !p->bn_rv[l])) return CP_ERR_ARG;
-    bn_finalize_kernel<<<F / 32, 1024, 0, st>>>(w.pa, w.pb, P, F, R, p->bn_w[l], p->bn_b[l], p->bn_rm[l],
-                                                p->bn_rv[l], o->bn_mode, o->bn_momentum, o->bn_eps,
-                                                w.mean[l], w.istd[l], w.scale[l], w.shift[l]);
+    bn_finalize_kernel<<<dim3(F / 32, o->bn_mode == CP_BN_RUNNING ? 1 : RP_SLABS), 1024, 0, st>>>(
+        w.pa, w.pb, P, F, R, p->bn_w[l], p->bn_b[l], p->bn_rm[l], p->bn_rv[l], o->bn_mode, o->bn_momentum, o->bn_eps,
+        w.mean[l], w.istd[l], w.scale[l], w.shift[l], w.rscratch, w.tickets);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
 
 // a_lo != null: write (hi, lo) tf32 planes instead of the fp32 value
 template <int F>
-int bn_apply(const float* y, float* a, float* a_lo, int64_t R, const Ws& w, int l, const uint8_t* keep,
-             float inv_keep, cudaStream_t st) {
+int bn_apply(const float* y, float* a, float* a_lo, int64_t R, const Ws& w, int l, uint8_t* keep,
+             float inv_keep, cudaStream_t st, float gen_p = 0.f, uint64_t seed = 0, uint64_t layer = 0) {
     if (a_lo)
-        bn_apply_kernel<F, true><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, a_lo, R, w.scale[l], w.shift[l], keep, inv_keep);
+        bn_apply_kernel<F, true><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, a_lo, R, w.scale[l], w.shift[l], keep,
+                                                                     inv_keep, gen_p, seed, layer);
     else
-        bn_apply_kernel<F, false><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, nullptr, R, w.scale[l], w.shift[l], keep, inv_keep);
+        bn_apply_kernel<F, false><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, nullptr, R, w.scale[l], w.shift[l], keep,
+                                                                      inv_keep, gen_p, seed, layer);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
@@ -203,7 +209,8 @@ int bn_backward(const float* g, const float* y, float* gz, float* gz_lo, int64_t
     const int P = (int)cp_cdiv(R, ColMap<F>::ROWS);
     bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb);
     CP_CHECK_LAUNCH();
-    bn_bwd_finalize_kernel<<<F / 32, 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta);
+    bn_bwd_finalize_kernel<<<dim3(F / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta,
+                                                                    w.rscratch, w.tickets);
     CP_CHECK_LAUNCH();
     if (gz_lo)
         bn_bwd_apply_kernel<F, true><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], gamma, w.m1,
@@ -278,6 +285,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t R12 = n * 12;
 
+    CP_CUDA(cudaMemsetAsync(w.tickets, 0, 64 * sizeof(unsigned int), st));
     prep_weights_kernel<<<(F_FC * K_FC1 + 255) / 256, 256, 0, st>>>(p->conv2_w, p->fc_w[0], w.Wc2, w.Wc2d, w.W1p,
                                                                     w.Wc2_lo, w.Wc2d_lo);
     CP_CHECK_LAUNCH();
@@ -322,23 +330,22 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
             CP_TRY((launch_nt<128, 128, 0, false>(in, n, K, K, W, F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb, 1, st)));
         }
         CP_TRY(bn_finalize(w, 2 + l, F_FC, (int)cp_cdiv(n, 128), n, p, o, st));
-        const uint8_t* keep = nullptr;
+        uint8_t* keep = nullptr;
+        float gen_p = 0.f;
         if (l >= 3 && o->dropout_p > 0.f) {
             const int d = l - 3;
-            if (o->ext_masks) {
+            if (o->ext_masks)
                 CP_CUDA(cudaMemcpyAsync(w.keep[d], o->ext_masks + (size_t)d * n * F_FC, (size_t)n * F_FC,
                                         cudaMemcpyDeviceToDevice, st));
-            } else {
-                dropout_mask_kernel<<<ew_grid(n * (F_FC / 4)), 256, 0, st>>>(w.keep[d], n * (F_FC / 4), o->dropout_p,
-                                                                          o->dropout_seed, (uint64_t)d);
-                CP_CHECK_LAUNCH();
-            }
+            else
+                gen_p = o->dropout_p;              // mask drawn (and stored) inside the BN-apply kernel
             keep = w.keep[d];
         }
-        CP_TRY(bn_apply<F_FC>(w.Y[l], w.A[l], w.A_lo[l], n, w, 2 + l, keep, inv_keep, st));
+        CP_TRY(bn_apply<F_FC>(w.Y[l], w.A[l], w.A_lo[l], n, w, 2 + l, keep, inv_keep, st, gen_p, o->dropout_seed,
+                              (uint64_t)(l - 3)));
     }
     // projection 512 -> 16
-    proj_fwd_kernel<<<(unsigned)std::min<int64_t>(cp_cdiv(n, 8), (int64_t)CP_NUM_SMS * 4), 256, 0, st>>>(
+    proj_fwd_kernel<<<(unsigned)std::min<int64_t>(cp_cdiv(n, 8 * PROJ_RPW), (int64_t)CP_NUM_SMS * 4), 256, 0, st>>>(
         w.A[CP_N_FC - 1], p->proj_w, emb, n);
     CP_CHECK_LAUNCH();
     return CP_OK;
@@ -362,7 +369,7 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     CP_CHECK_LAUNCH();
     colsum_finalize_kernel<<<CP_EMB_DIM * 512 / 32, 1024, 0, st>>>(w.ppart, Pp, CP_EMB_DIM * 512, gr->proj_w, 0);
     CP_CHECK_LAUNCH();
-    proj_bwd_data_kernel<<<(unsigned)std::min<int64_t>(cp_cdiv(n, 2), (int64_t)CP_NUM_SMS * 8), 256, 0, st>>>(
+    proj_bwd_data_kernel<<<(unsigned)std::min<int64_t>(cp_cdiv(n, 8), (int64_t)CP_NUM_SMS * 8), 256, 0, st>>>(
         d_emb, p->proj_w, w.G0, n);
     CP_CHECK_LAUNCH();
 
@@ -539,6 +546,35 @@ extern "C" int cp_linear_forward(const float* A, const float* W, const float* bi
         colsum_finalize_kernel<<<(N + 31) / 32, 1024, 0, st>>>(pa, P, N, col_sum, 0);
         CP_CHECK_LAUNCH();
         colsum_finalize_kernel<<<(N + 31) / 32, 1024, 0, st>>>(pb, P, N, col_sqsum, 0);
+        CP_CHECK_LAUNCH();
+    }
+    return CP_OK;
+}
+
+// tf32 (hi, lo) planes of a fp32 array (n multiple of 4): the operand format of the tensor-core engine
+extern "C" int cp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+    if (!x || !hi || !lo || n < 0) return CP_ERR_ARG;
+    if (n == 0) return CP_OK;
+    return split_planes(x, hi, lo, (size_t)n, (cudaStream_t)stream);
+}
+
+// cp_linear_forward on operands that are already split: exactly the launch the encoder issues per
+// linear layer (TMA-fed tcgen05 main loop + bias/ReLU/statistics epilogue)
+extern "C" int cp_linear_forward_planes(const float* A_hi, const float* A_lo, const float* W_hi, const float* W_lo,
+                                        const float* bias, float* Y, int64_t M, int N, int K, int relu,
+                                        float* col_sum, float* col_sqsum, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
+    if (!A_hi || !A_lo || !W_hi || !W_lo || !Y || !workspace || M <= 0 || N <= 0 || K <= 0) return CP_ERR_ARG;
+    if ((col_sum == nullptr) != (col_sqsum == nullptr)) return CP_ERR_ARG;
+    const LinWs w = carve_linear(workspace, M, N, K);
+    if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    CP_TRY(tcg::launch_nt(A_hi, A_lo, M, K, K, W_hi, W_lo, N, K, bias, Y, N, w.pa, w.pb, relu, st));
+    if (col_sum) {
+        const int P = (int)cp_cdiv(M, 128);
+        colsum_finalize_kernel<<<(N + 31) / 32, 1024, 0, st>>>(w.pa, P, N, col_sum, 0);
+        CP_CHECK_LAUNCH();
+        colsum_finalize_kernel<<<(N + 31) / 32, 1024, 0, st>>>(w.pb, P, N, col_sqsum, 0);
         CP_CHECK_LAUNCH();
     }
     return CP_OK;

@@ -135,6 +135,54 @@ __device__ __forceinline__ double reduce_partials(const float* __restrict__ part
     return t;      // valid for lane == 0
 }
 
+// Two-level variant for long partial lists: grid = (ceil(width/32), RP_SLABS); every CTA reduces its slab
+// of partial rows into `scratch[slab][q][width]` (double), the last CTA of a column group to finish
+// (atomic ticket) adds the RP_SLABS slab sums in a fixed order -> deterministic.  Returns true in the
+// threads (lane == 0, col < width) of that last CTA, with the totals in out[0..NQ).
+#define RP_SLABS 16
+template <int NQ>
+__device__ __forceinline__ bool reduce_partials_2level(const float* const (&part)[NQ], int P, int width,
+                                                       double* __restrict__ scratch, unsigned int* __restrict__ tickets,
+                                                       double (&out)[NQ], double* sm /*[32*33]*/) {
+    __shared__ bool is_last;
+    const int cx = threadIdx.x % 32, lane = threadIdx.x / 32;
+    const int col = blockIdx.x * 32 + cx;
+    const int slab = blockIdx.y;
+    const int per = (P + RP_SLABS - 1) / RP_SLABS;
+    const int p0 = slab * per, p1 = min(P, p0 + per);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        double s = 0.0;
+        if (col < width)
+            for (int p = p0 + lane; p < p1; p += 32) s += (double)__ldg(part[q] + (int64_t)p * width + col);
+        sm[lane * 33 + cx] = s;
+        __syncthreads();
+        if (lane == 0) {
+            double t = 0.0;
+            for (int l = 0; l < 32; ++l) t += sm[l * 33 + cx];
+            if (col < width) scratch[((int64_t)slab * NQ + q) * width + col] = t;
+        }
+        __syncthreads();
+    }
+    __threadfence();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(tickets + blockIdx.x, 1u);
+        is_last = (t == RP_SLABS - 1);
+        if (is_last) tickets[blockIdx.x] = 0;          // re-arm for the next launch
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    if (lane != 0 || col >= width) return false;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        double t = 0.0;
+        for (int sl = 0; sl < RP_SLABS; ++sl) t += __ldcg(scratch + ((int64_t)sl * NQ + q) * width + col);
+        out[q] = t;
+    }
+    return true;
+}
+
 // BatchNorm statistics -> mean, inv-std, and the affine (scale, shift) the apply kernels use:
 // y_bn = x*scale + shift with scale = gamma*istd, shift = beta - mean*scale (same arrangement as
 // torch's CPU batch-norm transform).  mode: CP_BN_BATCH / _BATCH_UPDATE / _RUNNING.
@@ -143,18 +191,20 @@ bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq
                    int64_t R, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ run_mean, float* __restrict__ run_var, int mode, float momentum,
                    float eps, float* __restrict__ mean_o, float* __restrict__ istd_o,
-                   float* __restrict__ scale_o, float* __restrict__ shift_o) {
+                   float* __restrict__ scale_o, float* __restrict__ shift_o, double* __restrict__ scratch,
+                   unsigned int* __restrict__ tickets) {
     __shared__ double sm[32 * 33];
     const int col = blockIdx.x * 32 + threadIdx.x % 32, lane = threadIdx.x / 32;
     double mean, var;
     if (mode == CP_BN_RUNNING) {
-        if (lane != 0 || col >= F) return;
+        if (lane != 0 || col >= F || blockIdx.y != 0) return;
         mean = (double)run_mean[col];
         var = (double)run_var[col];
     } else {
-        const double s = reduce_partials(psum, P, F, col, lane, sm);
-        const double q = reduce_partials(psq, P, F, col, lane, sm);
-        if (lane != 0 || col >= F) return;
+        const float* const parts[2] = {psum, psq};
+        double tot[2];
+        if (!reduce_partials_2level<2>(parts, P, F, scratch, tickets, tot, sm)) return;
+        const double s = tot[0], q = tot[1];
         mean = s / (double)R;
         var = q / (double)R - mean * mean;          // biased variance (normalisation)
         if (var < 0.0) var = 0.0;
@@ -174,12 +224,14 @@ bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq
 
 // ---------------------------------------------------------------------------------- BN apply
 // a = y*scale + shift, then (linear blocks 4..7) dropout: a * keep / (1-p)   (models.py:282-297)
-// SPLIT: write the result as the two tf32 planes (hi -> a, lo -> a_lo) the tensor-core GEMMs consume
+// SPLIT: write the result as the two tf32 planes (hi -> a, lo -> a_lo) the tensor-core GEMMs consume.
+// Dropout: `keep` holds a caller-provided mask, or (gen_p > 0) the mask is drawn here -- Philox4x32-10
+// keyed by (seed, layer), counter = element/4 -- and stored to `keep` for the backward pass.
 template <int F, bool SPLIT>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, float* __restrict__ a_lo, int64_t R,
                 const float* __restrict__ scale, const float* __restrict__ shift,
-                const uint8_t* __restrict__ keep, float inv_keep) {
+                uint8_t* __restrict__ keep, float inv_keep, float gen_p, uint64_t seed, uint64_t layer) {
     const int64_t total = R * (F / 4);
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < total;
          v += (int64_t)gridDim.x * blockDim.x) {
@@ -189,7 +241,16 @@ bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, float* __res
         const float4 t = __ldg(reinterpret_cast<const float4*>(shift + c));
         float4 o = make_float4(fmaf(x.x, s.x, t.x), fmaf(x.y, s.y, t.y), fmaf(x.z, s.z, t.z), fmaf(x.w, s.w, t.w));
         if (keep) {
-            const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(keep) + v);
+            uchar4 m;
+            if (gen_p > 0.f) {
+                curandStatePhilox4_32_10_t st;
+                curand_init(seed, /*subsequence=*/(unsigned long long)v, /*offset=*/layer * 4ull, &st);
+                const float4 u = curand_uniform4(&st);          // (0,1]
+                m.x = u.x > gen_p; m.y = u.y > gen_p; m.z = u.z > gen_p; m.w = u.w > gen_p;
+                reinterpret_cast<uchar4*>(keep)[v] = m;
+            } else {
+                m = *(reinterpret_cast<const uchar4*>(keep) + v);
+            }
             o.x = m.x ? o.x * inv_keep : 0.f; o.y = m.y ? o.y * inv_keep : 0.f;
             o.z = m.z ? o.z * inv_keep : 0.f; o.w = m.w ? o.w * inv_keep : 0.f;
         }
@@ -201,20 +262,6 @@ bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, float* __res
         } else {
             reinterpret_cast<float4*>(a)[v] = o;
         }
-    }
-}
-
-// keep mask ~ Bernoulli(1-p), Philox4x32-10 keyed by (seed, layer), counter = element/4
-__global__ void __launch_bounds__(256)
-dropout_mask_kernel(uint8_t* __restrict__ keep, int64_t n4, float p, uint64_t seed, uint64_t layer) {
-    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n4;
-         v += (int64_t)gridDim.x * blockDim.x) {
-        curandStatePhilox4_32_10_t st;
-        curand_init(seed, /*subsequence=*/(unsigned long long)v, /*offset=*/layer * 4ull, &st);
-        const float4 u = curand_uniform4(&st);          // (0,1]
-        uchar4 m;
-        m.x = u.x > p; m.y = u.y > p; m.z = u.z > p; m.w = u.w > p;
-        reinterpret_cast<uchar4*>(keep)[v] = m;
     }
 }
 
@@ -260,12 +307,13 @@ bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, i
 __global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int P, int F, int64_t R,
                        float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ d_gamma,
-                       float* __restrict__ d_beta) {
+                       float* __restrict__ d_beta, double* __restrict__ scratch, unsigned int* __restrict__ tickets) {
     __shared__ double sm[32 * 33];
-    const int col = blockIdx.x * 32 + threadIdx.x % 32, lane = threadIdx.x / 32;
-    const double a = reduce_partials(p1, P, F, col, lane, sm);
-    const double b = reduce_partials(p2, P, F, col, lane, sm);
-    if (lane != 0 || col >= F) return;
+    const int col = blockIdx.x * 32 + threadIdx.x % 32;
+    const float* const parts[2] = {p1, p2};
+    double tot[2];
+    if (!reduce_partials_2level<2>(parts, P, F, scratch, tickets, tot, sm)) return;
+    const double a = tot[0], b = tot[1];
     m1[col] = (float)(a / (double)R);
     m2[col] = (float)(b / (double)R);
     if (d_beta) d_beta[col] = (float)a;
@@ -355,6 +403,9 @@ colsum_rows_kernel(const float* __restrict__ G, int64_t M, int N, float* __restr
 
 // --------------------------------------------------------------------------------- projection
 // emb[r, o] = sum_k a[r,k] * Wp[o,k]    (models.py:314, bias-free 512 -> 16)
+// One warp per 4 rows: each lane owns 16 k-values of every row, the weight slice is read from shared
+// memory once per 4 rows, and the 16 outputs are reduced across the warp with a halving butterfly.
+#define PROJ_RPW 4
 __global__ void __launch_bounds__(256)
 proj_fwd_kernel(const float* __restrict__ a, const float* __restrict__ Wp, float* __restrict__ emb, int64_t R) {
     __shared__ __align__(16) float W[CP_EMB_DIM][512];
@@ -362,24 +413,47 @@ proj_fwd_kernel(const float* __restrict__ a, const float* __restrict__ Wp, float
         reinterpret_cast<float4*>(&W[0][0])[e] = __ldg(reinterpret_cast<const float4*>(Wp) + e);
     __syncthreads();
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < R; r += (int64_t)gridDim.x * 8) {
-        float4 x[4];
+    for (int64_t r0 = ((int64_t)blockIdx.x * 8 + warp) * PROJ_RPW; r0 < R; r0 += (int64_t)gridDim.x * 8 * PROJ_RPW) {
+        float4 x[PROJ_RPW][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) x[j] = __ldg(reinterpret_cast<const float4*>(a + r * 512) + lane + 32 * j);
-        float out = 0.f;
+        for (int i = 0; i < PROJ_RPW; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                x[i][j] = (r0 + i < R) ? __ldg(reinterpret_cast<const float4*>(a + (r0 + i) * 512) + lane + 32 * j)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        float acc[PROJ_RPW][CP_EMB_DIM];
 #pragma unroll
         for (int o = 0; o < CP_EMB_DIM; ++o) {
-            float s = 0.f;
+            float4 w[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 w = *reinterpret_cast<const float4*>(&W[o][(lane + 32 * j) * 4]);
-                s = fmaf(x[j].x, w.x, s); s = fmaf(x[j].y, w.y, s);
-                s = fmaf(x[j].z, w.z, s); s = fmaf(x[j].w, w.w, s);
+            for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(&W[o][(lane + 32 * j) * 4]);
+#pragma unroll
+            for (int i = 0; i < PROJ_RPW; ++i) {
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s = fmaf(x[i][j].x, w[j].x, s); s = fmaf(x[i][j].y, w[j].y, s);
+                    s = fmaf(x[i][j].z, w[j].z, s); s = fmaf(x[i][j].w, w[j].w, s);
+                }
+                acc[i][o] = s;
             }
-            s = warp_sum(s);
-            if (lane == o) out = s;
         }
-        if (lane < CP_EMB_DIM) emb[r * CP_EMB_DIM + lane] = out;
+#pragma unroll
+        for (int i = 0; i < PROJ_RPW; ++i) {
+            // 16 values per lane -> lane l (l < 16) ends with the warp total of output l
+#pragma unroll
+            for (int off = 8; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int k = 0; k < off; ++k) {
+                    const float send = up ? acc[i][k] : acc[i][k + off];
+                    const float keep = up ? acc[i][k + off] : acc[i][k];
+                    acc[i][k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            const float tot = acc[i][0] + __shfl_xor_sync(0xffffffffu, acc[i][0], 16);
+            if (lane < CP_EMB_DIM && r0 + i < R) emb[(r0 + i) * CP_EMB_DIM + lane] = tot;
+        }
     }
 }
 
@@ -390,20 +464,28 @@ proj_bwd_data_kernel(const float* __restrict__ d, const float* __restrict__ Wp, 
     float4 w[CP_EMB_DIM];
 #pragma unroll
     for (int o = 0; o < CP_EMB_DIM; ++o) w[o] = __ldg(reinterpret_cast<const float4*>(Wp + o * 512) + q);
-    for (int64_t r = (int64_t)blockIdx.x * 2 + rl; r < R; r += (int64_t)gridDim.x * 2) {
-        float dv[CP_EMB_DIM];
+    for (int64_t r0 = ((int64_t)blockIdx.x * 2 + rl) * 4; r0 < R; r0 += (int64_t)gridDim.x * 8) {
+        float4 dv[4][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(d + r * CP_EMB_DIM) + j);
-            dv[j * 4 + 0] = t.x; dv[j * 4 + 1] = t.y; dv[j * 4 + 2] = t.z; dv[j * 4 + 3] = t.w;
-        }
-        float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int o = 0; o < CP_EMB_DIM; ++o) {
-            o4.x = fmaf(dv[o], w[o].x, o4.x); o4.y = fmaf(dv[o], w[o].y, o4.y);
-            o4.z = fmaf(dv[o], w[o].z, o4.z); o4.w = fmaf(dv[o], w[o].w, o4.w);
+            for (int j = 0; j < 4; ++j)
+                dv[i][j] = (r0 + i < R) ? __ldg(reinterpret_cast<const float4*>(d + (r0 + i) * CP_EMB_DIM) + j)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (r0 + i >= R) break;
+            const float dd[CP_EMB_DIM] = {dv[i][0].x, dv[i][0].y, dv[i][0].z, dv[i][0].w, dv[i][1].x, dv[i][1].y,
+                                          dv[i][1].z, dv[i][1].w, dv[i][2].x, dv[i][2].y, dv[i][2].z, dv[i][2].w,
+                                          dv[i][3].x, dv[i][3].y, dv[i][3].z, dv[i][3].w};
+            float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int o = 0; o < CP_EMB_DIM; ++o) {
+                o4.x = fmaf(dd[o], w[o].x, o4.x); o4.y = fmaf(dd[o], w[o].y, o4.y);
+                o4.z = fmaf(dd[o], w[o].z, o4.z); o4.w = fmaf(dd[o], w[o].w, o4.w);
+            }
+            reinterpret_cast<float4*>(ga + (r0 + i) * 512)[q] = o4;
         }
-        reinterpret_cast<float4*>(ga + r * 512)[q] = o4;
     }
 }
 
@@ -418,20 +500,27 @@ proj_bwd_weight_kernel(const float* __restrict__ d, const float* __restrict__ a,
 #pragma unroll
     for (int o = 0; o < CP_EMB_DIM; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t r0 = (int64_t)blockIdx.x * PROJ_W_ROWS;
-    for (int k = rl; k < PROJ_W_ROWS; k += 2) {
-        const int64_t r = r0 + k;
-        if (r >= R) break;
-        const float4 x = __ldg(reinterpret_cast<const float4*>(a + r * 512) + q);
-        float dv[CP_EMB_DIM];
+    for (int k = rl * 4; k < PROJ_W_ROWS; k += 8) {          // 4 rows in flight per thread
+        float4 x[4], dv[4][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(d + r * CP_EMB_DIM) + j);
-            dv[j * 4 + 0] = t.x; dv[j * 4 + 1] = t.y; dv[j * 4 + 2] = t.z; dv[j * 4 + 3] = t.w;
+        for (int i = 0; i < 4; ++i) {
+            const int64_t r = r0 + k + i;
+            const bool ok = r < R;
+            x[i] = ok ? __ldg(reinterpret_cast<const float4*>(a + r * 512) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                dv[i][j] = ok ? __ldg(reinterpret_cast<const float4*>(d + r * CP_EMB_DIM) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int o = 0; o < CP_EMB_DIM; ++o) {
-            acc[o].x = fmaf(dv[o], x.x, acc[o].x); acc[o].y = fmaf(dv[o], x.y, acc[o].y);
-            acc[o].z = fmaf(dv[o], x.z, acc[o].z); acc[o].w = fmaf(dv[o], x.w, acc[o].w);
+        for (int i = 0; i < 4; ++i) {
+            const float dd[CP_EMB_DIM] = {dv[i][0].x, dv[i][0].y, dv[i][0].z, dv[i][0].w, dv[i][1].x, dv[i][1].y,
+                                          dv[i][1].z, dv[i][1].w, dv[i][2].x, dv[i][2].y, dv[i][2].z, dv[i][2].w,
+                                          dv[i][3].x, dv[i][3].y, dv[i][3].z, dv[i][3].w};
+#pragma unroll
+            for (int o = 0; o < CP_EMB_DIM; ++o) {
+                acc[o].x = fmaf(dd[o], x[i].x, acc[o].x); acc[o].y = fmaf(dd[o], x[i].y, acc[o].y);
+                acc[o].z = fmaf(dd[o], x[i].z, acc[o].z); acc[o].w = fmaf(dd[o], x[i].w, acc[o].w);
+            }
         }
     }
     float* out = partial + (int64_t)blockIdx.x * CP_EMB_DIM * 512;

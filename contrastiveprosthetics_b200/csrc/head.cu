@@ -223,7 +223,7 @@ head_finalize_kernel(const HeadPartial* __restrict__ partial, int n_part, int64_
 }
 
 static int head_blocks(int64_t G) {
-    const int64_t cap = (int64_t)CP_NUM_SMS * 8;
+    const int64_t cap = (int64_t)CP_NUM_SMS * 4;       // 64-thread CTAs; the finalize CTA walks this many partials
     return (int)(G < cap ? G : cap);
 }
 

@@ -108,6 +108,14 @@ int cp_encoder_read_activation(const void *workspace, size_t workspace_bytes, in
 int cp_linear_forward(const float *A, const float *W, const float *bias, float *Y, int64_t M, int N,
                       int K, int relu, float *col_sum, float *col_sqsum, void *workspace,
                       size_t workspace_bytes, int engine, void *stream);
+/* Tensor-core engine operand format: x = hi + lo with hi = tf32(x), lo = tf32(x - hi) (n % 4 == 0). */
+int cp_split_tf32(const float *x, float *hi, float *lo, int64_t n, void *stream);
+/* cp_linear_forward (CP_ENGINE_TC) on pre-split operands: exactly the per-layer launch of the encoder
+ * (N % 128 == 0, K % 32 == 0).  col_sum / col_sqsum may both be NULL. */
+int cp_linear_forward_planes(const float *A_hi, const float *A_lo, const float *W_hi, const float *W_lo,
+                             const float *bias, float *Y, int64_t M, int N, int K, int relu,
+                             float *col_sum, float *col_sqsum, void *workspace, size_t workspace_bytes,
+                             void *stream);
 /* dA[M,K] = G[M,N] @ W[N,K];  dW[N,K] = G^T @ A;  db[N] = colsum(G) */
 int cp_linear_backward(const float *G, const float *A, const float *W, float *dA, float *dW,
                        float *db, int64_t M, int N, int K, void *workspace, size_t workspace_bytes,
