@@ -245,6 +245,187 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM);
 }
 
+// ---------------------------------------------------------------------------- CTA-pair forward / dgrad
+// Same math as gemm_tc_nt_kernel<128>, issued as cta_group::2 MMAs on a 256 x 256 tile owned by a pair of
+// CTAs (cluster 2x1x1): each CTA stages its own 128 rows of A and only HALF of the B tile (128 of the 256
+// rows), so the shared-memory traffic per MMA cycle drops from ~208 to ~106 B/clk and the main loop becomes
+// tensor-pipe bound.  The leader CTA (cluster rank 0) issues every MMA; TMA completions of both CTAs are
+// accounted on the leader's `full` barriers; tcgen05.commit multicasts the `empty` / `tmem_full` arrivals
+// to both CTAs.  TMEM: 256 main + 256 correction columns per CTA (single buffered), eight epilogue warps.
+namespace pair {
+constexpr int BN2 = 256;                 // tile N (B rows per CTA = 128)
+constexpr int THREADS2 = 320;            // TMA warp, MMA warp, 8 epilogue warps
+constexpr int EPI2 = 256;
+struct Smem2 {
+    uint64_t full[STAGES], empty[STAGES], tmem_full, tmem_empty;
+    uint32_t tmem_base;
+    uint32_t pad;
+    float csum[4][BN2];
+    float csq[4][BN2];
+};
+constexpr int SMEM2 = STAGES * STAGE_BYTES + 1024 + (int)sizeof(Smem2);
+}  // namespace pair
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair::THREADS2, 1)
+gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                       const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                       const NtArgs g) {
+    using namespace pair;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    Smem2* sm = reinterpret_cast<Smem2*>(tiles + STAGES * STAGE_BYTES);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t rank = tc::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int tiles_n = g.N / BN2;
+    const int64_t tiles_m = (g.M + 2 * BM - 1) / (2 * BM);
+    const int64_t n_tiles = tiles_m * tiles_n;
+    const int kblocks = g.K / BK;
+    const int64_t cluster_id = blockIdx.x / 2, n_clusters = gridDim.x / 2;
+
+    if (warp == 0 && tc::elect_one()) {
+        tc::prefetch_tmap(&tm_a_hi); tc::prefetch_tmap(&tm_a_lo);
+        tc::prefetch_tmap(&tm_b_hi); tc::prefetch_tmap(&tm_b_lo);
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&sm->full[s], 1); tc::mbar_init(&sm->empty[s], 1); }
+        tc::mbar_init(&sm->tmem_full, 1);
+        tc::mbar_init(&sm->tmem_empty, 16);            // 8 epilogue warps x 2 CTAs arrive on the leader's copy
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) {
+        tc::tmem_alloc_pair(&sm->tmem_base, 512);
+        tc::tmem_relinquish_pair();
+    }
+    tc::tc_fence_before();
+    tc::cluster_sync();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = sm->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (tc::elect_one()) {
+            int s = 0; uint32_t ph = 0;
+            for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
+                const int m0 = (int)(t / tiles_n) * 2 * BM + (int)rank * BM;
+                const int n0 = (int)(t % tiles_n) * BN2 + (int)rank * BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    tc::mbar_wait(&sm->empty[s], ph ^ 1);
+                    uint8_t* st = tiles + s * STAGE_BYTES;
+                    if (leader) tc::mbar_expect_tx(&sm->full[s], 2 * STAGE_BYTES);     // bytes of both CTAs
+                    tc::tma_load_2d_pair(st + 0 * TILE_BYTES, &tm_a_hi, &sm->full[s], kb * BK, m0);
+                    tc::tma_load_2d_pair(st + 1 * TILE_BYTES, &tm_a_lo, &sm->full[s], kb * BK, m0);
+                    tc::tma_load_2d_pair(st + 2 * TILE_BYTES, &tm_b_hi, &sm->full[s], kb * BK, n0);
+                    tc::tma_load_2d_pair(st + 3 * TILE_BYTES, &tm_b_lo, &sm->full[s], kb * BK, n0);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && tc::elect_one()) {
+            constexpr uint32_t idesc = tc::idesc_tf32(2 * BM, BN2, 0, 0);
+            int s = 0; uint32_t ph = 0;
+            int it = 0;
+            for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
+                tc::mbar_wait(&sm->tmem_empty, (it & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d = tmem_base;
+                const uint32_t dc = tmem_base + BN2;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    tc::mbar_wait(&sm->full[s], ph);
+                    tc::tc_fence_after();
+                    const uint32_t base = tc::smem_u32(tiles + s * STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint32_t ko = k * UMMA_K * 4;
+                        const uint64_t a_hi = tc::smem_desc_sw128(base + 0 * TILE_BYTES + ko, 16, 1024);
+                        const uint64_t a_lo = tc::smem_desc_sw128(base + 1 * TILE_BYTES + ko, 16, 1024);
+                        const uint64_t b_hi = tc::smem_desc_sw128(base + 2 * TILE_BYTES + ko, 16, 1024);
+                        const uint64_t b_lo = tc::smem_desc_sw128(base + 3 * TILE_BYTES + ko, 16, 1024);
+                        tc::mma_tf32_pair(dc, a_lo, b_hi, idesc, (kb | k) != 0);
+                        tc::mma_tf32_pair(dc, a_hi, b_lo, idesc, 1);
+                        tc::mma_tf32_pair(d, a_hi, b_hi, idesc, (kb | k) != 0);
+                    }
+                    tc::mma_commit_pair(&sm->empty[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                tc::mma_commit_pair(&sm->tmem_full);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9 of both CTAs) =====================
+        const int q = warp % 4;                      // TMEM lane quadrant
+        const int half = (warp - 2) / 4;             // column half: 0 -> 0..127, 1 -> 128..255
+        const int et = threadIdx.x - 64;             // 0..255
+        const uint32_t empty_remote = tc::mapa(tc::smem_u32(&sm->tmem_empty), 0);
+        int it = 0;
+        for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
+            const int64_t tile_m = (t / tiles_n) * 2 + rank;            // 128-row tile index of this CTA
+            const int n0 = (int)(t % tiles_n) * BN2;
+            const int64_t row = tile_m * BM + q * 32 + lane;
+            const bool row_ok = row < g.M;
+            tc::mbar_wait(&sm->tmem_full, it & 1);
+            tc::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int cl = half * 128 + c * 32;                     // column inside the tile
+                float v[32], vc[32];
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + cl;
+                tc::tmem_ld32(ta, v);
+                tc::tmem_ld32(ta + BN2, vc);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += vc[j];
+                const int col = n0 + cl;
+                if (g.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col + j));
+                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                    }
+                }
+                if (g.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (row_ok) {
+                    float4* dst = reinterpret_cast<float4*>(g.C + row * g.ldc + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                if (g.psum) {
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = row_ok ? v[j] : 0.f;
+                        sq[j] = v[j] * v[j];
+                    }
+                    warp_col_reduce32(v, lane);
+                    warp_col_reduce32(sq, lane);
+                    sm->csum[q][cl + lane] = v[0];
+                    sm->csq[q][cl + lane] = sq[0];
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(empty_remote);
+            if (g.psum) {
+                tc::named_bar_sync(1, EPI2);
+                const float s = sm->csum[0][et] + sm->csum[1][et] + sm->csum[2][et] + sm->csum[3][et];
+                const float qq = sm->csq[0][et] + sm->csq[1][et] + sm->csq[2][et] + sm->csq[3][et];
+                if (tile_m * BM < g.M) {
+                    g.psum[tile_m * g.N + n0 + et] = s;
+                    g.psq[tile_m * g.N + n0 + et] = qq;
+                }
+                tc::named_bar_sync(1, EPI2);
+            }
+        }
+    }
+    tc::tc_fence_before();
+    tc::cluster_sync();
+    if (warp == 1) tc::tmem_dealloc_pair(tmem_base, 512);
+}
+
 // ---------------------------------------------------------------------------- weight gradient
 // P[z][o, c] = sum over rows r of slab z of G[r, o] * A[r, c].  Both operands are MN-major: a stage
 // holds, per plane, 4 blocks of [32 rows r][32 floats] (one 3-D TMA box {32, 32, 4}); MMA K-step j
@@ -625,6 +806,11 @@ inline int launch_nt_cfg(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, con
     return CP_OK;
 }
 
+// CTA-pair (cta_group::2) kernel for N % 256 == 0.  Measured on B200 at M = 167,936, N = K = 512: 0.399-0.449 ms vs
+// 0.392-0.402 ms for the single-CTA kernel (its 2 x 256 TMEM columns leave no room to double-buffer the accumulators,
+// so the epilogue is exposed: tensor pipe 57 % vs 69 %).  Correct (bring-up test green) but OFF by default.
+static bool g_use_pair = false;
+
 inline int launch_nt(const float* A_hi, const float* A_lo, int64_t M, int K, int lda, const float* B_hi,
                      const float* B_lo, int N, int ldb, const float* bias, float* C, int ldc, float* psum,
                      float* psq, int relu, cudaStream_t st) {
@@ -636,6 +822,18 @@ inline int launch_nt(const float* A_hi, const float* A_lo, int64_t M, int K, int
     if ((rc = make_tmap_2d(&tb_hi, B_hi, N, K, ldb, BN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, N, K, ldb, BN)) != CP_OK) return rc;
     NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu};
+    if (g_use_pair && N % pair::BN2 == 0) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
+            attr_set = true;
+        }
+        const int64_t n_tiles = cp_cdiv(M, 2 * BM) * (N / pair::BN2);
+        const int clusters = (int)(n_tiles < CP_NUM_SMS / 2 ? n_tiles : CP_NUM_SMS / 2);
+        gemm_tc_nt_pair_kernel<<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g);
+        CP_CHECK_LAUNCH();
+        return CP_OK;
+    }
     return launch_nt_cfg<128, false>(ta_hi, ta_lo, tb_hi, tb_lo, g, cp_cdiv(M, BM), st);
 }
 

@@ -67,14 +67,18 @@ int run_nt(int64_t M, int N, int K, bool check, int reps) {
     if (reps > 0) {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
-        for (int i = 0; i < 3; ++i) tcg::launch_nt(dAh, dAl, M, K, K, dBh, dBl, N, K, dbias, dC, N, dps, dpq, 1, 0);
-        cudaEventRecord(e0);
-        for (int i = 0; i < reps; ++i) tcg::launch_nt(dAh, dAl, M, K, K, dBh, dBl, N, K, dbias, dC, N, dps, dpq, 1, 0);
-        cudaEventRecord(e1);
-        CK(cudaDeviceSynchronize());
-        float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
-        printf("NT M=%lld N=%d K=%d: %.3f ms  %.1f TFLOP/s (fp32-equivalent), %.1f TFLOP/s tf32 issued\n", (long long)M, N, K,
-               ms, 2.0 * M * N * K / ms / 1e9, 6.0 * M * N * K / ms / 1e9);
+        for (int variant = 0; variant < 2; ++variant) {
+            float* ps = variant == 0 ? dps : nullptr;
+            float* pq = variant == 0 ? dpq : nullptr;
+            for (int i = 0; i < 3; ++i) tcg::launch_nt(dAh, dAl, M, K, K, dBh, dBl, N, K, dbias, dC, N, ps, pq, 1, 0);
+            cudaEventRecord(e0);
+            for (int i = 0; i < reps; ++i) tcg::launch_nt(dAh, dAl, M, K, K, dBh, dBl, N, K, dbias, dC, N, ps, pq, 1, 0);
+            cudaEventRecord(e1);
+            CK(cudaDeviceSynchronize());
+            float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+            printf("NT M=%lld N=%d K=%d stats=%d: %.3f ms  %.1f TFLOP/s (fp32-equivalent), %.1f TFLOP/s tf32 issued\n",
+                   (long long)M, N, K, variant == 0, ms, 2.0 * M * N * K / ms / 1e9, 6.0 * M * N * K / ms / 1e9);
+        }
     }
     cudaFree(dA); cudaFree(dAh); cudaFree(dAl); cudaFree(dB); cudaFree(dBh); cudaFree(dBl); cudaFree(dbias); cudaFree(dC);
     cudaFree(dps); cudaFree(dpq);
@@ -135,14 +139,19 @@ int run_tn(int64_t R, int Mo, int No, bool check, int reps) {
 
 int main(int argc, char** argv) {
     int bad = 0;
-    bad |= run_nt(128, 128, 32, true, 0);
-    bad |= run_nt(128, 128, 512, true, 0);
-    bad |= run_nt(1000, 512, 768, true, 0);
-    bad |= run_nt(4100, 512, 512, true, 0);
-    bad |= run_tn(32, 128, 128, true, 0);
-    bad |= run_tn(1000, 128, 128, true, 0);
-    bad |= run_tn(5000, 512, 768, true, 0);
-    bad |= run_tn(41 * 1000, 512, 512, true, 0);
+    if (argc > 1 && argv[1][0] == '1') tcg::g_use_pair = false;
+    printf("pair kernel: %d\n", (int)tcg::g_use_pair);
+    const bool quick = argc > 2;
+    if (!quick) {
+        bad |= run_nt(128, 128, 32, true, 0);
+        bad |= run_nt(128, 128, 512, true, 0);
+        bad |= run_nt(1000, 512, 768, true, 0);
+        bad |= run_nt(4100, 512, 512, true, 0);
+        bad |= run_tn(32, 128, 128, true, 0);
+        bad |= run_tn(1000, 128, 128, true, 0);
+        bad |= run_tn(5000, 512, 768, true, 0);
+        bad |= run_tn(41 * 1000, 512, 512, true, 0);
+    }
     if (!bad) run_nt(167936, 512, 512, false, 10);
     if (!bad) run_nt(167936, 768, 512, false, 10);
     if (!bad) run_tn(167936, 512, 512, false, 10);
