@@ -13,7 +13,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 SO_PATH = os.path.join(_PKG, "libcpros.so")
-SOURCES = ["version.cu", "gather.cu", "encoder.cu", "head.cu", "vote.cu"]
+SOURCES = ["version.cu", "gather.cu", "encoder.cu", "head.cu", "clip.cu", "vote.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -99,12 +99,20 @@ def lib():
     L.cp_head_forward_backward.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                            _vp, _sz, _vp]
     L.cp_logits_loss.argtypes = [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
+    _f = ctypes.c_float
+    L.cp_clip_normalize.argtypes = [_vp, _i64, _vp, _vp, _vp]
+    L.cp_clip_transpose.argtypes = [_vp, _i64, _i64, _vp, _vp]
+    L.cp_clip_sums.argtypes = [_vp, _i64, _vp, _i64, _i64, _f, _vp, _vp, _vp]
+    L.cp_clip_loss.argtypes = [_vp, _vp, _vp, _vp, _i64, _i64, _f, _vp, _i64, _vp, _vp, _vp]
+    L.cp_clip_grad.argtypes = [_vp, _i64, _vp, _i64, _i64, _f, _vp, _vp, _f, _vp, _vp]
+    L.cp_clip_embed_backward.argtypes = [_vp, _vp, _vp, _vp, _i64, _f, _vp, _vp]
     L.cp_vote_eval.argtypes = [_vp, _i64, _i32, _i32, _vp, _vp, _vp]
     L.cp_rank_rows.argtypes = [_vp, _i64, _vp, _vp]
     L.cp_subset_eval.argtypes = [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp]
     for name in ("cp_gather_norm", "cp_encoder_forward", "cp_encoder_backward", "cp_linear_forward",
                  "cp_linear_backward", "cp_head_forward_backward", "cp_logits_loss", "cp_vote_eval",
-                 "cp_rank_rows", "cp_subset_eval"):
+                 "cp_rank_rows", "cp_subset_eval", "cp_clip_normalize", "cp_clip_transpose", "cp_clip_sums",
+                 "cp_clip_loss", "cp_clip_grad", "cp_clip_embed_backward"):
         getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L
@@ -114,7 +122,8 @@ EXPORTS = ["cp_version", "cp_launch_count", "cp_status_string", "cp_gather_norm"
            "cp_encoder_forward", "cp_encoder_backward", "cp_encoder_read_activation", "cp_linear_workspace_bytes",
            "cp_linear_forward", "cp_linear_backward", "cp_split_tf32", "cp_linear_forward_planes", "cp_head_workspace_bytes",
            "cp_head_forward_backward", "cp_logits_loss", "cp_vote_eval", "cp_rank_rows",
-           "cp_subset_eval"]
+           "cp_subset_eval", "cp_clip_normalize", "cp_clip_transpose", "cp_clip_sums", "cp_clip_loss",
+           "cp_clip_grad", "cp_clip_embed_backward"]
 
 
 def check(status, what=""):

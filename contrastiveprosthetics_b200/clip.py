@@ -1,0 +1,161 @@
+"""Batch x batch (CLIP) contrastive head -- BASELINE.json config 5 (a8/a9
+generalised, 8e "one exchange step").
+
+    loss = clip_head(E, G, logit_scale)          E, G: this rank's (n,16) un-normalised embeddings
+
+    S = exp(logit_scale) * Ehat Ghat^T over the GLOBAL batch B = n * world_size     (models.py:112-130)
+    loss = 1/2 [ mean_i CE(S[i,:], i) + mean_j CE(S[:,j], j) ]                      (models.py:65, CLIP)
+
+All arithmetic runs in libcpros.so (cp_clip_*; csrc/clip.cu): the B x B matrix is never materialised.
+With world_size > 1 (one process per GPU, torch.distributed / NCCL over NVLink) every rank evaluates
+its row strip E_local x G_all:
+    all-gather      Ghat                       (B,16)   4 MB at B = 65,536
+    all-reduce      column sums                (B,)     256 KB
+    reduce-scatter  d Ghat partials            (B,16) -> (n,16)
+    all-reduce      loss, correct count        scalars
+The returned gradients are those of the GLOBAL loss w.r.t. the rank's own embeddings, so parameter
+gradients must be SUMMED over ranks (dist.FlatGradAllReduce(average=False)).
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+D_E = 16
+
+
+class _CudaOps:
+    """The six libcpros entry points of the head, on tensors."""
+
+    @staticmethod
+    def normalize(x):
+        xhat = torch.empty_like(x)
+        inv = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().cp_clip_normalize(_lib.ptr(x, torch.float32), x.shape[0], _lib.ptr(xhat), _lib.ptr(inv),
+                                                _lib.stream()), "cp_clip_normalize")
+        return xhat, inv
+
+    @staticmethod
+    def transpose(xhat):
+        n = xhat.shape[0]
+        ld = (n + 3) // 4 * 4
+        xt = torch.empty((D_E, ld), dtype=torch.float32, device=xhat.device)
+        _lib.check(_lib.lib().cp_clip_transpose(_lib.ptr(xhat, torch.float32), n, ld, _lib.ptr(xt), _lib.stream()),
+                   "cp_clip_transpose")
+        return xt
+
+    @staticmethod
+    def sums(own, loop_t, n_loop, scale, want_argmax):
+        n_own = own.shape[0]
+        s = torch.empty(n_own, dtype=torch.float32, device=own.device)
+        arg = torch.empty(n_own, dtype=torch.int32, device=own.device) if want_argmax else None
+        _lib.check(_lib.lib().cp_clip_sums(_lib.ptr(own, torch.float32), n_own, _lib.ptr(loop_t), n_loop,
+                                           loop_t.shape[1], scale, _lib.ptr(s), _lib.ptr(arg), _lib.stream()),
+                   "cp_clip_sums")
+        return s, arg
+
+    @staticmethod
+    def loss(ehat, ghat, rowsum, colsum, B, scale, row_arg, row0):
+        n = ehat.shape[0]
+        loss = torch.empty((), dtype=torch.float32, device=ehat.device)
+        ncor = torch.empty((), dtype=torch.int32, device=ehat.device)
+        _lib.check(_lib.lib().cp_clip_loss(_lib.ptr(ehat), _lib.ptr(ghat), _lib.ptr(rowsum), _lib.ptr(colsum), n, B,
+                                           scale, _lib.ptr(row_arg), row0, _lib.ptr(loss), _lib.ptr(ncor),
+                                           _lib.stream()), "cp_clip_loss")
+        return loss, ncor
+
+    @staticmethod
+    def grad(own, loop_t, n_loop, scale, own_sum, loop_sum, coef):
+        d = torch.empty_like(own)
+        _lib.check(_lib.lib().cp_clip_grad(_lib.ptr(own, torch.float32), own.shape[0], _lib.ptr(loop_t), n_loop,
+                                           loop_t.shape[1], scale, _lib.ptr(own_sum), _lib.ptr(loop_sum), coef,
+                                           _lib.ptr(d), _lib.stream()), "cp_clip_grad")
+        return d
+
+    @staticmethod
+    def embed_backward(d_hat, xhat, other_hat, inv_norm, diag_coef):
+        dx = torch.empty_like(xhat)
+        _lib.check(_lib.lib().cp_clip_embed_backward(_lib.ptr(d_hat), _lib.ptr(xhat), _lib.ptr(other_hat),
+                                                     _lib.ptr(inv_norm), xhat.shape[0], diag_coef, _lib.ptr(dx),
+                                                     _lib.stream()), "cp_clip_embed_backward")
+        return dx
+
+
+_ops = _CudaOps        # host-logic tests (gloo, CPU) substitute a test double; the product has only this one
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def _reduce_scatter_rows(full, n, rank, group):
+    """(world*n, 16) partials -> this rank's (n,16) sum."""
+    out = torch.empty((n, full.shape[1]), dtype=full.dtype, device=full.device)
+    if dist.get_backend(group) == "gloo":               # CPU host-logic tests
+        dist.all_reduce(full, group=group)
+        out.copy_(full[rank * n:(rank + 1) * n])
+    else:
+        dist.reduce_scatter_tensor(out, full, group=group)
+    return out
+
+
+class _ClipHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, E, G, scale, want_grad, group):
+        ops = _ops
+        world, rank = _world(group)
+        E, G = E.contiguous(), G.contiguous()
+        n = E.shape[0]
+        if G.shape != E.shape or E.shape[1] != D_E:
+            raise RuntimeError(f"clip_head expects two (n,{D_E}) tensors, got {tuple(E.shape)} and {tuple(G.shape)}")
+        B, row0 = n * world, rank * n
+        ehat, inv_e = ops.normalize(E)
+        ghat, inv_g = ops.normalize(G)
+        if world > 1:
+            ghat_all = torch.empty((B, D_E), dtype=ghat.dtype, device=ghat.device)
+            dist.all_gather_into_tensor(ghat_all, ghat, group=group)
+        else:
+            ghat_all = ghat
+        ght = ops.transpose(ghat_all)                       # (16, B)  loop operand of the row pass
+        eht = ops.transpose(ehat)                           # (16, n)  loop operand of the column pass
+        rowsum, row_arg = ops.sums(ehat, ght, B, scale, True)
+        colsum, _ = ops.sums(ghat_all, eht, n, scale, False)
+        if world > 1:
+            dist.all_reduce(colsum, group=group)
+        col_local = colsum[row0:row0 + n].contiguous()
+        loss, ncor = ops.loss(ehat, ghat, rowsum, col_local, B, scale, row_arg, row0)
+        if world > 1:
+            dist.all_reduce(loss, group=group)
+            dist.all_reduce(ncor, group=group)
+        if want_grad:
+            coef = scale / (2.0 * B)
+            d_ehat = ops.grad(ehat, ght, B, scale, rowsum, colsum, coef)
+            d_ghat = ops.grad(ghat_all, eht, n, scale, colsum, rowsum, coef)
+            if world > 1:
+                d_ghat = _reduce_scatter_rows(d_ghat, n, rank, group)
+            ctx.saved = (ops.embed_backward(d_ehat, ehat, ghat, inv_e, scale / B),
+                         ops.embed_backward(d_ghat, ghat, ehat, inv_g, scale / B))
+        else:
+            ctx.saved = None
+        ctx.mark_non_differentiable(ncor, row_arg)
+        return loss, ncor, row_arg
+
+    @staticmethod
+    def backward(ctx, g_loss, _gn, _ga):
+        if ctx.saved is None:
+            raise RuntimeError("clip_head was run without gradients")
+        dE, dG = ctx.saved
+        return dE * g_loss, dG * g_loss, None, None, None
+
+
+def clip_head(E, G, logit_scale=0.0, group=None):
+    """Returns (loss, n_correct, row_argmax): the global symmetric CLIP loss (differentiable w.r.t. E and
+    G), the global number of rows whose arg-max column is their own sample, and this rank's arg-max
+    columns (global indices, first maximum)."""
+    scale = float(math.exp(float(logit_scale)))
+    want_grad = torch.is_grad_enabled() and (E.requires_grad or G.requires_grad)
+    return _ClipHeadFn.apply(E, G, scale, want_grad, group)

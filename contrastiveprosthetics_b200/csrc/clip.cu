@@ -1,0 +1,364 @@
+// K3': batch x batch (CLIP) contrastive head -- BASELINE.json config 5.
+//
+// Generalises Model.forward's contrastive branch (models.py:112-130: L2-normalise both towers, inner
+// products) from the per-group 41 x 41 `bmm` to ONE B x B similarity matrix with the CLIP loss the
+// reference is "modeled after" (models.py:65): symmetric cross-entropy with arange targets,
+//     S = s * Ehat . Ghat^T,   s = exp(logit_scale)  (models.py:81,129),
+//     loss = 1/(2B) sum_i [ LSE_j S_ij - S_ii ] + 1/(2B) sum_j [ LSE_i S_ij - S_jj ].
+// The B x B matrix (17 GB at B = 65,536) is never materialised: every kernel below recomputes 128 x 64
+// tiles of it in registers.  Because both towers are L2-normalised, |S_ij| <= s, so exp(S_ij - s) can
+// neither overflow nor needs a running maximum: the row and column sums are plain sums.
+//
+// One kernel, `clip_sweep_kernel`, serves all four passes; a CTA owns 64 "own" rows and sweeps over
+// all "loop" rows:
+//   sums:   own_sum[i] = sum_j exp(s*(x_i.y_j - 1))                          (+ first-max argmax)
+//   grads:  d_own[i,:] = coef * sum_j exp(s*(x_i.y_j - 1)) * (1/own_sum[i] + 1/loop_sum[j]) * y_j
+// row pass:    own = Ehat (this rank's rows), loop = Ghat (all B rows)
+// column pass: own = Ghat (all B rows),       loop = Ehat (this rank's rows)  -> partial sums that the
+//              host all-reduces (column sums) / reduce-scatters (d Ghat) across ranks.
+// Results are deterministic (fixed-order shuffles, no float atomics).
+#include "common.cuh"
+
+namespace {
+constexpr int D = CP_EMB_DIM;
+constexpr int OWN = 64;          // own rows per CTA  (16 row lanes x 4)
+constexpr int LOOP = 128;        // loop rows per tile (16 column lanes x 8)
+constexpr int THREADS = 256;
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Sum v[0..15] over the 16 lanes that share an own-row group; lane l (of the 16) ends with the
+// total of element l in v[0] (halving butterfly, fixed order).
+__device__ __forceinline__ float reduce16_scatter(float (&v)[D], int l16) {
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+        const bool up = (l16 & off) != 0;
+#pragma unroll
+        for (int k = 0; k < off; ++k) {
+            const float send = up ? v[k] : v[k + off];
+            const float keep = up ? v[k + off] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+struct SweepArgs {
+    const float* X;          // (n_own, 16) normalised rows
+    const float* Yt;         // (16, ld_y) normalised loop rows, k-major
+    int64_t n_own, n_loop, ld_y;
+    float a;                 // s * log2(e)
+    // sums pass
+    float* own_sum;          // (n_own)
+    int32_t* own_arg;        // (n_own) first-max loop index, or null
+    // gradient pass
+    const float* own_sum_in; // (n_own)
+    const float* loop_sum;   // (n_loop)
+    float coef;
+    float* d_own;            // (n_own, 16)
+};
+
+template <bool GRAD>
+__global__ void __launch_bounds__(THREADS, 1) clip_sweep_kernel(const SweepArgs g) {
+    __shared__ __align__(16) float Ys[2][D][LOOP];
+    __shared__ __align__(16) float Ls[2][LOOP];          // 1 / loop_sum of the tile (GRAD)
+    __shared__ __align__(16) float Xs[D][OWN];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int64_t i0 = (int64_t)blockIdx.x * OWN + ty * 4;
+
+    // own rows, k-major in shared memory: Xs[k][row]  (one LDS.128 per k gives this thread's 4 rows)
+    {
+        const int row = tid / 4, q = tid % 4;
+        const int64_t r = (int64_t)blockIdx.x * OWN + row;
+        const float4 v = r < g.n_own ? __ldg(reinterpret_cast<const float4*>(g.X + r * D) + q)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        Xs[4 * q + 0][row] = v.x; Xs[4 * q + 1][row] = v.y; Xs[4 * q + 2][row] = v.z; Xs[4 * q + 3][row] = v.w;
+    }
+    float inv_own[4] = {0.f, 0.f, 0.f, 0.f};
+    if (GRAD) {
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+            if (i0 + ii < g.n_own) inv_own[ii] = 1.f / __ldg(g.own_sum_in + i0 + ii);
+    }
+
+    const int64_t n_tiles = (g.n_loop + LOOP - 1) / LOOP;
+    auto load_tile = [&](int64_t t, int buf) {
+        const int64_t j0 = t * LOOP;
+        // 16 x 128 floats = 512 16-byte chunks, two per thread
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int c = tid + q * THREADS, k = c / (LOOP / 4), jq = (c % (LOOP / 4)) * 4;
+            float* dst = &Ys[buf][k][jq];
+            if (j0 + jq < g.ld_y) cp_async16(dst, g.Yt + (int64_t)k * g.ld_y + j0 + jq);
+            else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (GRAD && tid < LOOP) {
+            const int64_t j = j0 + tid;
+            Ls[buf][tid] = j < g.n_loop ? 1.f / __ldg(g.loop_sum + j) : 0.f;
+        }
+        cp_async_commit();
+    };
+
+    float acc_sum[4] = {0.f, 0.f, 0.f, 0.f};
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int best_j[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    float d[4][D];
+    if (GRAD) {
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int k = 0; k < D; ++k) d[ii][k] = 0.f;
+    }
+
+    load_tile(0, 0);
+    for (int64_t t = 0; t < n_tiles; ++t) {
+        const int buf = (int)(t & 1);
+        if (t + 1 < n_tiles) {
+            load_tile(t + 1, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+
+        float s[4][8];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) s[ii][jj] = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float4 y0 = *reinterpret_cast<const float4*>(&Ys[buf][k][tx * 8]);
+            const float4 y1 = *reinterpret_cast<const float4*>(&Ys[buf][k][tx * 8 + 4]);
+            const float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+            const float4 xv = *reinterpret_cast<const float4*>(&Xs[k][ty * 4]);
+            const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) s[ii][jj] = fmaf(x[ii], y[jj], s[ii][jj]);
+        }
+        const int64_t jbase = t * LOOP + tx * 8;
+        if (!GRAD) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const bool ok = jbase + jj < g.n_loop;
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const float e = ok ? ex2(fmaf(s[ii][jj], g.a, -g.a)) : 0.f;
+                    acc_sum[ii] += e;
+                    if (ok && s[ii][jj] > best[ii]) { best[ii] = s[ii][jj]; best_j[ii] = (int)(jbase + jj); }
+                }
+            }
+        } else {
+            const float4 l0 = *reinterpret_cast<const float4*>(&Ls[buf][tx * 8]);
+            const float4 l1 = *reinterpret_cast<const float4*>(&Ls[buf][tx * 8 + 4]);
+            const float il[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const bool ok = jbase + jj < g.n_loop;
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const float e = ok ? ex2(fmaf(s[ii][jj], g.a, -g.a)) : 0.f;
+                    s[ii][jj] = e * (inv_own[ii] + il[jj]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float4 y0 = *reinterpret_cast<const float4*>(&Ys[buf][k][tx * 8]);
+                const float4 y1 = *reinterpret_cast<const float4*>(&Ys[buf][k][tx * 8 + 4]);
+                const float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) d[ii][k] = fmaf(s[ii][jj], y[jj], d[ii][k]);
+            }
+        }
+        __syncthreads();
+    }
+
+    // combine the 16 column lanes of each own row (fixed order)
+    if (!GRAD) {
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            float v = acc_sum[ii];
+            float b = best[ii];
+            int bj = best_j[ii];
+#pragma unroll
+            for (int off = 8; off >= 1; off >>= 1) {
+                v += __shfl_xor_sync(0xffffffffu, v, off);
+                const float ob = __shfl_xor_sync(0xffffffffu, b, off);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+                if (ob > b || (ob == b && oj < bj)) { b = ob; bj = oj; }
+            }
+            if (tx == 0 && i0 + ii < g.n_own) {
+                g.own_sum[i0 + ii] = v;
+                if (g.own_arg) g.own_arg[i0 + ii] = bj;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const float tot = reduce16_scatter(d[ii], tx);
+            if (i0 + ii < g.n_own) g.d_own[(i0 + ii) * D + tx] = g.coef * tot;
+        }
+    }
+}
+
+// xhat = x / ||x||, inv_norm = 1 / ||x||    (models.py:123,125: no epsilon)
+__global__ void __launch_bounds__(256)
+clip_normalize_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ xhat, float* __restrict__ inv_norm) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float4 v[D / 4];
+    float n2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < D / 4; ++q) {
+        v[q] = __ldg(reinterpret_cast<const float4*>(x + r * D) + q);
+        n2 = fmaf(v[q].x, v[q].x, n2); n2 = fmaf(v[q].y, v[q].y, n2);
+        n2 = fmaf(v[q].z, v[q].z, n2); n2 = fmaf(v[q].w, v[q].w, n2);
+    }
+    const float inv = 1.f / sqrtf(n2);
+#pragma unroll
+    for (int q = 0; q < D / 4; ++q)
+        reinterpret_cast<float4*>(xhat + r * D)[q] = make_float4(v[q].x * inv, v[q].y * inv, v[q].z * inv, v[q].w * inv);
+    inv_norm[r] = inv;
+}
+
+// (n,16) row-major -> (16, ld) k-major
+__global__ void __launch_bounds__(256)
+clip_transpose_kernel(const float* __restrict__ xhat, int64_t n, int64_t ld, float* __restrict__ xt) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= ld) return;
+#pragma unroll
+    for (int k = 0; k < D; ++k) xt[(int64_t)k * ld + r] = r < n ? __ldg(xhat + r * D + k) : 0.f;
+}
+
+// partial loss over the n samples whose row AND column this rank owns:
+//   sum_i [ log rowsum_i + log colsum_i + 2 s - 2 s ehat_i . ghat_i ] / (2 B)       (one CTA, double)
+__global__ void __launch_bounds__(1024)
+clip_loss_kernel(const float* __restrict__ ehat, const float* __restrict__ ghat, const float* __restrict__ rowsum,
+                 const float* __restrict__ colsum, int64_t n, int64_t B, float s, const int32_t* __restrict__ row_arg,
+                 int64_t row0, float* __restrict__ loss, int32_t* __restrict__ n_correct) {
+    __shared__ double red[32];
+    __shared__ int redc[32];
+    double acc = 0.0;
+    int cor = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) dot = fmaf(__ldg(ehat + i * D + k), __ldg(ghat + i * D + k), dot);
+        acc += log((double)rowsum[i]) + log((double)colsum[i]) + 2.0 * (double)s - 2.0 * (double)s * (double)dot;
+        if (row_arg) cor += (int64_t)row_arg[i] == row0 + i;
+    }
+    acc = warp_sum(acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cor += __shfl_xor_sync(0xffffffffu, cor, o);
+    if (threadIdx.x % 32 == 0) { red[threadIdx.x / 32] = acc; redc[threadIdx.x / 32] = cor; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        int c = 0;
+        for (int w = 0; w < 32; ++w) { t += red[w]; c += redc[w]; }
+        *loss = (float)(t / (2.0 * (double)B));
+        if (n_correct) *n_correct = c;
+    }
+}
+
+// dhat = d_hat - diag_coef * other;  dx = (dhat - xhat (xhat . dhat)) * inv_norm
+__global__ void __launch_bounds__(256)
+clip_embed_bwd_kernel(const float* __restrict__ d_hat, const float* __restrict__ xhat, const float* __restrict__ other,
+                      const float* __restrict__ inv_norm, int64_t n, float diag_coef, float* __restrict__ dx) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float dh[D], xh[D];
+    float dot = 0.f;
+#pragma unroll
+    for (int q = 0; q < D / 4; ++q) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(d_hat + r * D) + q);
+        const float4 o = __ldg(reinterpret_cast<const float4*>(other + r * D) + q);
+        const float4 h = __ldg(reinterpret_cast<const float4*>(xhat + r * D) + q);
+        dh[4 * q] = a.x - diag_coef * o.x; dh[4 * q + 1] = a.y - diag_coef * o.y;
+        dh[4 * q + 2] = a.z - diag_coef * o.z; dh[4 * q + 3] = a.w - diag_coef * o.w;
+        xh[4 * q] = h.x; xh[4 * q + 1] = h.y; xh[4 * q + 2] = h.z; xh[4 * q + 3] = h.w;
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) dot = fmaf(xh[k], dh[k], dot);
+    const float inv = __ldg(inv_norm + r);
+#pragma unroll
+    for (int q = 0; q < D / 4; ++q)
+        reinterpret_cast<float4*>(dx + r * D)[q] =
+            make_float4((dh[4 * q] - xh[4 * q] * dot) * inv, (dh[4 * q + 1] - xh[4 * q + 1] * dot) * inv,
+                        (dh[4 * q + 2] - xh[4 * q + 2] * dot) * inv, (dh[4 * q + 3] - xh[4 * q + 3] * dot) * inv);
+}
+
+inline unsigned row_grid(int64_t n) { return (unsigned)cp_cdiv(n, 256); }
+}  // namespace
+
+extern "C" int cp_clip_normalize(const float* x, int64_t n, float* xhat, float* inv_norm, void* stream) {
+    if (!x || !xhat || !inv_norm || n <= 0) return CP_ERR_ARG;
+    clip_normalize_kernel<<<row_grid(n), 256, 0, (cudaStream_t)stream>>>(x, n, xhat, inv_norm);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+extern "C" int cp_clip_transpose(const float* xhat, int64_t n, int64_t ld, float* xhat_t, void* stream) {
+    if (!xhat || !xhat_t || n <= 0 || ld < n || ld % 4 != 0) return CP_ERR_ARG;
+    clip_transpose_kernel<<<row_grid(ld), 256, 0, (cudaStream_t)stream>>>(xhat, n, ld, xhat_t);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+extern "C" int cp_clip_sums(const float* own, int64_t n_own, const float* loop_t, int64_t n_loop, int64_t ld_loop,
+                            float scale, float* own_sum, int32_t* own_argmax, void* stream) {
+    if (!own || !loop_t || !own_sum || n_own <= 0 || n_loop <= 0 || ld_loop < n_loop || ld_loop % 4 != 0 ||
+        !(scale > 0.f) || ((uintptr_t)loop_t % 16) != 0)
+        return CP_ERR_ARG;
+    SweepArgs g{own, loop_t, n_own, n_loop, ld_loop, scale * LOG2E, own_sum, own_argmax, nullptr, nullptr, 0.f, nullptr};
+    clip_sweep_kernel<false><<<(unsigned)cp_cdiv(n_own, OWN), THREADS, 0, (cudaStream_t)stream>>>(g);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+extern "C" int cp_clip_grad(const float* own, int64_t n_own, const float* loop_t, int64_t n_loop, int64_t ld_loop,
+                            float scale, const float* own_sum, const float* loop_sum, float coef, float* d_own,
+                            void* stream) {
+    if (!own || !loop_t || !own_sum || !loop_sum || !d_own || n_own <= 0 || n_loop <= 0 || ld_loop < n_loop ||
+        ld_loop % 4 != 0 || !(scale > 0.f) || ((uintptr_t)loop_t % 16) != 0)
+        return CP_ERR_ARG;
+    SweepArgs g{own, loop_t, n_own, n_loop, ld_loop, scale * LOG2E, nullptr, nullptr, own_sum, loop_sum, coef, d_own};
+    clip_sweep_kernel<true><<<(unsigned)cp_cdiv(n_own, OWN), THREADS, 0, (cudaStream_t)stream>>>(g);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+extern "C" int cp_clip_loss(const float* ehat, const float* ghat, const float* rowsum, const float* colsum, int64_t n,
+                            int64_t B, float scale, const int32_t* row_argmax, int64_t row0, float* loss,
+                            int32_t* n_correct, void* stream) {
+    if (!ehat || !ghat || !rowsum || !colsum || !loss || n <= 0 || B < n || !(scale > 0.f)) return CP_ERR_ARG;
+    clip_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ehat, ghat, rowsum, colsum, n, B, scale, row_argmax, row0, loss,
+                                                          n_correct);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+extern "C" int cp_clip_embed_backward(const float* d_hat, const float* xhat, const float* other_hat,
+                                      const float* inv_norm, int64_t n, float diag_coef, float* dx, void* stream) {
+    if (!d_hat || !xhat || !other_hat || !inv_norm || !dx || n <= 0) return CP_ERR_ARG;
+    clip_embed_bwd_kernel<<<row_grid(n), 256, 0, (cudaStream_t)stream>>>(d_hat, xhat, other_hat, inv_norm, n, diag_coef, dx);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}

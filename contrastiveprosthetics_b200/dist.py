@@ -39,9 +39,11 @@ def rank():
 
 
 class FlatGradAllReduce:
-    """Average the gradients of `params` across ranks with one all-reduce over a flat fp32 bucket."""
+    """Average (or, average=False, sum) the gradients of `params` across ranks with one all-reduce over a
+    flat fp32 bucket.  Sum is for losses that are already normalised by the GLOBAL batch (clip.clip_head)."""
 
-    def __init__(self, params):
+    def __init__(self, params, average=True):
+        self.average = average
         self.params = [p for p in params if p.requires_grad]
         self.numel = sum(p.numel() for p in self.params)
         self._flat = None
@@ -63,7 +65,8 @@ class FlatGradAllReduce:
             off += p.numel()
         torch._foreach_copy_(views, [p.grad for p in ps])
         dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
-        self._flat.div_(world_size())
+        if self.average:
+            self._flat.div_(world_size())
         torch._foreach_copy_([p.grad for p in ps], views)
 
 

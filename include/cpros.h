@@ -142,6 +142,37 @@ int cp_head_forward_backward(const float *emb, int64_t B, int W, const float *ta
 int cp_logits_loss(const float *logits, int64_t G, float *loss, float *d_logits, int32_t *pred,
                    int32_t *n_correct, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------- K3': batch x batch (CLIP) head
+ * BASELINE.json config 5.  Generalises the contrastive branch of Model.forward (models.py:112-130)
+ * from the per-group 41 x 41 bmm to one B x B similarity matrix with the CLIP loss the reference is
+ * modelled after (models.py:65): S = scale * Ehat Ghat^T, scale = exp(logit_scale) (models.py:81,129),
+ *   loss = 1/(2B) sum_i [LSE_j S_ij - S_ii] + 1/(2B) sum_j [LSE_i S_ij - S_jj].
+ * The B x B matrix is never materialised.  The entry points are the pieces between which a
+ * multi-GPU caller places its collectives (all-gather of Ghat, all-reduce of the column sums,
+ * reduce-scatter of d Ghat); on one GPU they are simply called in sequence:
+ *   cp_clip_normalize   xhat = x/||x|| (no epsilon, models.py:123,125), inv_norm = 1/||x||
+ *   cp_clip_transpose   (n,16) -> (16,ld) k-major copy of the "loop" operand (ld % 4 == 0, ld >= n)
+ *   cp_clip_sums        own_sum[i] = sum_j exp(scale*(own_i . loop_j - 1)); own_argmax[i] = first-max j
+ *                       row pass: own = Ehat (local rows), loop = Ghat (all); column pass: swapped
+ *   cp_clip_loss        sum over the n local samples of [log rowsum + log colsum + 2 scale
+ *                       - 2 scale ehat.ghat] / (2B); n_correct = #(row_argmax[i] == row0 + i)
+ *   cp_clip_grad        d_own[i,:] = coef * sum_j exp(scale*(own_i.loop_j - 1)) *
+ *                                    (1/own_sum[i] + 1/loop_sum[j]) * loop_j     (coef = scale/(2B))
+ *   cp_clip_embed_backward  dx = (I - xhat xhat^T)(d_hat - diag_coef * other_hat) * inv_norm
+ *                       (diag_coef = scale/B: the -S_ii terms; then the normalisation backward) */
+int cp_clip_normalize(const float *x, int64_t n, float *xhat, float *inv_norm, void *stream);
+int cp_clip_transpose(const float *xhat, int64_t n, int64_t ld, float *xhat_t, void *stream);
+int cp_clip_sums(const float *own, int64_t n_own, const float *loop_t, int64_t n_loop, int64_t ld_loop,
+                 float scale, float *own_sum, int32_t *own_argmax, void *stream);
+int cp_clip_loss(const float *ehat, const float *ghat, const float *rowsum, const float *colsum,
+                 int64_t n, int64_t B, float scale, const int32_t *row_argmax, int64_t row0,
+                 float *loss, int32_t *n_correct, void *stream);
+int cp_clip_grad(const float *own, int64_t n_own, const float *loop_t, int64_t n_loop, int64_t ld_loop,
+                 float scale, const float *own_sum, const float *loop_sum, float coef, float *d_own,
+                 void *stream);
+int cp_clip_embed_backward(const float *d_hat, const float *xhat, const float *other_hat,
+                           const float *inv_norm, int64_t n, float diag_coef, float *dx, void *stream);
+
 /* ---------------------------------------------------------------- K4: windowed majority vote
  * Replaces the vote loop of contrastive_loopy_loss (models.py:149-163, constants.py:74-78).
  * pred: (B,W,41) int32.  votes: (B,n_votes) int32 = #rows whose prefix-mode over the first

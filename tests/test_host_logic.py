@@ -143,3 +143,80 @@ def test_gloo_world_size_2(tmp_path):
                          env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+# ---- batch x batch (CLIP) head: the N > 1 exchange logic of clip.clip_head under gloo.  The six libcpros entry
+# points are replaced by a torch-CPU test double (tests only -- the product has no such path), so what is tested
+# is the partitioning: all-gather of Ghat, all-reduce of the column sums, reduce-scatter of d Ghat, global
+# loss / count, gradients of the GLOBAL loss w.r.t. the rank's own embeddings.
+_GLOO_CLIP_WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, os.environ["CP_ROOT"])
+from contrastiveprosthetics_b200 import clip as C, dist as cpdist
+from oracle import clip as OC
+
+class TorchOps:
+    @staticmethod
+    def normalize(x):
+        inv = 1.0 / x.norm(dim=1)
+        return x * inv[:, None], inv
+    @staticmethod
+    def transpose(xhat):
+        n = xhat.shape[0]; ld = (n + 3) // 4 * 4
+        out = torch.zeros(16, ld, dtype=xhat.dtype); out[:, :n] = xhat.t(); return out
+    @staticmethod
+    def _e(own, loop_t, n_loop, scale):
+        return torch.exp(scale * (own @ loop_t[:, :n_loop] - 1.0))
+    @staticmethod
+    def sums(own, loop_t, n_loop, scale, want_argmax):
+        S = own @ loop_t[:, :n_loop]
+        return TorchOps._e(own, loop_t, n_loop, scale).sum(1), (S.argmax(1).to(torch.int32) if want_argmax else None)
+    @staticmethod
+    def loss(ehat, ghat, rowsum, colsum, B, scale, row_arg, row0):
+        n = ehat.shape[0]
+        t = (rowsum.log() + colsum.log() + 2 * scale - 2 * scale * (ehat * ghat).sum(1)).sum() / (2 * B)
+        return t, (row_arg.long() == torch.arange(row0, row0 + n)).sum().to(torch.int32)
+    @staticmethod
+    def grad(own, loop_t, n_loop, scale, own_sum, loop_sum, coef):
+        c = TorchOps._e(own, loop_t, n_loop, scale) * (1.0 / own_sum[:, None] + 1.0 / loop_sum[None, :])
+        return coef * (c @ loop_t[:, :n_loop].t())
+    @staticmethod
+    def embed_backward(d_hat, xhat, other_hat, inv_norm, diag_coef):
+        dh = d_hat - diag_coef * other_hat
+        return (dh - xhat * (xhat * dh).sum(1, keepdim=True)) * inv_norm[:, None]
+
+C._ops = TorchOps
+rank, world, dev = cpdist.init_from_env("gloo")
+n = 5
+g = torch.Generator().manual_seed(0)
+E_all = torch.randn(world * n, 16, generator=g, dtype=torch.float64)
+G_all = torch.randn(world * n, 16, generator=g, dtype=torch.float64) + 0.5 * E_all
+for logit_scale in (0.0, 1.2):
+    E = E_all[rank * n:(rank + 1) * n].clone().requires_grad_(True)
+    G = G_all[rank * n:(rank + 1) * n].clone().requires_grad_(True)
+    loss, ncor, arg = C.clip_head(E, G, logit_scale)
+    loss.backward()
+    ref_loss, dE, dG = OC.clip_loss_sharded(list(E_all.split(n)), list(G_all.split(n)), logit_scale)
+    full = OC.clip_loss(E_all, G_all, logit_scale)
+    assert abs(loss.item() - ref_loss.item()) < 1e-12, (loss.item(), ref_loss.item())
+    assert torch.allclose(E.grad, dE[rank], rtol=1e-10, atol=1e-14)
+    assert torch.allclose(G.grad, dG[rank], rtol=1e-10, atol=1e-14)
+    assert int(ncor) == full["n_correct"]
+    assert torch.equal(arg.long(), full["pred"][rank * n:(rank + 1) * n])
+# gradient SUM (not average) for a loss normalised by the global batch
+p = torch.nn.Parameter(torch.zeros(3)); p.grad = torch.full((3,), float(rank + 1))
+cpdist.FlatGradAllReduce([p], average=False)()
+assert torch.allclose(p.grad, torch.full((3,), 3.0))
+print("rank", rank, "ok")
+'''
+
+
+def test_gloo_clip_head_exchange(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_CLIP_WORKER)
+    env = dict(os.environ, CP_ROOT=ROOT, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29612", str(script)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
