@@ -58,6 +58,18 @@ class EncoderOpts(ctypes.Structure):
                 ("dropout_seed", ctypes.c_uint64), ("ext_masks", ctypes.c_void_p)]
 
 
+class GloveTensors(ctypes.Structure):
+    _fields_ = [("w0", ctypes.c_void_p), ("bn0_w", ctypes.c_void_p), ("bn0_b", ctypes.c_void_p),
+                ("w", ctypes.c_void_p * 3), ("b", ctypes.c_void_p * 3),
+                ("bn_w", ctypes.c_void_p * 3), ("bn_b", ctypes.c_void_p * 3), ("proj_w", ctypes.c_void_p)]
+
+
+class GloveOpts(ctypes.Structure):
+    _fields_ = [("glove_dim", ctypes.c_int32), ("save_for_backward", ctypes.c_int32),
+                ("bn_eps", ctypes.c_float), ("dropout_p", ctypes.c_float),
+                ("dropout_seed", ctypes.c_uint64), ("ext_masks", ctypes.c_void_p)]
+
+
 _lib = None
 _vp, _i64, _i32, _sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_size_t
 
@@ -106,13 +118,18 @@ def lib():
     L.cp_clip_loss.argtypes = [_vp, _vp, _vp, _vp, _i64, _i64, _f, _vp, _i64, _vp, _vp, _vp]
     L.cp_clip_grad.argtypes = [_vp, _i64, _vp, _i64, _i64, _f, _vp, _vp, _f, _vp, _vp]
     L.cp_clip_embed_backward.argtypes = [_vp, _vp, _vp, _vp, _i64, _f, _vp, _vp]
+    L.cp_glove_workspace_bytes.restype = _sz
+    L.cp_glove_workspace_bytes.argtypes = [_i64, ctypes.POINTER(GloveOpts)]
+    L.cp_glove_forward.argtypes = [ctypes.POINTER(GloveTensors), _vp, _i64, _vp, _vp, _sz, ctypes.POINTER(GloveOpts), _vp]
+    L.cp_glove_backward.argtypes = [ctypes.POINTER(GloveTensors), _vp, _i64, ctypes.POINTER(GloveTensors), _vp, _sz,
+                                    ctypes.POINTER(GloveOpts), _vp]
     L.cp_vote_eval.argtypes = [_vp, _i64, _i32, _i32, _vp, _vp, _vp]
     L.cp_rank_rows.argtypes = [_vp, _i64, _vp, _vp]
     L.cp_subset_eval.argtypes = [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp]
     for name in ("cp_gather_norm", "cp_encoder_forward", "cp_encoder_backward", "cp_linear_forward",
                  "cp_linear_backward", "cp_head_forward_backward", "cp_logits_loss", "cp_vote_eval",
                  "cp_rank_rows", "cp_subset_eval", "cp_clip_normalize", "cp_clip_transpose", "cp_clip_sums",
-                 "cp_clip_loss", "cp_clip_grad", "cp_clip_embed_backward"):
+                 "cp_clip_loss", "cp_clip_grad", "cp_clip_embed_backward", "cp_glove_forward", "cp_glove_backward"):
         getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L
@@ -123,7 +140,8 @@ EXPORTS = ["cp_version", "cp_launch_count", "cp_status_string", "cp_gather_norm"
            "cp_linear_forward", "cp_linear_backward", "cp_split_tf32", "cp_linear_forward_planes", "cp_head_workspace_bytes",
            "cp_head_forward_backward", "cp_logits_loss", "cp_vote_eval", "cp_rank_rows",
            "cp_subset_eval", "cp_clip_normalize", "cp_clip_transpose", "cp_clip_sums", "cp_clip_loss",
-           "cp_clip_grad", "cp_clip_embed_backward"]
+           "cp_clip_grad", "cp_clip_embed_backward", "cp_glove_workspace_bytes", "cp_glove_forward",
+           "cp_glove_backward"]
 
 
 def check(status, what=""):

@@ -159,3 +159,135 @@ def clip_head(E, G, logit_scale=0.0, group=None):
     scale = float(math.exp(float(logit_scale)))
     want_grad = torch.is_grad_enabled() and (E.requires_grad or G.requires_grad)
     return _ClipHeadFn.apply(E, G, scale, want_grad, group)
+
+
+# =================================================================================== towers + model
+import ctypes  # noqa: E402
+
+import numpy as np  # noqa: E402
+import torch.nn as nn  # noqa: E402
+
+from .constants import GLOVE_DIM  # noqa: E402
+
+GLOVE_HIDDEN, GLOVE_BLOCKS = 256, 3
+
+
+class GloveTower(nn.Module):
+    """The glove-angle tower the reference keeps commented out (models.py:384-429), with the module
+    indices (and therefore state-dict keys: linear.1, linear.2.bn, linear.{4,8,12}, linear.{6,10,14}.bn,
+    last.0) the block would have had live:
+        Flatten, Linear(glove_dim->256, no bias), BN, ReLU, 3 x [Linear(256->256), ReLU, BN, Dropout];
+        last = Linear(256->d_e, no bias).
+    Parameter container only: forward / backward run in libcpros (cp_glove_forward / cp_glove_backward)."""
+
+    def __init__(self, glove_dim=GLOVE_DIM, d_e=D_E, dp=.5, device="cuda"):
+        super().__init__()
+        from .models import AdaBatchNorm1d
+        if d_e != D_E:
+            raise NotImplementedError("libcpros is built for d_e = 16")
+        self.device = torch.device(device)
+        self.glove_dim, self.d_e, self.dp = glove_dim, d_e, dp
+        blocks = [nn.Flatten(), nn.Linear(glove_dim, GLOVE_HIDDEN, bias=False),
+                  AdaBatchNorm1d(GLOVE_HIDDEN, device=device), nn.ReLU()]
+        for _ in range(GLOVE_BLOCKS):
+            blocks += [nn.Linear(GLOVE_HIDDEN, GLOVE_HIDDEN), nn.ReLU(), AdaBatchNorm1d(GLOVE_HIDDEN, device=device),
+                       nn.Dropout(dp)]
+        self.linear = nn.Sequential(*blocks)
+        self.last = nn.Sequential(nn.Linear(GLOVE_HIDDEN, d_e, bias=False))
+        self.to(self.device)
+        self.dropout_seed = 0x61073
+        self._step = 0
+        self.ext_dropout_masks = None          # (3, n, 256) uint8 keep masks injected by parity tests
+
+    def kernel_params(self):
+        lin = [m for m in self.linear if isinstance(m, nn.Linear)]
+        bns = [m.bn for m in self.linear if hasattr(m, "bn")]
+        return ([lin[0].weight, bns[0].weight, bns[0].bias] + [m.weight for m in lin[1:]] + [m.bias for m in lin[1:]] +
+                [m.weight for m in bns[1:]] + [m.bias for m in bns[1:]] + [self.last[0].weight])
+
+    def forward(self, GLOVE):
+        """(..., glove_dim) -> (n, d_e)."""
+        x = GLOVE.reshape(-1, self.glove_dim)
+        dp = float(self.dp) if self.training else 0.0
+        self._step += 1
+        cfg = {"glove_dim": self.glove_dim, "dropout_p": dp,
+               "seed": (self.dropout_seed * 1000003 + self._step) & 0xFFFFFFFFFFFFFFFF,
+               "ext_masks": self.ext_dropout_masks if dp > 0 else None,
+               "need_bwd": torch.is_grad_enabled() and self.training}
+        return _GloveFn.apply(x, cfg, *self.kernel_params())
+
+    def l2(self):
+        from .models import _l2_of
+        return _l2_of(self)
+
+
+def _fill_glove(struct, t):
+    P = _lib.ptr
+    struct.w0, struct.bn0_w, struct.bn0_b = P(t[0]), P(t[1]), P(t[2])
+    for b in range(GLOVE_BLOCKS):
+        struct.w[b], struct.b[b] = P(t[3 + b]), P(t[6 + b])
+        struct.bn_w[b], struct.bn_b[b] = P(t[9 + b]), P(t[12 + b])
+    struct.proj_w = P(t[15])
+    return struct
+
+
+class _GloveFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cfg, *params):
+        L = _lib.lib()
+        if x.dtype != torch.float32:
+            raise RuntimeError("glove input must be float32")
+        x = x.contiguous()
+        n = x.shape[0]
+        opts = _lib.GloveOpts(glove_dim=cfg["glove_dim"], save_for_backward=int(cfg["need_bwd"]), bn_eps=1e-5,
+                              dropout_p=float(cfg["dropout_p"]), dropout_seed=int(cfg["seed"]),
+                              ext_masks=_lib.ptr(cfg["ext_masks"], torch.uint8))
+        nbytes = L.cp_glove_workspace_bytes(n, ctypes.byref(opts))
+        if nbytes == 0:
+            raise RuntimeError("cp_glove_workspace_bytes rejected the configuration")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        emb = torch.empty((n, D_E), dtype=torch.float32, device=x.device)
+        tens = _fill_glove(_lib.GloveTensors(), params)
+        _lib.check(L.cp_glove_forward(ctypes.byref(tens), _lib.ptr(x), n, _lib.ptr(emb), _lib.ptr(ws), nbytes,
+                                      ctypes.byref(opts), _lib.stream()), "cp_glove_forward")
+        if cfg["need_bwd"]:
+            ctx.ws, ctx.opts, ctx.tens, ctx.n, ctx.params = ws, opts, tens, n, params
+        return emb
+
+    @staticmethod
+    def backward(ctx, d_emb):
+        L = _lib.lib()
+        grads = [torch.empty_like(p) for p in ctx.params]
+        gt = _fill_glove(_lib.GloveTensors(), grads)
+        _lib.check(L.cp_glove_backward(ctypes.byref(ctx.tens), _lib.ptr(d_emb.contiguous()), ctx.n, ctypes.byref(gt),
+                                       _lib.ptr(ctx.ws), ctx.ws.numel(), ctypes.byref(ctx.opts), _lib.stream()),
+                   "cp_glove_backward")
+        ctx.ws = None
+        return (None, None) + tuple(grads)
+
+
+class ClipModel(nn.Module):
+    """Config 5: EMG tower (models.EMGNet, one window per sample) + glove-angle tower, trained with the
+    batch x batch CLIP loss.  `forward(EMG, GLOVE)` -> (emg_emb, glove_emb); `loss(...)` -> global loss."""
+
+    def __init__(self, params, glove_dim=GLOVE_DIM, device="cuda"):
+        super().__init__()
+        from .models import EMGNet
+        self.params = params
+        self.device = torch.device(device)
+        self.emg_net = EMGNet(d_e=params['d_e'], dp=params['dp_emg'], adabn=True, device=device)
+        self.glove_net = GloveTower(glove_dim=glove_dim, d_e=params['d_e'], dp=params['dp_glove'], device=device)
+        self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1) / 0.07, requires_grad=False)   # models.py:81
+        self.to(self.device)
+        self.n_correct = []
+
+    def forward(self, EMG, GLOVE):
+        return self.emg_net.encode_flat(EMG), self.glove_net(GLOVE)
+
+    def loss(self, emg_emb, glove_emb, group=None):
+        loss, ncor, _ = clip_head(emg_emb, glove_emb, float(self.logit_scale), group)
+        self.n_correct.append(ncor)
+        return loss
+
+    def l2(self):
+        return self.glove_net.l2() * self.params['reg_glove'] + self.emg_net.l2() * self.params['reg_emg']

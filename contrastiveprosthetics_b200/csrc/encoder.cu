@@ -155,14 +155,15 @@ int launch_nt(const float* A, int64_t M, int K, int lda, const float* B, int N, 
 // dW[Mo,No] = G^T . A, split over row slabs; out written through wgrad_reduce (mode = re-layout)
 template <int BM, int BN, bool ACONV>
 int launch_wgrad(const float* G, int ldg, int Mo, const float* A, int lda, int No, int64_t R, float* wpart,
-                 float* out, int mode, cudaStream_t st, const float* G_lo = nullptr, const float* A_lo = nullptr) {
+                 float* out, int mode, cudaStream_t st, const float* G_lo = nullptr, const float* A_lo = nullptr,
+                 size_t wpart_elems = WPART_ELEMS) {
     if (Mo % BM != 0 || No % BN != 0) return CP_ERR_ARG;
     const int tiles = (Mo / BM) * (No / BN);
     constexpr int resident = BM * BN >= 128 * 128 ? 2 : 4;      // CTAs per SM the tile shape allows
     int S = (resident * CP_NUM_SMS + tiles - 1) / tiles;        // one full wave of 148 SMs
     const int64_t max_s = cp_cdiv(R, 8 * GEMM_BK);
     if (S > max_s) S = (int)max_s;
-    const int64_t cap = (int64_t)(WPART_ELEMS / ((size_t)Mo * No));
+    const int64_t cap = (int64_t)(wpart_elems / ((size_t)Mo * No));
     if (S > cap) S = (int)cap;
     if (S < 1) S = 1;
     int64_t rps = cp_cdiv(cp_cdiv(R, S), GEMM_BK) * GEMM_BK;
@@ -345,7 +346,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
                               (uint64_t)(l - 3)));
     }
     // projection 512 -> 16
-    proj_fwd_kernel<<<(unsigned)std::min<int64_t>(cp_cdiv(n, 8 * PROJ_RPW), (int64_t)CP_NUM_SMS * 4), 256, 0, st>>>(
+    proj_fwd_kernel<512><<<(unsigned)std::min<int64_t>(cp_cdiv(n, 8 * PROJ_RPW), (int64_t)CP_NUM_SMS * 4), 256, 0, st>>>(
         w.A[CP_N_FC - 1], p->proj_w, emb, n);
     CP_CHECK_LAUNCH();
     return CP_OK;
@@ -365,11 +366,11 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
 
     // projection
     const int Pp = (int)cp_cdiv(n, PROJ_W_ROWS);
-    proj_bwd_weight_kernel<<<Pp, 256, 0, st>>>(d_emb, w.A[CP_N_FC - 1], n, w.ppart);
+    proj_bwd_weight_kernel<512><<<Pp, 256, 0, st>>>(d_emb, w.A[CP_N_FC - 1], n, w.ppart);
     CP_CHECK_LAUNCH();
     colsum_finalize_kernel<<<CP_EMB_DIM * 512 / 32, 1024, 0, st>>>(w.ppart, Pp, CP_EMB_DIM * 512, gr->proj_w, 0);
     CP_CHECK_LAUNCH();
-    proj_bwd_data_kernel<<<(unsigned)std::min<int64_t>(cp_cdiv(n, 8), (int64_t)CP_NUM_SMS * 8), 256, 0, st>>>(
+    proj_bwd_data_kernel<512><<<(unsigned)std::min<int64_t>(cp_cdiv(n, 8), (int64_t)CP_NUM_SMS * 8), 256, 0, st>>>(
         d_emb, p->proj_w, w.G0, n);
     CP_CHECK_LAUNCH();
 
@@ -613,3 +614,5 @@ extern "C" int cp_linear_backward(const float* G, const float* A, const float* W
     }
     return CP_OK;
 }
+
+#include "tower.cuh"

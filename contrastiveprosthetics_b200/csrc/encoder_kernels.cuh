@@ -13,7 +13,7 @@
 template <int F> struct ColMap {
     static constexpr int QX = F / 4;            // float4 column groups
     static constexpr int RY = 256 / QX;         // row lanes per CTA
-    static constexpr int ROWS = F == 512 ? 128 : 1024;   // rows per CTA (64 per thread)
+    static constexpr int ROWS = F == 512 ? 128 : (F == 256 ? 256 : 1024);   // rows per CTA (64 per thread)
 };
 
 // sum over the RY row lanes of a CTA; result for column c valid in threads with ry == 0
@@ -267,11 +267,14 @@ bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, float* __res
 
 // ------------------------------------------------------------------------------- BN backward
 // g' = g * keep/(1-p);  xh = (y - mean)*istd;  partials: sum g', sum g'*xh
+// post != null: the block is Linear -> BN -> ReLU (glove tower block 0, models.py:398-400): `post` is the
+// block output relu(bn(y)), g' = g * 1[post > 0], and no ReLU mask follows the BN backward.
 template <int F>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t R,
                      const uint8_t* __restrict__ keep, float inv_keep, const float* __restrict__ mean,
-                     const float* __restrict__ istd, float* __restrict__ p1, float* __restrict__ p2) {
+                     const float* __restrict__ istd, float* __restrict__ p1, float* __restrict__ p2,
+                     const float* __restrict__ post = nullptr) {
     __shared__ float red[ColMap<F>::RY * F];
     const int qx = threadIdx.x % ColMap<F>::QX, ry = threadIdx.x / ColMap<F>::QX;
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + qx * 4));
@@ -288,6 +291,11 @@ bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, i
             const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(keep) + v);
             gv.x = m.x ? gv.x * inv_keep : 0.f; gv.y = m.y ? gv.y * inv_keep : 0.f;
             gv.z = m.z ? gv.z * inv_keep : 0.f; gv.w = m.w ? gv.w * inv_keep : 0.f;
+        }
+        if (post) {
+            const float4 pv = __ldg(reinterpret_cast<const float4*>(post) + v);
+            gv.x = pv.x > 0.f ? gv.x : 0.f; gv.y = pv.y > 0.f ? gv.y : 0.f;
+            gv.z = pv.z > 0.f ? gv.z : 0.f; gv.w = pv.w > 0.f ? gv.w : 0.f;
         }
         s1[0] += gv.x; s1[1] += gv.y; s1[2] += gv.z; s1[3] += gv.w;
         s2[0] = fmaf(gv.x, (yv.x - mu.x) * is.x, s2[0]);
@@ -328,7 +336,7 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, in
                     const uint8_t* __restrict__ keep, float inv_keep, const float* __restrict__ mean,
                     const float* __restrict__ istd, const float* __restrict__ gamma,
                     const float* __restrict__ m1, const float* __restrict__ m2, float* __restrict__ gz,
-                    float* __restrict__ gz_lo, float* __restrict__ pdb) {
+                    float* __restrict__ gz_lo, float* __restrict__ pdb, const float* __restrict__ post = nullptr) {
     __shared__ float red[ColMap<F>::RY * F];
     const int qx = threadIdx.x % ColMap<F>::QX, ry = threadIdx.x / ColMap<F>::QX;
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + qx * 4));
@@ -350,11 +358,17 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, in
             gv.x = m.x ? gv.x * inv_keep : 0.f; gv.y = m.y ? gv.y * inv_keep : 0.f;
             gv.z = m.z ? gv.z * inv_keep : 0.f; gv.w = m.w ? gv.w * inv_keep : 0.f;
         }
+        const bool pre = post == nullptr;         // ReLU precedes the BN: mask the result with 1[y > 0]
+        if (!pre) {
+            const float4 pv = __ldg(reinterpret_cast<const float4*>(post) + v);
+            gv.x = pv.x > 0.f ? gv.x : 0.f; gv.y = pv.y > 0.f ? gv.y : 0.f;
+            gv.z = pv.z > 0.f ? gv.z : 0.f; gv.w = pv.w > 0.f ? gv.w : 0.f;
+        }
         float4 o;
-        o.x = yv.x > 0.f ? k0 * (gv.x - a1.x - (yv.x - mu.x) * is.x * a2.x) : 0.f;
-        o.y = yv.y > 0.f ? k1 * (gv.y - a1.y - (yv.y - mu.y) * is.y * a2.y) : 0.f;
-        o.z = yv.z > 0.f ? k2 * (gv.z - a1.z - (yv.z - mu.z) * is.z * a2.z) : 0.f;
-        o.w = yv.w > 0.f ? k3 * (gv.w - a1.w - (yv.w - mu.w) * is.w * a2.w) : 0.f;
+        o.x = (!pre || yv.x > 0.f) ? k0 * (gv.x - a1.x - (yv.x - mu.x) * is.x * a2.x) : 0.f;
+        o.y = (!pre || yv.y > 0.f) ? k1 * (gv.y - a1.y - (yv.y - mu.y) * is.y * a2.y) : 0.f;
+        o.z = (!pre || yv.z > 0.f) ? k2 * (gv.z - a1.z - (yv.z - mu.z) * is.z * a2.z) : 0.f;
+        o.w = (!pre || yv.w > 0.f) ? k3 * (gv.w - a1.w - (yv.w - mu.w) * is.w * a2.w) : 0.f;
         if (SPLIT) {
             float4 h, l;
             split_tf32(o, h, l);
@@ -406,32 +420,34 @@ colsum_rows_kernel(const float* __restrict__ G, int64_t M, int N, float* __restr
 // One warp per 4 rows: each lane owns 16 k-values of every row, the weight slice is read from shared
 // memory once per 4 rows, and the 16 outputs are reduced across the warp with a halving butterfly.
 #define PROJ_RPW 4
+template <int K>
 __global__ void __launch_bounds__(256)
 proj_fwd_kernel(const float* __restrict__ a, const float* __restrict__ Wp, float* __restrict__ emb, int64_t R) {
-    __shared__ __align__(16) float W[CP_EMB_DIM][512];
-    for (int e = threadIdx.x; e < CP_EMB_DIM * 512 / 4; e += 256)
+    constexpr int JN = K / 128;                     // float4 chunks per lane
+    __shared__ __align__(16) float W[CP_EMB_DIM][K];
+    for (int e = threadIdx.x; e < CP_EMB_DIM * K / 4; e += 256)
         reinterpret_cast<float4*>(&W[0][0])[e] = __ldg(reinterpret_cast<const float4*>(Wp) + e);
     __syncthreads();
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     for (int64_t r0 = ((int64_t)blockIdx.x * 8 + warp) * PROJ_RPW; r0 < R; r0 += (int64_t)gridDim.x * 8 * PROJ_RPW) {
-        float4 x[PROJ_RPW][4];
+        float4 x[PROJ_RPW][JN];
 #pragma unroll
         for (int i = 0; i < PROJ_RPW; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                x[i][j] = (r0 + i < R) ? __ldg(reinterpret_cast<const float4*>(a + (r0 + i) * 512) + lane + 32 * j)
+            for (int j = 0; j < JN; ++j)
+                x[i][j] = (r0 + i < R) ? __ldg(reinterpret_cast<const float4*>(a + (r0 + i) * K) + lane + 32 * j)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
         float acc[PROJ_RPW][CP_EMB_DIM];
 #pragma unroll
         for (int o = 0; o < CP_EMB_DIM; ++o) {
-            float4 w[4];
+            float4 w[JN];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(&W[o][(lane + 32 * j) * 4]);
+            for (int j = 0; j < JN; ++j) w[j] = *reinterpret_cast<const float4*>(&W[o][(lane + 32 * j) * 4]);
 #pragma unroll
             for (int i = 0; i < PROJ_RPW; ++i) {
                 float s = 0.f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < JN; ++j) {
                     s = fmaf(x[i][j].x, w[j].x, s); s = fmaf(x[i][j].y, w[j].y, s);
                     s = fmaf(x[i][j].z, w[j].z, s); s = fmaf(x[i][j].w, w[j].w, s);
                 }
@@ -458,13 +474,15 @@ proj_fwd_kernel(const float* __restrict__ a, const float* __restrict__ Wp, float
 }
 
 // ga[r,k] = sum_o d[r,o] * Wp[o,k]
+template <int K>
 __global__ void __launch_bounds__(256)
 proj_bwd_data_kernel(const float* __restrict__ d, const float* __restrict__ Wp, float* __restrict__ ga, int64_t R) {
-    const int q = threadIdx.x % 128, rl = threadIdx.x / 128;
+    constexpr int KQ = K / 4, RL = 256 / KQ;        // float4 columns, row lanes per CTA
+    const int q = threadIdx.x % KQ, rl = threadIdx.x / KQ;
     float4 w[CP_EMB_DIM];
 #pragma unroll
-    for (int o = 0; o < CP_EMB_DIM; ++o) w[o] = __ldg(reinterpret_cast<const float4*>(Wp + o * 512) + q);
-    for (int64_t r0 = ((int64_t)blockIdx.x * 2 + rl) * 4; r0 < R; r0 += (int64_t)gridDim.x * 8) {
+    for (int o = 0; o < CP_EMB_DIM; ++o) w[o] = __ldg(reinterpret_cast<const float4*>(Wp + o * K) + q);
+    for (int64_t r0 = ((int64_t)blockIdx.x * RL + rl) * 4; r0 < R; r0 += (int64_t)gridDim.x * RL * 4) {
         float4 dv[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -484,29 +502,31 @@ proj_bwd_data_kernel(const float* __restrict__ d, const float* __restrict__ Wp, 
                 o4.x = fmaf(dd[o], w[o].x, o4.x); o4.y = fmaf(dd[o], w[o].y, o4.y);
                 o4.z = fmaf(dd[o], w[o].z, o4.z); o4.w = fmaf(dd[o], w[o].w, o4.w);
             }
-            reinterpret_cast<float4*>(ga + (r0 + i) * 512)[q] = o4;
+            reinterpret_cast<float4*>(ga + (r0 + i) * K)[q] = o4;
         }
     }
 }
 
 // dWp[o,k] partial over a slab of rows: partial[blk][o*512 + k]
 #define PROJ_W_ROWS 256
+template <int K>
 __global__ void __launch_bounds__(256)
 proj_bwd_weight_kernel(const float* __restrict__ d, const float* __restrict__ a, int64_t R,
                        float* __restrict__ partial) {
-    __shared__ float4 red[128];
-    const int q = threadIdx.x % 128, rl = threadIdx.x / 128;
+    constexpr int KQ = K / 4, RL = 256 / KQ;        // float4 columns, row lanes per CTA
+    __shared__ float4 red[RL][KQ];
+    const int q = threadIdx.x % KQ, rl = threadIdx.x / KQ;
     float4 acc[CP_EMB_DIM];
 #pragma unroll
     for (int o = 0; o < CP_EMB_DIM; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t r0 = (int64_t)blockIdx.x * PROJ_W_ROWS;
-    for (int k = rl * 4; k < PROJ_W_ROWS; k += 8) {          // 4 rows in flight per thread
+    for (int k = rl * 4; k < PROJ_W_ROWS; k += RL * 4) {     // 4 rows in flight per thread
         float4 x[4], dv[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int64_t r = r0 + k + i;
             const bool ok = r < R;
-            x[i] = ok ? __ldg(reinterpret_cast<const float4*>(a + r * 512) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[i] = ok ? __ldg(reinterpret_cast<const float4*>(a + r * K) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 dv[i][j] = ok ? __ldg(reinterpret_cast<const float4*>(d + r * CP_EMB_DIM) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -523,16 +543,20 @@ proj_bwd_weight_kernel(const float* __restrict__ d, const float* __restrict__ a,
             }
         }
     }
-    float* out = partial + (int64_t)blockIdx.x * CP_EMB_DIM * 512;
+    float* out = partial + (int64_t)blockIdx.x * CP_EMB_DIM * K;
 #pragma unroll
     for (int o = 0; o < CP_EMB_DIM; ++o) {
         __syncthreads();
-        if (rl == 1) red[q] = acc[o];
+        red[rl][q] = acc[o];
         __syncthreads();
         if (rl == 0) {
-            const float4 t = red[q];
-            reinterpret_cast<float4*>(out + o * 512)[q] =
-                make_float4(acc[o].x + t.x, acc[o].y + t.y, acc[o].z + t.z, acc[o].w + t.w);
+            float4 t = acc[o];
+#pragma unroll
+            for (int l = 1; l < RL; ++l) {
+                const float4 u = red[l][q];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            reinterpret_cast<float4*>(out + o * K)[q] = t;
         }
     }
 }

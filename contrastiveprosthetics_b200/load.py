@@ -65,10 +65,10 @@ class DB23(data.Dataset):
         self.glover.GLOVE = None if glove is None else glove.to(self.device, torch.float32)
         self.GLOVE = self.glover.GLOVE
 
-    def load_synthetic(self, seed=0, with_glove=True):
+    def load_synthetic(self, seed=0, with_glove=True, glove_dim=20):
         """Seeded NinaPro-shaped stand-in (the dataset download is unavailable offline)."""
         from .synthetic import synth_emg, synth_glove
-        self.load_tensors(synth_emg(seed), synth_glove(seed + 1) if with_glove else None)
+        self.load_tensors(synth_emg(seed), synth_glove(seed + 1, glove_dim, class_offset=glove_dim != 20) if with_glove else None)
 
     # ---- masks (load.py:157-203)
     @property

@@ -16,9 +16,12 @@ def synth_emg(seed=0, people=46):
     return emg + off[None, :, None, None, :]
 
 
-def synth_glove(seed=1, dim=20):
+def synth_glove(seed=1, dim=20, class_offset=False):
+    """dim = 20 (GLOVE_DIM, constants.py:96) or 22 (all CyberGlove sensors, config 5).  class_offset adds
+    a per-class posture offset so that glove rows are informative about the class (config 5)."""
     g = torch.Generator().manual_seed(seed)
-    return torch.randn(41, 5850, dim, generator=g)
+    x = torch.randn(41, 5850, dim, generator=g)
+    return x + torch.randn(41, 1, dim, generator=g) if class_offset else x
 
 
 def fixed_perm(T, D, seed):

@@ -159,6 +159,21 @@ class TaskWrapper:
             GLOVE = torch.zeros((B, self.dataset.TASKS, GLOVE_DIM), device=self.device)
         return EMG, GLOVE, self._labels(B)
 
+    def get_flat_batch(self, start, n):
+        """Flat sampling of the batch x batch variant (utils.py:56-59, commented in the reference): `n`
+        consecutive entries of the epoch's flat row permutation `self.idx` -> one window per sample,
+        label = row // D, and a glove row of the SAME class.  Returns (EMG (n,1,1,12), GLOVE (n,dim), label (n,))."""
+        rows = self.idx[start:start + n]
+        D = self.dataset.D
+        label = rows // D
+        EMG = self.dataset.slice_batch(rows)
+        gl = self.dataset.glover
+        if gl.GLOVE_use is not None:
+            GLOVE = gl[label * gl.D + (rows % D) % gl.D]
+        else:
+            GLOVE = torch.zeros((rows.numel(), GLOVE_DIM), device=self.device)
+        return EMG, GLOVE, label
+
     def batches(self, batch_size, shuffle=True, generator=None, rank=0, world_size=1):
         """Equivalent of `DataLoader(self, batch_size, shuffle)` (train.py:86): a permutation of the
         D items cut into batches (last one ragged).  With world_size > 1 every rank draws the same

@@ -173,6 +173,40 @@ int cp_clip_grad(const float *own, int64_t n_own, const float *loop_t, int64_t n
 int cp_clip_embed_backward(const float *d_hat, const float *xhat, const float *other_hat,
                            const float *inv_norm, int64_t n, float diag_coef, float *dx, void *stream);
 
+/* ---------------------------------------------------------------- K2': glove-angle tower (config 5)
+ * The tower the reference keeps commented out (models.py:384-429):
+ *   glove (n,glove_dim) -> Linear(glove_dim->256, no bias) -> BN -> ReLU
+ *                       -> 3 x [Linear(256->256) -> ReLU -> BN -> Dropout] -> Linear(256->16, no bias)
+ * Batch statistics (AdaBN, models.py:17-25) only.  Same conventions as the EMG encoder entry points. */
+#define CP_GLOVE_HIDDEN 256
+#define CP_GLOVE_BLOCKS 3
+typedef struct cp_glove_tensors {
+    float *w0;                          /* (256, glove_dim)  glove_net.linear.1.weight */
+    float *bn0_w, *bn0_b;               /* (256)             glove_net.linear.2.bn.*   */
+    float *w[CP_GLOVE_BLOCKS];          /* (256,256)         glove_net.linear.{4,8,12}.weight */
+    float *b[CP_GLOVE_BLOCKS];          /* (256)                                        .bias */
+    float *bn_w[CP_GLOVE_BLOCKS];       /* (256)             glove_net.linear.{6,10,14}.bn.*  */
+    float *bn_b[CP_GLOVE_BLOCKS];
+    float *proj_w;                      /* (16,256)          glove_net.last.0.weight   */
+} cp_glove_tensors;
+
+typedef struct cp_glove_opts {
+    int32_t glove_dim;                  /* 20 (constants.py:96) or 22 (all sensors); <= 64 */
+    int32_t save_for_backward;
+    float bn_eps;                       /* 1e-5 */
+    float dropout_p;                    /* after each of the 3 blocks; 0 = off */
+    uint64_t dropout_seed;
+    const uint8_t *ext_masks;           /* optional 3 x (n,256) {0,1} keep masks (parity tests) */
+} cp_glove_opts;
+
+size_t cp_glove_workspace_bytes(int64_t n, const cp_glove_opts *opts);
+int cp_glove_forward(const cp_glove_tensors *params, const float *glove, int64_t n, float *emb,
+                     void *workspace, size_t workspace_bytes, const cp_glove_opts *opts, void *stream);
+/* every grad tensor is OVERWRITTEN; must follow a cp_glove_forward(save_for_backward=1) on the workspace */
+int cp_glove_backward(const cp_glove_tensors *params, const float *d_emb, int64_t n,
+                      const cp_glove_tensors *grads, void *workspace, size_t workspace_bytes,
+                      const cp_glove_opts *opts, void *stream);
+
 /* ---------------------------------------------------------------- K4: windowed majority vote
  * Replaces the vote loop of contrastive_loopy_loss (models.py:149-163, constants.py:74-78).
  * pred: (B,W,41) int32.  votes: (B,n_votes) int32 = #rows whose prefix-mode over the first

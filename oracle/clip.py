@@ -72,11 +72,13 @@ def glove_init_state(seed=7, glove_dim=20, d_e=16):
     return sd
 
 
-def glove_forward(sd, glove, dp=0.0, dropout_masks=None, relu_masks=None):
+def glove_forward(sd, glove, dp=0.0, dropout_masks=None, relu_masks=None, taps=None):
     """glove (n, glove_dim) -> (n, d_e).  AdaBN semantics (batch statistics, models.py:17-25).
     dropout_masks: 3 x (n, 256) keep masks (scaled by 1/(1-dp)) or None.  relu_masks: optional list of
     4 boolean (n,256) patterns imposed on the ReLUs (kink-controlled gradient tests)."""
     def relu(x, i):
+        if taps is not None:
+            taps.append(x.detach())              # ReLU inputs (how close the kinks are)
         if relu_masks is not None and relu_masks[i] is not None:
             return x * relu_masks[i].to(x.dtype)
         return F.relu(x)
