@@ -349,6 +349,133 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- config 5 (CLIP) arm
+def run_c5(args):
+    """BASELINE.json config 5: glove-angle (22-dim) tower + EMG tower, batch x batch CLIP loss, GLOBAL batch
+    65,536 sharded over the ranks (strong scaling): all-gather of the glove embeddings, all-reduce of the
+    column sums, reduce-scatter of the glove-embedding gradients, one flat parameter-gradient all-reduce."""
+    import torch.distributed as dist
+    from contrastiveprosthetics_b200 import _lib, dist as cpdist
+    from contrastiveprosthetics_b200.clip import ClipModel
+    from contrastiveprosthetics_b200.load import DB23
+    from contrastiveprosthetics_b200.utils import TaskWrapper
+
+    rank, world, dev = cpdist.init_from_env()
+    assert dev.type == "cuda", "bench.py needs a GPU (no CPU fallback)"
+    L = _lib.lib()
+    B = args.clip_batch
+    n = B // world
+    torch.manual_seed(42)
+    model = ClipModel(dict(PARAMS), glove_dim=22, device=str(dev))
+    model.train()
+    opt_e = torch.optim.Adam(model.emg_net.parameters(), lr=PARAMS['lr_emg'], weight_decay=0)
+    opt_g = torch.optim.Adam(model.glove_net.parameters(), lr=PARAMS['lr_glove'], weight_decay=0)
+    sync_grads = cpdist.FlatGradAllReduce(list(model.emg_net.parameters()) + list(model.glove_net.parameters()),
+                                          average=False)
+    ds = DB23(db2=True, device=dev)
+    ds.load_synthetic(with_glove=True, glove_dim=22)
+    tw = TaskWrapper(ds, with_glove=True)
+    tw.set_train()
+    tw.idx = torch.randperm(tw.TASKS * tw.D, generator=torch.Generator().manual_seed(5)).to(dev)   # same on every rank
+    n_batches = (tw.TASKS * tw.D) // B
+    it = {"i": 0}
+
+    def train_on(EMG, GLOVE):
+        e, g = model(EMG, GLOVE)
+        loss = model.loss(e, g)
+        total = loss + model.l2()
+        opt_e.zero_grad(set_to_none=True)
+        opt_g.zero_grad(set_to_none=True)
+        total.backward()
+        sync_grads()
+        opt_e.step()
+        opt_g.step()
+        return loss
+
+    def resident_step():
+        it["i"] += 1
+        start = (it["i"] % n_batches) * B + rank * n
+        EMG, GLOVE, _ = tw.get_flat_batch(start, n)
+        train_on(EMG, GLOVE)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        model.n_correct.clear()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.cp_launch_count()
+        with ClockSampler(dev.index or 0) as cs:
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), cs.summary(), L.cp_launch_count() - l0
+
+    ms, clocks, launches = timed(resident_step, args.steps, args.warmup)
+
+    host = []
+    for i in range(3):
+        EMG, GLOVE, _ = tw.get_flat_batch(i * B + rank * n, n)
+        host.append((EMG.cpu().pin_memory(), GLOVE.cpu().pin_memory()))
+    sink = {}
+
+    def e2e_step():
+        it["i"] += 1
+        hE, hG = host[it["i"] % len(host)]
+        loss = train_on(hE.to(dev, non_blocking=True), hG.to(dev, non_blocking=True))
+        sink["loss"] = loss.item()
+        sink["ncor"] = int(model.n_correct[-1].item())
+
+    ms_e2e, _, _ = timed(e2e_step, max(3, args.steps // 2), 2)
+
+    # the head alone at this rank's strip (n x B): 2 sums + 2 gradient sweeps; algorithmic fp32 FLOPs =
+    # 2*16 per pair for the similarity in each of the 4 sweeps + 2*16 per pair in each gradient sweep
+    from contrastiveprosthetics_b200 import clip as C
+    E = torch.randn(n, 16, device=dev, requires_grad=True)
+    G = torch.randn(n, 16, device=dev, requires_grad=True)
+
+    def head_only():
+        E.grad = G.grad = None
+        C.clip_head(E, G, 0.0)[0].backward()
+
+    ms_head, _, _ = timed(head_only, 5, 2)
+    pairs = float(n) * float(B)
+    head_flops = pairs * 32.0 * 6
+    if rank == 0:
+        line = {
+            "metric": "train sEMG windows/s", "value": B / (ms / 1e3), "unit": "windows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C5: glove-angle (22-dim) tower + EMG tower, CLIP batch x batch loss, global batch {B} "
+                                   f"({n} samples per GPU), AdaBN (rank-local statistics), dropout 0.5, fp32",
+                       "global_batch": B, "parallelism": f"dp{world}: all-gather Ghat, all-reduce column sums, "
+                       "reduce-scatter d Ghat, one flat grad all-reduce (sum)",
+                       "l2_policy": "activation stream of the towers >> 126 MB L2; no explicit flush"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": B / (ms_e2e / 1e3), "unit": "windows/s",
+                    "h2d_bytes_per_step": int(host[0][0].numel() * 4 + host[0][1].numel() * 4),
+                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e},
+            "clip_head": {"ms": ms_head, "pairs_per_s": pairs / (ms_head / 1e3),
+                          "fp32_tflops": head_flops / (ms_head * 1e-3) / 1e12,
+                          "kernel": "clip_sweep_kernel (fp32 FFMA + MUFU.EX2; B x B never materialised)",
+                          "note": "bound by the fp32 FMA pipe, not HBM (inputs 8 MB) and not the tensor pipe (K = 16)"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -360,9 +487,14 @@ def main():
                     help="only the device-resident train steps (for ncu launch lists); prints a reduced line")
     ap.add_argument("--engine", default="tc", choices=["tc", "simt"],
                     help="tc: tcgen05 3xTF32 GEMMs (default); simt: fp32 FFMA GEMMs")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2: the headline train step (default); c5: glove CLIP batch x batch variant, global batch sharded")
+    ap.add_argument("--clip_batch", type=int, default=65536, help="global batch of --workload c5")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_cuda(args)
 

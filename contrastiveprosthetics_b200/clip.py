@@ -87,6 +87,8 @@ _ops = _CudaOps        # host-logic tests (gloo, CPU) substitute a test double; 
 
 
 def _world(group):
+    if group == "local":                       # force the single-process path inside a distributed job
+        return 1, 0
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size(group), dist.get_rank(group)
     return 1, 0
