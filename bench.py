@@ -158,12 +158,15 @@ def run_cuda(args):
     opt_e = torch.optim.Adam(model.emg_net.parameters(), lr=PARAMS['lr_emg'], weight_decay=0)
     opt_g = torch.optim.Adam(model.glove_net.parameters(), lr=PARAMS['lr_glove'], weight_decay=0)
     sync_grads = cpdist.FlatGradAllReduce(list(model.emg_net.parameters()) + list(model.glove_net.parameters()))
-    ds = DB23(db2=True, device=dev)
+    # N = 1: DB2-shaped (config C2).  N > 1: DB2 + DB3 subjects mixed, the 6 DB3 subjects 11-channel (config C3)
+    mixed = world > 1 or args.mixed
+    ds = DB23(db2=True, device=dev, mixed=mixed)
     ds.load_synthetic(with_glove=False)
     tw = TaskWrapper(ds, with_glove=False)
     tw.set_train()
     model.set_train()
     gen = torch.Generator().manual_seed(1234)
+    gen_rank = torch.Generator().manual_seed(4321 + rank)
 
     def step_resident(items):
         EMG, GLOVE, label = tw.get_batch(items)
@@ -179,10 +182,13 @@ def run_cuda(args):
         return loss
 
     def draw_items():
-        # every rank draws the same global batch and takes its slice (sample sharding)
-        order = torch.randperm(tw.D, generator=gen)[:min(B * world, tw.D)]
-        per = order.numel() // world
-        return order[rank * per:(rank + 1) * per].to(dev)
+        # sample sharding: every rank draws the same global batch and takes its slice.  When the global batch
+        # exceeds the D items of one epoch (mixed subjects: D = 13,800 < 8 x 4096) every rank draws its own
+        # B items instead, so the per-GPU batch stays B (weak scaling)
+        if B * world <= tw.D:
+            order = torch.randperm(tw.D, generator=gen)[:B * world]
+            return order[rank * B:(rank + 1) * B].to(dev)
+        return torch.randperm(tw.D, generator=gen_rank)[:B].to(dev)
 
     def barrier():
         if world > 1:
@@ -329,8 +335,11 @@ def run_cuda(args):
             "metric": "train sEMG windows/s", "value": value, "unit": "windows/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: train step, batch_size 4096 groups x 41 windows = 167,936 windows "
-                                   "per GPU per step, AdaBN on, dropout 0.5, fp32, DB2-shaped synthetic sEMG",
+            "config": {"workload": ("C3: sample-sharded train step, " if world > 1 else "C2: train step, ") +
+                                   f"batch_size {B} groups x 41 windows = {N} windows per GPU per step, AdaBN on, "
+                                   "dropout 0.5, fp32, " +
+                                   ("DB2+DB3 mixed-subject synthetic sEMG (46 subjects, DB3 subjects 11-channel)"
+                                    if mixed else "DB2-shaped synthetic sEMG"),
                        "batch_size_groups_per_gpu": B, "windows_per_step": N * world,
                        "engine": "simt-fp32" if model.emg_net.engine == 0 else "tcgen05-3xtf32",
                        "parallelism": f"dp{world} (sample-sharded, local BatchNorm, one flat grad all-reduce)",
@@ -487,6 +496,7 @@ def main():
                     help="only the device-resident train steps (for ncu launch lists); prints a reduced line")
     ap.add_argument("--engine", default="tc", choices=["tc", "simt"],
                     help="tc: tcgen05 3xTF32 GEMMs (default); simt: fp32 FFMA GEMMs")
+    ap.add_argument("--mixed", action="store_true", help="mixed DB2+DB3 subjects also at N = 1 (default at N > 1)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
                     help="c2: the headline train step (default); c5: glove CLIP batch x batch variant, global batch sharded")
     ap.add_argument("--clip_batch", type=int, default=65536, help="global batch of --workload c5")

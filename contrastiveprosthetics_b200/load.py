@@ -15,12 +15,15 @@ from .utils import Glover, default_device, gather_rows
 
 
 class DB23(data.Dataset):
-    def __init__(self, db2=False, train=True, val=False, device=None, emg_stats=None):
+    def __init__(self, db2=False, train=True, val=False, device=None, emg_stats=None, mixed=False):
         self.device = torch.device(device) if device is not None else default_device()
         self.train = train
         self.val = val
         self.raw = False
-        self.db2 = db2
+        self.db2 = db2 and not mixed
+        # mixed (BASELINE.json config 3; the reference picks DB2 OR DB3, load.py:179-183): all 46 subjects with
+        # the DB3 repetition split; the 6 DB3 amputee subjects are 11-channel, their channel 10 is zeroed
+        self.mixed = mixed
         self.emg_stats = emg_stats          # RunningStats -> normalise inside the gather kernel
 
         dev = lambda x: torch.from_numpy(np.array(x)).to(self.device)      # noqa: E731  (torchize, utils.py:18)
@@ -77,6 +80,8 @@ class DB23(data.Dataset):
 
     @property
     def people_mask(self):
+        if self.mixed:
+            return torch.cat((self._d2, self._d3))
         return self._d2 if self.db2 else self._d3
 
     @property
@@ -116,6 +121,8 @@ class DB23(data.Dataset):
             raise RuntimeError("no data: call load_stored(), load_tensors() or load_synthetic() first")
         sub = self.EMG[self.tasks_mask][:, self.people_mask][:, :, self.rep_mask][:, :, :, :WINDOW_OUTPUT_DIM]
         sub = sub.contiguous()
+        if self.mixed:
+            sub[:, self.people_mask >= len(self._d2), :, :, EMG_DIM - 2] = 0       # load.py:269-272 (commented there)
         self.EMG_use = sub.reshape(-1, EMG_DIM)
         self.tensor = sub.reshape(-1, self.OUTPUT_DIM, EMG_DIM)
         self._rows2d = self.tensor.reshape(self.tensor.shape[0], -1)       # (41*D, 25*12) in eval

@@ -168,7 +168,7 @@ def main(a):
     args = a
     rank, world, device = cpdist.init_from_env()
     np.random.seed(42)                       # train.py:22: the hyper-parameter draws depend on it
-    dataset23 = DB23(db2=args.db2, device=device)
+    dataset23 = DB23(db2=args.db2, device=device, mixed=getattr(args, "mixed", False))
     print("Loading dataset")
     if args.synthetic:
         dataset23.load_synthetic()
@@ -229,6 +229,8 @@ def build_parser():
     # --- additions (plumbing only)
     parser.add_argument('--synthetic', action='store_true', help='seeded NinaPro-shaped data instead of emg.pt')
     parser.add_argument('--item_loader', action='store_true', help="reference-style per-item DataLoader")
+    parser.add_argument('--mixed', action='store_true',
+                        help='DB2 + DB3 subjects mixed (46 people, DB3 repetition split, DB3 channel 10 zeroed)')
     parser.add_argument('--data_dir', default="../data/")
     parser.add_argument('--checkpoint_dir', default="../checkpoints/")
     return parser

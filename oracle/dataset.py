@@ -34,11 +34,16 @@ def ref_constants():
     }
 
 
-def masks(db2, split):
-    """load.py:157-203: (tasks_mask, people_mask, rep_mask) for split in train/val/test."""
+def masks(db2, split, mixed=False):
+    """load.py:157-203: (tasks_mask, people_mask, rep_mask) for split in train/val/test.
+    mixed (BASELINE.json config 3; not in the reference, which selects DB2 OR DB3 at load.py:179-183):
+    all 46 people with the DB3 repetition split."""
     c = ref_constants()
     tasks = np.concatenate((c["TASKS"].astype(np.int64), [0]))       # label 40 = rest (stimulus 0)
     people = c["d2_idxs"] if db2 else c["d3_idxs"] + 40
+    if mixed:
+        people = np.concatenate((c["d2_idxs"], c["d3_idxs"] + 40))
+        db2 = False
     if split == "train":
         rep = np.concatenate((c["rep_train"], c["rep_test"])) if db2 else c["rep_train"]
     elif split == "val":
@@ -48,7 +53,7 @@ def masks(db2, split):
     return tasks, people.astype(np.int64), rep.astype(np.int64)
 
 
-def load_valid(EMG, db2, split):
+def load_valid(EMG, db2, split, mixed=False):
     """load.py:233-251.  EMG: (41 stimuli, 46 people, 6 reps, 100, 12) float32.
 
     Returns (EMG_use (41*D*W? see below), tensor, D):
@@ -56,8 +61,13 @@ def load_valid(EMG, db2, split):
       val/test: tensor (41*D, 25, 12) with D = P*R*4.
     Row id = label*D + k (class-major, load.py:242-249).
     """
-    t, p, r = masks(db2, split)
+    t, p, r = masks(db2, split, mixed)
     sub = EMG[t][:, p][:, :, r][:, :, :, :OUT_DIM]
+    if mixed:
+        # the 6 DB3 (amputee) subjects are 11-channel recordings: channel index 10 carries no signal
+        # (the reference's only trace of this is the commented `EMG[:, :, :, -2] = 0`, load.py:269-272)
+        sub = sub.copy() if isinstance(sub, np.ndarray) else sub.clone()
+        sub[:, p >= 40, :, :, EMG_DIM - 2] = 0
     EMG_use = sub.reshape(-1, EMG_DIM)
     P, R = len(p), len(r)
     if split == "train":

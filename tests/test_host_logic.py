@@ -45,6 +45,26 @@ def test_db23_splits_match_reference(gd, emg, db2):
         assert np.array_equal(ds.tensor[gd[tag + "_trows"]].numpy(), gd[tag + "_tensor"])
 
 
+def test_db23_mixed_subjects_split(emg):
+    """Config 3: DB2 + DB3 subjects mixed (46 people, DB3 repetition split); the 6 DB3 subjects are
+    11-channel (channel 10 zeroed).  Checked against the oracle restatement."""
+    from oracle import dataset as OD
+    ds = DB23(mixed=True, device="cpu")
+    ds.load_tensors(emg)
+    E = emg.transpose(0, 1).numpy()
+    for split, D in (("train", 46 * 3 * 100), ("val", 46 * 1 * 4), ("test", 46 * 2 * 4)):
+        getattr(ds, "set_" + split)()
+        assert ds.D == D and ds.PEOPLE == 46 and len(TaskWrapper(ds)) == D
+        use, tensor, D0 = OD.load_valid(E, False, split, mixed=True)
+        assert D0 == D
+        assert np.array_equal(ds.EMG_use.numpy(), use)
+        assert np.array_equal(ds.tensor.numpy(), tensor)
+    ds.set_train()
+    rows = ds.EMG_use.reshape(41, 46, 3, 100, 12)
+    assert float(rows[:, 40:, :, :, 10].abs().max()) == 0.0 and float(rows[:, :40, :, :, 10].abs().min()) > 0.0
+    assert float(rows[:, 40:, :, :, 11].abs().min()) > 0.0
+
+
 def test_no_cpu_fallback(emg):
     """Indexing is the CUDA gather; on CPU tensors it must raise, not silently index with torch."""
     ds = DB23(db2=False, device="cpu")
