@@ -155,6 +155,7 @@ def run_cuda(args):
     torch.manual_seed(42)
     model = Model(dict(PARAMS), adabn=True, device=str(dev))
     model.emg_net.engine = _lib.ENGINE_TC if args.engine == "tc" else _lib.ENGINE_SIMT
+    model.emg_net.sync_bn = args.sync_bn
     opt_e = torch.optim.Adam(model.emg_net.parameters(), lr=PARAMS['lr_emg'], weight_decay=0)
     opt_g = torch.optim.Adam(model.glove_net.parameters(), lr=PARAMS['lr_glove'], weight_decay=0)
     sync_grads = cpdist.FlatGradAllReduce(list(model.emg_net.parameters()) + list(model.glove_net.parameters()))
@@ -342,7 +343,8 @@ def run_cuda(args):
                                     if mixed else "DB2-shaped synthetic sEMG"),
                        "batch_size_groups_per_gpu": B, "windows_per_step": N * world,
                        "engine": "simt-fp32" if model.emg_net.engine == 0 else "tcgen05-3xtf32",
-                       "parallelism": f"dp{world} (sample-sharded, local BatchNorm, one flat grad all-reduce)",
+                       "parallelism": f"dp{world} (sample-sharded, " + ("SyncBN" if args.sync_bn and world > 1 else "local BatchNorm")
+                                      + ", one flat grad all-reduce)",
                        "l2_policy": "per-step working set ~8 GB of activations >> 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(h2d),
@@ -496,6 +498,7 @@ def main():
                     help="only the device-resident train steps (for ncu launch lists); prints a reduced line")
     ap.add_argument("--engine", default="tc", choices=["tc", "simt"],
                     help="tc: tcgen05 3xTF32 GEMMs (default); simt: fp32 FFMA GEMMs")
+    ap.add_argument("--sync_bn", action="store_true", help="N > 1: BatchNorm statistics over every rank's rows")
     ap.add_argument("--mixed", action="store_true", help="mixed DB2+DB3 subjects also at N = 1 (default at N > 1)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
                     help="c2: the headline train step (default); c5: glove CLIP batch x batch variant, global batch sharded")

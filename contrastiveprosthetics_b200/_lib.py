@@ -55,7 +55,12 @@ class EncoderOpts(ctypes.Structure):
     _fields_ = [("bn_mode", ctypes.c_int32), ("engine", ctypes.c_int32),
                 ("bn_momentum", ctypes.c_float), ("bn_eps", ctypes.c_float),
                 ("dropout_p", ctypes.c_float), ("save_for_backward", ctypes.c_int32),
-                ("dropout_seed", ctypes.c_uint64), ("ext_masks", ctypes.c_void_p)]
+                ("dropout_seed", ctypes.c_uint64), ("ext_masks", ctypes.c_void_p),
+                ("allreduce", ctypes.c_void_p), ("allreduce_user", ctypes.c_void_p)]
+
+
+# int (*cp_allreduce_fn)(void *user, void *buf, size_t count, void *stream)   (SyncBN hook, include/cpros.h)
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
 
 
 class GloveTensors(ctypes.Structure):

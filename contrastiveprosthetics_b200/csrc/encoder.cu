@@ -38,6 +38,7 @@ struct Ws {
     float *mean[CP_N_BN], *istd[CP_N_BN], *scale[CP_N_BN], *shift[CP_N_BN];
     float *pa, *pb;            // per-CTA column partials
     float *m1, *m2;
+    double* totals;            // [2*512 + 1] SyncBN: rank-local column totals + row count, all-reduced in place
     double* rscratch;          // [RP_SLABS][2][512] slab sums of the two-level partial reductions
     unsigned int* tickets;     // [16] last-CTA tickets (zero-initialised once per workspace)
     float *wpart;              // split-K weight-gradient partials
@@ -96,6 +97,7 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     w.pb = c.take<float>(pr * F_FC);
     w.m1 = c.take<float>(F_FC);
     w.m2 = c.take<float>(F_FC);
+    w.totals = c.take<double>(2 * F_FC + 8);
     w.rscratch = c.take<double>((size_t)RP_SLABS * 2 * F_FC);
     w.tickets = c.take<unsigned int>(64);
     w.wpart = save ? c.take<float>(WPART_ELEMS) : nullptr;
@@ -177,9 +179,27 @@ int launch_wgrad(const float* G, int ldg, int Mo, const float* A, int lda, int N
     return CP_OK;
 }
 
+// SyncBN: sum the 2F+1 doubles at w.totals over all ranks through the caller's collective
+int sync_totals(const Ws& w, int F, const cp_encoder_opts* o, cudaStream_t st) {
+    const int rc = o->allreduce(o->allreduce_user, w.totals, (size_t)(2 * F + 1), (void*)st);
+    return rc == 0 ? CP_OK : CP_ERR_COLLECTIVE;
+}
+
 int bn_finalize(const Ws& w, int l, int F, int P, int64_t R, const cp_encoder_tensors* p,
                 const cp_encoder_opts* o, cudaStream_t st) {
     if (o->bn_mode != CP_BN_BATCH && (!p->bn_rm[l] || !p->bn_rv[l])) return CP_ERR_ARG;
+    if (o->allreduce && o->bn_mode != CP_BN_RUNNING) {
+        bn_finalize_kernel<<<dim3(F / 32, RP_SLABS), 1024, 0, st>>>(
+            w.pa, w.pb, P, F, R, nullptr, nullptr, nullptr, nullptr, o->bn_mode, 0.f, 0.f, nullptr, nullptr, nullptr,
+            nullptr, w.rscratch, w.tickets, w.totals);
+        CP_CHECK_LAUNCH();
+        if (int rc = sync_totals(w, F, o, st)) return rc;
+        bn_finalize_totals_kernel<<<(F + 511) / 512, 512, 0, st>>>(w.totals, F, p->bn_w[l], p->bn_b[l], p->bn_rm[l],
+                                                                   p->bn_rv[l], o->bn_mode, o->bn_momentum, o->bn_eps,
+                                                                   w.mean[l], w.istd[l], w.scale[l], w.shift[l]);
+        CP_CHECK_LAUNCH();
+        return CP_OK;
+    }
     bn_finalize_kernel<<<dim3(F / 32, o->bn_mode == CP_BN_RUNNING ? 1 : RP_SLABS), 1024, 0, st>>>(
         w.pa, w.pb, P, F, R, p->bn_w[l], p->bn_b[l], p->bn_rm[l], p->bn_rv[l], o->bn_mode, o->bn_momentum, o->bn_eps,
         w.mean[l], w.istd[l], w.scale[l], w.shift[l], w.rscratch, w.tickets);
@@ -206,13 +226,19 @@ int bn_apply(const float* y, float* a, float* a_lo, int64_t R, const Ws& w, int 
 template <int F>
 int bn_backward(const float* g, const float* y, float* gz, float* gz_lo, int64_t R, const Ws& w, int l,
                 const uint8_t* keep, float inv_keep, const float* gamma, float* d_gamma, float* d_beta,
-                float* d_bias, cudaStream_t st) {
+                float* d_bias, cudaStream_t st, const cp_encoder_opts* o) {
     const int P = (int)cp_cdiv(R, ColMap<F>::ROWS);
     bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb);
     CP_CHECK_LAUNCH();
+    const bool sync = o->allreduce != nullptr;
     bn_bwd_finalize_kernel<<<dim3(F / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta,
-                                                                    w.rscratch, w.tickets);
+                                                                    w.rscratch, w.tickets, sync ? w.totals : nullptr);
     CP_CHECK_LAUNCH();
+    if (sync) {
+        if (int rc = sync_totals(w, F, o, st)) return rc;
+        bn_bwd_means_totals_kernel<<<(F + 511) / 512, 512, 0, st>>>(w.totals, F, w.m1, w.m2);
+        CP_CHECK_LAUNCH();
+    }
     if (gz_lo)
         bn_bwd_apply_kernel<F, true><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], gamma, w.m1,
                                                         w.m2, gz, gz_lo, w.pa);
@@ -389,7 +415,7 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             const uint8_t* keep = (l >= 3 && o->dropout_p > 0.f) ? w.keep[l - 3] : nullptr;
             if (used[b]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b], 0));     // WAR on the G1 buffer
             CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], g1(b), g1lo(b), n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
-                                     gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st));
+                                     gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st, o));
             CP_CUDA(cudaEventRecord(g_side.ready[b], st));
             const int K = l == 0 ? K_FC1 : F_FC;
             const float* ah = l == 0 ? w.A2 : w.A[l - 1];
@@ -407,7 +433,7 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
         const int b = nb & 1;
         if (used[b]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b], 0));
         CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, g1(b), g1lo(b), R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1],
-                                   gr->bn_b[1], gr->conv2_b, st));
+                                   gr->bn_b[1], gr->conv2_b, st, o));
         CP_CUDA(cudaEventRecord(g_side.ready[b], st));
         CP_CUDA(cudaStreamWaitEvent(ss, g_side.ready[b], 0));
         CP_CUDA(cudaMemsetAsync(gr->conv2_w, 0, sizeof(float) * 64 * 64 * 9, ss));
@@ -425,7 +451,7 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
         for (int l = CP_N_FC - 1; l >= 0; --l) {
             const uint8_t* keep = (l >= 3 && o->dropout_p > 0.f) ? w.keep[l - 3] : nullptr;
             CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], w.G1, nullptr, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
-                                     gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st));
+                                     gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st, o));
             if (l > 0) {
                 CP_TRY((launch_wgrad<128, 128, false>(w.G1, F_FC, F_FC, w.A[l - 1], F_FC, F_FC, n, w.wpart, gr->fc_w[l], 0, st)));
                 CP_TRY((launch_nt<128, 128, 1, false>(w.G1, n, F_FC, F_FC, p->fc_w[l], F_FC, F_FC, nullptr, w.G0, F_FC,
@@ -438,14 +464,14 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
         }
         // conv2 block: G0 is [n*12, 64] (same memory order as the [n,768] position-major flatten)
         CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, w.G1, nullptr, R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1],
-                                   gr->bn_b[1], gr->conv2_b, st));
+                                   gr->bn_b[1], gr->conv2_b, st, o));
         CP_CUDA(cudaMemsetAsync(gr->conv2_w, 0, sizeof(float) * 64 * 64 * 9, st));
         CP_TRY((launch_wgrad<64, 64, true>(w.G1, 64, 64, w.A1, 64, 192, R12, w.wpart, gr->conv2_w, 2, st)));
         CP_TRY((launch_nt<128, 64, 0, true>(w.G1, R12, 192, 64, w.Wc2d, 64, 192, nullptr, w.G0, 64, nullptr, nullptr, 0, st)));
     }
     // conv1 block
     CP_TRY(bn_backward<F_CONV>(w.G0, w.Y1, g1_conv1, nullptr, R12, w, 0, nullptr, 1.f, p->bn_w[0], gr->bn_w[0],
-                               gr->bn_b[0], gr->conv1_b, st));
+                               gr->bn_b[0], gr->conv1_b, st, o));
     const int P1 = (int)cp_cdiv(R12, ColMap<F_CONV>::ROWS);
     float* c1part = w.ppart + (size_t)Pp * CP_EMB_DIM * 512;
     conv1_bwd_kernel<<<P1, 256, 0, st>>>(g1_conv1, w.X0, R12, c1part);

@@ -192,10 +192,21 @@ bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq
                    float* __restrict__ run_mean, float* __restrict__ run_var, int mode, float momentum,
                    float eps, float* __restrict__ mean_o, float* __restrict__ istd_o,
                    float* __restrict__ scale_o, float* __restrict__ shift_o, double* __restrict__ scratch,
-                   unsigned int* __restrict__ tickets) {
+                   unsigned int* __restrict__ tickets, double* __restrict__ totals = nullptr) {
     __shared__ double sm[32 * 33];
     const int col = blockIdx.x * 32 + threadIdx.x % 32, lane = threadIdx.x / 32;
     double mean, var;
+    if (totals) {
+        // SyncBN: only the rank-local column totals [sum | sum of squares | row count]; the caller all-reduces
+        // them across ranks and bn_finalize_totals_kernel finishes the statistics
+        const float* const parts[2] = {psum, psq};
+        double tot[2];
+        if (!reduce_partials_2level<2>(parts, P, F, scratch, tickets, tot, sm)) return;
+        totals[col] = tot[0];
+        totals[F + col] = tot[1];
+        if (col == 0) totals[2 * F] = (double)R;
+        return;
+    }
     if (mode == CP_BN_RUNNING) {
         if (lane != 0 || col >= F || blockIdx.y != 0) return;
         mean = (double)run_mean[col];
@@ -220,6 +231,41 @@ bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq
     istd_o[col] = istd;
     scale_o[col] = sc;
     shift_o[col] = beta[col] - (float)mean * sc;
+}
+
+// SyncBN second half: statistics from the (all-reduced) totals [sum | sumsq | rows] of every rank
+__global__ void __launch_bounds__(512)
+bn_finalize_totals_kernel(const double* __restrict__ totals, int F, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, float* __restrict__ run_mean, float* __restrict__ run_var,
+                          int mode, float momentum, float eps, float* __restrict__ mean_o, float* __restrict__ istd_o,
+                          float* __restrict__ scale_o, float* __restrict__ shift_o) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= F) return;
+    const double R = totals[2 * F];
+    const double mean = totals[col] / R;
+    double var = totals[F + col] / R - mean * mean;
+    if (var < 0.0) var = 0.0;
+    if (mode == CP_BN_BATCH_UPDATE) {
+        const double unbiased = R > 1.0 ? var * R / (R - 1.0) : var;
+        run_mean[col] = (float)((1.0 - (double)momentum) * (double)run_mean[col] + (double)momentum * mean);
+        run_var[col] = (float)((1.0 - (double)momentum) * (double)run_var[col] + (double)momentum * unbiased);
+    }
+    const float istd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[col] * istd;
+    mean_o[col] = (float)mean;
+    istd_o[col] = istd;
+    scale_o[col] = sc;
+    shift_o[col] = beta[col] - (float)mean * sc;
+}
+
+// SyncBN backward second half: m1 = sum g' / R, m2 = sum g'*xh / R over the rows of every rank
+__global__ void __launch_bounds__(512)
+bn_bwd_means_totals_kernel(const double* __restrict__ totals, int F, float* __restrict__ m1, float* __restrict__ m2) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= F) return;
+    const double R = totals[2 * F];
+    m1[col] = (float)(totals[col] / R);
+    m2[col] = (float)(totals[F + col] / R);
 }
 
 // ---------------------------------------------------------------------------------- BN apply
@@ -315,17 +361,26 @@ bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, i
 __global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int P, int F, int64_t R,
                        float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ d_gamma,
-                       float* __restrict__ d_beta, double* __restrict__ scratch, unsigned int* __restrict__ tickets) {
+                       float* __restrict__ d_beta, double* __restrict__ scratch, unsigned int* __restrict__ tickets,
+                       double* __restrict__ totals = nullptr) {
     __shared__ double sm[32 * 33];
     const int col = blockIdx.x * 32 + threadIdx.x % 32;
     const float* const parts[2] = {p1, p2};
     double tot[2];
     if (!reduce_partials_2level<2>(parts, P, F, scratch, tickets, tot, sm)) return;
     const double a = tot[0], b = tot[1];
-    m1[col] = (float)(a / (double)R);
-    m2[col] = (float)(b / (double)R);
+    // d_gamma / d_beta stay rank-local (the parameter-gradient all-reduce averages them like every other
+    // gradient); SyncBN only shares the two means that enter the data gradient
     if (d_beta) d_beta[col] = (float)a;
     if (d_gamma) d_gamma[col] = (float)b;
+    if (totals) {
+        totals[col] = a;
+        totals[F + col] = b;
+        if (col == 0) totals[2 * F] = (double)R;
+        return;
+    }
+    m1[col] = (float)(a / (double)R);
+    m2[col] = (float)(b / (double)R);
 }
 
 // gz = 1[y>0] * gamma*istd * (g' - m1 - xh*m2)     (BN backward, then ReLU backward);

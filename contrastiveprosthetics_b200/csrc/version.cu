@@ -14,6 +14,7 @@ extern "C" const char* cp_status_string(int status) {
         case CP_ERR_ARG: return "invalid argument (null pointer, bad size or misaligned workspace)";
         case CP_ERR_WORKSPACE: return "workspace too small";
         case CP_ERR_UNSUPPORTED: return "unsupported mode for this entry point";
+        case CP_ERR_COLLECTIVE: return "the caller's all-reduce callback (SyncBN) reported a failure";
         default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown libcpros status";
     }
 }

@@ -81,6 +81,23 @@ def _split(params):
     return conv1_w, conv1_b, conv2_w, conv2_b, fc_w, fc_b, proj_w, bn_w, bn_b
 
 
+def _make_sync_hook(ws, group):
+    """SyncBN hook (cp_allreduce_fn): the library hands back a device pointer inside the workspace tensor
+    `ws`; sum that slice over the ranks with torch.distributed (NCCL) on the current stream."""
+    import torch.distributed as dist
+    base = ws.data_ptr()
+
+    def hook(_user, buf, count, _stream):
+        try:
+            off = buf - base
+            dist.all_reduce(ws[off:off + 8 * count].view(torch.float64), group=group)
+            return 0
+        except Exception as e:          # never let an exception cross the C boundary
+            print(f"contrastiveprosthetics_b200: SyncBN all-reduce failed: {e!r}")
+            return 1
+    return _lib.ALLREDUCE_FN(hook)
+
+
 class _EncoderFn(torch.autograd.Function):
     """x (N,12) -> emb (N,16) through cp_encoder_forward; backward through cp_encoder_backward."""
 
@@ -101,11 +118,16 @@ class _EncoderFn(torch.autograd.Function):
             raise RuntimeError("cp_encoder_workspace_bytes rejected the configuration")
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         emb = torch.empty((n, 16), dtype=torch.float32, device=x.device)
+        hook = None
+        if cfg.get("sync_bn"):
+            hook = _make_sync_hook(ws, cfg.get("group"))
+            opts.allreduce = ctypes.cast(hook, ctypes.c_void_p)
         tens = _fill_tensors(_lib.EncoderTensors(), *_split(params), bn_rm=cfg["bn_rm"], bn_rv=cfg["bn_rv"])
         _lib.check(L.cp_encoder_forward(ctypes.byref(tens), _lib.ptr(x), n, _lib.ptr(emb), _lib.ptr(ws),
                                         nbytes, ctypes.byref(opts), _lib.stream()), "cp_encoder_forward")
         if need_bwd:
             ctx.ws, ctx.opts, ctx.tens, ctx.n = ws, opts, tens, n
+            ctx.hook = hook                # keeps the ctypes callback alive until backward has used it
             ctx.params = params            # keeps the storages (and pointers in `tens`) alive
             ctx.cfg = cfg
             if cfg.get("tap") is not None:
@@ -399,6 +421,8 @@ class EMGNet(nn.Module):
         self.engine = _lib.ENGINE_TC         # tcgen05 3xTF32 GEMMs (fp32-level accuracy); ENGINE_SIMT = fp32 FFMA
         self.dropout_seed = 0x5EED
         self._step = 0
+        self.sync_bn = False                 # True (+ torch.distributed initialised): BatchNorm statistics over the
+        self.process_group = None            # rows of EVERY rank (global-batch semantics) instead of rank-local ones
         self.ext_dropout_masks = None        # (4, N, 512) uint8 keep masks injected by parity tests
         self.debug_tap = None                # set to {} to keep the workspace for read_activation()
         self.shape = None
@@ -441,8 +465,13 @@ class EMGNet(nn.Module):
                "ext_masks": self.ext_dropout_masks if dp > 0 else None,
                "bn_rm": rm, "bn_rv": rv,
                "need_bwd": torch.is_grad_enabled() and self.training,
-               "tap": self.debug_tap}
+               "tap": self.debug_tap, "sync_bn": self._sync_active(), "group": self.process_group}
         return _EncoderFn.apply(x, cfg, *self.kernel_params())
+
+    def _sync_active(self):
+        import torch.distributed as dist
+        return bool(self.sync_bn and dist.is_available() and dist.is_initialized()
+                    and dist.get_world_size(self.process_group) > 1)
 
     def read_activation(self, stage, which=0):
         """Parity tap (tests): saved activation of BN stage 0..8 of the last training forward, in the

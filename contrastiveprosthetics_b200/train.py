@@ -64,6 +64,7 @@ def train_loop(dataset, params, checkpoint=False, checkpoint_dir="../checkpoints
                load=None, verbose=False):
     model = Model(params=params, train_model=True, adabn=args.no_adabn, prediction=args.prediction,
                   glove=args.glove, device=str(dataset.device)).to(torch.float32)
+    model.emg_net.sync_bn = getattr(args, "sync_bn", False)      # global-batch BatchNorm statistics under torchrun
     if load is not None:
         print("Loading model")
         model.load_state_dict(torch.load(load + ".pt"))
@@ -229,6 +230,9 @@ def build_parser():
     # --- additions (plumbing only)
     parser.add_argument('--synthetic', action='store_true', help='seeded NinaPro-shaped data instead of emg.pt')
     parser.add_argument('--item_loader', action='store_true', help="reference-style per-item DataLoader")
+    parser.add_argument('--sync_bn', action='store_true',
+                        help='under torchrun: BatchNorm statistics over the rows of every rank (global-batch parity) '
+                             'instead of rank-local ones')
     parser.add_argument('--mixed', action='store_true',
                         help='DB2 + DB3 subjects mixed (46 people, DB3 repetition split, DB3 channel 10 zeroed)')
     parser.add_argument('--data_dir', default="../data/")

@@ -24,6 +24,7 @@ extern "C" {
 #define CP_ERR_ARG (-1)        /* null pointer / bad size */
 #define CP_ERR_WORKSPACE (-2)  /* workspace too small */
 #define CP_ERR_UNSUPPORTED (-3)
+#define CP_ERR_COLLECTIVE (-4) /* the caller's all-reduce callback failed */
 
 #define CP_TASKS 41            /* constants.py:46  MAX_TASKS  */
 #define CP_EMG_DIM 12          /* constants.py:97  EMG_DIM    */
@@ -72,6 +73,13 @@ typedef struct cp_encoder_tensors {
 #define CP_ENGINE_SIMT 0       /* fp32 FFMA GEMMs */
 #define CP_ENGINE_TC 1         /* tcgen05 3xTF32 GEMMs (fp32-level accuracy) */
 
+/* SyncBN hook (optional).  Sums `count` doubles at device pointer `buf` over all ranks, in place, ordered on
+ * `stream`; returns 0 on success.  A C/C++ host implements it with
+ *     ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, comm, (cudaStream_t)stream)
+ * (user = the ncclComm_t); the Python host routes it to torch.distributed (NCCL).  The library calls it once
+ * per BatchNorm layer in forward (column sums, sums of squares, row count) and once in backward. */
+typedef int (*cp_allreduce_fn)(void *user, void *buf, size_t count, void *stream);
+
 typedef struct cp_encoder_opts {
     int32_t bn_mode;
     int32_t engine;
@@ -81,6 +89,8 @@ typedef struct cp_encoder_opts {
     int32_t save_for_backward; /* keep activations in the workspace for cp_encoder_backward */
     uint64_t dropout_seed;     /* Philox key; element stream = (layer, flat index) */
     const uint8_t *ext_masks;  /* optional 4 x (n,512) {0,1} keep masks (parity tests), else NULL */
+    cp_allreduce_fn allreduce; /* NULL: BatchNorm statistics over this rank's rows (local BN).  Non-NULL: SyncBN, */
+    void *allreduce_user;      /* statistics over the rows of every rank (global-batch parity)      */
 } cp_encoder_opts;
 
 size_t cp_encoder_workspace_bytes(int64_t n_windows, const cp_encoder_opts *opts);
