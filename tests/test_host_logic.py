@@ -83,15 +83,40 @@ def test_cabi_exports_every_declared_symbol():
     _lib.build()
     hdr = open(os.path.join(ROOT, "include", "cpros.h")).read()
     declared = set(re.findall(r"\b(cp_[a-z0-9_]+)\s*\(", hdr))
-    declared -= {"cp_encoder_tensors", "cp_encoder_opts"}
+    declared -= {"cp_encoder_tensors", "cp_encoder_opts", "cp_glove_tensors", "cp_glove_opts", "cp_allreduce_fn"}
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     L = ctypes.CDLL(_lib.SO_PATH)
     for name in declared:
         assert hasattr(L, name), name
     assert _lib.lib().cp_version() >= 100
-    # struct mirrors: 4 + 7 + 7 + 1 + 4*9 pointers; opts 40 bytes
+    # struct mirrors: 4 + 7 + 7 + 1 + 4*9 pointers
     assert ctypes.sizeof(_lib.EncoderTensors) == 8 * (4 + 14 + 1 + 36)
-    assert ctypes.sizeof(_lib.EncoderOpts) == 40
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """sizeof / offsetof of every struct in include/cpros.h, as gcc lays them out, == the ctypes mirrors."""
+    fields = {"cp_encoder_tensors": ["conv1_w", "fc_w", "proj_w", "bn_w", "bn_rv"],
+              "cp_encoder_opts": ["bn_mode", "engine", "bn_momentum", "bn_eps", "dropout_p", "save_for_backward",
+                                  "dropout_seed", "ext_masks", "allreduce", "allreduce_user"],
+              "cp_glove_tensors": ["w0", "bn0_b", "w", "b", "bn_w", "bn_b", "proj_w"],
+              "cp_glove_opts": ["glove_dim", "save_for_backward", "bn_eps", "dropout_p", "dropout_seed", "ext_masks"]}
+    mirrors = {"cp_encoder_tensors": _lib.EncoderTensors, "cp_encoder_opts": _lib.EncoderOpts,
+               "cp_glove_tensors": _lib.GloveTensors, "cp_glove_opts": _lib.GloveOpts}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "cpros.h"', 'int main(void) {']
+    for st, fs in fields.items():
+        lines.append(f'printf("{st} %zu\\n", sizeof({st}));')
+        for f in fs:
+            lines.append(f'printf("{st}.{f} %zu\\n", offsetof({st}, {f}));')
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for st, fs in fields.items():
+        assert int(got[st]) == ctypes.sizeof(mirrors[st]), st
+        for f in fs:
+            assert int(got[f"{st}.{f}"]) == getattr(mirrors[st], f).offset, (st, f)
 
 
 def test_missing_library_raises(monkeypatch, tmp_path):
