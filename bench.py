@@ -327,6 +327,14 @@ def run_cuda(args):
     ms_sub, _, _ = timed(subset_run, 5, 1)
     preds_per_s = items_eval * Wv * T * len(masks) / (ms_sub / 1e3)
 
+    c1 = None
+    if rank == 0 and world == 1:
+        # the reference's own launch-bound configuration (go.sh:6): eager vs CUDA-graph step
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        from bench_c1 import c1_small_batch
+        del model, opt_e, opt_g
+        torch.cuda.empty_cache()
+        c1 = c1_small_batch(dev)
     if rank == 0:
         wps, cms, cores = cpu_oracle_steps(n_steps=3, warmup=1, groups=256)
         cpu = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
@@ -350,6 +358,7 @@ def run_cuda(args):
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
             "roofline": roof, "cpu_baseline": cpu,
+            "c1_small_batch": c1,
             "subset_eval": {"value": preds_per_s, "unit": "preds/s", "ms": ms_sub,
                             "workload": "C4: 160 items x 25 x 41 test windows x 5760 trials (144 x 40 sizes), "
                                         "rank + vote + count; trials sharded over ranks"},

@@ -55,7 +55,7 @@ class EncoderOpts(ctypes.Structure):
     _fields_ = [("bn_mode", ctypes.c_int32), ("engine", ctypes.c_int32),
                 ("bn_momentum", ctypes.c_float), ("bn_eps", ctypes.c_float),
                 ("dropout_p", ctypes.c_float), ("save_for_backward", ctypes.c_int32),
-                ("dropout_seed", ctypes.c_uint64), ("ext_masks", ctypes.c_void_p),
+                ("dropout_seed", ctypes.c_uint64), ("ext_masks", ctypes.c_void_p), ("dropout_step", ctypes.c_void_p),
                 ("allreduce", ctypes.c_void_p), ("allreduce_user", ctypes.c_void_p)]
 
 
@@ -72,7 +72,7 @@ class GloveTensors(ctypes.Structure):
 class GloveOpts(ctypes.Structure):
     _fields_ = [("glove_dim", ctypes.c_int32), ("save_for_backward", ctypes.c_int32),
                 ("bn_eps", ctypes.c_float), ("dropout_p", ctypes.c_float),
-                ("dropout_seed", ctypes.c_uint64), ("ext_masks", ctypes.c_void_p)]
+                ("dropout_seed", ctypes.c_uint64), ("ext_masks", ctypes.c_void_p), ("dropout_step", ctypes.c_void_p)]
 
 
 _lib = None

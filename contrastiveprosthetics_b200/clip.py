@@ -199,6 +199,7 @@ class GloveTower(nn.Module):
         self.to(self.device)
         self.dropout_seed = 0x61073
         self._step = 0
+        self.dropout_step = None               # device int64 counter mixed into the Philox key (CUDA graphs)
         self.ext_dropout_masks = None          # (3, n, 256) uint8 keep masks injected by parity tests
 
     def kernel_params(self):
@@ -214,7 +215,7 @@ class GloveTower(nn.Module):
         self._step += 1
         cfg = {"glove_dim": self.glove_dim, "dropout_p": dp,
                "seed": (self.dropout_seed * 1000003 + self._step) & 0xFFFFFFFFFFFFFFFF,
-               "ext_masks": self.ext_dropout_masks if dp > 0 else None,
+               "ext_masks": self.ext_dropout_masks if dp > 0 else None, "dropout_step": self.dropout_step,
                "need_bwd": torch.is_grad_enabled() and self.training}
         return _GloveFn.apply(x, cfg, *self.kernel_params())
 
@@ -243,7 +244,8 @@ class _GloveFn(torch.autograd.Function):
         n = x.shape[0]
         opts = _lib.GloveOpts(glove_dim=cfg["glove_dim"], save_for_backward=int(cfg["need_bwd"]), bn_eps=1e-5,
                               dropout_p=float(cfg["dropout_p"]), dropout_seed=int(cfg["seed"]),
-                              ext_masks=_lib.ptr(cfg["ext_masks"], torch.uint8))
+                              ext_masks=_lib.ptr(cfg["ext_masks"], torch.uint8),
+                              dropout_step=_lib.ptr(cfg.get("dropout_step"), torch.int64))
         nbytes = L.cp_glove_workspace_bytes(n, ctypes.byref(opts))
         if nbytes == 0:
             raise RuntimeError("cp_glove_workspace_bytes rejected the configuration")

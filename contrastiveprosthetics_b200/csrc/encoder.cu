@@ -210,13 +210,14 @@ int bn_finalize(const Ws& w, int l, int F, int P, int64_t R, const cp_encoder_te
 // a_lo != null: write (hi, lo) tf32 planes instead of the fp32 value
 template <int F>
 int bn_apply(const float* y, float* a, float* a_lo, int64_t R, const Ws& w, int l, uint8_t* keep,
-             float inv_keep, cudaStream_t st, float gen_p = 0.f, uint64_t seed = 0, uint64_t layer = 0) {
+             float inv_keep, cudaStream_t st, float gen_p = 0.f, uint64_t seed = 0, uint64_t layer = 0,
+             const unsigned long long* seed_offset = nullptr) {
     if (a_lo)
         bn_apply_kernel<F, true><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, a_lo, R, w.scale[l], w.shift[l], keep,
-                                                                     inv_keep, gen_p, seed, layer);
+                                                                     inv_keep, gen_p, seed, layer, seed_offset);
     else
         bn_apply_kernel<F, false><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, nullptr, R, w.scale[l], w.shift[l], keep,
-                                                                      inv_keep, gen_p, seed, layer);
+                                                                      inv_keep, gen_p, seed, layer, seed_offset);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
@@ -369,7 +370,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
             keep = w.keep[d];
         }
         CP_TRY(bn_apply<F_FC>(w.Y[l], w.A[l], w.A_lo[l], n, w, 2 + l, keep, inv_keep, st, gen_p, o->dropout_seed,
-                              (uint64_t)(l - 3)));
+                              (uint64_t)(l - 3), (const unsigned long long*)o->dropout_step));
     }
     // projection 512 -> 16
     proj_fwd_kernel<512><<<(unsigned)std::min<int64_t>(cp_cdiv(n, 8 * PROJ_RPW), (int64_t)CP_NUM_SMS * 4), 256, 0, st>>>(

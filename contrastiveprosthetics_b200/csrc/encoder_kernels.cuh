@@ -272,13 +272,17 @@ bn_bwd_means_totals_kernel(const double* __restrict__ totals, int F, float* __re
 // a = y*scale + shift, then (linear blocks 4..7) dropout: a * keep / (1-p)   (models.py:282-297)
 // SPLIT: write the result as the two tf32 planes (hi -> a, lo -> a_lo) the tensor-core GEMMs consume.
 // Dropout: `keep` holds a caller-provided mask, or (gen_p > 0) the mask is drawn here -- Philox4x32-10
-// keyed by (seed, layer), counter = element/4 -- and stored to `keep` for the backward pass.
+// keyed by (seed [+ *seed_offset * odd constant], layer), counter = element/4 -- and stored to `keep` for the
+// backward pass.
 template <int F, bool SPLIT>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, float* __restrict__ a_lo, int64_t R,
                 const float* __restrict__ scale, const float* __restrict__ shift,
-                uint8_t* __restrict__ keep, float inv_keep, float gen_p, uint64_t seed, uint64_t layer) {
+                uint8_t* __restrict__ keep, float inv_keep, float gen_p, uint64_t seed, uint64_t layer,
+                const unsigned long long* __restrict__ seed_offset = nullptr) {
     const int64_t total = R * (F / 4);
+    // device-resident step counter: lets a CUDA-graph replay of the same launch draw a fresh mask
+    if (gen_p > 0.f && seed_offset) seed += __ldg(seed_offset) * 0x9E3779B97F4A7C15ull;
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < total;
          v += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(v % (F / 4)) * 4;

@@ -171,7 +171,8 @@ extern "C" int cp_glove_forward(const cp_glove_tensors* p, const float* glove, i
         }
         bn_apply_kernel<GH, false><<<ew_grid(n * (GH / 4)), 256, 0, st>>>(w.Y[b], w.A[b], nullptr, n, w.scale[1 + b],
                                                                           w.shift[1 + b], keep, inv_keep, gen_p,
-                                                                          o->dropout_seed, (uint64_t)(16 + b));
+                                                                          o->dropout_seed, (uint64_t)(16 + b),
+                                                                          (const unsigned long long*)o->dropout_step);
         CP_CHECK_LAUNCH();
         in = w.A[b];
     }

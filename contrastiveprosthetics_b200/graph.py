@@ -1,0 +1,91 @@
+"""CUDA-graph capture of the training step for launch-bound batch sizes.
+
+The reference's own workflow (go.sh:6: --batch_size=8, 150 one-epoch cross-validation folds of 2,500
+steps each, train.py:140-166) runs 328 windows per step: every kernel of the step is a few
+microseconds long and the step is bound by launch latency (~600 launches: ours + Adam / l2 / index
+kernels of torch), not by the GPU.  `GraphedTrainStep` captures
+
+    forward -> fused head/loss (+ l2) -> backward -> Adam x2            (train.py:96-108)
+
+once for a fixed batch size and replays it as ONE graph launch per step.  The batch gather stays an eager
+launch in front of the graph (its source table is re-sliced every epoch, load.py:233-251, so its address is
+not capturable); the gathered batch is copied into the graph's static input.
+
+Dropout: the Philox key of the in-kernel mask generator reads a device-resident step counter
+(cp_encoder_opts.dropout_step) that the graph itself increments, so every replay draws a fresh mask.
+"""
+import torch
+
+
+def _opt_tensors(opt):
+    return [v for st in opt.state.values() for v in st.values() if torch.is_tensor(v)]
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizers, example_emg, sync_grads=None, warmup=3):
+        """model: models.Model (training mode); optimizers: Adam(..., capturable=True) instances;
+        example_emg: a (B,41,1,1,12) CUDA batch that fixes the captured shape.  The capture runs `warmup`
+        + 1 real steps on it; parameters, BatchNorm buffers and optimizer state are restored afterwards."""
+        if sync_grads is not None:
+            raise NotImplementedError("graph capture covers the single-GPU step (cross-validation folds)")
+        for o in optimizers:
+            if not all(g.get("capturable", False) for g in o.param_groups):
+                raise RuntimeError("GraphedTrainStep needs optim.Adam(..., capturable=True)")
+        self.model, self.optimizers = model, list(optimizers)
+        dev = example_emg.device
+        self.B = example_emg.shape[0]
+        self.static_emg = example_emg.clone()
+        self.static_label = torch.arange(example_emg.shape[1], device=dev).repeat(self.B)
+        self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        model.emg_net.dropout_step = self._step_dev
+
+        saved_model = {k: v.clone() for k, v in model.state_dict().items()}
+        # optimizer state is created lazily by the first step: snapshot it if it exists, else it is reset to zero
+        saved_opt = [[t.clone() for t in _opt_tensors(o)] if len(o.state) else None for o in self.optimizers]
+        stream = torch.cuda.Stream(device=dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.n_correct = self._body()
+        # undo the warm-up / capture steps IN PLACE (the graph holds the addresses)
+        with torch.no_grad():
+            sd = model.state_dict()
+            for k, v in saved_model.items():
+                sd[k].copy_(v)
+            for o, saved in zip(self.optimizers, saved_opt):
+                for i, t in enumerate(_opt_tensors(o)):
+                    if saved is None:
+                        t.zero_()
+                    else:
+                        t.copy_(saved[i])
+            self._step_dev.zero_()
+        model.reset()
+        self.steps = 0
+
+    def _body(self):
+        m = self.model
+        self._step_dev.add_(1)
+        logits = m.forward(self.static_emg, None, self.static_label)
+        loss = m.loss(logits, self.static_label)
+        total = loss + m.l2()
+        for o in self.optimizers:
+            o.zero_grad(set_to_none=True)
+        total.backward()
+        for o in self.optimizers:
+            o.step()
+        handle = logits if not torch.is_tensor(logits) else logits._cp_handle
+        return loss.detach(), handle.ncor
+
+    def __call__(self, EMG):
+        """One training step on a (B,41,1,1,12) batch.  Returns the graph's static (loss, per-group correct
+        counts) tensors: valid until the next call -- copy what must be kept."""
+        if EMG.shape != self.static_emg.shape:
+            raise RuntimeError(f"graph was captured for {tuple(self.static_emg.shape)}, got {tuple(EMG.shape)}")
+        self.static_emg.copy_(EMG)
+        self.graph.replay()
+        self.steps += 1
+        return self.loss, self.n_correct

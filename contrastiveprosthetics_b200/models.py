@@ -112,7 +112,8 @@ class _EncoderFn(torch.autograd.Function):
         opts = _lib.EncoderOpts(bn_mode=cfg["bn_mode"], engine=cfg["engine"], bn_momentum=0.1, bn_eps=1e-5,
                                 dropout_p=float(cfg["dropout_p"]), save_for_backward=int(need_bwd),
                                 dropout_seed=int(cfg["seed"]),
-                                ext_masks=_lib.ptr(cfg["ext_masks"], torch.uint8))
+                                ext_masks=_lib.ptr(cfg["ext_masks"], torch.uint8),
+                                dropout_step=_lib.ptr(cfg.get("dropout_step"), torch.int64))
         nbytes = L.cp_encoder_workspace_bytes(n, ctypes.byref(opts))
         if nbytes == 0:
             raise RuntimeError("cp_encoder_workspace_bytes rejected the configuration")
@@ -421,6 +422,7 @@ class EMGNet(nn.Module):
         self.engine = _lib.ENGINE_TC         # tcgen05 3xTF32 GEMMs (fp32-level accuracy); ENGINE_SIMT = fp32 FFMA
         self.dropout_seed = 0x5EED
         self._step = 0
+        self.dropout_step = None             # device int64 counter mixed into the Philox key (graph.GraphedTrainStep)
         self.sync_bn = False                 # True (+ torch.distributed initialised): BatchNorm statistics over the
         self.process_group = None            # rows of EVERY rank (global-batch semantics) instead of rank-local ones
         self.ext_dropout_masks = None        # (4, N, 512) uint8 keep masks injected by parity tests
@@ -463,7 +465,7 @@ class EMGNet(nn.Module):
         cfg = {"bn_mode": bn_mode, "engine": self.engine, "dropout_p": dp,
                "seed": (self.dropout_seed * 1000003 + self._step) & 0xFFFFFFFFFFFFFFFF,
                "ext_masks": self.ext_dropout_masks if dp > 0 else None,
-               "bn_rm": rm, "bn_rv": rv,
+               "dropout_step": self.dropout_step, "bn_rm": rm, "bn_rv": rv,
                "need_bwd": torch.is_grad_enabled() and self.training,
                "tap": self.debug_tap, "sync_bn": self._sync_active(), "group": self.process_group}
         return _EncoderFn.apply(x, cfg, *self.kernel_params())

@@ -89,6 +89,8 @@ typedef struct cp_encoder_opts {
     int32_t save_for_backward; /* keep activations in the workspace for cp_encoder_backward */
     uint64_t dropout_seed;     /* Philox key; element stream = (layer, flat index) */
     const uint8_t *ext_masks;  /* optional 4 x (n,512) {0,1} keep masks (parity tests), else NULL */
+    const uint64_t *dropout_step; /* optional DEVICE counter mixed into the Philox key at run time: a CUDA-graph replay
+                                   * of the same launch then draws a fresh mask when the caller bumps the counter */
     cp_allreduce_fn allreduce; /* NULL: BatchNorm statistics over this rank's rows (local BN).  Non-NULL: SyncBN, */
     void *allreduce_user;      /* statistics over the rows of every rank (global-batch parity)      */
 } cp_encoder_opts;
@@ -207,6 +209,7 @@ typedef struct cp_glove_opts {
     float dropout_p;                    /* after each of the 3 blocks; 0 = off */
     uint64_t dropout_seed;
     const uint8_t *ext_masks;           /* optional 3 x (n,256) {0,1} keep masks (parity tests) */
+    const uint64_t *dropout_step;       /* optional device counter mixed into the Philox key (CUDA graphs) */
 } cp_glove_opts;
 
 size_t cp_glove_workspace_bytes(int64_t n, const cp_glove_opts *opts);

@@ -1,0 +1,64 @@
+"""Config C1 (the reference's own run: --batch_size=8 -> 328 windows/step): eager vs CUDA-graph step."""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def c1_small_batch(dev, B=8, steps=200):
+    from contrastiveprosthetics_b200.graph import GraphedTrainStep
+    from contrastiveprosthetics_b200.load import DB23
+    from contrastiveprosthetics_b200.models import Model
+    from contrastiveprosthetics_b200.utils import TaskWrapper
+    params = {'d_e': 16, 'dp_emg': 0.5, 'dp_glove': 0.5, 'reg_emg': 1e-5, 'reg_glove': 1e-5}
+    ds = DB23(db2=True, device=dev)
+    ds.load_synthetic(with_glove=False)
+    tw = TaskWrapper(ds, with_glove=False)
+    tw.set_train()
+    out = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(42)
+        model = Model(dict(params), adabn=True, device=str(dev))
+        model.set_train()
+        opts = [torch.optim.Adam(model.emg_net.parameters(), lr=1e-3, capturable=(mode == "graph")),
+                torch.optim.Adam(model.glove_net.parameters(), lr=1e-3, capturable=(mode == "graph"))]
+        items = [torch.randperm(tw.D)[:B].to(dev) for _ in range(16)]
+        if mode == "graph":
+            step = GraphedTrainStep(model, opts, tw.get_batch(items[0])[0])
+
+            def one(i):
+                step(tw.get_batch(items[i % 16])[0])
+        else:
+            def one(i):
+                EMG, GLOVE, label = tw.get_batch(items[i % 16])
+                label = label.reshape(-1)
+                lg = model.forward(EMG, GLOVE, label)
+                total = model.loss(lg, label) + model.l2()
+                for o in opts:
+                    o.zero_grad(set_to_none=True)
+                total.backward()
+                for o in opts:
+                    o.step()
+        for i in range(20):
+            one(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            one(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[mode] = {"ms_per_step": ms, "windows_per_s": B * 41 / (ms / 1e3),
+                     "wall_ms_per_step": 1e3 * (time.perf_counter() - t0) / steps}
+    out["workload"] = f"C1: batch_size {B} groups x 41 = {B * 41} windows/step (go.sh:6), AdaBN, dropout 0.5, {steps} steps"
+    return out
+
+
+if __name__ == "__main__":
+    import json
+    print(json.dumps(c1_small_batch(torch.device("cuda:0"))))
