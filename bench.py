@@ -332,8 +332,6 @@ def run_cuda(args):
         # the reference's own launch-bound configuration (go.sh:6): eager vs CUDA-graph step
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         from bench_c1 import c1_small_batch
-        del model, opt_e, opt_g
-        torch.cuda.empty_cache()
         c1 = c1_small_batch(dev)
     if rank == 0:
         wps, cms, cores = cpu_oracle_steps(n_steps=3, warmup=1, groups=256)
