@@ -275,9 +275,10 @@ def run_cuda(args):
 
         use_tc = model.emg_net.engine == _lib.ENGINE_TC
         if use_tc:      # operands pre-split, as they are inside the encoder (the producing kernels write planes)
-            Ah, Al, Wh, Wl = (torch.empty_like(A), torch.empty_like(A), torch.empty_like(Wt), torch.empty_like(Wt))
-            _lib.check(L.cp_split_tf32(P(A), P(Ah), P(Al), A.numel(), _lib.stream()))
-            _lib.check(L.cp_split_tf32(P(Wt), P(Wh), P(Wl), Wt.numel(), _lib.stream()))
+            Ah, Al, Wh, Wl = (torch.empty_like(A, dtype=torch.float16), torch.empty_like(A, dtype=torch.float16),
+                              torch.empty_like(Wt, dtype=torch.float16), torch.empty_like(Wt, dtype=torch.float16))
+            _lib.check(L.cp_split_planes(P(A), P(Ah), P(Al), A.numel(), _lib.stream()))
+            _lib.check(L.cp_split_planes(P(Wt), P(Wh), P(Wl), Wt.numel(), _lib.stream()))
 
         def gemm():
             if use_tc:
@@ -298,16 +299,16 @@ def run_cuda(args):
         torch.cuda.synchronize()
         gms = e0.elapsed_time(e1) / reps
         ach = 2.0 * M * Nn * K / (gms * 1e-3) / 1e12
-        kname = ("gemm_tc_nt_kernel (tcgen05 kind::tf32 x3, TMA, TMEM)" if model.emg_net.engine == _lib.ENGINE_TC
+        kname = ("gemm_tc_nt_kernel (tcgen05 kind::f16, 3-product fp16 split, TMA, TMEM)" if model.emg_net.engine == _lib.ENGINE_TC
                  else "gemm_nt_kernel<128,128> (fp32 FFMA)")
         roof = {"kernel": kname + ": Linear 512->512 + bias + ReLU + BN-stat partials at the step's shape "
                           "(M = 167,936); 7 fwd + 7 dgrad + 7 wgrad launches of this family per step",
                 "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
                 "ms_per_launch": gms,
-                "note": "achieved = algorithmic fp32 FLOPs (2MNK); the 3xTF32 split issues 3x that on the tensor "
-                        "pipe at the tf32 rate (half the bf16 rate), so the ceiling of this fp32-parity path is "
-                        "1/6 of the bf16 peak; step-level: "
+                "note": "achieved = algorithmic fp32 FLOPs (2MNK); the fp32-parity path issues 3 fp16 tensor-core "
+                        "products per algorithmic product (x = hi + lo/2048), so its ceiling is 1/3 of the "
+                        "bf16/fp16 peak; step-level: "
                         f"{FLOP_PER_WINDOW_TRAIN * N / (ms * 1e-3) / 1e12:.2f} TFLOP/s algorithmic"}
         del A, Wt, Y, ws
 
@@ -348,7 +349,7 @@ def run_cuda(args):
                                    ("DB2+DB3 mixed-subject synthetic sEMG (46 subjects, DB3 subjects 11-channel)"
                                     if mixed else "DB2-shaped synthetic sEMG"),
                        "batch_size_groups_per_gpu": B, "windows_per_step": N * world,
-                       "engine": "simt-fp32" if model.emg_net.engine == 0 else "tcgen05-3xtf32",
+                       "engine": "simt-fp32" if model.emg_net.engine == 0 else "tcgen05-3xfp16-split",
                        "parallelism": f"dp{world} (sample-sharded, " + ("SyncBN" if args.sync_bn and world > 1 else "local BatchNorm")
                                       + ", one flat grad all-reduce)",
                        "l2_policy": "per-step working set ~8 GB of activations >> 126 MB L2; no explicit flush"},

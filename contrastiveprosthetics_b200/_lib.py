@@ -106,8 +106,8 @@ def lib():
     L.cp_linear_workspace_bytes.restype = _sz
     L.cp_linear_workspace_bytes.argtypes = [_i64, _i32, _i32]
     L.cp_linear_forward.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _i32, _vp]
-    L.cp_split_tf32.argtypes = [_vp, _vp, _vp, _i64, _vp]
-    L.cp_split_tf32.restype = ctypes.c_int
+    L.cp_split_planes.argtypes = [_vp, _vp, _vp, _i64, _vp]
+    L.cp_split_planes.restype = ctypes.c_int
     L.cp_linear_forward_planes.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]
     L.cp_linear_forward_planes.restype = ctypes.c_int
     L.cp_linear_backward.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz, _i32, _vp]
@@ -142,7 +142,7 @@ def lib():
 
 EXPORTS = ["cp_version", "cp_launch_count", "cp_status_string", "cp_gather_norm", "cp_encoder_workspace_bytes",
            "cp_encoder_forward", "cp_encoder_backward", "cp_encoder_read_activation", "cp_linear_workspace_bytes",
-           "cp_linear_forward", "cp_linear_backward", "cp_split_tf32", "cp_linear_forward_planes", "cp_head_workspace_bytes",
+           "cp_linear_forward", "cp_linear_backward", "cp_split_planes", "cp_linear_forward_planes", "cp_head_workspace_bytes",
            "cp_head_forward_backward", "cp_logits_loss", "cp_vote_eval", "cp_rank_rows",
            "cp_subset_eval", "cp_clip_normalize", "cp_clip_transpose", "cp_clip_sums", "cp_clip_loss",
            "cp_clip_grad", "cp_clip_embed_backward", "cp_glove_workspace_bytes", "cp_glove_forward",

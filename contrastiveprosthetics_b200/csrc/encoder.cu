@@ -13,10 +13,11 @@
 // BatchNorm statistics are produced by the GEMM / conv epilogues as per-CTA partial column sums
 // (no second pass over the activation) and finalised in double precision.
 //
-// Engines (cp_encoder_opts.engine): CP_ENGINE_SIMT runs every GEMM as fp32 FFMA; CP_ENGINE_TC runs the
-// seven linear layers (97 % of the MACs outside conv2) on tcgen05 with the 3xTF32 split: the BN-apply
-// and BN-backward kernels then write their outputs as two tf32 planes (hi, lo) that the TMA-fed GEMMs
-// consume directly, and the weights are split (and transposed for the data gradient) once per call.
+// Engines (cp_encoder_opts.engine): CP_ENGINE_SIMT runs every GEMM as fp32 FFMA; CP_ENGINE_TC runs conv2 and
+// the seven linear layers on tcgen05 with the 3-product fp16 split of gemm_tc.cuh: the BN-apply and
+// BN-backward kernels then write their outputs as two fp16 planes (hi, lo) -- both inside the stage's fp32
+// slot, hi in the first half and lo in the second -- that the TMA-fed GEMMs consume directly, and the weights
+// are split (and transposed for the data gradient) once per call.
 #include <algorithm>
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -44,12 +45,18 @@ struct Ws {
     float *wpart;              // split-K weight-gradient partials
     float *Wc2, *Wc2d, *W1p;
     float *ppart;              // projection / conv1 weight-gradient partials
-    // tensor-core engine: low planes (the high plane reuses the fp32 slot) and split weights
-    float *A1_lo, *A2_lo, *A_lo[CP_N_FC], *G1_lo, *Wc2_lo, *Wc2d_lo;
-    float *G1b, *G1b_lo;      // second pre-activation-gradient buffer (weight-gradient GEMMs run on a side stream)
-    float *Wh[CP_N_FC], *Wl[CP_N_FC], *Wth[CP_N_FC], *Wtl[CP_N_FC];
+    // tensor-core engine: an activation / gradient slot holds both fp16 planes (hi_of / lo_of); split weights
+    float *Wc2_lo, *Wc2d_lo;
+    float *G1b;               // second pre-activation-gradient buffer (weight-gradient GEMMs run on a side stream)
+    plane_t *Wh[CP_N_FC], *Wl[CP_N_FC], *Wth[CP_N_FC], *Wtl[CP_N_FC];
+    unsigned int* gmax;        // [16] max |g'| per backward stage (bit pattern), zeroed per backward call
+    float* gscale_inv;         // [16] 1 / (power-of-two scale of the stage's G1 planes)
     size_t bytes;
 };
+
+// the two fp16 planes of a tensor-core operand live in the stage's fp32 slot of `elems` floats
+inline const plane_t* hi_of(const float* slot) { return reinterpret_cast<const plane_t*>(slot); }
+inline const plane_t* lo_of(const float* slot, size_t elems) { return reinterpret_cast<const plane_t*>(slot) + elems; }
 
 struct Carver {
     char* base;
@@ -107,29 +114,18 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     w.ppart = save ? c.take<float>((size_t)cp_cdiv(n, PROJ_W_ROWS) * CP_EMB_DIM * 512 +
                                    (size_t)cp_cdiv(n * 12, 1024) * 3 * 64)
                    : nullptr;
-    w.A1_lo = w.A2_lo = w.G1_lo = w.Wc2_lo = w.Wc2d_lo = w.G1b = w.G1b_lo = nullptr;
-    for (int l = 0; l < CP_N_FC; ++l) w.A_lo[l] = w.Wh[l] = w.Wl[l] = w.Wth[l] = w.Wtl[l] = nullptr;
+    w.Wc2_lo = w.Wc2d_lo = w.G1b = nullptr;
+    for (int l = 0; l < CP_N_FC; ++l) w.Wh[l] = w.Wl[l] = w.Wth[l] = w.Wtl[l] = nullptr;
+    w.gmax = c.take<unsigned int>(16);
+    w.gscale_inv = c.take<float>(16);
     if (o->engine == CP_ENGINE_TC) {
         w.Wc2_lo = c.take<float>(64 * 192);
         w.Wc2d_lo = c.take<float>(64 * 192);
-        if (save) {
-            w.A1_lo = c.take<float>(conv_elems);
-            w.A2_lo = c.take<float>(conv_elems);
-            for (int l = 0; l + 1 < CP_N_FC; ++l) w.A_lo[l] = c.take<float>(fc_elems);
-            w.G1_lo = c.take<float>(conv_elems);
-            w.G1b = c.take<float>(conv_elems);
-            w.G1b_lo = c.take<float>(conv_elems);
-        } else {
-            float* l0 = c.take<float>(conv_elems);
-            float* l1 = c.take<float>(conv_elems);
-            w.A1_lo = l0;                                   // pairs with A1 = a0
-            w.A2_lo = l1;                                   // pairs with A2 = a1
-            for (int l = 0; l + 1 < CP_N_FC; ++l) w.A_lo[l] = (l & 1) ? l1 : l0;
-        }
+        if (save) w.G1b = c.take<float>(conv_elems);
         for (int l = 0; l < CP_N_FC; ++l) {
             const size_t we = (size_t)F_FC * (l == 0 ? K_FC1 : F_FC);
-            w.Wh[l] = c.take<float>(we); w.Wl[l] = c.take<float>(we);
-            w.Wth[l] = c.take<float>(we); w.Wtl[l] = c.take<float>(we);
+            w.Wh[l] = c.take<plane_t>(we); w.Wl[l] = c.take<plane_t>(we);
+            w.Wth[l] = c.take<plane_t>(we); w.Wtl[l] = c.take<plane_t>(we);
         }
     }
     w.bytes = c.off;
@@ -207,12 +203,13 @@ int bn_finalize(const Ws& w, int l, int F, int P, int64_t R, const cp_encoder_te
     return CP_OK;
 }
 
-// a_lo != null: write (hi, lo) tf32 planes instead of the fp32 value
+// planes: write the (hi, lo) fp16 planes into the slot `a` instead of the fp32 value
 template <int F>
-int bn_apply(const float* y, float* a, float* a_lo, int64_t R, const Ws& w, int l, uint8_t* keep,
+int bn_apply(const float* y, float* a, bool planes, int64_t R, const Ws& w, int l, uint8_t* keep,
              float inv_keep, cudaStream_t st, float gen_p = 0.f, uint64_t seed = 0, uint64_t layer = 0,
              const unsigned long long* seed_offset = nullptr) {
-    if (a_lo)
+    float* a_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(a) + (size_t)R * F) : nullptr;
+    if (planes)
         bn_apply_kernel<F, true><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, a_lo, R, w.scale[l], w.shift[l], keep,
                                                                      inv_keep, gen_p, seed, layer, seed_offset);
     else
@@ -225,11 +222,13 @@ int bn_apply(const float* y, float* a, float* a_lo, int64_t R, const Ws& w, int 
 // BN backward + ReLU backward of stage l:  g (grad w.r.t. stage output A) -> gz (grad w.r.t. the
 // pre-activation), d_gamma, d_beta, d_bias
 template <int F>
-int bn_backward(const float* g, const float* y, float* gz, float* gz_lo, int64_t R, const Ws& w, int l,
+int bn_backward(const float* g, const float* y, float* gz, bool planes, int64_t R, const Ws& w, int l,
                 const uint8_t* keep, float inv_keep, const float* gamma, float* d_gamma, float* d_beta,
                 float* d_bias, cudaStream_t st, const cp_encoder_opts* o) {
     const int P = (int)cp_cdiv(R, ColMap<F>::ROWS);
-    bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb);
+    float* gz_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)R * F) : nullptr;
+    bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb, nullptr,
+                                               planes ? w.gmax + l : nullptr);
     CP_CHECK_LAUNCH();
     const bool sync = o->allreduce != nullptr;
     bn_bwd_finalize_kernel<<<dim3(F / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta,
@@ -240,9 +239,9 @@ int bn_backward(const float* g, const float* y, float* gz, float* gz_lo, int64_t
         bn_bwd_means_totals_kernel<<<(F + 511) / 512, 512, 0, st>>>(w.totals, F, w.m1, w.m2);
         CP_CHECK_LAUNCH();
     }
-    if (gz_lo)
+    if (planes)
         bn_bwd_apply_kernel<F, true><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], gamma, w.m1,
-                                                        w.m2, gz, gz_lo, w.pa);
+                                                        w.m2, gz, gz_lo, w.pa, nullptr, w.gmax + l, w.gscale_inv + l);
     else
         bn_bwd_apply_kernel<F, false><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], gamma, w.m1,
                                                          w.m2, gz, nullptr, w.pa);
@@ -286,11 +285,11 @@ bool opts_ok(const cp_encoder_opts* o) {
 }
 
 // weight-gradient through the tensor-core split-K kernel + the shared re-layout / reduce kernel
-int tc_wgrad(const float* Gh, const float* Gl, int Mo, const float* Ah, const float* Al, int No, int64_t R,
-             float* wpart, float* out, int mode, cudaStream_t st) {
+int tc_wgrad(const plane_t* Gh, const plane_t* Gl, int Mo, const plane_t* Ah, const plane_t* Al, int No, int64_t R,
+             float* wpart, float* out, int mode, cudaStream_t st, const float* g_scale_inv) {
     int S = 0;
     CP_TRY(tcg::launch_tn(Gh, Gl, Mo, Mo, Ah, Al, No, No, R, wpart, WPART_ELEMS, &S, st));
-    wgrad_reduce_kernel<<<(unsigned)cp_cdiv((int64_t)Mo * No, 256), 256, 0, st>>>(wpart, S, Mo, No, out, mode);
+    wgrad_reduce_kernel<<<(unsigned)cp_cdiv((int64_t)Mo * No, 256), 256, 0, st>>>(wpart, S, Mo, No, out, mode, g_scale_inv);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
@@ -312,6 +311,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t R12 = n * 12;
+    const size_t conv_elems = (size_t)n * 12 * F_CONV, fc_elems = (size_t)n * F_FC;
 
     CP_CUDA(cudaMemsetAsync(w.tickets, 0, 64 * sizeof(unsigned int), st));
     prep_weights_kernel<<<(F_FC * K_FC1 + 255) / 256, 256, 0, st>>>(p->conv2_w, p->fc_w[0], w.Wc2, w.Wc2d, w.W1p,
@@ -332,17 +332,18 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     conv1_fwd_kernel<<<P1, 256, 0, st>>>(w.X0, R12, p->conv1_w, p->conv1_b, w.Y1, w.pa, w.pb);
     CP_CHECK_LAUNCH();
     CP_TRY(bn_finalize(w, 0, F_CONV, P1, R12, p, o, st));
-    CP_TRY(bn_apply<F_CONV>(w.Y1, w.A1, w.A1_lo, R12, w, 0, nullptr, 1.f, st));
+    CP_TRY(bn_apply<F_CONV>(w.Y1, w.A1, tcE, R12, w, 0, nullptr, 1.f, st));
 
     // conv2 as implicit GEMM [n*12, 192] x [64, 192]^T
     if (tcE) {
-        CP_TRY(tcg::launch_conv_nt(w.A1, w.A1_lo, n, w.Wc2, w.Wc2_lo, p->conv2_b, w.Y2, w.pa, w.pb, 1, st));
+        CP_TRY(tcg::launch_conv_nt(hi_of(w.A1), lo_of(w.A1, conv_elems), n, hi_of(w.Wc2), hi_of(w.Wc2_lo), p->conv2_b,
+                                   w.Y2, w.pa, w.pb, 1, st));
         CP_TRY(bn_finalize(w, 1, F_CONV, (int)cp_cdiv(n, tcg::CONV_WIN), R12, p, o, st));
     } else {
         CP_TRY((launch_nt<128, 64, 0, true>(w.A1, R12, 192, 64, w.Wc2, 64, 192, p->conv2_b, w.Y2, 64, w.pa, w.pb, 1, st)));
         CP_TRY(bn_finalize(w, 1, F_CONV, (int)cp_cdiv(R12, 128), R12, p, o, st));
     }
-    CP_TRY(bn_apply<F_CONV>(w.Y2, w.A2, w.A2_lo, R12, w, 1, nullptr, 1.f, st));
+    CP_TRY(bn_apply<F_CONV>(w.Y2, w.A2, tcE, R12, w, 1, nullptr, 1.f, st));
 
     // 7 x Linear -> ReLU -> BN (-> Dropout)
     const float inv_keep = o->dropout_p > 0.f ? 1.f / (1.f - o->dropout_p) : 1.f;
@@ -351,8 +352,8 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
         const int K = l == 0 ? K_FC1 : F_FC;
         const float* W = l == 0 ? w.W1p : p->fc_w[l];
         if (tcE) {
-            const float* in_lo = l == 0 ? w.A2_lo : w.A_lo[l - 1];
-            CP_TRY(tcg::launch_nt(in, in_lo, n, K, K, w.Wh[l], w.Wl[l], F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb,
+            const plane_t* in_lo = lo_of(in, l == 0 ? conv_elems : fc_elems);
+            CP_TRY(tcg::launch_nt(hi_of(in), in_lo, n, K, K, w.Wh[l], w.Wl[l], F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb,
                                   1, st));
         } else {
             CP_TRY((launch_nt<128, 128, 0, false>(in, n, K, K, W, F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb, 1, st)));
@@ -369,7 +370,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
                 gen_p = o->dropout_p;              // mask drawn (and stored) inside the BN-apply kernel
             keep = w.keep[d];
         }
-        CP_TRY(bn_apply<F_FC>(w.Y[l], w.A[l], w.A_lo[l], n, w, 2 + l, keep, inv_keep, st, gen_p, o->dropout_seed,
+        CP_TRY(bn_apply<F_FC>(w.Y[l], w.A[l], tcE && l + 1 < CP_N_FC, n, w, 2 + l, keep, inv_keep, st, gen_p, o->dropout_seed,
                               (uint64_t)(l - 3), (const unsigned long long*)o->dropout_step));
     }
     // projection 512 -> 16
@@ -389,7 +390,9 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t R12 = n * 12;
+    const size_t conv_elems = (size_t)n * 12 * F_CONV, fc_elems = (size_t)n * F_FC;
     const float inv_keep = o->dropout_p > 0.f ? 1.f / (1.f - o->dropout_p) : 1.f;
+    CP_CUDA(cudaMemsetAsync(w.gmax, 0, 16 * sizeof(unsigned int), st));
 
     // projection
     const int Pp = (int)cp_cdiv(n, PROJ_W_ROWS);
@@ -410,40 +413,44 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
         int nb = 0;                                    // stages processed so far -> G1 buffer parity
         bool used[2] = {false, false};
         auto g1 = [&](int b) { return b ? w.G1b : w.G1; };
-        auto g1lo = [&](int b) { return b ? w.G1b_lo : w.G1_lo; };
+        auto g1lo = [&](int b, size_t elems) { return lo_of(g1(b), elems); };
         for (int l = CP_N_FC - 1; l >= 0; --l, ++nb) {
             const int b = nb & 1;
             const uint8_t* keep = (l >= 3 && o->dropout_p > 0.f) ? w.keep[l - 3] : nullptr;
             if (used[b]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b], 0));     // WAR on the G1 buffer
-            CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], g1(b), g1lo(b), n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
+            CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], g1(b), true, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
                                      gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st, o));
             CP_CUDA(cudaEventRecord(g_side.ready[b], st));
             const int K = l == 0 ? K_FC1 : F_FC;
-            const float* ah = l == 0 ? w.A2 : w.A[l - 1];
-            const float* al = l == 0 ? w.A2_lo : w.A_lo[l - 1];
+            const float* ain = l == 0 ? w.A2 : w.A[l - 1];
+            const plane_t* ah = hi_of(ain);
+            const plane_t* al = lo_of(ain, l == 0 ? conv_elems : fc_elems);
+            const float* gsi = w.gscale_inv + 2 + l;
             // side stream: dW_l = G1^T . A_{l-1}
             CP_CUDA(cudaStreamWaitEvent(ss, g_side.ready[b], 0));
-            CP_TRY(tc_wgrad(g1(b), g1lo(b), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, ss));
+            CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, ss, gsi));
             CP_CUDA(cudaEventRecord(g_side.done[b], ss));
             used[b] = true;
             // main stream: G0 = G1 . W_l
-            CP_TRY(tcg::launch_nt(g1(b), g1lo(b), n, F_FC, F_FC, w.Wth[l], w.Wtl[l], K, F_FC, nullptr, w.G0, K, nullptr,
-                                  nullptr, 0, st));
+            CP_TRY(tcg::launch_nt(hi_of(g1(b)), g1lo(b, fc_elems), n, F_FC, F_FC, w.Wth[l], w.Wtl[l], K, F_FC, nullptr, w.G0,
+                                  K, nullptr, nullptr, 0, st, gsi));
         }
         // conv2 block: G0 is [n*12, 64] (same memory order as the [n,768] position-major flatten)
         const int b = nb & 1;
         if (used[b]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b], 0));
-        CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, g1(b), g1lo(b), R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1],
+        CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, g1(b), true, R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1],
                                    gr->bn_b[1], gr->conv2_b, st, o));
         CP_CUDA(cudaEventRecord(g_side.ready[b], st));
         CP_CUDA(cudaStreamWaitEvent(ss, g_side.ready[b], 0));
         CP_CUDA(cudaMemsetAsync(gr->conv2_w, 0, sizeof(float) * 64 * 64 * 9, ss));
         int S = 0;
-        CP_TRY(tcg::launch_conv_tn(w.A1, w.A1_lo, g1(b), g1lo(b), n, w.wpart, WPART_ELEMS, &S, ss));
-        wgrad_reduce_kernel<<<(192 * 64 + 255) / 256, 256, 0, ss>>>(w.wpart, S, 192, 64, gr->conv2_w, 3);
+        CP_TRY(tcg::launch_conv_tn(hi_of(w.A1), lo_of(w.A1, conv_elems), hi_of(g1(b)), g1lo(b, conv_elems), n, w.wpart,
+                                   WPART_ELEMS, &S, ss));
+        wgrad_reduce_kernel<<<(192 * 64 + 255) / 256, 256, 0, ss>>>(w.wpart, S, 192, 64, gr->conv2_w, 3, w.gscale_inv + 1);
         CP_CHECK_LAUNCH();
         CP_CUDA(cudaEventRecord(g_side.done[b], ss));
-        CP_TRY(tcg::launch_conv_nt(g1(b), g1lo(b), n, w.Wc2d, w.Wc2d_lo, nullptr, w.G0, nullptr, nullptr, 0, st));
+        CP_TRY(tcg::launch_conv_nt(hi_of(g1(b)), g1lo(b, conv_elems), n, hi_of(w.Wc2d), hi_of(w.Wc2d_lo), nullptr, w.G0,
+                                   nullptr, nullptr, 0, st, w.gscale_inv + 1));
         // conv1's pre-activation gradient goes to the other buffer (its last reader is two stages back)
         if (used[b ^ 1]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b ^ 1], 0));
         g1_conv1 = g1(b ^ 1);
@@ -451,7 +458,7 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     } else {
         for (int l = CP_N_FC - 1; l >= 0; --l) {
             const uint8_t* keep = (l >= 3 && o->dropout_p > 0.f) ? w.keep[l - 3] : nullptr;
-            CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], w.G1, nullptr, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
+            CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], w.G1, false, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
                                      gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st, o));
             if (l > 0) {
                 CP_TRY((launch_wgrad<128, 128, false>(w.G1, F_FC, F_FC, w.A[l - 1], F_FC, F_FC, n, w.wpart, gr->fc_w[l], 0, st)));
@@ -464,14 +471,14 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             }
         }
         // conv2 block: G0 is [n*12, 64] (same memory order as the [n,768] position-major flatten)
-        CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, w.G1, nullptr, R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1],
+        CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, w.G1, false, R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1],
                                    gr->bn_b[1], gr->conv2_b, st, o));
         CP_CUDA(cudaMemsetAsync(gr->conv2_w, 0, sizeof(float) * 64 * 64 * 9, st));
         CP_TRY((launch_wgrad<64, 64, true>(w.G1, 64, 64, w.A1, 64, 192, R12, w.wpart, gr->conv2_w, 2, st)));
         CP_TRY((launch_nt<128, 64, 0, true>(w.G1, R12, 192, 64, w.Wc2d, 64, 192, nullptr, w.G0, 64, nullptr, nullptr, 0, st)));
     }
     // conv1 block
-    CP_TRY(bn_backward<F_CONV>(w.G0, w.Y1, g1_conv1, nullptr, R12, w, 0, nullptr, 1.f, p->bn_w[0], gr->bn_w[0],
+    CP_TRY(bn_backward<F_CONV>(w.G0, w.Y1, g1_conv1, false, R12, w, 0, nullptr, 1.f, p->bn_w[0], gr->bn_w[0],
                                gr->bn_b[0], gr->conv1_b, st, o));
     const int P1 = (int)cp_cdiv(R12, ColMap<F_CONV>::ROWS);
     float* c1part = w.ppart + (size_t)Pp * CP_EMB_DIM * 512;
@@ -494,6 +501,8 @@ extern "C" int cp_encoder_read_activation(const void* workspace, size_t workspac
     if (!o->save_for_backward) return CP_ERR_UNSUPPORTED;
     const Ws w = carve(const_cast<void*>(workspace), n, o);
     if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
+    // tensor-core engine: the post-BN slots of all stages but the last hold fp16 planes, not fp32 values
+    if (which == 1 && o->engine == CP_ENGINE_TC && stage < CP_N_BN - 1) return CP_ERR_UNSUPPORTED;
     const float* src;
     size_t elems;
     if (stage < 2) {
@@ -510,7 +519,10 @@ extern "C" int cp_encoder_read_activation(const void* workspace, size_t workspac
 // ------------------------------------------------------------------- layer-level entry points
 namespace {
 struct LinWs {
-    float *pa, *pb, *wpart, *Ah, *Al, *Gh, *Gl, *Wh, *Wl;
+    float *pa, *pb, *wpart;
+    plane_t *Ah, *Al, *Gh, *Gl, *Wh, *Wl;
+    unsigned int* gmax;
+    float* gscale;         // [0] scale of the G planes, [1] its inverse
     size_t bytes;
 };
 LinWs carve_linear(void* base, int64_t M, int N, int K) {
@@ -520,26 +532,50 @@ LinWs carve_linear(void* base, int64_t M, int N, int K) {
     w.pa = c.take<float>(part);
     w.pb = c.take<float>(part);
     w.wpart = c.take<float>(WPART_ELEMS);
-    w.Ah = c.take<float>((size_t)M * K); w.Al = c.take<float>((size_t)M * K);
-    w.Gh = c.take<float>((size_t)M * N); w.Gl = c.take<float>((size_t)M * N);
-    w.Wh = c.take<float>((size_t)N * K); w.Wl = c.take<float>((size_t)N * K);
+    w.Ah = c.take<plane_t>((size_t)M * K); w.Al = c.take<plane_t>((size_t)M * K);
+    w.Gh = c.take<plane_t>((size_t)M * N); w.Gl = c.take<plane_t>((size_t)M * N);
+    w.Wh = c.take<plane_t>((size_t)N * K); w.Wl = c.take<plane_t>((size_t)N * K);
+    w.gmax = c.take<unsigned int>(4);
+    w.gscale = c.take<float>(4);
     w.bytes = c.off;
     return w;
 }
-int split_planes(const float* x, float* hi, float* lo, size_t elems, cudaStream_t st) {
+int split_planes(const float* x, plane_t* hi, plane_t* lo, size_t elems, cudaStream_t st, float scale = 1.f) {
     if (elems % 4 != 0) return CP_ERR_ARG;
-    split_tf32_kernel<<<ew_grid((int64_t)(elems / 4)), 256, 0, st>>>(x, hi, lo, (int64_t)(elems / 4));
+    split_planes_kernel<<<ew_grid((int64_t)(elems / 4)), 256, 0, st>>>(x, hi, lo, (int64_t)(elems / 4), scale);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
 __global__ void __launch_bounds__(256)
-transpose_split_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ th, float* __restrict__ tl) {
+transpose_split_kernel(const float* __restrict__ W, int N, int K, plane_t* __restrict__ th, plane_t* __restrict__ tl) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * K) return;
-    float h, l;
-    split_tf32(__ldg(W + i), h, l);
+    plane_t h, l;
+    split_f16(__ldg(W + i), h, l);
     const int n = i / K, k = i % K;
     th[(size_t)k * N + n] = h; tl[(size_t)k * N + n] = l;
+}
+// max |x| (bit pattern of a non-negative float) -> atomicMax into *out (zero-initialised)
+__global__ void __launch_bounds__(256)
+absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* __restrict__ out) {
+    float m = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(__ldg(x + i)));
+    m = warp_max(m);
+    if (threadIdx.x % 32 == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+// gradient operand of the layer-level backward: planes of G * S, S = 2^(8 - ceil(log2 max|G|)); gscale = {S, 1/S}
+__global__ void __launch_bounds__(256)
+split_scaled_kernel(const float* __restrict__ x, plane_t* __restrict__ hi, plane_t* __restrict__ lo, int64_t n4,
+                    const unsigned int* __restrict__ gmax, float* __restrict__ gscale) {
+    const float mx = __uint_as_float(__ldg(gmax));
+    const float S = (mx > 0.f && mx < 3.0e38f) ? exp2f(8.f - ceilf(log2f(mx))) : 1.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { gscale[0] = S; gscale[1] = 1.f / S; }
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n4; v += (int64_t)gridDim.x * blockDim.x) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(x) + v);
+        a.x *= S; a.y *= S; a.z *= S; a.w *= S;
+        split_store4(a, hi, lo, v);
+    }
 }
 }  // namespace
 
@@ -579,19 +615,21 @@ extern "C" int cp_linear_forward(const float* A, const float* W, const float* bi
     return CP_OK;
 }
 
-// tf32 (hi, lo) planes of a fp32 array (n multiple of 4): the operand format of the tensor-core engine
-extern "C" int cp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+// fp16 (hi, lo) planes of a fp32 array (n multiple of 4): the operand format of the tensor-core engine
+extern "C" int cp_split_planes(const float* x, uint16_t* hi, uint16_t* lo, int64_t n, void* stream) {
     if (!x || !hi || !lo || n < 0) return CP_ERR_ARG;
     if (n == 0) return CP_OK;
-    return split_planes(x, hi, lo, (size_t)n, (cudaStream_t)stream);
+    return split_planes(x, reinterpret_cast<plane_t*>(hi), reinterpret_cast<plane_t*>(lo), (size_t)n, (cudaStream_t)stream);
 }
 
 // cp_linear_forward on operands that are already split: exactly the launch the encoder issues per
 // linear layer (TMA-fed tcgen05 main loop + bias/ReLU/statistics epilogue)
-extern "C" int cp_linear_forward_planes(const float* A_hi, const float* A_lo, const float* W_hi, const float* W_lo,
-                                        const float* bias, float* Y, int64_t M, int N, int K, int relu,
+extern "C" int cp_linear_forward_planes(const uint16_t* A_hi_, const uint16_t* A_lo_, const uint16_t* W_hi_,
+                                        const uint16_t* W_lo_, const float* bias, float* Y, int64_t M, int N, int K, int relu,
                                         float* col_sum, float* col_sqsum, void* workspace, size_t workspace_bytes,
                                         void* stream) {
+    const plane_t *A_hi = reinterpret_cast<const plane_t*>(A_hi_), *A_lo = reinterpret_cast<const plane_t*>(A_lo_);
+    const plane_t *W_hi = reinterpret_cast<const plane_t*>(W_hi_), *W_lo = reinterpret_cast<const plane_t*>(W_lo_);
     if (!A_hi || !A_lo || !W_hi || !W_lo || !Y || !workspace || M <= 0 || N <= 0 || K <= 0) return CP_ERR_ARG;
     if ((col_sum == nullptr) != (col_sqsum == nullptr)) return CP_ERR_ARG;
     const LinWs w = carve_linear(workspace, M, N, K);
@@ -618,15 +656,21 @@ extern "C" int cp_linear_backward(const float* G, const float* A, const float* W
     if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     if (engine == CP_ENGINE_TC) {
-        CP_TRY(split_planes(G, w.Gh, w.Gl, (size_t)M * N, st));
+        if (((size_t)M * N) % 4 != 0) return CP_ERR_ARG;
+        CP_CUDA(cudaMemsetAsync(w.gmax, 0, sizeof(unsigned int), st));
+        absmax_kernel<<<ew_grid((int64_t)M * N / 4), 256, 0, st>>>(G, (int64_t)M * N, w.gmax);
+        CP_CHECK_LAUNCH();
+        split_scaled_kernel<<<ew_grid((int64_t)M * N / 4), 256, 0, st>>>(G, w.Gh, w.Gl, (int64_t)M * N / 4, w.gmax, w.gscale);
+        CP_CHECK_LAUNCH();
         if (dA) {
             transpose_split_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(W, N, K, w.Wh, w.Wl);
             CP_CHECK_LAUNCH();
-            CP_TRY(tcg::launch_nt(w.Gh, w.Gl, M, N, N, w.Wh, w.Wl, K, N, nullptr, dA, K, nullptr, nullptr, 0, st));
+            CP_TRY(tcg::launch_nt(w.Gh, w.Gl, M, N, N, w.Wh, w.Wl, K, N, nullptr, dA, K, nullptr, nullptr, 0, st,
+                                  w.gscale + 1));
         }
         if (dW) {
             CP_TRY(split_planes(A, w.Ah, w.Al, (size_t)M * K, st));
-            CP_TRY(tc_wgrad(w.Gh, w.Gl, N, w.Ah, w.Al, K, M, w.wpart, dW, 0, st));
+            CP_TRY(tc_wgrad(w.Gh, w.Gl, N, w.Ah, w.Al, K, M, w.wpart, dW, 0, st, w.gscale + 1));
         }
     } else {
         if (dA) CP_TRY((launch_nt<128, 128, 1, false>(G, M, N, N, W, K, K, nullptr, dA, K, nullptr, nullptr, 0, st)));

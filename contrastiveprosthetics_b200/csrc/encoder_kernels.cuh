@@ -270,7 +270,7 @@ bn_bwd_means_totals_kernel(const double* __restrict__ totals, int F, float* __re
 
 // ---------------------------------------------------------------------------------- BN apply
 // a = y*scale + shift, then (linear blocks 4..7) dropout: a * keep / (1-p)   (models.py:282-297)
-// SPLIT: write the result as the two tf32 planes (hi -> a, lo -> a_lo) the tensor-core GEMMs consume.
+// SPLIT: write the result as the two fp16 planes (hi -> a, lo -> a_lo; see gemm_tc.cuh) the tensor-core GEMMs consume.
 // Dropout: `keep` holds a caller-provided mask, or (gen_p > 0) the mask is drawn here -- Philox4x32-10
 // keyed by (seed [+ *seed_offset * odd constant], layer), counter = element/4 -- and stored to `keep` for the
 // backward pass.
@@ -305,10 +305,7 @@ bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, float* __res
             o.z = m.z ? o.z * inv_keep : 0.f; o.w = m.w ? o.w * inv_keep : 0.f;
         }
         if (SPLIT) {
-            float4 h, l;
-            split_tf32(o, h, l);
-            reinterpret_cast<float4*>(a)[v] = h;
-            reinterpret_cast<float4*>(a_lo)[v] = l;
+            split_store4(o, reinterpret_cast<plane_t*>(a), reinterpret_cast<plane_t*>(a_lo), v);
         } else {
             reinterpret_cast<float4*>(a)[v] = o;
         }
@@ -324,8 +321,9 @@ __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t R,
                      const uint8_t* __restrict__ keep, float inv_keep, const float* __restrict__ mean,
                      const float* __restrict__ istd, float* __restrict__ p1, float* __restrict__ p2,
-                     const float* __restrict__ post = nullptr) {
+                     const float* __restrict__ post = nullptr, unsigned int* __restrict__ gmax_bits = nullptr) {
     __shared__ float red[ColMap<F>::RY * F];
+    float gmax = 0.f;                     // max |g'| (feeds the fp16 plane scale of bn_bwd_apply_kernel<.., true>)
     const int qx = threadIdx.x % ColMap<F>::QX, ry = threadIdx.x / ColMap<F>::QX;
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + qx * 4));
     const float4 is = __ldg(reinterpret_cast<const float4*>(istd + qx * 4));
@@ -347,6 +345,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, i
             gv.x = pv.x > 0.f ? gv.x : 0.f; gv.y = pv.y > 0.f ? gv.y : 0.f;
             gv.z = pv.z > 0.f ? gv.z : 0.f; gv.w = pv.w > 0.f ? gv.w : 0.f;
         }
+        gmax = fmaxf(fmaxf(gmax, fmaxf(fabsf(gv.x), fabsf(gv.y))), fmaxf(fabsf(gv.z), fabsf(gv.w)));
         s1[0] += gv.x; s1[1] += gv.y; s1[2] += gv.z; s1[3] += gv.w;
         s2[0] = fmaf(gv.x, (yv.x - mu.x) * is.x, s2[0]);
         s2[1] = fmaf(gv.y, (yv.y - mu.y) * is.y, s2[1]);
@@ -358,6 +357,11 @@ bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, i
     if (ry == 0) {
         *reinterpret_cast<float4*>(p1 + (int64_t)blockIdx.x * F + qx * 4) = make_float4(s1[0], s1[1], s1[2], s1[3]);
         *reinterpret_cast<float4*>(p2 + (int64_t)blockIdx.x * F + qx * 4) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+    }
+    if (gmax_bits) {
+        gmax = warp_max(gmax);
+        // non-negative floats order like their bit patterns; NaN / Inf gradients are the caller's problem
+        if (threadIdx.x % 32 == 0 && gmax > 0.f) atomicMax(gmax_bits, __float_as_uint(gmax));
     }
 }
 
@@ -389,13 +393,17 @@ bn_bwd_finalize_kernel(const float* __restrict__ p1, const float* __restrict__ p
 
 // gz = 1[y>0] * gamma*istd * (g' - m1 - xh*m2)     (BN backward, then ReLU backward);
 // partial column sums of gz = bias gradient of the preceding Linear / Conv.
+// SPLIT: gz is written as fp16 (hi, lo) planes of gz * S with S a power of two chosen from a bound on |gz|
+// (max |gamma*istd| * max |g'| * 18: |m1| <= max|g'|, |m2| <= max|g'| E|xh| <= max|g'|, |xh| <= 16) so that
+// S * bound = 2^8; 1/S goes to *gscale_inv for the consumers' epilogues (data gradient, weight gradient).
 template <int F, bool SPLIT>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t R,
                     const uint8_t* __restrict__ keep, float inv_keep, const float* __restrict__ mean,
                     const float* __restrict__ istd, const float* __restrict__ gamma,
                     const float* __restrict__ m1, const float* __restrict__ m2, float* __restrict__ gz,
-                    float* __restrict__ gz_lo, float* __restrict__ pdb, const float* __restrict__ post = nullptr) {
+                    float* __restrict__ gz_lo, float* __restrict__ pdb, const float* __restrict__ post = nullptr,
+                    const unsigned int* __restrict__ gmax_bits = nullptr, float* __restrict__ gscale_inv = nullptr) {
     __shared__ float red[ColMap<F>::RY * F];
     const int qx = threadIdx.x % ColMap<F>::QX, ry = threadIdx.x / ColMap<F>::QX;
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + qx * 4));
@@ -404,6 +412,19 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, in
     const float4 a1 = __ldg(reinterpret_cast<const float4*>(m1 + qx * 4));
     const float4 a2 = __ldg(reinterpret_cast<const float4*>(m2 + qx * 4));
     const float k0 = ga.x * is.x, k1 = ga.y * is.y, k2 = ga.z * is.z, k3 = ga.w * is.w;
+    float S = 1.f;
+    if (SPLIT) {
+        __shared__ float kred[8];
+        float km = warp_max(fmaxf(fmaxf(fabsf(k0), fabsf(k1)), fmaxf(fabsf(k2), fabsf(k3))));
+        if (threadIdx.x % 32 == 0) kred[threadIdx.x / 32] = km;
+        __syncthreads();
+        km = kred[0];
+#pragma unroll
+        for (int w8 = 1; w8 < 8; ++w8) km = fmaxf(km, kred[w8]);
+        const float bound = km * __uint_as_float(__ldg(gmax_bits)) * 18.f;
+        if (bound > 0.f && bound < 3.0e38f) S = exp2f(8.f - ceilf(log2f(bound)));
+        if (blockIdx.x == 0 && threadIdx.x == 0) *gscale_inv = 1.f / S;
+    }
     float sb[4] = {0, 0, 0, 0};
     const int64_t r0 = (int64_t)blockIdx.x * ColMap<F>::ROWS;
     for (int k = ry; k < ColMap<F>::ROWS; k += ColMap<F>::RY) {
@@ -429,10 +450,8 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, in
         o.z = (!pre || yv.z > 0.f) ? k2 * (gv.z - a1.z - (yv.z - mu.z) * is.z * a2.z) : 0.f;
         o.w = (!pre || yv.w > 0.f) ? k3 * (gv.w - a1.w - (yv.w - mu.w) * is.w * a2.w) : 0.f;
         if (SPLIT) {
-            float4 h, l;
-            split_tf32(o, h, l);
-            reinterpret_cast<float4*>(gz)[v] = h;
-            reinterpret_cast<float4*>(gz_lo)[v] = l;
+            split_store4(make_float4(o.x * S, o.y * S, o.z * S, o.w * S), reinterpret_cast<plane_t*>(gz),
+                         reinterpret_cast<plane_t*>(gz_lo), v);
         } else {
             reinterpret_cast<float4*>(gz)[v] = o;
         }
@@ -624,7 +643,7 @@ proj_bwd_weight_kernel(const float* __restrict__ d, const float* __restrict__ a,
 // Wc2 [o][tap*64+c]  = conv2_w[o][c][1][tap]         conv2 forward  (B operand, [N=64,K=192])
 // Wc2d[c][tap*64+o]  = conv2_w[o][c][1][2-tap]       conv2 data-gradient
 // W1p [o][p*64+c]    = fc1_w[o][c*12+p]              fc1 on the position-major flatten
-// Wc2_lo / Wc2d_lo non-null: write the tf32 (hi, lo) planes (tensor-core engine) instead of fp32
+// Wc2_lo / Wc2d_lo non-null: write the fp16 (hi, lo) planes (tensor-core engine) instead of fp32
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(const float* __restrict__ conv2_w, const float* __restrict__ fc1_w,
                     float* __restrict__ Wc2, float* __restrict__ Wc2d, float* __restrict__ W1p,
@@ -636,8 +655,8 @@ prep_weights_kernel(const float* __restrict__ conv2_w, const float* __restrict__
         // same flat index read as [c'][tap*64 + o'] with c' = o, o' = c
         const float b = __ldg(conv2_w + (c * 64 + o) * 9 + 3 + (2 - tap));
         if (Wc2_lo) {
-            split_tf32(a, Wc2[i], Wc2_lo[i]);
-            split_tf32(b, Wc2d[i], Wc2d_lo[i]);
+            split_f16(a, reinterpret_cast<plane_t*>(Wc2)[i], reinterpret_cast<plane_t*>(Wc2_lo)[i]);
+            split_f16(b, reinterpret_cast<plane_t*>(Wc2d)[i], reinterpret_cast<plane_t*>(Wc2d_lo)[i]);
         } else {
             Wc2[i] = a;
             Wc2d[i] = b;
@@ -653,14 +672,14 @@ prep_weights_kernel(const float* __restrict__ conv2_w, const float* __restrict__
 //   fwd  Wh/Wl [512][K]   = split(W (l = 0: W1p))          B operand of Y = A . W^T      (K-major)
 //   dgrad Wth/Wtl [K][512] = split(transpose)                B operand of dA = G . W       (K-major)
 __global__ void __launch_bounds__(256)
-prep_weights_tc_kernel(const float* __restrict__ W, int K, int permute_fc1, float* __restrict__ Wh,
-                       float* __restrict__ Wl, float* __restrict__ Wth, float* __restrict__ Wtl) {
+prep_weights_tc_kernel(const float* __restrict__ W, int K, int permute_fc1, plane_t* __restrict__ Wh,
+                       plane_t* __restrict__ Wl, plane_t* __restrict__ Wth, plane_t* __restrict__ Wtl) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 512 * K) return;
     const int o = i / K, k = i % K;
     const float w = permute_fc1 ? __ldg(W + o * 768 + (k % 64) * 12 + k / 64) : __ldg(W + i);
-    float h, l;
-    split_tf32(w, h, l);
+    plane_t h, l;
+    split_f16(w, h, l);
     Wh[i] = h; Wl[i] = l;
     Wth[(size_t)k * 512 + o] = h; Wtl[(size_t)k * 512 + o] = l;
 }
@@ -669,18 +688,21 @@ prep_weights_tc_kernel(const float* __restrict__ W, int K, int permute_fc1, floa
 // 2: conv2 (cols tap*64+c -> [o][c][1][tap] of a zero-initialised (64,64,3,3) tensor);
 // 3: conv2 from the transposed tensor-core partials P[z][256][64] (row tap*64+c, column o)
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ P, int S, int Mo, int No, float* __restrict__ out, int mode) {
+wgrad_reduce_kernel(const float* __restrict__ P, int S, int Mo, int No, float* __restrict__ out, int mode,
+                    const float* __restrict__ scale = nullptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Mo * No) return;
+    const double sc = scale ? (double)__ldg(scale) : 1.0;      // undoes the power-of-two scale of the G planes
     if (mode == 3) {
         const int m = i / 64, o = i % 64;                 // Mo = 192 rows used of 256, No = 64
         double s = 0.0;
         for (int z = 0; z < S; ++z) s += (double)__ldg(P + ((int64_t)z * 256 + m) * 64 + o);
-        out[(o * 64 + m % 64) * 9 + 3 + m / 64] = (float)s;
+        out[(o * 64 + m % 64) * 9 + 3 + m / 64] = (float)(s * sc);
         return;
     }
     double s = 0.0;
     for (int z = 0; z < S; ++z) s += (double)__ldg(P + (int64_t)z * Mo * No + i);
+    s *= sc;
     const int o = i / No, k = i % No;
     if (mode == 0) out[i] = (float)s;
     else if (mode == 1) out[o * 768 + (k % 64) * 12 + k / 64] = (float)s;

@@ -1,8 +1,12 @@
-// Tensor-core engine: fp32-accurate GEMMs on tcgen05 (kind::tf32) with the 3xTF32 split
-//   x = hi + lo, hi = tf32(x), lo = tf32(x - hi);   a.b ~= hi_a.hi_b + hi_a.lo_b + lo_a.hi_b
-// (dropped term lo.lo <= 2^-22 |a||b|), accumulated in fp32 in TMEM.  Operands arrive pre-split as
-// separate fp32 planes (written by the producing elementwise kernels), so the main loop is pure
-// TMA -> shared memory -> tcgen05.mma with no register traffic.
+// Tensor-core engine: fp32-accurate GEMMs on tcgen05 (kind::f16) with a 3-product fp16 split
+//   x = hi + lo/2048, hi = fp16(x), lo = fp16((x - hi) * 2048);   a.b ~= hi_a.hi_b + (hi_a.lo_b + lo_a.hi_b)/2048
+// (two 11-bit significands = 22 bits per operand; dropped term lo.lo <= 2^-22 |a||b|), accumulated in fp32
+// in TMEM.  Same accuracy as the 3xTF32 split it replaces (tf32 also carries an 11-bit significand) at TWICE
+// the tensor-pipe rate and HALF the operand bytes (HBM, TMA and shared-memory traffic); fp16's narrow exponent
+// is handled by the producers: activations / weights are O(1) after BatchNorm, pre-activation gradients are
+// written with a per-layer power-of-two scale (bn_bwd_apply_kernel) that the consumers' epilogues undo.
+// Operands arrive pre-split as separate fp16 planes (written by the producing elementwise kernels), so the
+// main loop is pure TMA -> shared memory -> tcgen05.mma with no register traffic.
 //
 //   gemm_tc_nt : C[M,N] = act(A[M,K] . B[N,K]^T + bias) + per-column sum / sum-of-squares partials
 //                (both operands K-major, 128B-swizzled tiles).           forward + data gradient
@@ -14,17 +18,22 @@
 // min(#tiles, 148); two TMEM accumulators (2 x 128 columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1; 3-stage shared-memory ring (A_hi, A_lo, B_hi, B_lo: 4 x 16 KB per stage).
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
+typedef __half plane_t;                            // element type of the (hi, lo) operand planes
+#define CP_LO_SCALE 2048.f                         // lo plane = (x - hi) * 2^11
+#define CP_LO_INV (1.f / 2048.f)
+
 namespace tcg {
 
-constexpr int BM = 128, BN = 128, BK = 32;        // BK floats = 128 bytes = one swizzle row
+constexpr int BM = 128, BN = 128, BK = 64;        // BK halves = 128 bytes = one swizzle row
 constexpr int STAGES = 3;
 constexpr int MAX_STAGES = 4;
-constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB per operand plane per stage
+constexpr int TILE_BYTES = BM * BK * 2;           // 16 KB per operand plane per stage
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi, A_lo, B_hi, B_lo
-constexpr int UMMA_K = 8;                         // tf32: 32 bytes of K per instruction
+constexpr int UMMA_K = 16;                        // fp16: 32 bytes of K per instruction
 constexpr int THREADS = 192;
 constexpr int EPI_THREADS = 128;
 constexpr int TMEM_COLS = 512;                    // 2 buffers x (main + correction accumulator) x 128 fp32 columns
@@ -43,7 +52,7 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + (int)si
 
 // geometry of the K-major kernel as a function of the N tile
 template <int BN_> struct NtCfg {
-    static constexpr int B_TILE = BN_ * BK * 4;
+    static constexpr int B_TILE = BN_ * BK * 2;
     static constexpr int STAGE = 2 * TILE_BYTES + 2 * B_TILE;
     static constexpr int NSTAGES = BN_ == 128 ? 3 : 4;
     static constexpr int ACC = 2 * BN_;               // main + correction accumulator
@@ -57,6 +66,8 @@ struct NtArgs {
     float* psum; float* psq;        // [ceil(M/128)][N] or null
     int64_t M; int N; int K;
     int relu;
+    const float* out_scale;         // device scalar multiplied into the result before bias (undoes the
+                                    // power-of-two scale of a gradient operand), or null
 };
 
 // warp-transposing reduction: on return v[0] of lane l = sum over the 32 lanes of their v[l]
@@ -74,8 +85,8 @@ __device__ __forceinline__ void warp_col_reduce32(float (&v)[32], int lane) {
 }
 
 // CONV: the A operand is the conv-view of a [windows][12][64] activation (k = 3 convolution as an
-// implicit GEMM, K = 3 taps x 64 channels = 6 k-blocks of 32): tm_a_* are 3-D maps (32 ch, 12 pos,
-// windows) and k-block kb loads the box at (channel half, tap-1, window0) -- positions -1 and 12 are
+// implicit GEMM, K = 3 taps x 64 channels = 3 k-blocks of 64): tm_a_* are 3-D maps (64 ch, 12 pos,
+// windows) and k-block kb loads the box at (0, tap-1, window0) -- positions -1 and 12 are
 // out of range and arrive as zeros, which is exactly the padding of models.py:255,259.
 template <int BN_, bool CONV>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -84,7 +95,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                   const NtArgs g) {
     using Cfg = NtCfg<BN_>;
     constexpr int ROWS = CONV ? CONV_ROWS : BM;                 // data rows per tile
-    constexpr uint32_t A_BYTES = ROWS * BK * 4;
+    constexpr uint32_t A_BYTES = ROWS * BK * 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     Smem* sm = reinterpret_cast<Smem*>(tiles + Cfg::NSTAGES * Cfg::STAGE);
@@ -123,9 +134,9 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                     uint8_t* st = tiles + s * Cfg::STAGE;
                     tc::mbar_expect_tx(&sm->full[s], 2 * A_BYTES + 2 * Cfg::B_TILE);
                     if (CONV) {
-                        const int c0 = (kb & 1) * 32, p0 = (kb >> 1) - 1, w0 = (int)tile_m * CONV_WIN;
-                        tc::tma_load_3d(st, &tm_a_hi, &sm->full[s], c0, p0, w0);
-                        tc::tma_load_3d(st + TILE_BYTES, &tm_a_lo, &sm->full[s], c0, p0, w0);
+                        const int p0 = kb - 1, w0 = (int)tile_m * CONV_WIN;
+                        tc::tma_load_3d(st, &tm_a_hi, &sm->full[s], 0, p0, w0);
+                        tc::tma_load_3d(st + TILE_BYTES, &tm_a_lo, &sm->full[s], 0, p0, w0);
                     } else {
                         tc::tma_load_2d(st, &tm_a_hi, &sm->full[s], kb * BK, (int)tile_m * BM);
                         tc::tma_load_2d(st + TILE_BYTES, &tm_a_lo, &sm->full[s], kb * BK, (int)tile_m * BM);
@@ -139,7 +150,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::idesc_tf32(BM, BN_, 0, 0);
+            constexpr uint32_t idesc = tc::idesc_f16(BM, BN_, 0, 0);
             int s = 0; uint32_t ph = 0;
             int it = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
@@ -156,14 +167,14 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                     const uint32_t base = tc::smem_u32(tiles + s * Cfg::STAGE);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint32_t ko = k * UMMA_K * 4;                       // bytes along K inside the swizzle row
+                        const uint32_t ko = k * UMMA_K * 2;                       // bytes along K inside the swizzle row
                         const uint64_t a_hi = tc::smem_desc_sw128(base + ko, 16, 1024);
                         const uint64_t a_lo = tc::smem_desc_sw128(base + TILE_BYTES + ko, 16, 1024);
                         const uint64_t b_hi = tc::smem_desc_sw128(base + 2 * TILE_BYTES + ko, 16, 1024);
                         const uint64_t b_lo = tc::smem_desc_sw128(base + 2 * TILE_BYTES + Cfg::B_TILE + ko, 16, 1024);
-                        tc::mma_tf32(dc, a_lo, b_hi, idesc, (kb | k) != 0);
-                        tc::mma_tf32(dc, a_hi, b_lo, idesc, 1);
-                        tc::mma_tf32(d, a_hi, b_hi, idesc, (kb | k) != 0);
+                        tc::mma_f16(dc, a_lo, b_hi, idesc, (kb | k) != 0);
+                        tc::mma_f16(dc, a_hi, b_lo, idesc, 1);
+                        tc::mma_f16(d, a_hi, b_hi, idesc, (kb | k) != 0);
                     }
                     tc::mma_commit(&sm->empty[s]);                                // frees the stage when the MMAs retire
                     if (++s == Cfg::NSTAGES) { s = 0; ph ^= 1; }
@@ -175,6 +186,8 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp % 4;                      // TMEM lane quadrant this warp may access
         const int et = threadIdx.x - 64;             // 0..127
+        const float oscale = g.out_scale ? __ldg(g.out_scale) : 1.f;
+        const float cscale = CP_LO_INV * oscale;
         int it = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -193,7 +206,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 tc::tmem_ld32(ta + BN_, vc);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += vc[j];
+                for (int j = 0; j < 32; ++j) v[j] = fmaf(vc[j], cscale, v[j] * oscale);
                 const int col = n0 + c * 32;
                 if (g.bias) {
 #pragma unroll
@@ -245,196 +258,16 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM);
 }
 
-// ---------------------------------------------------------------------------- CTA-pair forward / dgrad
-// Same math as gemm_tc_nt_kernel<128>, issued as cta_group::2 MMAs on a 256 x 256 tile owned by a pair of
-// CTAs (cluster 2x1x1): each CTA stages its own 128 rows of A and only HALF of the B tile (128 of the 256
-// rows), so the shared-memory traffic per MMA cycle drops from ~208 to ~106 B/clk and the main loop becomes
-// tensor-pipe bound.  The leader CTA (cluster rank 0) issues every MMA; TMA completions of both CTAs are
-// accounted on the leader's `full` barriers; tcgen05.commit multicasts the `empty` / `tmem_full` arrivals
-// to both CTAs.  TMEM: 256 main + 256 correction columns per CTA (single buffered), eight epilogue warps.
-namespace pair {
-constexpr int BN2 = 256;                 // tile N (B rows per CTA = 128)
-constexpr int THREADS2 = 320;            // TMA warp, MMA warp, 8 epilogue warps
-constexpr int EPI2 = 256;
-struct Smem2 {
-    uint64_t full[STAGES], empty[STAGES], tmem_full, tmem_empty;
-    uint32_t tmem_base;
-    uint32_t pad;
-    float csum[4][BN2];
-    float csq[4][BN2];
-};
-constexpr int SMEM2 = STAGES * STAGE_BYTES + 1024 + (int)sizeof(Smem2);
-}  // namespace pair
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair::THREADS2, 1)
-gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-                       const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                       const NtArgs g) {
-    using namespace pair;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    Smem2* sm = reinterpret_cast<Smem2*>(tiles + STAGES * STAGE_BYTES);
-
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const uint32_t rank = tc::cluster_ctarank();
-    const bool leader = rank == 0;
-    const int tiles_n = g.N / BN2;
-    const int64_t tiles_m = (g.M + 2 * BM - 1) / (2 * BM);
-    const int64_t n_tiles = tiles_m * tiles_n;
-    const int kblocks = g.K / BK;
-    const int64_t cluster_id = blockIdx.x / 2, n_clusters = gridDim.x / 2;
-
-    if (warp == 0 && tc::elect_one()) {
-        tc::prefetch_tmap(&tm_a_hi); tc::prefetch_tmap(&tm_a_lo);
-        tc::prefetch_tmap(&tm_b_hi); tc::prefetch_tmap(&tm_b_lo);
-        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&sm->full[s], 1); tc::mbar_init(&sm->empty[s], 1); }
-        tc::mbar_init(&sm->tmem_full, 1);
-        tc::mbar_init(&sm->tmem_empty, 16);            // 8 epilogue warps x 2 CTAs arrive on the leader's copy
-        tc::fence_barrier_init();
-    }
-    if (warp == 1) {
-        tc::tmem_alloc_pair(&sm->tmem_base, 512);
-        tc::tmem_relinquish_pair();
-    }
-    tc::tc_fence_before();
-    tc::cluster_sync();
-    tc::tc_fence_after();
-    const uint32_t tmem_base = sm->tmem_base;
-
-    if (warp == 0) {
-        // ===================== TMA producer (both CTAs) =====================
-        if (tc::elect_one()) {
-            int s = 0; uint32_t ph = 0;
-            for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
-                const int m0 = (int)(t / tiles_n) * 2 * BM + (int)rank * BM;
-                const int n0 = (int)(t % tiles_n) * BN2 + (int)rank * BN;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    tc::mbar_wait(&sm->empty[s], ph ^ 1);
-                    uint8_t* st = tiles + s * STAGE_BYTES;
-                    if (leader) tc::mbar_expect_tx(&sm->full[s], 2 * STAGE_BYTES);     // bytes of both CTAs
-                    tc::tma_load_2d_pair(st + 0 * TILE_BYTES, &tm_a_hi, &sm->full[s], kb * BK, m0);
-                    tc::tma_load_2d_pair(st + 1 * TILE_BYTES, &tm_a_lo, &sm->full[s], kb * BK, m0);
-                    tc::tma_load_2d_pair(st + 2 * TILE_BYTES, &tm_b_hi, &sm->full[s], kb * BK, n0);
-                    tc::tma_load_2d_pair(st + 3 * TILE_BYTES, &tm_b_lo, &sm->full[s], kb * BK, n0);
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA only) =====================
-        if (leader && tc::elect_one()) {
-            constexpr uint32_t idesc = tc::idesc_tf32(2 * BM, BN2, 0, 0);
-            int s = 0; uint32_t ph = 0;
-            int it = 0;
-            for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
-                tc::mbar_wait(&sm->tmem_empty, (it & 1) ^ 1);
-                tc::tc_fence_after();
-                const uint32_t d = tmem_base;
-                const uint32_t dc = tmem_base + BN2;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    tc::mbar_wait(&sm->full[s], ph);
-                    tc::tc_fence_after();
-                    const uint32_t base = tc::smem_u32(tiles + s * STAGE_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint32_t ko = k * UMMA_K * 4;
-                        const uint64_t a_hi = tc::smem_desc_sw128(base + 0 * TILE_BYTES + ko, 16, 1024);
-                        const uint64_t a_lo = tc::smem_desc_sw128(base + 1 * TILE_BYTES + ko, 16, 1024);
-                        const uint64_t b_hi = tc::smem_desc_sw128(base + 2 * TILE_BYTES + ko, 16, 1024);
-                        const uint64_t b_lo = tc::smem_desc_sw128(base + 3 * TILE_BYTES + ko, 16, 1024);
-                        tc::mma_tf32_pair(dc, a_lo, b_hi, idesc, (kb | k) != 0);
-                        tc::mma_tf32_pair(dc, a_hi, b_lo, idesc, 1);
-                        tc::mma_tf32_pair(d, a_hi, b_hi, idesc, (kb | k) != 0);
-                    }
-                    tc::mma_commit_pair(&sm->empty[s]);
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
-                }
-                tc::mma_commit_pair(&sm->tmem_full);
-            }
-        }
-    } else {
-        // ===================== epilogue (warps 2..9 of both CTAs) =====================
-        const int q = warp % 4;                      // TMEM lane quadrant
-        const int half = (warp - 2) / 4;             // column half: 0 -> 0..127, 1 -> 128..255
-        const int et = threadIdx.x - 64;             // 0..255
-        const uint32_t empty_remote = tc::mapa(tc::smem_u32(&sm->tmem_empty), 0);
-        int it = 0;
-        for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
-            const int64_t tile_m = (t / tiles_n) * 2 + rank;            // 128-row tile index of this CTA
-            const int n0 = (int)(t % tiles_n) * BN2;
-            const int64_t row = tile_m * BM + q * 32 + lane;
-            const bool row_ok = row < g.M;
-            tc::mbar_wait(&sm->tmem_full, it & 1);
-            tc::tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int cl = half * 128 + c * 32;                     // column inside the tile
-                float v[32], vc[32];
-                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + cl;
-                tc::tmem_ld32(ta, v);
-                tc::tmem_ld32(ta + BN2, vc);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += vc[j];
-                const int col = n0 + cl;
-                if (g.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col + j));
-                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                    }
-                }
-                if (g.relu) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                }
-                if (row_ok) {
-                    float4* dst = reinterpret_cast<float4*>(g.C + row * g.ldc + col);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                }
-                if (g.psum) {
-                    float sq[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = row_ok ? v[j] : 0.f;
-                        sq[j] = v[j] * v[j];
-                    }
-                    warp_col_reduce32(v, lane);
-                    warp_col_reduce32(sq, lane);
-                    sm->csum[q][cl + lane] = v[0];
-                    sm->csq[q][cl + lane] = sq[0];
-                }
-            }
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive_cluster(empty_remote);
-            if (g.psum) {
-                tc::named_bar_sync(1, EPI2);
-                const float s = sm->csum[0][et] + sm->csum[1][et] + sm->csum[2][et] + sm->csum[3][et];
-                const float qq = sm->csq[0][et] + sm->csq[1][et] + sm->csq[2][et] + sm->csq[3][et];
-                if (tile_m * BM < g.M) {
-                    g.psum[tile_m * g.N + n0 + et] = s;
-                    g.psq[tile_m * g.N + n0 + et] = qq;
-                }
-                tc::named_bar_sync(1, EPI2);
-            }
-        }
-    }
-    tc::tc_fence_before();
-    tc::cluster_sync();
-    if (warp == 1) tc::tmem_dealloc_pair(tmem_base, 512);
-}
-
 // ---------------------------------------------------------------------------- weight gradient
 // P[z][o, c] = sum over rows r of slab z of G[r, o] * A[r, c].  Both operands are MN-major: a stage
-// holds, per plane, 4 blocks of [32 rows r][32 floats] (one 3-D TMA box {32, 32, 4}); MMA K-step j
-// reads the 8 rows at +j*1024 B (two 4-row swizzle groups, SBO = 512 B), the four 32-wide MN blocks
-// are LBO = 4096 B apart.  MN-major tf32 operands must use the 32-byte-atom 128B swizzle.
+// holds, per plane, 2 blocks of [64 rows r][64 halves] (one 3-D TMA box {64, 64, 2}, plain 128B swizzle);
+// MMA K-step j reads the 16 rows at +j*2048 B (two 8-row swizzle groups, SBO = 1024 B), the two 64-wide
+// MN blocks are LBO = 8192 B apart.
 // The fp32 accumulators in TMEM are rounded toward zero at every MMA, so a chain over ~20k rows
 // would carry a ~1e-4 bias: the chain is cut every CHUNK_KB k-blocks (512 rows) and the epilogue
 // threads keep the running sum in registers (round-to-nearest adds), 128 per thread.
-constexpr int CHUNK_KB = 16;
+constexpr int CHUNK_KB = 8;
+constexpr int MN_BLOCK = BK * 128;                // bytes of one [64 rows][64 halves] block
 
 struct TnArgs {
     float* P;                 // [splits][Mo][No]
@@ -481,16 +314,16 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_cons
                 uint8_t* st = tiles + s * STAGE_BYTES;
                 const int r = (int)(r_begin + (int64_t)kb * BK);
                 tc::mbar_expect_tx(&sm->full[s], STAGE_BYTES);
-                tc::tma_load_3d(st + 0 * TILE_BYTES, &tm_g_hi, &sm->full[s], 0, r, o0 / 32);
-                tc::tma_load_3d(st + 1 * TILE_BYTES, &tm_g_lo, &sm->full[s], 0, r, o0 / 32);
-                tc::tma_load_3d(st + 2 * TILE_BYTES, &tm_a_hi, &sm->full[s], 0, r, c0 / 32);
-                tc::tma_load_3d(st + 3 * TILE_BYTES, &tm_a_lo, &sm->full[s], 0, r, c0 / 32);
+                tc::tma_load_3d(st + 0 * TILE_BYTES, &tm_g_hi, &sm->full[s], 0, r, o0 / 64);
+                tc::tma_load_3d(st + 1 * TILE_BYTES, &tm_g_lo, &sm->full[s], 0, r, o0 / 64);
+                tc::tma_load_3d(st + 2 * TILE_BYTES, &tm_a_hi, &sm->full[s], 0, r, c0 / 64);
+                tc::tma_load_3d(st + 3 * TILE_BYTES, &tm_a_lo, &sm->full[s], 0, r, c0 / 64);
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::idesc_tf32(BM, BN, 1, 1);
+            constexpr uint32_t idesc = tc::idesc_f16(BM, BN, 1, 1);
             int s = 0; uint32_t ph = 0;
             int kb = 0;
             for (int ch = 0; ch < chunks; ++ch) {
@@ -506,15 +339,15 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_cons
                     const uint32_t base = tc::smem_u32(tiles + s * STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint32_t ko = k * 1024;                 // 8 rows of 128 B
-                        const uint64_t g_hi = tc::smem_desc(base + 0 * TILE_BYTES + ko, 4096, 512, 1);
-                        const uint64_t g_lo = tc::smem_desc(base + 1 * TILE_BYTES + ko, 4096, 512, 1);
-                        const uint64_t a_hi = tc::smem_desc(base + 2 * TILE_BYTES + ko, 4096, 512, 1);
-                        const uint64_t a_lo = tc::smem_desc(base + 3 * TILE_BYTES + ko, 4096, 512, 1);
+                        const uint32_t ko = k * 2048;                 // 16 rows of 128 B
+                        const uint64_t g_hi = tc::smem_desc_sw128(base + 0 * TILE_BYTES + ko, MN_BLOCK, 1024);
+                        const uint64_t g_lo = tc::smem_desc_sw128(base + 1 * TILE_BYTES + ko, MN_BLOCK, 1024);
+                        const uint64_t a_hi = tc::smem_desc_sw128(base + 2 * TILE_BYTES + ko, MN_BLOCK, 1024);
+                        const uint64_t a_lo = tc::smem_desc_sw128(base + 3 * TILE_BYTES + ko, MN_BLOCK, 1024);
                         const uint32_t accum = (first && k == 0) ? 0u : 1u;
-                        tc::mma_tf32(dc, g_lo, a_hi, idesc, accum);
-                        tc::mma_tf32(dc, g_hi, a_lo, idesc, 1);
-                        tc::mma_tf32(d, g_hi, a_hi, idesc, accum);
+                        tc::mma_f16(dc, g_lo, a_hi, idesc, accum);
+                        tc::mma_f16(dc, g_hi, a_lo, idesc, 1);
+                        tc::mma_f16(d, g_hi, a_hi, idesc, accum);
                     }
                     first = false;
                     tc::mma_commit(&sm->empty[s]);
@@ -540,7 +373,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_cons
                 tc::tmem_ld32(ta + BN, vc);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sum[c * 32 + j] += v[j] + vc[j];
+                for (int j = 0; j < 32; ++j) sum[c * 32 + j] += fmaf(vc[j], CP_LO_INV, v[j]);
             }
             tc::tc_fence_before();
             __syncwarp();
@@ -560,12 +393,12 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_cons
 // P[z][tap*64 + c][o] = sum over the windows of slab z, positions p, of X[w, p+tap-1, c] * G[(w,p), o]
 // (the transposed weight gradient of the k = 3 convolution).  M side = conv-view of X (192 columns,
 // padded to two 128-row MMA tiles: tile 0 = taps 0,1, tile 1 = tap 2 + 64 unused rows), N side = the
-// 64 output channels of G.  A k-block is 4 windows = 48 rows: per plane the M side is up to four
-// [48 rows][32 ch] boxes of the 3-D conv map shifted by tap-1 (zero padded by TMA), the N side two
-// [48][32] boxes of G.  Same MN-major 32B-atom swizzle / register-side chain cutting as gemm_tc_tn.
+// 64 output channels of G.  A k-block is 4 windows = 48 rows: per plane the M side is up to two
+// [48 rows][64 ch] boxes of the 3-D conv map shifted by tap-1 (zero padded by TMA), the N side one
+// [48][64] box of G.  Same MN-major layout / register-side chain cutting as gemm_tc_tn.
 constexpr int CW_WIN = 4, CW_ROWS = 48;                   // windows / rows per k-block
-constexpr int CW_BLOCK = CW_ROWS * 128;                   // bytes of one [48][32 floats] block
-constexpr int CW_STAGE = (4 + 2) * 2 * CW_BLOCK;          // (X: 4 blocks, G: 2 blocks) x (hi, lo)
+constexpr int CW_BLOCK = CW_ROWS * 128;                   // bytes of one [48][64 halves] block
+constexpr int CW_STAGE = (2 + 1) * 2 * CW_BLOCK;          // (X: 2 blocks, G: 1 block) x (hi, lo)
 constexpr int CW_STAGES = 3;
 constexpr int CW_CHUNK_KB = 11;                           // 528 rows per accumulation chain
 constexpr int CW_SMEM = CW_STAGES * CW_STAGE + 1024 + (int)sizeof(Smem);
@@ -585,7 +418,7 @@ gemm_tc_tn_conv_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid
     Smem* sm = reinterpret_cast<Smem*>(tiles + CW_STAGES * CW_STAGE);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int mt = blockIdx.x;                               // 0: taps 0,1   1: tap 2
-    const int n_blocks = mt == 0 ? 4 : 2;                    // 32-channel blocks that carry data
+    const int n_blocks = mt == 0 ? 2 : 1;                    // 64-channel blocks (taps) that carry data
     const int64_t w_begin = (int64_t)blockIdx.y * g.win_per_split;
     const int64_t w_end = min(g.windows, w_begin + g.win_per_split);
     const int kblocks = (int)((w_end - w_begin + CW_WIN - 1) / CW_WIN);
@@ -614,21 +447,21 @@ gemm_tc_tn_conv_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid
                 tc::mbar_wait(&sm->empty[s], ph ^ 1);
                 uint8_t* st = tiles + s * CW_STAGE;
                 const int w0 = (int)(w_begin + (int64_t)kb * CW_WIN);
-                tc::mbar_expect_tx(&sm->full[s], (uint32_t)(2 * n_blocks + 4) * CW_BLOCK);
+                tc::mbar_expect_tx(&sm->full[s], (uint32_t)(2 * n_blocks + 2) * CW_BLOCK);
                 for (int b = 0; b < n_blocks; ++b) {
-                    const int tap = mt * 2 + b / 2, c0 = (b & 1) * 32;
-                    tc::tma_load_3d(st + b * CW_BLOCK, &tm_x_hi, &sm->full[s], c0, tap - 1, w0);
-                    tc::tma_load_3d(st + (4 + b) * CW_BLOCK, &tm_x_lo, &sm->full[s], c0, tap - 1, w0);
+                    const int tap = mt * 2 + b;
+                    tc::tma_load_3d(st + b * CW_BLOCK, &tm_x_hi, &sm->full[s], 0, tap - 1, w0);
+                    tc::tma_load_3d(st + (2 + b) * CW_BLOCK, &tm_x_lo, &sm->full[s], 0, tap - 1, w0);
                 }
-                // G: [rows][64] as (32 ch, row, 2 halves) -> two [48][32] blocks per plane
-                tc::tma_load_3d(st + 8 * CW_BLOCK, &tm_g_hi, &sm->full[s], 0, w0 * 12, 0);
-                tc::tma_load_3d(st + 10 * CW_BLOCK, &tm_g_lo, &sm->full[s], 0, w0 * 12, 0);
+                // G: [rows][64] -> one [48][64] block per plane
+                tc::tma_load_2d(st + 4 * CW_BLOCK, &tm_g_hi, &sm->full[s], 0, w0 * 12);
+                tc::tma_load_2d(st + 5 * CW_BLOCK, &tm_g_lo, &sm->full[s], 0, w0 * 12);
                 if (++s == CW_STAGES) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::idesc_tf32(BM, 64, 1, 1);
+            constexpr uint32_t idesc = tc::idesc_f16(BM, 64, 1, 1);
             int s = 0; uint32_t ph = 0;
             int kb = 0;
             for (int ch = 0; ch < chunks; ++ch) {
@@ -644,15 +477,15 @@ gemm_tc_tn_conv_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid
                     const uint32_t base = tc::smem_u32(tiles + s * CW_STAGE);
 #pragma unroll
                     for (int k = 0; k < CW_ROWS / UMMA_K; ++k) {
-                        const uint32_t ko = k * 1024;
-                        const uint64_t x_hi = tc::smem_desc(base + 0 * CW_BLOCK + ko, CW_BLOCK, 512, 1);
-                        const uint64_t x_lo = tc::smem_desc(base + 4 * CW_BLOCK + ko, CW_BLOCK, 512, 1);
-                        const uint64_t g_hi = tc::smem_desc(base + 8 * CW_BLOCK + ko, CW_BLOCK, 512, 1);
-                        const uint64_t g_lo = tc::smem_desc(base + 10 * CW_BLOCK + ko, CW_BLOCK, 512, 1);
+                        const uint32_t ko = k * 2048;
+                        const uint64_t x_hi = tc::smem_desc_sw128(base + 0 * CW_BLOCK + ko, CW_BLOCK, 1024);
+                        const uint64_t x_lo = tc::smem_desc_sw128(base + 2 * CW_BLOCK + ko, CW_BLOCK, 1024);
+                        const uint64_t g_hi = tc::smem_desc_sw128(base + 4 * CW_BLOCK + ko, CW_BLOCK, 1024);
+                        const uint64_t g_lo = tc::smem_desc_sw128(base + 5 * CW_BLOCK + ko, CW_BLOCK, 1024);
                         const uint32_t accum = (first && k == 0) ? 0u : 1u;
-                        tc::mma_tf32(dc, x_lo, g_hi, idesc, accum);
-                        tc::mma_tf32(dc, x_hi, g_lo, idesc, 1);
-                        tc::mma_tf32(d, x_hi, g_hi, idesc, accum);
+                        tc::mma_f16(dc, x_lo, g_hi, idesc, accum);
+                        tc::mma_f16(dc, x_hi, g_lo, idesc, 1);
+                        tc::mma_f16(d, x_hi, g_hi, idesc, accum);
                     }
                     first = false;
                     tc::mma_commit(&sm->empty[s]);
@@ -678,7 +511,7 @@ gemm_tc_tn_conv_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid
                 tc::tmem_ld32(ta + 64, vc);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sum[c * 32 + j] += v[j] + vc[j];
+                for (int j = 0; j < 32; ++j) sum[c * 32 + j] += fmaf(vc[j], CP_LO_INV, v[j]);
             }
             tc::tc_fence_before();
             __syncwarp();
@@ -714,41 +547,41 @@ inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// row-major fp32 [rows, cols] (leading dimension ld floats), box {32 cols, box_rows}, 128B swizzle,
+// row-major fp16 [rows, cols] (leading dimension ld halves), box {64 cols, box_rows}, 128B swizzle,
 // out-of-range elements read as zero
-inline int make_tmap_2d(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+inline int make_tmap_2d(CUtensorMap* m, const plane_t* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return CP_ERR_UNSUPPORTED;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<plane_t*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? CP_OK : CP_ERR_ARG;
 }
 
-// row-major fp32 [rows, cols] viewed as (32 cols, rows, cols/32 blocks): box {32, 32 rows, 4 blocks}
-// lands in shared memory as 4 x [32 rows][128 B], i.e. the MN-major 128B-swizzle canonical layout
-inline int make_tmap_mn(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+// row-major fp16 [rows, cols] viewed as (64 cols, rows, cols/64 blocks): box {64, 64 rows, 2 blocks}
+// lands in shared memory as 2 x [64 rows][128 B], i.e. the MN-major 128B-swizzle canonical layout
+inline int make_tmap_mn(CUtensorMap* m, const plane_t* base, int64_t rows, int64_t cols, int64_t ld) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return CP_ERR_UNSUPPORTED;
-    cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
-    cuuint32_t box[3] = {32, 32, 4};
+    cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(cols / 64)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, 128};
+    cuuint32_t box[3] = {64, 64, 2};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<plane_t*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? CP_OK : CP_ERR_ARG;
 }
 
 // returns the number of splits written to P ([splits][Mo][No]) through *splits_out
-inline int launch_tn(const float* G_hi, const float* G_lo, int ldg, int Mo, const float* A_hi, const float* A_lo,
+inline int launch_tn(const plane_t* G_hi, const plane_t* G_lo, int ldg, int Mo, const plane_t* A_hi, const plane_t* A_lo,
                      int lda, int No, int64_t R, float* P, size_t p_capacity_elems, int* splits_out,
                      cudaStream_t st) {
-    if (Mo % BM != 0 || No % BN != 0 || ldg % 4 != 0 || lda % 4 != 0 || R <= 0) return CP_ERR_ARG;
+    if (Mo % BM != 0 || No % BN != 0 || ldg % 8 != 0 || lda % 8 != 0 || R <= 0) return CP_ERR_ARG;
     CUtensorMap tg_hi, tg_lo, ta_hi, ta_lo;
     int rc;
     if ((rc = make_tmap_mn(&tg_hi, G_hi, R, Mo, ldg)) != CP_OK) return rc;
@@ -776,15 +609,15 @@ inline int launch_tn(const float* G_hi, const float* G_lo, int ldg, int Mo, cons
     return CP_OK;
 }
 
-// [windows][12][64] fp32 activation as (32-channel half, position, window) boxes {32, 12, 10}
-inline int make_tmap_conv(CUtensorMap* m, const float* base, int64_t windows) {
+// [windows][12][64] fp16 activation as (64 channels, position, window) boxes {64, 12, box_windows}
+inline int make_tmap_conv(CUtensorMap* m, const plane_t* base, int64_t windows, int box_windows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return CP_ERR_UNSUPPORTED;
     cuuint64_t dims[3] = {64, 12, (cuuint64_t)windows};
-    cuuint64_t strides[2] = {64 * 4, 12 * 64 * 4};
-    cuuint32_t box[3] = {32, 12, CONV_WIN};
+    cuuint64_t strides[2] = {64 * 2, 12 * 64 * 2};
+    cuuint32_t box[3] = {64, 12, (cuuint32_t)box_windows};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<plane_t*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? CP_OK : CP_ERR_ARG;
@@ -806,77 +639,47 @@ inline int launch_nt_cfg(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, con
     return CP_OK;
 }
 
-// CTA-pair (cta_group::2) kernel for N % 256 == 0.  Measured on B200 at M = 167,936, N = K = 512: 0.399-0.449 ms vs
-// 0.392-0.402 ms for the single-CTA kernel (its 2 x 256 TMEM columns leave no room to double-buffer the accumulators,
-// so the epilogue is exposed: tensor pipe 57 % vs 69 %).  Correct (bring-up test green) but OFF by default.
-static bool g_use_pair = false;
-
-inline int launch_nt(const float* A_hi, const float* A_lo, int64_t M, int K, int lda, const float* B_hi,
-                     const float* B_lo, int N, int ldb, const float* bias, float* C, int ldc, float* psum,
-                     float* psq, int relu, cudaStream_t st) {
-    if (K % BK != 0 || N % BN != 0 || lda % 4 != 0 || ldb % 4 != 0) return CP_ERR_ARG;
+// (A cta_group::2 CTA-pair variant of this kernel -- 256 x 256 tiles, each CTA staging half of B -- was built
+// and measured in round 1: correct, but 0.399-0.449 ms vs 0.392-0.402 ms at M = 167,936, N = K = 512, because its
+// 2 x 256 TMEM columns leave no room to double-buffer the accumulators and the epilogue is exposed.  Removed.)
+inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K, int lda, const plane_t* B_hi,
+                     const plane_t* B_lo, int N, int ldb, const float* bias, float* C, int ldc, float* psum,
+                     float* psq, int relu, cudaStream_t st, const float* out_scale = nullptr) {
+    if (K % BK != 0 || N % BN != 0 || lda % 8 != 0 || ldb % 8 != 0) return CP_ERR_ARG;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     int rc;
     if ((rc = make_tmap_2d(&ta_hi, A_hi, M, K, lda, BM)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&ta_lo, A_lo, M, K, lda, BM)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi, B_hi, N, K, ldb, BN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, N, K, ldb, BN)) != CP_OK) return rc;
-    NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu};
-    if (g_use_pair && N % pair::BN2 == 0) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
-            attr_set = true;
-        }
-        const int64_t n_tiles = cp_cdiv(M, 2 * BM) * (N / pair::BN2);
-        const int clusters = (int)(n_tiles < CP_NUM_SMS / 2 ? n_tiles : CP_NUM_SMS / 2);
-        gemm_tc_nt_pair_kernel<<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g);
-        CP_CHECK_LAUNCH();
-        return CP_OK;
-    }
+    NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu, out_scale};
     return launch_nt_cfg<128, false>(ta_hi, ta_lo, tb_hi, tb_lo, g, cp_cdiv(M, BM), st);
 }
 
 // conv2 as implicit GEMM: C[(w,p), o] = act(sum_{tap,c} X[w, p+tap-1, c] * B[o, tap*64+c] + bias[o]);
 // X planes are [windows][12][64], B planes [64][192]; partial statistics rows = ceil(windows/10)
-inline int launch_conv_nt(const float* X_hi, const float* X_lo, int64_t windows, const float* B_hi,
-                          const float* B_lo, const float* bias, float* C, float* psum, float* psq, int relu,
-                          cudaStream_t st) {
+inline int launch_conv_nt(const plane_t* X_hi, const plane_t* X_lo, int64_t windows, const plane_t* B_hi,
+                          const plane_t* B_lo, const float* bias, float* C, float* psum, float* psq, int relu,
+                          cudaStream_t st, const float* out_scale = nullptr) {
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     int rc;
-    if ((rc = make_tmap_conv(&ta_hi, X_hi, windows)) != CP_OK) return rc;
-    if ((rc = make_tmap_conv(&ta_lo, X_lo, windows)) != CP_OK) return rc;
+    if ((rc = make_tmap_conv(&ta_hi, X_hi, windows, CONV_WIN)) != CP_OK) return rc;
+    if ((rc = make_tmap_conv(&ta_lo, X_lo, windows, CONV_WIN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi, B_hi, 64, 192, 192, 64)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, 64, 192, 192, 64)) != CP_OK) return rc;
-    NtArgs g{C, 64, bias, psum, psq, windows * 12, 64, 192, relu};
+    NtArgs g{C, 64, bias, psum, psq, windows * 12, 64, 192, relu, out_scale};
     return launch_nt_cfg<64, true>(ta_hi, ta_lo, tb_hi, tb_lo, g, cp_cdiv(windows, CONV_WIN), st);
 }
 
 // conv2 weight gradient; P capacity >= splits*256*64 floats; *splits_out = number of slabs written
-inline int launch_conv_tn(const float* X_hi, const float* X_lo, const float* G_hi, const float* G_lo,
+inline int launch_conv_tn(const plane_t* X_hi, const plane_t* X_lo, const plane_t* G_hi, const plane_t* G_lo,
                           int64_t windows, float* P, size_t p_capacity_elems, int* splits_out, cudaStream_t st) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return CP_ERR_UNSUPPORTED;
     CUtensorMap tx_hi, tx_lo, tg_hi, tg_lo;
-    auto mk_x = [&](CUtensorMap* m, const float* base) {
-        cuuint64_t dims[3] = {64, 12, (cuuint64_t)windows};
-        cuuint64_t strides[2] = {64 * 4, 12 * 64 * 4};
-        cuuint32_t box[3] = {32, 12, CW_WIN};
-        cuuint32_t estr[3] = {1, 1, 1};
-        return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-    };
-    auto mk_g = [&](CUtensorMap* m, const float* base) {
-        cuuint64_t dims[3] = {32, (cuuint64_t)(windows * 12), 2};
-        cuuint64_t strides[2] = {64 * 4, 128};
-        cuuint32_t box[3] = {32, CW_ROWS, 2};
-        cuuint32_t estr[3] = {1, 1, 1};
-        return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-    };
-    if (!mk_x(&tx_hi, X_hi) || !mk_x(&tx_lo, X_lo) || !mk_g(&tg_hi, G_hi) || !mk_g(&tg_lo, G_lo)) return CP_ERR_ARG;
+    int rc;
+    if ((rc = make_tmap_conv(&tx_hi, X_hi, windows, CW_WIN)) != CP_OK) return rc;
+    if ((rc = make_tmap_conv(&tx_lo, X_lo, windows, CW_WIN)) != CP_OK) return rc;
+    if ((rc = make_tmap_2d(&tg_hi, G_hi, windows * 12, 64, 64, CW_ROWS)) != CP_OK) return rc;
+    if ((rc = make_tmap_2d(&tg_lo, G_lo, windows * 12, 64, 64, CW_ROWS)) != CP_OK) return rc;
     static bool attr_set = false;
     if (!attr_set) {
         CP_CUDA(cudaFuncSetAttribute(gemm_tc_tn_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM));
@@ -899,27 +702,28 @@ inline int launch_conv_tn(const float* X_hi, const float* X_lo, const float* G_h
 
 }  // namespace tcg
 
-// x -> (hi, lo) planes: hi = rna_tf32(x), lo = rna_tf32(x - hi)
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+// x*scale -> (hi, lo) fp16 planes: hi = fp16(x), lo = fp16((x - hi) * 2048); x = hi + lo/2048 to 22 bits.
+// The clamp keeps hi finite for |x| beyond the fp16 range (never reached by BatchNorm outputs or weights).
+__device__ __forceinline__ void split_f16(float x, plane_t& hi, plane_t& lo) {
+    x = fminf(fmaxf(x, -65000.f), 65000.f);
+    hi = __float2half_rn(x);
+    lo = __float2half_rn((x - __half2float(hi)) * CP_LO_SCALE);
 }
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = tf32_rna(x);
-    lo = tf32_rna(x - hi);
-}
-__device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
-    split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y);
-    split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+// four consecutive elements -> 8-byte stores into the two planes (element index v*4)
+__device__ __forceinline__ void split_store4(const float4& x, plane_t* hi, plane_t* lo, int64_t v) {
+    plane_t h[4], l[4];
+    split_f16(x.x, h[0], l[0]); split_f16(x.y, h[1], l[1]);
+    split_f16(x.z, h[2], l[2]); split_f16(x.w, h[3], l[3]);
+    reinterpret_cast<uint2*>(hi)[v] = *reinterpret_cast<const uint2*>(h);
+    reinterpret_cast<uint2*>(lo)[v] = *reinterpret_cast<const uint2*>(l);
 }
 
 __global__ void __launch_bounds__(256)
-split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n4) {
+split_planes_kernel(const float* __restrict__ x, plane_t* __restrict__ hi, plane_t* __restrict__ lo, int64_t n4,
+                    float scale) {
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n4; v += (int64_t)gridDim.x * blockDim.x) {
-        float4 h, l;
-        split_tf32(__ldg(reinterpret_cast<const float4*>(x) + v), h, l);
-        reinterpret_cast<float4*>(hi)[v] = h;
-        reinterpret_cast<float4*>(lo)[v] = l;
+        float4 a = __ldg(reinterpret_cast<const float4*>(x) + v);
+        a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+        split_store4(a, hi, lo, v);
     }
 }

@@ -1,4 +1,4 @@
-// Stand-alone bring-up test of the tcgen05 3xTF32 GEMM (not part of libcpros.so).
+// Stand-alone bring-up test of the tcgen05 fp16-split GEMMs (not part of libcpros.so).
 //   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o build/tc_gemm_test <this file>
 #include <cstdio>
 #include <cstdlib>
@@ -17,9 +17,10 @@ int run_nt(int64_t M, int N, int K, bool check, int reps) {
     for (auto& v : A) v = frand();
     for (auto& v : B) v = frand() * 0.1f;
     for (auto& v : bias) v = frand();
-    float *dA, *dAh, *dAl, *dB, *dBh, *dBl, *dbias, *dC, *dps, *dpq;
-    CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dAh, A.size() * 4)); CK(cudaMalloc(&dAl, A.size() * 4));
-    CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dBh, B.size() * 4)); CK(cudaMalloc(&dBl, B.size() * 4));
+    float *dA, *dB, *dbias, *dC, *dps, *dpq;
+    plane_t *dAh, *dAl, *dBh, *dBl;
+    CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dAh, A.size() * 2)); CK(cudaMalloc(&dAl, A.size() * 2));
+    CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dBh, B.size() * 2)); CK(cudaMalloc(&dBl, B.size() * 2));
     CK(cudaMalloc(&dbias, N * 4)); CK(cudaMalloc(&dC, (size_t)M * N * 4));
     const int64_t tm = (M + 127) / 128;
     CK(cudaMalloc(&dps, tm * N * 4)); CK(cudaMalloc(&dpq, tm * N * 4));
@@ -27,8 +28,8 @@ int run_nt(int64_t M, int N, int K, bool check, int reps) {
     CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dbias, bias.data(), N * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(dC, 0xff, (size_t)M * N * 4));
-    split_tf32_kernel<<<1024, 256>>>(dA, dAh, dAl, (int64_t)A.size() / 4);
-    split_tf32_kernel<<<256, 256>>>(dB, dBh, dBl, (int64_t)B.size() / 4);
+    split_planes_kernel<<<1024, 256>>>(dA, dAh, dAl, (int64_t)A.size() / 4, 1.f);
+    split_planes_kernel<<<256, 256>>>(dB, dBh, dBl, (int64_t)B.size() / 4, 1.f);
     CK(cudaDeviceSynchronize());
     int rc = tcg::launch_nt(dAh, dAl, M, K, K, dBh, dBl, N, K, dbias, dC, N, dps, dpq, 1, 0);
     if (rc) { printf("launch rc=%d\n", rc); return 1; }
@@ -76,7 +77,7 @@ int run_nt(int64_t M, int N, int K, bool check, int reps) {
             cudaEventRecord(e1);
             CK(cudaDeviceSynchronize());
             float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
-            printf("NT M=%lld N=%d K=%d stats=%d: %.3f ms  %.1f TFLOP/s (fp32-equivalent), %.1f TFLOP/s tf32 issued\n",
+            printf("NT M=%lld N=%d K=%d stats=%d: %.3f ms  %.1f TFLOP/s (fp32-equivalent), %.1f TFLOP/s fp16 issued\n",
                    (long long)M, N, K, variant == 0, ms, 2.0 * M * N * K / ms / 1e9, 6.0 * M * N * K / ms / 1e9);
         }
     }
@@ -89,15 +90,16 @@ int run_tn(int64_t R, int Mo, int No, bool check, int reps) {
     std::vector<float> G((size_t)R * Mo), A((size_t)R * No);
     for (auto& v : G) v = frand();
     for (auto& v : A) v = frand() + 0.3f;
-    float *dG, *dGh, *dGl, *dA, *dAh, *dAl, *dP;
+    float *dG, *dA, *dP;
+    plane_t *dGh, *dGl, *dAh, *dAl;
     const size_t cap = (size_t)32 * Mo * No;
-    CK(cudaMalloc(&dG, G.size() * 4)); CK(cudaMalloc(&dGh, G.size() * 4)); CK(cudaMalloc(&dGl, G.size() * 4));
-    CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dAh, A.size() * 4)); CK(cudaMalloc(&dAl, A.size() * 4));
+    CK(cudaMalloc(&dG, G.size() * 4)); CK(cudaMalloc(&dGh, G.size() * 2)); CK(cudaMalloc(&dGl, G.size() * 2));
+    CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dAh, A.size() * 2)); CK(cudaMalloc(&dAl, A.size() * 2));
     CK(cudaMalloc(&dP, cap * 4));
     CK(cudaMemcpy(dG, G.data(), G.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
-    split_tf32_kernel<<<1024, 256>>>(dG, dGh, dGl, (int64_t)G.size() / 4);
-    split_tf32_kernel<<<1024, 256>>>(dA, dAh, dAl, (int64_t)A.size() / 4);
+    split_planes_kernel<<<1024, 256>>>(dG, dGh, dGl, (int64_t)G.size() / 4, 1.f);
+    split_planes_kernel<<<1024, 256>>>(dA, dAh, dAl, (int64_t)A.size() / 4, 1.f);
     CK(cudaDeviceSynchronize());
     int S = 0;
     int rc = tcg::launch_tn(dGh, dGl, Mo, Mo, dAh, dAl, No, No, R, dP, cap, &S, 0);
@@ -139,15 +141,14 @@ int run_tn(int64_t R, int Mo, int No, bool check, int reps) {
 
 int main(int argc, char** argv) {
     int bad = 0;
-    if (argc > 1 && argv[1][0] == '1') tcg::g_use_pair = false;
-    printf("pair kernel: %d\n", (int)tcg::g_use_pair);
     const bool quick = argc > 2;
     if (!quick) {
-        bad |= run_nt(128, 128, 32, true, 0);
+        bad |= run_nt(128, 128, 64, true, 0);
         bad |= run_nt(128, 128, 512, true, 0);
         bad |= run_nt(1000, 512, 768, true, 0);
         bad |= run_nt(4100, 512, 512, true, 0);
-        bad |= run_tn(32, 128, 128, true, 0);
+        bad |= run_tn(64, 128, 128, true, 0);
+        bad |= run_tn(48, 128, 128, true, 0);
         bad |= run_tn(1000, 128, 128, true, 0);
         bad |= run_tn(5000, 512, 768, true, 0);
         bad |= run_tn(41 * 1000, 512, 512, true, 0);

@@ -71,7 +71,7 @@ typedef struct cp_encoder_tensors {
 #define CP_BN_RUNNING 2        /* running statistics (nn.BatchNorm eval) */
 
 #define CP_ENGINE_SIMT 0       /* fp32 FFMA GEMMs */
-#define CP_ENGINE_TC 1         /* tcgen05 3xTF32 GEMMs (fp32-level accuracy) */
+#define CP_ENGINE_TC 1         /* tcgen05 GEMMs on a 3-product fp16 split (fp32-level accuracy) */
 
 /* SyncBN hook (optional).  Sums `count` doubles at device pointer `buf` over all ranks, in place, ordered on
  * `stream`; returns 0 on success.  A C/C++ host implements it with
@@ -120,11 +120,12 @@ int cp_encoder_read_activation(const void *workspace, size_t workspace_bytes, in
 int cp_linear_forward(const float *A, const float *W, const float *bias, float *Y, int64_t M, int N,
                       int K, int relu, float *col_sum, float *col_sqsum, void *workspace,
                       size_t workspace_bytes, int engine, void *stream);
-/* Tensor-core engine operand format: x = hi + lo with hi = tf32(x), lo = tf32(x - hi) (n % 4 == 0). */
-int cp_split_tf32(const float *x, float *hi, float *lo, int64_t n, void *stream);
+/* Tensor-core engine operand format: two fp16 planes, x = hi + lo/2048 with hi = fp16(x),
+ * lo = fp16((x - hi) * 2048) (22 significand bits; n % 4 == 0). */
+int cp_split_planes(const float *x, uint16_t *hi, uint16_t *lo, int64_t n, void *stream);
 /* cp_linear_forward (CP_ENGINE_TC) on pre-split operands: exactly the per-layer launch of the encoder
- * (N % 128 == 0, K % 32 == 0).  col_sum / col_sqsum may both be NULL. */
-int cp_linear_forward_planes(const float *A_hi, const float *A_lo, const float *W_hi, const float *W_lo,
+ * (N % 128 == 0, K % 64 == 0).  col_sum / col_sqsum may both be NULL. */
+int cp_linear_forward_planes(const uint16_t *A_hi, const uint16_t *A_lo, const uint16_t *W_hi, const uint16_t *W_lo,
                              const float *bias, float *Y, int64_t M, int N, int K, int relu,
                              float *col_sum, float *col_sqsum, void *workspace, size_t workspace_bytes,
                              void *stream);
