@@ -420,20 +420,21 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             if (used[b]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b], 0));     // WAR on the G1 buffer
             CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], g1(b), true, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
                                      gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st, o));
-            CP_CUDA(cudaEventRecord(g_side.ready[b], st));
             const int K = l == 0 ? K_FC1 : F_FC;
             const float* ain = l == 0 ? w.A2 : w.A[l - 1];
             const plane_t* ah = hi_of(ain);
             const plane_t* al = lo_of(ain, l == 0 ? conv_elems : fc_elems);
             const float* gsi = w.gscale_inv + 2 + l;
-            // side stream: dW_l = G1^T . A_{l-1}
+            // main stream: G0 = G1 . W_l
+            CP_TRY(tcg::launch_nt(hi_of(g1(b)), g1lo(b, fc_elems), n, F_FC, F_FC, w.Wth[l], w.Wtl[l], K, F_FC, nullptr, w.G0,
+                                  K, nullptr, nullptr, 0, st, gsi));
+            // side stream: dW_l = G1^T . A_{l-1}.  It starts when the data-gradient GEMM above has finished (two
+            // persistent GEMMs cannot share an SM), i.e. alongside the HBM-bound BN-backward kernels of layer l-1
+            CP_CUDA(cudaEventRecord(g_side.ready[b], st));
             CP_CUDA(cudaStreamWaitEvent(ss, g_side.ready[b], 0));
             CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, ss, gsi));
             CP_CUDA(cudaEventRecord(g_side.done[b], ss));
             used[b] = true;
-            // main stream: G0 = G1 . W_l
-            CP_TRY(tcg::launch_nt(hi_of(g1(b)), g1lo(b, fc_elems), n, F_FC, F_FC, w.Wth[l], w.Wtl[l], K, F_FC, nullptr, w.G0,
-                                  K, nullptr, nullptr, 0, st, gsi));
         }
         // conv2 block: G0 is [n*12, 64] (same memory order as the [n,768] position-major flatten)
         const int b = nb & 1;

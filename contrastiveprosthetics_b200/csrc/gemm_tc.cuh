@@ -51,14 +51,35 @@ struct Smem {
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + (int)sizeof(Smem);
 
 // geometry of the K-major kernel as a function of the N tile
+constexpr int OUT_BOX = 32 * 32 * 4;                  // epilogue staging: one 32 x 32 fp32 box per warp (TMA store)
 template <int BN_> struct NtCfg {
     static constexpr int B_TILE = BN_ * BK * 2;
     static constexpr int STAGE = 2 * TILE_BYTES + 2 * B_TILE;
     static constexpr int NSTAGES = BN_ == 128 ? 3 : 4;
     static constexpr int ACC = 2 * BN_;               // main + correction accumulator
     static constexpr int TMEM = 4 * BN_;              // double buffered
-    static constexpr int SMEM = NSTAGES * STAGE + 1024 + (int)sizeof(Smem);
+    static constexpr int SMEM = NSTAGES * STAGE + 4 * OUT_BOX + 1024 + (int)sizeof(Smem);
 };
+
+// Epilogue store of one warp's 32 rows x 32 columns: the lane's 32 values go to the warp's staging box in
+// the 128B-swizzled layout (conflict-free 16-byte shared stores), then ONE TMA store writes the box -- rows
+// beyond M are clipped by the tensor map.  Direct per-lane global stores (32 half-used sectors per instruction)
+// made the epilogue LSU-bound once the fp16 main loop halved the time per tile.
+__device__ __forceinline__ void store_box_tma(const CUtensorMap* tm_c, uint8_t* box, const float (&v)[32], int lane,
+                                              int col, int64_t row0) {
+    if (lane == 0) tc::tma_store_wait_read();          // the previous store of this warp has left the box
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    tc::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        tc::tma_store_2d(tm_c, box, col, (int)row0);
+        tc::tma_store_commit();
+    }
+}
 
 struct NtArgs {
     float* C; int ldc;
@@ -92,13 +113,14 @@ template <int BN_, bool CONV>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                  const NtArgs g) {
+                  const __grid_constant__ CUtensorMap tm_c, const NtArgs g) {
     using Cfg = NtCfg<BN_>;
     constexpr int ROWS = CONV ? CONV_ROWS : BM;                 // data rows per tile
     constexpr uint32_t A_BYTES = ROWS * BK * 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    Smem* sm = reinterpret_cast<Smem*>(tiles + Cfg::NSTAGES * Cfg::STAGE);
+    uint8_t* out_boxes = tiles + Cfg::NSTAGES * Cfg::STAGE;                     // 4 x 4 KB, 1024-aligned
+    Smem* sm = reinterpret_cast<Smem*>(out_boxes + 4 * OUT_BOX);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int tiles_n = g.N / BN_;
@@ -109,6 +131,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     if (warp == 0 && tc::elect_one()) {
         tc::prefetch_tmap(&tm_a_hi); tc::prefetch_tmap(&tm_a_lo);
         tc::prefetch_tmap(&tm_b_hi); tc::prefetch_tmap(&tm_b_lo);
+        tc::prefetch_tmap(&tm_c);
         for (int s = 0; s < Cfg::NSTAGES; ++s) { tc::mbar_init(&sm->full[s], 1); tc::mbar_init(&sm->empty[s], 1); }
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&sm->tmem_full[a], 1); tc::mbar_init(&sm->tmem_empty[a], 4); }
         tc::fence_barrier_init();
@@ -219,10 +242,22 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
-                if (row_ok) {
-                    float4* dst = reinterpret_cast<float4*>(g.C + row * g.ldc + col);
+                if (CONV) {
+                    // one [120 rows][32 columns] box per CTA and chunk (the tile's last 8 MMA rows carry no data)
+                    if (et == 0) tc::tma_store_wait_read();
+                    tc::named_bar_sync(2, EPI_THREADS);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(out_boxes + rl * 128 + ((j ^ (rl & 7)) << 4)) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    tc::fence_proxy_async();
+                    tc::named_bar_sync(2, EPI_THREADS);
+                    if (et == 0) {
+                        tc::tma_store_2d(&tm_c, out_boxes, col, (int)(tile_m * ROWS));
+                        tc::tma_store_commit();
+                    }
+                } else {
+                    store_box_tma(&tm_c, out_boxes + q * OUT_BOX, v, lane, col, tile_m * ROWS + q * 32);
                 }
                 if (g.psum) {
                     float sq[32];
@@ -252,10 +287,198 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 tc::named_bar_sync(1, EPI_THREADS);
             }
         }
+        if (lane == 0) tc::tma_store_wait_read();                 // shared memory must outlive the last TMA store
     }
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM);
+}
+
+// ---------------------------------------------------------------------------- CTA-pair forward / dgrad
+// Same math as gemm_tc_nt_kernel<128>, issued as cta_group::2 MMAs on a 256 x 128 tile owned by a pair of CTAs
+// (cluster 2x1x1).  The single-CTA kernel is bound by L2 -> SM bandwidth (every CTA re-fetches the full
+// 128-column B tile: 512 KB of operand loads per 128 x 128 tile, ~9 TB/s chip-wide); here each CTA stages its
+// own 128 rows of A but only HALF of the B tile (64 of the 128 rows) -- the tensor cores of the pair read each
+// other's half -- so operand loads drop to 384 KB per 128 x 128 tile and shared-memory reads per MMA by 25 %.
+// The leader CTA (cluster rank 0) issues every MMA; TMA completions of both CTAs are accounted on the leader's
+// `full` barriers; tcgen05.commit multicasts the `empty` / `tmem_full` arrivals to both CTAs.  TMEM per CTA:
+// 2 buffers x (128 main + 128 correction) columns, so the epilogue (8 warps) overlaps the next main loop.
+namespace pair {
+constexpr int THREADS2 = 320;            // TMA warp, MMA warp, 8 epilogue warps
+constexpr int EPI2 = 256;
+constexpr int B_HALF = (BN / 2) * BK * 2;                 // 8 KB: this CTA's 64 rows of a B plane
+constexpr int STAGE2 = 2 * TILE_BYTES + 2 * B_HALF;       // A_hi, A_lo, B_hi/2, B_lo/2 = 48 KB
+constexpr int STAGES2 = 3;
+struct Smem2 {
+    uint64_t full[STAGES2], empty[STAGES2], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+    float csum[4][BN];
+    float csq[4][BN];
+};
+constexpr int SMEM2 = STAGES2 * STAGE2 + 8 * OUT_BOX + 1024 + (int)sizeof(Smem2);
+}  // namespace pair
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair::THREADS2, 1)
+gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                       const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                       const __grid_constant__ CUtensorMap tm_c, const NtArgs g) {
+    using namespace pair;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* out_boxes = tiles + STAGES2 * STAGE2;                              // 8 x 4 KB, 1024-aligned
+    Smem2* sm = reinterpret_cast<Smem2*>(out_boxes + 8 * OUT_BOX);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t rank = tc::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int tiles_n = g.N / BN;
+    const int64_t tiles_m = (g.M + 2 * BM - 1) / (2 * BM);
+    const int64_t n_tiles = tiles_m * tiles_n;
+    const int kblocks = g.K / BK;
+    const int64_t cluster_id = blockIdx.x / 2, n_clusters = gridDim.x / 2;
+
+    if (warp == 0 && tc::elect_one()) {
+        tc::prefetch_tmap(&tm_a_hi); tc::prefetch_tmap(&tm_a_lo);
+        tc::prefetch_tmap(&tm_b_hi); tc::prefetch_tmap(&tm_b_lo);
+        for (int s = 0; s < STAGES2; ++s) { tc::mbar_init(&sm->full[s], 1); tc::mbar_init(&sm->empty[s], 1); }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(&sm->tmem_full[a], 1);
+            tc::mbar_init(&sm->tmem_empty[a], 16);       // 8 epilogue warps x 2 CTAs arrive on the leader's copy
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) {
+        tc::tmem_alloc_pair(&sm->tmem_base, 512);
+        tc::tmem_relinquish_pair();
+    }
+    tc::tc_fence_before();
+    tc::cluster_sync();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = sm->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (tc::elect_one()) {
+            int s = 0; uint32_t ph = 0;
+            for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
+                const int m0 = (int)(t / tiles_n) * 2 * BM + (int)rank * BM;
+                const int n0 = (int)(t % tiles_n) * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    tc::mbar_wait(&sm->empty[s], ph ^ 1);
+                    uint8_t* st = tiles + s * STAGE2;
+                    if (leader) tc::mbar_expect_tx(&sm->full[s], 2 * STAGE2);          // bytes of both CTAs
+                    tc::tma_load_2d_pair(st, &tm_a_hi, &sm->full[s], kb * BK, m0);
+                    tc::tma_load_2d_pair(st + TILE_BYTES, &tm_a_lo, &sm->full[s], kb * BK, m0);
+                    tc::tma_load_2d_pair(st + 2 * TILE_BYTES, &tm_b_hi, &sm->full[s], kb * BK, n0);
+                    tc::tma_load_2d_pair(st + 2 * TILE_BYTES + B_HALF, &tm_b_lo, &sm->full[s], kb * BK, n0);
+                    if (++s == STAGES2) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && tc::elect_one()) {
+            constexpr uint32_t idesc = tc::idesc_f16(2 * BM, BN, 0, 0);
+            int s = 0; uint32_t ph = 0;
+            int it = 0;
+            for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
+                const int acc = it & 1;
+                tc::mbar_wait(&sm->tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d = tmem_base + acc * ACC_COLS;
+                const uint32_t dc = d + BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    tc::mbar_wait(&sm->full[s], ph);
+                    tc::tc_fence_after();
+                    const uint32_t base = tc::smem_u32(tiles + s * STAGE2);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint32_t ko = k * UMMA_K * 2;
+                        const uint64_t a_hi = tc::smem_desc_sw128(base + ko, 16, 1024);
+                        const uint64_t a_lo = tc::smem_desc_sw128(base + TILE_BYTES + ko, 16, 1024);
+                        const uint64_t b_hi = tc::smem_desc_sw128(base + 2 * TILE_BYTES + ko, 16, 1024);
+                        const uint64_t b_lo = tc::smem_desc_sw128(base + 2 * TILE_BYTES + B_HALF + ko, 16, 1024);
+                        tc::mma_f16_pair(dc, a_lo, b_hi, idesc, (kb | k) != 0);
+                        tc::mma_f16_pair(dc, a_hi, b_lo, idesc, 1);
+                        tc::mma_f16_pair(d, a_hi, b_hi, idesc, (kb | k) != 0);
+                    }
+                    tc::mma_commit_pair(&sm->empty[s]);
+                    if (++s == STAGES2) { s = 0; ph ^= 1; }
+                }
+                tc::mma_commit_pair(&sm->tmem_full[acc]);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9 of both CTAs) =====================
+        const int q = warp % 4;                      // TMEM lane quadrant
+        const int half = (warp - 2) / 4;             // column half: 0 -> 0..63, 1 -> 64..127
+        const int et = threadIdx.x - 64;             // 0..255
+        const float oscale = g.out_scale ? __ldg(g.out_scale) : 1.f;
+        const float cscale = CP_LO_INV * oscale;
+        int it = 0;
+        for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
+            const int acc = it & 1;
+            const int64_t tile_m = (t / tiles_n) * 2 + rank;            // 128-row tile index of this CTA
+            const int n0 = (int)(t % tiles_n) * BN;
+            const int64_t row = tile_m * BM + q * 32 + lane;
+            const bool row_ok = row < g.M;
+            tc::mbar_wait(&sm->tmem_full[acc], (it >> 1) & 1);
+            tc::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                const int cl = half * 64 + c * 32;                      // column inside the tile
+                float v[32], vc[32];
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + cl;
+                tc::tmem_ld32(ta, v);
+                tc::tmem_ld32(ta + BN, vc);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaf(vc[j], cscale, v[j] * oscale);
+                const int col = n0 + cl;
+                if (g.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col + j));
+                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                    }
+                }
+                if (g.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                store_box_tma(&tm_c, out_boxes + (warp - 2) * OUT_BOX, v, lane, col, tile_m * BM + q * 32);
+                if (g.psum) {
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = row_ok ? v[j] : 0.f;
+                        sq[j] = v[j] * v[j];
+                    }
+                    warp_col_reduce32(v, lane);
+                    warp_col_reduce32(sq, lane);
+                    sm->csum[q][cl + lane] = v[0];
+                    sm->csq[q][cl + lane] = sq[0];
+                }
+            }
+            // accumulator drained -> hand it back to the leader's MMA warp
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(tc::mapa(tc::smem_u32(&sm->tmem_empty[acc]), 0));
+            if (g.psum) {
+                tc::named_bar_sync(1, EPI2);
+                if (et < BN && tile_m * BM < g.M) {
+                    g.psum[tile_m * g.N + n0 + et] = sm->csum[0][et] + sm->csum[1][et] + sm->csum[2][et] + sm->csum[3][et];
+                    g.psq[tile_m * g.N + n0 + et] = sm->csq[0][et] + sm->csq[1][et] + sm->csq[2][et] + sm->csq[3][et];
+                }
+                tc::named_bar_sync(1, EPI2);
+            }
+        }
+        if (lane == 0) tc::tma_store_wait_read();
+    }
+    tc::tc_fence_before();
+    tc::cluster_sync();
+    if (warp == 1) tc::tmem_dealloc_pair(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------- weight gradient
@@ -623,9 +846,23 @@ inline int make_tmap_conv(CUtensorMap* m, const plane_t* base, int64_t windows, 
     return r == CUDA_SUCCESS ? CP_OK : CP_ERR_ARG;
 }
 
+// fp32 output [rows, cols] (leading dimension ld floats): 32 x 32 boxes, 128B swizzle (TMA store, rows clipped)
+inline int make_tmap_out(CUtensorMap* m, float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows = 32) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return CP_ERR_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? CP_OK : CP_ERR_ARG;
+}
+
 template <int BN_, bool CONV>
 inline int launch_nt_cfg(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
-                         const CUtensorMap& tb_lo, const NtArgs& g, int64_t tiles_m, cudaStream_t st) {
+                         const CUtensorMap& tb_lo, const CUtensorMap& tc_out, const NtArgs& g, int64_t tiles_m,
+                         cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_kernel<BN_, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -634,26 +871,40 @@ inline int launch_nt_cfg(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, con
     }
     const int64_t n_tiles = tiles_m * (g.N / BN_);
     const int grid = (int)(n_tiles < CP_NUM_SMS ? n_tiles : CP_NUM_SMS);
-    gemm_tc_nt_kernel<BN_, CONV><<<grid, THREADS, NtCfg<BN_>::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g);
+    gemm_tc_nt_kernel<BN_, CONV><<<grid, THREADS, NtCfg<BN_>::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
 
-// (A cta_group::2 CTA-pair variant of this kernel -- 256 x 256 tiles, each CTA staging half of B -- was built
-// and measured in round 1: correct, but 0.399-0.449 ms vs 0.392-0.402 ms at M = 167,936, N = K = 512, because its
-// 2 x 256 TMEM columns leave no room to double-buffer the accumulators and the epilogue is exposed.  Removed.)
+static bool g_use_pair = true;       // CTA-pair (cta_group::2) kernel for the plain (non-conv) K-major GEMMs
 inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K, int lda, const plane_t* B_hi,
                      const plane_t* B_lo, int N, int ldb, const float* bias, float* C, int ldc, float* psum,
                      float* psq, int relu, cudaStream_t st, const float* out_scale = nullptr) {
-    if (K % BK != 0 || N % BN != 0 || lda % 8 != 0 || ldb % 8 != 0) return CP_ERR_ARG;
-    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    if (K % BK != 0 || N % BN != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldc % 4 != 0) return CP_ERR_ARG;
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_out;
     int rc;
+    if ((rc = make_tmap_out(&tc_out, C, M, N, ldc)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&ta_hi, A_hi, M, K, lda, BM)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&ta_lo, A_lo, M, K, lda, BM)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi, B_hi, N, K, ldb, BN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, N, K, ldb, BN)) != CP_OK) return rc;
     NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu, out_scale};
-    return launch_nt_cfg<128, false>(ta_hi, ta_lo, tb_hi, tb_lo, g, cp_cdiv(M, BM), st);
+    if (g_use_pair && M > BM) {
+        CUtensorMap tb_hi2, tb_lo2;                                   // B boxes of 64 rows: half a tile per CTA
+        if ((rc = make_tmap_2d(&tb_hi2, B_hi, N, K, ldb, BN / 2)) != CP_OK) return rc;
+        if ((rc = make_tmap_2d(&tb_lo2, B_lo, N, K, ldb, BN / 2)) != CP_OK) return rc;
+        static bool attr_set = false;
+        if (!attr_set) {
+            CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
+            attr_set = true;
+        }
+        const int64_t n_tiles = cp_cdiv(M, 2 * BM) * (N / BN);
+        const int clusters = (int)(n_tiles < CP_NUM_SMS / 2 ? n_tiles : CP_NUM_SMS / 2);
+        gemm_tc_nt_pair_kernel<<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, g);
+        CP_CHECK_LAUNCH();
+        return CP_OK;
+    }
+    return launch_nt_cfg<128, false>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(M, BM), st);
 }
 
 // conv2 as implicit GEMM: C[(w,p), o] = act(sum_{tap,c} X[w, p+tap-1, c] * B[o, tap*64+c] + bias[o]);
@@ -661,14 +912,15 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
 inline int launch_conv_nt(const plane_t* X_hi, const plane_t* X_lo, int64_t windows, const plane_t* B_hi,
                           const plane_t* B_lo, const float* bias, float* C, float* psum, float* psq, int relu,
                           cudaStream_t st, const float* out_scale = nullptr) {
-    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_out;
     int rc;
+    if ((rc = make_tmap_out(&tc_out, C, windows * 12, 64, 64, CONV_ROWS)) != CP_OK) return rc;
     if ((rc = make_tmap_conv(&ta_hi, X_hi, windows, CONV_WIN)) != CP_OK) return rc;
     if ((rc = make_tmap_conv(&ta_lo, X_lo, windows, CONV_WIN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi, B_hi, 64, 192, 192, 64)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, 64, 192, 192, 64)) != CP_OK) return rc;
     NtArgs g{C, 64, bias, psum, psq, windows * 12, 64, 192, relu, out_scale};
-    return launch_nt_cfg<64, true>(ta_hi, ta_lo, tb_hi, tb_lo, g, cp_cdiv(windows, CONV_WIN), st);
+    return launch_nt_cfg<64, true>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st);
 }
 
 // conv2 weight gradient; P capacity >= splits*256*64 floats; *splits_out = number of slabs written

@@ -141,6 +141,8 @@ int run_tn(int64_t R, int Mo, int No, bool check, int reps) {
 
 int main(int argc, char** argv) {
     int bad = 0;
+    if (argc > 1 && argv[1][0] == '1') tcg::g_use_pair = false;
+    printf("pair kernel: %d\n", (int)tcg::g_use_pair);
     const bool quick = argc > 2;
     if (!quick) {
         bad |= run_nt(128, 128, 64, true, 0);
