@@ -304,7 +304,12 @@ def run_cuda(args):
         roof = {"kernel": kname + ": Linear 512->512 + bias + ReLU + BN-stat partials at the step's shape "
                           "(M = 167,936); 7 fwd + 7 dgrad + 7 wgrad launches of this family per step",
                 "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                "frac": ach / peaks["bf16_tflops"],
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this shape, from the
+                # ncu --set full capture profiles/r1_ncu_gemm_nt_pair_f16_summary.txt (algorithmic: 344 MB of fp16
+                # operand planes in + 344 MB of fp32 out = 688 MB; the weights stay in L2)
+                "traffic": 649.2e6 if use_tc else None, "traffic_unit": "bytes/launch",
+                "peak_source": peaks["source"],
                 "ms_per_launch": gms,
                 "note": "achieved = algorithmic fp32 FLOPs (2MNK); the fp32-parity path issues 3 fp16 tensor-core "
                         "products per algorithmic product (x = hi + lo/2048), so its ceiling is 1/3 of the "
