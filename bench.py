@@ -38,6 +38,32 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+class stdout_to_stderr:
+    """fd-level redirect: NCCL prints its version banner to stdout when the first communicator is created; the
+    driver wants exactly ONE JSON line there."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
+def init_distributed():
+    import torch.distributed as dist
+    from contrastiveprosthetics_b200 import dist as cpdist
+    with stdout_to_stderr():
+        rank, world, dev = cpdist.init_from_env()
+        if world > 1:
+            dist.barrier()                 # creates the NCCL communicator (and its banner) now
+            torch.cuda.synchronize()
+    return rank, world, dev
+
+
 class ClockSampler:
     """Samples SM clock + throttle reasons during the timed region (NVML, 100 ms period)."""
 
@@ -147,7 +173,7 @@ def run_cuda(args):
     from contrastiveprosthetics_b200.models import Model
     from contrastiveprosthetics_b200.utils import TaskWrapper
 
-    rank, world, dev = cpdist.init_from_env()
+    rank, world, dev = init_distributed()
     assert dev.type == "cuda", "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
     L = _lib.lib()
     B = args.batch_size
@@ -384,7 +410,7 @@ def run_c5(args):
     from contrastiveprosthetics_b200.load import DB23
     from contrastiveprosthetics_b200.utils import TaskWrapper
 
-    rank, world, dev = cpdist.init_from_env()
+    rank, world, dev = init_distributed()
     assert dev.type == "cuda", "bench.py needs a GPU (no CPU fallback)"
     L = _lib.lib()
     B = args.clip_batch
