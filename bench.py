@@ -334,7 +334,7 @@ def run_cuda(args):
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this shape, from the
                 # ncu --set full capture profiles/r1_ncu_gemm_nt_pair_f16_summary.txt (algorithmic: 344 MB of fp16
                 # operand planes in + 344 MB of fp32 out = 688 MB; the weights stay in L2)
-                "traffic": 649.2e6 if use_tc else None, "traffic_unit": "bytes/launch",
+                "traffic": 654.8e6 if use_tc else None, "traffic_unit": "bytes/launch",
                 "peak_source": peaks["source"],
                 "ms_per_launch": gms,
                 "note": "achieved = algorithmic fp32 FLOPs (2MNK); the fp32-parity path issues 3 fp16 tensor-core "
