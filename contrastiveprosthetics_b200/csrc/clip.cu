@@ -115,12 +115,12 @@ __global__ void __launch_bounds__(THREADS, 1) clip_sweep_kernel(const SweepArgs 
     float acc_sum[4] = {0.f, 0.f, 0.f, 0.f};
     float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     int best_j[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
-    float d[4][D];
+    float2 d2[2][D];                                     // rows (0,1) and (2,3) of this thread, packed
     if (GRAD) {
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii)
+        for (int ip = 0; ip < 2; ++ip)
 #pragma unroll
-            for (int k = 0; k < D; ++k) d[ii][k] = 0.f;
+            for (int k = 0; k < D; ++k) d2[ip][k] = make_float2(0.f, 0.f);
     }
 
     load_tile(0, 0);
@@ -134,57 +134,70 @@ __global__ void __launch_bounds__(THREADS, 1) clip_sweep_kernel(const SweepArgs 
         }
         __syncthreads();
 
-        float s[4][8];
+        // similarities of this thread's 4 x 8 micro-tile, two own rows per packed FMA
+        float2 s2[2][8];
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii)
+        for (int ip = 0; ip < 2; ++ip)
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) s[ii][jj] = 0.f;
+            for (int jj = 0; jj < 8; ++jj) s2[ip][jj] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            const float4 y0 = *reinterpret_cast<const float4*>(&Ys[buf][k][tx * 8]);
-            const float4 y1 = *reinterpret_cast<const float4*>(&Ys[buf][k][tx * 8 + 4]);
+            const float4 y0 = *reinterpret_cast<const float4*>(&Ys[buf][k][tx * 4]);
+            const float4 y1 = *reinterpret_cast<const float4*>(&Ys[buf][k][64 + tx * 4]);
             const float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
             const float4 xv = *reinterpret_cast<const float4*>(&Xs[k][ty * 4]);
-            const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float2 xp[2] = {make_float2(xv.x, xv.y), make_float2(xv.z, xv.w)};
 #pragma unroll
-            for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) s[ii][jj] = fmaf(x[ii], y[jj], s[ii][jj]);
+            for (int jj = 0; jj < 8; ++jj) {
+                const float2 yy = make_float2(y[jj], y[jj]);
+                ffma2(s2[0][jj], xp[0], yy);
+                ffma2(s2[1][jj], xp[1], yy);
+            }
         }
-        const int64_t jbase = t * LOOP + tx * 8;
+        float s[4][8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            s[0][jj] = s2[0][jj].x; s[1][jj] = s2[0][jj].y; s[2][jj] = s2[1][jj].x; s[3][jj] = s2[1][jj].y;
+        }
+        // this thread's 8 loop columns: tx*4 .. tx*4+3 and 64 + tx*4 .. (two conflict-free 16-byte lanes per row)
+        const int64_t jbase = t * LOOP + tx * 4;
+#define CLIP_COL(jj) (jbase + ((jj) < 4 ? (jj) : 60 + (jj)))
         if (!GRAD) {
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
-                const bool ok = jbase + jj < g.n_loop;
+                const bool ok = CLIP_COL(jj) < g.n_loop;
 #pragma unroll
                 for (int ii = 0; ii < 4; ++ii) {
                     const float e = ok ? ex2(fmaf(s[ii][jj], g.a, -g.a)) : 0.f;
                     acc_sum[ii] += e;
-                    if (ok && s[ii][jj] > best[ii]) { best[ii] = s[ii][jj]; best_j[ii] = (int)(jbase + jj); }
+                    if (ok && s[ii][jj] > best[ii]) { best[ii] = s[ii][jj]; best_j[ii] = (int)CLIP_COL(jj); }
                 }
             }
         } else {
-            const float4 l0 = *reinterpret_cast<const float4*>(&Ls[buf][tx * 8]);
-            const float4 l1 = *reinterpret_cast<const float4*>(&Ls[buf][tx * 8 + 4]);
+            const float4 l0 = *reinterpret_cast<const float4*>(&Ls[buf][tx * 4]);
+            const float4 l1 = *reinterpret_cast<const float4*>(&Ls[buf][64 + tx * 4]);
             const float il[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
-                const bool ok = jbase + jj < g.n_loop;
+                const bool ok = CLIP_COL(jj) < g.n_loop;
 #pragma unroll
                 for (int ii = 0; ii < 4; ++ii) {
                     const float e = ok ? ex2(fmaf(s[ii][jj], g.a, -g.a)) : 0.f;
                     s[ii][jj] = e * (inv_own[ii] + il[jj]);
                 }
             }
+            // d[ii][k] += sum_jj c[ii][jj] * y[k][jj], two own rows per packed FMA
 #pragma unroll
             for (int k = 0; k < D; ++k) {
-                const float4 y0 = *reinterpret_cast<const float4*>(&Ys[buf][k][tx * 8]);
-                const float4 y1 = *reinterpret_cast<const float4*>(&Ys[buf][k][tx * 8 + 4]);
+                const float4 y0 = *reinterpret_cast<const float4*>(&Ys[buf][k][tx * 4]);
+                const float4 y1 = *reinterpret_cast<const float4*>(&Ys[buf][k][64 + tx * 4]);
                 const float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
 #pragma unroll
-                for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) d[ii][k] = fmaf(s[ii][jj], y[jj], d[ii][k]);
+                for (int jj = 0; jj < 8; ++jj) {
+                    const float2 yy = make_float2(y[jj], y[jj]);
+                    ffma2(d2[0][k], make_float2(s[0][jj], s[1][jj]), yy);
+                    ffma2(d2[1][k], make_float2(s[2][jj], s[3][jj]), yy);
+                }
             }
         }
         __syncthreads();
@@ -212,7 +225,10 @@ __global__ void __launch_bounds__(THREADS, 1) clip_sweep_kernel(const SweepArgs 
     } else {
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
-            const float tot = reduce16_scatter(d[ii], tx);
+            float dsum[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) dsum[k] = (ii & 1) ? d2[ii >> 1][k].y : d2[ii >> 1][k].x;
+            const float tot = reduce16_scatter(dsum, tx);
             if (i0 + ii < g.n_own) g.d_own[(i0 + ii) * D + tx] = g.coef * tot;
         }
     }

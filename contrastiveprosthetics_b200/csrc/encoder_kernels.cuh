@@ -577,8 +577,9 @@ proj_bwd_data_kernel(const float* __restrict__ d, const float* __restrict__ Wp, 
             float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int o = 0; o < CP_EMB_DIM; ++o) {
-                o4.x = fmaf(dd[o], w[o].x, o4.x); o4.y = fmaf(dd[o], w[o].y, o4.y);
-                o4.z = fmaf(dd[o], w[o].z, o4.z); o4.w = fmaf(dd[o], w[o].w, o4.w);
+                const float2 d2 = make_float2(dd[o], dd[o]);
+                ffma2(reinterpret_cast<float2*>(&o4)[0], d2, make_float2(w[o].x, w[o].y));
+                ffma2(reinterpret_cast<float2*>(&o4)[1], d2, make_float2(w[o].z, w[o].w));
             }
             reinterpret_cast<float4*>(ga + (r0 + i) * K)[q] = o4;
         }
@@ -614,10 +615,12 @@ proj_bwd_weight_kernel(const float* __restrict__ d, const float* __restrict__ a,
             const float dd[CP_EMB_DIM] = {dv[i][0].x, dv[i][0].y, dv[i][0].z, dv[i][0].w, dv[i][1].x, dv[i][1].y,
                                           dv[i][1].z, dv[i][1].w, dv[i][2].x, dv[i][2].y, dv[i][2].z, dv[i][2].w,
                                           dv[i][3].x, dv[i][3].y, dv[i][3].z, dv[i][3].w};
+            const float2 xlo = make_float2(x[i].x, x[i].y), xhi = make_float2(x[i].z, x[i].w);
 #pragma unroll
             for (int o = 0; o < CP_EMB_DIM; ++o) {
-                acc[o].x = fmaf(dd[o], x[i].x, acc[o].x); acc[o].y = fmaf(dd[o], x[i].y, acc[o].y);
-                acc[o].z = fmaf(dd[o], x[i].z, acc[o].z); acc[o].w = fmaf(dd[o], x[i].w, acc[o].w);
+                const float2 d2 = make_float2(dd[o], dd[o]);
+                ffma2(reinterpret_cast<float2*>(&acc[o])[0], d2, xlo);
+                ffma2(reinterpret_cast<float2*>(&acc[o])[1], d2, xhi);
             }
         }
     }
