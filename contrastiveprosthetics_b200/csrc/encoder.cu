@@ -10,6 +10,7 @@
 //                              column-permuted copy of its weight (prep_weights_kernel).
 //   linear stages [n, 512]
 //   per stage: Y (post-ReLU, pre-BN; kept for backward) and A (post-BN/dropout = next GEMM input).
+//   The conv1 stage has no Y: its 3-FMA activation is recomputed from the 48-byte window wherever it is needed.
 // BatchNorm statistics are produced by the GEMM / conv epilogues as per-CTA partial column sums
 // (no second pass over the activation) and finalised in double precision.
 //
@@ -44,6 +45,7 @@ struct Ws {
     unsigned int* tickets;     // [16] last-CTA tickets (zero-initialised once per workspace)
     float *wpart;              // split-K weight-gradient partials
     float *Wc2, *Wc2d, *W1p;
+    float *c1w, *c1b;          // copy of the conv1 parameters (parity tap)
     float *ppart;              // projection / conv1 weight-gradient partials
     // tensor-core engine: an activation / gradient slot holds both fp16 planes (hi_of / lo_of); split weights
     float *Wc2_lo, *Wc2d_lo;
@@ -80,7 +82,7 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     const size_t conv_elems = (size_t)n * 12 * F_CONV, fc_elems = (size_t)n * F_FC;
     w.X0 = c.take<float>((size_t)n * 12);
     if (save) {
-        w.Y1 = c.take<float>(conv_elems); w.A1 = c.take<float>(conv_elems);
+        w.Y1 = nullptr; w.A1 = c.take<float>(conv_elems);
         w.Y2 = c.take<float>(conv_elems); w.A2 = c.take<float>(conv_elems);
         for (int l = 0; l < CP_N_FC; ++l) { w.Y[l] = c.take<float>(fc_elems); w.A[l] = c.take<float>(fc_elems); }
         w.G0 = c.take<float>(conv_elems);
@@ -90,7 +92,7 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
         float* y = c.take<float>(conv_elems);
         float* a0 = c.take<float>(conv_elems);
         float* a1 = c.take<float>(conv_elems);
-        w.Y1 = w.Y2 = y; w.A1 = a0; w.A2 = a1;
+        w.Y1 = nullptr; w.Y2 = y; w.A1 = a0; w.A2 = a1;
         for (int l = 0; l < CP_N_FC; ++l) { w.Y[l] = y; w.A[l] = (l & 1) ? a1 : a0; }
         w.G0 = w.G1 = nullptr;
     }
@@ -111,8 +113,10 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     w.Wc2 = c.take<float>(64 * 192);
     w.Wc2d = c.take<float>(64 * 192);
     w.W1p = c.take<float>(F_FC * K_FC1);
+    w.c1w = c.take<float>(64 * 9);
+    w.c1b = c.take<float>(64);
     w.ppart = save ? c.take<float>((size_t)cp_cdiv(n, PROJ_W_ROWS) * CP_EMB_DIM * 512 +
-                                   (size_t)cp_cdiv(n * 12, 1024) * 3 * 64)
+                                   (size_t)cp_cdiv(n, C1_WIN) * 3 * 64)
                    : nullptr;
     w.Wc2_lo = w.Wc2d_lo = w.G1b = nullptr;
     for (int l = 0; l < CP_N_FC; ++l) w.Wh[l] = w.Wl[l] = w.Wth[l] = w.Wtl[l] = nullptr;
@@ -315,7 +319,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
 
     CP_CUDA(cudaMemsetAsync(w.tickets, 0, 64 * sizeof(unsigned int), st));
     prep_weights_kernel<<<(F_FC * K_FC1 + 255) / 256, 256, 0, st>>>(p->conv2_w, p->fc_w[0], w.Wc2, w.Wc2d, w.W1p,
-                                                                    w.Wc2_lo, w.Wc2d_lo);
+                                                                    w.Wc2_lo, w.Wc2d_lo, p->conv1_w, p->conv1_b, w.c1w, w.c1b);
     CP_CHECK_LAUNCH();
     if (tcE) {
         for (int l = 0; l < CP_N_FC; ++l) {
@@ -327,12 +331,19 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     }
     CP_CUDA(cudaMemcpyAsync(w.X0, x, sizeof(float) * R12, cudaMemcpyDeviceToDevice, st));
 
-    // conv1 -> ReLU (+stats) -> BN
-    const int P1 = (int)cp_cdiv(R12, ColMap<F_CONV>::ROWS);
-    conv1_fwd_kernel<<<P1, 256, 0, st>>>(w.X0, R12, p->conv1_w, p->conv1_b, w.Y1, w.pa, w.pb);
+    // conv1 -> ReLU -> BN: a statistics pass and an apply pass, both recomputing the activation from x
+    const int P1 = (int)cp_cdiv(n, C1_WIN);
+    conv1_fwd_kernel<<<P1, 256, 0, st>>>(w.X0, n, p->conv1_w, p->conv1_b, nullptr, w.pa, w.pb);
     CP_CHECK_LAUNCH();
     CP_TRY(bn_finalize(w, 0, F_CONV, P1, R12, p, o, st));
-    CP_TRY(bn_apply<F_CONV>(w.Y1, w.A1, tcE, R12, w, 0, nullptr, 1.f, st));
+    if (tcE)
+        conv1_bn_apply_kernel<true><<<ew_grid(n * 16), 256, 0, st>>>(
+            w.X0, n, p->conv1_w, p->conv1_b, w.scale[0], w.shift[0], w.A1,
+            reinterpret_cast<float*>(reinterpret_cast<plane_t*>(w.A1) + conv_elems));
+    else
+        conv1_bn_apply_kernel<false><<<ew_grid(n * 16), 256, 0, st>>>(w.X0, n, p->conv1_w, p->conv1_b, w.scale[0],
+                                                                       w.shift[0], w.A1, nullptr);
+    CP_CHECK_LAUNCH();
 
     // conv2 as implicit GEMM [n*12, 192] x [64, 192]^T
     if (tcE) {
@@ -405,7 +416,6 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     CP_CHECK_LAUNCH();
 
     // linear blocks, last to first.  G0 = grad w.r.t. block output, G1 = grad w.r.t. pre-activation
-    float* g1_conv1 = w.G1;
     cudaEvent_t join_event = nullptr;
     if (tcE) {
         CP_TRY(g_side.init());
@@ -452,9 +462,6 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
         CP_CUDA(cudaEventRecord(g_side.done[b], ss));
         CP_TRY(tcg::launch_conv_nt(hi_of(g1(b)), g1lo(b, conv_elems), n, hi_of(w.Wc2d), hi_of(w.Wc2d_lo), nullptr, w.G0,
                                    nullptr, nullptr, 0, st, w.gscale_inv + 1));
-        // conv1's pre-activation gradient goes to the other buffer (its last reader is two stages back)
-        if (used[b ^ 1]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b ^ 1], 0));
-        g1_conv1 = g1(b ^ 1);
         join_event = g_side.done[b];
     } else {
         for (int l = CP_N_FC - 1; l >= 0; --l) {
@@ -478,12 +485,25 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
         CP_TRY((launch_wgrad<64, 64, true>(w.G1, 64, 64, w.A1, 64, 192, R12, w.wpart, gr->conv2_w, 2, st)));
         CP_TRY((launch_nt<128, 64, 0, true>(w.G1, R12, 192, 64, w.Wc2d, 64, 192, nullptr, w.G0, 64, nullptr, nullptr, 0, st)));
     }
-    // conv1 block
-    CP_TRY(bn_backward<F_CONV>(w.G0, w.Y1, g1_conv1, false, R12, w, 0, nullptr, 1.f, p->bn_w[0], gr->bn_w[0],
-                               gr->bn_b[0], gr->conv1_b, st, o));
-    const int P1 = (int)cp_cdiv(R12, ColMap<F_CONV>::ROWS);
+    // conv1 block: BN backward + ReLU backward + weight / bias gradients in two passes over (G0, x); the
+    // pre-activation gradient is never written (the first layer has no data gradient)
+    const int P1 = (int)cp_cdiv(n, C1_WIN);
     float* c1part = w.ppart + (size_t)Pp * CP_EMB_DIM * 512;
-    conv1_bwd_kernel<<<P1, 256, 0, st>>>(g1_conv1, w.X0, R12, c1part);
+    conv1_bn_bwd_reduce_kernel<<<P1, 256, 0, st>>>(w.G0, w.X0, n, p->conv1_w, p->conv1_b, w.mean[0], w.istd[0], w.pa, w.pb);
+    CP_CHECK_LAUNCH();
+    bn_bwd_finalize_kernel<<<dim3(F_CONV / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P1, F_CONV, R12, w.m1, w.m2, gr->bn_w[0],
+                                                                         gr->bn_b[0], w.rscratch, w.tickets,
+                                                                         o->allreduce ? w.totals : nullptr);
+    CP_CHECK_LAUNCH();
+    if (o->allreduce) {
+        CP_TRY(sync_totals(w, F_CONV, o, st));
+        bn_bwd_means_totals_kernel<<<1, 512, 0, st>>>(w.totals, F_CONV, w.m1, w.m2);
+        CP_CHECK_LAUNCH();
+    }
+    conv1_bn_bwd_apply_kernel<<<P1, 256, 0, st>>>(w.G0, w.X0, n, p->conv1_w, p->conv1_b, w.mean[0], w.istd[0], p->bn_w[0],
+                                                  w.m1, w.m2, w.pa, c1part);
+    CP_CHECK_LAUNCH();
+    colsum_finalize_kernel<<<F_CONV / 32, 1024, 0, st>>>(w.pa, P1, F_CONV, gr->conv1_b, 0);
     CP_CHECK_LAUNCH();
     CP_CUDA(cudaMemsetAsync(gr->conv1_w, 0, sizeof(float) * 64 * 9, st));
     colsum_finalize_kernel<<<3 * 64 / 32, 1024, 0, st>>>(c1part, P1, 3 * 64, gr->conv1_w, 1);
@@ -504,6 +524,13 @@ extern "C" int cp_encoder_read_activation(const void* workspace, size_t workspac
     if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     // tensor-core engine: the post-BN slots of all stages but the last hold fp16 planes, not fp32 values
     if (which == 1 && o->engine == CP_ENGINE_TC && stage < CP_N_BN - 1) return CP_ERR_UNSUPPORTED;
+    if (stage == 0 && which == 0) {
+        // the conv1 activation is not stored: recompute it from the saved input and parameter copy
+        conv1_fwd_kernel<<<(unsigned)cp_cdiv(n, C1_WIN), 256, 0, (cudaStream_t)stream>>>(w.X0, n, w.c1w, w.c1b, dst,
+                                                                                         nullptr, nullptr);
+        CP_CHECK_LAUNCH();
+        return CP_OK;
+    }
     const float* src;
     size_t elems;
     if (stage < 2) {

@@ -37,84 +37,216 @@ __device__ __forceinline__ void block_col_reduce(float (&v)[4], float* red /*[RY
 // ------------------------------------------------------------------------------------ conv1
 // y1[(n,p), c] = relu(b[c] + sum_tap w[c,tap] * x[n, p+tap-1])   (models.py:255-256; a 3x3 conv
 // with padding 1 on a 1x12 image only ever sees the middle kernel row)
-__global__ void __launch_bounds__(256)
-conv1_fwd_kernel(const float* __restrict__ x, int64_t R /* = n*12 */, const float* __restrict__ w9,
-                 const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ psum,
-                 float* __restrict__ psq) {
-    constexpr int F = 64;
-    __shared__ float red[ColMap<F>::RY * F];
-    const int qx = threadIdx.x % 16, ry = threadIdx.x / 16;
-    float w[4][3], b[4];
+//
+// The stage costs 3 FMAs per output but its activation is 3 KB per window, so y1 is NEVER stored: every
+// kernel that needs it (statistics, BN apply, BN backward) recomputes it from the 48-byte window -- the same
+// fmaf chain each time, hence bit-identical values in every pass.
+struct Conv1Taps { float w[4][3], b[4]; };          // 4 consecutive output channels
+__device__ __forceinline__ Conv1Taps conv1_taps(const float* __restrict__ w9, const float* __restrict__ bias, int qx) {
+    Conv1Taps t;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int c = qx * 4 + j;
-        b[j] = __ldg(bias + c);
+        t.b[j] = __ldg(bias + c);
 #pragma unroll
-        for (int t = 0; t < 3; ++t) w[j][t] = __ldg(w9 + c * 9 + 3 + t);
+        for (int k = 0; k < 3; ++k) t.w[j][k] = __ldg(w9 + c * 9 + 3 + k);
     }
-    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-    const int64_t r0 = (int64_t)blockIdx.x * ColMap<F>::ROWS;
-    for (int k = ry; k < ColMap<F>::ROWS; k += ColMap<F>::RY) {
-        const int64_t r = r0 + k;
-        if (r >= R) break;
-        const int p = (int)(r % 12);
-        const float xm = p > 0 ? __ldg(x + r - 1) : 0.f;
-        const float x0 = __ldg(x + r);
-        const float xp = p < 11 ? __ldg(x + r + 1) : 0.f;
-        float v[4];
+    return t;
+}
+// Thread layout of the conv1 kernels: 16 threads per window (one per group of 4 channels); a thread holds the
+// 12 samples of its window in registers and walks the 12 positions, so there is no index arithmetic per element
+// and a warp touches 2 x 256 contiguous bytes of the [n*12, 64] activation per position.
+#define C1_WIN 64                                     // windows per CTA of the slab (statistics / backward) kernels
+struct Conv1Window { float x[14]; };                // x[0] = x[13] = 0: the padding of models.py:255
+__device__ __forceinline__ Conv1Window conv1_window(const float* __restrict__ x, int64_t w) {
+    Conv1Window v;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + w * 12));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x + w * 12) + 1);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(x + w * 12) + 2);
+    v.x[0] = 0.f; v.x[13] = 0.f;
+    v.x[1] = a.x; v.x[2] = a.y; v.x[3] = a.z; v.x[4] = a.w;
+    v.x[5] = b.x; v.x[6] = b.y; v.x[7] = b.z; v.x[8] = b.w;
+    v.x[9] = c.x; v.x[10] = c.y; v.x[11] = c.z; v.x[12] = c.w;
+    return v;
+}
+// relu(conv1) at position p (taps x[p-1], x[p], x[p+1] = v.x[p], v.x[p+1], v.x[p+2]) for the thread's 4 channels
+__device__ __forceinline__ void conv1_eval(const Conv1Taps& t, const Conv1Window& v, int p, float (&y)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a = t.b[j];
+        a = fmaf(t.w[j][0], v.x[p], a);
+        a = fmaf(t.w[j][1], v.x[p + 1], a);
+        a = fmaf(t.w[j][2], v.x[p + 2], a);
+        y[j] = fmaxf(a, 0.f);
+    }
+}
+// sum over the 16 window lanes of a CTA; result for the 4 channels of group qx valid in threads with wl == 0
+__device__ __forceinline__ void conv1_block_reduce(float (&v)[4], float* red /*[16][64]*/, int qx, int wl) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[wl * 64 + qx * 4 + j] = v[j];
+    __syncthreads();
+    if (wl == 0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float a = b[j];
-            a = fmaf(w[j][0], xm, a);
-            a = fmaf(w[j][1], x0, a);
-            a = fmaf(w[j][2], xp, a);
-            v[j] = fmaxf(a, 0.f);
-            s[j] += v[j];
-            q[j] = fmaf(v[j], v[j], q[j]);
+            float s = 0.f;
+            for (int y = 0; y < 16; ++y) s += red[y * 64 + qx * 4 + j];
+            v[j] = s;
         }
-        *reinterpret_cast<float4*>(y + r * F + qx * 4) = make_float4(v[0], v[1], v[2], v[3]);
-    }
-    block_col_reduce<F>(s, red, qx, ry);
-    block_col_reduce<F>(q, red, qx, ry);
-    if (ry == 0) {
-        *reinterpret_cast<float4*>(psum + (int64_t)blockIdx.x * F + qx * 4) = make_float4(s[0], s[1], s[2], s[3]);
-        *reinterpret_cast<float4*>(psq + (int64_t)blockIdx.x * F + qx * 4) = make_float4(q[0], q[1], q[2], q[3]);
     }
 }
 
-// dW1[c,tap] = sum_r gz[r,c] * x[r+tap-1]; partial[blk][tap][64]
+// statistics partials of relu(conv1(x)) (psum/psq non-null, [ceil(n/C1_WIN)][64]) and/or the activation itself
+// (y non-null: parity tap)
 __global__ void __launch_bounds__(256)
-conv1_bwd_kernel(const float* __restrict__ gz, const float* __restrict__ x, int64_t R,
-                 float* __restrict__ partial) {
-    constexpr int F = 64;
-    __shared__ float red[ColMap<F>::RY * F];
-    const int qx = threadIdx.x % 16, ry = threadIdx.x / 16;
-    float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
-    const int64_t r0 = (int64_t)blockIdx.x * ColMap<F>::ROWS;
-    for (int k = ry; k < ColMap<F>::ROWS; k += ColMap<F>::RY) {
-        const int64_t r = r0 + k;
-        if (r >= R) break;
-        const int p = (int)(r % 12);
-        const float xm = p > 0 ? __ldg(x + r - 1) : 0.f;
-        const float x0 = __ldg(x + r);
-        const float xp = p < 11 ? __ldg(x + r + 1) : 0.f;
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gz + r * F + qx * 4));
-        const float gv[4] = {g.x, g.y, g.z, g.w};
+conv1_fwd_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ w9,
+                 const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ psum,
+                 float* __restrict__ psq) {
+    __shared__ float red[16 * 64];
+    const int qx = threadIdx.x % 16, wl = threadIdx.x / 16;
+    const Conv1Taps t = conv1_taps(w9, bias, qx);
+    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    for (int wi = wl; wi < C1_WIN; wi += 16) {
+        const int64_t w = (int64_t)blockIdx.x * C1_WIN + wi;
+        if (w >= n) break;
+        const Conv1Window xv = conv1_window(x, w);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            a0[j] = fmaf(gv[j], xm, a0[j]);
-            a1[j] = fmaf(gv[j], x0, a1[j]);
-            a2[j] = fmaf(gv[j], xp, a2[j]);
+        for (int p = 0; p < 12; ++p) {
+            float v[4];
+            conv1_eval(t, xv, p, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s[j] += v[j];
+                q[j] = fmaf(v[j], v[j], q[j]);
+            }
+            if (y) reinterpret_cast<float4*>(y + (w * 12 + p) * 64)[qx] = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
-    block_col_reduce<F>(a0, red, qx, ry);
-    block_col_reduce<F>(a1, red, qx, ry);
-    block_col_reduce<F>(a2, red, qx, ry);
-    if (ry == 0) {
-        float* o = partial + (int64_t)blockIdx.x * 3 * F;
-        *reinterpret_cast<float4*>(o + 0 * F + qx * 4) = make_float4(a0[0], a0[1], a0[2], a0[3]);
-        *reinterpret_cast<float4*>(o + 1 * F + qx * 4) = make_float4(a1[0], a1[1], a1[2], a1[3]);
-        *reinterpret_cast<float4*>(o + 2 * F + qx * 4) = make_float4(a2[0], a2[1], a2[2], a2[3]);
+    if (!psum) return;
+    conv1_block_reduce(s, red, qx, wl);
+    conv1_block_reduce(q, red, qx, wl);
+    if (wl == 0) {
+        *reinterpret_cast<float4*>(psum + (int64_t)blockIdx.x * 64 + qx * 4) = make_float4(s[0], s[1], s[2], s[3]);
+        *reinterpret_cast<float4*>(psq + (int64_t)blockIdx.x * 64 + qx * 4) = make_float4(q[0], q[1], q[2], q[3]);
+    }
+}
+
+// a1 = relu(conv1(x)) * scale + shift, written as fp32 or (SPLIT) as the two fp16 planes of the tensor-core engine
+template <bool SPLIT>
+__global__ void __launch_bounds__(256)
+conv1_bn_apply_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ w9,
+                      const float* __restrict__ bias, const float* __restrict__ scale,
+                      const float* __restrict__ shift, float* __restrict__ a, float* __restrict__ a_lo) {
+    const int qx = threadIdx.x % 16;
+    const Conv1Taps t = conv1_taps(w9, bias, qx);
+    const float4 s = __ldg(reinterpret_cast<const float4*>(scale + qx * 4));
+    const float4 h = __ldg(reinterpret_cast<const float4*>(shift + qx * 4));
+    for (int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 16; w < n;
+         w += (int64_t)gridDim.x * (blockDim.x / 16)) {
+        const Conv1Window xv = conv1_window(x, w);
+#pragma unroll
+        for (int p = 0; p < 12; ++p) {
+            float y[4];
+            conv1_eval(t, xv, p, y);
+            const float4 o = make_float4(fmaf(y[0], s.x, h.x), fmaf(y[1], s.y, h.y), fmaf(y[2], s.z, h.z), fmaf(y[3], s.w, h.w));
+            const int64_t v = (w * 12 + p) * 16 + qx;
+            if (SPLIT) split_store4(o, reinterpret_cast<plane_t*>(a), reinterpret_cast<plane_t*>(a_lo), v);
+            else reinterpret_cast<float4*>(a)[v] = o;
+        }
+    }
+}
+
+// BN backward of the conv1 stage, pass 1: partials of sum g and sum g*xh with xh from the recomputed activation
+__global__ void __launch_bounds__(256)
+conv1_bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ x, int64_t n,
+                           const float* __restrict__ w9, const float* __restrict__ bias,
+                           const float* __restrict__ mean, const float* __restrict__ istd,
+                           float* __restrict__ p1, float* __restrict__ p2) {
+    __shared__ float red[16 * 64];
+    const int qx = threadIdx.x % 16, wl = threadIdx.x / 16;
+    const Conv1Taps t = conv1_taps(w9, bias, qx);
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + qx * 4));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(istd + qx * 4));
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    for (int wi = wl; wi < C1_WIN; wi += 16) {
+        const int64_t w = (int64_t)blockIdx.x * C1_WIN + wi;
+        if (w >= n) break;
+        const Conv1Window xv = conv1_window(x, w);
+        float4 gv[12];
+#pragma unroll
+        for (int p = 0; p < 12; ++p) gv[p] = __ldg(reinterpret_cast<const float4*>(g + (w * 12 + p) * 64) + qx);
+#pragma unroll
+        for (int p = 0; p < 12; ++p) {
+            float y[4];
+            conv1_eval(t, xv, p, y);
+            s1[0] += gv[p].x; s1[1] += gv[p].y; s1[2] += gv[p].z; s1[3] += gv[p].w;
+            s2[0] = fmaf(gv[p].x, (y[0] - mu.x) * is.x, s2[0]);
+            s2[1] = fmaf(gv[p].y, (y[1] - mu.y) * is.y, s2[1]);
+            s2[2] = fmaf(gv[p].z, (y[2] - mu.z) * is.z, s2[2]);
+            s2[3] = fmaf(gv[p].w, (y[3] - mu.w) * is.w, s2[3]);
+        }
+    }
+    conv1_block_reduce(s1, red, qx, wl);
+    conv1_block_reduce(s2, red, qx, wl);
+    if (wl == 0) {
+        *reinterpret_cast<float4*>(p1 + (int64_t)blockIdx.x * 64 + qx * 4) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+        *reinterpret_cast<float4*>(p2 + (int64_t)blockIdx.x * 64 + qx * 4) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+    }
+}
+
+// pass 2: gz = 1[y>0] * gamma*istd * (g - m1 - xh*m2) stays in registers (the first layer has no data gradient);
+// partials of the bias gradient sum gz -> pdb[blk][64] and of the weight gradient
+// dW1[c,tap] = sum_(w,p) gz[(w,p),c] * x[w, p+tap-1] -> pdw[blk][tap][64]
+__global__ void __launch_bounds__(256)
+conv1_bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x, int64_t n,
+                          const float* __restrict__ w9, const float* __restrict__ bias,
+                          const float* __restrict__ mean, const float* __restrict__ istd,
+                          const float* __restrict__ gamma, const float* __restrict__ m1,
+                          const float* __restrict__ m2, float* __restrict__ pdb, float* __restrict__ pdw) {
+    __shared__ float red[16 * 64];
+    const int qx = threadIdx.x % 16, wl = threadIdx.x / 16;
+    const Conv1Taps t = conv1_taps(w9, bias, qx);
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + qx * 4));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(istd + qx * 4));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + qx * 4));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(m1 + qx * 4));
+    const float4 a2 = __ldg(reinterpret_cast<const float4*>(m2 + qx * 4));
+    const float k0 = ga.x * is.x, k1 = ga.y * is.y, k2 = ga.z * is.z, k3 = ga.w * is.w;
+    float sb[4] = {0, 0, 0, 0}, w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0}, w2[4] = {0, 0, 0, 0};
+    for (int wi = wl; wi < C1_WIN; wi += 16) {
+        const int64_t w = (int64_t)blockIdx.x * C1_WIN + wi;
+        if (w >= n) break;
+        const Conv1Window xv = conv1_window(x, w);
+        float4 gv[12];
+#pragma unroll
+        for (int p = 0; p < 12; ++p) gv[p] = __ldg(reinterpret_cast<const float4*>(g + (w * 12 + p) * 64) + qx);
+#pragma unroll
+        for (int p = 0; p < 12; ++p) {
+            float y[4], o[4];
+            conv1_eval(t, xv, p, y);
+            o[0] = y[0] > 0.f ? k0 * (gv[p].x - a1.x - (y[0] - mu.x) * is.x * a2.x) : 0.f;
+            o[1] = y[1] > 0.f ? k1 * (gv[p].y - a1.y - (y[1] - mu.y) * is.y * a2.y) : 0.f;
+            o[2] = y[2] > 0.f ? k2 * (gv[p].z - a1.z - (y[2] - mu.z) * is.z * a2.z) : 0.f;
+            o[3] = y[3] > 0.f ? k3 * (gv[p].w - a1.w - (y[3] - mu.w) * is.w * a2.w) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                sb[j] += o[j];
+                w0[j] = fmaf(o[j], xv.x[p], w0[j]);
+                w1[j] = fmaf(o[j], xv.x[p + 1], w1[j]);
+                w2[j] = fmaf(o[j], xv.x[p + 2], w2[j]);
+            }
+        }
+    }
+    conv1_block_reduce(sb, red, qx, wl);
+    conv1_block_reduce(w0, red, qx, wl);
+    conv1_block_reduce(w1, red, qx, wl);
+    conv1_block_reduce(w2, red, qx, wl);
+    if (wl == 0) {
+        *reinterpret_cast<float4*>(pdb + (int64_t)blockIdx.x * 64 + qx * 4) = make_float4(sb[0], sb[1], sb[2], sb[3]);
+        float* o = pdw + (int64_t)blockIdx.x * 3 * 64;
+        *reinterpret_cast<float4*>(o + 0 * 64 + qx * 4) = make_float4(w0[0], w0[1], w0[2], w0[3]);
+        *reinterpret_cast<float4*>(o + 1 * 64 + qx * 4) = make_float4(w1[0], w1[1], w1[2], w1[3]);
+        *reinterpret_cast<float4*>(o + 2 * 64 + qx * 4) = make_float4(w2[0], w2[1], w2[2], w2[3]);
     }
 }
 
@@ -647,11 +779,16 @@ proj_bwd_weight_kernel(const float* __restrict__ d, const float* __restrict__ a,
 // Wc2d[c][tap*64+o]  = conv2_w[o][c][1][2-tap]       conv2 data-gradient
 // W1p [o][p*64+c]    = fc1_w[o][c*12+p]              fc1 on the position-major flatten
 // Wc2_lo / Wc2d_lo non-null: write the fp16 (hi, lo) planes (tensor-core engine) instead of fp32
+// c1w / c1b: workspace copy of the conv1 parameters (the parity tap recomputes the unsaved conv1 activation)
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(const float* __restrict__ conv2_w, const float* __restrict__ fc1_w,
                     float* __restrict__ Wc2, float* __restrict__ Wc2d, float* __restrict__ W1p,
-                    float* __restrict__ Wc2_lo, float* __restrict__ Wc2d_lo) {
+                    float* __restrict__ Wc2_lo, float* __restrict__ Wc2d_lo,
+                    const float* __restrict__ conv1_w, const float* __restrict__ conv1_b,
+                    float* __restrict__ c1w, float* __restrict__ c1b) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 64 * 9) c1w[i] = __ldg(conv1_w + i);
+    if (i < 64) c1b[i] = __ldg(conv1_b + i);
     if (i < 64 * 192) {
         const int o = i / 192, k = i % 192, tap = k / 64, c = k % 64;
         const float a = __ldg(conv2_w + (o * 64 + c) * 9 + 3 + tap);

@@ -161,3 +161,42 @@ extern "C" int cp_subset_eval(const uint8_t* order, int64_t B, int W, const uint
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
+
+// ------------------------------------------------------------------------- confusion matrix
+// counts[t, p] = #{k : y_true[k] == t and y_pred[k] == p}   (results.py:58: sklearn's confusion_matrix on the
+// voted decisions, labels 0..C-1).  Per-CTA shared-memory histogram (C <= 64: 16 KB of int32), one 64-bit
+// atomic per non-zero cell per CTA; integer adds, so the result does not depend on the order.
+#define CM_MAX_C 64
+__global__ void __launch_bounds__(256)
+confusion_kernel(const int64_t* __restrict__ y_true, const int64_t* __restrict__ y_pred, int64_t n, int C,
+                 unsigned long long* __restrict__ counts, int* __restrict__ err_flag) {
+    __shared__ unsigned int h[CM_MAX_C * CM_MAX_C];
+    for (int e = threadIdx.x; e < C * C; e += blockDim.x) h[e] = 0;
+    __syncthreads();
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = __ldg(y_true + k), p = __ldg(y_pred + k);
+        if (t < 0 || t >= C || p < 0 || p >= C) {
+            if (err_flag) *err_flag = 1;
+            continue;
+        }
+        atomicAdd(&h[(int)t * C + (int)p], 1u);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < C * C; e += blockDim.x)
+        if (h[e]) atomicAdd(counts + e, (unsigned long long)h[e]);
+}
+
+extern "C" int cp_confusion_matrix(const int64_t* y_true, const int64_t* y_pred, int64_t n, int n_classes,
+                                   int64_t* counts, int* err_flag, void* stream) {
+    if (!counts || n < 0 || n_classes <= 0 || n_classes > CM_MAX_C || (n > 0 && (!y_true || !y_pred)))
+        return CP_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    CP_CUDA(cudaMemsetAsync(counts, 0, sizeof(int64_t) * n_classes * n_classes, st));
+    if (n == 0) return CP_OK;
+    int64_t blocks = cp_cdiv(n, 256 * 8);
+    if (blocks > CP_NUM_SMS * 4) blocks = CP_NUM_SMS * 4;
+    confusion_kernel<<<(unsigned)blocks, 256, 0, st>>>(y_true, y_pred, n, n_classes,
+                                                       reinterpret_cast<unsigned long long*>(counts), err_flag);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}

@@ -243,6 +243,24 @@ int cp_rank_rows(const float *logits, int64_t n_rows, uint8_t *order, void *stre
 int cp_subset_eval(const uint8_t *order, int64_t B, int W, const uint8_t *masks, int64_t n_trials,
                    int64_t *correct, int64_t *total, void *stream);
 
+/* ---------------------------------------------------------------- results.py:58 confusion matrix
+ * counts[t*C + p] = number of decisions with y_true == t and y_pred == p (sklearn.metrics.confusion_matrix
+ * on labels 0..C-1, C <= 64).  counts (C*C int64) is OVERWRITTEN; labels outside [0, C) set *err_flag (may be
+ * NULL) and are skipped. */
+int cp_confusion_matrix(const int64_t *y_true, const int64_t *y_pred, int64_t n, int n_classes,
+                        int64_t *counts, int *err_flag, void *stream);
+
+/* ---------------------------------------------------------------- K5: l2 regulariser
+ * Model.l2 / EMGNet.l2 / GLOVENet.l2 (models.py:225-228, 344-349, 467-472): sum over a parameter list of the
+ * un-squared Frobenius norms.  `tensors` / `sizes` / `grads` are HOST arrays of n_tensors (<= 32) device pointers /
+ * element counts.  forward: norms[t] = ||W_t||_2, *total = sum_t norms[t] (both device, OVERWRITTEN).
+ * backward: grads[t] = coef * (*g_total) * W_t / norms[t] (0 where norms[t] == 0), OVERWRITTEN. */
+size_t cp_l2_workspace_bytes(int n_tensors);
+int cp_l2_forward(const float *const *tensors, const int64_t *sizes, int n_tensors, float *norms, float *total,
+                  void *workspace, size_t workspace_bytes, void *stream);
+int cp_l2_backward(const float *const *tensors, const int64_t *sizes, int n_tensors, const float *norms,
+                   const float *g_total, float coef, float *const *grads, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,3 +45,13 @@ def subset_eval(logits, masks):
             correct[t] += int((modes == S).sum())
         total[t] = B * len(S)
     return correct, total
+
+
+def confusion_counts(y_true, y_pred, n_classes):
+    """/root/reference/code/results.py:58 (sklearn.metrics.confusion_matrix with labels 0..C-1): counts[t, p].
+    Pinned by tests/test_oracle_vote.py against sklearn and the reference's data/confusion_matrix.npy."""
+    y_true = np.asarray(y_true).reshape(-1)
+    y_pred = np.asarray(y_pred).reshape(-1)
+    counts = np.zeros((n_classes, n_classes), dtype=np.int64)
+    np.add.at(counts, (y_true, y_pred), 1)
+    return counts

@@ -169,3 +169,25 @@ def test_c1_shaped_training_run(tw):
     assert np.isfinite(losses).all()
     assert np.mean(losses[-10:]) < np.mean(losses[:10]) - 0.1
     assert model.correct() > 2.0 / 41
+
+
+def test_l2_kernel_matches_torch_norms():
+    """K5 (cp_l2_forward / cp_l2_backward) == sum of torch.norm(p) and its autograd gradient (models.py:344-349),
+    including an all-zero tensor (torch's norm backward gives 0 there) and a scaled upstream gradient."""
+    from contrastiveprosthetics_b200.models import _L2Fn
+    g = torch.Generator().manual_seed(3)
+    shapes = [(64, 1, 3, 3), (512, 768), (16, 512), (41,), (7, 5), (1,)]
+    ps = [torch.randn(s, generator=g).cuda().requires_grad_() for s in shapes]
+    ps[4].data.zero_()
+    out = _L2Fn.apply(*ps)
+    (out * 0.37).backward()
+    qs = [p.detach().double().cpu().requires_grad_() for p in ps]
+    ref = sum(torch.norm(q) for q in qs)
+    (ref * 0.37).backward()
+    assert abs(out.item() - ref.item()) <= 1e-6 * ref.item()
+    for p, q in zip(ps, qs):
+        assert torch.isfinite(p.grad).all()
+        assert (p.grad.cpu().double() - q.grad).norm() <= 1e-6 * max(q.grad.norm().item(), 1e-30) + 1e-12
+    assert torch.count_nonzero(ps[4].grad) == 0
+    out2 = _L2Fn.apply(*ps)                                   # deterministic: bit-identical on a second call
+    assert out2.item() == out.item()

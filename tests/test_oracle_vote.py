@@ -92,3 +92,16 @@ def test_grasp_table_structure(golden_dir):
     assert t["mean_grasp"].shape == (40,)
     assert abs(t["min_grasp"][-1] - t["max_grasp"][-1]) < 1e-4
     assert t["mean_grasp"][0] > t["mean_grasp"][9] > t["mean_grasp"][39]
+
+
+def test_confusion_counts_match_sklearn_and_reference_artifact(ref):
+    """results.py:58: the oracle's confusion counts == sklearn's, and reproduce data/confusion_matrix.npy."""
+    import sklearn.metrics as me
+    y_true, y_pred = ref["y_true"], ref["y_pred"]
+    counts = OV.confusion_counts(y_true, y_pred, 41)
+    assert np.array_equal(counts, me.confusion_matrix(y_true, y_pred, labels=np.arange(41)))
+    assert np.array_equal(counts / 48, ref["confusion_matrix"])
+    rs = np.random.RandomState(0)
+    a, b = rs.randint(0, 7, 1000), rs.randint(0, 7, 1000)
+    assert np.array_equal(OV.confusion_counts(a, b, 7), me.confusion_matrix(a, b, labels=np.arange(7)))
+    assert OV.confusion_counts(np.zeros(0, int), np.zeros(0, int), 5).sum() == 0
