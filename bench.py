@@ -281,8 +281,43 @@ def run_cuda(args):
         sink["acc"] = model.corrects[-1]                 # per-group correct counts (B int32) -> host
 
     ms_e2e, _, _ = timed(e2e_step, max(3, args.steps // 2), 2)
-    e2e_value = N * world / (ms_e2e / 1e3)
     d2h = 4 + B * 4
+    modes = {"eager": {"ms_per_step": ms, "e2e_ms_per_step": ms_e2e}}
+    step_mode = e2e_mode = "eager"
+
+    # ---- same step captured once as a CUDA graph (single GPU; bit-identical to the eager step,
+    #      tests/test_gpu_graph.py): one graph launch per step instead of ~400 kernel launches
+    if world == 1 and not args.no_graph:
+        from contrastiveprosthetics_b200.graph import GraphedTrainStep
+        torch.manual_seed(42)
+        model_g = Model(dict(PARAMS), adabn=True, device=str(dev))
+        model_g.emg_net.engine = model.emg_net.engine
+        model_g.set_train()
+        opts_g = [torch.optim.Adam(model_g.emg_net.parameters(), lr=PARAMS['lr_emg'], weight_decay=0, capturable=True),
+                  torch.optim.Adam(model_g.glove_net.parameters(), lr=PARAMS['lr_glove'], weight_decay=0, capturable=True)]
+        gstep = GraphedTrainStep(model_g, opts_g, tw.get_batch(items_ring[0])[0])
+
+        def graph_resident():
+            it["i"] += 1
+            gstep(tw.get_batch(items_ring[it["i"] % len(items_ring)])[0])
+
+        def graph_e2e():
+            it["i"] += 1
+            hE, hl = host_batches[it["i"] % len(host_batches)]
+            loss, ncor = gstep(hE.to(dev, non_blocking=True))
+            sink["loss"] = loss.item()
+            sink["acc"] = ncor.cpu()
+
+        ms_g, clocks_g, _ = timed(graph_resident, args.steps, args.warmup)
+        ms_g_e2e, _, _ = timed(graph_e2e, max(3, args.steps // 2), 2)
+        modes["cuda_graph"] = {"ms_per_step": ms_g, "e2e_ms_per_step": ms_g_e2e}
+        if ms_g < ms:
+            step_mode, ms, clocks = "cuda_graph", ms_g, clocks_g
+            value = N * world / (ms / 1e3)
+        if ms_g_e2e < ms_e2e:
+            e2e_mode, ms_e2e = "cuda_graph", ms_g_e2e
+        del gstep, model_g, opts_g
+    e2e_value = N * world / (ms_e2e / 1e3)
 
     # ---- dominant kernel alone: fc forward GEMM at the step's shape (CUDA events on its stream)
     roof = None
@@ -384,13 +419,15 @@ def run_cuda(args):
                                     if mixed else "DB2-shaped synthetic sEMG"),
                        "batch_size_groups_per_gpu": B, "windows_per_step": N * world,
                        "engine": "simt-fp32" if model.emg_net.engine == 0 else "tcgen05-3xfp16-split",
+                       "step_mode": step_mode + (" (one graph launch per step; gpu_launches counts the kernels of the "
+                                                 "eager step, the graph replays the same ones)" if step_mode == "cuda_graph" else ""),
                        "parallelism": f"dp{world} (sample-sharded, " + ("SyncBN" if args.sync_bn and world > 1 else "local BatchNorm")
                                       + ", one flat grad all-reduce)",
                        "l2_policy": "per-step working set ~8 GB of activations >> 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
-            "roofline": roof, "cpu_baseline": cpu,
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e, "step_mode": e2e_mode},
+            "roofline": roof, "cpu_baseline": cpu, "step_modes": modes,
             "c1_small_batch": c1, "torch_eager_gpu": eager, "hbm_kernels": hbm,
             "subset_eval": {"value": preds_per_s, "unit": "preds/s", "ms": ms_sub,
                             "workload": "C4: 160 items x 25 x 41 test windows x 5760 trials (144 x 40 sizes), "
@@ -540,6 +577,7 @@ def main():
                     help="only the device-resident train steps (for ncu launch lists); prints a reduced line")
     ap.add_argument("--engine", default="tc", choices=["tc", "simt"],
                     help="tc: tcgen05 3xTF32 GEMMs (default); simt: fp32 FFMA GEMMs")
+    ap.add_argument("--no_graph", action="store_true", help="N = 1: skip the CUDA-graph variant of the step")
     ap.add_argument("--sync_bn", action="store_true", help="N > 1: BatchNorm statistics over every rank's rows")
     ap.add_argument("--mixed", action="store_true", help="mixed DB2+DB3 subjects also at N = 1 (default at N > 1)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],

@@ -23,6 +23,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "encoder_kernels.cuh"
+#include "proj_fused.cuh"
 
 namespace {
 
@@ -84,7 +85,11 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     if (save) {
         w.Y1 = nullptr; w.A1 = c.take<float>(conv_elems);
         w.Y2 = c.take<float>(conv_elems); w.A2 = c.take<float>(conv_elems);
-        for (int l = 0; l < CP_N_FC; ++l) { w.Y[l] = c.take<float>(fc_elems); w.A[l] = c.take<float>(fc_elems); }
+        for (int l = 0; l < CP_N_FC; ++l) {
+            w.Y[l] = c.take<float>(fc_elems);
+            // the last block's output only feeds the projection: fused, never stored (proj_fused.cuh)
+            w.A[l] = l + 1 < CP_N_FC ? c.take<float>(fc_elems) : nullptr;
+        }
         w.G0 = c.take<float>(conv_elems);
         w.G1 = c.take<float>(conv_elems);
     } else {
@@ -115,7 +120,7 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     w.W1p = c.take<float>(F_FC * K_FC1);
     w.c1w = c.take<float>(64 * 9);
     w.c1b = c.take<float>(64);
-    w.ppart = save ? c.take<float>((size_t)cp_cdiv(n, PROJ_W_ROWS) * CP_EMB_DIM * 512 +
+    w.ppart = save ? c.take<float>((size_t)pf::grid_for(n) * CP_EMB_DIM * 512 +
                                    (size_t)cp_cdiv(n, C1_WIN) * 3 * 64)
                    : nullptr;
     w.Wc2_lo = w.Wc2d_lo = w.G1b = nullptr;
@@ -283,6 +288,59 @@ struct SideStream {
 };
 SideStream g_side;
 
+// Backward of the last linear block from d_emb: projection weight gradient, BN backward, ReLU backward and the
+// bias gradient in two passes over (Y7, mask, d_emb) -- see proj_fused.cuh.  gz: pre-activation gradient
+// (fp16 planes when `planes`).
+int last_block_backward(const float* d_emb, float* gz, bool planes, int64_t n, const Ws& w, const uint8_t* keep,
+                        float inv_keep, const cp_encoder_tensors* p, const cp_encoder_tensors* gr, cudaStream_t st,
+                        const cp_encoder_opts* o) {
+    constexpr int LL = CP_N_FC - 1, S = CP_N_BN - 1;           // linear layer / BN stage of the last block
+    if (((uintptr_t)d_emb) % 16 != 0) return CP_ERR_ARG;
+    const int G = pf::grid_for(n);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CP_TRY(pf::set_smem(pf::proj_bwd_reduce_kernel<false>));
+        CP_TRY(pf::set_smem(pf::proj_bwd_reduce_kernel<true>));
+        CP_TRY(pf::set_smem(pf::proj_bwd_apply_kernel<false, false>));
+        CP_TRY(pf::set_smem(pf::proj_bwd_apply_kernel<false, true>));
+        CP_TRY(pf::set_smem(pf::proj_bwd_apply_kernel<true, false>));
+        CP_TRY(pf::set_smem(pf::proj_bwd_apply_kernel<true, true>));
+        attr_set = true;
+    }
+    unsigned int* gmax = planes ? w.gmax + S : nullptr;
+    if (keep)
+        pf::proj_bwd_reduce_kernel<true><<<G, 256, pf::SMEM, st>>>(w.Y[LL], keep, d_emb, n, inv_keep, w.scale[S], w.shift[S],
+                                                                   w.mean[S], w.istd[S], p->proj_w, w.pa, w.pb, w.ppart, gmax);
+    else
+        pf::proj_bwd_reduce_kernel<false><<<G, 256, pf::SMEM, st>>>(w.Y[LL], nullptr, d_emb, n, 1.f, w.scale[S], w.shift[S],
+                                                                    w.mean[S], w.istd[S], p->proj_w, w.pa, w.pb, w.ppart, gmax);
+    CP_CHECK_LAUNCH();
+    colsum_finalize_kernel<<<CP_EMB_DIM * F_FC / 32, 1024, 0, st>>>(w.ppart, G, CP_EMB_DIM * F_FC, gr->proj_w, 0);
+    CP_CHECK_LAUNCH();
+    const bool sync = o->allreduce != nullptr;
+    bn_bwd_finalize_kernel<<<dim3(F_FC / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, G, F_FC, n, w.m1, w.m2, gr->bn_w[S],
+                                                                       gr->bn_b[S], w.rscratch, w.tickets,
+                                                                       sync ? w.totals : nullptr);
+    CP_CHECK_LAUNCH();
+    if (sync) {
+        CP_TRY(sync_totals(w, F_FC, o, st));
+        bn_bwd_means_totals_kernel<<<1, 512, 0, st>>>(w.totals, F_FC, w.m1, w.m2);
+        CP_CHECK_LAUNCH();
+    }
+    float* gz_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)n * F_FC) : nullptr;
+#define CP_PF_APPLY(K, SP)                                                                                              \
+    pf::proj_bwd_apply_kernel<K, SP><<<G, 256, pf::SMEM, st>>>(w.Y[LL], keep, d_emb, n, inv_keep, w.mean[S], w.istd[S],  \
+                                                               p->bn_w[S], w.m1, w.m2, p->proj_w, gz, gz_lo, w.pa, gmax, \
+                                                               w.gscale_inv + S)
+    if (keep) { if (planes) CP_PF_APPLY(true, true); else CP_PF_APPLY(true, false); }
+    else { if (planes) CP_PF_APPLY(false, true); else CP_PF_APPLY(false, false); }
+#undef CP_PF_APPLY
+    CP_CHECK_LAUNCH();
+    colsum_finalize_kernel<<<F_FC / 32, 1024, 0, st>>>(w.pa, G, F_FC, gr->fc_b[LL], 0);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
 bool opts_ok(const cp_encoder_opts* o) {
     return o && o->bn_mode >= 0 && o->bn_mode <= 2 && o->dropout_p >= 0.f && o->dropout_p < 1.f &&
            (o->engine == CP_ENGINE_SIMT || o->engine == CP_ENGINE_TC);
@@ -381,13 +439,32 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
                 gen_p = o->dropout_p;              // mask drawn (and stored) inside the BN-apply kernel
             keep = w.keep[d];
         }
-        CP_TRY(bn_apply<F_FC>(w.Y[l], w.A[l], tcE && l + 1 < CP_N_FC, n, w, 2 + l, keep, inv_keep, st, gen_p, o->dropout_seed,
-                              (uint64_t)(l - 3), (const unsigned long long*)o->dropout_step));
+        if (l + 1 < CP_N_FC) {
+            CP_TRY(bn_apply<F_FC>(w.Y[l], w.A[l], tcE, n, w, 2 + l, keep, inv_keep, st, gen_p, o->dropout_seed,
+                                  (uint64_t)(l - 3), (const unsigned long long*)o->dropout_step));
+            continue;
+        }
+        // last block: BN (+ dropout) fused with the 512 -> 16 projection
+        const int G = pf::grid_for(n);
+        const unsigned long long* step = (const unsigned long long*)o->dropout_step;
+        static bool attr_set = false;
+        if (!attr_set) {
+            CP_TRY(pf::set_smem(pf::bn_apply_proj_kernel<0>));
+            CP_TRY(pf::set_smem(pf::bn_apply_proj_kernel<1>));
+            CP_TRY(pf::set_smem(pf::bn_apply_proj_kernel<2>));
+            attr_set = true;
+        }
+        if (!keep)
+            pf::bn_apply_proj_kernel<0><<<G, pf::FWD_THREADS, pf::SMEM, st>>>(w.Y[l], n, w.scale[2 + l], w.shift[2 + l], nullptr, 1.f, 0.f, 0, 0,
+                                                                  nullptr, p->proj_w, emb);
+        else if (gen_p > 0.f)
+            pf::bn_apply_proj_kernel<2><<<G, pf::FWD_THREADS, pf::SMEM, st>>>(w.Y[l], n, w.scale[2 + l], w.shift[2 + l], keep, inv_keep, gen_p,
+                                                                  o->dropout_seed, (uint64_t)(l - 3), step, p->proj_w, emb);
+        else
+            pf::bn_apply_proj_kernel<1><<<G, pf::FWD_THREADS, pf::SMEM, st>>>(w.Y[l], n, w.scale[2 + l], w.shift[2 + l], keep, inv_keep, 0.f, 0,
+                                                                  0, nullptr, p->proj_w, emb);
+        CP_CHECK_LAUNCH();
     }
-    // projection 512 -> 16
-    proj_fwd_kernel<512><<<(unsigned)std::min<int64_t>(cp_cdiv(n, 8 * PROJ_RPW), (int64_t)CP_NUM_SMS * 4), 256, 0, st>>>(
-        w.A[CP_N_FC - 1], p->proj_w, emb, n);
-    CP_CHECK_LAUNCH();
     return CP_OK;
 }
 
@@ -405,15 +482,7 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     const float inv_keep = o->dropout_p > 0.f ? 1.f / (1.f - o->dropout_p) : 1.f;
     CP_CUDA(cudaMemsetAsync(w.gmax, 0, 16 * sizeof(unsigned int), st));
 
-    // projection
-    const int Pp = (int)cp_cdiv(n, PROJ_W_ROWS);
-    proj_bwd_weight_kernel<512><<<Pp, 256, 0, st>>>(d_emb, w.A[CP_N_FC - 1], n, w.ppart);
-    CP_CHECK_LAUNCH();
-    colsum_finalize_kernel<<<CP_EMB_DIM * 512 / 32, 1024, 0, st>>>(w.ppart, Pp, CP_EMB_DIM * 512, gr->proj_w, 0);
-    CP_CHECK_LAUNCH();
-    proj_bwd_data_kernel<512><<<(unsigned)std::min<int64_t>(cp_cdiv(n, 8), (int64_t)CP_NUM_SMS * 8), 256, 0, st>>>(
-        d_emb, p->proj_w, w.G0, n);
-    CP_CHECK_LAUNCH();
+    const int Pp = pf::grid_for(n);          // projection weight-gradient partial rows (last_block_backward)
 
     // linear blocks, last to first.  G0 = grad w.r.t. block output, G1 = grad w.r.t. pre-activation
     cudaEvent_t join_event = nullptr;
@@ -428,8 +497,11 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             const int b = nb & 1;
             const uint8_t* keep = (l >= 3 && o->dropout_p > 0.f) ? w.keep[l - 3] : nullptr;
             if (used[b]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b], 0));     // WAR on the G1 buffer
-            CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], g1(b), true, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
-                                     gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st, o));
+            if (l == CP_N_FC - 1)
+                CP_TRY(last_block_backward(d_emb, g1(b), true, n, w, keep, inv_keep, p, gr, st, o));
+            else
+                CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], g1(b), true, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
+                                         gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st, o));
             const int K = l == 0 ? K_FC1 : F_FC;
             const float* ain = l == 0 ? w.A2 : w.A[l - 1];
             const plane_t* ah = hi_of(ain);
@@ -466,8 +538,11 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     } else {
         for (int l = CP_N_FC - 1; l >= 0; --l) {
             const uint8_t* keep = (l >= 3 && o->dropout_p > 0.f) ? w.keep[l - 3] : nullptr;
-            CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], w.G1, false, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
-                                     gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st, o));
+            if (l == CP_N_FC - 1)
+                CP_TRY(last_block_backward(d_emb, w.G1, false, n, w, keep, inv_keep, p, gr, st, o));
+            else
+                CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], w.G1, false, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
+                                         gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st, o));
             if (l > 0) {
                 CP_TRY((launch_wgrad<128, 128, false>(w.G1, F_FC, F_FC, w.A[l - 1], F_FC, F_FC, n, w.wpart, gr->fc_w[l], 0, st)));
                 CP_TRY((launch_nt<128, 128, 1, false>(w.G1, n, F_FC, F_FC, p->fc_w[l], F_FC, F_FC, nullptr, w.G0, F_FC,
@@ -523,7 +598,8 @@ extern "C" int cp_encoder_read_activation(const void* workspace, size_t workspac
     const Ws w = carve(const_cast<void*>(workspace), n, o);
     if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     // tensor-core engine: the post-BN slots of all stages but the last hold fp16 planes, not fp32 values
-    if (which == 1 && o->engine == CP_ENGINE_TC && stage < CP_N_BN - 1) return CP_ERR_UNSUPPORTED;
+    // ... and the last block's output is fused into the projection, never stored
+    if (which == 1 && (o->engine == CP_ENGINE_TC || stage == CP_N_BN - 1)) return CP_ERR_UNSUPPORTED;
     if (stage == 0 && which == 0) {
         // the conv1 activation is not stored: recompute it from the saved input and parameter copy
         conv1_fwd_kernel<<<(unsigned)cp_cdiv(n, C1_WIN), 256, 0, (cudaStream_t)stream>>>(w.X0, n, w.c1w, w.c1b, dst,

@@ -59,9 +59,9 @@ def test_results_main_after_train_main(tmp_path):
     # subset tables: one row per size 1..40; 40 grasps + rest = the full class set -> every trial identical
     mean, std, mn, mx = (np.load(out + f"{s}_grasp.npy") for s in ("mean", "std", "min", "max"))
     assert mean.shape == std.shape == mn.shape == mx.shape == (40,)
-    assert mn[-1] == mx[-1] == mean[-1] and std[-1] == 0.0
+    assert mn[-1] == mx[-1] and abs(mean[-1] - mn[-1]) < 1e-12 and std[-1] < 1e-12
     assert abs(mean[-1] - np.trace(counts) / (G * 41)) < 1e-12
     assert np.all(mn <= mean) and np.all(mean <= mx)
     # the full-set subset decision equals the voted y_pred (restricted argmax == argmax, same vote)
     tables1 = cpres.subset_tables(torch.from_numpy(logs).cuda(), 25, sizes=[40], trials_per_size=2)
-    assert tables1["mean"][0] == mean[-1]
+    assert abs(tables1["mean"][0] - mean[-1]) < 1e-12
