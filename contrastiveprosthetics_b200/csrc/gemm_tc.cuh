@@ -817,7 +817,10 @@ inline int launch_tn(const plane_t* G_hi, const plane_t* G_lo, int ldg, int Mo, 
         attr_set = true;
     }
     const int tiles = (Mo / BM) * (No / BN);
-    int S = CP_NUM_SMS / tiles;                                   // one CTA per SM, one wave
+    // one wave on ~2/3 of the SMs: this GEMM runs on a side stream next to the HBM-bound BN-backward kernels, and
+    // each of its CTAs pins 48 K registers (255 x 192 threads), leaving room for ONE 256-thread BN CTA on that SM.
+    // Measured at M = 167,936: 9 splits (144 CTAs) 11.10 ms/step, 6 splits 10.96, 4 splits 11.06, 3 splits 11.35
+    int S = (CP_NUM_SMS * 2 / 3) / tiles;
     const int64_t max_s = cp_cdiv(R, (int64_t)BK * CHUNK_KB);
     if (S > max_s) S = (int)max_s;
     const int64_t cap = (int64_t)(p_capacity_elems / ((size_t)Mo * No));
