@@ -176,11 +176,13 @@ def run_cuda(args):
     rank, world, dev = init_distributed()
     assert dev.type == "cuda", "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
     L = _lib.lib()
-    B = args.batch_size
+    # weak scaling (default): --batch_size groups per GPU; strong scaling: --global_batch groups split over the ranks
+    B = args.global_batch // world if args.global_batch else args.batch_size
+    strong = bool(args.global_batch)
     N = B * T
     torch.manual_seed(42)
     model = Model(dict(PARAMS), adabn=True, device=str(dev))
-    model.emg_net.engine = _lib.ENGINE_TC if args.engine == "tc" else _lib.ENGINE_SIMT
+    model.emg_net.engine = {"tc": _lib.ENGINE_TC, "simt": _lib.ENGINE_SIMT, "tc_fp16": _lib.ENGINE_TC_FP16}[args.engine]
     model.emg_net.sync_bn = args.sync_bn
     opt_e = torch.optim.Adam(model.emg_net.parameters(), lr=PARAMS['lr_emg'], weight_decay=0)
     opt_g = torch.optim.Adam(model.glove_net.parameters(), lr=PARAMS['lr_glove'], weight_decay=0)
@@ -287,7 +289,7 @@ def run_cuda(args):
 
     # ---- same step captured once as a CUDA graph (single GPU; bit-identical to the eager step,
     #      tests/test_gpu_graph.py): one graph launch per step instead of ~400 kernel launches
-    if world == 1 and not args.no_graph:
+    if world == 1 and not args.no_graph and not strong:
         from contrastiveprosthetics_b200.graph import GraphedTrainStep
         torch.manual_seed(42)
         model_g = Model(dict(PARAMS), adabn=True, device=str(dev))
@@ -334,7 +336,8 @@ def run_cuda(args):
         ws = torch.empty(nb, dtype=torch.uint8, device=dev)
         P = _lib.ptr
 
-        use_tc = model.emg_net.engine == _lib.ENGINE_TC
+        use_tc = model.emg_net.engine != _lib.ENGINE_SIMT
+        one_product = model.emg_net.engine == _lib.ENGINE_TC_FP16
         if use_tc:      # operands pre-split, as they are inside the encoder (the producing kernels write planes)
             Ah, Al, Wh, Wl = (torch.empty_like(A, dtype=torch.float16), torch.empty_like(A, dtype=torch.float16),
                               torch.empty_like(Wt, dtype=torch.float16), torch.empty_like(Wt, dtype=torch.float16))
@@ -343,8 +346,8 @@ def run_cuda(args):
 
         def gemm():
             if use_tc:
-                _lib.check(L.cp_linear_forward_planes(P(Ah), P(Al), P(Wh), P(Wl), P(bias), P(Y), M, Nn, K, 1, None, None,
-                                                      P(ws), nb, _lib.stream()))
+                _lib.check(L.cp_linear_forward_planes(P(Ah), None if one_product else P(Al), P(Wh), None if one_product else P(Wl),
+                                                      P(bias), P(Y), M, Nn, K, 1, None, None, P(ws), nb, _lib.stream()))
             else:
                 _lib.check(L.cp_linear_forward(P(A), P(Wt), P(bias), P(Y), M, Nn, K, 1, None, None, P(ws), nb,
                                                _lib.ENGINE_SIMT, _lib.stream()))
@@ -360,7 +363,8 @@ def run_cuda(args):
         torch.cuda.synchronize()
         gms = e0.elapsed_time(e1) / reps
         ach = 2.0 * M * Nn * K / (gms * 1e-3) / 1e12
-        kname = ("gemm_tc_nt_kernel (tcgen05 kind::f16, 3-product fp16 split, TMA, TMEM)" if model.emg_net.engine == _lib.ENGINE_TC
+        kname = ("gemm_tc_nt_pair_kernel (tcgen05 kind::f16 cta_group::2, ONE fp16 product, TMA, TMEM)" if one_product else
+                 "gemm_tc_nt_pair_kernel (tcgen05 kind::f16 cta_group::2, 3-product fp16 split, TMA, TMEM)" if use_tc
                  else "gemm_nt_kernel<128,128> (fp32 FFMA)")
         roof = {"kernel": kname + ": Linear 512->512 + bias + ReLU + BN-stat partials at the step's shape "
                           "(M = 167,936); 7 fwd + 7 dgrad + 7 wgrad launches of this family per step",
@@ -369,7 +373,7 @@ def run_cuda(args):
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this shape, from the
                 # ncu --set full capture profiles/r1_ncu_gemm_nt_pair_f16_summary.txt (algorithmic: 344 MB of fp16
                 # operand planes in + 344 MB of fp32 out = 688 MB; the weights stay in L2)
-                "traffic": 654.8e6 if use_tc else None, "traffic_unit": "bytes/launch",
+                "traffic": 654.8e6 if use_tc and not one_product else None, "traffic_unit": "bytes/launch",
                 "peak_source": peaks["source"],
                 "ms_per_launch": gms,
                 "note": "achieved = algorithmic fp32 FLOPs (2MNK); the fp32-parity path issues 3 fp16 tensor-core "
@@ -395,7 +399,7 @@ def run_cuda(args):
     preds_per_s = items_eval * Wv * T * len(masks) / (ms_sub / 1e3)
 
     c1 = eager = hbm = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not strong:
         # the reference's own launch-bound configuration (go.sh:6): eager vs CUDA-graph step
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         from bench_c1 import c1_small_batch
@@ -411,14 +415,15 @@ def run_cuda(args):
         line = {
             "metric": "train sEMG windows/s", "value": value, "unit": "windows/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": ("C3: sample-sharded train step, " if world > 1 else "C2: train step, ") +
+                                   (f"global batch {args.global_batch} groups, " if strong else "") +
                                    f"batch_size {B} groups x 41 windows = {N} windows per GPU per step, AdaBN on, "
                                    "dropout 0.5, fp32, " +
                                    ("DB2+DB3 mixed-subject synthetic sEMG (46 subjects, DB3 subjects 11-channel)"
                                     if mixed else "DB2-shaped synthetic sEMG"),
                        "batch_size_groups_per_gpu": B, "windows_per_step": N * world,
-                       "engine": "simt-fp32" if model.emg_net.engine == 0 else "tcgen05-3xfp16-split",
+                       "engine": {0: "simt-fp32", 1: "tcgen05-3xfp16-split", 2: "tcgen05-1xfp16 (reduced precision, 1e-2 path)"}[model.emg_net.engine],
                        "step_mode": step_mode + (" (one graph launch per step; gpu_launches counts the kernels of the "
                                                  "eager step, the graph replays the same ones)" if step_mode == "cuda_graph" else ""),
                        "parallelism": f"dp{world} (sample-sharded, " + ("SyncBN" if args.sync_bn and world > 1 else "local BatchNorm")
@@ -573,10 +578,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch_size", type=int, default=4096, help="groups of 41 windows per GPU per step")
+    ap.add_argument("--global_batch", type=int, default=0,
+                    help="strong scaling: this many groups per step split over the ranks (C3: 32768); default: weak "
+                         "scaling at --batch_size groups per GPU")
     ap.add_argument("--profile", action="store_true",
                     help="only the device-resident train steps (for ncu launch lists); prints a reduced line")
-    ap.add_argument("--engine", default="tc", choices=["tc", "simt"],
-                    help="tc: tcgen05 3xTF32 GEMMs (default); simt: fp32 FFMA GEMMs")
+    ap.add_argument("--engine", default="tc", choices=["tc", "simt", "tc_fp16"],
+                    help="tc: tcgen05 GEMMs on the 3-product fp16 split, fp32 parity (default); simt: fp32 FFMA GEMMs; "
+                         "tc_fp16: ONE fp16 tensor-core product (TF32-class accuracy; the 1e-2 path, not the headline)")
     ap.add_argument("--no_graph", action="store_true", help="N = 1: skip the CUDA-graph variant of the step")
     ap.add_argument("--sync_bn", action="store_true", help="N > 1: BatchNorm statistics over every rank's rows")
     ap.add_argument("--mixed", action="store_true", help="mixed DB2+DB3 subjects also at N = 1 (default at N > 1)")

@@ -19,7 +19,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 N_BN, N_FC = 9, 7
 BN_BATCH, BN_BATCH_UPDATE, BN_RUNNING = 0, 1, 2
-ENGINE_SIMT, ENGINE_TC = 0, 1
+ENGINE_SIMT, ENGINE_TC, ENGINE_TC_FP16 = 0, 1, 2
 
 
 def _stale():

@@ -14,7 +14,8 @@
 // BatchNorm statistics are produced by the GEMM / conv epilogues as per-CTA partial column sums
 // (no second pass over the activation) and finalised in double precision.
 //
-// Engines (cp_encoder_opts.engine): CP_ENGINE_SIMT runs every GEMM as fp32 FFMA; CP_ENGINE_TC runs conv2 and
+// Engines (cp_encoder_opts.engine): CP_ENGINE_SIMT runs every GEMM as fp32 FFMA; CP_ENGINE_TC_FP16 is CP_ENGINE_TC with
+// ONE tensor-core product on the hi planes only (TF32-class accuracy; the reduced-precision path); CP_ENGINE_TC runs conv2 and
 // the seven linear layers on tcgen05 with the 3-product fp16 split of gemm_tc.cuh: the BN-apply and
 // BN-backward kernels then write their outputs as two fp16 planes (hi, lo) -- both inside the stage's fp32
 // slot, hi in the first half and lo in the second -- that the TMA-fed GEMMs consume directly, and the weights
@@ -127,7 +128,7 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     for (int l = 0; l < CP_N_FC; ++l) w.Wh[l] = w.Wl[l] = w.Wth[l] = w.Wtl[l] = nullptr;
     w.gmax = c.take<unsigned int>(16);
     w.gscale_inv = c.take<float>(16);
-    if (o->engine == CP_ENGINE_TC) {
+    if (o->engine != CP_ENGINE_SIMT) {
         w.Wc2_lo = c.take<float>(64 * 192);
         w.Wc2d_lo = c.take<float>(64 * 192);
         if (save) w.G1b = c.take<float>(conv_elems);
@@ -216,8 +217,8 @@ int bn_finalize(const Ws& w, int l, int F, int P, int64_t R, const cp_encoder_te
 template <int F>
 int bn_apply(const float* y, float* a, bool planes, int64_t R, const Ws& w, int l, uint8_t* keep,
              float inv_keep, cudaStream_t st, float gen_p = 0.f, uint64_t seed = 0, uint64_t layer = 0,
-             const unsigned long long* seed_offset = nullptr) {
-    float* a_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(a) + (size_t)R * F) : nullptr;
+             const unsigned long long* seed_offset = nullptr, int fast = 0) {
+    float* a_lo = planes && !fast ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(a) + (size_t)R * F) : nullptr;
     if (planes)
         bn_apply_kernel<F, true><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, a_lo, R, w.scale[l], w.shift[l], keep,
                                                                      inv_keep, gen_p, seed, layer, seed_offset);
@@ -235,7 +236,8 @@ int bn_backward(const float* g, const float* y, float* gz, bool planes, int64_t 
                 const uint8_t* keep, float inv_keep, const float* gamma, float* d_gamma, float* d_beta,
                 float* d_bias, cudaStream_t st, const cp_encoder_opts* o) {
     const int P = (int)cp_cdiv(R, ColMap<F>::ROWS);
-    float* gz_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)R * F) : nullptr;
+    const bool lo = planes && o->engine != CP_ENGINE_TC_FP16;
+    float* gz_lo = lo ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)R * F) : nullptr;
     bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb, nullptr,
                                                planes ? w.gmax + l : nullptr);
     CP_CHECK_LAUNCH();
@@ -327,7 +329,8 @@ int last_block_backward(const float* d_emb, float* gz, bool planes, int64_t n, c
         bn_bwd_means_totals_kernel<<<1, 512, 0, st>>>(w.totals, F_FC, w.m1, w.m2);
         CP_CHECK_LAUNCH();
     }
-    float* gz_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)n * F_FC) : nullptr;
+    float* gz_lo = planes && o->engine != CP_ENGINE_TC_FP16
+                       ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)n * F_FC) : nullptr;
 #define CP_PF_APPLY(K, SP)                                                                                              \
     pf::proj_bwd_apply_kernel<K, SP><<<G, 256, pf::SMEM, st>>>(w.Y[LL], keep, d_emb, n, inv_keep, w.mean[S], w.istd[S],  \
                                                                p->bn_w[S], w.m1, w.m2, p->proj_w, gz, gz_lo, w.pa, gmax, \
@@ -343,14 +346,14 @@ int last_block_backward(const float* d_emb, float* gz, bool planes, int64_t n, c
 
 bool opts_ok(const cp_encoder_opts* o) {
     return o && o->bn_mode >= 0 && o->bn_mode <= 2 && o->dropout_p >= 0.f && o->dropout_p < 1.f &&
-           (o->engine == CP_ENGINE_SIMT || o->engine == CP_ENGINE_TC);
+           (o->engine == CP_ENGINE_SIMT || o->engine == CP_ENGINE_TC || o->engine == CP_ENGINE_TC_FP16);
 }
 
 // weight-gradient through the tensor-core split-K kernel + the shared re-layout / reduce kernel
 int tc_wgrad(const plane_t* Gh, const plane_t* Gl, int Mo, const plane_t* Ah, const plane_t* Al, int No, int64_t R,
-             float* wpart, float* out, int mode, cudaStream_t st, const float* g_scale_inv) {
+             float* wpart, float* out, int mode, cudaStream_t st, const float* g_scale_inv, int fast = 0) {
     int S = 0;
-    CP_TRY(tcg::launch_tn(Gh, Gl, Mo, Mo, Ah, Al, No, No, R, wpart, WPART_ELEMS, &S, st));
+    CP_TRY(tcg::launch_tn(Gh, Gl, Mo, Mo, Ah, Al, No, No, R, wpart, WPART_ELEMS, &S, st, fast));
     wgrad_reduce_kernel<<<(unsigned)cp_cdiv((int64_t)Mo * No, 256), 256, 0, st>>>(wpart, S, Mo, No, out, mode, g_scale_inv);
     CP_CHECK_LAUNCH();
     return CP_OK;
@@ -368,7 +371,8 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
                                   void* stream) {
     if (!p || !x || !emb || !workspace || n <= 0 || !opts_ok(o)) return CP_ERR_ARG;
     if (((uintptr_t)workspace) % 256 != 0) return CP_ERR_ARG;
-    const bool tcE = o->engine == CP_ENGINE_TC;
+    const bool tcE = o->engine != CP_ENGINE_SIMT;
+    const int fast = o->engine == CP_ENGINE_TC_FP16;      // hi planes only: lo planes are neither written nor read
     const Ws w = carve(workspace, n, o);
     if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -397,7 +401,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     if (tcE)
         conv1_bn_apply_kernel<true><<<ew_grid(n * 16), 256, 0, st>>>(
             w.X0, n, p->conv1_w, p->conv1_b, w.scale[0], w.shift[0], w.A1,
-            reinterpret_cast<float*>(reinterpret_cast<plane_t*>(w.A1) + conv_elems));
+            fast ? nullptr : reinterpret_cast<float*>(reinterpret_cast<plane_t*>(w.A1) + conv_elems));
     else
         conv1_bn_apply_kernel<false><<<ew_grid(n * 16), 256, 0, st>>>(w.X0, n, p->conv1_w, p->conv1_b, w.scale[0],
                                                                        w.shift[0], w.A1, nullptr);
@@ -406,13 +410,13 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     // conv2 as implicit GEMM [n*12, 192] x [64, 192]^T
     if (tcE) {
         CP_TRY(tcg::launch_conv_nt(hi_of(w.A1), lo_of(w.A1, conv_elems), n, hi_of(w.Wc2), hi_of(w.Wc2_lo), p->conv2_b,
-                                   w.Y2, w.pa, w.pb, 1, st));
+                                   w.Y2, w.pa, w.pb, 1, st, nullptr, fast));
         CP_TRY(bn_finalize(w, 1, F_CONV, (int)cp_cdiv(n, tcg::CONV_WIN), R12, p, o, st));
     } else {
         CP_TRY((launch_nt<128, 64, 0, true>(w.A1, R12, 192, 64, w.Wc2, 64, 192, p->conv2_b, w.Y2, 64, w.pa, w.pb, 1, st)));
         CP_TRY(bn_finalize(w, 1, F_CONV, (int)cp_cdiv(R12, 128), R12, p, o, st));
     }
-    CP_TRY(bn_apply<F_CONV>(w.Y2, w.A2, tcE, R12, w, 1, nullptr, 1.f, st));
+    CP_TRY(bn_apply<F_CONV>(w.Y2, w.A2, tcE, R12, w, 1, nullptr, 1.f, st, 0.f, 0, 0, nullptr, fast));
 
     // 7 x Linear -> ReLU -> BN (-> Dropout)
     const float inv_keep = o->dropout_p > 0.f ? 1.f / (1.f - o->dropout_p) : 1.f;
@@ -423,7 +427,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
         if (tcE) {
             const plane_t* in_lo = lo_of(in, l == 0 ? conv_elems : fc_elems);
             CP_TRY(tcg::launch_nt(hi_of(in), in_lo, n, K, K, w.Wh[l], w.Wl[l], F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb,
-                                  1, st));
+                                  1, st, nullptr, fast));
         } else {
             CP_TRY((launch_nt<128, 128, 0, false>(in, n, K, K, W, F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb, 1, st)));
         }
@@ -441,7 +445,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
         }
         if (l + 1 < CP_N_FC) {
             CP_TRY(bn_apply<F_FC>(w.Y[l], w.A[l], tcE, n, w, 2 + l, keep, inv_keep, st, gen_p, o->dropout_seed,
-                                  (uint64_t)(l - 3), (const unsigned long long*)o->dropout_step));
+                                  (uint64_t)(l - 3), (const unsigned long long*)o->dropout_step, fast));
             continue;
         }
         // last block: BN (+ dropout) fused with the 512 -> 16 projection
@@ -473,7 +477,8 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
                                    const cp_encoder_opts* o, void* stream) {
     if (!p || !d_emb || !gr || !workspace || n <= 0 || !opts_ok(o)) return CP_ERR_ARG;
     if (!o->save_for_backward || o->bn_mode == CP_BN_RUNNING) return CP_ERR_UNSUPPORTED;
-    const bool tcE = o->engine == CP_ENGINE_TC;
+    const bool tcE = o->engine != CP_ENGINE_SIMT;
+    const int fast = o->engine == CP_ENGINE_TC_FP16;      // hi planes only: lo planes are neither written nor read
     const Ws w = carve(workspace, n, o);
     if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -509,12 +514,12 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             const float* gsi = w.gscale_inv + 2 + l;
             // main stream: G0 = G1 . W_l
             CP_TRY(tcg::launch_nt(hi_of(g1(b)), g1lo(b, fc_elems), n, F_FC, F_FC, w.Wth[l], w.Wtl[l], K, F_FC, nullptr, w.G0,
-                                  K, nullptr, nullptr, 0, st, gsi));
+                                  K, nullptr, nullptr, 0, st, gsi, fast));
             // side stream: dW_l = G1^T . A_{l-1}.  It starts when the data-gradient GEMM above has finished (two
             // persistent GEMMs cannot share an SM), i.e. alongside the HBM-bound BN-backward kernels of layer l-1
             CP_CUDA(cudaEventRecord(g_side.ready[b], st));
             CP_CUDA(cudaStreamWaitEvent(ss, g_side.ready[b], 0));
-            CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, ss, gsi));
+            CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, ss, gsi, fast));
             CP_CUDA(cudaEventRecord(g_side.done[b], ss));
             used[b] = true;
         }
@@ -528,12 +533,12 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
         CP_CUDA(cudaMemsetAsync(gr->conv2_w, 0, sizeof(float) * 64 * 64 * 9, ss));
         int S = 0;
         CP_TRY(tcg::launch_conv_tn(hi_of(w.A1), lo_of(w.A1, conv_elems), hi_of(g1(b)), g1lo(b, conv_elems), n, w.wpart,
-                                   WPART_ELEMS, &S, ss));
+                                   WPART_ELEMS, &S, ss, fast));
         wgrad_reduce_kernel<<<(192 * 64 + 255) / 256, 256, 0, ss>>>(w.wpart, S, 192, 64, gr->conv2_w, 3, w.gscale_inv + 1);
         CP_CHECK_LAUNCH();
         CP_CUDA(cudaEventRecord(g_side.done[b], ss));
         CP_TRY(tcg::launch_conv_nt(hi_of(g1(b)), g1lo(b, conv_elems), n, hi_of(w.Wc2d), hi_of(w.Wc2d_lo), nullptr, w.G0,
-                                   nullptr, nullptr, 0, st, w.gscale_inv + 1));
+                                   nullptr, nullptr, 0, st, w.gscale_inv + 1, fast));
         join_event = g_side.done[b];
     } else {
         for (int l = CP_N_FC - 1; l >= 0; --l) {
@@ -599,7 +604,7 @@ extern "C" int cp_encoder_read_activation(const void* workspace, size_t workspac
     if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     // tensor-core engine: the post-BN slots of all stages but the last hold fp16 planes, not fp32 values
     // ... and the last block's output is fused into the projection, never stored
-    if (which == 1 && (o->engine == CP_ENGINE_TC || stage == CP_N_BN - 1)) return CP_ERR_UNSUPPORTED;
+    if (which == 1 && (o->engine != CP_ENGINE_SIMT || stage == CP_N_BN - 1)) return CP_ERR_UNSUPPORTED;
     if (stage == 0 && which == 0) {
         // the conv1 activation is not stored: recompute it from the saved input and parameter copy
         conv1_fwd_kernel<<<(unsigned)cp_cdiv(n, C1_WIN), 256, 0, (cudaStream_t)stream>>>(w.X0, n, w.c1w, w.c1b, dst,
@@ -734,12 +739,15 @@ extern "C" int cp_linear_forward_planes(const uint16_t* A_hi_, const uint16_t* A
                                         void* stream) {
     const plane_t *A_hi = reinterpret_cast<const plane_t*>(A_hi_), *A_lo = reinterpret_cast<const plane_t*>(A_lo_);
     const plane_t *W_hi = reinterpret_cast<const plane_t*>(W_hi_), *W_lo = reinterpret_cast<const plane_t*>(W_lo_);
-    if (!A_hi || !A_lo || !W_hi || !W_lo || !Y || !workspace || M <= 0 || N <= 0 || K <= 0) return CP_ERR_ARG;
+    // both lo planes NULL: the single-product engine (CP_ENGINE_TC_FP16) on the hi planes alone
+    const int fast = !A_lo && !W_lo;
+    if (!A_hi || !W_hi || (!fast && (!A_lo || !W_lo)) || !Y || !workspace || M <= 0 || N <= 0 || K <= 0) return CP_ERR_ARG;
     if ((col_sum == nullptr) != (col_sqsum == nullptr)) return CP_ERR_ARG;
     const LinWs w = carve_linear(workspace, M, N, K);
     if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    CP_TRY(tcg::launch_nt(A_hi, A_lo, M, K, K, W_hi, W_lo, N, K, bias, Y, N, w.pa, w.pb, relu, st));
+    CP_TRY(tcg::launch_nt(A_hi, fast ? A_hi : A_lo, M, K, K, W_hi, fast ? W_hi : W_lo, N, K, bias, Y, N, w.pa, w.pb, relu, st,
+                          nullptr, fast));
     if (col_sum) {
         const int P = (int)cp_cdiv(M, 128);
         colsum_finalize_kernel<<<(N + 31) / 32, 1024, 0, st>>>(w.pa, P, N, col_sum, 0);

@@ -89,6 +89,7 @@ struct NtArgs {
     int relu;
     const float* out_scale;         // device scalar multiplied into the result before bias (undoes the
                                     // power-of-two scale of a gradient operand), or null
+    int fast;                       // CP_ENGINE_TC_FP16: hi planes only, ONE tensor-core product (11-bit operands)
 };
 
 // warp-transposing reduction: on return v[0] of lane l = sum over the 32 lanes of their v[l]
@@ -155,17 +156,17 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 for (int kb = 0; kb < kblocks; ++kb) {
                     tc::mbar_wait(&sm->empty[s], ph ^ 1);
                     uint8_t* st = tiles + s * Cfg::STAGE;
-                    tc::mbar_expect_tx(&sm->full[s], 2 * A_BYTES + 2 * Cfg::B_TILE);
+                    tc::mbar_expect_tx(&sm->full[s], (g.fast ? 1 : 2) * (A_BYTES + Cfg::B_TILE));
                     if (CONV) {
                         const int p0 = kb - 1, w0 = (int)tile_m * CONV_WIN;
                         tc::tma_load_3d(st, &tm_a_hi, &sm->full[s], 0, p0, w0);
-                        tc::tma_load_3d(st + TILE_BYTES, &tm_a_lo, &sm->full[s], 0, p0, w0);
+                        if (!g.fast) tc::tma_load_3d(st + TILE_BYTES, &tm_a_lo, &sm->full[s], 0, p0, w0);
                     } else {
                         tc::tma_load_2d(st, &tm_a_hi, &sm->full[s], kb * BK, (int)tile_m * BM);
-                        tc::tma_load_2d(st + TILE_BYTES, &tm_a_lo, &sm->full[s], kb * BK, (int)tile_m * BM);
+                        if (!g.fast) tc::tma_load_2d(st + TILE_BYTES, &tm_a_lo, &sm->full[s], kb * BK, (int)tile_m * BM);
                     }
                     tc::tma_load_2d(st + 2 * TILE_BYTES, &tm_b_hi, &sm->full[s], kb * BK, n0);
-                    tc::tma_load_2d(st + 2 * TILE_BYTES + Cfg::B_TILE, &tm_b_lo, &sm->full[s], kb * BK, n0);
+                    if (!g.fast) tc::tma_load_2d(st + 2 * TILE_BYTES + Cfg::B_TILE, &tm_b_lo, &sm->full[s], kb * BK, n0);
                     if (++s == Cfg::NSTAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -195,8 +196,10 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                         const uint64_t a_lo = tc::smem_desc_sw128(base + TILE_BYTES + ko, 16, 1024);
                         const uint64_t b_hi = tc::smem_desc_sw128(base + 2 * TILE_BYTES + ko, 16, 1024);
                         const uint64_t b_lo = tc::smem_desc_sw128(base + 2 * TILE_BYTES + Cfg::B_TILE + ko, 16, 1024);
-                        tc::mma_f16(dc, a_lo, b_hi, idesc, (kb | k) != 0);
-                        tc::mma_f16(dc, a_hi, b_lo, idesc, 1);
+                        if (!g.fast) {
+                            tc::mma_f16(dc, a_lo, b_hi, idesc, (kb | k) != 0);
+                            tc::mma_f16(dc, a_hi, b_lo, idesc, 1);
+                        }
                         tc::mma_f16(d, a_hi, b_hi, idesc, (kb | k) != 0);
                     }
                     tc::mma_commit(&sm->empty[s]);                                // frees the stage when the MMAs retire
@@ -226,10 +229,15 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 float v[32], vc[32];
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC + c * 32;
                 tc::tmem_ld32(ta, v);
-                tc::tmem_ld32(ta + BN_, vc);
+                if (!g.fast) tc::tmem_ld32(ta + BN_, vc);
                 tc::tmem_ld_wait();
+                if (g.fast) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaf(vc[j], cscale, v[j] * oscale);
+                    for (int j = 0; j < 32; ++j) v[j] *= oscale;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaf(vc[j], cscale, v[j] * oscale);
+                }
                 const int col = n0 + c * 32;
                 if (g.bias) {
 #pragma unroll
@@ -367,11 +375,11 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                 for (int kb = 0; kb < kblocks; ++kb) {
                     tc::mbar_wait(&sm->empty[s], ph ^ 1);
                     uint8_t* st = tiles + s * STAGE2;
-                    if (leader) tc::mbar_expect_tx(&sm->full[s], 2 * STAGE2);          // bytes of both CTAs
+                    if (leader) tc::mbar_expect_tx(&sm->full[s], g.fast ? STAGE2 : 2 * STAGE2);   // bytes of both CTAs
                     tc::tma_load_2d_pair(st, &tm_a_hi, &sm->full[s], kb * BK, m0);
-                    tc::tma_load_2d_pair(st + TILE_BYTES, &tm_a_lo, &sm->full[s], kb * BK, m0);
+                    if (!g.fast) tc::tma_load_2d_pair(st + TILE_BYTES, &tm_a_lo, &sm->full[s], kb * BK, m0);
                     tc::tma_load_2d_pair(st + 2 * TILE_BYTES, &tm_b_hi, &sm->full[s], kb * BK, n0);
-                    tc::tma_load_2d_pair(st + 2 * TILE_BYTES + B_HALF, &tm_b_lo, &sm->full[s], kb * BK, n0);
+                    if (!g.fast) tc::tma_load_2d_pair(st + 2 * TILE_BYTES + B_HALF, &tm_b_lo, &sm->full[s], kb * BK, n0);
                     if (++s == STAGES2) { s = 0; ph ^= 1; }
                 }
             }
@@ -399,8 +407,10 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                         const uint64_t a_lo = tc::smem_desc_sw128(base + TILE_BYTES + ko, 16, 1024);
                         const uint64_t b_hi = tc::smem_desc_sw128(base + 2 * TILE_BYTES + ko, 16, 1024);
                         const uint64_t b_lo = tc::smem_desc_sw128(base + 2 * TILE_BYTES + B_HALF + ko, 16, 1024);
-                        tc::mma_f16_pair(dc, a_lo, b_hi, idesc, (kb | k) != 0);
-                        tc::mma_f16_pair(dc, a_hi, b_lo, idesc, 1);
+                        if (!g.fast) {
+                            tc::mma_f16_pair(dc, a_lo, b_hi, idesc, (kb | k) != 0);
+                            tc::mma_f16_pair(dc, a_hi, b_lo, idesc, 1);
+                        }
                         tc::mma_f16_pair(d, a_hi, b_hi, idesc, (kb | k) != 0);
                     }
                     tc::mma_commit_pair(&sm->empty[s]);
@@ -431,10 +441,15 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                 float v[32], vc[32];
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + cl;
                 tc::tmem_ld32(ta, v);
-                tc::tmem_ld32(ta + BN, vc);
+                if (!g.fast) tc::tmem_ld32(ta + BN, vc);
                 tc::tmem_ld_wait();
+                if (g.fast) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaf(vc[j], cscale, v[j] * oscale);
+                    for (int j = 0; j < 32; ++j) v[j] *= oscale;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaf(vc[j], cscale, v[j] * oscale);
+                }
                 const int col = n0 + cl;
                 if (g.bias) {
 #pragma unroll
@@ -497,6 +512,7 @@ struct TnArgs {
     int Mo, No;
     int64_t R;                // total rows
     int64_t rows_per_split;   // multiple of BK
+    int fast;                 // hi planes only
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -536,11 +552,11 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_cons
                 tc::mbar_wait(&sm->empty[s], ph ^ 1);
                 uint8_t* st = tiles + s * STAGE_BYTES;
                 const int r = (int)(r_begin + (int64_t)kb * BK);
-                tc::mbar_expect_tx(&sm->full[s], STAGE_BYTES);
+                tc::mbar_expect_tx(&sm->full[s], g.fast ? STAGE_BYTES / 2 : STAGE_BYTES);
                 tc::tma_load_3d(st + 0 * TILE_BYTES, &tm_g_hi, &sm->full[s], 0, r, o0 / 64);
-                tc::tma_load_3d(st + 1 * TILE_BYTES, &tm_g_lo, &sm->full[s], 0, r, o0 / 64);
+                if (!g.fast) tc::tma_load_3d(st + 1 * TILE_BYTES, &tm_g_lo, &sm->full[s], 0, r, o0 / 64);
                 tc::tma_load_3d(st + 2 * TILE_BYTES, &tm_a_hi, &sm->full[s], 0, r, c0 / 64);
-                tc::tma_load_3d(st + 3 * TILE_BYTES, &tm_a_lo, &sm->full[s], 0, r, c0 / 64);
+                if (!g.fast) tc::tma_load_3d(st + 3 * TILE_BYTES, &tm_a_lo, &sm->full[s], 0, r, c0 / 64);
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
@@ -568,8 +584,10 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_cons
                         const uint64_t a_hi = tc::smem_desc_sw128(base + 2 * TILE_BYTES + ko, MN_BLOCK, 1024);
                         const uint64_t a_lo = tc::smem_desc_sw128(base + 3 * TILE_BYTES + ko, MN_BLOCK, 1024);
                         const uint32_t accum = (first && k == 0) ? 0u : 1u;
-                        tc::mma_f16(dc, g_lo, a_hi, idesc, accum);
-                        tc::mma_f16(dc, g_hi, a_lo, idesc, 1);
+                        if (!g.fast) {
+                            tc::mma_f16(dc, g_lo, a_hi, idesc, accum);
+                            tc::mma_f16(dc, g_hi, a_lo, idesc, 1);
+                        }
                         tc::mma_f16(d, g_hi, a_hi, idesc, accum);
                     }
                     first = false;
@@ -593,10 +611,15 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_cons
                 float v[32], vc[32];
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + c * 32;
                 tc::tmem_ld32(ta, v);
-                tc::tmem_ld32(ta + BN, vc);
+                if (!g.fast) tc::tmem_ld32(ta + BN, vc);
                 tc::tmem_ld_wait();
+                if (g.fast) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sum[c * 32 + j] += fmaf(vc[j], CP_LO_INV, v[j]);
+                    for (int j = 0; j < 32; ++j) sum[c * 32 + j] += v[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[c * 32 + j] += fmaf(vc[j], CP_LO_INV, v[j]);
+                }
             }
             tc::tc_fence_before();
             __syncwarp();
@@ -630,6 +653,7 @@ struct CwArgs {
     float* P;                    // [splits][256][64]
     int64_t windows;
     int64_t win_per_split;       // multiple of CW_WIN
+    int fast;                    // hi planes only
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -670,15 +694,15 @@ gemm_tc_tn_conv_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid
                 tc::mbar_wait(&sm->empty[s], ph ^ 1);
                 uint8_t* st = tiles + s * CW_STAGE;
                 const int w0 = (int)(w_begin + (int64_t)kb * CW_WIN);
-                tc::mbar_expect_tx(&sm->full[s], (uint32_t)(2 * n_blocks + 2) * CW_BLOCK);
+                tc::mbar_expect_tx(&sm->full[s], (uint32_t)(n_blocks + 1) * (g.fast ? 1 : 2) * CW_BLOCK);
                 for (int b = 0; b < n_blocks; ++b) {
                     const int tap = mt * 2 + b;
                     tc::tma_load_3d(st + b * CW_BLOCK, &tm_x_hi, &sm->full[s], 0, tap - 1, w0);
-                    tc::tma_load_3d(st + (2 + b) * CW_BLOCK, &tm_x_lo, &sm->full[s], 0, tap - 1, w0);
+                    if (!g.fast) tc::tma_load_3d(st + (2 + b) * CW_BLOCK, &tm_x_lo, &sm->full[s], 0, tap - 1, w0);
                 }
                 // G: [rows][64] -> one [48][64] block per plane
                 tc::tma_load_2d(st + 4 * CW_BLOCK, &tm_g_hi, &sm->full[s], 0, w0 * 12);
-                tc::tma_load_2d(st + 5 * CW_BLOCK, &tm_g_lo, &sm->full[s], 0, w0 * 12);
+                if (!g.fast) tc::tma_load_2d(st + 5 * CW_BLOCK, &tm_g_lo, &sm->full[s], 0, w0 * 12);
                 if (++s == CW_STAGES) { s = 0; ph ^= 1; }
             }
         }
@@ -706,8 +730,10 @@ gemm_tc_tn_conv_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid
                         const uint64_t g_hi = tc::smem_desc_sw128(base + 4 * CW_BLOCK + ko, CW_BLOCK, 1024);
                         const uint64_t g_lo = tc::smem_desc_sw128(base + 5 * CW_BLOCK + ko, CW_BLOCK, 1024);
                         const uint32_t accum = (first && k == 0) ? 0u : 1u;
-                        tc::mma_f16(dc, x_lo, g_hi, idesc, accum);
-                        tc::mma_f16(dc, x_hi, g_lo, idesc, 1);
+                        if (!g.fast) {
+                            tc::mma_f16(dc, x_lo, g_hi, idesc, accum);
+                            tc::mma_f16(dc, x_hi, g_lo, idesc, 1);
+                        }
                         tc::mma_f16(d, x_hi, g_hi, idesc, accum);
                     }
                     first = false;
@@ -731,10 +757,15 @@ gemm_tc_tn_conv_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid
                 float v[32], vc[32];
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + c * 32;
                 tc::tmem_ld32(ta, v);
-                tc::tmem_ld32(ta + 64, vc);
+                if (!g.fast) tc::tmem_ld32(ta + 64, vc);
                 tc::tmem_ld_wait();
+                if (g.fast) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sum[c * 32 + j] += fmaf(vc[j], CP_LO_INV, v[j]);
+                    for (int j = 0; j < 32; ++j) sum[c * 32 + j] += v[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[c * 32 + j] += fmaf(vc[j], CP_LO_INV, v[j]);
+                }
             }
             tc::tc_fence_before();
             __syncwarp();
@@ -803,7 +834,7 @@ inline int make_tmap_mn(CUtensorMap* m, const plane_t* base, int64_t rows, int64
 // returns the number of splits written to P ([splits][Mo][No]) through *splits_out
 inline int launch_tn(const plane_t* G_hi, const plane_t* G_lo, int ldg, int Mo, const plane_t* A_hi, const plane_t* A_lo,
                      int lda, int No, int64_t R, float* P, size_t p_capacity_elems, int* splits_out,
-                     cudaStream_t st) {
+                     cudaStream_t st, int fast = 0) {
     if (Mo % BM != 0 || No % BN != 0 || ldg % 8 != 0 || lda % 8 != 0 || R <= 0) return CP_ERR_ARG;
     CUtensorMap tg_hi, tg_lo, ta_hi, ta_lo;
     int rc;
@@ -828,7 +859,7 @@ inline int launch_tn(const plane_t* G_hi, const plane_t* G_lo, int ldg, int Mo, 
     if (S < 1) S = 1;
     const int64_t rps = cp_cdiv(cp_cdiv(R, S), BK) * BK;
     S = (int)cp_cdiv(R, rps);
-    TnArgs g{P, Mo, No, R, rps};
+    TnArgs g{P, Mo, No, R, rps, fast};
     gemm_tc_tn_kernel<<<dim3(No / BN, Mo / BM, S), THREADS, SMEM_BYTES, st>>>(tg_hi, tg_lo, ta_hi, ta_lo, g);
     CP_CHECK_LAUNCH();
     *splits_out = S;
@@ -882,7 +913,7 @@ inline int launch_nt_cfg(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, con
 static bool g_use_pair = true;       // CTA-pair (cta_group::2) kernel for the plain (non-conv) K-major GEMMs
 inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K, int lda, const plane_t* B_hi,
                      const plane_t* B_lo, int N, int ldb, const float* bias, float* C, int ldc, float* psum,
-                     float* psq, int relu, cudaStream_t st, const float* out_scale = nullptr) {
+                     float* psq, int relu, cudaStream_t st, const float* out_scale = nullptr, int fast = 0) {
     if (K % BK != 0 || N % BN != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldc % 4 != 0) return CP_ERR_ARG;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_out;
     int rc;
@@ -891,7 +922,7 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
     if ((rc = make_tmap_2d(&ta_lo, A_lo, M, K, lda, BM)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi, B_hi, N, K, ldb, BN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, N, K, ldb, BN)) != CP_OK) return rc;
-    NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu, out_scale};
+    NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu, out_scale, fast};
     if (g_use_pair && M > BM) {
         CUtensorMap tb_hi2, tb_lo2;                                   // B boxes of 64 rows: half a tile per CTA
         if ((rc = make_tmap_2d(&tb_hi2, B_hi, N, K, ldb, BN / 2)) != CP_OK) return rc;
@@ -914,7 +945,7 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
 // X planes are [windows][12][64], B planes [64][192]; partial statistics rows = ceil(windows/10)
 inline int launch_conv_nt(const plane_t* X_hi, const plane_t* X_lo, int64_t windows, const plane_t* B_hi,
                           const plane_t* B_lo, const float* bias, float* C, float* psum, float* psq, int relu,
-                          cudaStream_t st, const float* out_scale = nullptr) {
+                          cudaStream_t st, const float* out_scale = nullptr, int fast = 0) {
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_out;
     int rc;
     if ((rc = make_tmap_out(&tc_out, C, windows * 12, 64, 64, CONV_ROWS)) != CP_OK) return rc;
@@ -922,13 +953,14 @@ inline int launch_conv_nt(const plane_t* X_hi, const plane_t* X_lo, int64_t wind
     if ((rc = make_tmap_conv(&ta_lo, X_lo, windows, CONV_WIN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi, B_hi, 64, 192, 192, 64)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, 64, 192, 192, 64)) != CP_OK) return rc;
-    NtArgs g{C, 64, bias, psum, psq, windows * 12, 64, 192, relu, out_scale};
+    NtArgs g{C, 64, bias, psum, psq, windows * 12, 64, 192, relu, out_scale, fast};
     return launch_nt_cfg<64, true>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st);
 }
 
 // conv2 weight gradient; P capacity >= splits*256*64 floats; *splits_out = number of slabs written
 inline int launch_conv_tn(const plane_t* X_hi, const plane_t* X_lo, const plane_t* G_hi, const plane_t* G_lo,
-                          int64_t windows, float* P, size_t p_capacity_elems, int* splits_out, cudaStream_t st) {
+                          int64_t windows, float* P, size_t p_capacity_elems, int* splits_out, cudaStream_t st,
+                          int fast = 0) {
     CUtensorMap tx_hi, tx_lo, tg_hi, tg_lo;
     int rc;
     if ((rc = make_tmap_conv(&tx_hi, X_hi, windows, CW_WIN)) != CP_OK) return rc;
@@ -948,7 +980,7 @@ inline int launch_conv_tn(const plane_t* X_hi, const plane_t* X_lo, const plane_
     if (S < 1) S = 1;
     const int64_t wps = cp_cdiv(cp_cdiv(windows, S), CW_WIN) * CW_WIN;
     S = (int)cp_cdiv(windows, wps);
-    CwArgs g{P, windows, wps};
+    CwArgs g{P, windows, wps, fast};
     gemm_tc_tn_conv_kernel<<<dim3(2, S), THREADS, CW_SMEM, st>>>(tx_hi, tx_lo, tg_hi, tg_lo, g);
     CP_CHECK_LAUNCH();
     *splits_out = S;
@@ -970,7 +1002,7 @@ __device__ __forceinline__ void split_store4(const float4& x, plane_t* hi, plane
     split_f16(x.x, h[0], l[0]); split_f16(x.y, h[1], l[1]);
     split_f16(x.z, h[2], l[2]); split_f16(x.w, h[3], l[3]);
     reinterpret_cast<uint2*>(hi)[v] = *reinterpret_cast<const uint2*>(h);
-    reinterpret_cast<uint2*>(lo)[v] = *reinterpret_cast<const uint2*>(l);
+    if (lo) reinterpret_cast<uint2*>(lo)[v] = *reinterpret_cast<const uint2*>(l);      // null: single-product engine
 }
 
 __global__ void __launch_bounds__(256)

@@ -72,6 +72,8 @@ typedef struct cp_encoder_tensors {
 
 #define CP_ENGINE_SIMT 0       /* fp32 FFMA GEMMs */
 #define CP_ENGINE_TC 1         /* tcgen05 GEMMs on a 3-product fp16 split (fp32-level accuracy) */
+#define CP_ENGINE_TC_FP16 2    /* tcgen05 GEMMs, ONE fp16 product (11-bit operands like TF32, fp32 accumulate):
+                                  the reduced-precision path BASELINE.json allows at 1e-2; not the parity path */
 
 /* SyncBN hook (optional).  Sums `count` doubles at device pointer `buf` over all ranks, in place, ordered on
  * `stream`; returns 0 on success.  A C/C++ host implements it with
@@ -124,7 +126,8 @@ int cp_linear_forward(const float *A, const float *W, const float *bias, float *
  * lo = fp16((x - hi) * 2048) (22 significand bits; n % 4 == 0). */
 int cp_split_planes(const float *x, uint16_t *hi, uint16_t *lo, int64_t n, void *stream);
 /* cp_linear_forward (CP_ENGINE_TC) on pre-split operands: exactly the per-layer launch of the encoder
- * (N % 128 == 0, K % 64 == 0).  col_sum / col_sqsum may both be NULL. */
+ * (N % 128 == 0, K % 64 == 0).  col_sum / col_sqsum may both be NULL.  A_lo == W_lo == NULL selects the
+ * single-product launch of CP_ENGINE_TC_FP16 (hi planes only). */
 int cp_linear_forward_planes(const uint16_t *A_hi, const uint16_t *A_lo, const uint16_t *W_hi, const uint16_t *W_lo,
                              const float *bias, float *Y, int64_t M, int N, int K, int relu,
                              float *col_sum, float *col_sqsum, void *workspace, size_t workspace_bytes,

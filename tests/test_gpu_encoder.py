@@ -174,6 +174,50 @@ def test_encoder_backward(adabn, n, engine):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("n", [9, 15, 16, 17, 63, 64, 65, 129, 257, 148 * 16, 148 * 16 + 1])
+def test_encoder_shape_sweep(n, engine):
+    """Ragged sizes around every tiling boundary of the kernels: 16-row slabs of the fused last block (and its
+    148-CTA persistent grid), 64-window slabs of the conv1 passes, 128-row GEMM / BN tiles, 256-row CTA pairs.
+    Forward (every stage) and, with the ReLU pattern fixed, every gradient against the fp32 oracle."""
+    # BatchNorm over a handful of rows is ill-conditioned (the fp32 oracle is 3e-6 from the fp64 one at n = 9,
+    # 3e-2 at n = 2): 3x the tolerance below 64 rows
+    k_tol = 1 if n >= 64 else 3
+    sd = perturbed_state(13, True)
+    g = torch.Generator().manual_seed(1000 + n)
+    x, d_emb = torch.randn(n, 12, generator=g), torch.randn(n, 16, generator=g)
+    taps, otaps = {}, {}
+    emb, got = _grads_cuda(sd, True, x, d_emb, taps=taps, engine=engine)
+    ref_emb, _ = _grads_oracle(sd, True, x, d_emb, torch.float32, taps=otaps)
+    assert rel_err(emb, ref_emb) < k_tol * FWD_TOL
+    for stage in range(9):
+        assert rel_err(taps[f"relu{stage}"], otaps[f"relu{stage}"].detach()) < k_tol * FWD_TOL, stage
+    _, ref = _grads_oracle(sd, True, x, d_emb, torch.float32, relu_masks=_relu_pattern(taps))
+    worst = max((rel_err(got[k], ref[k]), k) for k in ref)
+    assert worst[0] < k_tol * GRAD_TOL, worst
+
+
+@pytest.mark.parametrize("adabn", [True, False])
+@pytest.mark.parametrize("n", [41 * 8, 41 * 100])
+def test_single_product_fp16_engine(adabn, n):
+    """CP_ENGINE_TC_FP16: one fp16 tensor-core product per GEMM (11-bit operands, like TF32).  BASELINE.json allows
+    1e-2 relative for a reduced-precision path; it is NOT the parity path (that is ENGINE_TC, 1e-5)."""
+    tol = 1e-2
+    sd = perturbed_state(17, adabn)
+    g = torch.Generator().manual_seed(n + 5)
+    x, d_emb = torch.randn(n, 12, generator=g), torch.randn(n, 16, generator=g)
+    taps = {}
+    emb, got = _grads_cuda(sd, adabn, x, d_emb, taps=taps, engine=_lib.ENGINE_TC_FP16)
+    ref_emb, _ = _grads_oracle(sd, adabn, x, d_emb, torch.float32)
+    assert rel_err(emb, ref_emb) < tol
+    _, ref = _grads_oracle(sd, adabn, x, d_emb, torch.float32, relu_masks=_relu_pattern(taps))
+    worst = max((rel_err(got[k], ref[k]), k) for k in ref)
+    assert worst[0] < tol, worst
+    # and it really is the reduced-precision path: measurably less accurate than the 3-product engine
+    emb3, _ = _grads_cuda(sd, adabn, x, d_emb, engine=_lib.ENGINE_TC)
+    assert rel_err(emb3, ref_emb) < FWD_TOL < rel_err(emb, ref_emb)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
 def test_backward_error_in_fp64_context(engine):
     """With the ReLU pattern fixed, fp32 CUDA gradients are as close to the fp64 truth as the fp32
     oracle (the reference's own arithmetic) is (FFMA engine), or within the 1e-5 budget (3xTF32)."""
