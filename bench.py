@@ -408,10 +408,11 @@ def run_cuda(args):
         eager = torch_eager_gpu(dev, B)              # stock PyTorch on the same GPU, the practical bar
         hbm = hbm_kernels(dev, measured_peaks()["hbm_gbs"])
     if rank == 0:
-        wps, cms, cores = cpu_oracle_steps(n_steps=3, warmup=1, groups=256)
-        cpu = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
-               "sample": f"3 steps x {256 * T} windows of the same train step (oracle/ torch-CPU port), "
-                         f"{cms:.0f} ms/step"}
+        if world == 1:       # N = 1 only: at N > 1 the other ranks spin in the barrier on the same host cores
+            wps, cms, cores = cpu_oracle_steps(n_steps=3, warmup=1, groups=256)
+            cpu = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
+                   "sample": f"3 steps x {256 * T} windows of the same train step (oracle/ torch-CPU port), "
+                             f"{cms:.0f} ms/step"}
         line = {
             "metric": "train sEMG windows/s", "value": value, "unit": "windows/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
