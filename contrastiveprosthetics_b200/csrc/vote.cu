@@ -54,36 +54,48 @@ extern "C" int cp_vote_eval(const int32_t* pred, int64_t B, int W, int n_votes, 
 }
 
 // ------------------------------------------------------------------------------- K4' rank rows
-// 64 rows per CTA staged in shared memory; thread (row, j) counts the entries that beat entry j:
-// rank_j = #{k : v_k > v_j or (v_k == v_j and k < j)}  ->  order[rank_j] = j.
-#define RR_ROWS 64
-__global__ void __launch_bounds__(256)
+// One thread per row: the row's 41 logits live in registers and every unordered pair is compared ONCE,
+//   k beats j (j < k)  <=>  v_k > v_j        (ties: the smaller label ranks first)
+// crediting rank_j or rank_k -- 820 compares per row instead of 41 x 41 -- then order[rank_j] = j.
+// Rows are staged through shared memory so that global loads / stores stay coalesced (row stride 41 floats is
+// odd: conflict-free when each thread reads its own row).  ALU-bound: 205 B of traffic per ~2.5 k instructions.
+#define RR_ROWS 128
+__global__ void __launch_bounds__(RR_ROWS)
 rank_rows_kernel(const float* __restrict__ logits, int64_t n_rows, uint8_t* __restrict__ order) {
-    __shared__ float v[RR_ROWS][T + 1];
-    __shared__ uint8_t ord[RR_ROWS][T + 3];
+    __shared__ float v[RR_ROWS * T];
+    __shared__ __align__(4) uint8_t ord[RR_ROWS * T];
     const int64_t r0 = (int64_t)blockIdx.x * RR_ROWS;
     const int nr = (int)min((int64_t)RR_ROWS, n_rows - r0);
-    for (int e = threadIdx.x; e < nr * T; e += blockDim.x) v[e / T][e % T] = __ldg(logits + r0 * T + e);
+    for (int e = threadIdx.x; e < nr * T; e += RR_ROWS) v[e] = __ldg(logits + r0 * T + e);
     __syncthreads();
-    for (int e = threadIdx.x; e < nr * T; e += blockDim.x) {
-        const int r = e / T, j = e % T;
-        const float x = v[r][j];
-        int rank = 0;
+    if (threadIdx.x < nr) {
+        float x[T];
+        int rank[T];
 #pragma unroll
-        for (int k = 0; k < T; ++k) {
-            const float y = v[r][k];
-            rank += (y > x) || (y == x && k < j);
+        for (int j = 0; j < T; ++j) {
+            x[j] = v[threadIdx.x * T + j];
+            rank[j] = 0;
         }
-        ord[r][rank] = (uint8_t)j;
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+#pragma unroll
+            for (int k = j + 1; k < T; ++k) {
+                const int beats = x[k] > x[j];
+                rank[j] += beats;
+                rank[k] += 1 - beats;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < T; ++j) ord[threadIdx.x * T + rank[j]] = (uint8_t)j;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < nr * T; e += blockDim.x) order[r0 * T + e] = ord[e / T][e % T];
+    for (int e = threadIdx.x; e < nr * T; e += RR_ROWS) order[r0 * T + e] = ord[e];
 }
 
 extern "C" int cp_rank_rows(const float* logits, int64_t n_rows, uint8_t* order, void* stream) {
     if (n_rows == 0) return CP_OK;
     if (!logits || !order || n_rows < 0) return CP_ERR_ARG;
-    rank_rows_kernel<<<(unsigned)cp_cdiv(n_rows, RR_ROWS), 256, 0, (cudaStream_t)stream>>>(logits, n_rows, order);
+    rank_rows_kernel<<<(unsigned)cp_cdiv(n_rows, RR_ROWS), RR_ROWS, 0, (cudaStream_t)stream>>>(logits, n_rows, order);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }

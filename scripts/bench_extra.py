@@ -90,6 +90,41 @@ def torch_eager_gpu(dev, B=4096, steps=5, warmup=2):
     return out
 
 
+def eval_pipeline(dev, batch_groups=64, reps=3):
+    """The --test pass of train.py:27-44 on the DB2-shaped test split (160 items x 41 classes x 25-sample voting
+    windows = 164,000 sEMG windows): gather -> encoder (inference) -> head/logits -> loss + argmax -> windowed vote,
+    test batch = 8 x batch_size 8 = 64 items like the reference.  Returns windows/s and voted decisions/s."""
+    from contrastiveprosthetics_b200.load import DB23
+    from contrastiveprosthetics_b200.models import Model
+    from contrastiveprosthetics_b200.utils import TaskWrapper
+    params = {'d_e': 16, 'dp_emg': 0.5, 'dp_glove': 0.5, 'reg_emg': 1e-5, 'reg_glove': 1e-5}
+    torch.manual_seed(42)
+    model = Model(dict(params), adabn=True, device=str(dev))
+    ds = DB23(db2=True, device=dev)
+    ds.load_synthetic(with_glove=False)
+    tw = TaskWrapper(ds, with_glove=False)
+    tw.set_test()
+    model.set_test()
+    sink = {}
+
+    def one_pass():
+        model.reset()
+        losses = []
+        with torch.no_grad():
+            for (EMG, GLOVE, label) in tw.batches(batch_groups, shuffle=True):
+                label = label.reshape(-1)
+                losses.append(model.loss(model.forward(EMG, GLOVE, label), label))
+        sink["loss"] = torch.stack(losses).mean().item()
+        sink["acc"] = model.correct()                      # resolves the vote counts on the host
+
+    ms = _events(one_pass, reps, 1)
+    windows = tw.D * T * 25
+    return {"ms_per_pass": ms, "windows": windows, "windows_per_s": windows / (ms / 1e3),
+            "voted_decisions_per_s": tw.D * T / (ms / 1e3),
+            "workload": f"--test pass: {tw.D} items x 41 x 25 windows, test batch {batch_groups} items, AdaBN "
+                        "(batch statistics in eval, models.py:17-35), logits materialised, vote over 249 window lengths"}
+
+
 def hbm_kernels(dev, hbm_gbs, scale=64):
     """K1 and K4' at x`scale` of the native DB2-shaped sizes, so that inputs exceed the L2."""
     from contrastiveprosthetics_b200 import subset as cps
