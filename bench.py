@@ -398,16 +398,17 @@ def run_cuda(args):
     ms_sub, _, _ = timed(subset_run, 5, 1)
     preds_per_s = items_eval * Wv * T * len(masks) / (ms_sub / 1e3)
 
-    c1 = eager = hbm = evalp = None
+    c1 = eager = hbm = evalp = prep = None
     if rank == 0 and world == 1 and not strong:
         # the reference's own launch-bound configuration (go.sh:6): eager vs CUDA-graph step
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         from bench_c1 import c1_small_batch
-        from bench_extra import eval_pipeline, hbm_kernels, torch_eager_gpu
+        from bench_extra import eval_pipeline, hbm_kernels, preprocess_leg, torch_eager_gpu
         c1 = c1_small_batch(dev)
         eager = torch_eager_gpu(dev, B)              # stock PyTorch on the same GPU, the practical bar
         hbm = hbm_kernels(dev, measured_peaks()["hbm_gbs"])
         evalp = eval_pipeline(dev)
+        prep = preprocess_leg(dev)
     if rank == 0:
         if world == 1:       # N = 1 only: at N > 1 the other ranks spin in the barrier on the same host cores
             wps, cms, cores = cpu_oracle_steps(n_steps=3, warmup=1, groups=256)
@@ -435,7 +436,7 @@ def run_cuda(args):
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e, "step_mode": e2e_mode},
             "roofline": roof, "cpu_baseline": cpu, "step_modes": modes,
-            "c1_small_batch": c1, "torch_eager_gpu": eager, "hbm_kernels": hbm, "eval_pipeline": evalp,
+            "c1_small_batch": c1, "torch_eager_gpu": eager, "hbm_kernels": hbm, "eval_pipeline": evalp, "offline_preprocess": prep,
             "subset_eval": {"value": preds_per_s, "unit": "preds/s", "ms": ms_sub,
                             "workload": "C4: 160 items x 25 x 41 test windows x 5760 trials (144 x 40 sizes), "
                                         "rank + vote + count; trials sharded over ranks"},

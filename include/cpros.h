@@ -264,6 +264,17 @@ int cp_l2_forward(const float *const *tensors, const int64_t *sizes, int n_tenso
 int cp_l2_backward(const float *const *tensors, const int64_t *sizes, int n_tensors, const float *norms,
                    const float *g_total, float coef, float *const *grads, void *stream);
 
+/* ---------------------------------------------------------------- offline preprocessing
+ * load.py:85-101 / utils.py:134-156: per (subject, stimulus, repetition) segment raw[seg_len, n_ch] (float32, time
+ * major): x = raw * gain -> IIR filter (b, a: HOST arrays of n_coef <= 17 doubles, a[0] == 1; scipy lfilter
+ * semantics, result rounded to float32) -> moving RMS (odd rms_window <= 33, uniform_filter1d mode 'nearest',
+ * trimmed by rms_window/2 on both sides) -> out[seg, j, c] = rms[time_idx[j]] for the n_out DEVICE indices
+ * time_idx[j] in [0, n_rms).  Bit-exact with scipy's double-precision loops.  scratch: n_seg*n_ch*n_rms floats. */
+size_t cp_emg_preprocess_scratch_elems(int64_t n_seg, int n_ch, int n_rms);
+int cp_emg_preprocess(const float *raw, int64_t n_seg, int seg_len, int n_ch, const double *b, const double *a,
+                      int n_coef, float gain, int rms_window, int n_rms, const int32_t *time_idx, int n_out,
+                      float *out, float *scratch, size_t scratch_elems, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

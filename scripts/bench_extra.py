@@ -125,6 +125,37 @@ def eval_pipeline(dev, batch_groups=64, reps=3):
                         "(batch statistics in eval, models.py:17-35), logits materialised, vote over 249 window lengths"}
 
 
+def preprocess_leg(dev):
+    """offline preprocessing of the whole dataset shape (46 x 41 x 6 segments of 2010 x 12
+    float32 samples = 1.09 GB) on the GPU, next to the reference's scipy calls (utils.py:134-156) on a sample."""
+    import time
+    import numpy as np
+    from scipy import signal
+    from scipy.ndimage import uniform_filter1d
+    from contrastiveprosthetics_b200 import preprocess as PP
+    raw = PP.synthetic_raw(people=46, seed=0, device=dev)
+    n_seg = raw.numel() // (PP.SEG_LEN * 12)
+    out = {"segments": n_seg, "raw_gb": raw.numel() * 4 / 1e9}
+    for name, wrap in (("reference_time_mask_uint8_wrap", True), ("full_2000_samples", False)):
+        out[name + "_ms"] = _events(lambda: PP.preprocess_segments(raw, wrap=wrap), 3, 1)
+    b, a = PP.butter_bandpass()
+    sample = raw[0, :8].reshape(-1, PP.SEG_LEN, 12).cpu().numpy()         # 48 segments
+    t0 = time.perf_counter()
+    for x in sample:
+        x = x * 2 ** 10
+        for c in range(12):
+            f = signal.lfilter(b, a, x[:, c]).astype(np.float32)
+            np.sqrt(uniform_filter1d(np.square(f), size=11, mode="nearest"))[5:-5]
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / len(sample)
+    out["cpu_scipy_ms_per_segment"] = cpu_ms
+    out["cpu_scipy_ms_whole_dataset_extrapolated"] = cpu_ms * n_seg
+    out["note"] = ("one thread per (segment, channel), sequential in time, bit-exact with scipy's lfilter / "
+                   "uniform_filter1d loops (un-fused fp64); bound by the 2010-step fp64 recurrence, not by HBM")
+    del raw
+    torch.cuda.empty_cache()
+    return out
+
+
 def hbm_kernels(dev, hbm_gbs, scale=64):
     """K1 and K4' at x`scale` of the native DB2-shaped sizes, so that inputs exceed the L2."""
     from contrastiveprosthetics_b200 import subset as cps

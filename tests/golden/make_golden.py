@@ -268,8 +268,52 @@ def copy_ref_artifacts():
     np.savez_compressed(os.path.join(dst, "grasp_tables.npz"), **tab)
 
 
+def gen_preprocess():
+    """Offline preprocessing (load.py:85-101, utils.py:79-156): the reference's own filter / rms / time_mask /
+    RunningStats on seeded raw segments (float32 like the NinaPro .mat files, plus one float64 segment)."""
+    import tempfile
+    rs = np.random.RandomState(2024)
+    L = RC.TOTAL_WINDOW_SIZE + 2 * RC.WINDOW_EDGE
+    t = np.arange(L)[:, None] / RC.Hz
+    raws = []
+    for s in range(6):
+        # broadband noise + a 50 Hz line + slow drift, channel-dependent amplitude (roughly raw-sEMG-in-volts scale)
+        amp = (1e-5 * (1 + rs.rand(1, 12) * 4)).astype(np.float64)
+        x = amp * rs.randn(L, 12) + 2e-5 * np.sin(2 * np.pi * 50 * t + s) + 1e-4 * (s - 2.5) * t
+        raws.append(x.astype(np.float32))
+    raw = np.stack(raws)                                                   # (6, 2010, 12) float32
+    mask_wrap = np.arange(0, RC.TOTAL_WINDOW_SIZE, RC.FACTOR, dtype=np.uint8)       # load.py:116 verbatim
+    mask_full = np.arange(0, RC.TOTAL_WINDOW_SIZE, RC.FACTOR)
+    out = {"raw": raw, "time_mask": mask_wrap.astype(np.int64)}
+
+    def ref_segment(x, mask):
+        f = RU.filter(x * 2 ** 10, (20, 450), butterworth_order=4, btype="bandpass")   # load.py:96
+        return RU.rms(f)[mask]                                                          # load.py:98,100
+
+    out["emg_wrap"] = np.stack([ref_segment(x.copy(), mask_wrap) for x in raw])
+    out["emg_full"] = np.stack([ref_segment(x.copy(), mask_full) for x in raw])
+    out["emg_wrap_f64"] = ref_segment(raw[0].astype(np.float64), mask_wrap)
+    assert out["emg_wrap"].dtype == np.float32 and out["emg_wrap_f64"].dtype == np.float64
+    with tempfile.TemporaryDirectory() as d:
+        for complete in (False, True):
+            st = RU.RunningStats(d + "/emg_", complete=complete)
+            for w in out["emg_wrap"][:5]:                                  # the "training subset": 5 of 6 segments
+                st.push(RU.torchize(w))
+            mean, std = st.mean_std()
+            tag = "complete" if complete else "perch"
+            out[f"stats_mean_{tag}"] = np.asarray(mean.cpu().numpy())
+            out[f"stats_std_{tag}"] = np.asarray(std.cpu().numpy())
+            out[f"normalized_{tag}"] = st.normalize(RU.torchize(out["emg_wrap"])).cpu().numpy()
+    np.savez_compressed(os.path.join(HERE, "preprocess.npz"), **out)
+    print("preprocess.npz", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
+        gen_preprocess()
+        sys.exit(0)
     gen_dataset()
     gen_model()
     gen_dropout()
+    gen_preprocess()
     copy_ref_artifacts()
