@@ -402,9 +402,10 @@ def run_cuda(args):
     if rank == 0 and world == 1 and not strong:
         # the reference's own launch-bound configuration (go.sh:6): eager vs CUDA-graph step
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
-        from bench_c1 import c1_small_batch
+        from bench_c1 import c1_concurrent_folds, c1_small_batch
         from bench_extra import eval_pipeline, hbm_kernels, preprocess_leg, torch_eager_gpu
         c1 = c1_small_batch(dev)
+        c1["concurrent_folds"] = c1_concurrent_folds(dev)
         eager = torch_eager_gpu(dev, B)              # stock PyTorch on the same GPU, the practical bar
         hbm = hbm_kernels(dev, measured_peaks()["hbm_gbs"])
         evalp = eval_pipeline(dev)

@@ -139,11 +139,36 @@ def cross_validate(des, hyperparams, dataset, id_, epochs=6, save=True, load=Fal
     r, w = cpdist.rank(), cpdist.world_size()
     mine = {}
     saved = (cpdist.rank, cpdist.world_size)
+    K = int(getattr(args, "concurrent_folds", 1) or 1)
     try:
         cpdist.rank, cpdist.world_size = (lambda: 0), (lambda: 1)       # folds train un-sharded
-        for i, key in enumerate(combos):
-            if i % w != r:
-                continue
+        my_folds = [i for i in range(len(combos)) if i % w == r]
+        # the learning rates are constant for the first 5 epochs (StepLR(step_size=5), train.py:79-80), which is
+        # what a captured graph needs; longer folds, checkpoints to resume from or the item loader run one by one
+        if K > 1 and epochs <= 5 and load_dir is None and not getattr(args, "item_loader", False):
+            from .folds import ConcurrentFolds
+            for g0 in range(0, len(my_folds), K):
+                group = my_folds[g0:g0 + K]
+                plist = []
+                for i in group:
+                    params = {'d_e': combos[i][0], 'epochs': epochs}
+                    params.update(dict(zip(names, combos[i][1:])))
+                    print(params)
+                    plist.append(params)
+                dataset.set_train()
+                folds = ConcurrentFolds(dataset, plist, args.batch_size, adabn=args.no_adabn)
+                for _ in range(epochs):
+                    loss_train = folds.run_epoch()
+                for i, model, lt, acc_train in zip(group, folds.models, loss_train, folds.train_accuracy()):
+                    loss_val, acc_val = validate(model, dataset)
+                    print("Epoch %d. Train loss: %.4f\tVal loss: %.4f\tVal acc: %.6f\tTrain acc: %.4f"
+                          % (epochs - 1, lt, loss_val, acc_val, acc_train))
+                    mine[i] = (loss_val, acc_val)
+                    dataset.set_train()
+                del folds
+            my_folds = []
+        for i in my_folds:
+            key = combos[i]
             params = {'d_e': key[0], 'epochs': epochs}
             params.update(dict(zip(names, key[1:])))
             print(params)
@@ -233,6 +258,9 @@ def build_parser():
     parser.add_argument('--sync_bn', action='store_true',
                         help='under torchrun: BatchNorm statistics over the rows of every rank (global-batch parity) '
                              'instead of rank-local ones')
+    parser.add_argument('--concurrent_folds', type=int, default=1,
+                        help='cross-validation: train this many hyper-parameter folds at a time on one GPU, each as a '
+                             'CUDA graph on its own stream (folds.ConcurrentFolds); 1 = one after the other')
     parser.add_argument('--mixed', action='store_true',
                         help='DB2 + DB3 subjects mixed (46 people, DB3 repetition split, DB3 channel 10 zeroed)')
     parser.add_argument('--data_dir', default="../data/")

@@ -62,3 +62,40 @@ def c1_small_batch(dev, B=8, steps=200):
 if __name__ == "__main__":
     import json
     print(json.dumps(c1_small_batch(torch.device("cuda:0"))))
+
+
+def c1_concurrent_folds(dev, B=8, steps=200, ks=(1, 4, 8, 16)):
+    """The reference's cross-validation workload (150 folds x 2,500 steps at batch_size 8, train.py:140-166): K folds
+    in lockstep on one GPU, one CUDA graph + one stream per fold (folds.ConcurrentFolds).  Aggregate windows/s."""
+    from contrastiveprosthetics_b200.folds import ConcurrentFolds
+    from contrastiveprosthetics_b200.load import DB23
+    from contrastiveprosthetics_b200.utils import TaskWrapper
+    ds = DB23(db2=True, device=dev)
+    ds.load_synthetic(with_glove=False)
+    tw = TaskWrapper(ds, with_glove=False)
+    tw.set_train()
+    params = {'d_e': 16, 'dp_emg': 0.5, 'dp_glove': 0.5, 'reg_emg': 1e-5, 'reg_glove': 1e-5, 'lr_emg': 1e-3, 'lr_glove': 1e-3}
+    items = [torch.randperm(tw.D)[:B].to(dev) for _ in range(16)]
+    out = {}
+    for K in ks:
+        folds = ConcurrentFolds(tw, [dict(params) for _ in range(K)], B)
+
+        def one(i):
+            folds.step(tw.get_batch(items[i % 16])[0])
+            if i % 8 == 7:
+                folds.losses = [[] for _ in range(K)]
+                folds.accs = [[] for _ in range(K)]
+        for i in range(20):
+            one(i)
+        folds.join()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            one(i)
+        folds.join()
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0) / steps
+        out[f"K={K}"] = {"ms_per_lockstep": ms, "fold_steps_per_s": K / (ms / 1e3), "windows_per_s": K * B * 41 / (ms / 1e3)}
+        del folds
+    out["workload"] = f"batch_size {B} groups x 41 = {B * 41} windows per fold-step, AdaBN, dropout 0.5, {steps} lock-steps, wall clock"
+    return out
