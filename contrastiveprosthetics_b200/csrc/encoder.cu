@@ -384,12 +384,13 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
                                                                     w.Wc2_lo, w.Wc2d_lo, p->conv1_w, p->conv1_b, w.c1w, w.c1b);
     CP_CHECK_LAUNCH();
     if (tcE) {
+        PrepTcArgs a;
         for (int l = 0; l < CP_N_FC; ++l) {
-            const int K = l == 0 ? K_FC1 : F_FC;
-            prep_weights_tc_kernel<<<(F_FC * K + 255) / 256, 256, 0, st>>>(p->fc_w[l], K, l == 0, w.Wh[l], w.Wl[l],
-                                                                         w.Wth[l], w.Wtl[l]);
-            CP_CHECK_LAUNCH();
+            a.W[l] = p->fc_w[l];
+            a.Wh[l] = w.Wh[l]; a.Wl[l] = w.Wl[l]; a.Wth[l] = w.Wth[l]; a.Wtl[l] = w.Wtl[l];
         }
+        prep_weights_tc_kernel<<<dim3((F_FC * K_FC1 + 255) / 256, CP_N_FC), 256, 0, st>>>(a);
+        CP_CHECK_LAUNCH();
     }
     CP_CUDA(cudaMemcpyAsync(w.X0, x, sizeof(float) * R12, cudaMemcpyDeviceToDevice, st));
 

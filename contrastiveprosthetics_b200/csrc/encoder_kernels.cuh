@@ -811,17 +811,24 @@ prep_weights_kernel(const float* __restrict__ conv2_w, const float* __restrict__
 // Tensor-core engine weight planes, per linear layer l (K = 768 for l = 0 on the permuted flatten):
 //   fwd  Wh/Wl [512][K]   = split(W (l = 0: W1p))          B operand of Y = A . W^T      (K-major)
 //   dgrad Wth/Wtl [K][512] = split(transpose)                B operand of dA = G . W       (K-major)
+// One launch for all 7 layers: blockIdx.y = layer.
+struct PrepTcArgs {
+    const float* W[7];
+    plane_t *Wh[7], *Wl[7], *Wth[7], *Wtl[7];
+};
 __global__ void __launch_bounds__(256)
-prep_weights_tc_kernel(const float* __restrict__ W, int K, int permute_fc1, plane_t* __restrict__ Wh,
-                       plane_t* __restrict__ Wl, plane_t* __restrict__ Wth, plane_t* __restrict__ Wtl) {
+prep_weights_tc_kernel(const PrepTcArgs a) {
+    const int l = blockIdx.y;
+    const int K = l == 0 ? 768 : 512;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 512 * K) return;
     const int o = i / K, k = i % K;
-    const float w = permute_fc1 ? __ldg(W + o * 768 + (k % 64) * 12 + k / 64) : __ldg(W + i);
-    plane_t h, l;
-    split_f16(w, h, l);
-    Wh[i] = h; Wl[i] = l;
-    Wth[(size_t)k * 512 + o] = h; Wtl[(size_t)k * 512 + o] = l;
+    // fc1 runs on the position-major flatten: column p*64+c of the operand is column c*12+p of the parameter
+    const float w = l == 0 ? __ldg(a.W[0] + o * 768 + (k % 64) * 12 + k / 64) : __ldg(a.W[l] + i);
+    plane_t h, lo;
+    split_f16(w, h, lo);
+    a.Wh[l][i] = h; a.Wl[l][i] = lo;
+    a.Wth[l][(size_t)k * 512 + o] = h; a.Wtl[l][(size_t)k * 512 + o] = lo;
 }
 
 // dW = sum_z P[z]  with the inverse re-layouts.  mode 0: identity; 1: fc1 (cols p*64+c -> c*12+p);

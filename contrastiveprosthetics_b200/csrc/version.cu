@@ -2,7 +2,7 @@
 
 unsigned long long g_cp_launches = 0;
 
-extern "C" int cp_version(void) { return 100; }   // 0.1.0
+extern "C" int cp_version(void) { return 110; }   // 0.1.1: + l2, confusion matrix, preprocessing, CP_ENGINE_TC_FP16
 
 // number of kernels this library has launched in this process (host-side counter, not thread-safe
 // across concurrent callers; used by bench.py's gpu_launches)
