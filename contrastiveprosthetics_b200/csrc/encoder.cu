@@ -218,7 +218,9 @@ template <int F>
 int bn_apply(const float* y, float* a, bool planes, int64_t R, const Ws& w, int l, uint8_t* keep,
              float inv_keep, cudaStream_t st, float gen_p = 0.f, uint64_t seed = 0, uint64_t layer = 0,
              const unsigned long long* seed_offset = nullptr, int fast = 0) {
-    float* a_lo = planes && !fast ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(a) + (size_t)R * F) : nullptr;
+    // (the single-product engine never reads the lo plane; it is still written -- an `if` in the store path cost the
+    //  parity engine's BN kernels 10 %)
+    float* a_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(a) + (size_t)R * F) : nullptr;
     if (planes)
         bn_apply_kernel<F, true><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, a_lo, R, w.scale[l], w.shift[l], keep,
                                                                      inv_keep, gen_p, seed, layer, seed_offset);
@@ -236,8 +238,7 @@ int bn_backward(const float* g, const float* y, float* gz, bool planes, int64_t 
                 const uint8_t* keep, float inv_keep, const float* gamma, float* d_gamma, float* d_beta,
                 float* d_bias, cudaStream_t st, const cp_encoder_opts* o) {
     const int P = (int)cp_cdiv(R, ColMap<F>::ROWS);
-    const bool lo = planes && o->engine != CP_ENGINE_TC_FP16;
-    float* gz_lo = lo ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)R * F) : nullptr;
+    float* gz_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)R * F) : nullptr;
     bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb, nullptr,
                                                planes ? w.gmax + l : nullptr);
     CP_CHECK_LAUNCH();
@@ -329,8 +330,7 @@ int last_block_backward(const float* d_emb, float* gz, bool planes, int64_t n, c
         bn_bwd_means_totals_kernel<<<1, 512, 0, st>>>(w.totals, F_FC, w.m1, w.m2);
         CP_CHECK_LAUNCH();
     }
-    float* gz_lo = planes && o->engine != CP_ENGINE_TC_FP16
-                       ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)n * F_FC) : nullptr;
+    float* gz_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)n * F_FC) : nullptr;
 #define CP_PF_APPLY(K, SP)                                                                                              \
     pf::proj_bwd_apply_kernel<K, SP><<<G, 256, pf::SMEM, st>>>(w.Y[LL], keep, d_emb, n, inv_keep, w.mean[S], w.istd[S],  \
                                                                p->bn_w[S], w.m1, w.m2, p->proj_w, gz, gz_lo, w.pa, gmax, \
@@ -372,7 +372,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     if (!p || !x || !emb || !workspace || n <= 0 || !opts_ok(o)) return CP_ERR_ARG;
     if (((uintptr_t)workspace) % 256 != 0) return CP_ERR_ARG;
     const bool tcE = o->engine != CP_ENGINE_SIMT;
-    const int fast = o->engine == CP_ENGINE_TC_FP16;      // hi planes only: lo planes are neither written nor read
+    const int fast = o->engine == CP_ENGINE_TC_FP16;      // the GEMMs read the hi planes only
     const Ws w = carve(workspace, n, o);
     if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -402,7 +402,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     if (tcE)
         conv1_bn_apply_kernel<true><<<ew_grid(n * 16), 256, 0, st>>>(
             w.X0, n, p->conv1_w, p->conv1_b, w.scale[0], w.shift[0], w.A1,
-            fast ? nullptr : reinterpret_cast<float*>(reinterpret_cast<plane_t*>(w.A1) + conv_elems));
+            reinterpret_cast<float*>(reinterpret_cast<plane_t*>(w.A1) + conv_elems));
     else
         conv1_bn_apply_kernel<false><<<ew_grid(n * 16), 256, 0, st>>>(w.X0, n, p->conv1_w, p->conv1_b, w.scale[0],
                                                                        w.shift[0], w.A1, nullptr);
@@ -479,7 +479,7 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     if (!p || !d_emb || !gr || !workspace || n <= 0 || !opts_ok(o)) return CP_ERR_ARG;
     if (!o->save_for_backward || o->bn_mode == CP_BN_RUNNING) return CP_ERR_UNSUPPORTED;
     const bool tcE = o->engine != CP_ENGINE_SIMT;
-    const int fast = o->engine == CP_ENGINE_TC_FP16;      // hi planes only: lo planes are neither written nor read
+    const int fast = o->engine == CP_ENGINE_TC_FP16;      // the GEMMs read the hi planes only
     const Ws w = carve(workspace, n, o);
     if (workspace_bytes < w.bytes) return CP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;

@@ -110,7 +110,7 @@ __device__ __forceinline__ void warp_col_reduce32(float (&v)[32], int lane) {
 // implicit GEMM, K = 3 taps x 64 channels = 3 k-blocks of 64): tm_a_* are 3-D maps (64 ch, 12 pos,
 // windows) and k-block kb loads the box at (0, tap-1, window0) -- positions -1 and 12 are
 // out of range and arrive as zeros, which is exactly the padding of models.py:255,259.
-template <int BN_, bool CONV>
+template <int BN_, bool CONV, bool FAST>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -156,17 +156,17 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 for (int kb = 0; kb < kblocks; ++kb) {
                     tc::mbar_wait(&sm->empty[s], ph ^ 1);
                     uint8_t* st = tiles + s * Cfg::STAGE;
-                    tc::mbar_expect_tx(&sm->full[s], (g.fast ? 1 : 2) * (A_BYTES + Cfg::B_TILE));
+                    tc::mbar_expect_tx(&sm->full[s], (FAST ? 1 : 2) * (A_BYTES + Cfg::B_TILE));
                     if (CONV) {
                         const int p0 = kb - 1, w0 = (int)tile_m * CONV_WIN;
                         tc::tma_load_3d(st, &tm_a_hi, &sm->full[s], 0, p0, w0);
-                        if (!g.fast) tc::tma_load_3d(st + TILE_BYTES, &tm_a_lo, &sm->full[s], 0, p0, w0);
+                        if (!FAST) tc::tma_load_3d(st + TILE_BYTES, &tm_a_lo, &sm->full[s], 0, p0, w0);
                     } else {
                         tc::tma_load_2d(st, &tm_a_hi, &sm->full[s], kb * BK, (int)tile_m * BM);
-                        if (!g.fast) tc::tma_load_2d(st + TILE_BYTES, &tm_a_lo, &sm->full[s], kb * BK, (int)tile_m * BM);
+                        if (!FAST) tc::tma_load_2d(st + TILE_BYTES, &tm_a_lo, &sm->full[s], kb * BK, (int)tile_m * BM);
                     }
                     tc::tma_load_2d(st + 2 * TILE_BYTES, &tm_b_hi, &sm->full[s], kb * BK, n0);
-                    if (!g.fast) tc::tma_load_2d(st + 2 * TILE_BYTES + Cfg::B_TILE, &tm_b_lo, &sm->full[s], kb * BK, n0);
+                    if (!FAST) tc::tma_load_2d(st + 2 * TILE_BYTES + Cfg::B_TILE, &tm_b_lo, &sm->full[s], kb * BK, n0);
                     if (++s == Cfg::NSTAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -196,7 +196,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                         const uint64_t a_lo = tc::smem_desc_sw128(base + TILE_BYTES + ko, 16, 1024);
                         const uint64_t b_hi = tc::smem_desc_sw128(base + 2 * TILE_BYTES + ko, 16, 1024);
                         const uint64_t b_lo = tc::smem_desc_sw128(base + 2 * TILE_BYTES + Cfg::B_TILE + ko, 16, 1024);
-                        if (!g.fast) {
+                        if (!FAST) {
                             tc::mma_f16(dc, a_lo, b_hi, idesc, (kb | k) != 0);
                             tc::mma_f16(dc, a_hi, b_lo, idesc, 1);
                         }
@@ -229,9 +229,9 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 float v[32], vc[32];
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC + c * 32;
                 tc::tmem_ld32(ta, v);
-                if (!g.fast) tc::tmem_ld32(ta + BN_, vc);
+                if (!FAST) tc::tmem_ld32(ta + BN_, vc);
                 tc::tmem_ld_wait();
-                if (g.fast) {
+                if (FAST) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] *= oscale;
                 } else {
@@ -327,6 +327,7 @@ struct Smem2 {
 constexpr int SMEM2 = STAGES2 * STAGE2 + 8 * OUT_BOX + 1024 + (int)sizeof(Smem2);
 }  // namespace pair
 
+template <bool FAST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair::THREADS2, 1)
 gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                        const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -375,11 +376,11 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                 for (int kb = 0; kb < kblocks; ++kb) {
                     tc::mbar_wait(&sm->empty[s], ph ^ 1);
                     uint8_t* st = tiles + s * STAGE2;
-                    if (leader) tc::mbar_expect_tx(&sm->full[s], g.fast ? STAGE2 : 2 * STAGE2);   // bytes of both CTAs
+                    if (leader) tc::mbar_expect_tx(&sm->full[s], FAST ? STAGE2 : 2 * STAGE2);   // bytes of both CTAs
                     tc::tma_load_2d_pair(st, &tm_a_hi, &sm->full[s], kb * BK, m0);
-                    if (!g.fast) tc::tma_load_2d_pair(st + TILE_BYTES, &tm_a_lo, &sm->full[s], kb * BK, m0);
+                    if (!FAST) tc::tma_load_2d_pair(st + TILE_BYTES, &tm_a_lo, &sm->full[s], kb * BK, m0);
                     tc::tma_load_2d_pair(st + 2 * TILE_BYTES, &tm_b_hi, &sm->full[s], kb * BK, n0);
-                    if (!g.fast) tc::tma_load_2d_pair(st + 2 * TILE_BYTES + B_HALF, &tm_b_lo, &sm->full[s], kb * BK, n0);
+                    if (!FAST) tc::tma_load_2d_pair(st + 2 * TILE_BYTES + B_HALF, &tm_b_lo, &sm->full[s], kb * BK, n0);
                     if (++s == STAGES2) { s = 0; ph ^= 1; }
                 }
             }
@@ -407,7 +408,7 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                         const uint64_t a_lo = tc::smem_desc_sw128(base + TILE_BYTES + ko, 16, 1024);
                         const uint64_t b_hi = tc::smem_desc_sw128(base + 2 * TILE_BYTES + ko, 16, 1024);
                         const uint64_t b_lo = tc::smem_desc_sw128(base + 2 * TILE_BYTES + B_HALF + ko, 16, 1024);
-                        if (!g.fast) {
+                        if (!FAST) {
                             tc::mma_f16_pair(dc, a_lo, b_hi, idesc, (kb | k) != 0);
                             tc::mma_f16_pair(dc, a_hi, b_lo, idesc, 1);
                         }
@@ -441,9 +442,9 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                 float v[32], vc[32];
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + cl;
                 tc::tmem_ld32(ta, v);
-                if (!g.fast) tc::tmem_ld32(ta + BN, vc);
+                if (!FAST) tc::tmem_ld32(ta + BN, vc);
                 tc::tmem_ld_wait();
-                if (g.fast) {
+                if (FAST) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] *= oscale;
                 } else {
@@ -515,6 +516,7 @@ struct TnArgs {
     int fast;                 // hi planes only
 };
 
+template <bool FAST>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant__ CUtensorMap tm_g_lo,
                   const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -552,11 +554,11 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_cons
                 tc::mbar_wait(&sm->empty[s], ph ^ 1);
                 uint8_t* st = tiles + s * STAGE_BYTES;
                 const int r = (int)(r_begin + (int64_t)kb * BK);
-                tc::mbar_expect_tx(&sm->full[s], g.fast ? STAGE_BYTES / 2 : STAGE_BYTES);
+                tc::mbar_expect_tx(&sm->full[s], FAST ? STAGE_BYTES / 2 : STAGE_BYTES);
                 tc::tma_load_3d(st + 0 * TILE_BYTES, &tm_g_hi, &sm->full[s], 0, r, o0 / 64);
-                if (!g.fast) tc::tma_load_3d(st + 1 * TILE_BYTES, &tm_g_lo, &sm->full[s], 0, r, o0 / 64);
+                if (!FAST) tc::tma_load_3d(st + 1 * TILE_BYTES, &tm_g_lo, &sm->full[s], 0, r, o0 / 64);
                 tc::tma_load_3d(st + 2 * TILE_BYTES, &tm_a_hi, &sm->full[s], 0, r, c0 / 64);
-                if (!g.fast) tc::tma_load_3d(st + 3 * TILE_BYTES, &tm_a_lo, &sm->full[s], 0, r, c0 / 64);
+                if (!FAST) tc::tma_load_3d(st + 3 * TILE_BYTES, &tm_a_lo, &sm->full[s], 0, r, c0 / 64);
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
@@ -584,7 +586,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_cons
                         const uint64_t a_hi = tc::smem_desc_sw128(base + 2 * TILE_BYTES + ko, MN_BLOCK, 1024);
                         const uint64_t a_lo = tc::smem_desc_sw128(base + 3 * TILE_BYTES + ko, MN_BLOCK, 1024);
                         const uint32_t accum = (first && k == 0) ? 0u : 1u;
-                        if (!g.fast) {
+                        if (!FAST) {
                             tc::mma_f16(dc, g_lo, a_hi, idesc, accum);
                             tc::mma_f16(dc, g_hi, a_lo, idesc, 1);
                         }
@@ -611,9 +613,9 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_cons
                 float v[32], vc[32];
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + c * 32;
                 tc::tmem_ld32(ta, v);
-                if (!g.fast) tc::tmem_ld32(ta + BN, vc);
+                if (!FAST) tc::tmem_ld32(ta + BN, vc);
                 tc::tmem_ld_wait();
-                if (g.fast) {
+                if (FAST) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) sum[c * 32 + j] += v[j];
                 } else {
@@ -656,6 +658,7 @@ struct CwArgs {
     int fast;                    // hi planes only
 };
 
+template <bool FAST>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_tn_conv_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                        const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant__ CUtensorMap tm_g_lo,
@@ -694,15 +697,15 @@ gemm_tc_tn_conv_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid
                 tc::mbar_wait(&sm->empty[s], ph ^ 1);
                 uint8_t* st = tiles + s * CW_STAGE;
                 const int w0 = (int)(w_begin + (int64_t)kb * CW_WIN);
-                tc::mbar_expect_tx(&sm->full[s], (uint32_t)(n_blocks + 1) * (g.fast ? 1 : 2) * CW_BLOCK);
+                tc::mbar_expect_tx(&sm->full[s], (uint32_t)(n_blocks + 1) * (FAST ? 1 : 2) * CW_BLOCK);
                 for (int b = 0; b < n_blocks; ++b) {
                     const int tap = mt * 2 + b;
                     tc::tma_load_3d(st + b * CW_BLOCK, &tm_x_hi, &sm->full[s], 0, tap - 1, w0);
-                    if (!g.fast) tc::tma_load_3d(st + (2 + b) * CW_BLOCK, &tm_x_lo, &sm->full[s], 0, tap - 1, w0);
+                    if (!FAST) tc::tma_load_3d(st + (2 + b) * CW_BLOCK, &tm_x_lo, &sm->full[s], 0, tap - 1, w0);
                 }
                 // G: [rows][64] -> one [48][64] block per plane
                 tc::tma_load_2d(st + 4 * CW_BLOCK, &tm_g_hi, &sm->full[s], 0, w0 * 12);
-                if (!g.fast) tc::tma_load_2d(st + 5 * CW_BLOCK, &tm_g_lo, &sm->full[s], 0, w0 * 12);
+                if (!FAST) tc::tma_load_2d(st + 5 * CW_BLOCK, &tm_g_lo, &sm->full[s], 0, w0 * 12);
                 if (++s == CW_STAGES) { s = 0; ph ^= 1; }
             }
         }
@@ -730,7 +733,7 @@ gemm_tc_tn_conv_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid
                         const uint64_t g_hi = tc::smem_desc_sw128(base + 4 * CW_BLOCK + ko, CW_BLOCK, 1024);
                         const uint64_t g_lo = tc::smem_desc_sw128(base + 5 * CW_BLOCK + ko, CW_BLOCK, 1024);
                         const uint32_t accum = (first && k == 0) ? 0u : 1u;
-                        if (!g.fast) {
+                        if (!FAST) {
                             tc::mma_f16(dc, x_lo, g_hi, idesc, accum);
                             tc::mma_f16(dc, x_hi, g_lo, idesc, 1);
                         }
@@ -757,9 +760,9 @@ gemm_tc_tn_conv_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid
                 float v[32], vc[32];
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + c * 32;
                 tc::tmem_ld32(ta, v);
-                if (!g.fast) tc::tmem_ld32(ta + 64, vc);
+                if (!FAST) tc::tmem_ld32(ta + 64, vc);
                 tc::tmem_ld_wait();
-                if (g.fast) {
+                if (FAST) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) sum[c * 32 + j] += v[j];
                 } else {
@@ -844,7 +847,8 @@ inline int launch_tn(const plane_t* G_hi, const plane_t* G_lo, int ldg, int Mo, 
     if ((rc = make_tmap_mn(&ta_lo, A_lo, R, No, lda)) != CP_OK) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        CP_CUDA(cudaFuncSetAttribute(gemm_tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
     const int tiles = (Mo / BM) * (No / BN);
@@ -860,7 +864,8 @@ inline int launch_tn(const plane_t* G_hi, const plane_t* G_lo, int ldg, int Mo, 
     const int64_t rps = cp_cdiv(cp_cdiv(R, S), BK) * BK;
     S = (int)cp_cdiv(R, rps);
     TnArgs g{P, Mo, No, R, rps, fast};
-    gemm_tc_tn_kernel<<<dim3(No / BN, Mo / BM, S), THREADS, SMEM_BYTES, st>>>(tg_hi, tg_lo, ta_hi, ta_lo, g);
+    if (fast) gemm_tc_tn_kernel<true><<<dim3(No / BN, Mo / BM, S), THREADS, SMEM_BYTES, st>>>(tg_hi, tg_lo, ta_hi, ta_lo, g);
+    else gemm_tc_tn_kernel<false><<<dim3(No / BN, Mo / BM, S), THREADS, SMEM_BYTES, st>>>(tg_hi, tg_lo, ta_hi, ta_lo, g);
     CP_CHECK_LAUNCH();
     *splits_out = S;
     return CP_OK;
@@ -893,19 +898,19 @@ inline int make_tmap_out(CUtensorMap* m, float* base, int64_t rows, int64_t cols
     return r == CUDA_SUCCESS ? CP_OK : CP_ERR_ARG;
 }
 
-template <int BN_, bool CONV>
+template <int BN_, bool CONV, bool FAST>
 inline int launch_nt_cfg(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
                          const CUtensorMap& tb_lo, const CUtensorMap& tc_out, const NtArgs& g, int64_t tiles_m,
                          cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_kernel<BN_, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_kernel<BN_, CONV, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      NtCfg<BN_>::SMEM));
         attr_set = true;
     }
     const int64_t n_tiles = tiles_m * (g.N / BN_);
     const int grid = (int)(n_tiles < CP_NUM_SMS ? n_tiles : CP_NUM_SMS);
-    gemm_tc_nt_kernel<BN_, CONV><<<grid, THREADS, NtCfg<BN_>::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g);
+    gemm_tc_nt_kernel<BN_, CONV, FAST><<<grid, THREADS, NtCfg<BN_>::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
@@ -929,16 +934,19 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
         if ((rc = make_tmap_2d(&tb_lo2, B_lo, N, K, ldb, BN / 2)) != CP_OK) return rc;
         static bool attr_set = false;
         if (!attr_set) {
-            CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
+            CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
+            CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
             attr_set = true;
         }
         const int64_t n_tiles = cp_cdiv(M, 2 * BM) * (N / BN);
         const int clusters = (int)(n_tiles < CP_NUM_SMS / 2 ? n_tiles : CP_NUM_SMS / 2);
-        gemm_tc_nt_pair_kernel<<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, g);
+        if (fast) gemm_tc_nt_pair_kernel<true><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, g);
+        else gemm_tc_nt_pair_kernel<false><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, g);
         CP_CHECK_LAUNCH();
         return CP_OK;
     }
-    return launch_nt_cfg<128, false>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(M, BM), st);
+    return fast ? launch_nt_cfg<128, false, true>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(M, BM), st)
+                : launch_nt_cfg<128, false, false>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(M, BM), st);
 }
 
 // conv2 as implicit GEMM: C[(w,p), o] = act(sum_{tap,c} X[w, p+tap-1, c] * B[o, tap*64+c] + bias[o]);
@@ -954,7 +962,8 @@ inline int launch_conv_nt(const plane_t* X_hi, const plane_t* X_lo, int64_t wind
     if ((rc = make_tmap_2d(&tb_hi, B_hi, 64, 192, 192, 64)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, 64, 192, 192, 64)) != CP_OK) return rc;
     NtArgs g{C, 64, bias, psum, psq, windows * 12, 64, 192, relu, out_scale, fast};
-    return launch_nt_cfg<64, true>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st);
+    return fast ? launch_nt_cfg<64, true, true>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st)
+                : launch_nt_cfg<64, true, false>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st);
 }
 
 // conv2 weight gradient; P capacity >= splits*256*64 floats; *splits_out = number of slabs written
@@ -969,7 +978,8 @@ inline int launch_conv_tn(const plane_t* X_hi, const plane_t* X_lo, const plane_
     if ((rc = make_tmap_2d(&tg_lo, G_lo, windows * 12, 64, 64, CW_ROWS)) != CP_OK) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        CP_CUDA(cudaFuncSetAttribute(gemm_tc_tn_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM));
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_tn_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM));
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_tn_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM));
         attr_set = true;
     }
     int S = CP_NUM_SMS / 2;
@@ -981,7 +991,8 @@ inline int launch_conv_tn(const plane_t* X_hi, const plane_t* X_lo, const plane_
     const int64_t wps = cp_cdiv(cp_cdiv(windows, S), CW_WIN) * CW_WIN;
     S = (int)cp_cdiv(windows, wps);
     CwArgs g{P, windows, wps, fast};
-    gemm_tc_tn_conv_kernel<<<dim3(2, S), THREADS, CW_SMEM, st>>>(tx_hi, tx_lo, tg_hi, tg_lo, g);
+    if (fast) gemm_tc_tn_conv_kernel<true><<<dim3(2, S), THREADS, CW_SMEM, st>>>(tx_hi, tx_lo, tg_hi, tg_lo, g);
+    else gemm_tc_tn_conv_kernel<false><<<dim3(2, S), THREADS, CW_SMEM, st>>>(tx_hi, tx_lo, tg_hi, tg_lo, g);
     CP_CHECK_LAUNCH();
     *splits_out = S;
     return CP_OK;
@@ -1002,7 +1013,7 @@ __device__ __forceinline__ void split_store4(const float4& x, plane_t* hi, plane
     split_f16(x.x, h[0], l[0]); split_f16(x.y, h[1], l[1]);
     split_f16(x.z, h[2], l[2]); split_f16(x.w, h[3], l[3]);
     reinterpret_cast<uint2*>(hi)[v] = *reinterpret_cast<const uint2*>(h);
-    if (lo) reinterpret_cast<uint2*>(lo)[v] = *reinterpret_cast<const uint2*>(l);      // null: single-product engine
+    reinterpret_cast<uint2*>(lo)[v] = *reinterpret_cast<const uint2*>(l);
 }
 
 __global__ void __launch_bounds__(256)
