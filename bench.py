@@ -412,9 +412,9 @@ def run_cuda(args):
         prep = preprocess_leg(dev)
     if rank == 0:
         if world == 1:       # N = 1 only: at N > 1 the other ranks spin in the barrier on the same host cores
-            wps, cms, cores = cpu_oracle_steps(n_steps=3, warmup=1, groups=256)
+            wps, cms, cores = cpu_oracle_steps(n_steps=16, warmup=2, groups=512)
             cpu = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
-                   "sample": f"3 steps x {256 * T} windows of the same train step (oracle/ torch-CPU port), "
+                   "sample": f"16 steps x {512 * T} windows of the same train step (oracle/ torch-CPU port), "
                              f"{cms:.0f} ms/step"}
         line = {
             "metric": "train sEMG windows/s", "value": value, "unit": "windows/s", "n_gpus": world,
