@@ -117,7 +117,8 @@ class _EncoderFn(torch.autograd.Function):
         nbytes = L.cp_encoder_workspace_bytes(n, ctypes.byref(opts))
         if nbytes == 0:
             raise RuntimeError("cp_encoder_workspace_bytes rejected the configuration")
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        alloc = cfg.get("ws_alloc")          # tests: a caller-owned (guarded) workspace; default: a fresh tensor
+        ws = alloc(nbytes) if alloc is not None else torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         emb = torch.empty((n, 16), dtype=torch.float32, device=x.device)
         hook = None
         if cfg.get("sync_bn"):
@@ -501,7 +502,8 @@ class EMGNet(nn.Module):
                "ext_masks": self.ext_dropout_masks if dp > 0 else None,
                "dropout_step": self.dropout_step, "bn_rm": rm, "bn_rv": rv,
                "need_bwd": torch.is_grad_enabled() and self.training,
-               "tap": self.debug_tap, "sync_bn": self._sync_active(), "group": self.process_group}
+               "tap": self.debug_tap, "sync_bn": self._sync_active(), "group": self.process_group,
+               "ws_alloc": getattr(self, "ws_alloc", None)}
         return _EncoderFn.apply(x, cfg, *self.kernel_params())
 
     def _sync_active(self):

@@ -217,6 +217,31 @@ def test_single_product_fp16_engine(adabn, n):
     assert rel_err(emb3, ref_emb) < FWD_TOL < rel_err(emb, ref_emb)
 
 
+@pytest.mark.parametrize("engine", ENGINES + [_lib.ENGINE_TC_FP16])
+@pytest.mark.parametrize("n,dp", [(41 * 8, 0.5), (777, 0.0), (148 * 16 + 5, 0.5)])
+def test_workspace_is_never_overrun(n, dp, engine):
+    """The workspace handed to cp_encoder_forward / backward sits between two guard bands: no kernel (TMA stores,
+    bulk-copy rings, partial-sum rows, planes) may write a byte outside the cp_encoder_workspace_bytes it asked for."""
+    guard = 1 << 16
+    held = {}
+
+    def alloc(nbytes):
+        buf = torch.full((nbytes + 2 * guard,), 0xA5, dtype=torch.uint8, device="cuda")
+        held["buf"], held["n"] = buf, nbytes
+        return buf[guard:guard + nbytes]
+
+    m = _model(perturbed_state(5, True), True, dp, engine)
+    m.train(True)
+    m.emg_net.ws_alloc = alloc
+    g = torch.Generator().manual_seed(n)
+    emb = m.emg_net.encode_flat(torch.randn(n, 12, generator=g).cuda())
+    emb.backward(torch.randn(n, 16, generator=g).cuda())
+    torch.cuda.synchronize()
+    buf, nb = held["buf"], held["n"]
+    assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + nb:] == 0xA5).all())
+    assert all(torch.isfinite(p.grad).all() for p in m.emg_net.parameters())
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 def test_backward_error_in_fp64_context(engine):
     """With the ReLU pattern fixed, fp32 CUDA gradients are as close to the fp64 truth as the fp32
