@@ -234,22 +234,26 @@ int bn_apply(const float* y, float* a, bool planes, int64_t R, const Ws& w, int 
 // BN backward + ReLU backward of stage l:  g (grad w.r.t. stage output A) -> gz (grad w.r.t. the
 // pre-activation), d_gamma, d_beta, d_bias
 template <int F>
+// stats_ready: w.m1 / w.m2 / d_gamma / d_beta / w.gmax[l] were already produced from the next layer's parameter
+// gradients (bn_bwd_stats_from_wgrad_kernel + the data-gradient GEMM's max|C|): no reduce pass
 int bn_backward(const float* g, const float* y, float* gz, bool planes, int64_t R, const Ws& w, int l,
                 const uint8_t* keep, float inv_keep, const float* gamma, float* d_gamma, float* d_beta,
-                float* d_bias, cudaStream_t st, const cp_encoder_opts* o) {
+                float* d_bias, cudaStream_t st, const cp_encoder_opts* o, bool stats_ready = false) {
     const int P = (int)cp_cdiv(R, ColMap<F>::ROWS);
     float* gz_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)R * F) : nullptr;
-    bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb, nullptr,
-                                               planes ? w.gmax + l : nullptr);
-    CP_CHECK_LAUNCH();
-    const bool sync = o->allreduce != nullptr;
-    bn_bwd_finalize_kernel<<<dim3(F / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta,
-                                                                    w.rscratch, w.tickets, sync ? w.totals : nullptr);
-    CP_CHECK_LAUNCH();
-    if (sync) {
-        if (int rc = sync_totals(w, F, o, st)) return rc;
-        bn_bwd_means_totals_kernel<<<(F + 511) / 512, 512, 0, st>>>(w.totals, F, w.m1, w.m2);
+    if (!stats_ready) {
+        bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb, nullptr,
+                                                   planes ? w.gmax + l : nullptr);
         CP_CHECK_LAUNCH();
+        const bool sync = o->allreduce != nullptr;
+        bn_bwd_finalize_kernel<<<dim3(F / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta,
+                                                                        w.rscratch, w.tickets, sync ? w.totals : nullptr);
+        CP_CHECK_LAUNCH();
+        if (sync) {
+            if (int rc = sync_totals(w, F, o, st)) return rc;
+            bn_bwd_means_totals_kernel<<<(F + 511) / 512, 512, 0, st>>>(w.totals, F, w.m1, w.m2);
+            CP_CHECK_LAUNCH();
+        }
     }
     if (planes)
         bn_bwd_apply_kernel<F, true><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], gamma, w.m1,
@@ -351,9 +355,10 @@ bool opts_ok(const cp_encoder_opts* o) {
 
 // weight-gradient through the tensor-core split-K kernel + the shared re-layout / reduce kernel
 int tc_wgrad(const plane_t* Gh, const plane_t* Gl, int Mo, const plane_t* Ah, const plane_t* Al, int No, int64_t R,
-             float* wpart, float* out, int mode, cudaStream_t st, const float* g_scale_inv, int fast = 0) {
+             float* wpart, float* out, int mode, cudaStream_t st, const float* g_scale_inv, int fast = 0,
+             bool alone = false) {
     int S = 0;
-    CP_TRY(tcg::launch_tn(Gh, Gl, Mo, Mo, Ah, Al, No, No, R, wpart, WPART_ELEMS, &S, st, fast));
+    CP_TRY(tcg::launch_tn(Gh, Gl, Mo, Mo, Ah, Al, No, No, R, wpart, WPART_ELEMS, &S, st, fast, alone));
     wgrad_reduce_kernel<<<(unsigned)cp_cdiv((int64_t)Mo * No, 256), 256, 0, st>>>(wpart, S, Mo, No, out, mode, g_scale_inv);
     CP_CHECK_LAUNCH();
     return CP_OK;
@@ -499,6 +504,8 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
         bool used[2] = {false, false};
         auto g1 = [&](int b) { return b ? w.G1b : w.G1; };
         auto g1lo = [&](int b, size_t elems) { return lo_of(g1(b), elems); };
+        bool stats_ready = false;                      // BN sums of the stage about to be processed already known
+        cudaEvent_t last_side = nullptr;               // completion of the latest side-stream GEMM (owner of w.wpart)
         for (int l = CP_N_FC - 1; l >= 0; --l, ++nb) {
             const int b = nb & 1;
             const uint8_t* keep = (l >= 3 && o->dropout_p > 0.f) ? w.keep[l - 3] : nullptr;
@@ -507,15 +514,39 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
                 CP_TRY(last_block_backward(d_emb, g1(b), true, n, w, keep, inv_keep, p, gr, st, o));
             else
                 CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], g1(b), true, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
-                                         gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st, o));
+                                         gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st, o, stats_ready));
             const int K = l == 0 ? K_FC1 : F_FC;
             const float* ain = l == 0 ? w.A2 : w.A[l - 1];
             const plane_t* ah = hi_of(ain);
             const plane_t* al = lo_of(ain, l == 0 ? conv_elems : fc_elems);
             const float* gsi = w.gscale_inv + 2 + l;
+            // The stage below (BN stage 1 + l: conv2 for l = 0) feeds this layer without dropout and statistics are
+            // rank-local: its BN-backward sums follow from this layer's dW / db (bn_bwd_stats_from_wgrad_kernel), so
+            // the weight gradient runs in line (its overlap with the BN backward bought nothing) and the
+            // reduce pass over (dA, Y) of that stage is skipped
+            const bool below_has_dropout = l - 1 >= 3 && o->dropout_p > 0.f;
+            const bool algebraic = !below_has_dropout && o->allreduce == nullptr;
             // main stream: G0 = G1 . W_l
             CP_TRY(tcg::launch_nt(hi_of(g1(b)), g1lo(b, fc_elems), n, F_FC, F_FC, w.Wth[l], w.Wtl[l], K, F_FC, nullptr, w.G0,
-                                  K, nullptr, nullptr, 0, st, gsi, fast));
+                                  K, nullptr, nullptr, 0, st, gsi, fast, algebraic ? w.gmax + 1 + l : nullptr));
+            if (algebraic) {
+                if (last_side) CP_CUDA(cudaStreamWaitEvent(st, last_side, 0));     // w.wpart is shared with the side stream
+                CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, st, gsi, fast,
+                                true));
+                const int s_below = 1 + l;             // BN stage of this layer's input
+                if (l == 0)
+                    bn_bwd_stats_from_wgrad_kernel<12><<<K_FC1 / 96, 512, 0, st>>>(
+                        p->fc_w[0], gr->fc_w[0], gr->fc_b[0], F_FC, K_FC1, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
+                        gr->bn_w[s_below], gr->bn_b[s_below]);
+                else
+                    bn_bwd_stats_from_wgrad_kernel<1><<<F_FC / 64, 512, 0, st>>>(
+                        p->fc_w[l], gr->fc_w[l], gr->fc_b[l], F_FC, F_FC, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
+                        gr->bn_w[s_below], gr->bn_b[s_below]);
+                CP_CHECK_LAUNCH();
+                stats_ready = true;
+                continue;
+            }
+            stats_ready = false;
             // side stream: dW_l = G1^T . A_{l-1}.  It starts when the data-gradient GEMM above has finished (two
             // persistent GEMMs cannot share an SM), i.e. alongside the HBM-bound BN-backward kernels of layer l-1
             CP_CUDA(cudaEventRecord(g_side.ready[b], st));
@@ -523,12 +554,13 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, ss, gsi, fast));
             CP_CUDA(cudaEventRecord(g_side.done[b], ss));
             used[b] = true;
+            last_side = g_side.done[b];
         }
         // conv2 block: G0 is [n*12, 64] (same memory order as the [n,768] position-major flatten)
         const int b = nb & 1;
         if (used[b]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b], 0));
         CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, g1(b), true, R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1],
-                                   gr->bn_b[1], gr->conv2_b, st, o));
+                                   gr->bn_b[1], gr->conv2_b, st, o, stats_ready));
         CP_CUDA(cudaEventRecord(g_side.ready[b], st));
         CP_CUDA(cudaStreamWaitEvent(ss, g_side.ready[b], 0));
         CP_CUDA(cudaMemsetAsync(gr->conv2_w, 0, sizeof(float) * 64 * 64 * 9, ss));

@@ -594,6 +594,57 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, in
         *reinterpret_cast<float4*>(pdb + (int64_t)blockIdx.x * F + qx * 4) = make_float4(sb[0], sb[1], sb[2], sb[3]);
 }
 
+// ------------------------------------------------- BN-backward sums without a pass over the activations
+// For a BN stage whose output A = gamma*xh + beta feeds the next Linear layer UNMASKED (no dropout), the gradient
+// g = dA = G1 . W of that layer is linear in G1, so the two sums the BN backward needs over all R rows are already
+// contained in the layer's own parameter gradients db = colsum(G1), dW = G1^T . A:
+//     sum_r g[r,c]          = sum_k db[k] W[k,c]
+//     sum_r g[r,c] xh[r,c]  = sum_k W[k,c] (G1^T xh)[k,c] = (sum_k W[k,c] dW[k,c] - beta[c] sum_k db[k] W[k,c]) / gamma[c]
+// -- a [512 x F] reduction instead of two reads of [R x F] (bn_bwd_reduce_kernel).  GROUP = 12 folds the 12 positions of
+// a conv-stage channel (flatten column ch*12 + p, models.py:263) into its per-channel BN2d sums.  gamma == 0 makes the
+// second sum unobservable from dW -- and irrelevant to the data gradient, which is multiplied by gamma -- it is reported
+// as 0.  Double accumulation in a fixed order (deterministic).  Outputs like bn_bwd_finalize_kernel.
+template <int GROUP>
+__global__ void __launch_bounds__(512)
+bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restrict__ dW, const float* __restrict__ db,
+                               int K_out /*rows of W*/, int cols /*columns of W = F * GROUP*/, int64_t R /*rows per column*/,
+                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                               float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ d_gamma,
+                               float* __restrict__ d_beta) {
+    constexpr int COLS = GROUP == 1 ? 64 : 96;       // columns per CTA (96 = 8 channels x 12 positions)
+    __shared__ double s_a[4][COLS], s_t[4][COLS];
+    const int cx = threadIdx.x % 128, ky = threadIdx.x / 128;          // 128 column slots (COLS used) x 4 row lanes
+    const int col = blockIdx.x * COLS + cx;
+    double a = 0.0, t = 0.0;
+    if (cx < COLS && col < cols) {
+        for (int k = ky; k < K_out; k += 4) {
+            const double w = (double)__ldg(W + (size_t)k * cols + col);
+            a += (double)__ldg(db + k) * w;
+            t += w * (double)__ldg(dW + (size_t)k * cols + col);
+        }
+    }
+    if (cx < COLS) { s_a[ky][cx] = a; s_t[ky][cx] = t; }
+    __syncthreads();
+    // one thread per BN feature of this CTA
+    const int nfeat = COLS / GROUP;
+    if (threadIdx.x < nfeat) {
+        const int f = blockIdx.x * nfeat + threadIdx.x;
+        if (f * GROUP < cols) {
+            double sa = 0.0, stt = 0.0;
+            for (int p = 0; p < GROUP; ++p)
+                for (int y = 0; y < 4; ++y) { sa += s_a[y][threadIdx.x * GROUP + p]; stt += s_t[y][threadIdx.x * GROUP + p]; }
+            const double ga = (double)__ldg(gamma + f), be = (double)__ldg(beta + f);
+            const double sum_g = sa;
+            const double sum_gx = ga != 0.0 ? (stt - be * sa) / ga : 0.0;
+            const double rows = (double)R * GROUP;
+            m1[f] = (float)(sum_g / rows);
+            m2[f] = (float)(sum_gx / rows);
+            if (d_beta) d_beta[f] = (float)sum_g;
+            if (d_gamma) d_gamma[f] = (float)sum_gx;
+        }
+    }
+}
+
 // out[c] = sum_p partial[p][c]   (bias gradients, projection / conv1 weight gradients)
 // remap: 0 identity; 1 conv1 weight: partial col = tap*64 + c -> out[c*9 + 3 + tap]
 __global__ void __launch_bounds__(1024)

@@ -90,6 +90,8 @@ struct NtArgs {
     const float* out_scale;         // device scalar multiplied into the result before bias (undoes the
                                     // power-of-two scale of a gradient operand), or null
     int fast;                       // CP_ENGINE_TC_FP16: hi planes only, ONE tensor-core product (11-bit operands)
+    unsigned int* gmax_bits;        // non-null: atomicMax of the bit pattern of max |C| (feeds the fp16 plane scale of the
+                                    // BN backward that consumes C when its reduce pass is skipped)
 };
 
 // warp-transposing reduction: on return v[0] of lane l = sum over the 32 lanes of their v[l]
@@ -249,6 +251,13 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 if (g.relu) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (g.gmax_bits) {
+                    float mx = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fabsf(v[j]));
+                    mx = warp_max(row_ok ? mx : 0.f);
+                    if (lane == 0 && mx > 0.f) atomicMax(g.gmax_bits, __float_as_uint(mx));
                 }
                 if (CONV) {
                     // one [120 rows][32 columns] box per CTA and chunk (the tile's last 8 MMA rows carry no data)
@@ -462,6 +471,13 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                 if (g.relu) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (g.gmax_bits) {
+                    float mx = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fabsf(v[j]));
+                    mx = warp_max(row_ok ? mx : 0.f);
+                    if (lane == 0 && mx > 0.f) atomicMax(g.gmax_bits, __float_as_uint(mx));
                 }
                 store_box_tma(&tm_c, out_boxes + (warp - 2) * OUT_BOX, v, lane, col, tile_m * BM + q * 32);
                 if (g.psum) {
@@ -837,7 +853,7 @@ inline int make_tmap_mn(CUtensorMap* m, const plane_t* base, int64_t rows, int64
 // returns the number of splits written to P ([splits][Mo][No]) through *splits_out
 inline int launch_tn(const plane_t* G_hi, const plane_t* G_lo, int ldg, int Mo, const plane_t* A_hi, const plane_t* A_lo,
                      int lda, int No, int64_t R, float* P, size_t p_capacity_elems, int* splits_out,
-                     cudaStream_t st, int fast = 0) {
+                     cudaStream_t st, int fast = 0, bool alone = false) {
     if (Mo % BM != 0 || No % BN != 0 || ldg % 8 != 0 || lda % 8 != 0 || R <= 0) return CP_ERR_ARG;
     CUtensorMap tg_hi, tg_lo, ta_hi, ta_lo;
     int rc;
@@ -856,6 +872,7 @@ inline int launch_tn(const plane_t* G_hi, const plane_t* G_lo, int ldg, int Mo, 
     // each of its CTAs pins 48 K registers (255 x 192 threads), leaving room for ONE 256-thread BN CTA on that SM.
     // Measured at M = 167,936: 9 splits (144 CTAs) 11.10 ms/step, 6 splits 10.96, 4 splits 11.06, 3 splits 11.35
     int S = (CP_NUM_SMS * 2 / 3) / tiles;
+    if (alone) S = CP_NUM_SMS / tiles;                            // in line on the caller's stream: every SM
     const int64_t max_s = cp_cdiv(R, (int64_t)BK * CHUNK_KB);
     if (S > max_s) S = (int)max_s;
     const int64_t cap = (int64_t)(p_capacity_elems / ((size_t)Mo * No));
@@ -918,7 +935,8 @@ inline int launch_nt_cfg(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, con
 static bool g_use_pair = true;       // CTA-pair (cta_group::2) kernel for the plain (non-conv) K-major GEMMs
 inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K, int lda, const plane_t* B_hi,
                      const plane_t* B_lo, int N, int ldb, const float* bias, float* C, int ldc, float* psum,
-                     float* psq, int relu, cudaStream_t st, const float* out_scale = nullptr, int fast = 0) {
+                     float* psq, int relu, cudaStream_t st, const float* out_scale = nullptr, int fast = 0,
+                     unsigned int* gmax_bits = nullptr) {
     if (K % BK != 0 || N % BN != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldc % 4 != 0) return CP_ERR_ARG;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_out;
     int rc;
@@ -927,7 +945,7 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
     if ((rc = make_tmap_2d(&ta_lo, A_lo, M, K, lda, BM)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi, B_hi, N, K, ldb, BN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, N, K, ldb, BN)) != CP_OK) return rc;
-    NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu, out_scale, fast};
+    NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu, out_scale, fast, gmax_bits};
     if (g_use_pair && M > BM) {
         CUtensorMap tb_hi2, tb_lo2;                                   // B boxes of 64 rows: half a tile per CTA
         if ((rc = make_tmap_2d(&tb_hi2, B_hi, N, K, ldb, BN / 2)) != CP_OK) return rc;
@@ -961,7 +979,7 @@ inline int launch_conv_nt(const plane_t* X_hi, const plane_t* X_lo, int64_t wind
     if ((rc = make_tmap_conv(&ta_lo, X_lo, windows, CONV_WIN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi, B_hi, 64, 192, 192, 64)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, 64, 192, 192, 64)) != CP_OK) return rc;
-    NtArgs g{C, 64, bias, psum, psq, windows * 12, 64, 192, relu, out_scale, fast};
+    NtArgs g{C, 64, bias, psum, psq, windows * 12, 64, 192, relu, out_scale, fast, nullptr};
     return fast ? launch_nt_cfg<64, true, true>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st)
                 : launch_nt_cfg<64, true, false>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st);
 }
