@@ -535,11 +535,11 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
                                 true));
                 const int s_below = 1 + l;             // BN stage of this layer's input
                 if (l == 0)
-                    bn_bwd_stats_from_wgrad_kernel<12><<<K_FC1 / 96, 512, 0, st>>>(
+                    bn_bwd_stats_from_wgrad_kernel<12><<<K_FC1 / WgradStats<12>::COLS, 512, 0, st>>>(
                         p->fc_w[0], gr->fc_w[0], gr->fc_b[0], F_FC, K_FC1, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
                         gr->bn_w[s_below], gr->bn_b[s_below]);
                 else
-                    bn_bwd_stats_from_wgrad_kernel<1><<<F_FC / 64, 512, 0, st>>>(
+                    bn_bwd_stats_from_wgrad_kernel<1><<<F_FC / WgradStats<1>::COLS, 512, 0, st>>>(
                         p->fc_w[l], gr->fc_w[l], gr->fc_b[l], F_FC, F_FC, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
                         gr->bn_w[s_below], gr->bn_b[s_below]);
                 CP_CHECK_LAUNCH();

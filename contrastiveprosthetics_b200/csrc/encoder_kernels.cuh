@@ -604,6 +604,10 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, in
 // a conv-stage channel (flatten column ch*12 + p, models.py:263) into its per-channel BN2d sums.  gamma == 0 makes the
 // second sum unobservable from dW -- and irrelevant to the data gradient, which is multiplied by gamma -- it is reported
 // as 0.  Double accumulation in a fixed order (deterministic).  Outputs like bn_bwd_finalize_kernel.
+#define WS_LANES 16                                   // row lanes per CTA (512 threads = 32 column slots x 16 lanes)
+template <int GROUP> struct WgradStats {
+    static constexpr int COLS = GROUP == 1 ? 16 : 24;                  // columns of W per CTA (24 = 2 channels x 12 positions)
+};
 template <int GROUP>
 __global__ void __launch_bounds__(512)
 bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restrict__ dW, const float* __restrict__ db,
@@ -611,13 +615,14 @@ bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restr
                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ d_gamma,
                                float* __restrict__ d_beta) {
-    constexpr int COLS = GROUP == 1 ? 64 : 96;       // columns per CTA (96 = 8 channels x 12 positions)
-    __shared__ double s_a[4][COLS], s_t[4][COLS];
-    const int cx = threadIdx.x % 128, ky = threadIdx.x / 128;          // 128 column slots (COLS used) x 4 row lanes
+    constexpr int COLS = WgradStats<GROUP>::COLS;
+    __shared__ double s_a[WS_LANES][COLS], s_t[WS_LANES][COLS];
+    const int cx = threadIdx.x % 32, ky = threadIdx.x / 32;
     const int col = blockIdx.x * COLS + cx;
     double a = 0.0, t = 0.0;
     if (cx < COLS && col < cols) {
-        for (int k = ky; k < K_out; k += 4) {
+#pragma unroll 4
+        for (int k = ky; k < K_out; k += WS_LANES) {
             const double w = (double)__ldg(W + (size_t)k * cols + col);
             a += (double)__ldg(db + k) * w;
             t += w * (double)__ldg(dW + (size_t)k * cols + col);
@@ -625,14 +630,16 @@ bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restr
     }
     if (cx < COLS) { s_a[ky][cx] = a; s_t[ky][cx] = t; }
     __syncthreads();
-    // one thread per BN feature of this CTA
-    const int nfeat = COLS / GROUP;
-    if (threadIdx.x < nfeat) {
-        const int f = blockIdx.x * nfeat + threadIdx.x;
+    constexpr int NFEAT = COLS / GROUP;                   // BN features of this CTA: one thread each
+    if (threadIdx.x < NFEAT) {
+        const int f = blockIdx.x * NFEAT + threadIdx.x;
         if (f * GROUP < cols) {
             double sa = 0.0, stt = 0.0;
             for (int p = 0; p < GROUP; ++p)
-                for (int y = 0; y < 4; ++y) { sa += s_a[y][threadIdx.x * GROUP + p]; stt += s_t[y][threadIdx.x * GROUP + p]; }
+                for (int y = 0; y < WS_LANES; ++y) {
+                    sa += s_a[y][threadIdx.x * GROUP + p];
+                    stt += s_t[y][threadIdx.x * GROUP + p];
+                }
             const double ga = (double)__ldg(gamma + f), be = (double)__ldg(beta + f);
             const double sum_g = sa;
             const double sum_gx = ga != 0.0 ? (stt - be * sa) / ga : 0.0;
