@@ -524,17 +524,29 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             // rank-local: its BN-backward sums follow from this layer's dW / db (bn_bwd_stats_from_wgrad_kernel), so
             // the weight gradient runs in line (its overlap with the BN backward bought nothing) and the
             // reduce pass over (dA, Y) of that stage is skipped
+            // With dropout between the stage and this layer the column sums of g' = dA * keep/(1-p) come from the
+            // data-gradient GEMM's epilogue (masked column sums), the second sum still from dW.
             const bool below_has_dropout = l - 1 >= 3 && o->dropout_p > 0.f;
-            const bool algebraic = !below_has_dropout && o->allreduce == nullptr;
+            const bool algebraic = o->allreduce == nullptr;
+            const uint8_t* keep_below = below_has_dropout ? w.keep[l - 1 - 3] : nullptr;
+            const bool masked = algebraic && keep_below != nullptr;
             // main stream: G0 = G1 . W_l
             CP_TRY(tcg::launch_nt(hi_of(g1(b)), g1lo(b, fc_elems), n, F_FC, F_FC, w.Wth[l], w.Wtl[l], K, F_FC, nullptr, w.G0,
-                                  K, nullptr, nullptr, 0, st, gsi, fast, algebraic ? w.gmax + 1 + l : nullptr));
+                                  K, masked ? w.pa : nullptr, masked ? w.pb : nullptr, 0, st, gsi, fast,
+                                  algebraic ? w.gmax + 1 + l : nullptr, masked ? keep_below : nullptr, inv_keep));
             if (algebraic) {
                 if (last_side) CP_CUDA(cudaStreamWaitEvent(st, last_side, 0));     // w.wpart is shared with the side stream
                 CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, st, gsi, fast,
                                 true));
                 const int s_below = 1 + l;             // BN stage of this layer's input
-                if (l == 0)
+                if (masked) {
+                    // sum over the GEMM's per-tile partial rows -> w.m1 (scratch until the statistics kernel overwrites it)
+                    colsum_finalize_kernel<<<F_FC / 32, 1024, 0, st>>>(w.pa, (int)cp_cdiv(n, 128), F_FC, w.m1, 0);
+                    CP_CHECK_LAUNCH();
+                    bn_bwd_stats_from_wgrad_kernel<1><<<F_FC / WgradStats<1>::COLS, 512, 0, st>>>(
+                        p->fc_w[l], gr->fc_w[l], gr->fc_b[l], F_FC, F_FC, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
+                        gr->bn_w[s_below], gr->bn_b[s_below], w.m1);
+                } else if (l == 0)
                     bn_bwd_stats_from_wgrad_kernel<12><<<K_FC1 / WgradStats<12>::COLS, 512, 0, st>>>(
                         p->fc_w[0], gr->fc_w[0], gr->fc_b[0], F_FC, K_FC1, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
                         gr->bn_w[s_below], gr->bn_b[s_below]);

@@ -604,6 +604,7 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, in
 // a conv-stage channel (flatten column ch*12 + p, models.py:263) into its per-channel BN2d sums.  gamma == 0 makes the
 // second sum unobservable from dW -- and irrelevant to the data gradient, which is multiplied by gamma -- it is reported
 // as 0.  Double accumulation in a fixed order (deterministic).  Outputs like bn_bwd_finalize_kernel.
+// With dropout between the stage and the layer only the first identity is lost (see sum_g_in below).
 #define WS_LANES 16                                   // row lanes per CTA (512 threads = 32 column slots x 16 lanes)
 template <int GROUP> struct WgradStats {
     static constexpr int COLS = GROUP == 1 ? 16 : 24;                  // columns of W per CTA (24 = 2 channels x 12 positions)
@@ -613,8 +614,8 @@ __global__ void __launch_bounds__(512)
 bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restrict__ dW, const float* __restrict__ db,
                                int K_out /*rows of W*/, int cols /*columns of W = F * GROUP*/, int64_t R /*rows per column*/,
                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                               float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ d_gamma,
-                               float* __restrict__ d_beta) {
+                               float* m1, float* __restrict__ m2, float* __restrict__ d_gamma,
+                               float* __restrict__ d_beta, const float* sum_g_in = nullptr) {
     constexpr int COLS = WgradStats<GROUP>::COLS;
     __shared__ double s_a[WS_LANES][COLS], s_t[WS_LANES][COLS];
     const int cx = threadIdx.x % 32, ky = threadIdx.x / 32;
@@ -641,8 +642,11 @@ bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restr
                     stt += s_t[y][threadIdx.x * GROUP + p];
                 }
             const double ga = (double)__ldg(gamma + f), be = (double)__ldg(beta + f);
-            const double sum_g = sa;
-            const double sum_gx = ga != 0.0 ? (stt - be * sa) / ga : 0.0;
+            // below a dropout mask (sum_g_in, GROUP == 1; may alias m1): g' = g * keep/(1-p) is no longer linear in G1,
+            // its column sums come from the data-gradient GEMM's epilogue; with A = (gamma xh + beta) keep/(1-p) the
+            // second identity still holds:  sum g' xh = (sum_k W dW - beta sum g') / gamma
+            const double sum_g = sum_g_in ? (double)sum_g_in[f] : sa;
+            const double sum_gx = ga != 0.0 ? (stt - be * sum_g) / ga : 0.0;
             const double rows = (double)R * GROUP;
             m1[f] = (float)(sum_g / rows);
             m2[f] = (float)(sum_gx / rows);

@@ -92,6 +92,9 @@ struct NtArgs {
     int fast;                       // CP_ENGINE_TC_FP16: hi planes only, ONE tensor-core product (11-bit operands)
     unsigned int* gmax_bits;        // non-null: atomicMax of the bit pattern of max |C| (feeds the fp16 plane scale of the
                                     // BN backward that consumes C when its reduce pass is skipped)
+    const uint8_t* keep;            // non-null (with psum): C is the gradient w.r.t. a dropout output; psum then holds the
+    float inv_keep;                 // column sums of C * keep / (1-p) (mask [M][N] bytes), psq is not written, and
+                                    // gmax_bits takes the masked maximum
 };
 
 // warp-transposing reduction: on return v[0] of lane l = sum over the 32 lanes of their v[l]
@@ -106,6 +109,29 @@ __device__ __forceinline__ void warp_col_reduce32(float (&v)[32], int lane) {
             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
         }
     }
+}
+
+// v (this thread's 32 consecutive columns of row `row`) *= keep / (1-p); masked max -> gmax_bits; on return v[0] of
+// lane l = the warp's column sum of column col + l.  The 32 mask bytes of a thread are one full 32-byte sector.
+__device__ __forceinline__ void masked_col_sums(float (&v)[32], const NtArgs& g, int64_t row, int col, bool row_ok, int lane) {
+    uint4 m[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if (row_ok) {
+        const uint4* mp = reinterpret_cast<const uint4*>(g.keep + row * (int64_t)g.N + col);
+        m[0] = __ldg(mp);
+        m[1] = __ldg(mp + 1);
+    }
+    const uint8_t* mb = reinterpret_cast<const uint8_t*>(m);
+    float mx = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        v[j] = mb[j] ? v[j] * g.inv_keep : 0.f;        // rows beyond M: mask bytes 0
+        mx = fmaxf(mx, fabsf(v[j]));
+    }
+    if (g.gmax_bits) {
+        mx = warp_max(mx);
+        if (lane == 0 && mx > 0.f) atomicMax(g.gmax_bits, __float_as_uint(mx));
+    }
+    warp_col_reduce32(v, lane);
 }
 
 // CONV: the A operand is the conv-view of a [windows][12][64] activation (k = 3 convolution as an
@@ -252,7 +278,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
-                if (g.gmax_bits) {
+                if (g.gmax_bits && !g.keep) {
                     float mx = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fabsf(v[j]));
@@ -276,7 +302,11 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 } else {
                     store_box_tma(&tm_c, out_boxes + q * OUT_BOX, v, lane, col, tile_m * ROWS + q * 32);
                 }
-                if (g.psum) {
+                if (g.psum && g.keep) {
+                    masked_col_sums(v, g, row, col, row_ok, lane);
+                    sm->csum[q][c * 32 + lane] = v[0];
+                    sm->csq[q][c * 32 + lane] = 0.f;
+                } else if (g.psum) {
                     float sq[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -472,7 +502,7 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
-                if (g.gmax_bits) {
+                if (g.gmax_bits && !g.keep) {
                     float mx = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fabsf(v[j]));
@@ -480,7 +510,11 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                     if (lane == 0 && mx > 0.f) atomicMax(g.gmax_bits, __float_as_uint(mx));
                 }
                 store_box_tma(&tm_c, out_boxes + (warp - 2) * OUT_BOX, v, lane, col, tile_m * BM + q * 32);
-                if (g.psum) {
+                if (g.psum && g.keep) {
+                    masked_col_sums(v, g, row, col, row_ok, lane);
+                    sm->csum[q][cl + lane] = v[0];
+                    sm->csq[q][cl + lane] = 0.f;
+                } else if (g.psum) {
                     float sq[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -936,8 +970,9 @@ static bool g_use_pair = true;       // CTA-pair (cta_group::2) kernel for the p
 inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K, int lda, const plane_t* B_hi,
                      const plane_t* B_lo, int N, int ldb, const float* bias, float* C, int ldc, float* psum,
                      float* psq, int relu, cudaStream_t st, const float* out_scale = nullptr, int fast = 0,
-                     unsigned int* gmax_bits = nullptr) {
+                     unsigned int* gmax_bits = nullptr, const uint8_t* keep = nullptr, float inv_keep = 1.f) {
     if (K % BK != 0 || N % BN != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldc % 4 != 0) return CP_ERR_ARG;
+    if (keep && (ldc != N || ((uintptr_t)keep) % 16 != 0)) return CP_ERR_ARG;     // mask laid out like a dense [M][N] C
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_out;
     int rc;
     if ((rc = make_tmap_out(&tc_out, C, M, N, ldc)) != CP_OK) return rc;
@@ -945,7 +980,7 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
     if ((rc = make_tmap_2d(&ta_lo, A_lo, M, K, lda, BM)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi, B_hi, N, K, ldb, BN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, N, K, ldb, BN)) != CP_OK) return rc;
-    NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu, out_scale, fast, gmax_bits};
+    NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu, out_scale, fast, gmax_bits, keep, inv_keep};
     if (g_use_pair && M > BM) {
         CUtensorMap tb_hi2, tb_lo2;                                   // B boxes of 64 rows: half a tile per CTA
         if ((rc = make_tmap_2d(&tb_hi2, B_hi, N, K, ldb, BN / 2)) != CP_OK) return rc;
@@ -979,7 +1014,7 @@ inline int launch_conv_nt(const plane_t* X_hi, const plane_t* X_lo, int64_t wind
     if ((rc = make_tmap_conv(&ta_lo, X_lo, windows, CONV_WIN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi, B_hi, 64, 192, 192, 64)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, 64, 192, 192, 64)) != CP_OK) return rc;
-    NtArgs g{C, 64, bias, psum, psq, windows * 12, 64, 192, relu, out_scale, fast, nullptr};
+    NtArgs g{C, 64, bias, psum, psq, windows * 12, 64, 192, relu, out_scale, fast, nullptr, nullptr, 1.f};
     return fast ? launch_nt_cfg<64, true, true>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st)
                 : launch_nt_cfg<64, true, false>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st);
 }
