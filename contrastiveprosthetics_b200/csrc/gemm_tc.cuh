@@ -113,14 +113,19 @@ __device__ __forceinline__ void warp_col_reduce32(float (&v)[32], int lane) {
 
 // v (this thread's 32 consecutive columns of row `row`) *= keep / (1-p); masked max -> gmax_bits; on return v[0] of
 // lane l = the warp's column sum of column col + l.  The 32 mask bytes of a thread are one full 32-byte sector.
-__device__ __forceinline__ void masked_col_sums(float (&v)[32], const NtArgs& g, int64_t row, int col, bool row_ok, int lane) {
-    uint4 m[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+struct Mask32 { uint4 m[2]; };
+__device__ __forceinline__ Mask32 load_mask32(const NtArgs& g, int64_t row, int col, bool row_ok) {
+    Mask32 k;
+    k.m[0] = k.m[1] = make_uint4(0, 0, 0, 0);
     if (row_ok) {
         const uint4* mp = reinterpret_cast<const uint4*>(g.keep + row * (int64_t)g.N + col);
-        m[0] = __ldg(mp);
-        m[1] = __ldg(mp + 1);
+        k.m[0] = __ldg(mp);
+        k.m[1] = __ldg(mp + 1);
     }
-    const uint8_t* mb = reinterpret_cast<const uint8_t*>(m);
+    return k;
+}
+__device__ __forceinline__ void masked_col_sums(float (&v)[32], const NtArgs& g, const Mask32& k, int lane) {
+    const uint8_t* mb = reinterpret_cast<const uint8_t*>(k.m);
     float mx = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -303,7 +308,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                     store_box_tma(&tm_c, out_boxes + q * OUT_BOX, v, lane, col, tile_m * ROWS + q * 32);
                 }
                 if (g.psum && g.keep) {
-                    masked_col_sums(v, g, row, col, row_ok, lane);
+                    masked_col_sums(v, g, load_mask32(g, row, col, row_ok), lane);
                     sm->csum[q][c * 32 + lane] = v[0];
                     sm->csq[q][c * 32 + lane] = 0.f;
                 } else if (g.psum) {
@@ -473,9 +478,15 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             const int n0 = (int)(t % tiles_n) * BN;
             const int64_t row = tile_m * BM + q * 32 + lane;
             const bool row_ok = row < g.M;
+            // dropout mask of this thread's two chunks, fetched while the tile's MMAs are still running
+            Mask32 mk[2];
+            if (g.keep) {
+                mk[0] = load_mask32(g, row, n0 + half * 64, row_ok);
+                mk[1] = load_mask32(g, row, n0 + half * 64 + 32, row_ok);
+            }
             tc::mbar_wait(&sm->tmem_full[acc], (it >> 1) & 1);
             tc::tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const int cl = half * 64 + c * 32;                      // column inside the tile
                 float v[32], vc[32];
@@ -511,7 +522,7 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                 }
                 store_box_tma(&tm_c, out_boxes + (warp - 2) * OUT_BOX, v, lane, col, tile_m * BM + q * 32);
                 if (g.psum && g.keep) {
-                    masked_col_sums(v, g, row, col, row_ok, lane);
+                    masked_col_sums(v, g, mk[c], lane);
                     sm->csum[q][cl + lane] = v[0];
                     sm->csq[q][cl + lane] = 0.f;
                 } else if (g.psum) {
