@@ -53,7 +53,8 @@ struct Ws {
     float *Wc2_lo, *Wc2d_lo;
     float *G1b;               // second pre-activation-gradient buffer (weight-gradient GEMMs run on a side stream)
     plane_t *Wh[CP_N_FC], *Wl[CP_N_FC], *Wth[CP_N_FC], *Wtl[CP_N_FC];
-    unsigned int* gmax;        // [16] max |g'| per backward stage (bit pattern), zeroed per backward call
+    unsigned int* gmax;        // [16] max |g'| per backward stage (bit pattern) + [16] gamma == 0 flags per stage,
+                               // zeroed per backward call
     float* gscale_inv;         // [16] 1 / (power-of-two scale of the stage's G1 planes)
     size_t bytes;
 };
@@ -126,7 +127,7 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
                    : nullptr;
     w.Wc2_lo = w.Wc2d_lo = w.G1b = nullptr;
     for (int l = 0; l < CP_N_FC; ++l) w.Wh[l] = w.Wl[l] = w.Wth[l] = w.Wtl[l] = nullptr;
-    w.gmax = c.take<unsigned int>(16);
+    w.gmax = c.take<unsigned int>(32);
     w.gscale_inv = c.take<float>(16);
     if (o->engine != CP_ENGINE_SIMT) {
         w.Wc2_lo = c.take<float>(64 * 192);
@@ -241,13 +242,16 @@ int bn_backward(const float* g, const float* y, float* gz, bool planes, int64_t 
                 float* d_bias, cudaStream_t st, const cp_encoder_opts* o, bool stats_ready = false) {
     const int P = (int)cp_cdiv(R, ColMap<F>::ROWS);
     float* gz_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)R * F) : nullptr;
-    if (!stats_ready) {
+    // stats_ready: the two kernels below still launch, but return at once unless a gamma == 0 was met (flag w.gmax[16 + l])
+    const unsigned int* run_flag = stats_ready ? w.gmax + 16 + l : nullptr;
+    {
         bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb, nullptr,
-                                                   planes ? w.gmax + l : nullptr);
+                                                   planes ? w.gmax + l : nullptr, run_flag);
         CP_CHECK_LAUNCH();
         const bool sync = o->allreduce != nullptr;
         bn_bwd_finalize_kernel<<<dim3(F / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta,
-                                                                        w.rscratch, w.tickets, sync ? w.totals : nullptr);
+                                                                        w.rscratch, w.tickets, sync ? w.totals : nullptr,
+                                                                        run_flag);
         CP_CHECK_LAUNCH();
         if (sync) {
             if (int rc = sync_totals(w, F, o, st)) return rc;
@@ -491,7 +495,7 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     const int64_t R12 = n * 12;
     const size_t conv_elems = (size_t)n * 12 * F_CONV, fc_elems = (size_t)n * F_FC;
     const float inv_keep = o->dropout_p > 0.f ? 1.f / (1.f - o->dropout_p) : 1.f;
-    CP_CUDA(cudaMemsetAsync(w.gmax, 0, 16 * sizeof(unsigned int), st));
+    CP_CUDA(cudaMemsetAsync(w.gmax, 0, 32 * sizeof(unsigned int), st));
 
     const int Pp = pf::grid_for(n);          // projection weight-gradient partial rows (last_block_backward)
 
@@ -545,15 +549,15 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
                     CP_CHECK_LAUNCH();
                     bn_bwd_stats_from_wgrad_kernel<1><<<F_FC / WgradStats<1>::COLS, 512, 0, st>>>(
                         p->fc_w[l], gr->fc_w[l], gr->fc_b[l], F_FC, F_FC, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
-                        gr->bn_w[s_below], gr->bn_b[s_below], w.m1);
+                        gr->bn_w[s_below], gr->bn_b[s_below], w.m1, w.gmax + 16 + s_below);
                 } else if (l == 0)
                     bn_bwd_stats_from_wgrad_kernel<12><<<K_FC1 / WgradStats<12>::COLS, 512, 0, st>>>(
                         p->fc_w[0], gr->fc_w[0], gr->fc_b[0], F_FC, K_FC1, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
-                        gr->bn_w[s_below], gr->bn_b[s_below]);
+                        gr->bn_w[s_below], gr->bn_b[s_below], nullptr, w.gmax + 16 + s_below);
                 else
                     bn_bwd_stats_from_wgrad_kernel<1><<<F_FC / WgradStats<1>::COLS, 512, 0, st>>>(
                         p->fc_w[l], gr->fc_w[l], gr->fc_b[l], F_FC, F_FC, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
-                        gr->bn_w[s_below], gr->bn_b[s_below]);
+                        gr->bn_w[s_below], gr->bn_b[s_below], nullptr, w.gmax + 16 + s_below);
                 CP_CHECK_LAUNCH();
                 stats_ready = true;
                 continue;

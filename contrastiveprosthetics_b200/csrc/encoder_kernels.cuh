@@ -453,8 +453,11 @@ __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t R,
                      const uint8_t* __restrict__ keep, float inv_keep, const float* __restrict__ mean,
                      const float* __restrict__ istd, float* __restrict__ p1, float* __restrict__ p2,
-                     const float* __restrict__ post = nullptr, unsigned int* __restrict__ gmax_bits = nullptr) {
+                     const float* __restrict__ post = nullptr, unsigned int* __restrict__ gmax_bits = nullptr,
+                     const unsigned int* __restrict__ run_flag = nullptr) {
     __shared__ float red[ColMap<F>::RY * F];
+    // fallback pass of the reduce-free BN backward: runs only when bn_bwd_stats_from_wgrad_kernel met a gamma == 0
+    if (run_flag && __ldg(run_flag) == 0u) return;
     float gmax = 0.f;                     // max |g'| (feeds the fp16 plane scale of bn_bwd_apply_kernel<.., true>)
     const int qx = threadIdx.x % ColMap<F>::QX, ry = threadIdx.x / ColMap<F>::QX;
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + qx * 4));
@@ -502,8 +505,9 @@ __global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int P, int F, int64_t R,
                        float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ d_gamma,
                        float* __restrict__ d_beta, double* __restrict__ scratch, unsigned int* __restrict__ tickets,
-                       double* __restrict__ totals = nullptr) {
+                       double* __restrict__ totals = nullptr, const unsigned int* __restrict__ run_flag = nullptr) {
     __shared__ double sm[32 * 33];
+    if (run_flag && __ldg(run_flag) == 0u) return;          // see bn_bwd_reduce_kernel
     const int col = blockIdx.x * 32 + threadIdx.x % 32;
     const float* const parts[2] = {p1, p2};
     double tot[2];
@@ -602,8 +606,9 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, in
 //     sum_r g[r,c] xh[r,c]  = sum_k W[k,c] (G1^T xh)[k,c] = (sum_k W[k,c] dW[k,c] - beta[c] sum_k db[k] W[k,c]) / gamma[c]
 // -- a [512 x F] reduction instead of two reads of [R x F] (bn_bwd_reduce_kernel).  GROUP = 12 folds the 12 positions of
 // a conv-stage channel (flatten column ch*12 + p, models.py:263) into its per-channel BN2d sums.  gamma == 0 makes the
-// second sum unobservable from dW -- and irrelevant to the data gradient, which is multiplied by gamma -- it is reported
-// as 0.  Double accumulation in a fixed order (deterministic).  Outputs like bn_bwd_finalize_kernel.
+// second sum unobservable from dW: the kernel then raises *zero_gamma_flag and the caller's conditional reduce pass
+// (bn_bwd_reduce_kernel / bn_bwd_finalize_kernel with run_flag) recomputes the stage's sums the long way.
+// Double accumulation in a fixed order (deterministic).  Outputs like bn_bwd_finalize_kernel.
 // With dropout between the stage and the layer only the first identity is lost (see sum_g_in below).
 #define WS_LANES 16                                   // row lanes per CTA (512 threads = 32 column slots x 16 lanes)
 template <int GROUP> struct WgradStats {
@@ -615,7 +620,8 @@ bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restr
                                int K_out /*rows of W*/, int cols /*columns of W = F * GROUP*/, int64_t R /*rows per column*/,
                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                float* m1, float* __restrict__ m2, float* __restrict__ d_gamma,
-                               float* __restrict__ d_beta, const float* sum_g_in = nullptr) {
+                               float* __restrict__ d_beta, const float* sum_g_in = nullptr,
+                               unsigned int* __restrict__ zero_gamma_flag = nullptr) {
     constexpr int COLS = WgradStats<GROUP>::COLS;
     __shared__ double s_a[WS_LANES][COLS], s_t[WS_LANES][COLS];
     const int cx = threadIdx.x % 32, ky = threadIdx.x / 32;
@@ -647,6 +653,8 @@ bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restr
             // second identity still holds:  sum g' xh = (sum_k W dW - beta sum g') / gamma
             const double sum_g = sum_g_in ? (double)sum_g_in[f] : sa;
             const double sum_gx = ga != 0.0 ? (stt - be * sum_g) / ga : 0.0;
+            // gamma == 0: d_gamma is not observable from dW -> the caller's (otherwise skipped) reduce pass runs
+            if (ga == 0.0 && zero_gamma_flag) atomicOr(zero_gamma_flag, 1u);
             const double rows = (double)R * GROUP;
             m1[f] = (float)(sum_g / rows);
             m2[f] = (float)(sum_gx / rows);

@@ -276,6 +276,35 @@ def test_dropout_with_injected_masks(engine):
     assert worst[0] < GRAD_TOL, worst
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("dp", [0.0, 0.5])
+def test_zero_gamma_channels(dp, engine):
+    """BatchNorm weights that are EXACTLY zero in some channels of every stage: the reduce-free BN backward cannot
+    recover d_gamma of such a channel from the next layer's weight gradient (the activation no longer depends on
+    x-hat) and must fall back to the reduce pass -- d_gamma there is non-zero in the reference."""
+    adabn, n = True, 41 * 6
+    sd = perturbed_state(23, adabn)
+    zeroed = []
+    for k in sd:
+        if ".bn." in k and k.endswith(".weight"):
+            sd[k] = sd[k].clone()
+            sd[k][::5] = 0.0
+            zeroed.append(k)
+    assert len(zeroed) == 9
+    g = torch.Generator().manual_seed(31)
+    x, d_emb = torch.randn(n, 12, generator=g), torch.randn(n, 16, generator=g)
+    masks = [torch.empty(n, 512).bernoulli_(0.5, generator=g) for _ in range(4)] if dp > 0 else None
+    taps = {}
+    emb, got = _grads_cuda(sd, adabn, x, d_emb, dp, masks, taps=taps, engine=engine)
+    ref_emb, ref = _grads_oracle(sd, adabn, x, d_emb, torch.float32, dp, masks, relu_masks=_relu_pattern(taps))
+    assert rel_err(emb, ref_emb) < FWD_TOL
+    worst = max((rel_err(got[k], ref[k]), k) for k in ref)
+    assert worst[0] < GRAD_TOL, worst
+    for k in zeroed:                                  # the gradient of a zeroed gamma is itself far from zero
+        assert float(ref[k][::5].abs().max()) > 0
+        assert rel_err(got[k][::5], ref[k][::5]) < 10 * GRAD_TOL, k
+
+
 def test_inkernel_dropout_statistics():
     """Philox keep masks: keep rate ~ 1-p, different per layer / per step, eval is deterministic."""
     sd = perturbed_state(19, True)
