@@ -370,6 +370,8 @@ def run_cuda(args):
                           "(M = 167,936); 7 fwd + 7 dgrad + 7 wgrad launches of this family per step",
                 "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops"],
+                # the fp32-parity split issues 3 tensor-core products per algorithmic product: its own ceiling
+                "frac_of_parity_ceiling": (ach / (peaks["bf16_tflops"] / 3.0)) if (use_tc and not one_product) else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this shape, from the
                 # ncu --set full capture profiles/r1_ncu_gemm_nt_pair_f16_summary.txt (algorithmic: 344 MB of fp16
                 # operand planes in + 344 MB of fp32 out = 688 MB; the weights stay in L2)
