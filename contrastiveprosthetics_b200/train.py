@@ -69,8 +69,9 @@ def train_loop(dataset, params, checkpoint=False, checkpoint_dir="../checkpoints
         print("Loading model")
         model.load_state_dict(torch.load(load + ".pt"))
 
-    optimizer_emg = optim.Adam(model.emg_net.parameters(), lr=params['lr_emg'], weight_decay=0)
-    optimizer_glove = optim.Adam(model.glove_net.parameters(), lr=params['lr_glove'], weight_decay=0)
+    fused = True if getattr(args, "fused_adam", False) else None     # None: torch's default implementation
+    optimizer_emg = optim.Adam(model.emg_net.parameters(), lr=params['lr_emg'], weight_decay=0, fused=fused)
+    optimizer_glove = optim.Adam(model.glove_net.parameters(), lr=params['lr_glove'], weight_decay=0, fused=fused)
     if annealing:
         scheduler_emg = optim.lr_scheduler.CosineAnnealingLR(optimizer_emg, T_max=args.final_epochs, eta_min=0)
         scheduler_glove = optim.lr_scheduler.CosineAnnealingLR(optimizer_glove, T_max=args.final_epochs, eta_min=0)
@@ -258,6 +259,8 @@ def build_parser():
     parser.add_argument('--sync_bn', action='store_true',
                         help='under torchrun: BatchNorm statistics over the rows of every rank (global-batch parity) '
                              'instead of rank-local ones')
+    parser.add_argument('--fused_adam', action='store_true',
+                        help="torch.optim.Adam(fused=True): same update rule in one kernel per optimizer (what bench.py uses)")
     parser.add_argument('--concurrent_folds', type=int, default=1,
                         help='cross-validation: train this many hyper-parameter folds at a time on one GPU, each as a '
                              'CUDA graph on its own stream (folds.ConcurrentFolds); 1 = one after the other')
