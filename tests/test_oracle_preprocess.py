@@ -48,3 +48,16 @@ def test_running_stats(gp):
     assert gp["stats_mean_complete"].shape == () and gp["stats_std_complete"].shape == (12,)
     np.testing.assert_allclose(mean.mean(), gp["stats_mean_complete"], rtol=1e-5)
     np.testing.assert_allclose((gp["emg_wrap"] - mean) / std, gp["normalized_perch"], rtol=1e-4, atol=1e-5)
+
+
+def test_host_module_agrees_with_the_oracle_on_the_cpu_side():
+    """contrastiveprosthetics_b200/preprocess.py's host-side pieces (filter design, index list, constants) -- no GPU."""
+    from contrastiveprosthetics_b200 import preprocess as PP
+    b0, a0 = OP.butter_bandpass()
+    b1, a1 = PP.butter_bandpass()
+    assert np.array_equal(b0, b1) and np.array_equal(a0, a1) and len(b1) == 9 and a1[0] == 1.0
+    assert np.array_equal(PP.time_mask(True), OP.time_mask(True)) and np.array_equal(PP.time_mask(False), OP.time_mask(False))
+    assert PP.SEG_LEN == OP.SEG_LEN == 2010 and PP.GAIN == OP.GAIN == 1024.0
+    import torch
+    with pytest.raises(RuntimeError):                       # no CPU fallback: host tensors are refused
+        PP.preprocess_segments(torch.zeros(1, PP.SEG_LEN, 12))
