@@ -48,3 +48,30 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11): counter-based generator, 128 random
+// bits per call.  Hand-rolled (about 70 integer instructions) because the dropout layers' BN-apply kernels are bound by
+// the generator, not by HBM; keep-decisions compare the raw 32-bit words with an integer threshold (no float conversion).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+// keep mask of 4 consecutive elements: element index v*4.., dropout layer `layer`, P(drop) = thr / 2^32
+__device__ __forceinline__ uchar4 dropout_keep4(uint64_t seed, uint64_t v, unsigned int layer, unsigned int thr) {
+    const uint4 r = philox4x32_10(make_uint4((unsigned int)v, (unsigned int)(v >> 32), layer, 0x43505253u),
+                                  make_uint2((unsigned int)seed, (unsigned int)(seed >> 32)));
+    uchar4 m;
+    m.x = r.x >= thr; m.y = r.y >= thr; m.z = r.z >= thr; m.w = r.w >= thr;
+    return m;
+}
+// threshold for drop probability p in [0, 1)
+__device__ __forceinline__ unsigned int dropout_threshold(float p) {
+    return (unsigned int)fminf(p * 4294967296.0f, 4294967040.0f);
+}

@@ -8,7 +8,6 @@
 // contiguous) or F = 512 (linear stages, rows = windows).
 #pragma once
 #include "common.cuh"
-#include <curand_kernel.h>
 
 template <int F> struct ColMap {
     static constexpr int QX = F / 4;            // float4 column groups
@@ -403,8 +402,8 @@ bn_bwd_means_totals_kernel(const double* __restrict__ totals, int F, float* __re
 // ---------------------------------------------------------------------------------- BN apply
 // a = y*scale + shift, then (linear blocks 4..7) dropout: a * keep / (1-p)   (models.py:282-297)
 // SPLIT: write the result as the two fp16 planes (hi -> a, lo -> a_lo; see gemm_tc.cuh) the tensor-core GEMMs consume.
-// Dropout: `keep` holds a caller-provided mask, or (gen_p > 0) the mask is drawn here -- Philox4x32-10
-// keyed by (seed [+ *seed_offset * odd constant], layer), counter = element/4 -- and stored to `keep` for the
+// Dropout: `keep` holds a caller-provided mask, or (gen_p > 0) the mask is drawn here -- Philox4x32-10 (common.cuh)
+// keyed by seed [+ *seed_offset * odd constant], counter = (element/4, layer) -- and stored to `keep` for the
 // backward pass.
 template <int F, bool SPLIT>
 __global__ void __launch_bounds__(256)
@@ -425,10 +424,7 @@ bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, float* __res
         if (keep) {
             uchar4 m;
             if (gen_p > 0.f) {
-                curandStatePhilox4_32_10_t st;
-                curand_init(seed, /*subsequence=*/(unsigned long long)v, /*offset=*/layer * 4ull, &st);
-                const float4 u = curand_uniform4(&st);          // (0,1]
-                m.x = u.x > gen_p; m.y = u.y > gen_p; m.z = u.z > gen_p; m.w = u.w > gen_p;
+                m = dropout_keep4(seed, (uint64_t)v, (unsigned int)layer, dropout_threshold(gen_p));
                 reinterpret_cast<uchar4*>(keep)[v] = m;
             } else {
                 m = *(reinterpret_cast<const uchar4*>(keep) + v);

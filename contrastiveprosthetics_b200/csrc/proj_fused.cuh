@@ -17,7 +17,6 @@
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
-#include <curand_kernel.h>
 
 namespace pf {
 
@@ -82,7 +81,7 @@ __device__ __forceinline__ float4 keep_scale(const float4& v, const uchar4& m, f
 
 // ------------------------------------------------------------------------------------------ forward
 // MODE 0: no dropout; 1: caller-provided mask in `keep`; 2: mask drawn here (same Philox stream as
-// bn_apply_kernel: key (seed [+ step * odd constant], layer), counter = element / 4) and stored to `keep`.
+// bn_apply_kernel: key seed [+ step * odd constant], counter (element / 4, layer)) and stored to `keep`.
 constexpr int FWD_THREADS = 512;                         // 4 row lanes: the Philox chain needs warps, not registers
 template <int MODE>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
@@ -100,6 +99,7 @@ bn_apply_proj_kernel(const float* __restrict__ y, int64_t n, const float* __rest
     const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + qx);
     const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + qx);
     if (MODE == 2 && seed_offset) seed += __ldg(seed_offset) * 0x9E3779B97F4A7C15ull;
+    const unsigned int thr = dropout_threshold(gen_p);
 
     stream_rows<MODE == 1, false>(y, keep, nullptr, n, smem, [&](int64_t row0, int rows, const float4* ys,
                                                                  const uchar4* ks, const float4*) {
@@ -109,11 +109,7 @@ bn_apply_proj_kernel(const float* __restrict__ y, int64_t n, const float* __rest
             if (MODE == 1) a = keep_scale(a, ks[r * QX + qx], inv_keep);
             if (MODE == 2) {
                 const int64_t v = (row0 + r) * QX + qx;
-                curandStatePhilox4_32_10_t st;
-                curand_init(seed, /*subsequence=*/(unsigned long long)v, /*offset=*/layer * 4ull, &st);
-                const float4 u = curand_uniform4(&st);          // (0,1]
-                uchar4 m;
-                m.x = u.x > gen_p; m.y = u.y > gen_p; m.z = u.z > gen_p; m.w = u.w > gen_p;
+                const uchar4 m = dropout_keep4(seed, (uint64_t)v, (unsigned int)layer, thr);
                 reinterpret_cast<uchar4*>(keep)[v] = m;
                 a = keep_scale(a, m, inv_keep);
             }
