@@ -65,7 +65,8 @@ def init_distributed():
 
 
 class ClockSampler:
-    """Samples SM clock + throttle reasons during the timed region (NVML, 100 ms period)."""
+    """Samples SM clock + throttle reasons during the timed region (NVML, 20 ms period: the default
+    timed region is ~0.1 s)."""
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -95,7 +96,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         if self.nv is not None:
