@@ -22,8 +22,10 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from . import dist as cpdist
 
 D_E = 16
+MAX_SCALE = 43.0          # largest exp(logit_scale) for which no row / column sum can underflow (see clip_head)
 
 
 class _CudaOps:
@@ -83,9 +85,6 @@ class _CudaOps:
         return dx
 
 
-_ops = _CudaOps        # host-logic tests (gloo, CPU) substitute a test double; the product has only this one
-
-
 def _world(group):
     if group == "local":                       # force the single-process path inside a distributed job
         return 1, 0
@@ -94,21 +93,10 @@ def _world(group):
     return 1, 0
 
 
-def _reduce_scatter_rows(full, n, rank, group):
-    """(world*n, 16) partials -> this rank's (n,16) sum."""
-    out = torch.empty((n, full.shape[1]), dtype=full.dtype, device=full.device)
-    if dist.get_backend(group) == "gloo":               # CPU host-logic tests
-        dist.all_reduce(full, group=group)
-        out.copy_(full[rank * n:(rank + 1) * n])
-    else:
-        dist.reduce_scatter_tensor(out, full, group=group)
-    return out
-
-
 class _ClipHeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, E, G, scale, want_grad, group):
-        ops = _ops
+        ops = _CudaOps
         world, rank = _world(group)
         E, G = E.contiguous(), G.contiguous()
         n = E.shape[0]
@@ -118,8 +106,7 @@ class _ClipHeadFn(torch.autograd.Function):
         ehat, inv_e = ops.normalize(E)
         ghat, inv_g = ops.normalize(G)
         if world > 1:
-            ghat_all = torch.empty((B, D_E), dtype=ghat.dtype, device=ghat.device)
-            dist.all_gather_into_tensor(ghat_all, ghat, group=group)
+            ghat_all = cpdist.all_gather_rows(ghat, group)
         else:
             ghat_all = ghat
         ght = ops.transpose(ghat_all)                       # (16, B)  loop operand of the row pass
@@ -138,7 +125,7 @@ class _ClipHeadFn(torch.autograd.Function):
             d_ehat = ops.grad(ehat, ght, B, scale, rowsum, colsum, coef)
             d_ghat = ops.grad(ghat_all, eht, n, scale, colsum, rowsum, coef)
             if world > 1:
-                d_ghat = _reduce_scatter_rows(d_ghat, n, rank, group)
+                d_ghat = cpdist.reduce_scatter_rows(d_ghat, group)
             ctx.saved = (ops.embed_backward(d_ehat, ehat, ghat, inv_e, scale / B),
                          ops.embed_backward(d_ghat, ghat, ehat, inv_g, scale / B))
         else:
@@ -159,6 +146,11 @@ def clip_head(E, G, logit_scale=0.0, group=None):
     G), the global number of rows whose arg-max column is their own sample, and this rank's arg-max
     columns (global indices, first maximum)."""
     scale = float(math.exp(float(logit_scale)))
+    if not scale <= MAX_SCALE:
+        # the sweeps shift every exponent by the largest possible logit (`scale`, cos = 1) and use ex2.approx.ftz:
+        # a row whose best cosine is c keeps a non-zero sum only while scale * (1 - c) * log2(e) < 126, which holds
+        # for ANY data when scale <= 43 (c >= -1).  Beyond that the sums could flush to 0 (inf loss): refuse.
+        raise ValueError(f"clip_head: exp(logit_scale) = {scale:.3g} exceeds the supported maximum {MAX_SCALE}")
     want_grad = torch.is_grad_enabled() and (E.requires_grad or G.requires_grad)
     return _ClipHeadFn.apply(E, G, scale, want_grad, group)
 

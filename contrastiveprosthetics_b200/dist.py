@@ -21,12 +21,20 @@ def init_from_env(backend=None):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     use_cuda = torch.cuda.is_available()
+    backend = backend or os.environ.get("CP_DIST_BACKEND") or ("nccl" if use_cuda else "gloo")
     if use_cuda:
+        ndev = torch.cuda.device_count()
+        if local >= ndev:
+            # more local ranks than GPUs: only gloo can put two ranks on one device (NCCL refuses); this is how the
+            # multi-rank paths are exercised on a 1-GPU box
+            if backend == "nccl":
+                raise RuntimeError(f"LOCAL_RANK {local} but {ndev} GPU(s): NCCL needs one GPU per rank")
+            local %= ndev
         torch.cuda.set_device(local)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
-        dist.init_process_group(backend or ("nccl" if use_cuda else "gloo"), rank=rank, world_size=world)
+        dist.init_process_group(backend, rank=rank, world_size=world)
     return rank, world, torch.device(f"cuda:{local}" if use_cuda else "cpu")
 
 
@@ -36,6 +44,84 @@ def world_size():
 
 def rank():
     return dist.get_rank() if dist.is_initialized() else 0
+
+
+def _needs_staging(t, group=None):
+    """NCCL moves CUDA tensors only; a CPU tensor (a host-side permutation) is staged through the device."""
+    return dist.get_backend(group) == "nccl" and not t.is_cuda
+
+
+def broadcast_(t, src=0, group=None):
+    """In-place broadcast of `t` from rank `src` (no-op in a single process).  Returns t."""
+    if world_size() == 1:
+        return t
+    if _needs_staging(t, group):
+        d = t.cuda()
+        dist.broadcast(d, src=src, group=group)
+        t.copy_(d)
+    else:
+        dist.broadcast(t, src=src, group=group)
+    return t
+
+
+def broadcast_module(module, src=0, group=None):
+    """Every parameter and buffer of `module` takes rank `src`'s value: the replicas of sample-sharded training
+    must start (and, after load_state_dict, restart) from ONE model.  Integer buffers (num_batches_tracked) included."""
+    if world_size() == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            broadcast_(t.data, src=src, group=group)
+
+
+def even_shard(n, r=None, w=None):
+    """[lo, hi) of rank r when n items are dealt as evenly as possible to w ranks: sizes differ by at most one and,
+    for n >= w, every rank gets at least one item (every rank then runs the same number of steps and collectives)."""
+    r = rank() if r is None else r
+    w = world_size() if w is None else w
+    return (r * n) // w, ((r + 1) * n) // w
+
+
+def assemble_rows(local, lo, total, group=None):
+    """Rows [lo, lo + len(local)) of a (total, ...) array live on this rank: returns the whole array on every rank
+    (exact for integers: each row is written by exactly one rank, the rest contribute zeros to the sum)."""
+    if world_size() == 1:
+        return local
+    full = torch.zeros((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    full[lo:lo + local.shape[0]] = local
+    dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+    return full
+
+
+def _has_tensor_collectives(group=None):
+    """all_gather_into_tensor / reduce_scatter_tensor exist for NCCL; gloo offers all_reduce / broadcast only."""
+    return dist.get_backend(group) == "nccl"
+
+
+def all_gather_rows(x, group=None):
+    """(n, ...) per rank -> (world*n, ...) on every rank, rank-major."""
+    w, r = dist.get_world_size(group), dist.get_rank(group)
+    n = x.shape[0]
+    out = torch.empty((w * n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    if _has_tensor_collectives(group):
+        dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    else:
+        out.zero_()
+        out[r * n:(r + 1) * n] = x
+        dist.all_reduce(out, group=group)
+    return out
+
+
+def reduce_scatter_rows(full, group=None):
+    """(world*n, ...) partials on every rank -> this rank's (n, ...) block of the sum."""
+    w, r = dist.get_world_size(group), dist.get_rank(group)
+    n = full.shape[0] // w
+    if _has_tensor_collectives(group):
+        out = torch.empty((n,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
+        dist.reduce_scatter_tensor(out, full.contiguous(), group=group)
+        return out
+    dist.all_reduce(full, group=group)
+    return full[r * n:(r + 1) * n].clone()
 
 
 class FlatGradAllReduce:

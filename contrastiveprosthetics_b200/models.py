@@ -325,6 +325,17 @@ class Model(nn.Module):
             self._pending.append(("train", ncor, None))
         return loss
 
+    def assemble_last(self, lo, n_global):
+        """Sharded evaluation (train._evaluate under torchrun): the result of the last loss() call covers groups
+        [lo, lo + B_local) of a global batch of n_global groups; replace it by the whole batch's integer arrays
+        (every rank then resolves the same accuracy / voting / y_pred a single GPU would)."""
+        from . import dist as cpdist
+        kind, a, b = self._pending[-1]
+        a = cpdist.assemble_rows(a, lo, n_global)
+        if b is not None:
+            b = cpdist.assemble_rows(b, lo, n_global)
+        self._pending[-1] = (kind, a, b)
+
     # -- accumulators.  The kernels return INTEGER counts; the float arithmetic of the reference
     #    (float32 running sum of count/41 per batch, models.py:134,166,170-172) is reproduced here.
     def _resolve(self):
@@ -454,7 +465,7 @@ class EMGNet(nn.Module):
         self.last = nn.Sequential(nn.Linear(512, self.d_e, bias=False))
         self.to(self.device)
 
-        self.engine = _lib.ENGINE_TC         # tcgen05 3xTF32 GEMMs (fp32-level accuracy); ENGINE_SIMT = fp32 FFMA
+        self.engine = _lib.ENGINE_TC         # tcgen05 GEMMs on the 3-product fp16 split (fp32-level accuracy); ENGINE_SIMT = fp32 FFMA
         self.dropout_seed = 0x5EED
         self._step = 0
         self.dropout_step = None             # device int64 counter mixed into the Philox key (graph.GraphedTrainStep)
@@ -497,8 +508,12 @@ class EMGNet(nn.Module):
                     m.num_batches_tracked += 1
         dp = float(self.dp) if self.training else 0.0
         self._step += 1
+        # sample-sharded ranks hold different rows of the global batch: mix the rank into the Philox key so that they
+        # do not all apply the same keep mask to their local rows
+        from . import dist as cpdist
+        seed = (self.dropout_seed * 1000003 + self._step) ^ (cpdist.rank() << 48)
         cfg = {"bn_mode": bn_mode, "engine": self.engine, "dropout_p": dp,
-               "seed": (self.dropout_seed * 1000003 + self._step) & 0xFFFFFFFFFFFFFFFF,
+               "seed": seed & 0xFFFFFFFFFFFFFFFF,
                "ext_masks": self.ext_dropout_masks if dp > 0 else None,
                "dropout_step": self.dropout_step, "bn_rm": rm, "bn_rv": rv,
                "need_bwd": torch.is_grad_enabled() and self.training,

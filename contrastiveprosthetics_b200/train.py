@@ -31,19 +31,46 @@ shuff = True
 args = None
 
 
-def _loader(dataset, batch_size):
+def _loader(dataset, batch_size, with_span=False):
     if getattr(args, "item_loader", False):
+        if cpdist.world_size() > 1:
+            raise RuntimeError("--item_loader is the reference's single-process DataLoader path; drop it under torchrun")
         return data.DataLoader(dataset, batch_size=batch_size, shuffle=shuff)
-    return dataset.batches(batch_size, shuffle=shuff, rank=cpdist.rank(), world_size=cpdist.world_size())
+    return dataset.batches(batch_size, shuffle=shuff, rank=cpdist.rank(), world_size=cpdist.world_size(),
+                           with_span=with_span)
 
 
 def _evaluate(model, dataset, batch_size):
+    """validate / test body (train.py:27-63).  Under torchrun every global eval batch is sharded over the ranks and
+    put back together before anything is reported (SURVEY.md section 8e "voting eval: shard groups; integer counts
+    summed"): BatchNorm statistics are taken over the rows of EVERY rank (the AdaBN eval batch is the global batch,
+    as on one GPU), the per-group vote / y_pred arrays of each batch are assembled across ranks (exact integers),
+    and the batch loss is the row-weighted mean -- so every rank returns the numbers a single GPU would."""
+    world = cpdist.world_size()
+    if world == 1:
+        total_loss = []
+        for (EMG, GLOVE, label) in _loader(dataset, batch_size):
+            label = label.reshape(-1)
+            with torch.no_grad():
+                logits = model.forward(EMG, GLOVE, label)
+                total_loss.append(model.loss(logits, label))
+        mean_loss = torch.stack(total_loss).mean().item()
+        return mean_loss, model.correct()
+    saved_sync = model.emg_net.sync_bn
+    model.emg_net.sync_bn = True
     total_loss = []
-    for (EMG, GLOVE, label) in _loader(dataset, batch_size):
-        label = label.reshape(-1)
-        with torch.no_grad():
-            logits = model.forward(EMG, GLOVE, label)
-            total_loss.append(model.loss(logits, label))
+    try:
+        for (EMG, GLOVE, label, lo, n_global) in _loader(dataset, batch_size, with_span=True):
+            label = label.reshape(-1)
+            with torch.no_grad():
+                logits = model.forward(EMG, GLOVE, label)
+                loss = model.loss(logits, label)
+            model.assemble_last(lo, n_global)
+            part = loss.detach().double() * (EMG.shape[0] / n_global)
+            torch.distributed.all_reduce(part)
+            total_loss.append(part)
+    finally:
+        model.emg_net.sync_bn = saved_sync
     mean_loss = torch.stack(total_loss).mean().item()
     return mean_loss, model.correct()
 
@@ -68,6 +95,8 @@ def train_loop(dataset, params, checkpoint=False, checkpoint_dir="../checkpoints
     if load is not None:
         print("Loading model")
         model.load_state_dict(torch.load(load + ".pt"))
+    # sample-sharded replicas must be ONE model: rank 0's initial values (or checkpoint) everywhere
+    cpdist.broadcast_module(model)
 
     fused = True if getattr(args, "fused_adam", False) else None     # None: torch's default implementation
     optimizer_emg = optim.Adam(model.emg_net.parameters(), lr=params['lr_emg'], weight_decay=0, fused=fused)
@@ -104,6 +133,10 @@ def train_loop(dataset, params, checkpoint=False, checkpoint_dir="../checkpoints
         scheduler_emg.step()
         scheduler_glove.step()
         loss_train = torch.stack(loss_train).mean().item()
+        if cpdist.world_size() > 1:         # logging only: mean over the ranks' local shards
+            t = torch.tensor([loss_train, acc_train], dtype=torch.float64, device=dataset.device)
+            torch.distributed.all_reduce(t)
+            loss_train, acc_train = (t / cpdist.world_size()).tolist()
 
         if verbose:
             loss_val, acc_val = validate(model, dataset)
@@ -195,6 +228,11 @@ def main(a):
     args = a
     rank, world, device = cpdist.init_from_env()
     np.random.seed(42)                       # train.py:22: the hyper-parameter draws depend on it
+    # the reference seeds torch at import (models.py:12, utils.py:14, load.py:18): same initial weights / sampling
+    # streams on every run -- and on every rank
+    torch.manual_seed(42)
+    if device.type == "cuda":
+        torch.cuda.manual_seed(42)
     dataset23 = DB23(db2=args.db2, device=device, mixed=getattr(args, "mixed", False))
     print("Loading dataset")
     if args.synthetic:

@@ -40,12 +40,35 @@ def gather_rows(src2d, idx, mean=None, std=None, n_ch=1):
     n, row_len = idx.numel(), src2d.shape[1]
     dst = torch.empty((n, row_len), dtype=torch.float32, device=src2d.device)
     stat_len = 0 if mean is None else int(mean.numel())
-    err = torch.zeros(1, dtype=torch.int32, device=src2d.device)
     _lib.check(L.cp_gather_norm(_lib.ptr(src2d, torch.float32), src2d.shape[0], row_len, _lib.ptr(idx), n,
                                 _lib.ptr(dst), _lib.ptr(mean), _lib.ptr(std), stat_len, n_ch,
-                                _lib.ptr(err), _lib.stream()), "cp_gather_norm")
-    dst._cp_err = err        # checked lazily by callers that can afford a sync
+                                _lib.ptr(_err_flag(src2d.device)), _lib.stream()), "cp_gather_norm")
     return dst
+
+
+_ERR_FLAGS = {}
+
+
+def _err_flag(device):
+    """One sticky device-side out-of-range flag per device (the kernel only ever ORs into it): no per-call
+    allocation or fill launch, no per-call host sync.  `check_gather_errors` reads it where a sync is affordable."""
+    f = _ERR_FLAGS.get(device)
+    if f is None:
+        f = _ERR_FLAGS[device] = torch.zeros(1, dtype=torch.int32, device=device)
+    return f
+
+
+def check_gather_errors(device=None):
+    """Raise IndexError if any gather since the last check saw an out-of-range row index (the reference's
+    advanced indexing raises at once, load.py:256-273; here the check costs a sync, so it runs at epoch /
+    split boundaries: TaskWrapper.batches end, set_train / set_val / set_test)."""
+    for dev, f in list(_ERR_FLAGS.items()):
+        if device is not None and dev != torch.device(device):
+            continue
+        if int(f.item()) != 0:
+            f.zero_()
+            raise IndexError("cp_gather_norm: a row index was out of range (rows outside the source table were "
+                             "read as row 0)")
 
 
 class RunningStats:
@@ -123,10 +146,16 @@ class TaskWrapper:
         return torch.rand((T, D), device=self.device).argsort(dim=-1) + base
 
     def reset(self):
+        from . import dist as cpdist
         self.emg_rand = self.return_rand(self.dataset.D)
         gd = self.dataset.glover.D
         self.glove_rand = self.return_rand(gd) if (self.with_glove and gd > 0) else None
         self.idx = torch.randperm(self.dataset.TASKS * self.dataset.D, device=self.device, dtype=torch.long)
+        if cpdist.world_size() > 1:
+            # sample sharding: every rank must index the SAME per-class permutations (rank 0's)
+            for t in (self.emg_rand, self.glove_rand, self.idx):
+                if t is not None:
+                    cpdist.broadcast_(t)
 
     def __getattr__(self, name):
         return getattr(self.__dict__["dataset"], name)
@@ -174,20 +203,38 @@ class TaskWrapper:
             GLOVE = torch.zeros((rows.numel(), GLOVE_DIM), device=self.device)
         return EMG, GLOVE, label
 
-    def batches(self, batch_size, shuffle=True, generator=None, rank=0, world_size=1):
-        """Equivalent of `DataLoader(self, batch_size, shuffle)` (train.py:86): a permutation of the
-        D items cut into batches (last one ragged).  With world_size > 1 every rank draws the same
-        permutation and takes a disjoint slice of each global batch (sample sharding)."""
+    def batch_plan(self, batch_size, shuffle=True, generator=None, rank=0, world_size=1):
+        """Item ids of every batch of one epoch for `rank`: list of (items, lo, n_global) with `items` this rank's
+        slice [lo, lo + len) of a global batch of n_global items.  Every rank runs the SAME number of batches (equal
+        collective counts): a global batch is dealt out evenly (sizes differ by at most one), and a ragged last
+        batch with fewer items than ranks is dropped on all of them."""
+        from . import dist as cpdist
         D = len(self)
         order = torch.randperm(D, generator=generator) if shuffle else torch.arange(D)
+        if world_size > 1 and shuffle:
+            cpdist.broadcast_(order)                # one permutation for the job, whatever the ranks' RNG states
+        plan = []
         for s in range(0, D, batch_size):
             chunk = order[s:s + batch_size]
+            n = chunk.numel()
             if world_size > 1:
-                per = (chunk.numel() + world_size - 1) // world_size
-                chunk = chunk[rank * per:(rank + 1) * per]
-                if chunk.numel() == 0:
+                if n < world_size:
                     continue
-            yield self.get_batch(chunk)
+                lo, hi = cpdist.even_shard(n, rank, world_size)
+                plan.append((chunk[lo:hi], lo, n))
+            else:
+                plan.append((chunk, 0, n))
+        return plan
+
+    def batches(self, batch_size, shuffle=True, generator=None, rank=0, world_size=1, with_span=False):
+        """Equivalent of `DataLoader(self, batch_size, shuffle)` (train.py:86): a permutation of the
+        D items cut into batches (last one ragged).  With world_size > 1 every rank uses the same
+        permutation and takes a disjoint slice of each global batch (sample sharding).  with_span: also
+        yield (lo, n_global), the position of the slice inside its global batch."""
+        for items, lo, n in self.batch_plan(batch_size, shuffle, generator, rank, world_size):
+            b = self.get_batch(items)
+            yield (b + (lo, n)) if with_span else b
+        check_gather_errors(self.device)
 
     def set_train(self):
         self.dataset.set_train()

@@ -7,7 +7,7 @@ import torch
 
 from contrastiveprosthetics_b200.load import DB23
 from contrastiveprosthetics_b200.synthetic import fixed_perm, synth_emg, synth_glove
-from contrastiveprosthetics_b200.utils import RunningStats, TaskWrapper, gather_rows
+from contrastiveprosthetics_b200.utils import RunningStats, TaskWrapper, check_gather_errors, gather_rows
 from oracle import dataset as OD
 
 pytestmark = pytest.mark.gpu
@@ -79,9 +79,11 @@ def test_edge_cases():
     assert torch.equal(out, src[idx])
     empty = gather_rows(src, torch.zeros(0, dtype=torch.int64, device="cuda"))
     assert empty.shape == (0, 5)
-    bad = gather_rows(src, torch.tensor([1, 99, -1], device="cuda"))
-    assert int(bad._cp_err.item()) == 1                                               # out-of-range flagged
-    assert int(out._cp_err.item()) == 0
+    check_gather_errors("cuda:0")                                                     # nothing flagged so far
+    gather_rows(src, torch.tensor([1, 99, -1], device="cuda"))
+    with pytest.raises(IndexError):                                                   # out-of-range flagged (sticky)
+        check_gather_errors("cuda:0")
+    check_gather_errors("cuda:0")                                                     # ... and cleared by the check
 
 
 def test_full_size_round_trip(emg):

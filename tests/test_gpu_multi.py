@@ -1,5 +1,9 @@
-"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): one process per GPU under torchrun,
-NCCL.  The sharded computation must reproduce the single-GPU one on the concatenated batch."""
+"""Multi-rank parity: one process per rank under torchrun.  With >= 2 GPUs on the box the ranks sit on separate
+GPUs and talk NCCL; on a 1-GPU box (the driver's test box) the SAME workers run as two ranks on cuda:0 over
+gloo (CP_DIST_BACKEND=gloo; dist.init_from_env folds LOCAL_RANK onto the GPUs that exist), so the sharded
+code paths -- SyncBN, the sharded batch x batch head, the flat gradient all-reduce, sharded evaluation,
+train.main under WORLD_SIZE 2, the per-rank fold split -- are exercised on the final code either way.
+The sharded computation must reproduce the single-GPU one on the concatenated batch."""
 import os
 import subprocess
 import sys
@@ -17,6 +21,7 @@ sys.path.insert(0, os.environ["CP_ROOT"])
 from contrastiveprosthetics_b200 import clip as C, dist as cpdist
 rank, world, dev = cpdist.init_from_env()
 assert dev.type == "cuda" and world >= 2
+nccl = dist.get_backend() == "nccl"
 
 def rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm())
@@ -96,13 +101,88 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-def test_two_gpu_sharded_paths(tmp_path):
+_TRAIN_WORKER = r'''
+import os, sys, numpy as np, torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["CP_ROOT"])
+from contrastiveprosthetics_b200 import dist as cpdist, train as T
+tmp = os.environ["CP_TMP"]
+argv = ["--final_epochs=1", "--crossval_size=3", "--crossval_epochs=1", "--batch_size=24", "--test", "--synthetic",
+        "--no_verbose", f"--data_dir={tmp}/data/", f"--checkpoint_dir={tmp}/ckpt/"]
+args = T.build_parser().parse_args(argv)
+# keep the model train.main builds for the checks below
+kept = {}
+orig = T.train_loop
+def spy(*a, **k):
+    out = orig(*a, **k)
+    kept["model"] = out[1]
+    return out
+T.train_loop = spy
+loss, acc = T.main(args)
+rank, world = cpdist.rank(), cpdist.world_size()
+assert world == 2
+dev = torch.device("cuda", torch.cuda.current_device())
+# (1) the replicas are ONE model after training: identical parameters and buffers on every rank
+m = kept["model"]
+for name, t in list(m.named_parameters()) + list(m.named_buffers()):
+    ref = t.detach().clone()
+    cpdist.broadcast_(ref)
+    assert torch.equal(ref, t.detach()), name
+# (2) sharded evaluation reports the same numbers on every rank ...
+r = torch.tensor([loss, acc], dtype=torch.float64, device=dev)
+r0 = r.clone(); cpdist.broadcast_(r0)
+assert torch.equal(r, r0), (r, r0)
+# (3) ... and they are the numbers of an UN-sharded evaluation of the same model on the same batches
+from contrastiveprosthetics_b200.load import DB23
+from contrastiveprosthetics_b200.utils import TaskWrapper
+ds = DB23(db2=False, device=dev); ds.load_synthetic()
+tw = TaskWrapper(ds)
+T.shuff = False
+torch.manual_seed(7); torch.cuda.manual_seed(7)          # same per-class window draws in both evaluations
+sh_loss, sh_acc = T.test(m, tw)
+sh_vote, sh_pred = m.voting_raw().copy(), m.y_pred_raw().copy()
+saved = (cpdist.rank, cpdist.world_size)
+cpdist.rank, cpdist.world_size = (lambda: 0), (lambda: 1)
+try:
+    torch.manual_seed(7); torch.cuda.manual_seed(7)
+    one_loss, one_acc = T.test(m, tw)
+    one_vote, one_pred = m.voting_raw().copy(), m.y_pred_raw().copy()
+finally:
+    cpdist.rank, cpdist.world_size = saved
+assert abs(sh_loss - one_loss) < 1e-5 * abs(one_loss), (sh_loss, one_loss)
+assert sh_vote.shape == one_vote.shape and sh_pred.shape == one_pred.shape
+# integer decisions: identical unless a logit pair sits within rounding noise (statistics are reduced in another order)
+assert (sh_pred != one_pred).mean() < 1e-3 and abs(sh_acc - one_acc) < 1e-3, (sh_acc, one_acc)
+# (4) cross-validation folds were split per rank and gathered: both ranks hold the full table, and each fold's row
+#     is the one its owner computed
+vals = np.load(f"{tmp}/data/cross_val_values.npy"); keys = np.load(f"{tmp}/data/cross_val_keys.npy")
+assert vals.shape == (3, 2) and keys.shape == (3, 7) and np.isfinite(vals).all()
+print("rank", rank, "ok", loss, acc)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def _run_two_ranks(tmp_path, worker, port, timeout=900):
     script = tmp_path / "w.py"
-    script.write_text(_WORKER)
-    env = dict(os.environ, CP_ROOT=ROOT)
+    script.write_text(worker)
+    env = dict(os.environ, CP_ROOT=ROOT, CP_TMP=str(tmp_path))
+    if torch.cuda.device_count() < 2:
+        env["CP_DIST_BACKEND"] = "gloo"             # two ranks on the one GPU
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29621", str(script)],
-                         env=env, capture_output=True, text=True, timeout=600)
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         env=env, capture_output=True, text=True, timeout=timeout)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count(" ok") == 2
+    assert out.stdout.count(" ok") == 2, out.stdout[-2000:]
+    return out.stdout
+
+
+def test_two_rank_sharded_paths(tmp_path):
+    """SyncBN == global batch, sharded batch x batch head == single GPU, flat gradient all-reduce."""
+    _run_two_ranks(tmp_path, _WORKER, 29621)
+
+
+def test_two_rank_train_main(tmp_path):
+    """train.main under WORLD_SIZE 2: identical replicas after training, sharded evaluation == un-sharded
+    evaluation, folds split per rank."""
+    _run_two_ranks(tmp_path, _TRAIN_WORKER, 29623)

@@ -157,12 +157,75 @@ def test_batches_cover_every_item_once_per_rank_split(emg):
     assert torch.equal(allitems, torch.arange(ds.D))
 
 
+@pytest.mark.parametrize("D,batch,world", [(160, 64, 8), (9, 9, 8), (100, 33, 8), (48, 8, 3), (17, 5, 4), (7, 64, 8),
+                                            (13800, 4096, 8), (24, 7, 2)])
+def test_every_rank_runs_the_same_number_of_batches(D, batch, world):
+    """Sample sharding must not let a rank skip a step the others run (its all-reduces would never be matched):
+    every global batch is dealt out evenly, and a ragged tail smaller than the world is dropped on ALL ranks."""
+    class _DS:
+        device = torch.device("cpu")
+    tw = TaskWrapper.__new__(TaskWrapper)
+    tw.__dict__["dataset"] = _DS()
+    tw.__dict__["device"] = torch.device("cpu")
+    TaskWrapper.__len__ = TaskWrapper.__len__          # (len() goes through the class)
+    tw.__dict__["dataset"].D = D
+    plans = []
+    for r in range(world):
+        g = torch.Generator().manual_seed(11)
+        plans.append(tw.batch_plan(batch, shuffle=True, generator=g, rank=r, world_size=world))
+    counts = {len(p) for p in plans}
+    assert len(counts) == 1, counts
+    seen = []
+    for b in range(len(plans[0])):
+        n_global = plans[0][b][2]
+        assert n_global >= world
+        sizes = [p[b][0].numel() for p in plans]
+        assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1 and sum(sizes) == n_global
+        los = [p[b][1] for p in plans]
+        assert los == [sum(sizes[:r]) for r in range(world)]
+        seen.append(torch.cat([p[b][0] for p in plans]))
+    covered = torch.cat(seen).sort().values if seen else torch.zeros(0, dtype=torch.long)
+    tail = D % batch
+    dropped = tail if 0 < tail < world else 0
+    assert covered.numel() == D - dropped and covered.unique().numel() == covered.numel()
+
+
 _GLOO_WORKER = r'''
 import os, sys, torch, numpy as np
 sys.path.insert(0, os.environ["CP_ROOT"])
 from contrastiveprosthetics_b200 import dist as cpdist, subset
 rank, world, dev = cpdist.init_from_env("gloo")
 assert world == 2 and dev.type == "cpu"
+# replicas start from ONE model: rank 0's parameters and buffers everywhere (train.train_loop)
+torch.manual_seed(100 + rank)
+net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3))
+net[1].running_mean.fill_(float(rank)); net[1].num_batches_tracked.fill_(7 * rank + 1)
+cpdist.broadcast_module(net)
+ref = [t.clone() for t in list(net.parameters()) + list(net.buffers())]
+for t in ref:
+    cpdist.broadcast_(t)                     # rank 0's copy of what this rank now holds
+assert all(torch.equal(a, b) for a, b in zip(ref, list(net.parameters()) + list(net.buffers())))
+assert float(net[1].running_mean[0]) == 0.0 and int(net[1].num_batches_tracked) == 1
+# sharded evaluation: per-group integer arrays of a global batch put back together (exact), uneven shards
+n_global = 7
+lo, hi = cpdist.even_shard(n_global)
+full = torch.arange(n_global * 3, dtype=torch.int32).reshape(n_global, 3) + 1
+got = cpdist.assemble_rows(full[lo:hi].clone(), lo, n_global)
+assert torch.equal(got, full)
+# the row collectives the batch x batch head needs, on a backend without tensor collectives
+x = torch.full((2, 3), float(rank + 1))
+assert torch.equal(cpdist.all_gather_rows(x), torch.tensor([[1.0] * 3] * 2 + [[2.0] * 3] * 2))
+part = torch.arange(12, dtype=torch.float32).reshape(4, 3) * (rank + 1)
+assert torch.equal(cpdist.reduce_scatter_rows(part.clone()), 3 * torch.arange(12, dtype=torch.float32).reshape(4, 3)[rank * 2:rank * 2 + 2])
+# one permutation per job whatever the ranks' generators say
+from contrastiveprosthetics_b200.utils import TaskWrapper
+class _DS:
+    device = torch.device("cpu"); D = 23
+tw = TaskWrapper.__new__(TaskWrapper); tw.__dict__["dataset"] = _DS(); tw.__dict__["device"] = torch.device("cpu")
+plan = tw.batch_plan(6, shuffle=True, generator=torch.Generator().manual_seed(50 + rank), rank=rank, world_size=world)
+mine = torch.cat([p[0] for p in plan])
+both = cpdist.assemble_rows(mine.clone(), 0 if rank == 0 else 23 - mine.numel(), 23)
+assert both.sort().values.tolist() == list(range(23)), both
 # flat-bucket gradient averaging
 torch.manual_seed(0)
 ps = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7))]
@@ -231,7 +294,8 @@ class TorchOps:
         dh = d_hat - diag_coef * other_hat
         return (dh - xhat * (xhat * dh).sum(1, keepdim=True)) * inv_norm[:, None]
 
-C._ops = TorchOps
+for name in ("normalize", "transpose", "sums", "loss", "grad", "embed_backward"):      # test-side patch of the six entry points
+    setattr(C._CudaOps, name, staticmethod(getattr(TorchOps, name)))
 rank, world, dev = cpdist.init_from_env("gloo")
 n = 5
 g = torch.Generator().manual_seed(0)
