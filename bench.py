@@ -2,7 +2,7 @@
 """bench.py -- train sEMG windows/s (+ subset-eval preds/s) of the B200 hot path.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU oracle port
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own code on the host CPU
 
 A "step" is one full train_loop iteration (train.py:95-108) on one batch of synthetic DB2-shaped
 data: gather -> encoder forward -> fused head/loss (+ l2) -> backward -> [gradient all-reduce]
@@ -144,22 +144,44 @@ def cpu_oracle_steps(n_steps, warmup, groups=256, seed=0):
     return N / (ms / 1e3), ms, torch.get_num_threads()
 
 
+CPU_SAMPLE_GROUPS = 256          # ONE bounded sample of the workload for every CPU number of both arms
+
+
+def cpu_reference_baseline(n_steps, warmup):
+    """cpu_baseline object: the reference's OWN code (oracle/_ref, staged by oracle/ref_fetch.py) timed on this
+    box's host cores on CPU_SAMPLE_GROUPS groups per step, with the oracle port (oracle/model.py) beside it on
+    the same sample; falls back to the port alone when the staged reference is absent."""
+    from oracle import ref_fetch
+    groups = CPU_SAMPLE_GROUPS
+    port_wps, port_ms, cores = cpu_oracle_steps(n_steps, warmup, groups)
+    sample = f"{n_steps} steps x {groups * T} windows ({groups} groups) of the C2 train step, same per-window work"
+    if ref_fetch.staged():
+        from oracle import refrun
+        wps, ms, cores = refrun.train_steps(n_steps, warmup, groups, PARAMS)
+        return {"value": wps, "unit": "windows/s", "cores": cores, "kind": "reference", "ms_per_step": ms,
+                "sample": sample + "; the UNMODIFIED reference (models.py / utils.py / load.py via oracle/_ref, "
+                          "'cuda' -> 'cpu', stub imports) running train.py:83-108's loop body: DataLoader over its "
+                          "TaskWrapper, Model.forward / loss / l2, backward, Adam x2",
+                "port": {"value": port_wps, "unit": "windows/s", "ms_per_step": port_ms,
+                         "what": "oracle/model.py (vectorised torch-CPU restatement) on the same sample"}}
+    return {"value": port_wps, "unit": "windows/s", "cores": cores, "kind": "port", "ms_per_step": port_ms,
+            "sample": sample + "; oracle/ torch-CPU port of train.py:95-108 (oracle/_ref not staged)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    groups = 256
-    wps, ms, cores = cpu_oracle_steps(args.steps, args.warmup, groups)
+    cpu = cpu_reference_baseline(args.steps, args.warmup)
+    wps, ms = cpu["value"], cpu["ms_per_step"]
     line = {
         "impl": "reference", "metric": "train sEMG windows/s", "value": wps, "unit": "windows/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C2: train step, batch_size 4096 groups x 41 windows, AdaBN on, fp32",
-                   "note": f"CPU arm times a bounded sample of the workload: {groups} groups "
-                           f"({groups * T} windows) per step, same per-window work"},
-        "cpu_baseline": {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {groups * T} windows (oracle/ torch-CPU port of "
-                                   "train.py:95-108; the Python reference cannot travel to the GPU box)"},
+                   "note": f"CPU arm times a bounded sample of the workload: {CPU_SAMPLE_GROUPS} groups "
+                           f"({CPU_SAMPLE_GROUPS * T} windows) per step, same per-window work"},
+        "cpu_baseline": cpu,
         "e2e": {"value": wps, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -420,10 +442,7 @@ def run_cuda(args):
         prep = preprocess_leg(dev)
     if rank == 0:
         if world == 1:       # N = 1 only: at N > 1 the other ranks spin in the barrier on the same host cores
-            wps, cms, cores = cpu_oracle_steps(n_steps=16, warmup=2, groups=512)
-            cpu = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
-                   "sample": f"16 steps x {512 * T} windows of the same train step (oracle/ torch-CPU port), "
-                             f"{cms:.0f} ms/step"}
+            cpu = cpu_reference_baseline(n_steps=10, warmup=2)
         line = {
             "metric": "train sEMG windows/s", "value": value, "unit": "windows/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
