@@ -13,7 +13,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 SO_PATH = os.path.join(_PKG, "libcpros.so")
-SOURCES = ["version.cu", "gather.cu", "encoder.cu", "head.cu", "clip.cu", "vote.cu", "l2.cu", "preprocess.cu"]
+SOURCES = ["version.cu", "gather.cu", "encoder.cu", "head.cu", "clip.cu", "vote.cu", "l2.cu", "preprocess.cu", "philox.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -103,6 +103,10 @@ def lib():
                                       ctypes.POINTER(EncoderOpts), _vp]
     L.cp_encoder_read_activation.argtypes = [_vp, _sz, _i64, ctypes.POINTER(EncoderOpts), _i32, _i32, _vp, _vp]
     L.cp_encoder_read_activation.restype = ctypes.c_int
+    L.cp_philox4x32_10.argtypes = [_vp, _vp, _i64, _vp, _vp]
+    L.cp_philox4x32_10.restype = ctypes.c_int
+    L.cp_dropout_mask.argtypes = [_vp, _i64, ctypes.c_float, ctypes.c_uint64, _i32, _vp, _vp]
+    L.cp_dropout_mask.restype = ctypes.c_int
     L.cp_linear_workspace_bytes.restype = _sz
     L.cp_linear_workspace_bytes.argtypes = [_i64, _i32, _i32]
     L.cp_linear_forward.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _i32, _vp]
@@ -157,7 +161,7 @@ EXPORTS = ["cp_version", "cp_launch_count", "cp_status_string", "cp_gather_norm"
            "cp_subset_eval", "cp_clip_normalize", "cp_clip_transpose", "cp_clip_sums", "cp_clip_loss",
            "cp_clip_grad", "cp_clip_embed_backward", "cp_glove_workspace_bytes", "cp_glove_forward",
            "cp_glove_backward", "cp_confusion_matrix", "cp_l2_workspace_bytes", "cp_l2_forward", "cp_l2_backward",
-           "cp_emg_preprocess_scratch_elems", "cp_emg_preprocess"]
+           "cp_emg_preprocess_scratch_elems", "cp_emg_preprocess", "cp_philox4x32_10", "cp_dropout_mask"]
 
 
 def check(status, what=""):

@@ -21,6 +21,29 @@ extern unsigned long long g_cp_launches;
         if (e__ != cudaSuccess) return (int)e__;           \
     } while (0)
 
+// Function attributes (dynamic shared-memory opt-in) are per DEVICE: CP_ONCE_PER_DEVICE runs its body the first time
+// a call site is reached on each device of the process.  Idempotent bodies only (two host threads may both run one).
+#include <atomic>
+struct CpOncePerDevice {
+    std::atomic<unsigned long long> mask{0};
+    bool need(unsigned long long& bit) const {
+        int d = 0;
+        cudaGetDevice(&d);
+        bit = 1ull << (d & 63);
+        return !(mask.load(std::memory_order_acquire) & bit);
+    }
+    void done(unsigned long long bit) { mask.fetch_or(bit, std::memory_order_release); }
+};
+#define CP_ONCE_PER_DEVICE(...)                                \
+    do {                                                       \
+        static CpOncePerDevice once__;                         \
+        unsigned long long bit__;                              \
+        if (once__.need(bit__)) {                              \
+            __VA_ARGS__;                                       \
+            once__.done(bit__);                                \
+        }                                                      \
+    } while (0)
+
 static inline int64_t cp_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t cp_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 

@@ -21,6 +21,7 @@
 // slot, hi in the first half and lo in the second -- that the TMA-fed GEMMs consume directly, and the weights
 // are split (and transposed for the data gradient) once per call.
 #include <algorithm>
+#include <mutex>
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "encoder_kernels.cuh"
@@ -280,13 +281,16 @@ int bn_backward(const float* g, const float* y, float* gz, bool planes, int64_t 
 // Side stream for the weight-gradient GEMMs of the tensor-core engine: they are off the critical
 // path (dgrad -> BN backward -> dgrad ...) and, being tensor-pipe bound, overlap with the HBM-bound
 // BN-backward kernels of the next layer.  Fork/join is by events, so the caller's stream semantics
-// (and CUDA-graph capture) are preserved.  Created once per process.
+// (and CUDA-graph capture) are preserved.  One per DEVICE, created on first use; `lock` serialises the host-side
+// enqueue of cp_encoder_backward calls on that device (two host threads recording / waiting on the same events
+// would otherwise pick up each other's records) -- the GPU work of different caller streams still overlaps.
 struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t ready[2] = {nullptr, nullptr};     // main -> side: G1 buffer b has been written
     cudaEvent_t done[2] = {nullptr, nullptr};      // side -> main: G1 buffer b has been consumed
     bool ok = false;
-    int init() {
+    std::mutex lock;
+    int init() {                                   // call with `lock` held
         if (ok) return CP_OK;
         CP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
@@ -297,7 +301,13 @@ struct SideStream {
         return CP_OK;
     }
 };
-SideStream g_side;
+constexpr int CP_MAX_DEVICES = 64;
+SideStream g_side_of[CP_MAX_DEVICES];
+SideStream* side_of_current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= CP_MAX_DEVICES) return nullptr;
+    return &g_side_of[d];
+}
 
 // Backward of the last linear block from d_emb: projection weight gradient, BN backward, ReLU backward and the
 // bias gradient in two passes over (Y7, mask, d_emb) -- see proj_fused.cuh.  gz: pre-activation gradient
@@ -308,16 +318,14 @@ int last_block_backward(const float* d_emb, float* gz, bool planes, int64_t n, c
     constexpr int LL = CP_N_FC - 1, S = CP_N_BN - 1;           // linear layer / BN stage of the last block
     if (((uintptr_t)d_emb) % 16 != 0) return CP_ERR_ARG;
     const int G = pf::grid_for(n);
-    static bool attr_set = false;
-    if (!attr_set) {
+    CP_ONCE_PER_DEVICE({
         CP_TRY(pf::set_smem(pf::proj_bwd_reduce_kernel<false>));
         CP_TRY(pf::set_smem(pf::proj_bwd_reduce_kernel<true>));
         CP_TRY(pf::set_smem(pf::proj_bwd_apply_kernel<false, false>));
         CP_TRY(pf::set_smem(pf::proj_bwd_apply_kernel<false, true>));
         CP_TRY(pf::set_smem(pf::proj_bwd_apply_kernel<true, false>));
         CP_TRY(pf::set_smem(pf::proj_bwd_apply_kernel<true, true>));
-        attr_set = true;
-    }
+    });
     unsigned int* gmax = planes ? w.gmax + S : nullptr;
     if (keep)
         pf::proj_bwd_reduce_kernel<true><<<G, 256, pf::SMEM, st>>>(w.Y[LL], keep, d_emb, n, inv_keep, w.scale[S], w.shift[S],
@@ -461,13 +469,11 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
         // last block: BN (+ dropout) fused with the 512 -> 16 projection
         const int G = pf::grid_for(n);
         const unsigned long long* step = (const unsigned long long*)o->dropout_step;
-        static bool attr_set = false;
-        if (!attr_set) {
+        CP_ONCE_PER_DEVICE({
             CP_TRY(pf::set_smem(pf::bn_apply_proj_kernel<0>));
             CP_TRY(pf::set_smem(pf::bn_apply_proj_kernel<1>));
             CP_TRY(pf::set_smem(pf::bn_apply_proj_kernel<2>));
-            attr_set = true;
-        }
+        });
         if (!keep)
             pf::bn_apply_proj_kernel<0><<<G, pf::FWD_THREADS, pf::SMEM, st>>>(w.Y[l], n, w.scale[2 + l], w.shift[2 + l], nullptr, 1.f, 0.f, 0, 0,
                                                                   nullptr, p->proj_w, emb);
@@ -501,7 +507,12 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
 
     // linear blocks, last to first.  G0 = grad w.r.t. block output, G1 = grad w.r.t. pre-activation
     cudaEvent_t join_event = nullptr;
+    SideStream* side = tcE ? side_of_current_device() : nullptr;
+    if (tcE && !side) return CP_ERR_UNSUPPORTED;
+    std::unique_lock<std::mutex> side_guard;
+    if (side) side_guard = std::unique_lock<std::mutex>(side->lock);
     if (tcE) {
+        SideStream& g_side = *side;
         CP_TRY(g_side.init());
         cudaStream_t ss = g_side.stream;
         int nb = 0;                                    // stages processed so far -> G1 buffer parity

@@ -906,12 +906,10 @@ inline int launch_tn(const plane_t* G_hi, const plane_t* G_lo, int ldg, int Mo, 
     if ((rc = make_tmap_mn(&tg_lo, G_lo, R, Mo, ldg)) != CP_OK) return rc;
     if ((rc = make_tmap_mn(&ta_hi, A_hi, R, No, lda)) != CP_OK) return rc;
     if ((rc = make_tmap_mn(&ta_lo, A_lo, R, No, lda)) != CP_OK) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    CP_ONCE_PER_DEVICE({
         CP_CUDA(cudaFuncSetAttribute(gemm_tc_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         CP_CUDA(cudaFuncSetAttribute(gemm_tc_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
+    });
     const int tiles = (Mo / BM) * (No / BN);
     // one wave on ~2/3 of the SMs: this GEMM runs on a side stream next to the HBM-bound BN-backward kernels, and
     // each of its CTAs pins 48 K registers (255 x 192 threads), leaving room for ONE 256-thread BN CTA on that SM.
@@ -964,12 +962,10 @@ template <int BN_, bool CONV, bool FAST>
 inline int launch_nt_cfg(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
                          const CUtensorMap& tb_lo, const CUtensorMap& tc_out, const NtArgs& g, int64_t tiles_m,
                          cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    CP_ONCE_PER_DEVICE({
         CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_kernel<BN_, CONV, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      NtCfg<BN_>::SMEM));
-        attr_set = true;
-    }
+    });
     const int64_t n_tiles = tiles_m * (g.N / BN_);
     const int grid = (int)(n_tiles < CP_NUM_SMS ? n_tiles : CP_NUM_SMS);
     gemm_tc_nt_kernel<BN_, CONV, FAST><<<grid, THREADS, NtCfg<BN_>::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g);
@@ -996,12 +992,10 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
         CUtensorMap tb_hi2, tb_lo2;                                   // B boxes of 64 rows: half a tile per CTA
         if ((rc = make_tmap_2d(&tb_hi2, B_hi, N, K, ldb, BN / 2)) != CP_OK) return rc;
         if ((rc = make_tmap_2d(&tb_lo2, B_lo, N, K, ldb, BN / 2)) != CP_OK) return rc;
-        static bool attr_set = false;
-        if (!attr_set) {
+        CP_ONCE_PER_DEVICE({
             CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
             CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
-            attr_set = true;
-        }
+        });
         const int64_t n_tiles = cp_cdiv(M, 2 * BM) * (N / BN);
         const int clusters = (int)(n_tiles < CP_NUM_SMS / 2 ? n_tiles : CP_NUM_SMS / 2);
         if (fast) gemm_tc_nt_pair_kernel<true><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, g);
@@ -1040,12 +1034,10 @@ inline int launch_conv_tn(const plane_t* X_hi, const plane_t* X_lo, const plane_
     if ((rc = make_tmap_conv(&tx_lo, X_lo, windows, CW_WIN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tg_hi, G_hi, windows * 12, 64, 64, CW_ROWS)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tg_lo, G_lo, windows * 12, 64, 64, CW_ROWS)) != CP_OK) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    CP_ONCE_PER_DEVICE({
         CP_CUDA(cudaFuncSetAttribute(gemm_tc_tn_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM));
         CP_CUDA(cudaFuncSetAttribute(gemm_tc_tn_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM));
-        attr_set = true;
-    }
+    });
     int S = CP_NUM_SMS / 2;
     const int64_t max_s = cp_cdiv(windows, (int64_t)CW_WIN * CW_CHUNK_KB);
     if (S > max_s) S = (int)max_s;

@@ -17,7 +17,7 @@
 __global__ void __launch_bounds__(64)
 vote_kernel(const int32_t* __restrict__ pred, int W, int n_votes, int32_t* __restrict__ votes,
             int64_t* __restrict__ y_pred) {
-    __shared__ uint8_t cnt[T][T + 3];
+    __shared__ uint16_t cnt[T][T + 1];            // 16-bit: a row may collect all W <= 256 votes on one label
     __shared__ int correct_at[MAXW * 8];
     const int64_t b = blockIdx.x;
     const int i = threadIdx.x;
@@ -29,6 +29,10 @@ vote_kernel(const int32_t* __restrict__ pred, int W, int n_votes, int32_t* __res
     if (i < T) {
         for (int w = 0; w < W; ++w) {
             const int l = pred[(b * W + w) * T + i];
+            if ((unsigned)l >= (unsigned)T) {        // not a class label: no vote (the prefix mode is unchanged)
+                if (best == i && best_c > 0) atomicAdd(&correct_at[w], 1);
+                continue;
+            }
             const int c = ++cnt[i][l];
             // prefix mode, ties -> smallest label: the incremented label wins iff it now has
             // strictly more votes, or as many votes and a smaller label

@@ -3,7 +3,10 @@
  * Every entry point takes raw DEVICE pointers, explicit sizes and a CUDA stream (void* =
  * cudaStream_t), returns an int status (0 ok, <0 argument error, >0 cudaError_t), never
  * allocates or frees caller memory, never throws, never synchronises the device, and is
- * re-entrant per stream.  There is no CPU implementation behind any symbol.
+ * re-entrant per stream: host threads may call concurrently on different streams / devices.  Per-device state of
+ * the library (function attributes, the side stream + events cp_encoder_backward forks its weight-gradient GEMMs
+ * onto) is created on first use on that device; concurrent cp_encoder_backward calls on ONE device are serialised
+ * on the host for the duration of their enqueue only.  There is no CPU implementation behind any symbol.
  *
  * The reference (FibonacciDude/ContrastiveProsthetics) is pure Python and has no FFI; each
  * symbol below cites the reference Python code it replaces (paths under /root/reference/code).
@@ -109,6 +112,15 @@ int cp_encoder_forward(const cp_encoder_tensors *params, const float *x, int64_t
 int cp_encoder_backward(const cp_encoder_tensors *params, const float *d_emb, int64_t n,
                         const cp_encoder_tensors *grads, void *workspace, size_t workspace_bytes,
                         const cp_encoder_opts *opts, void *stream);
+
+/* Dropout mask generator taps (tests).  cp_philox4x32_10: out[i] = Philox4x32-10(ctr[i] (4 words), key[i] (2 words))
+ * -- the raw block function, checked against the published known-answer vectors.  cp_dropout_mask: the {0,1} keep
+ * mask of dropout layer `layer` (0..3) exactly as cp_encoder_forward draws it for opts {dropout_seed = seed,
+ * dropout_step = step}: element e = row*512 + col keeps iff word (e % 4) of Philox(ctr = {e/4 lo, e/4 hi, layer,
+ * 0x43505253}, key = seed [+ *step * 0x9E3779B97F4A7C15]) >= p * 2^32.  n % 4 == 0. */
+int cp_philox4x32_10(const uint32_t *ctr, const uint32_t *key, int64_t n, uint32_t *out, void *stream);
+int cp_dropout_mask(uint8_t *keep, int64_t n, float p, uint64_t seed, int layer, const uint64_t *step,
+                    void *stream);
 
 /* Parity tap: copy the saved activation of BN stage `stage` (0,1: conv stages, layout (n*12,64)
  * position-major/channel-contiguous; 2..8: linear stages, (n,512)) out of a workspace written by
@@ -226,9 +238,9 @@ int cp_glove_backward(const cp_glove_tensors *params, const float *d_emb, int64_
 
 /* ---------------------------------------------------------------- K4: windowed majority vote
  * Replaces the vote loop of contrastive_loopy_loss (models.py:149-163, constants.py:74-78).
- * pred: (B,W,41) int32.  votes: (B,n_votes) int32 = #rows whose prefix-mode over the first
+ * pred: (B,W,41) int32, W <= 256.  votes: (B,n_votes) int32 = #rows whose prefix-mode over the first
  * min(v+1,W) samples equals the row label (mode ties -> smallest label).  y_pred: (B,41) int64 =
- * full-window mode. */
+ * full-window mode.  Entries of pred outside [0,41) cast no vote. */
 int cp_vote_eval(const int32_t *pred, int64_t B, int W, int n_votes, int32_t *votes,
                  int64_t *y_pred, void *stream);
 
