@@ -1,0 +1,67 @@
+"""Encoder parity at the size that is benchmarked, and over the dynamic range of the fp16-plane operand format.
+
+* C2 size (BASELINE.json configs[1]: 4096 groups x 41 = 167,936 windows, AdaBN, dropout 0.5 with injected masks)
+  and a C3-shaped mixed-subject batch (DB3 subjects' channel 10 zeroed, load.py:269-272): the size-dependent
+  mechanisms of the tensor-core engine -- weight-gradient chains cut every 512 rows and re-summed over 328 chunks,
+  per-layer power-of-two plane scales, two-level partial sums over 1,312 tiles, 32-bit gather indexing -- against
+  the fp32 oracle with the kernel's ReLU pattern (DESIGN.md "ReLU kinks").
+* range: BatchNorm gammas x {1e-3, 3e2}, weights x {1e-4, 1e3}, inputs x 1e3.
+
+Tolerance: north_star's 1e-5 relative (norm-wise per tensor) for the loss-side values (embeddings, every stage)
+and for the gradients.  Measured worst cases: profiles/parity_r2.json (scripts/parity_report.py)."""
+import os
+
+import pytest
+import torch
+
+from contrastiveprosthetics_b200 import _lib
+from gpu_util import encoder_parity_errors, perturbed_state, scale_state, worst
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _inputs(n, seed, mixed=False, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 12, generator=g) + 0.5 * torch.randn(41, 12, generator=g).repeat((n + 40) // 41, 1)[:n]
+    if mixed:                       # 6 of 46 subjects are 11-channel DB3 recordings: channel 10 is zero
+        x[torch.rand(n, generator=g) < 6.0 / 46.0, 10] = 0.0
+    d_emb = torch.randn(n, 16, generator=g) / n
+    return x * scale, d_emb
+
+
+@pytest.mark.parametrize("mixed", [False, True])
+def test_c2_size_forward_and_gradients(mixed):
+    n, dp = 4096 * 41, 0.5
+    torch.set_num_threads(os.cpu_count() or 8)
+    sd = perturbed_state(3, True)
+    x, d_emb = _inputs(n, 100 + mixed, mixed)
+    g = torch.Generator().manual_seed(7)
+    masks = [torch.empty(n, 512, dtype=torch.uint8).bernoulli_(0.5, generator=g) for _ in range(4)]
+    e = encoder_parity_errors(sd, True, x, d_emb, _lib.ENGINE_TC, dp, masks)
+    assert e["emb"] < TOL, e["emb"]
+    assert worst(e, "stage")[0] < TOL, worst(e, "stage")
+    assert worst(e, "grad|")[0] < TOL, worst(e, "grad|")
+    assert e["relu_flip_fraction"] < 1e-4
+
+
+@pytest.mark.parametrize("engine", [_lib.ENGINE_SIMT, _lib.ENGINE_TC])
+@pytest.mark.parametrize("gamma,weight,xscale", [(1e-3, 1.0, 1.0), (3e2, 1.0, 1.0), (1.0, 1e-4, 1.0), (1.0, 1e3, 1.0),
+                                                 (1.0, 1.0, 1e3), (3e2, 1e3, 1e3), (1e-3, 1e-4, 1.0)])
+def test_dynamic_range(gamma, weight, xscale, engine):
+    """Trained BatchNorm gammas far from 1, tiny / huge weights, un-normalised inputs: the plane format (fp16 hi/lo with
+    per-tensor power-of-two scales) must keep fp32-level accuracy, not silently fall into fp16 subnormals / overflow."""
+    n, dp = 41 * 40, 0.5
+    sd = scale_state(perturbed_state(29, True), True, gamma, weight)
+    x, d_emb = _inputs(n, 200, scale=xscale)
+    g = torch.Generator().manual_seed(9)
+    masks = [torch.empty(n, 512, dtype=torch.uint8).bernoulli_(0.5, generator=g) for _ in range(4)]
+    e = encoder_parity_errors(sd, True, x, d_emb, engine, dp, masks, fp64=True)
+    assert e["emb"] < TOL, e["emb"]
+    assert worst(e, "stage")[0] < TOL, worst(e, "stage")
+    # gradients: within the budget of the fp32 oracle, or as close to the float64 truth as the fp32 oracle itself is
+    # (tiny weights make the BatchNorm of a nearly-constant pre-activation ill-conditioned in ANY fp32 evaluation)
+    for k in [k for k in e if k.startswith("grad|")]:
+        name = k.split("|", 1)[1]
+        ok = e[k] < TOL or e["grad64|" + name] < max(3 * e["oracle32_vs_64|" + name], TOL)
+        assert ok, (name, e[k], e["grad64|" + name], e["oracle32_vs_64|" + name])
