@@ -45,7 +45,11 @@ struct Ws {
     float *m1, *m2;
     double* totals;            // [2*512 + 1] SyncBN: rank-local column totals + row count, all-reduced in place
     double* rscratch;          // [RP_SLABS][2][512] slab sums of the two-level partial reductions
-    unsigned int* tickets;     // [16] last-CTA tickets (zero-initialised once per workspace)
+    unsigned int* tickets;     // [64] last-CTA tickets, then (zeroed together, once per forward call):
+    unsigned int* abound;      // [16] bound on |BatchNorm output| per stage (bit pattern) -> scale of the A planes
+    unsigned int* wmax;        // [8] max |W| of the 7 linear layers and conv2 (bit pattern) -> scale of the W planes
+    float* ascale_inv;         // [16] 1 / (power-of-two scale of the stage's A planes)
+    float* wscale_inv;         // [8]  1 / (power-of-two scale of the layer's W planes; 7 = conv2)
     float *wpart;              // split-K weight-gradient partials
     float *Wc2, *Wc2d, *W1p;
     float *c1w, *c1b;          // copy of the conv1 parameters (parity tap)
@@ -116,7 +120,11 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     w.m2 = c.take<float>(F_FC);
     w.totals = c.take<double>(2 * F_FC + 8);
     w.rscratch = c.take<double>((size_t)RP_SLABS * 2 * F_FC);
-    w.tickets = c.take<unsigned int>(64);
+    w.tickets = c.take<unsigned int>(64 + 16 + 8);
+    w.abound = w.tickets + 64;
+    w.wmax = w.abound + 16;
+    w.ascale_inv = c.take<float>(16);
+    w.wscale_inv = c.take<float>(8);
     w.wpart = save ? c.take<float>(WPART_ELEMS) : nullptr;
     w.Wc2 = c.take<float>(64 * 192);
     w.Wc2d = c.take<float>(64 * 192);
@@ -204,13 +212,14 @@ int bn_finalize(const Ws& w, int l, int F, int P, int64_t R, const cp_encoder_te
         if (int rc = sync_totals(w, F, o, st)) return rc;
         bn_finalize_totals_kernel<<<(F + 511) / 512, 512, 0, st>>>(w.totals, F, p->bn_w[l], p->bn_b[l], p->bn_rm[l],
                                                                    p->bn_rv[l], o->bn_mode, o->bn_momentum, o->bn_eps,
-                                                                   w.mean[l], w.istd[l], w.scale[l], w.shift[l]);
+                                                                   w.mean[l], w.istd[l], w.scale[l], w.shift[l],
+                                                                   w.abound + l);
         CP_CHECK_LAUNCH();
         return CP_OK;
     }
     bn_finalize_kernel<<<dim3(F / 32, o->bn_mode == CP_BN_RUNNING ? 1 : RP_SLABS), 1024, 0, st>>>(
         w.pa, w.pb, P, F, R, p->bn_w[l], p->bn_b[l], p->bn_rm[l], p->bn_rv[l], o->bn_mode, o->bn_momentum, o->bn_eps,
-        w.mean[l], w.istd[l], w.scale[l], w.shift[l], w.rscratch, w.tickets);
+        w.mean[l], w.istd[l], w.scale[l], w.shift[l], w.rscratch, w.tickets, nullptr, w.abound + l);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
@@ -225,7 +234,8 @@ int bn_apply(const float* y, float* a, bool planes, int64_t R, const Ws& w, int 
     float* a_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(a) + (size_t)R * F) : nullptr;
     if (planes)
         bn_apply_kernel<F, true><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, a_lo, R, w.scale[l], w.shift[l], keep,
-                                                                     inv_keep, gen_p, seed, layer, seed_offset);
+                                                                     inv_keep, gen_p, seed, layer, seed_offset,
+                                                                     w.abound + l, w.ascale_inv + l);
     else
         bn_apply_kernel<F, false><<<ew_grid(R * (F / 4)), 256, 0, st>>>(y, a, nullptr, R, w.scale[l], w.shift[l], keep,
                                                                       inv_keep, gen_p, seed, layer, seed_offset);
@@ -368,10 +378,11 @@ bool opts_ok(const cp_encoder_opts* o) {
 // weight-gradient through the tensor-core split-K kernel + the shared re-layout / reduce kernel
 int tc_wgrad(const plane_t* Gh, const plane_t* Gl, int Mo, const plane_t* Ah, const plane_t* Al, int No, int64_t R,
              float* wpart, float* out, int mode, cudaStream_t st, const float* g_scale_inv, int fast = 0,
-             bool alone = false) {
+             bool alone = false, const float* a_scale_inv = nullptr) {
     int S = 0;
     CP_TRY(tcg::launch_tn(Gh, Gl, Mo, Mo, Ah, Al, No, No, R, wpart, WPART_ELEMS, &S, st, fast, alone));
-    wgrad_reduce_kernel<<<(unsigned)cp_cdiv((int64_t)Mo * No, 256), 256, 0, st>>>(wpart, S, Mo, No, out, mode, g_scale_inv);
+    wgrad_reduce_kernel<<<(unsigned)cp_cdiv((int64_t)Mo * No, 256), 256, 0, st>>>(wpart, S, Mo, No, out, mode, g_scale_inv,
+                                                                                  a_scale_inv);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
@@ -396,12 +407,21 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     const int64_t R12 = n * 12;
     const size_t conv_elems = (size_t)n * 12 * F_CONV, fc_elems = (size_t)n * F_FC;
 
-    CP_CUDA(cudaMemsetAsync(w.tickets, 0, 64 * sizeof(unsigned int), st));
+    CP_CUDA(cudaMemsetAsync(w.tickets, 0, (64 + 16 + 8) * sizeof(unsigned int), st));
+    if (tcE) {
+        WmaxArgs wa;
+        for (int l = 0; l < CP_N_FC; ++l) { wa.W[l] = p->fc_w[l]; wa.n[l] = F_FC * (l == 0 ? K_FC1 : F_FC); }
+        wa.W[7] = p->conv2_w; wa.n[7] = 64 * 64 * 9;
+        weights_absmax_kernel<<<dim3(48, 8), 256, 0, st>>>(wa, w.wmax);
+        CP_CHECK_LAUNCH();
+    }
     prep_weights_kernel<<<(F_FC * K_FC1 + 255) / 256, 256, 0, st>>>(p->conv2_w, p->fc_w[0], w.Wc2, w.Wc2d, w.W1p,
-                                                                    w.Wc2_lo, w.Wc2d_lo, p->conv1_w, p->conv1_b, w.c1w, w.c1b);
+                                                                    w.Wc2_lo, w.Wc2d_lo, p->conv1_w, p->conv1_b, w.c1w, w.c1b,
+                                                                    w.wmax, w.wscale_inv);
     CP_CHECK_LAUNCH();
     if (tcE) {
         PrepTcArgs a;
+        a.wmax = w.wmax; a.wscale_inv = w.wscale_inv;
         for (int l = 0; l < CP_N_FC; ++l) {
             a.W[l] = p->fc_w[l];
             a.Wh[l] = w.Wh[l]; a.Wl[l] = w.Wl[l]; a.Wth[l] = w.Wth[l]; a.Wtl[l] = w.Wtl[l];
@@ -419,7 +439,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     if (tcE)
         conv1_bn_apply_kernel<true><<<ew_grid(n * 16), 256, 0, st>>>(
             w.X0, n, p->conv1_w, p->conv1_b, w.scale[0], w.shift[0], w.A1,
-            reinterpret_cast<float*>(reinterpret_cast<plane_t*>(w.A1) + conv_elems));
+            reinterpret_cast<float*>(reinterpret_cast<plane_t*>(w.A1) + conv_elems), w.abound + 0, w.ascale_inv + 0);
     else
         conv1_bn_apply_kernel<false><<<ew_grid(n * 16), 256, 0, st>>>(w.X0, n, p->conv1_w, p->conv1_b, w.scale[0],
                                                                        w.shift[0], w.A1, nullptr);
@@ -428,7 +448,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     // conv2 as implicit GEMM [n*12, 192] x [64, 192]^T
     if (tcE) {
         CP_TRY(tcg::launch_conv_nt(hi_of(w.A1), lo_of(w.A1, conv_elems), n, hi_of(w.Wc2), hi_of(w.Wc2_lo), p->conv2_b,
-                                   w.Y2, w.pa, w.pb, 1, st, nullptr, fast));
+                                   w.Y2, w.pa, w.pb, 1, st, w.ascale_inv + 0, fast, w.wscale_inv + 7));
         CP_TRY(bn_finalize(w, 1, F_CONV, (int)cp_cdiv(n, tcg::CONV_WIN), R12, p, o, st));
     } else {
         CP_TRY((launch_nt<128, 64, 0, true>(w.A1, R12, 192, 64, w.Wc2, 64, 192, p->conv2_b, w.Y2, 64, w.pa, w.pb, 1, st)));
@@ -445,7 +465,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
         if (tcE) {
             const plane_t* in_lo = lo_of(in, l == 0 ? conv_elems : fc_elems);
             CP_TRY(tcg::launch_nt(hi_of(in), in_lo, n, K, K, w.Wh[l], w.Wl[l], F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb,
-                                  1, st, nullptr, fast));
+                                  1, st, w.ascale_inv + 1 + l, fast, nullptr, nullptr, 1.f, w.wscale_inv + l));
         } else {
             CP_TRY((launch_nt<128, 128, 0, false>(in, n, K, K, W, F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb, 1, st)));
         }
@@ -548,11 +568,12 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             // main stream: G0 = G1 . W_l
             CP_TRY(tcg::launch_nt(hi_of(g1(b)), g1lo(b, fc_elems), n, F_FC, F_FC, w.Wth[l], w.Wtl[l], K, F_FC, nullptr, w.G0,
                                   K, masked ? w.pa : nullptr, masked ? w.pb : nullptr, 0, st, gsi, fast,
-                                  algebraic ? w.gmax + 1 + l : nullptr, masked ? keep_below : nullptr, inv_keep));
+                                  algebraic ? w.gmax + 1 + l : nullptr, masked ? keep_below : nullptr, inv_keep,
+                                  w.wscale_inv + l));
             if (algebraic) {
                 if (last_side) CP_CUDA(cudaStreamWaitEvent(st, last_side, 0));     // w.wpart is shared with the side stream
                 CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, st, gsi, fast,
-                                true));
+                                true, w.ascale_inv + 1 + l));
                 const int s_below = 1 + l;             // BN stage of this layer's input
                 if (masked) {
                     // sum over the GEMM's per-tile partial rows -> w.m1 (scratch until the statistics kernel overwrites it)
@@ -578,7 +599,8 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             // persistent GEMMs cannot share an SM), i.e. alongside the HBM-bound BN-backward kernels of layer l-1
             CP_CUDA(cudaEventRecord(g_side.ready[b], st));
             CP_CUDA(cudaStreamWaitEvent(ss, g_side.ready[b], 0));
-            CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, ss, gsi, fast));
+            CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, ss, gsi, fast,
+                            false, w.ascale_inv + 1 + l));
             CP_CUDA(cudaEventRecord(g_side.done[b], ss));
             used[b] = true;
             last_side = g_side.done[b];
@@ -594,11 +616,12 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
         int S = 0;
         CP_TRY(tcg::launch_conv_tn(hi_of(w.A1), lo_of(w.A1, conv_elems), hi_of(g1(b)), g1lo(b, conv_elems), n, w.wpart,
                                    WPART_ELEMS, &S, ss, fast));
-        wgrad_reduce_kernel<<<(192 * 64 + 255) / 256, 256, 0, ss>>>(w.wpart, S, 192, 64, gr->conv2_w, 3, w.gscale_inv + 1);
+        wgrad_reduce_kernel<<<(192 * 64 + 255) / 256, 256, 0, ss>>>(w.wpart, S, 192, 64, gr->conv2_w, 3, w.gscale_inv + 1,
+                                                                    w.ascale_inv + 0);
         CP_CHECK_LAUNCH();
         CP_CUDA(cudaEventRecord(g_side.done[b], ss));
         CP_TRY(tcg::launch_conv_nt(hi_of(g1(b)), g1lo(b, conv_elems), n, hi_of(w.Wc2d), hi_of(w.Wc2d_lo), nullptr, w.G0,
-                                   nullptr, nullptr, 0, st, w.gscale_inv + 1, fast));
+                                   nullptr, nullptr, 0, st, w.gscale_inv + 1, fast, w.wscale_inv + 7));
         join_event = g_side.done[b];
     } else {
         for (int l = CP_N_FC - 1; l >= 0; --l) {

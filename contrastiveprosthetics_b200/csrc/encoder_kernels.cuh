@@ -135,11 +135,18 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 conv1_bn_apply_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ w9,
                       const float* __restrict__ bias, const float* __restrict__ scale,
-                      const float* __restrict__ shift, float* __restrict__ a, float* __restrict__ a_lo) {
+                      const float* __restrict__ shift, float* __restrict__ a, float* __restrict__ a_lo,
+                      const unsigned int* __restrict__ abound = nullptr, float* __restrict__ ascale_inv = nullptr) {
     const int qx = threadIdx.x % 16;
     const Conv1Taps t = conv1_taps(w9, bias, qx);
-    const float4 s = __ldg(reinterpret_cast<const float4*>(scale + qx * 4));
-    const float4 h = __ldg(reinterpret_cast<const float4*>(shift + qx * 4));
+    float4 s = __ldg(reinterpret_cast<const float4*>(scale + qx * 4));
+    float4 h = __ldg(reinterpret_cast<const float4*>(shift + qx * 4));
+    if (SPLIT) {        // planes of a1 * S (power of two: exact), S from the stage's BatchNorm output bound
+        const float S = plane_scale(__uint_as_float(__ldg(abound)));
+        s.x *= S; s.y *= S; s.z *= S; s.w *= S;
+        h.x *= S; h.y *= S; h.z *= S; h.w *= S;
+        if (blockIdx.x == 0 && threadIdx.x == 0) *ascale_inv = 1.f / S;
+    }
     for (int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 16; w < n;
          w += (int64_t)gridDim.x * (blockDim.x / 16)) {
         const Conv1Window xv = conv1_window(x, w);
@@ -314,6 +321,16 @@ __device__ __forceinline__ bool reduce_partials_2level(const float* const (&part
     return true;
 }
 
+// Bound on |gamma*xh + beta| of one BatchNorm channel, max-reduced over the channels of the stage into *abound (bit
+// pattern of a non-negative float, zeroed per forward call): |xh| <= 16 is assumed and plane_scale() leaves another
+// factor 2^8 of headroom, i.e. |xh| up to 4096 > sqrt(rows) for any batch this library is given.  The BN-apply kernels
+// turn it into the power-of-two scale of the stage's fp16 planes.
+__device__ __forceinline__ void bn_output_bound(unsigned int* abound, float gamma, float beta) {
+    if (!abound) return;
+    const float b = fmaf(fabsf(gamma), 16.f, fabsf(beta));
+    if (b > 0.f && b < 3.0e38f) atomicMax(abound, __float_as_uint(b));
+}
+
 // BatchNorm statistics -> mean, inv-std, and the affine (scale, shift) the apply kernels use:
 // y_bn = x*scale + shift with scale = gamma*istd, shift = beta - mean*scale (same arrangement as
 // torch's CPU batch-norm transform).  mode: CP_BN_BATCH / _BATCH_UPDATE / _RUNNING.
@@ -323,7 +340,8 @@ bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq
                    float* __restrict__ run_mean, float* __restrict__ run_var, int mode, float momentum,
                    float eps, float* __restrict__ mean_o, float* __restrict__ istd_o,
                    float* __restrict__ scale_o, float* __restrict__ shift_o, double* __restrict__ scratch,
-                   unsigned int* __restrict__ tickets, double* __restrict__ totals = nullptr) {
+                   unsigned int* __restrict__ tickets, double* __restrict__ totals = nullptr,
+                   unsigned int* __restrict__ abound = nullptr) {
     __shared__ double sm[32 * 33];
     const int col = blockIdx.x * 32 + threadIdx.x % 32, lane = threadIdx.x / 32;
     double mean, var;
@@ -362,6 +380,7 @@ bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq
     istd_o[col] = istd;
     scale_o[col] = sc;
     shift_o[col] = beta[col] - (float)mean * sc;
+    bn_output_bound(abound, gamma[col], beta[col]);
 }
 
 // SyncBN second half: statistics from the (all-reduced) totals [sum | sumsq | rows] of every rank
@@ -369,7 +388,8 @@ __global__ void __launch_bounds__(512)
 bn_finalize_totals_kernel(const double* __restrict__ totals, int F, const float* __restrict__ gamma,
                           const float* __restrict__ beta, float* __restrict__ run_mean, float* __restrict__ run_var,
                           int mode, float momentum, float eps, float* __restrict__ mean_o, float* __restrict__ istd_o,
-                          float* __restrict__ scale_o, float* __restrict__ shift_o) {
+                          float* __restrict__ scale_o, float* __restrict__ shift_o,
+                          unsigned int* __restrict__ abound = nullptr) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= F) return;
     const double R = totals[2 * F];
@@ -387,6 +407,7 @@ bn_finalize_totals_kernel(const double* __restrict__ totals, int F, const float*
     istd_o[col] = istd;
     scale_o[col] = sc;
     shift_o[col] = beta[col] - (float)mean * sc;
+    bn_output_bound(abound, gamma[col], beta[col]);
 }
 
 // SyncBN backward second half: m1 = sum g' / R, m2 = sum g'*xh / R over the rows of every rank
@@ -410,8 +431,14 @@ __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, float* __restrict__ a_lo, int64_t R,
                 const float* __restrict__ scale, const float* __restrict__ shift,
                 uint8_t* __restrict__ keep, float inv_keep, float gen_p, uint64_t seed, uint64_t layer,
-                const unsigned long long* __restrict__ seed_offset = nullptr) {
+                const unsigned long long* __restrict__ seed_offset = nullptr,
+                const unsigned int* __restrict__ abound = nullptr, float* __restrict__ ascale_inv = nullptr) {
     const int64_t total = R * (F / 4);
+    float S = 1.f;
+    if (SPLIT) {        // planes of a * S: S from the BatchNorm output bound (times the dropout scale)
+        S = plane_scale(__uint_as_float(__ldg(abound)) * inv_keep);
+        if (blockIdx.x == 0 && threadIdx.x == 0) *ascale_inv = 1.f / S;
+    }
     // device-resident step counter: lets a CUDA-graph replay of the same launch draw a fresh mask
     if (gen_p > 0.f && seed_offset) seed += __ldg(seed_offset) * 0x9E3779B97F4A7C15ull;
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < total;
@@ -433,7 +460,8 @@ bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, float* __res
             o.z = m.z ? o.z * inv_keep : 0.f; o.w = m.w ? o.w * inv_keep : 0.f;
         }
         if (SPLIT) {
-            split_store4(o, reinterpret_cast<plane_t*>(a), reinterpret_cast<plane_t*>(a_lo), v);
+            split_store4(make_float4(o.x * S, o.y * S, o.z * S, o.w * S), reinterpret_cast<plane_t*>(a),
+                         reinterpret_cast<plane_t*>(a_lo), v);
         } else {
             reinterpret_cast<float4*>(a)[v] = o;
         }
@@ -553,8 +581,7 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, in
         km = kred[0];
 #pragma unroll
         for (int w8 = 1; w8 < 8; ++w8) km = fmaxf(km, kred[w8]);
-        const float bound = km * __uint_as_float(__ldg(gmax_bits)) * 18.f;
-        if (bound > 0.f && bound < 3.0e38f) S = exp2f(8.f - ceilf(log2f(bound)));
+        S = plane_scale(km * __uint_as_float(__ldg(gmax_bits)) * 18.f);
         if (blockIdx.x == 0 && threadIdx.x == 0) *gscale_inv = 1.f / S;
     }
     float sb[4] = {0, 0, 0, 0};
@@ -649,8 +676,10 @@ bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restr
             // second identity still holds:  sum g' xh = (sum_k W dW - beta sum g') / gamma
             const double sum_g = sum_g_in ? (double)sum_g_in[f] : sa;
             const double sum_gx = ga != 0.0 ? (stt - be * sum_g) / ga : 0.0;
-            // gamma == 0: d_gamma is not observable from dW -> the caller's (otherwise skipped) reduce pass runs
-            if (ga == 0.0 && zero_gamma_flag) atomicOr(zero_gamma_flag, 1u);
+            // gamma == 0: d_gamma is not observable from dW -> the caller's (otherwise skipped) reduce pass runs.
+            // |gamma| << |beta| (or tiny): the subtraction above cancels to a 1/gamma-amplified remainder -- an
+            // amplification beyond 16x (a 5e-7 weight gradient -> 1e-5) takes the same exact path
+            if (zero_gamma_flag && (fabs(ga) * 16.0 < fabs(be) || fabs(ga) < 9.5e-7)) atomicOr(zero_gamma_flag, 1u);
             const double rows = (double)R * GROUP;
             m1[f] = (float)(sum_g / rows);
             m2[f] = (float)(sum_gx / rows);
@@ -846,13 +875,37 @@ proj_bwd_weight_kernel(const float* __restrict__ d, const float* __restrict__ a,
 // W1p [o][p*64+c]    = fc1_w[o][c*12+p]              fc1 on the position-major flatten
 // Wc2_lo / Wc2d_lo non-null: write the fp16 (hi, lo) planes (tensor-core engine) instead of fp32
 // c1w / c1b: workspace copy of the conv1 parameters (the parity tap recomputes the unsaved conv1 activation)
+// max |W| of the 7 linear weights (blockIdx.y = 0..6) and of conv2's middle kernel row (7) -> wmax[8] (bit patterns,
+// zeroed per forward call): the power-of-two scales of the weight planes
+struct WmaxArgs { const float* W[8]; int n[8]; };
+__global__ void __launch_bounds__(256)
+weights_absmax_kernel(const WmaxArgs a, unsigned int* __restrict__ wmax) {
+    const int l = blockIdx.y;
+    float m = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n[l]; i += gridDim.x * blockDim.x) {
+        // conv2: only the middle row of the 3 x 3 kernels ever meets data
+        if (l == 7 && (i % 9) / 3 != 1) continue;
+        m = fmaxf(m, fabsf(__ldg(a.W[l] + i)));
+    }
+    m = warp_max(m);
+    if (threadIdx.x % 32 == 0 && m > 0.f && m < 3.0e38f) atomicMax(wmax + l, __float_as_uint(m));
+}
+// S with max|W| * S in (1/2, 1]
+__device__ __forceinline__ float weight_scale(const unsigned int* wmax_slot) {
+    const float m = __uint_as_float(__ldg(wmax_slot));
+    return m > 0.f ? exp2f(-ceilf(log2f(m))) : 1.f;
+}
+
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(const float* __restrict__ conv2_w, const float* __restrict__ fc1_w,
                     float* __restrict__ Wc2, float* __restrict__ Wc2d, float* __restrict__ W1p,
                     float* __restrict__ Wc2_lo, float* __restrict__ Wc2d_lo,
                     const float* __restrict__ conv1_w, const float* __restrict__ conv1_b,
-                    float* __restrict__ c1w, float* __restrict__ c1b) {
+                    float* __restrict__ c1w, float* __restrict__ c1b,
+                    const unsigned int* __restrict__ wmax = nullptr, float* __restrict__ wscale_inv = nullptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float S2 = Wc2_lo ? weight_scale(wmax + 7) : 1.f;
+    if (Wc2_lo && i == 0) wscale_inv[7] = 1.f / S2;
     if (i < 64 * 9) c1w[i] = __ldg(conv1_w + i);
     if (i < 64) c1b[i] = __ldg(conv1_b + i);
     if (i < 64 * 192) {
@@ -861,8 +914,8 @@ prep_weights_kernel(const float* __restrict__ conv2_w, const float* __restrict__
         // same flat index read as [c'][tap*64 + o'] with c' = o, o' = c
         const float b = __ldg(conv2_w + (c * 64 + o) * 9 + 3 + (2 - tap));
         if (Wc2_lo) {
-            split_f16(a, reinterpret_cast<plane_t*>(Wc2)[i], reinterpret_cast<plane_t*>(Wc2_lo)[i]);
-            split_f16(b, reinterpret_cast<plane_t*>(Wc2d)[i], reinterpret_cast<plane_t*>(Wc2d_lo)[i]);
+            split_f16(a * S2, reinterpret_cast<plane_t*>(Wc2)[i], reinterpret_cast<plane_t*>(Wc2_lo)[i]);
+            split_f16(b * S2, reinterpret_cast<plane_t*>(Wc2d)[i], reinterpret_cast<plane_t*>(Wc2d_lo)[i]);
         } else {
             Wc2[i] = a;
             Wc2d[i] = b;
@@ -881,18 +934,22 @@ prep_weights_kernel(const float* __restrict__ conv2_w, const float* __restrict__
 struct PrepTcArgs {
     const float* W[7];
     plane_t *Wh[7], *Wl[7], *Wth[7], *Wtl[7];
+    const unsigned int* wmax;      // [8] from weights_absmax_kernel
+    float* wscale_inv;             // [8] 1 / (power-of-two scale of the layer's weight planes)
 };
 __global__ void __launch_bounds__(256)
 prep_weights_tc_kernel(const PrepTcArgs a) {
     const int l = blockIdx.y;
     const int K = l == 0 ? 768 : 512;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float S = weight_scale(a.wmax + l);
+    if (i == 0) a.wscale_inv[l] = 1.f / S;
     if (i >= 512 * K) return;
     const int o = i / K, k = i % K;
     // fc1 runs on the position-major flatten: column p*64+c of the operand is column c*12+p of the parameter
     const float w = l == 0 ? __ldg(a.W[0] + o * 768 + (k % 64) * 12 + k / 64) : __ldg(a.W[l] + i);
     plane_t h, lo;
-    split_f16(w, h, lo);
+    split_f16(w * S, h, lo);
     a.Wh[l][i] = h; a.Wl[l][i] = lo;
     a.Wth[l][(size_t)k * 512 + o] = h; a.Wtl[l][(size_t)k * 512 + o] = lo;
 }
@@ -902,10 +959,11 @@ prep_weights_tc_kernel(const PrepTcArgs a) {
 // 3: conv2 from the transposed tensor-core partials P[z][256][64] (row tap*64+c, column o)
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ P, int S, int Mo, int No, float* __restrict__ out, int mode,
-                    const float* __restrict__ scale = nullptr) {
+                    const float* __restrict__ scale = nullptr, const float* __restrict__ scale2 = nullptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Mo * No) return;
-    const double sc = scale ? (double)__ldg(scale) : 1.0;      // undoes the power-of-two scale of the G planes
+    // undoes the power-of-two scales of the G planes and of the activation planes
+    const double sc = (scale ? (double)__ldg(scale) : 1.0) * (scale2 ? (double)__ldg(scale2) : 1.0);
     if (mode == 3) {
         const int m = i / 64, o = i % 64;                 // Mo = 192 rows used of 256, No = 64
         double s = 0.0;

@@ -95,6 +95,7 @@ struct NtArgs {
     const uint8_t* keep;            // non-null (with psum): C is the gradient w.r.t. a dropout output; psum then holds the
     float inv_keep;                 // column sums of C * keep / (1-p) (mask [M][N] bytes), psq is not written, and
                                     // gmax_bits takes the masked maximum
+    const float* out_scale2;        // second device scalar multiplied into the result (the other operand's plane scale), or null
 };
 
 // warp-transposing reduction: on return v[0] of lane l = sum over the 32 lanes of their v[l]
@@ -245,7 +246,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp % 4;                      // TMEM lane quadrant this warp may access
         const int et = threadIdx.x - 64;             // 0..127
-        const float oscale = g.out_scale ? __ldg(g.out_scale) : 1.f;
+        const float oscale = (g.out_scale ? __ldg(g.out_scale) : 1.f) * (g.out_scale2 ? __ldg(g.out_scale2) : 1.f);
         const float cscale = CP_LO_INV * oscale;
         int it = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
@@ -469,7 +470,7 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
         const int q = warp % 4;                      // TMEM lane quadrant
         const int half = (warp - 2) / 4;             // column half: 0 -> 0..63, 1 -> 64..127
         const int et = threadIdx.x - 64;             // 0..255
-        const float oscale = g.out_scale ? __ldg(g.out_scale) : 1.f;
+        const float oscale = (g.out_scale ? __ldg(g.out_scale) : 1.f) * (g.out_scale2 ? __ldg(g.out_scale2) : 1.f);
         const float cscale = CP_LO_INV * oscale;
         int it = 0;
         for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
@@ -977,7 +978,8 @@ static bool g_use_pair = true;       // CTA-pair (cta_group::2) kernel for the p
 inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K, int lda, const plane_t* B_hi,
                      const plane_t* B_lo, int N, int ldb, const float* bias, float* C, int ldc, float* psum,
                      float* psq, int relu, cudaStream_t st, const float* out_scale = nullptr, int fast = 0,
-                     unsigned int* gmax_bits = nullptr, const uint8_t* keep = nullptr, float inv_keep = 1.f) {
+                     unsigned int* gmax_bits = nullptr, const uint8_t* keep = nullptr, float inv_keep = 1.f,
+                     const float* out_scale2 = nullptr) {
     if (K % BK != 0 || N % BN != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldc % 4 != 0) return CP_ERR_ARG;
     if (keep && (ldc != N || ((uintptr_t)keep) % 16 != 0)) return CP_ERR_ARG;     // mask laid out like a dense [M][N] C
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_out;
@@ -987,7 +989,7 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
     if ((rc = make_tmap_2d(&ta_lo, A_lo, M, K, lda, BM)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi, B_hi, N, K, ldb, BN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, N, K, ldb, BN)) != CP_OK) return rc;
-    NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu, out_scale, fast, gmax_bits, keep, inv_keep};
+    NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu, out_scale, fast, gmax_bits, keep, inv_keep, out_scale2};
     if (g_use_pair && M > BM) {
         CUtensorMap tb_hi2, tb_lo2;                                   // B boxes of 64 rows: half a tile per CTA
         if ((rc = make_tmap_2d(&tb_hi2, B_hi, N, K, ldb, BN / 2)) != CP_OK) return rc;
@@ -1011,7 +1013,8 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
 // X planes are [windows][12][64], B planes [64][192]; partial statistics rows = ceil(windows/10)
 inline int launch_conv_nt(const plane_t* X_hi, const plane_t* X_lo, int64_t windows, const plane_t* B_hi,
                           const plane_t* B_lo, const float* bias, float* C, float* psum, float* psq, int relu,
-                          cudaStream_t st, const float* out_scale = nullptr, int fast = 0) {
+                          cudaStream_t st, const float* out_scale = nullptr, int fast = 0,
+                          const float* out_scale2 = nullptr) {
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_out;
     int rc;
     if ((rc = make_tmap_out(&tc_out, C, windows * 12, 64, 64, CONV_ROWS)) != CP_OK) return rc;
@@ -1019,7 +1022,7 @@ inline int launch_conv_nt(const plane_t* X_hi, const plane_t* X_lo, int64_t wind
     if ((rc = make_tmap_conv(&ta_lo, X_lo, windows, CONV_WIN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi, B_hi, 64, 192, 192, 64)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, 64, 192, 192, 64)) != CP_OK) return rc;
-    NtArgs g{C, 64, bias, psum, psq, windows * 12, 64, 192, relu, out_scale, fast, nullptr, nullptr, 1.f};
+    NtArgs g{C, 64, bias, psum, psq, windows * 12, 64, 192, relu, out_scale, fast, nullptr, nullptr, 1.f, out_scale2};
     return fast ? launch_nt_cfg<64, true, true>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st)
                 : launch_nt_cfg<64, true, false>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st);
 }
@@ -1056,8 +1059,14 @@ inline int launch_conv_tn(const plane_t* X_hi, const plane_t* X_lo, const plane_
 
 }  // namespace tcg
 
-// x*scale -> (hi, lo) fp16 planes: hi = fp16(x), lo = fp16((x - hi) * 2048); x = hi + lo/2048 to 22 bits.
-// The clamp keeps hi finite for |x| beyond the fp16 range (never reached by BatchNorm outputs or weights).
+// x -> (hi, lo) fp16 planes: hi = fp16(x), lo = fp16((x - hi) * 2048); x = hi + lo/2048 to 22 bits.
+// Every producer multiplies by a per-tensor power of two first (plane_scale below: activations from the BatchNorm
+// affine's bound, weights from max|W|, gradients from max|g'|) so that the values sit in fp16's normal range whatever
+// the magnitude of the tensor; the clamp only keeps hi finite for a value 256x beyond its bound.
+// S with bound * S = 2^8 (exact power of two; 1 for a zero / non-finite bound)
+__device__ __forceinline__ float plane_scale(float bound) {
+    return (bound > 0.f && bound < 3.0e38f) ? exp2f(8.f - ceilf(log2f(bound))) : 1.f;
+}
 __device__ __forceinline__ void split_f16(float x, plane_t& hi, plane_t& lo) {
     x = fminf(fmaxf(x, -65000.f), 65000.f);
     hi = __float2half_rn(x);

@@ -256,7 +256,7 @@ proj_bwd_apply_kernel(const float* __restrict__ y, const uint8_t* __restrict__ k
 #pragma unroll
         for (int w8 = 1; w8 < 8; ++w8) km = fmaxf(km, kred[w8]);
         const float bound = km * __uint_as_float(__ldg(gmax_bits)) * 18.f;
-        if (bound > 0.f && bound < 3.0e38f) S = exp2f(8.f - ceilf(log2f(bound)));
+        S = plane_scale(bound);
         if (blockIdx.x == 0 && threadIdx.x == 0) *gscale_inv = 1.f / S;
     }
     float4 sb = make_float4(0.f, 0.f, 0.f, 0.f);

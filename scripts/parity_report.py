@@ -39,7 +39,7 @@ def main():
              ("n1640_gamma1e-3", 1640, True, 0.5, 1e-3, 1.0, True), ("n1640_gamma3e2", 1640, True, 0.5, 3e2, 1.0, True),
              ("n1640_weight1e-4", 1640, True, 0.5, 1.0, 1e-4, True), ("n1640_weight1e3", 1640, True, 0.5, 1.0, 1e3, True)]
     if args.full:
-        cases.append(("n167936_adabn_dp0.5_C2", 4096 * 41, True, 0.5, 1.0, 1.0, False))
+        cases.append(("n167936_adabn_dp0.5_C2", 4096 * 41, True, 0.5, 1.0, 1.0, True))
     report = {"what": "norm-wise relative error per tensor, CUDA path vs CPU oracle", "tolerance": 1e-5, "cases": {}}
     for name, n, adabn, dp, gamma, weight, fp64 in cases:
         sd = scale_state(perturbed_state(3, adabn), adabn, gamma, weight)
@@ -55,6 +55,8 @@ def main():
                        "worst_grad_unconditioned": worst(e, "grad_unconditioned|"),
                        "relu_flip_fraction": e["relu_flip_fraction"]}
             if fp64:
+                summary["emb_vs_fp64"] = e["emb64"]
+                summary["emb_fp32_oracle_vs_fp64"] = e["emb_oracle32_vs_64"]
                 summary["worst_grad_vs_fp64"] = worst(e, "grad64|")
                 summary["worst_fp32_oracle_vs_fp64"] = worst(e, "oracle32_vs_64|")
             report["cases"][f"{name}|{eng_name}"] = {"summary": summary, "per_tensor": e, "seconds": time.time() - t0}

@@ -96,12 +96,13 @@ def encoder_parity_errors(sd, adabn, x, d_emb, engine, dp=0.0, masks=None, fp64=
     del ot
     for k in g32:
         out[f"grad_unconditioned|{k}"] = rel_err(got[k], g32[k])
-    _, g32p, _ = oracle(torch.float32, pattern, False)
+    e32p, g32p, _ = oracle(torch.float32, pattern, False)
     for k in g32p:
         out[f"grad|{k}"] = rel_err(got[k], g32p[k])
     if fp64:
         e64, g64, _ = oracle(torch.float64, pattern, False)
         out["emb64"] = rel_err(emb, e64)
+        out["emb_oracle32_vs_64"] = rel_err(e32p, e64)
         for k in g64:
             out[f"grad64|{k}"] = rel_err(got[k], g64[k])
             out[f"oracle32_vs_64|{k}"] = rel_err(g32p[k], g64[k])

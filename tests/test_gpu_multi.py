@@ -96,7 +96,7 @@ for adabn in (True, False):
     print("rank", rank, "adabn", adabn, "syncbn worst grad rel", worst)
 torch.cuda.synchronize()
 dist.barrier()
-print("rank", rank, "ok")
+sys.stdout.write(f"rank {rank} ok\n"); sys.stdout.flush()          # one write: the ranks share the pipe
 dist.destroy_process_group()
 '''
 
@@ -157,7 +157,7 @@ assert (sh_pred != one_pred).mean() < 1e-3 and abs(sh_acc - one_acc) < 1e-3, (sh
 #     is the one its owner computed
 vals = np.load(f"{tmp}/data/cross_val_values.npy"); keys = np.load(f"{tmp}/data/cross_val_keys.npy")
 assert vals.shape == (3, 2) and keys.shape == (3, 7) and np.isfinite(vals).all()
-print("rank", rank, "ok", loss, acc)
+sys.stdout.write(f"rank {rank} ok {loss} {acc}\n"); sys.stdout.flush()
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -173,7 +173,7 @@ def _run_two_ranks(tmp_path, worker, port, timeout=900):
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          env=env, capture_output=True, text=True, timeout=timeout)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count(" ok") == 2, out.stdout[-2000:]
+    assert out.stdout.count(" ok") == 2, out.stdout[-2000:] + out.stderr[-2000:]
     return out.stdout
 
 
