@@ -32,13 +32,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "parity_r2.json"))
     ap.add_argument("--full", action="store_true", help="include the C2-size case (167,936 windows)")
+    ap.add_argument("--only_full", action="store_true", help="only the C2-size case")
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count() or 8)
     cases = [("n328_adabn_dp0", 328, True, 0.0, 1.0, 1.0, True), ("n328_stockbn_dp0", 328, False, 0.0, 1.0, 1.0, True),
              ("n4100_adabn_dp0.5", 4100, True, 0.5, 1.0, 1.0, True), ("n20992_adabn_dp0.5", 20992, True, 0.5, 1.0, 1.0, True),
              ("n1640_gamma1e-3", 1640, True, 0.5, 1e-3, 1.0, True), ("n1640_gamma3e2", 1640, True, 0.5, 3e2, 1.0, True),
              ("n1640_weight1e-4", 1640, True, 0.5, 1.0, 1e-4, True), ("n1640_weight1e3", 1640, True, 0.5, 1.0, 1e3, True)]
-    if args.full:
+    if args.only_full:
+        cases = []
+    if args.full or args.only_full:
         cases.append(("n167936_adabn_dp0.5_C2", 4096 * 41, True, 0.5, 1.0, 1.0, True))
     report = {"what": "norm-wise relative error per tensor, CUDA path vs CPU oracle", "tolerance": 1e-5, "cases": {}}
     for name, n, adabn, dp, gamma, weight, fp64 in cases:

@@ -103,9 +103,17 @@ def encoder_parity_errors(sd, adabn, x, d_emb, engine, dp=0.0, masks=None, fp64=
         e64, g64, _ = oracle(torch.float64, pattern, False)
         out["emb64"] = rel_err(emb, e64)
         out["emb_oracle32_vs_64"] = rel_err(e32p, e64)
+        num = den = num32 = 0.0
         for k in g64:
             out[f"grad64|{k}"] = rel_err(got[k], g64[k])
             out[f"oracle32_vs_64|{k}"] = rel_err(g32p[k], g64[k])
+            out[f"norm64|{k}"] = float(g64[k].norm())
+            num += float((got[k].double() - g64[k]).norm()) ** 2
+            num32 += float((g32p[k].double() - g64[k]).norm()) ** 2
+            den += float(g64[k].norm()) ** 2
+        # the whole gradient as ONE vector (what an optimizer step sees)
+        out["grad64_global"] = (num / den) ** 0.5
+        out["oracle32_vs_64_global"] = (num32 / den) ** 0.5
     return out
 
 
