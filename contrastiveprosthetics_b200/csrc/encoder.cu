@@ -61,6 +61,7 @@ struct Ws {
     unsigned int* gmax;        // [16] max |g'| per backward stage (bit pattern) + [16] gamma == 0 flags per stage,
                                // zeroed per backward call
     float* gscale_inv;         // [16] 1 / (power-of-two scale of the stage's G1 planes)
+    double* cancel;            // [16][WS_CANCEL_PARTS][2] cancellation estimates of the reduce-free BN backward
     size_t bytes;
 };
 
@@ -138,6 +139,7 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     for (int l = 0; l < CP_N_FC; ++l) w.Wh[l] = w.Wl[l] = w.Wth[l] = w.Wtl[l] = nullptr;
     w.gmax = c.take<unsigned int>(32);
     w.gscale_inv = c.take<float>(16);
+    w.cancel = c.take<double>(16 * WS_CANCEL_PARTS * 2);
     if (o->engine != CP_ENGINE_SIMT) {
         w.Wc2_lo = c.take<float>(64 * 192);
         w.Wc2d_lo = c.take<float>(64 * 192);
@@ -255,14 +257,15 @@ int bn_backward(const float* g, const float* y, float* gz, bool planes, int64_t 
     float* gz_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)R * F) : nullptr;
     // stats_ready: the two kernels below still launch, but return at once unless a gamma == 0 was met (flag w.gmax[16 + l])
     const unsigned int* run_flag = stats_ready ? w.gmax + 16 + l : nullptr;
+    const double* cancel = stats_ready ? w.cancel + (size_t)l * WS_CANCEL_PARTS * 2 : nullptr;
     {
         bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb, nullptr,
-                                                   planes ? w.gmax + l : nullptr, run_flag);
+                                                   planes ? w.gmax + l : nullptr, run_flag, cancel);
         CP_CHECK_LAUNCH();
         const bool sync = o->allreduce != nullptr;
         bn_bwd_finalize_kernel<<<dim3(F / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta,
                                                                         w.rscratch, w.tickets, sync ? w.totals : nullptr,
-                                                                        run_flag);
+                                                                        run_flag, cancel);
         CP_CHECK_LAUNCH();
         if (sync) {
             if (int rc = sync_totals(w, F, o, st)) return rc;
@@ -581,15 +584,18 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
                     CP_CHECK_LAUNCH();
                     bn_bwd_stats_from_wgrad_kernel<1><<<F_FC / WgradStats<1>::COLS, 512, 0, st>>>(
                         p->fc_w[l], gr->fc_w[l], gr->fc_b[l], F_FC, F_FC, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
-                        gr->bn_w[s_below], gr->bn_b[s_below], w.m1, w.gmax + 16 + s_below);
+                        gr->bn_w[s_below], gr->bn_b[s_below], w.m1, w.gmax + 16 + s_below,
+                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2);
                 } else if (l == 0)
                     bn_bwd_stats_from_wgrad_kernel<12><<<K_FC1 / WgradStats<12>::COLS, 512, 0, st>>>(
                         p->fc_w[0], gr->fc_w[0], gr->fc_b[0], F_FC, K_FC1, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
-                        gr->bn_w[s_below], gr->bn_b[s_below], nullptr, w.gmax + 16 + s_below);
+                        gr->bn_w[s_below], gr->bn_b[s_below], nullptr, w.gmax + 16 + s_below,
+                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2);
                 else
                     bn_bwd_stats_from_wgrad_kernel<1><<<F_FC / WgradStats<1>::COLS, 512, 0, st>>>(
                         p->fc_w[l], gr->fc_w[l], gr->fc_b[l], F_FC, F_FC, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
-                        gr->bn_w[s_below], gr->bn_b[s_below], nullptr, w.gmax + 16 + s_below);
+                        gr->bn_w[s_below], gr->bn_b[s_below], nullptr, w.gmax + 16 + s_below,
+                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2);
                 CP_CHECK_LAUNCH();
                 stats_ready = true;
                 continue;

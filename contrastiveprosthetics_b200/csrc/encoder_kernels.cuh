@@ -472,16 +472,35 @@ bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, float* __res
 // g' = g * keep/(1-p);  xh = (y - mean)*istd;  partials: sum g', sum g'*xh
 // post != null: the block is Linear -> BN -> ReLU (glove tower block 0, models.py:398-400): `post` is the
 // block output relu(bn(y)), g' = g * 1[post > 0], and no ReLU mask follows the BN backward.
+// Does the stage whose BN-backward sums were derived from the next layer's parameter gradients
+// (bn_bwd_stats_from_wgrad_kernel) have to be recomputed the long way?  Yes when a gamma == 0 was met (*flag), or when
+// the derivation cancelled badly: `cancel` holds WS_CANCEL_PARTS per-CTA pairs (E^2, D^2) with E_f = (|sum W dW| +
+// |beta sum g'|) / |gamma| the magnitude of the terms and D_f = |sum g' xh| the result -- a weight-gradient error eps
+// becomes eps * E / D in d_gamma (norm-wise over the stage); beyond 8x the exact reduce pass runs.  Summed in a fixed
+// order: every thread of every consumer reaches the same decision.
+#define WS_CANCEL_PARTS 32
+__device__ __forceinline__ bool stage_needs_exact(const unsigned int* __restrict__ flag, const double* __restrict__ cancel) {
+    if (__ldg(flag) != 0u) return true;
+    if (!cancel) return false;
+    double E = 0.0, D = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < WS_CANCEL_PARTS; ++i) {
+        E += __ldg(cancel + 2 * i);
+        D += __ldg(cancel + 2 * i + 1);
+    }
+    return E > 64.0 * D;
+}
+
 template <int F>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t R,
                      const uint8_t* __restrict__ keep, float inv_keep, const float* __restrict__ mean,
                      const float* __restrict__ istd, float* __restrict__ p1, float* __restrict__ p2,
                      const float* __restrict__ post = nullptr, unsigned int* __restrict__ gmax_bits = nullptr,
-                     const unsigned int* __restrict__ run_flag = nullptr) {
+                     const unsigned int* __restrict__ run_flag = nullptr, const double* __restrict__ cancel = nullptr) {
     __shared__ float red[ColMap<F>::RY * F];
-    // fallback pass of the reduce-free BN backward: runs only when bn_bwd_stats_from_wgrad_kernel met a gamma == 0
-    if (run_flag && __ldg(run_flag) == 0u) return;
+    // fallback pass of the reduce-free BN backward: runs only when bn_bwd_stats_from_wgrad_kernel asked for it
+    if (run_flag && !stage_needs_exact(run_flag, cancel)) return;
     float gmax = 0.f;                     // max |g'| (feeds the fp16 plane scale of bn_bwd_apply_kernel<.., true>)
     const int qx = threadIdx.x % ColMap<F>::QX, ry = threadIdx.x / ColMap<F>::QX;
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + qx * 4));
@@ -529,9 +548,10 @@ __global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int P, int F, int64_t R,
                        float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ d_gamma,
                        float* __restrict__ d_beta, double* __restrict__ scratch, unsigned int* __restrict__ tickets,
-                       double* __restrict__ totals = nullptr, const unsigned int* __restrict__ run_flag = nullptr) {
+                       double* __restrict__ totals = nullptr, const unsigned int* __restrict__ run_flag = nullptr,
+                       const double* __restrict__ cancel = nullptr) {
     __shared__ double sm[32 * 33];
-    if (run_flag && __ldg(run_flag) == 0u) return;          // see bn_bwd_reduce_kernel
+    if (run_flag && !stage_needs_exact(run_flag, cancel)) return;          // see bn_bwd_reduce_kernel
     const int col = blockIdx.x * 32 + threadIdx.x % 32;
     const float* const parts[2] = {p1, p2};
     double tot[2];
@@ -644,9 +664,11 @@ bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restr
                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                float* m1, float* __restrict__ m2, float* __restrict__ d_gamma,
                                float* __restrict__ d_beta, const float* sum_g_in = nullptr,
-                               unsigned int* __restrict__ zero_gamma_flag = nullptr) {
+                               unsigned int* __restrict__ zero_gamma_flag = nullptr,
+                               double* __restrict__ cancel = nullptr /*[gridDim.x][2]: see stage_needs_exact*/) {
     constexpr int COLS = WgradStats<GROUP>::COLS;
     __shared__ double s_a[WS_LANES][COLS], s_t[WS_LANES][COLS];
+    __shared__ double s_E[COLS], s_D[COLS];
     const int cx = threadIdx.x % 32, ky = threadIdx.x / 32;
     const int col = blockIdx.x * COLS + cx;
     double a = 0.0, t = 0.0;
@@ -676,15 +698,29 @@ bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restr
             // second identity still holds:  sum g' xh = (sum_k W dW - beta sum g') / gamma
             const double sum_g = sum_g_in ? (double)sum_g_in[f] : sa;
             const double sum_gx = ga != 0.0 ? (stt - be * sum_g) / ga : 0.0;
-            // gamma == 0: d_gamma is not observable from dW -> the caller's (otherwise skipped) reduce pass runs.
-            // |gamma| << |beta| (or tiny): the subtraction above cancels to a 1/gamma-amplified remainder -- an
-            // amplification beyond 16x (a 5e-7 weight gradient -> 1e-5) takes the same exact path
-            if (zero_gamma_flag && (fabs(ga) * 16.0 < fabs(be) || fabs(ga) < 9.5e-7)) atomicOr(zero_gamma_flag, 1u);
+            // gamma == 0: d_gamma is not observable from dW -> the caller's (otherwise skipped) reduce pass runs
+            if (ga == 0.0 && zero_gamma_flag) atomicOr(zero_gamma_flag, 1u);
+            // magnitude of the cancelling terms vs the result (stage_needs_exact)
+            const double Ef = ga != 0.0 ? (fabs(stt) + fabs(be * sum_g)) / fabs(ga) : 0.0;
+            s_E[threadIdx.x] = fmin(Ef * Ef, 1e300);
+            s_D[threadIdx.x] = fmin(sum_gx * sum_gx, 1e300);
             const double rows = (double)R * GROUP;
             m1[f] = (float)(sum_g / rows);
             m2[f] = (float)(sum_gx / rows);
             if (d_beta) d_beta[f] = (float)sum_g;
             if (d_gamma) d_gamma[f] = (float)sum_gx;
+        } else {
+            s_E[threadIdx.x] = 0.0;
+            s_D[threadIdx.x] = 0.0;
+        }
+    }
+    if (cancel) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double E = 0.0, D = 0.0;
+            for (int i = 0; i < NFEAT; ++i) { E += s_E[i]; D += s_D[i]; }
+            cancel[2 * blockIdx.x] = E;
+            cancel[2 * blockIdx.x + 1] = D;
         }
     }
 }
