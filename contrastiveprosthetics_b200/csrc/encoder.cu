@@ -21,6 +21,7 @@
 // slot, hi in the first half and lo in the second -- that the TMA-fed GEMMs consume directly, and the weights
 // are split (and transposed for the data gradient) once per call.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -62,6 +63,10 @@ struct Ws {
                                // zeroed per backward call
     float* gscale_inv;         // [16] 1 / (power-of-two scale of the stage's G1 planes)
     double* cancel;            // [16][WS_CANCEL_PARTS][2] cancellation estimates of the reduce-free BN backward
+    unsigned int* l1max;       // [8] max column L1 norm of the linear weights (bit pattern; zeroed with tickets, forward)
+    unsigned int* g1max;       // [16] max |pre-activation gradient| per stage (bit pattern; zeroed with gmax, backward)
+    float* coef;               // [3][512] c1, c2, c3 of the fused BN-backward epilogue (one stage at a time)
+    float* gz_bound;           // [16] bound on |gz| per stage
     size_t bytes;
 };
 
@@ -121,9 +126,10 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     w.m2 = c.take<float>(F_FC);
     w.totals = c.take<double>(2 * F_FC + 8);
     w.rscratch = c.take<double>((size_t)RP_SLABS * 2 * F_FC);
-    w.tickets = c.take<unsigned int>(64 + 16 + 8);
+    w.tickets = c.take<unsigned int>(64 + 16 + 8 + 8);
     w.abound = w.tickets + 64;
     w.wmax = w.abound + 16;
+    w.l1max = w.wmax + 8;
     w.ascale_inv = c.take<float>(16);
     w.wscale_inv = c.take<float>(8);
     w.wpart = save ? c.take<float>(WPART_ELEMS) : nullptr;
@@ -137,7 +143,10 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
                    : nullptr;
     w.Wc2_lo = w.Wc2d_lo = w.G1b = nullptr;
     for (int l = 0; l < CP_N_FC; ++l) w.Wh[l] = w.Wl[l] = w.Wth[l] = w.Wtl[l] = nullptr;
-    w.gmax = c.take<unsigned int>(32);
+    w.gmax = c.take<unsigned int>(48);
+    w.g1max = w.gmax + 32;
+    w.coef = c.take<float>(3 * F_FC);
+    w.gz_bound = c.take<float>(16);
     w.gscale_inv = c.take<float>(16);
     w.cancel = c.take<double>(16 * WS_CANCEL_PARTS * 2);
     if (o->engine != CP_ENGINE_SIMT) {
@@ -247,35 +256,46 @@ int bn_apply(const float* y, float* a, bool planes, int64_t R, const Ws& w, int 
 
 // BN backward + ReLU backward of stage l:  g (grad w.r.t. stage output A) -> gz (grad w.r.t. the
 // pre-activation), d_gamma, d_beta, d_bias
+// BN backward sums of stage l:  m1 = mean g', m2 = mean g' xh, d_gamma, d_beta.
+// stats_ready: w.m1 / w.m2 / d_gamma / d_beta were already produced from the next layer's parameter gradients
+// (bn_bwd_stats_from_wgrad_kernel): the two kernels still launch, but return at once unless that derivation asked for
+// the exact pass (gamma == 0: flag w.gmax[16 + l]; bad cancellation: w.cancel, see stage_needs_exact)
 template <int F>
-// stats_ready: w.m1 / w.m2 / d_gamma / d_beta / w.gmax[l] were already produced from the next layer's parameter
-// gradients (bn_bwd_stats_from_wgrad_kernel + the data-gradient GEMM's max|C|): no reduce pass
+int bn_bwd_sums(const float* g, const float* y, bool planes, int64_t R, const Ws& w, int l, const uint8_t* keep,
+                float inv_keep, float* d_gamma, float* d_beta, cudaStream_t st, const cp_encoder_opts* o,
+                bool stats_ready) {
+    const int P = (int)cp_cdiv(R, ColMap<F>::ROWS);
+    const unsigned int* run_flag = stats_ready ? w.gmax + 16 + l : nullptr;
+    const double* cancel = stats_ready ? w.cancel + (size_t)l * WS_CANCEL_PARTS * 2 : nullptr;
+    bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb, nullptr,
+                                               planes ? w.gmax + l : nullptr, run_flag, cancel);
+    CP_CHECK_LAUNCH();
+    const bool sync = o->allreduce != nullptr;
+    bn_bwd_finalize_kernel<<<dim3(F / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta,
+                                                                    w.rscratch, w.tickets, sync ? w.totals : nullptr,
+                                                                    run_flag, cancel);
+    CP_CHECK_LAUNCH();
+    if (sync) {
+        if (int rc = sync_totals(w, F, o, st)) return rc;
+        bn_bwd_means_totals_kernel<<<(F + 511) / 512, 512, 0, st>>>(w.totals, F, w.m1, w.m2);
+        CP_CHECK_LAUNCH();
+    }
+    return CP_OK;
+}
+
+// BN backward + ReLU backward of stage l:  g (grad w.r.t. stage output A) -> gz (grad w.r.t. the
+// pre-activation), d_gamma, d_beta, d_bias
+template <int F>
 int bn_backward(const float* g, const float* y, float* gz, bool planes, int64_t R, const Ws& w, int l,
                 const uint8_t* keep, float inv_keep, const float* gamma, float* d_gamma, float* d_beta,
                 float* d_bias, cudaStream_t st, const cp_encoder_opts* o, bool stats_ready = false) {
     const int P = (int)cp_cdiv(R, ColMap<F>::ROWS);
     float* gz_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)R * F) : nullptr;
-    // stats_ready: the two kernels below still launch, but return at once unless a gamma == 0 was met (flag w.gmax[16 + l])
-    const unsigned int* run_flag = stats_ready ? w.gmax + 16 + l : nullptr;
-    const double* cancel = stats_ready ? w.cancel + (size_t)l * WS_CANCEL_PARTS * 2 : nullptr;
-    {
-        bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb, nullptr,
-                                                   planes ? w.gmax + l : nullptr, run_flag, cancel);
-        CP_CHECK_LAUNCH();
-        const bool sync = o->allreduce != nullptr;
-        bn_bwd_finalize_kernel<<<dim3(F / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta,
-                                                                        w.rscratch, w.tickets, sync ? w.totals : nullptr,
-                                                                        run_flag, cancel);
-        CP_CHECK_LAUNCH();
-        if (sync) {
-            if (int rc = sync_totals(w, F, o, st)) return rc;
-            bn_bwd_means_totals_kernel<<<(F + 511) / 512, 512, 0, st>>>(w.totals, F, w.m1, w.m2);
-            CP_CHECK_LAUNCH();
-        }
-    }
+    if (int rc = bn_bwd_sums<F>(g, y, planes, R, w, l, keep, inv_keep, d_gamma, d_beta, st, o, stats_ready)) return rc;
     if (planes)
         bn_bwd_apply_kernel<F, true><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], gamma, w.m1,
-                                                        w.m2, gz, gz_lo, w.pa, nullptr, w.gmax + l, w.gscale_inv + l);
+                                                        w.m2, gz, gz_lo, w.pa, nullptr, w.gmax + l, w.gscale_inv + l,
+                                                        w.g1max + l);
     else
         bn_bwd_apply_kernel<F, false><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], gamma, w.m1,
                                                          w.m2, gz, nullptr, w.pa);
@@ -314,6 +334,8 @@ struct SideStream {
         return CP_OK;
     }
 };
+// CP_FUSE_BNBWD=0 in the environment keeps the un-fused BN backward (A/B measurements)
+const bool g_fuse_bnbwd = []() { const char* e = getenv("CP_FUSE_BNBWD"); return !(e && e[0] == '0'); }();
 constexpr int CP_MAX_DEVICES = 64;
 SideStream g_side_of[CP_MAX_DEVICES];
 SideStream* side_of_current_device() {
@@ -363,7 +385,7 @@ int last_block_backward(const float* d_emb, float* gz, bool planes, int64_t n, c
 #define CP_PF_APPLY(K, SP)                                                                                              \
     pf::proj_bwd_apply_kernel<K, SP><<<G, 256, pf::SMEM, st>>>(w.Y[LL], keep, d_emb, n, inv_keep, w.mean[S], w.istd[S],  \
                                                                p->bn_w[S], w.m1, w.m2, p->proj_w, gz, gz_lo, w.pa, gmax, \
-                                                               w.gscale_inv + S)
+                                                               w.gscale_inv + S, planes ? w.g1max + S : nullptr)
     if (keep) { if (planes) CP_PF_APPLY(true, true); else CP_PF_APPLY(true, false); }
     else { if (planes) CP_PF_APPLY(false, true); else CP_PF_APPLY(false, false); }
 #undef CP_PF_APPLY
@@ -410,13 +432,17 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     const int64_t R12 = n * 12;
     const size_t conv_elems = (size_t)n * 12 * F_CONV, fc_elems = (size_t)n * F_FC;
 
-    CP_CUDA(cudaMemsetAsync(w.tickets, 0, (64 + 16 + 8) * sizeof(unsigned int), st));
+    CP_CUDA(cudaMemsetAsync(w.tickets, 0, (64 + 16 + 8 + 8) * sizeof(unsigned int), st));
     if (tcE) {
         WmaxArgs wa;
         for (int l = 0; l < CP_N_FC; ++l) { wa.W[l] = p->fc_w[l]; wa.n[l] = F_FC * (l == 0 ? K_FC1 : F_FC); }
         wa.W[7] = p->conv2_w; wa.n[7] = 64 * 64 * 9;
         weights_absmax_kernel<<<dim3(48, 8), 256, 0, st>>>(wa, w.wmax);
         CP_CHECK_LAUNCH();
+        if (o->save_for_backward) {
+            weights_col_l1_kernel<<<dim3(K_FC1 / 256, CP_N_FC), 256, 0, st>>>(wa, w.l1max);
+            CP_CHECK_LAUNCH();
+        }
     }
     prep_weights_kernel<<<(F_FC * K_FC1 + 255) / 256, 256, 0, st>>>(p->conv2_w, p->fc_w[0], w.Wc2, w.Wc2d, w.W1p,
                                                                     w.Wc2_lo, w.Wc2d_lo, p->conv1_w, p->conv1_b, w.c1w, w.c1b,
@@ -524,7 +550,7 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     const int64_t R12 = n * 12;
     const size_t conv_elems = (size_t)n * 12 * F_CONV, fc_elems = (size_t)n * F_FC;
     const float inv_keep = o->dropout_p > 0.f ? 1.f / (1.f - o->dropout_p) : 1.f;
-    CP_CUDA(cudaMemsetAsync(w.gmax, 0, 32 * sizeof(unsigned int), st));
+    CP_CUDA(cudaMemsetAsync(w.gmax, 0, 48 * sizeof(unsigned int), st));
 
     const int Pp = pf::grid_for(n);          // projection weight-gradient partial rows (last_block_backward)
 
@@ -543,16 +569,23 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
         auto g1 = [&](int b) { return b ? w.G1b : w.G1; };
         auto g1lo = [&](int b, size_t elems) { return lo_of(g1(b), elems); };
         bool stats_ready = false;                      // BN sums of the stage about to be processed already known
+        bool stage_done = false;                       // ... and its whole BN backward already done (fused epilogue)
+        // The BN + ReLU backward of a stage that feeds its layer WITHOUT dropout (conv2 stage, linear blocks 1..3) is
+        // fused into that layer's data-gradient GEMM: the gradient w.r.t. the stage output is never stored.
+        const bool fuse_ok = o->allreduce == nullptr && tcg::bnbwd_supported(n) && g_fuse_bnbwd;
         cudaEvent_t last_side = nullptr;               // completion of the latest side-stream GEMM (owner of w.wpart)
         for (int l = CP_N_FC - 1; l >= 0; --l, ++nb) {
             const int b = nb & 1;
             const uint8_t* keep = (l >= 3 && o->dropout_p > 0.f) ? w.keep[l - 3] : nullptr;
             if (used[b]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b], 0));     // WAR on the G1 buffer
-            if (l == CP_N_FC - 1)
+            if (stage_done)
+                ;                                      // g1(b) already holds this stage's pre-activation gradient
+            else if (l == CP_N_FC - 1)
                 CP_TRY(last_block_backward(d_emb, g1(b), true, n, w, keep, inv_keep, p, gr, st, o));
             else
                 CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], g1(b), true, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
                                          gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st, o, stats_ready));
+            stage_done = false;
             const int K = l == 0 ? K_FC1 : F_FC;
             const float* ain = l == 0 ? w.A2 : w.A[l - 1];
             const plane_t* ah = hi_of(ain);
@@ -568,6 +601,64 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             const bool algebraic = o->allreduce == nullptr;
             const uint8_t* keep_below = below_has_dropout ? w.keep[l - 1 - 3] : nullptr;
             const bool masked = algebraic && keep_below != nullptr;
+            if (fuse_ok && !below_has_dropout) {
+                const int s_below = 1 + l;             // BN stage of this layer's input
+                const int Fb = l == 0 ? F_CONV : F_FC;
+                const int64_t Rb = l == 0 ? R12 : n;
+                const float* y_below = l == 0 ? w.Y2 : w.Y[l - 1];
+                const unsigned int* flag = w.gmax + 16 + s_below;
+                const double* cancel = w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2;
+                // (1) dW_l, (2) the stage's BN-backward sums from dW_l / db_l
+                if (last_side) CP_CUDA(cudaStreamWaitEvent(st, last_side, 0));
+                CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, st, gsi, fast,
+                                true, w.ascale_inv + 1 + l));
+                if (l == 0)
+                    bn_bwd_stats_from_wgrad_kernel<12><<<K_FC1 / WgradStats<12>::COLS, 512, 0, st>>>(
+                        p->fc_w[0], gr->fc_w[0], gr->fc_b[0], F_FC, K_FC1, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
+                        gr->bn_w[s_below], gr->bn_b[s_below], nullptr, w.gmax + 16 + s_below,
+                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2);
+                else
+                    bn_bwd_stats_from_wgrad_kernel<1><<<F_FC / WgradStats<1>::COLS, 512, 0, st>>>(
+                        p->fc_w[l], gr->fc_w[l], gr->fc_b[l], F_FC, F_FC, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
+                        gr->bn_w[s_below], gr->bn_b[s_below], nullptr, w.gmax + 16 + s_below,
+                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2);
+                CP_CHECK_LAUNCH();
+                // (3) exact fallback, all three launches return at once unless the derivation above asked for it:
+                //     the plain data gradient -> G0, then the sums the long way
+                CP_TRY(tcg::launch_nt(hi_of(g1(b)), g1lo(b, fc_elems), n, F_FC, F_FC, w.Wth[l], w.Wtl[l], K, F_FC, nullptr, w.G0,
+                                      K, nullptr, nullptr, 0, st, gsi, fast, nullptr, nullptr, 1.f, w.wscale_inv + l, flag, cancel));
+                if (l == 0)
+                    CP_TRY(bn_bwd_sums<F_CONV>(w.G0, y_below, false, Rb, w, s_below, nullptr, 1.f, gr->bn_w[s_below],
+                                               gr->bn_b[s_below], st, o, true));
+                else
+                    CP_TRY(bn_bwd_sums<F_FC>(w.G0, y_below, false, Rb, w, s_below, nullptr, 1.f, gr->bn_w[s_below],
+                                             gr->bn_b[s_below], st, o, true));
+                // (4) epilogue coefficients + plane-scale bound, (5) the fused data gradient
+                float *c1 = w.coef, *c2 = w.coef + F_FC, *c3 = w.coef + 2 * F_FC;
+                if (l == 0)
+                    bn_bwd_coef_kernel<F_CONV><<<1, F_CONV, 0, st>>>(p->bn_w[s_below], w.mean[s_below], w.istd[s_below], w.m1, w.m2,
+                                                                     w.g1max + 2 + l, w.l1max + l, c1, c2, c3, w.gz_bound + s_below);
+                else
+                    bn_bwd_coef_kernel<F_FC><<<1, F_FC, 0, st>>>(p->bn_w[s_below], w.mean[s_below], w.istd[s_below], w.m1, w.m2,
+                                                                 w.g1max + 2 + l, w.l1max + l, c1, c2, c3, w.gz_bound + s_below);
+                CP_CHECK_LAUNCH();
+                const int bo = b ^ 1;                  // the other G1 buffer receives the stage's pre-activation gradient
+                if (used[bo]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[bo], 0));
+                plane_t* go_hi = reinterpret_cast<plane_t*>(g1(bo));
+                plane_t* go_lo = go_hi + (l == 0 ? conv_elems : fc_elems);
+                CP_TRY(tcg::launch_nt_bnbwd(hi_of(g1(b)), g1lo(b, fc_elems), n, F_FC, w.Wth[l], w.Wtl[l], K, y_below, c1, c2, c3, Fb,
+                                            w.gz_bound + s_below, go_hi, go_lo, w.pa, w.g1max + s_below, w.gscale_inv + s_below,
+                                            gsi, w.wscale_inv + l, fast, st));
+                if (l == 0)
+                    colsum_fold12_kernel<<<F_CONV / 32, 1024, 0, st>>>(w.pa, (int)cp_cdiv(n, 128), gr->conv2_b);
+                else
+                    colsum_finalize_kernel<<<F_FC / 32, 1024, 0, st>>>(w.pa, (int)cp_cdiv(n, 128), F_FC, gr->fc_b[l - 1], 0);
+                CP_CHECK_LAUNCH();
+                (void)Fb; (void)flag;
+                stage_done = true;
+                stats_ready = false;
+                continue;
+            }
             // main stream: G0 = G1 . W_l
             CP_TRY(tcg::launch_nt(hi_of(g1(b)), g1lo(b, fc_elems), n, F_FC, F_FC, w.Wth[l], w.Wtl[l], K, F_FC, nullptr, w.G0,
                                   K, masked ? w.pa : nullptr, masked ? w.pb : nullptr, 0, st, gsi, fast,
@@ -614,8 +705,9 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
         // conv2 block: G0 is [n*12, 64] (same memory order as the [n,768] position-major flatten)
         const int b = nb & 1;
         if (used[b]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b], 0));
-        CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, g1(b), true, R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1],
-                                   gr->bn_b[1], gr->conv2_b, st, o, stats_ready));
+        if (!stage_done)
+            CP_TRY(bn_backward<F_CONV>(w.G0, w.Y2, g1(b), true, R12, w, 1, nullptr, 1.f, p->bn_w[1], gr->bn_w[1],
+                                       gr->bn_b[1], gr->conv2_b, st, o, stats_ready));
         CP_CUDA(cudaEventRecord(g_side.ready[b], st));
         CP_CUDA(cudaStreamWaitEvent(ss, g_side.ready[b], 0));
         CP_CUDA(cudaMemsetAsync(gr->conv2_w, 0, sizeof(float) * 64 * 64 * 9, ss));

@@ -583,8 +583,10 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, in
                     const float* __restrict__ istd, const float* __restrict__ gamma,
                     const float* __restrict__ m1, const float* __restrict__ m2, float* __restrict__ gz,
                     float* __restrict__ gz_lo, float* __restrict__ pdb, const float* __restrict__ post = nullptr,
-                    const unsigned int* __restrict__ gmax_bits = nullptr, float* __restrict__ gscale_inv = nullptr) {
+                    const unsigned int* __restrict__ gmax_bits = nullptr, float* __restrict__ gscale_inv = nullptr,
+                    unsigned int* __restrict__ g1max_out = nullptr /*max |gz| (bit pattern), zeroed per backward call*/) {
     __shared__ float red[ColMap<F>::RY * F];
+    float zmax = 0.f;
     const int qx = threadIdx.x % ColMap<F>::QX, ry = threadIdx.x / ColMap<F>::QX;
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + qx * 4));
     const float4 is = __ldg(reinterpret_cast<const float4*>(istd + qx * 4));
@@ -635,10 +637,63 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, in
             reinterpret_cast<float4*>(gz)[v] = o;
         }
         sb[0] += o.x; sb[1] += o.y; sb[2] += o.z; sb[3] += o.w;
+        zmax = fmaxf(fmaxf(zmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
     }
     block_col_reduce<F>(sb, red, qx, ry);
     if (ry == 0)
         *reinterpret_cast<float4*>(pdb + (int64_t)blockIdx.x * F + qx * 4) = make_float4(sb[0], sb[1], sb[2], sb[3]);
+    if (g1max_out) {
+        zmax = warp_max(zmax);
+        if (threadIdx.x % 32 == 0 && zmax > 0.f) atomicMax(g1max_out, __float_as_uint(zmax));
+    }
+}
+
+// Coefficients of the BN + ReLU backward that the data-gradient GEMM of the layer above applies in its epilogue
+// (tcg::EPI_BNBWD):  gz = 1[y > 0] (c1 g + c2 y + c3)  ==  1[y > 0] gamma istd (g - m1 - xh m2),
+//   c1 = gamma istd,  c2 = -c1 istd m2,  c3 = -c1 m1 - c2 mean;
+// and a bound on |gz| for the power-of-two scale of its fp16 planes: max|c1| * 18 * max|g| (|m1| <= max|g|, |m2| <=
+// max|g|, |xh| <= 16, as in bn_bwd_apply_kernel) with max|g| <= max|G1 above| * max column L1 norm of the layer's W.
+// One CTA of F threads.
+template <int F>
+__global__ void __launch_bounds__(F)
+bn_bwd_coef_kernel(const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ istd,
+                   const float* __restrict__ m1, const float* __restrict__ m2,
+                   const unsigned int* __restrict__ g1max_above, const unsigned int* __restrict__ l1max,
+                   float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ c3, float* __restrict__ gz_bound) {
+    __shared__ float red[F / 32];
+    const int t = threadIdx.x;
+    const float k = gamma[t] * istd[t];
+    const float k2 = -k * istd[t] * m2[t];
+    c1[t] = k;
+    c2[t] = k2;
+    c3[t] = fmaf(-k2, mean[t], -k * m1[t]);
+    const float km = warp_max(fabsf(k));
+    if (t % 32 == 0) red[t / 32] = km;
+    __syncthreads();
+    if (t == 0) {
+        float m = red[0];
+        for (int i = 1; i < F / 32; ++i) m = fmaxf(m, red[i]);
+        *gz_bound = m * 18.f * (__uint_as_float(__ldg(g1max_above)) * __uint_as_float(__ldg(l1max)));
+    }
+}
+
+// out[ch] = sum_p sum_pos partial[p][pos*64 + ch]: the conv2 bias gradient from the [tiles][768] column sums of the
+// position-major pre-activation gradient (12 positions x 64 channels per window)
+__global__ void __launch_bounds__(1024)
+colsum_fold12_kernel(const float* __restrict__ part, int P, float* __restrict__ out) {
+    __shared__ double sm[32 * 33];
+    const int ch = blockIdx.x * 32 + threadIdx.x % 32, lane = threadIdx.x / 32;
+    double s = 0.0;
+    for (int p = lane; p < P; p += 32)
+        for (int pos = 0; pos < 12; ++pos) s += (double)__ldg(part + (int64_t)p * 768 + pos * 64 + ch);
+    const int cx = threadIdx.x % 32;
+    sm[lane * 33 + cx] = s;
+    __syncthreads();
+    if (lane == 0) {
+        double t = 0.0;
+        for (int l = 0; l < 32; ++l) t += sm[l * 33 + cx];
+        out[ch] = (float)t;
+    }
 }
 
 // ------------------------------------------------- BN-backward sums without a pass over the activations
@@ -925,6 +980,19 @@ weights_absmax_kernel(const WmaxArgs a, unsigned int* __restrict__ wmax) {
     }
     m = warp_max(m);
     if (threadIdx.x % 32 == 0 && m > 0.f && m < 3.0e38f) atomicMax(wmax + l, __float_as_uint(m));
+}
+// max over the columns k of sum_n |W_l[n, k]| for the 7 linear weights (blockIdx.y) -> l1max[7] (bit patterns, zeroed per
+// forward call): |G1 . W| <= max|G1| * this, the bound the fused BN-backward epilogue scales its planes by
+__global__ void __launch_bounds__(256)
+weights_col_l1_kernel(const WmaxArgs a, unsigned int* __restrict__ l1max) {
+    const int l = blockIdx.y;
+    const int K = a.n[l] / 512;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    float s = 0.f;
+    if (k < K)
+        for (int n = 0; n < 512; ++n) s += fabsf(__ldg(a.W[l] + (size_t)n * K + k));
+    s = warp_max(s);
+    if (threadIdx.x % 32 == 0 && s > 0.f && s < 3.0e38f) atomicMax(l1max + l, __float_as_uint(s));
 }
 // S with max|W| * S in (1/2, 1]
 __device__ __forceinline__ float weight_scale(const unsigned int* wmax_slot) {

@@ -26,6 +26,20 @@ typedef __half plane_t;                            // element type of the (hi, l
 #define CP_LO_SCALE 2048.f                         // lo plane = (x - hi) * 2^11
 #define CP_LO_INV (1.f / 2048.f)
 
+// x -> (hi, lo) fp16 planes: hi = fp16(x), lo = fp16((x - hi) * 2048); x = hi + lo/2048 to 22 bits.
+// Every producer multiplies by a per-tensor power of two first (plane_scale below: activations from the BatchNorm
+// affine's bound, weights from max|W|, gradients from max|g'|) so that the values sit in fp16's normal range whatever
+// the magnitude of the tensor; the clamp only keeps hi finite for a value 256x beyond its bound.
+// S with bound * S = 2^8 (exact power of two; 1 for a zero / non-finite bound)
+__device__ __forceinline__ float plane_scale(float bound) {
+    return (bound > 0.f && bound < 3.0e38f) ? exp2f(8.f - ceilf(log2f(bound))) : 1.f;
+}
+__device__ __forceinline__ void split_f16(float x, plane_t& hi, plane_t& lo) {
+    x = fminf(fmaxf(x, -65000.f), 65000.f);
+    hi = __float2half_rn(x);
+    lo = __float2half_rn((x - __half2float(hi)) * CP_LO_SCALE);
+}
+
 namespace tcg {
 
 constexpr int BM = 128, BN = 128, BK = 64;        // BK halves = 128 bytes = one swizzle row
@@ -96,6 +110,20 @@ struct NtArgs {
     float inv_keep;                 // column sums of C * keep / (1-p) (mask [M][N] bytes), psq is not written, and
                                     // gmax_bits takes the masked maximum
     const float* out_scale2;        // second device scalar multiplied into the result (the other operand's plane scale), or null
+    // ---- EPI_BNBWD (pair kernel): C = the gradient w.r.t. the BatchNorm output of the stage below is NOT stored; the
+    // epilogue turns it into the gradient w.r.t. that stage's pre-activation,
+    //     gz = 1[y > 0] * (c1 * g + c2 * y + c3)        (BN backward + ReLU backward; coefficients per BN channel =
+    //                                                     column % bn_period, from bn_bwd_coef_kernel)
+    // and writes gz * S as fp16 (hi, lo) planes through tm_c / tm_c2, with S = plane_scale(*gz_bound); psum receives
+    // the per-tile column sums of gz (bias gradient partials), *g1max_out the maximum |gz|, *gscale_inv_out = 1 / S.
+    const float* Y; int ldy;        // post-ReLU pre-BN activation of the stage below, [M][N] fp32
+    const float *c1, *c2, *c3;      // [bn_period]
+    int bn_period;
+    const float* gz_bound;          // device scalar: bound on |gz| (bn_bwd_coef_kernel)
+    unsigned int* g1max_out;
+    float* gscale_inv_out;
+    const unsigned int* skip_flag;  // non-null: a device word; the kernel returns at once when it is zero (the conditional
+    const double* skip_cancel;      // plain data-gradient launch of the exact fallback, see stage_needs_exact)
 };
 
 // warp-transposing reduction: on return v[0] of lane l = sum over the 32 lanes of their v[l]
@@ -370,18 +398,34 @@ struct Smem2 {
     float csq[4][BN];
 };
 constexpr int SMEM2 = STAGES2 * STAGE2 + 8 * OUT_BOX + 1024 + (int)sizeof(Smem2);
+// EPI_BNBWD: per epilogue warp one [32 rows][64 halves] box per plane (hi, lo) = 2 x 4 KB
+constexpr int SMEM2_BNBWD = STAGES2 * STAGE2 + 8 * 2 * OUT_BOX + 1024 + (int)sizeof(Smem2);
 }  // namespace pair
 
-template <bool FAST>
+constexpr int EPI_STD = 0, EPI_BNBWD = 1;
+
+// the device-side decision of encoder_kernels.cuh (stage_needs_exact), restated here for the conditional launch
+__device__ __forceinline__ bool nt_skip(const NtArgs& g) {
+    if (!g.skip_flag) return false;
+    if (__ldg(g.skip_flag) != 0u) return false;
+    if (!g.skip_cancel) return true;
+    double E = 0.0, D = 0.0;
+    for (int i = 0; i < 32; ++i) { E += __ldg(g.skip_cancel + 2 * i); D += __ldg(g.skip_cancel + 2 * i + 1); }
+    return !(E > 64.0 * D);
+}
+
+template <bool FAST, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair::THREADS2, 1)
 gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                        const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                       const __grid_constant__ CUtensorMap tm_c, const NtArgs g) {
+                       const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_c2,
+                       const NtArgs g) {
     using namespace pair;
+    if (nt_skip(g)) return;                      // uniform over the grid: taken before any barrier / TMEM allocation
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* out_boxes = tiles + STAGES2 * STAGE2;                              // 8 x 4 KB, 1024-aligned
-    Smem2* sm = reinterpret_cast<Smem2*>(out_boxes + 8 * OUT_BOX);
+    uint8_t* out_boxes = tiles + STAGES2 * STAGE2;                              // 8 x 4 KB (EPI_BNBWD: 8 x 8 KB), 1024-aligned
+    Smem2* sm = reinterpret_cast<Smem2*>(out_boxes + 8 * OUT_BOX * (EPI == EPI_BNBWD ? 2 : 1));
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const uint32_t rank = tc::cluster_ctarank();
@@ -473,6 +517,106 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
         const float oscale = (g.out_scale ? __ldg(g.out_scale) : 1.f) * (g.out_scale2 ? __ldg(g.out_scale2) : 1.f);
         const float cscale = CP_LO_INV * oscale;
         int it = 0;
+        if (EPI == EPI_BNBWD) {
+            // ---- fused BatchNorm + ReLU backward of the stage below (see NtArgs)
+            const float S = plane_scale(__ldg(g.gz_bound));
+            if (blockIdx.x == 0 && et == 0) *g.gscale_inv_out = 1.f / S;
+            uint8_t* box_hi = out_boxes + (warp - 2) * 2 * OUT_BOX;
+            uint8_t* box_lo = box_hi + OUT_BOX;
+            float gzmax = 0.f;
+            for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
+                const int acc = it & 1;
+                const int64_t tile_m = (t / tiles_n) * 2 + rank;
+                const int n0 = (int)(t % tiles_n) * BN;
+                const int64_t row = tile_m * BM + q * 32 + lane;
+                const bool row_ok = row < g.M;
+                // this thread's 32 activations of the stage below per chunk: chunk 0 is fetched while the tile's MMAs are
+                // still running, chunk 1 while chunk 0 is being written out
+                const float4* yp = reinterpret_cast<const float4*>(g.Y + row * (int64_t)g.ldy + n0 + half * 64);
+                float4 yv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) yv[j] = row_ok ? __ldg(yp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                tc::mbar_wait(&sm->tmem_full[acc], (it >> 1) & 1);
+                tc::tc_fence_after();
+                if (lane == 0) tc::tma_store_wait_read();          // the previous tile's plane stores have left the boxes
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int cl = half * 64 + c * 32;
+                    float v[32];
+                    {
+                        float vc[32];
+                        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + cl;
+                        tc::tmem_ld32(ta, v);
+                        if (!FAST) tc::tmem_ld32(ta + BN, vc);
+                        tc::tmem_ld_wait();
+                        const int ch0 = (n0 + cl) % g.bn_period;           // 32 consecutive BN channels
+                        const float* yy = reinterpret_cast<const float*>(yv);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 k1 = __ldg(reinterpret_cast<const float4*>(g.c1 + ch0 + j));
+                            const float4 k2 = __ldg(reinterpret_cast<const float4*>(g.c2 + ch0 + j));
+                            const float4 k3 = __ldg(reinterpret_cast<const float4*>(g.c3 + ch0 + j));
+                            const float kk1[4] = {k1.x, k1.y, k1.z, k1.w}, kk2[4] = {k2.x, k2.y, k2.z, k2.w},
+                                        kk3[4] = {k3.x, k3.y, k3.z, k3.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float gg = FAST ? v[j + u] * oscale : fmaf(vc[j + u], cscale, v[j + u] * oscale);
+                                const float yj = yy[j + u];
+                                const float z = yj > 0.f ? fmaf(kk1[u], gg, fmaf(kk2[u], yj, kk3[u])) : 0.f;
+                                gzmax = fmaxf(gzmax, fabsf(z));
+                                v[j + u] = z;
+                            }
+                        }
+                    }
+                    if (c == 0) {                    // chunk 1's activations: in flight during the stores below
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) yv[j] = row_ok ? __ldg(yp + 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    // planes of gz * S into the warp's boxes: 16-byte chunk (c*4 + j/8) of the 128-byte row, 128B swizzle
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        uint32_t hq[4], lq[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float a = fminf(fmaxf(v[j8 * 8 + 2 * u] * S, -65000.f), 65000.f);
+                            const float b = fminf(fmaxf(v[j8 * 8 + 2 * u + 1] * S, -65000.f), 65000.f);
+                            const __half2 h2 = __floats2half2_rn(a, b);
+                            const float2 hf = __half22float2(h2);
+                            const __half2 l2 = __floats2half2_rn((a - hf.x) * CP_LO_SCALE, (b - hf.y) * CP_LO_SCALE);
+                            hq[u] = *reinterpret_cast<const uint32_t*>(&h2);
+                            lq[u] = *reinterpret_cast<const uint32_t*>(&l2);
+                        }
+                        const int slot = ((c * 4 + j8) ^ (lane & 7)) << 4;
+                        *reinterpret_cast<uint4*>(box_hi + lane * 128 + slot) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+                        *reinterpret_cast<uint4*>(box_lo + lane * 128 + slot) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+                    }
+                    if (g.psum) {                    // column sums of gz: bias gradient partials
+                        warp_col_reduce32(v, lane);
+                        sm->csum[q][cl + lane] = v[0];
+                    }
+                }
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tc::tma_store_2d(&tm_c, box_hi, n0 + half * 64, (int)(tile_m * BM + q * 32));
+                    tc::tma_store_2d(&tm_c2, box_lo, n0 + half * 64, (int)(tile_m * BM + q * 32));
+                    tc::tma_store_commit();
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive_cluster(tc::mapa(tc::smem_u32(&sm->tmem_empty[acc]), 0));
+                if (g.psum) {
+                    tc::named_bar_sync(1, EPI2);
+                    if (et < BN && tile_m * BM < g.M)
+                        g.psum[tile_m * g.N + n0 + et] = sm->csum[0][et] + sm->csum[1][et] + sm->csum[2][et] + sm->csum[3][et];
+                    tc::named_bar_sync(1, EPI2);
+                }
+            }
+            gzmax = warp_max(gzmax);
+            if (lane == 0 && gzmax > 0.f && g.g1max_out) atomicMax(g.g1max_out, __float_as_uint(gzmax));
+            if (lane == 0) tc::tma_store_wait_read();
+        } else
         for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
             const int acc = it & 1;
             const int64_t tile_m = (t / tiles_n) * 2 + rank;            // 128-row tile index of this CTA
@@ -975,11 +1119,21 @@ inline int launch_nt_cfg(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, con
 }
 
 static bool g_use_pair = true;       // CTA-pair (cta_group::2) kernel for the plain (non-conv) K-major GEMMs
+inline int set_pair_attrs() {
+    CP_ONCE_PER_DEVICE({
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<false, EPI_STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<true, EPI_STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<false, EPI_BNBWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2_BNBWD));
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<true, EPI_BNBWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2_BNBWD));
+    });
+    return CP_OK;
+}
 inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K, int lda, const plane_t* B_hi,
                      const plane_t* B_lo, int N, int ldb, const float* bias, float* C, int ldc, float* psum,
                      float* psq, int relu, cudaStream_t st, const float* out_scale = nullptr, int fast = 0,
                      unsigned int* gmax_bits = nullptr, const uint8_t* keep = nullptr, float inv_keep = 1.f,
-                     const float* out_scale2 = nullptr) {
+                     const float* out_scale2 = nullptr, const unsigned int* skip_flag = nullptr,
+                     const double* skip_cancel = nullptr) {
     if (K % BK != 0 || N % BN != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldc % 4 != 0) return CP_ERR_ARG;
     if (keep && (ldc != N || ((uintptr_t)keep) % 16 != 0)) return CP_ERR_ARG;     // mask laid out like a dense [M][N] C
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_out;
@@ -990,23 +1144,59 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
     if ((rc = make_tmap_2d(&tb_hi, B_hi, N, K, ldb, BN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, N, K, ldb, BN)) != CP_OK) return rc;
     NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu, out_scale, fast, gmax_bits, keep, inv_keep, out_scale2};
+    g.skip_flag = skip_flag;
+    g.skip_cancel = skip_cancel;
     if (g_use_pair && M > BM) {
         CUtensorMap tb_hi2, tb_lo2;                                   // B boxes of 64 rows: half a tile per CTA
         if ((rc = make_tmap_2d(&tb_hi2, B_hi, N, K, ldb, BN / 2)) != CP_OK) return rc;
         if ((rc = make_tmap_2d(&tb_lo2, B_lo, N, K, ldb, BN / 2)) != CP_OK) return rc;
-        CP_ONCE_PER_DEVICE({
-            CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
-            CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
-        });
+        if ((rc = set_pair_attrs()) != CP_OK) return rc;
         const int64_t n_tiles = cp_cdiv(M, 2 * BM) * (N / BN);
         const int clusters = (int)(n_tiles < CP_NUM_SMS / 2 ? n_tiles : CP_NUM_SMS / 2);
-        if (fast) gemm_tc_nt_pair_kernel<true><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, g);
-        else gemm_tc_nt_pair_kernel<false><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, g);
+        if (fast) gemm_tc_nt_pair_kernel<true, EPI_STD><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, tc_out, g);
+        else gemm_tc_nt_pair_kernel<false, EPI_STD><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, tc_out, g);
         CP_CHECK_LAUNCH();
         return CP_OK;
     }
+    if (skip_flag) return CP_ERR_UNSUPPORTED;                         // conditional launches exist for the pair kernel only
     return fast ? launch_nt_cfg<128, false, true>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(M, BM), st)
                 : launch_nt_cfg<128, false, false>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(M, BM), st);
+}
+
+// Data gradient of a linear layer fused with the BatchNorm + ReLU backward of the stage below (EPI_BNBWD, see NtArgs):
+//   g = A . B^T * out_scale * out_scale2 ;  gz = 1[Y > 0] (c1 g + c2 Y + c3) ;  planes (G_hi, G_lo) = split(gz * S)
+// A: [M][K] planes of the layer's pre-activation gradient, B: [N][K] planes of W^T, Y: [M][N] fp32, G planes [M][N].
+// pdb: [ceil(M/128)][N] column sums of gz.  Needs M > 128 (the CTA-pair kernel).
+inline bool bnbwd_supported(int64_t M) { return g_use_pair && M > BM; }
+inline int launch_nt_bnbwd(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K, const plane_t* B_hi,
+                           const plane_t* B_lo, int N, const float* Y, const float* c1, const float* c2, const float* c3,
+                           int bn_period, const float* gz_bound, plane_t* G_hi, plane_t* G_lo, float* pdb,
+                           unsigned int* g1max_out, float* gscale_inv_out, const float* out_scale,
+                           const float* out_scale2, int fast, cudaStream_t st) {
+    if (!bnbwd_supported(M) || K % BK != 0 || N % BN != 0 || bn_period % 32 != 0 || ((uintptr_t)Y) % 16 != 0)
+        return CP_ERR_ARG;
+    CUtensorMap ta_hi, ta_lo, tb_hi2, tb_lo2, tg_hi, tg_lo;
+    int rc;
+    if ((rc = make_tmap_2d(&ta_hi, A_hi, M, K, K, BM)) != CP_OK) return rc;
+    if ((rc = make_tmap_2d(&ta_lo, A_lo, M, K, K, BM)) != CP_OK) return rc;
+    if ((rc = make_tmap_2d(&tb_hi2, B_hi, N, K, K, BN / 2)) != CP_OK) return rc;
+    if ((rc = make_tmap_2d(&tb_lo2, B_lo, N, K, K, BN / 2)) != CP_OK) return rc;
+    if ((rc = make_tmap_2d(&tg_hi, G_hi, M, N, N, 32)) != CP_OK) return rc;      // store boxes: 64 halves x 32 rows
+    if ((rc = make_tmap_2d(&tg_lo, G_lo, M, N, N, 32)) != CP_OK) return rc;
+    if ((rc = set_pair_attrs()) != CP_OK) return rc;
+    NtArgs g{nullptr, N, nullptr, pdb, nullptr, M, N, K, 0, out_scale, fast, nullptr, nullptr, 1.f, out_scale2};
+    g.Y = Y; g.ldy = N;
+    g.c1 = c1; g.c2 = c2; g.c3 = c3;
+    g.bn_period = bn_period;
+    g.gz_bound = gz_bound;
+    g.g1max_out = g1max_out;
+    g.gscale_inv_out = gscale_inv_out;
+    const int64_t n_tiles = cp_cdiv(M, 2 * BM) * (N / BN);
+    const int clusters = (int)(n_tiles < CP_NUM_SMS / 2 ? n_tiles : CP_NUM_SMS / 2);
+    if (fast) gemm_tc_nt_pair_kernel<true, EPI_BNBWD><<<2 * clusters, pair::THREADS2, pair::SMEM2_BNBWD, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tg_hi, tg_lo, g);
+    else gemm_tc_nt_pair_kernel<false, EPI_BNBWD><<<2 * clusters, pair::THREADS2, pair::SMEM2_BNBWD, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tg_hi, tg_lo, g);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
 }
 
 // conv2 as implicit GEMM: C[(w,p), o] = act(sum_{tap,c} X[w, p+tap-1, c] * B[o, tap*64+c] + bias[o]);
@@ -1059,19 +1249,6 @@ inline int launch_conv_tn(const plane_t* X_hi, const plane_t* X_lo, const plane_
 
 }  // namespace tcg
 
-// x -> (hi, lo) fp16 planes: hi = fp16(x), lo = fp16((x - hi) * 2048); x = hi + lo/2048 to 22 bits.
-// Every producer multiplies by a per-tensor power of two first (plane_scale below: activations from the BatchNorm
-// affine's bound, weights from max|W|, gradients from max|g'|) so that the values sit in fp16's normal range whatever
-// the magnitude of the tensor; the clamp only keeps hi finite for a value 256x beyond its bound.
-// S with bound * S = 2^8 (exact power of two; 1 for a zero / non-finite bound)
-__device__ __forceinline__ float plane_scale(float bound) {
-    return (bound > 0.f && bound < 3.0e38f) ? exp2f(8.f - ceilf(log2f(bound))) : 1.f;
-}
-__device__ __forceinline__ void split_f16(float x, plane_t& hi, plane_t& lo) {
-    x = fminf(fmaxf(x, -65000.f), 65000.f);
-    hi = __float2half_rn(x);
-    lo = __float2half_rn((x - __half2float(hi)) * CP_LO_SCALE);
-}
 // four consecutive elements -> 8-byte stores into the two planes (element index v*4)
 __device__ __forceinline__ void split_store4(const float4& x, plane_t* hi, plane_t* lo, int64_t v) {
     plane_t h[4], l[4];

@@ -234,9 +234,10 @@ proj_bwd_apply_kernel(const float* __restrict__ y, const uint8_t* __restrict__ k
                       const float* __restrict__ gamma, const float* __restrict__ m1, const float* __restrict__ m2,
                       const float* __restrict__ Wp, float* __restrict__ gz, float* __restrict__ gz_lo,
                       float* __restrict__ pdb, const unsigned int* __restrict__ gmax_bits,
-                      float* __restrict__ gscale_inv) {
+                      float* __restrict__ gscale_inv, unsigned int* __restrict__ g1max_out = nullptr) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int qx = threadIdx.x % QX, rl = threadIdx.x / QX;
+    float zmax = 0.f;
     float4 wp[CP_EMB_DIM];
 #pragma unroll
     for (int o = 0; o < CP_EMB_DIM; ++o) wp[o] = __ldg(reinterpret_cast<const float4*>(Wp + o * F) + qx);
@@ -292,8 +293,13 @@ proj_bwd_apply_kernel(const float* __restrict__ y, const uint8_t* __restrict__ k
             else
                 reinterpret_cast<float4*>(gz)[v] = o;
             sb.x += o.x; sb.y += o.y; sb.z += o.z; sb.w += o.w;
+            zmax = fmaxf(fmaxf(zmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
         }
     });
+    if (g1max_out) {                  // max |gz|: bounds the next data gradient (fused BN-backward epilogue)
+        zmax = warp_max(zmax);
+        if (threadIdx.x % 32 == 0 && zmax > 0.f) atomicMax(g1max_out, __float_as_uint(zmax));
+    }
     float4* red = reinterpret_cast<float4*>(smem + BAR_BYTES);
     if (rl == 1) red[qx] = sb;
     __syncthreads();
