@@ -392,13 +392,15 @@ constexpr int STAGE2 = 2 * TILE_BYTES + 2 * B_HALF;       // A_hi, A_lo, B_hi/2,
 constexpr int STAGES2 = 3;
 struct Smem2 {
     uint64_t full[STAGES2], empty[STAGES2], tmem_full[2], tmem_empty[2];
+    uint64_t ybar[16];              // EPI_BNBWD: arrival of the two activation boxes of each epilogue warp
     uint32_t tmem_base;
     uint32_t pad;
     float csum[4][BN];
     float csq[4][BN];
 };
 constexpr int SMEM2 = STAGES2 * STAGE2 + 8 * OUT_BOX + 1024 + (int)sizeof(Smem2);
-// EPI_BNBWD: per epilogue warp one [32 rows][64 halves] box per plane (hi, lo) = 2 x 4 KB
+// EPI_BNBWD: per epilogue warp two 4 KB boxes, one per 32-column chunk: first the TMA-loaded [32 rows][32 fp32]
+// activation tile, then (once it is in registers) the chunk's [32][32] fp16 hi and lo planes on their way out
 constexpr int SMEM2_BNBWD = STAGES2 * STAGE2 + 8 * 2 * OUT_BOX + 1024 + (int)sizeof(Smem2);
 }  // namespace pair
 
@@ -419,7 +421,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair::THREADS2, 1)
 gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                        const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                        const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_c2,
-                       const NtArgs g) {
+                       const __grid_constant__ CUtensorMap tm_y, const NtArgs g) {
     using namespace pair;
     if (nt_skip(g)) return;                      // uniform over the grid: taken before any barrier / TMEM allocation
     extern __shared__ uint8_t smem_raw[];
@@ -444,6 +446,8 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             tc::mbar_init(&sm->tmem_full[a], 1);
             tc::mbar_init(&sm->tmem_empty[a], 16);       // 8 epilogue warps x 2 CTAs arrive on the leader's copy
         }
+        if (EPI == EPI_BNBWD)
+            for (int a = 0; a < 16; ++a) tc::mbar_init(&sm->ybar[a], 1);
         tc::fence_barrier_init();
     }
     if (warp == 1) {
@@ -521,28 +525,30 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             // ---- fused BatchNorm + ReLU backward of the stage below (see NtArgs)
             const float S = plane_scale(__ldg(g.gz_bound));
             if (blockIdx.x == 0 && et == 0) *g.gscale_inv_out = 1.f / S;
-            uint8_t* box_hi = out_boxes + (warp - 2) * 2 * OUT_BOX;
-            uint8_t* box_lo = box_hi + OUT_BOX;
+            uint8_t* boxes = out_boxes + (warp - 2) * 2 * OUT_BOX;            // chunk c uses boxes + c * OUT_BOX
+            uint64_t* ybar = &sm->ybar[(warp - 2) * 2];
             float gzmax = 0.f;
             for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
                 const int acc = it & 1;
                 const int64_t tile_m = (t / tiles_n) * 2 + rank;
                 const int n0 = (int)(t % tiles_n) * BN;
-                const int64_t row = tile_m * BM + q * 32 + lane;
-                const bool row_ok = row < g.M;
-                // this thread's 32 activations of the stage below per chunk: chunk 0 is fetched while the tile's MMAs are
-                // still running, chunk 1 while chunk 0 is being written out
-                const float4* yp = reinterpret_cast<const float4*>(g.Y + row * (int64_t)g.ldy + n0 + half * 64);
-                float4 yv[8];
+                const int row0 = (int)(tile_m * BM + q * 32);
+                // the warp's two [32 x 32] activation tiles of the stage below, fetched (TMA, rows beyond M arrive as
+                // zeros) while the tile's MMAs are still running
+                if (lane == 0) {
+                    tc::tma_store_wait_read();                     // the previous tile's plane stores have left the boxes
 #pragma unroll
-                for (int j = 0; j < 8; ++j) yv[j] = row_ok ? __ldg(yp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int c = 0; c < 2; ++c) {
+                        tc::mbar_expect_tx(&ybar[c], OUT_BOX);
+                        tc::tma_load_2d(boxes + c * OUT_BOX, &tm_y, &ybar[c], n0 + half * 64 + c * 32, row0);
+                    }
+                }
                 tc::mbar_wait(&sm->tmem_full[acc], (it >> 1) & 1);
                 tc::tc_fence_after();
-                if (lane == 0) tc::tma_store_wait_read();          // the previous tile's plane stores have left the boxes
-                __syncwarp();
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const int cl = half * 64 + c * 32;
+                    uint8_t* box = boxes + c * OUT_BOX;
                     float v[32];
                     {
                         float vc[32];
@@ -550,6 +556,16 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                         tc::tmem_ld32(ta, v);
                         if (!FAST) tc::tmem_ld32(ta + BN, vc);
                         tc::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = FAST ? v[j] * oscale : fmaf(vc[j], cscale, v[j] * oscale);
+                    }
+                    {
+                        tc::mbar_wait(&ybar[c], it & 1);
+                        float4 yv[8];                                  // row `lane` of the 128B-swizzled box
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            yv[j] = *reinterpret_cast<const float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4));
+                        __syncwarp();                                  // every lane has its row: the box may be overwritten
                         const int ch0 = (n0 + cl) % g.bn_period;           // 32 consecutive BN channels
                         const float* yy = reinterpret_cast<const float*>(yv);
 #pragma unroll
@@ -561,19 +577,14 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                                         kk3[4] = {k3.x, k3.y, k3.z, k3.w};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                const float gg = FAST ? v[j + u] * oscale : fmaf(vc[j + u], cscale, v[j + u] * oscale);
                                 const float yj = yy[j + u];
-                                const float z = yj > 0.f ? fmaf(kk1[u], gg, fmaf(kk2[u], yj, kk3[u])) : 0.f;
+                                const float z = yj > 0.f ? fmaf(kk1[u], v[j + u], fmaf(kk2[u], yj, kk3[u])) : 0.f;
                                 gzmax = fmaxf(gzmax, fabsf(z));
                                 v[j + u] = z;
                             }
                         }
                     }
-                    if (c == 0) {                    // chunk 1's activations: in flight during the stores below
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) yv[j] = row_ok ? __ldg(yp + 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    // planes of gz * S into the warp's boxes: 16-byte chunk (c*4 + j/8) of the 128-byte row, 128B swizzle
+                    // planes of gz * S into the chunk's box: hi [32 rows][64 B] then lo [32 rows][64 B], no swizzle
 #pragma unroll
                     for (int j8 = 0; j8 < 4; ++j8) {
                         uint32_t hq[4], lq[4];
@@ -587,21 +598,20 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                             hq[u] = *reinterpret_cast<const uint32_t*>(&h2);
                             lq[u] = *reinterpret_cast<const uint32_t*>(&l2);
                         }
-                        const int slot = ((c * 4 + j8) ^ (lane & 7)) << 4;
-                        *reinterpret_cast<uint4*>(box_hi + lane * 128 + slot) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
-                        *reinterpret_cast<uint4*>(box_lo + lane * 128 + slot) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+                        *reinterpret_cast<uint4*>(box + lane * 64 + j8 * 16) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+                        *reinterpret_cast<uint4*>(box + OUT_BOX / 2 + lane * 64 + j8 * 16) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+                    }
+                    tc::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tc::tma_store_2d(&tm_c, box, n0 + cl, row0);
+                        tc::tma_store_2d(&tm_c2, box + OUT_BOX / 2, n0 + cl, row0);
+                        tc::tma_store_commit();
                     }
                     if (g.psum) {                    // column sums of gz: bias gradient partials
                         warp_col_reduce32(v, lane);
                         sm->csum[q][cl + lane] = v[0];
                     }
-                }
-                tc::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    tc::tma_store_2d(&tm_c, box_hi, n0 + half * 64, (int)(tile_m * BM + q * 32));
-                    tc::tma_store_2d(&tm_c2, box_lo, n0 + half * 64, (int)(tile_m * BM + q * 32));
-                    tc::tma_store_commit();
                 }
                 tc::tc_fence_before();
                 __syncwarp();
@@ -1103,6 +1113,19 @@ inline int make_tmap_out(CUtensorMap* m, float* base, int64_t rows, int64_t cols
     return r == CUDA_SUCCESS ? CP_OK : CP_ERR_ARG;
 }
 
+// fp16 plane output [rows, cols] (leading dimension ld halves): 32 x 32 boxes (64-byte rows), no swizzle (TMA store)
+inline int make_tmap_plane_out(CUtensorMap* m, plane_t* base, int64_t rows, int64_t cols, int64_t ld) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return CP_ERR_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? CP_OK : CP_ERR_ARG;
+}
+
 template <int BN_, bool CONV, bool FAST>
 inline int launch_nt_cfg(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
                          const CUtensorMap& tb_lo, const CUtensorMap& tc_out, const NtArgs& g, int64_t tiles_m,
@@ -1153,8 +1176,8 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
         if ((rc = set_pair_attrs()) != CP_OK) return rc;
         const int64_t n_tiles = cp_cdiv(M, 2 * BM) * (N / BN);
         const int clusters = (int)(n_tiles < CP_NUM_SMS / 2 ? n_tiles : CP_NUM_SMS / 2);
-        if (fast) gemm_tc_nt_pair_kernel<true, EPI_STD><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, tc_out, g);
-        else gemm_tc_nt_pair_kernel<false, EPI_STD><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, tc_out, g);
+        if (fast) gemm_tc_nt_pair_kernel<true, EPI_STD><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, tc_out, tc_out, g);
+        else gemm_tc_nt_pair_kernel<false, EPI_STD><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, tc_out, tc_out, g);
         CP_CHECK_LAUNCH();
         return CP_OK;
     }
@@ -1175,14 +1198,15 @@ inline int launch_nt_bnbwd(const plane_t* A_hi, const plane_t* A_lo, int64_t M, 
                            const float* out_scale2, int fast, cudaStream_t st) {
     if (!bnbwd_supported(M) || K % BK != 0 || N % BN != 0 || bn_period % 32 != 0 || ((uintptr_t)Y) % 16 != 0)
         return CP_ERR_ARG;
-    CUtensorMap ta_hi, ta_lo, tb_hi2, tb_lo2, tg_hi, tg_lo;
+    CUtensorMap ta_hi, ta_lo, tb_hi2, tb_lo2, tg_hi, tg_lo, ty;
     int rc;
+    if ((rc = make_tmap_out(&ty, const_cast<float*>(Y), M, N, N)) != CP_OK) return rc;        // load boxes: 32 fp32 x 32 rows
     if ((rc = make_tmap_2d(&ta_hi, A_hi, M, K, K, BM)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&ta_lo, A_lo, M, K, K, BM)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi2, B_hi, N, K, K, BN / 2)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo2, B_lo, N, K, K, BN / 2)) != CP_OK) return rc;
-    if ((rc = make_tmap_2d(&tg_hi, G_hi, M, N, N, 32)) != CP_OK) return rc;      // store boxes: 64 halves x 32 rows
-    if ((rc = make_tmap_2d(&tg_lo, G_lo, M, N, N, 32)) != CP_OK) return rc;
+    if ((rc = make_tmap_plane_out(&tg_hi, G_hi, M, N, N)) != CP_OK) return rc;   // store boxes: 32 halves x 32 rows
+    if ((rc = make_tmap_plane_out(&tg_lo, G_lo, M, N, N)) != CP_OK) return rc;
     if ((rc = set_pair_attrs()) != CP_OK) return rc;
     NtArgs g{nullptr, N, nullptr, pdb, nullptr, M, N, K, 0, out_scale, fast, nullptr, nullptr, 1.f, out_scale2};
     g.Y = Y; g.ldy = N;
@@ -1193,8 +1217,8 @@ inline int launch_nt_bnbwd(const plane_t* A_hi, const plane_t* A_lo, int64_t M, 
     g.gscale_inv_out = gscale_inv_out;
     const int64_t n_tiles = cp_cdiv(M, 2 * BM) * (N / BN);
     const int clusters = (int)(n_tiles < CP_NUM_SMS / 2 ? n_tiles : CP_NUM_SMS / 2);
-    if (fast) gemm_tc_nt_pair_kernel<true, EPI_BNBWD><<<2 * clusters, pair::THREADS2, pair::SMEM2_BNBWD, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tg_hi, tg_lo, g);
-    else gemm_tc_nt_pair_kernel<false, EPI_BNBWD><<<2 * clusters, pair::THREADS2, pair::SMEM2_BNBWD, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tg_hi, tg_lo, g);
+    if (fast) gemm_tc_nt_pair_kernel<true, EPI_BNBWD><<<2 * clusters, pair::THREADS2, pair::SMEM2_BNBWD, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tg_hi, tg_lo, ty, g);
+    else gemm_tc_nt_pair_kernel<false, EPI_BNBWD><<<2 * clusters, pair::THREADS2, pair::SMEM2_BNBWD, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tg_hi, tg_lo, ty, g);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
