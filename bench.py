@@ -312,20 +312,24 @@ def run_cuda(args):
     modes = {"eager": {"ms_per_step": ms, "e2e_ms_per_step": ms_e2e}}
     step_mode = e2e_mode = "eager"
 
-    # ---- same step captured once as a CUDA graph (single GPU; bit-identical to the eager step,
-    #      tests/test_gpu_graph.py): one graph launch per step instead of ~400 kernel launches
-    if world == 1 and not args.no_graph and not strong:
+    # ---- same step captured once as a CUDA graph (bit-identical to the eager step, tests/test_gpu_graph.py): one
+    #      graph launch per step instead of ~400 kernel launches; at N > 1 the NCCL gradient all-reduce (and the SyncBN
+    #      all-reduces) are captured inside the graph
+    if not args.no_graph and not strong and (world == 1 or dist.get_backend() == "nccl"):
         from contrastiveprosthetics_b200.graph import GraphedTrainStep
         torch.manual_seed(42)
         model_g = Model(dict(PARAMS), adabn=True, device=str(dev))
         model_g.emg_net.engine = model.emg_net.engine
+        model_g.emg_net.sync_bn = args.sync_bn
         model_g.set_train()
         # same optimizer, torch's single-kernel implementation (fused=True): 2 graph nodes instead of ~14
         opts_g = [torch.optim.Adam(model_g.emg_net.parameters(), lr=PARAMS['lr_emg'], weight_decay=0, capturable=True,
                                    fused=True),
                   torch.optim.Adam(model_g.glove_net.parameters(), lr=PARAMS['lr_glove'], weight_decay=0, capturable=True,
                                    fused=True)]
-        gstep = GraphedTrainStep(model_g, opts_g, tw.get_batch(items_ring[0])[0])
+        sync_g = cpdist.FlatGradAllReduce(list(model_g.emg_net.parameters()) + list(model_g.glove_net.parameters())) \
+            if world > 1 else None
+        gstep = GraphedTrainStep(model_g, opts_g, tw.get_batch(items_ring[0])[0], sync_grads=sync_g)
 
         def graph_resident():
             it["i"] += 1
@@ -341,12 +345,13 @@ def run_cuda(args):
         ms_g, clocks_g, _ = timed(graph_resident, args.steps, args.warmup)
         ms_g_e2e, _, _ = timed(graph_e2e, max(3, args.steps // 2), 2)
         modes["cuda_graph"] = {"ms_per_step": ms_g, "e2e_ms_per_step": ms_g_e2e}
+        # every rank must take the same branch: the timings are already the max over ranks
         if ms_g < ms:
             step_mode, ms, clocks = "cuda_graph", ms_g, clocks_g
             value = N * world / (ms / 1e3)
         if ms_g_e2e < ms_e2e:
             e2e_mode, ms_e2e = "cuda_graph", ms_g_e2e
-        del gstep, model_g, opts_g
+        del gstep, model_g, opts_g, sync_g
     e2e_value = N * world / (ms_e2e / 1e3)
 
     # ---- dominant kernel alone: fc forward GEMM at the step's shape (CUDA events on its stream)

@@ -266,14 +266,13 @@ int bn_bwd_sums(const float* g, const float* y, bool planes, int64_t R, const Ws
                 bool stats_ready) {
     const int P = (int)cp_cdiv(R, ColMap<F>::ROWS);
     const unsigned int* run_flag = stats_ready ? w.gmax + 16 + l : nullptr;
-    const double* cancel = stats_ready ? w.cancel + (size_t)l * WS_CANCEL_PARTS * 2 : nullptr;
     bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb, nullptr,
-                                               planes ? w.gmax + l : nullptr, run_flag, cancel);
+                                               planes ? w.gmax + l : nullptr, run_flag);
     CP_CHECK_LAUNCH();
     const bool sync = o->allreduce != nullptr;
     bn_bwd_finalize_kernel<<<dim3(F / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta,
                                                                     w.rscratch, w.tickets, sync ? w.totals : nullptr,
-                                                                    run_flag, cancel);
+                                                                    run_flag);
     CP_CHECK_LAUNCH();
     if (sync) {
         if (int rc = sync_totals(w, F, o, st)) return rc;
@@ -607,7 +606,6 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
                 const int64_t Rb = l == 0 ? R12 : n;
                 const float* y_below = l == 0 ? w.Y2 : w.Y[l - 1];
                 const unsigned int* flag = w.gmax + 16 + s_below;
-                const double* cancel = w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2;
                 // (1) dW_l, (2) the stage's BN-backward sums from dW_l / db_l
                 if (last_side) CP_CUDA(cudaStreamWaitEvent(st, last_side, 0));
                 CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, st, gsi, fast,
@@ -616,17 +614,17 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
                     bn_bwd_stats_from_wgrad_kernel<12><<<K_FC1 / WgradStats<12>::COLS, 512, 0, st>>>(
                         p->fc_w[0], gr->fc_w[0], gr->fc_b[0], F_FC, K_FC1, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
                         gr->bn_w[s_below], gr->bn_b[s_below], nullptr, w.gmax + 16 + s_below,
-                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2);
+                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2, w.tickets + 32 + s_below);
                 else
                     bn_bwd_stats_from_wgrad_kernel<1><<<F_FC / WgradStats<1>::COLS, 512, 0, st>>>(
                         p->fc_w[l], gr->fc_w[l], gr->fc_b[l], F_FC, F_FC, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
                         gr->bn_w[s_below], gr->bn_b[s_below], nullptr, w.gmax + 16 + s_below,
-                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2);
+                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2, w.tickets + 32 + s_below);
                 CP_CHECK_LAUNCH();
                 // (3) exact fallback, all three launches return at once unless the derivation above asked for it:
                 //     the plain data gradient -> G0, then the sums the long way
                 CP_TRY(tcg::launch_nt(hi_of(g1(b)), g1lo(b, fc_elems), n, F_FC, F_FC, w.Wth[l], w.Wtl[l], K, F_FC, nullptr, w.G0,
-                                      K, nullptr, nullptr, 0, st, gsi, fast, nullptr, nullptr, 1.f, w.wscale_inv + l, flag, cancel));
+                                      K, nullptr, nullptr, 0, st, gsi, fast, nullptr, nullptr, 1.f, w.wscale_inv + l, flag));
                 if (l == 0)
                     CP_TRY(bn_bwd_sums<F_CONV>(w.G0, y_below, false, Rb, w, s_below, nullptr, 1.f, gr->bn_w[s_below],
                                                gr->bn_b[s_below], st, o, true));
@@ -676,17 +674,17 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
                     bn_bwd_stats_from_wgrad_kernel<1><<<F_FC / WgradStats<1>::COLS, 512, 0, st>>>(
                         p->fc_w[l], gr->fc_w[l], gr->fc_b[l], F_FC, F_FC, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
                         gr->bn_w[s_below], gr->bn_b[s_below], w.m1, w.gmax + 16 + s_below,
-                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2);
+                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2, w.tickets + 32 + s_below);
                 } else if (l == 0)
                     bn_bwd_stats_from_wgrad_kernel<12><<<K_FC1 / WgradStats<12>::COLS, 512, 0, st>>>(
                         p->fc_w[0], gr->fc_w[0], gr->fc_b[0], F_FC, K_FC1, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
                         gr->bn_w[s_below], gr->bn_b[s_below], nullptr, w.gmax + 16 + s_below,
-                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2);
+                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2, w.tickets + 32 + s_below);
                 else
                     bn_bwd_stats_from_wgrad_kernel<1><<<F_FC / WgradStats<1>::COLS, 512, 0, st>>>(
                         p->fc_w[l], gr->fc_w[l], gr->fc_b[l], F_FC, F_FC, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
                         gr->bn_w[s_below], gr->bn_b[s_below], nullptr, w.gmax + 16 + s_below,
-                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2);
+                        w.cancel + (size_t)s_below * WS_CANCEL_PARTS * 2, w.tickets + 32 + s_below);
                 CP_CHECK_LAUNCH();
                 stats_ready = true;
                 continue;

@@ -474,22 +474,11 @@ bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, float* __res
 // block output relu(bn(y)), g' = g * 1[post > 0], and no ReLU mask follows the BN backward.
 // Does the stage whose BN-backward sums were derived from the next layer's parameter gradients
 // (bn_bwd_stats_from_wgrad_kernel) have to be recomputed the long way?  Yes when a gamma == 0 was met (*flag), or when
-// the derivation cancelled badly: `cancel` holds WS_CANCEL_PARTS per-CTA pairs (E^2, D^2) with E_f = (|sum W dW| +
+// the derivation cancelled badly: that kernel collects per-CTA pairs (E^2, D^2) with E_f = (|sum W dW| +
 // |beta sum g'|) / |gamma| the magnitude of the terms and D_f = |sum g' xh| the result -- a weight-gradient error eps
-// becomes eps * E / D in d_gamma (norm-wise over the stage); beyond 8x the exact reduce pass runs.  Summed in a fixed
-// order: every thread of every consumer reaches the same decision.
+// becomes eps * E / D in d_gamma (norm-wise over the stage); beyond 8x its last CTA raises the flag too.
 #define WS_CANCEL_PARTS 32
-__device__ __forceinline__ bool stage_needs_exact(const unsigned int* __restrict__ flag, const double* __restrict__ cancel) {
-    if (__ldg(flag) != 0u) return true;
-    if (!cancel) return false;
-    double E = 0.0, D = 0.0;
-#pragma unroll 8
-    for (int i = 0; i < WS_CANCEL_PARTS; ++i) {
-        E += __ldg(cancel + 2 * i);
-        D += __ldg(cancel + 2 * i + 1);
-    }
-    return E > 64.0 * D;
-}
+__device__ __forceinline__ bool stage_needs_exact(const unsigned int* __restrict__ flag) { return __ldg(flag) != 0u; }
 
 template <int F>
 __global__ void __launch_bounds__(256)
@@ -497,10 +486,10 @@ bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, i
                      const uint8_t* __restrict__ keep, float inv_keep, const float* __restrict__ mean,
                      const float* __restrict__ istd, float* __restrict__ p1, float* __restrict__ p2,
                      const float* __restrict__ post = nullptr, unsigned int* __restrict__ gmax_bits = nullptr,
-                     const unsigned int* __restrict__ run_flag = nullptr, const double* __restrict__ cancel = nullptr) {
+                     const unsigned int* __restrict__ run_flag = nullptr) {
     __shared__ float red[ColMap<F>::RY * F];
     // fallback pass of the reduce-free BN backward: runs only when bn_bwd_stats_from_wgrad_kernel asked for it
-    if (run_flag && !stage_needs_exact(run_flag, cancel)) return;
+    if (run_flag && !stage_needs_exact(run_flag)) return;
     float gmax = 0.f;                     // max |g'| (feeds the fp16 plane scale of bn_bwd_apply_kernel<.., true>)
     const int qx = threadIdx.x % ColMap<F>::QX, ry = threadIdx.x / ColMap<F>::QX;
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + qx * 4));
@@ -548,10 +537,9 @@ __global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int P, int F, int64_t R,
                        float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ d_gamma,
                        float* __restrict__ d_beta, double* __restrict__ scratch, unsigned int* __restrict__ tickets,
-                       double* __restrict__ totals = nullptr, const unsigned int* __restrict__ run_flag = nullptr,
-                       const double* __restrict__ cancel = nullptr) {
+                       double* __restrict__ totals = nullptr, const unsigned int* __restrict__ run_flag = nullptr) {
     __shared__ double sm[32 * 33];
-    if (run_flag && !stage_needs_exact(run_flag, cancel)) return;          // see bn_bwd_reduce_kernel
+    if (run_flag && !stage_needs_exact(run_flag)) return;          // see bn_bwd_reduce_kernel
     const int col = blockIdx.x * 32 + threadIdx.x % 32;
     const float* const parts[2] = {p1, p2};
     double tot[2];
@@ -720,7 +708,8 @@ bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restr
                                float* m1, float* __restrict__ m2, float* __restrict__ d_gamma,
                                float* __restrict__ d_beta, const float* sum_g_in = nullptr,
                                unsigned int* __restrict__ zero_gamma_flag = nullptr,
-                               double* __restrict__ cancel = nullptr /*[gridDim.x][2]: see stage_needs_exact*/) {
+                               double* __restrict__ cancel = nullptr /*[gridDim.x][2]: see stage_needs_exact*/,
+                               unsigned int* __restrict__ cancel_ticket = nullptr /*zero on entry, re-armed*/) {
     constexpr int COLS = WgradStats<GROUP>::COLS;
     __shared__ double s_a[WS_LANES][COLS], s_t[WS_LANES][COLS];
     __shared__ double s_E[COLS], s_D[COLS];
@@ -776,6 +765,20 @@ bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restr
             for (int i = 0; i < NFEAT; ++i) { E += s_E[i]; D += s_D[i]; }
             cancel[2 * blockIdx.x] = E;
             cancel[2 * blockIdx.x + 1] = D;
+            // the last CTA to finish adds the per-CTA pairs in a fixed order (deterministic whichever CTA that is) and
+            // raises the stage's flag when the derivation cancelled by more than 8x norm-wise (stage_needs_exact)
+            __threadfence();
+            const unsigned int t = atomicAdd(cancel_ticket, 1u);
+            if (t == gridDim.x - 1) {
+                *cancel_ticket = 0;                   // re-arm for the next launch
+                __threadfence();
+                E = D = 0.0;
+                for (unsigned int i = 0; i < gridDim.x; ++i) {
+                    E += __ldcg(cancel + 2 * i);
+                    D += __ldcg(cancel + 2 * i + 1);
+                }
+                if (E > 64.0 * D && zero_gamma_flag) atomicOr(zero_gamma_flag, 1u);
+            }
         }
     }
 }

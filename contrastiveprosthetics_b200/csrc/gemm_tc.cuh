@@ -123,7 +123,7 @@ struct NtArgs {
     unsigned int* g1max_out;
     float* gscale_inv_out;
     const unsigned int* skip_flag;  // non-null: a device word; the kernel returns at once when it is zero (the conditional
-    const double* skip_cancel;      // plain data-gradient launch of the exact fallback, see stage_needs_exact)
+                                    // plain data-gradient launch of the exact fallback, see stage_needs_exact)
 };
 
 // warp-transposing reduction: on return v[0] of lane l = sum over the 32 lanes of their v[l]
@@ -406,15 +406,7 @@ constexpr int SMEM2_BNBWD = STAGES2 * STAGE2 + 8 * 2 * OUT_BOX + 1024 + (int)siz
 
 constexpr int EPI_STD = 0, EPI_BNBWD = 1;
 
-// the device-side decision of encoder_kernels.cuh (stage_needs_exact), restated here for the conditional launch
-__device__ __forceinline__ bool nt_skip(const NtArgs& g) {
-    if (!g.skip_flag) return false;
-    if (__ldg(g.skip_flag) != 0u) return false;
-    if (!g.skip_cancel) return true;
-    double E = 0.0, D = 0.0;
-    for (int i = 0; i < 32; ++i) { E += __ldg(g.skip_cancel + 2 * i); D += __ldg(g.skip_cancel + 2 * i + 1); }
-    return !(E > 64.0 * D);
-}
+__device__ __forceinline__ bool nt_skip(const NtArgs& g) { return g.skip_flag && __ldg(g.skip_flag) == 0u; }
 
 template <bool FAST, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair::THREADS2, 1)
@@ -1155,8 +1147,7 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
                      const plane_t* B_lo, int N, int ldb, const float* bias, float* C, int ldc, float* psum,
                      float* psq, int relu, cudaStream_t st, const float* out_scale = nullptr, int fast = 0,
                      unsigned int* gmax_bits = nullptr, const uint8_t* keep = nullptr, float inv_keep = 1.f,
-                     const float* out_scale2 = nullptr, const unsigned int* skip_flag = nullptr,
-                     const double* skip_cancel = nullptr) {
+                     const float* out_scale2 = nullptr, const unsigned int* skip_flag = nullptr) {
     if (K % BK != 0 || N % BN != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldc % 4 != 0) return CP_ERR_ARG;
     if (keep && (ldc != N || ((uintptr_t)keep) % 16 != 0)) return CP_ERR_ARG;     // mask laid out like a dense [M][N] C
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_out;
@@ -1168,7 +1159,6 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
     if ((rc = make_tmap_2d(&tb_lo, B_lo, N, K, ldb, BN)) != CP_OK) return rc;
     NtArgs g{C, ldc, bias, psum, psq, M, N, K, relu, out_scale, fast, gmax_bits, keep, inv_keep, out_scale2};
     g.skip_flag = skip_flag;
-    g.skip_cancel = skip_cancel;
     if (g_use_pair && M > BM) {
         CUtensorMap tb_hi2, tb_lo2;                                   // B boxes of 64 rows: half a tile per CTA
         if ((rc = make_tmap_2d(&tb_hi2, B_hi, N, K, ldb, BN / 2)) != CP_OK) return rc;

@@ -178,8 +178,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
 }
+// Arrive on an mbarrier of (possibly) another CTA of the cluster.  Default semantics (.release at .cta scope), as
+// CUTLASS' ClusterBarrier::arrive does: the TMEM reads this hands back are ordered by tcgen05.fence::before_thread_sync
+// + the barrier itself.  The .release.cluster form costs a MEMBAR.ALL.GPU + ERRBAR per arrival -- 23 % of the epilogue
+// warps' stall samples in the CTA-pair GEMM (profiles/r2_ncu_gemm_stalls.txt) -- and orders nothing this kernel needs.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // bit 24 of a shared::cluster address selects the odd CTA of a pair: clearing it addresses the leader
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;

@@ -150,9 +150,12 @@ class FlatGradAllReduce:
             views.append(v)
             off += p.numel()
         torch._foreach_copy_(views, [p.grad for p in ps])
-        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
-        if self.average:
-            self._flat.div_(world_size())
+        if self.average and dist.get_backend() == "nccl":
+            dist.all_reduce(self._flat, op=dist.ReduceOp.AVG)          # the division happens inside the collective
+        else:
+            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+            if self.average:
+                self._flat.div_(world_size())
         torch._foreach_copy_([p.grad for p in ps], views)
 
 

@@ -25,9 +25,16 @@ class GraphedTrainStep:
     def __init__(self, model, optimizers, example_emg, sync_grads=None, warmup=3):
         """model: models.Model (training mode); optimizers: Adam(..., capturable=True) instances;
         example_emg: a (B,41,1,1,12) CUDA batch that fixes the captured shape.  The capture runs `warmup`
-        + 1 real steps on it; parameters, BatchNorm buffers and optimizer state are restored afterwards."""
+        + 1 real steps on it; parameters, BatchNorm buffers and optimizer state are restored afterwards.
+        sync_grads: dist.FlatGradAllReduce for sample-sharded training (one process per GPU): the gradient
+        all-reduce (and, with model.emg_net.sync_bn, the BatchNorm-statistics all-reduces) are captured INSIDE the
+        graph -- NCCL collectives are capturable -- so every rank replays one graph per step and the ranks' host
+        threads stop being a source of skew.  Every rank must construct and call the step in lockstep."""
+        self.sync_grads = sync_grads
         if sync_grads is not None:
-            raise NotImplementedError("graph capture covers the single-GPU step (cross-validation folds)")
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_backend() != "nccl":
+                raise RuntimeError("capturing the gradient all-reduce in a CUDA graph needs the NCCL backend")
         for o in optimizers:
             if not all(g.get("capturable", False) for g in o.param_groups):
                 raise RuntimeError("GraphedTrainStep needs optim.Adam(..., capturable=True)")
@@ -75,6 +82,8 @@ class GraphedTrainStep:
         for o in self.optimizers:
             o.zero_grad(set_to_none=True)
         total.backward()
+        if self.sync_grads is not None:
+            self.sync_grads()
         for o in self.optimizers:
             o.step()
         handle = logits if not torch.is_tensor(logits) else logits._cp_handle
