@@ -12,7 +12,8 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
-SO_PATH = os.path.join(_PKG, "libcpros.so")
+# CP_LIBCPROS: another build of the same sources (A/B measurements of kernel variants); default: the in-tree library
+SO_PATH = os.environ.get("CP_LIBCPROS") or os.path.join(_PKG, "libcpros.so")
 SOURCES = ["version.cu", "gather.cu", "encoder.cu", "head.cu", "clip.cu", "vote.cu", "l2.cu", "preprocess.cu", "philox.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

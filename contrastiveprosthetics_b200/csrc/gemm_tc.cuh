@@ -389,19 +389,23 @@ constexpr int THREADS2 = 320;            // TMA warp, MMA warp, 8 epilogue warps
 constexpr int EPI2 = 256;
 constexpr int B_HALF = (BN / 2) * BK * 2;                 // 8 KB: this CTA's 64 rows of a B plane
 constexpr int STAGE2 = 2 * TILE_BYTES + 2 * B_HALF;       // A_hi, A_lo, B_hi/2, B_lo/2 = 48 KB
-constexpr int STAGES2 = 3;
+// operand ring depth: 4 stages when the epilogue boxes leave room for them (plain epilogue: 192 + 32 KB), 3 with the
+// 64 KB of boxes of the fused BN-backward epilogue
+constexpr int MAX_STAGES2 = 4;
+__host__ __device__ constexpr int stages2(int epi) { return epi == 1 ? 3 : 4; }
 struct Smem2 {
-    uint64_t full[STAGES2], empty[STAGES2], tmem_full[2], tmem_empty[2];
+    uint64_t full[MAX_STAGES2], empty[MAX_STAGES2], tmem_full[2], tmem_empty[2];
     uint64_t ybar[16];              // EPI_BNBWD: arrival of the two activation boxes of each epilogue warp
     uint32_t tmem_base;
     uint32_t pad;
-    float csum[4][BN];
-    float csq[4][BN];
+    float csum[4][BN];              // per TMEM-quadrant column sums of a tile (sums, then sums of squares: two phases)
 };
-constexpr int SMEM2 = STAGES2 * STAGE2 + 8 * OUT_BOX + 1024 + (int)sizeof(Smem2);
+// no alignment slack: the dynamic shared-memory array is declared __align__(1024)
+constexpr int SMEM2 = stages2(0) * STAGE2 + 8 * OUT_BOX + (int)sizeof(Smem2);
 // EPI_BNBWD: per epilogue warp two 4 KB boxes, one per 32-column chunk: first the TMA-loaded [32 rows][32 fp32]
 // activation tile, then (once it is in registers) the chunk's [32][32] fp16 hi and lo planes on their way out
-constexpr int SMEM2_BNBWD = STAGES2 * STAGE2 + 8 * 2 * OUT_BOX + 1024 + (int)sizeof(Smem2);
+constexpr int SMEM2_BNBWD = stages2(1) * STAGE2 + 8 * 2 * OUT_BOX + (int)sizeof(Smem2);
+static_assert(SMEM2 <= 232448 && SMEM2_BNBWD <= 232448, "shared memory per CTA");
 }  // namespace pair
 
 constexpr int EPI_STD = 0, EPI_BNBWD = 1;
@@ -415,9 +419,10 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                        const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_c2,
                        const __grid_constant__ CUtensorMap tm_y, const NtArgs g) {
     using namespace pair;
+    constexpr int STAGES2 = stages2(EPI);
     if (nt_skip(g)) return;                      // uniform over the grid: taken before any barrier / TMEM allocation
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_pair[];
+    uint8_t* tiles = smem_pair;                  // 1024-aligned (128B-swizzled TMA boxes / UMMA descriptors)
     uint8_t* out_boxes = tiles + STAGES2 * STAGE2;                              // 8 x 4 KB (EPI_BNBWD: 8 x 8 KB), 1024-aligned
     Smem2* sm = reinterpret_cast<Smem2*>(out_boxes + 8 * OUT_BOX * (EPI == EPI_BNBWD ? 2 : 1));
 
@@ -625,6 +630,7 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             const int n0 = (int)(t % tiles_n) * BN;
             const int64_t row = tile_m * BM + q * 32 + lane;
             const bool row_ok = row < g.M;
+            float cs[2] = {0.f, 0.f}, cq[2] = {0.f, 0.f};               // this lane's column sum / sum of squares per chunk
             // dropout mask of this thread's two chunks, fetched while the tile's MMAs are still running
             Mask32 mk[2];
             if (g.keep) {
@@ -670,8 +676,8 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                 store_box_tma(&tm_c, out_boxes + (warp - 2) * OUT_BOX, v, lane, col, tile_m * BM + q * 32);
                 if (g.psum && g.keep) {
                     masked_col_sums(v, g, mk[c], lane);
-                    sm->csum[q][cl + lane] = v[0];
-                    sm->csq[q][cl + lane] = 0.f;
+                    cs[c] = v[0];
+                    cq[c] = 0.f;
                 } else if (g.psum) {
                     float sq[32];
 #pragma unroll
@@ -681,8 +687,8 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                     }
                     warp_col_reduce32(v, lane);
                     warp_col_reduce32(sq, lane);
-                    sm->csum[q][cl + lane] = v[0];
-                    sm->csq[q][cl + lane] = sq[0];
+                    cs[c] = v[0];
+                    cq[c] = sq[0];
                 }
             }
             // accumulator drained -> hand it back to the leader's MMA warp
@@ -690,12 +696,25 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_cluster(tc::mapa(tc::smem_u32(&sm->tmem_empty[acc]), 0));
             if (g.psum) {
+                // sum over the 4 TMEM quadrants (warps) through one shared array: sums first, then sums of squares
+                const bool writer = et < BN && tile_m * BM < g.M;
+                sm->csum[q][half * 64 + lane] = cs[0];
+                sm->csum[q][half * 64 + 32 + lane] = cs[1];
                 tc::named_bar_sync(1, EPI2);
-                if (et < BN && tile_m * BM < g.M) {
+                if (writer)
                     g.psum[tile_m * g.N + n0 + et] = sm->csum[0][et] + sm->csum[1][et] + sm->csum[2][et] + sm->csum[3][et];
-                    g.psq[tile_m * g.N + n0 + et] = sm->csq[0][et] + sm->csq[1][et] + sm->csq[2][et] + sm->csq[3][et];
+                if (g.keep) {                                   // masked column sums: no second moment
+                    if (writer) g.psq[tile_m * g.N + n0 + et] = 0.f;
+                    tc::named_bar_sync(1, EPI2);
+                } else {
+                    tc::named_bar_sync(1, EPI2);
+                    sm->csum[q][half * 64 + lane] = cq[0];
+                    sm->csum[q][half * 64 + 32 + lane] = cq[1];
+                    tc::named_bar_sync(1, EPI2);
+                    if (writer)
+                        g.psq[tile_m * g.N + n0 + et] = sm->csum[0][et] + sm->csum[1][et] + sm->csum[2][et] + sm->csum[3][et];
+                    tc::named_bar_sync(1, EPI2);
                 }
-                tc::named_bar_sync(1, EPI2);
             }
         }
         if (lane == 0) tc::tma_store_wait_read();
