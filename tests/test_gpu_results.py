@@ -61,7 +61,7 @@ def test_results_main_after_train_main(tmp_path):
     assert mean.shape == std.shape == mn.shape == mx.shape == (40,)
     assert mn[-1] == mx[-1] and abs(mean[-1] - mn[-1]) < 1e-12 and std[-1] < 1e-12
     assert abs(mean[-1] - np.trace(counts) / (G * 41)) < 1e-12
-    assert np.all(mn <= mean) and np.all(mean <= mx)
+    assert np.all(mn <= mean + 1e-12) and np.all(mean <= mx + 1e-12)      # (a mean of equal values may round up an ulp)
     # the full-set subset decision equals the voted y_pred (restricted argmax == argmax, same vote)
     tables1 = cpres.subset_tables(torch.from_numpy(logs).cuda(), 25, sizes=[40], trials_per_size=2)
     assert abs(tables1["mean"][0] - mean[-1]) < 1e-12
