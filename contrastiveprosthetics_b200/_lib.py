@@ -57,11 +57,17 @@ class EncoderOpts(ctypes.Structure):
                 ("bn_momentum", ctypes.c_float), ("bn_eps", ctypes.c_float),
                 ("dropout_p", ctypes.c_float), ("save_for_backward", ctypes.c_int32),
                 ("dropout_seed", ctypes.c_uint64), ("ext_masks", ctypes.c_void_p), ("dropout_step", ctypes.c_void_p),
-                ("allreduce", ctypes.c_void_p), ("allreduce_user", ctypes.c_void_p)]
+                ("allreduce", ctypes.c_void_p), ("allreduce_user", ctypes.c_void_p),
+                ("trunk_only", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 # int (*cp_allreduce_fn)(void *user, void *buf, size_t count, void *stream)   (SyncBN hook, include/cpros.h)
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
+
+
+class ClsTensors(ctypes.Structure):
+    _fields_ = [("w1", ctypes.c_void_p), ("b1", ctypes.c_void_p), ("bn_w", ctypes.c_void_p), ("bn_b", ctypes.c_void_p),
+                ("bn_rm", ctypes.c_void_p), ("bn_rv", ctypes.c_void_p), ("w2", ctypes.c_void_p)]
 
 
 class GloveTensors(ctypes.Structure):
@@ -133,6 +139,11 @@ def lib():
     L.cp_glove_forward.argtypes = [ctypes.POINTER(GloveTensors), _vp, _i64, _vp, _vp, _sz, ctypes.POINTER(GloveOpts), _vp]
     L.cp_glove_backward.argtypes = [ctypes.POINTER(GloveTensors), _vp, _i64, ctypes.POINTER(GloveTensors), _vp, _sz,
                                     ctypes.POINTER(GloveOpts), _vp]
+    L.cp_cls_workspace_bytes.restype = _sz
+    L.cp_cls_workspace_bytes.argtypes = [_i64]
+    L.cp_cls_forward_backward.argtypes = [ctypes.POINTER(ClsTensors), _vp, _vp, _i64, _i32, ctypes.c_float, ctypes.c_float,
+                                          _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ClsTensors), _vp, _sz, _vp]
+    L.cp_cls_forward_backward.restype = ctypes.c_int
     L.cp_vote_eval.argtypes = [_vp, _i64, _i32, _i32, _vp, _vp, _vp]
     L.cp_rank_rows.argtypes = [_vp, _i64, _vp, _vp]
     L.cp_subset_eval.argtypes = [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp]
@@ -162,7 +173,8 @@ EXPORTS = ["cp_version", "cp_launch_count", "cp_status_string", "cp_gather_norm"
            "cp_subset_eval", "cp_clip_normalize", "cp_clip_transpose", "cp_clip_sums", "cp_clip_loss",
            "cp_clip_grad", "cp_clip_embed_backward", "cp_glove_workspace_bytes", "cp_glove_forward",
            "cp_glove_backward", "cp_confusion_matrix", "cp_l2_workspace_bytes", "cp_l2_forward", "cp_l2_backward",
-           "cp_emg_preprocess_scratch_elems", "cp_emg_preprocess", "cp_philox4x32_10", "cp_dropout_mask"]
+           "cp_emg_preprocess_scratch_elems", "cp_emg_preprocess", "cp_philox4x32_10", "cp_dropout_mask", "cp_cls_workspace_bytes",
+           "cp_cls_forward_backward"]
 
 
 def check(status, what=""):

@@ -514,6 +514,12 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
                                   (uint64_t)(l - 3), (const unsigned long long*)o->dropout_step, fast));
             continue;
         }
+        if (o->trunk_only) {
+            // --prediction mode: the block output itself (fp32) is the result; the classifier head follows (cls.cuh)
+            CP_TRY(bn_apply<F_FC>(w.Y[l], emb, false, n, w, 2 + l, keep, inv_keep, st, gen_p, o->dropout_seed,
+                                  (uint64_t)(l - 3), (const unsigned long long*)o->dropout_step, fast));
+            continue;
+        }
         // last block: BN (+ dropout) fused with the 512 -> 16 projection
         const int G = pf::grid_for(n);
         const unsigned long long* step = (const unsigned long long*)o->dropout_step;
@@ -579,6 +585,9 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             if (used[b]) CP_CUDA(cudaStreamWaitEvent(st, g_side.done[b], 0));     // WAR on the G1 buffer
             if (stage_done)
                 ;                                      // g1(b) already holds this stage's pre-activation gradient
+            else if (l == CP_N_FC - 1 && o->trunk_only)  // d_emb IS the gradient w.r.t. the last block's output
+                CP_TRY(bn_backward<F_FC>(d_emb, w.Y[l], g1(b), true, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
+                                         gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st, o, false));
             else if (l == CP_N_FC - 1)
                 CP_TRY(last_block_backward(d_emb, g1(b), true, n, w, keep, inv_keep, p, gr, st, o));
             else
@@ -722,7 +731,10 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     } else {
         for (int l = CP_N_FC - 1; l >= 0; --l) {
             const uint8_t* keep = (l >= 3 && o->dropout_p > 0.f) ? w.keep[l - 3] : nullptr;
-            if (l == CP_N_FC - 1)
+            if (l == CP_N_FC - 1 && o->trunk_only)
+                CP_TRY(bn_backward<F_FC>(d_emb, w.Y[l], w.G1, false, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
+                                         gr->bn_w[2 + l], gr->bn_b[2 + l], gr->fc_b[l], st, o));
+            else if (l == CP_N_FC - 1)
                 CP_TRY(last_block_backward(d_emb, w.G1, false, n, w, keep, inv_keep, p, gr, st, o));
             else
                 CP_TRY(bn_backward<F_FC>(w.G0, w.Y[l], w.G1, false, n, w, 2 + l, keep, inv_keep, p->bn_w[2 + l],
@@ -978,3 +990,4 @@ extern "C" int cp_linear_backward(const float* G, const float* A, const float* W
 }
 
 #include "tower.cuh"
+#include "cls.cuh"

@@ -9,8 +9,12 @@ backward goes through libcpros.so (hand-written sm_100a CUDA, see include/cpros.
     Model.forward + .loss     -> cp_head_forward_backward (one fused launch)    (models.py:112-208)
     vote loop in .loss (eval) -> cp_vote_eval                                   (models.py:149-163)
 
-There is no PyTorch/CPU fallback: CPU tensors raise.  `--prediction` and `--glove` modes are out
-of scope (broken in the reference) and raise NotImplementedError.
+    Model.forward + .loss, --prediction -> cp_encoder_forward(trunk_only) + cp_cls_forward_backward
+                                  (classifier head + normalised-logit CE)           (models.py:113-119, 175-196, 300-309)
+
+There is no PyTorch/CPU fallback: CPU tensors raise.  `--glove` (with `--prediction`) is broken in the reference
+(models.py:417 vs 451: a 20-dim input into Linear(256,128)) and raises NotImplementedError; the vote evaluation of
+`--prediction` fails the reference's own shape assertion (models.py:178) and raises the same AssertionError here.
 """
 import ctypes
 
@@ -76,7 +80,7 @@ def _split(params):
     """flat list of 37 tensors -> named groups (order = EMGNet.kernel_params())."""
     conv1_w, conv1_b, conv2_w, conv2_b = params[0:4]
     fc_w, fc_b = params[4:11], params[11:18]
-    proj_w = params[18]
+    proj_w = params[18]                   # None in trunk-only (--prediction) mode
     bn_w, bn_b = params[19:28], params[28:37]
     return conv1_w, conv1_b, conv2_w, conv2_b, fc_w, fc_b, proj_w, bn_w, bn_b
 
@@ -109,17 +113,19 @@ class _EncoderFn(torch.autograd.Function):
         x = x.contiguous()
         n = x.shape[0]
         need_bwd = cfg["need_bwd"]
+        trunk = bool(cfg.get("trunk_only"))
         opts = _lib.EncoderOpts(bn_mode=cfg["bn_mode"], engine=cfg["engine"], bn_momentum=0.1, bn_eps=1e-5,
                                 dropout_p=float(cfg["dropout_p"]), save_for_backward=int(need_bwd),
                                 dropout_seed=int(cfg["seed"]),
                                 ext_masks=_lib.ptr(cfg["ext_masks"], torch.uint8),
-                                dropout_step=_lib.ptr(cfg.get("dropout_step"), torch.int64))
+                                dropout_step=_lib.ptr(cfg.get("dropout_step"), torch.int64),
+                                trunk_only=int(trunk))
         nbytes = L.cp_encoder_workspace_bytes(n, ctypes.byref(opts))
         if nbytes == 0:
             raise RuntimeError("cp_encoder_workspace_bytes rejected the configuration")
         alloc = cfg.get("ws_alloc")          # tests: a caller-owned (guarded) workspace; default: a fresh tensor
         ws = alloc(nbytes) if alloc is not None else torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-        emb = torch.empty((n, 16), dtype=torch.float32, device=x.device)
+        emb = torch.empty((n, 512 if trunk else 16), dtype=torch.float32, device=x.device)
         hook = None
         if cfg.get("sync_bn"):
             hook = _make_sync_hook(ws, cfg.get("group"))
@@ -140,7 +146,7 @@ class _EncoderFn(torch.autograd.Function):
     def backward(ctx, d_emb):
         L = _lib.lib()
         d_emb = d_emb.contiguous()
-        grads = [torch.empty_like(p) for p in ctx.params]
+        grads = [torch.empty_like(p) if p is not None else None for p in ctx.params]
         gt = _fill_tensors(_lib.EncoderTensors(), *_split(grads))
         _lib.check(L.cp_encoder_backward(ctypes.byref(ctx.tens), _lib.ptr(d_emb), ctx.n, ctypes.byref(gt),
                                          _lib.ptr(ctx.ws), ctx.ws.numel(), ctypes.byref(ctx.opts),
@@ -215,6 +221,49 @@ class _LogitsLossFn(torch.autograd.Function):
         return ctx.saved * g_loss, None
 
 
+class _ClsHeadFn(torch.autograd.Function):
+    """--prediction mode: trunk output a7 (N,512) + labels -> (features (N,41), loss, pred, n_correct) through
+    cp_cls_forward_backward; the gradients come out of the SAME call and are scaled by grad_output in backward."""
+
+    @staticmethod
+    def forward(ctx, a7, labels, cfg, w1, b1, bn_w, bn_b, w2):
+        L = _lib.lib()
+        dev = a7.device
+        a7 = a7.contiguous()
+        n = a7.shape[0]
+        labels = labels.reshape(-1).to(torch.int64).contiguous()
+        if labels.numel() != n:
+            raise RuntimeError(f"prediction head: {n} rows but {labels.numel()} labels")
+        feats = torch.empty((n, MAX_TASKS_TRAIN), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        pred = torch.empty((n,), dtype=torch.int32, device=dev)
+        ncor = torch.empty((), dtype=torch.int32, device=dev)
+        want_grad = cfg["want_grad"]
+        P = _lib.ptr
+        params = _lib.ClsTensors(w1=P(w1), b1=P(b1), bn_w=P(bn_w), bn_b=P(bn_b), bn_rm=P(cfg["bn_rm"]),
+                                 bn_rv=P(cfg["bn_rv"]), w2=P(w2))
+        d_a7 = torch.empty_like(a7) if want_grad else None
+        grads = [torch.empty_like(t) for t in (w1, b1, bn_w, bn_b, w2)] if want_grad else None
+        gstruct = _lib.ClsTensors(w1=P(grads[0]), b1=P(grads[1]), bn_w=P(grads[2]), bn_b=P(grads[3]),
+                                  w2=P(grads[4])) if want_grad else None
+        nbytes = L.cp_cls_workspace_bytes(n)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(L.cp_cls_forward_backward(ctypes.byref(params), P(a7), P(labels), n, cfg["bn_mode"], 0.1, 1e-5,
+                                             P(feats), P(loss), P(pred), P(ncor), P(d_a7),
+                                             ctypes.byref(gstruct) if want_grad else None, P(ws), nbytes, _lib.stream()),
+                   "cp_cls_forward_backward")
+        ctx.saved = (d_a7, grads)
+        ctx.mark_non_differentiable(feats, pred, ncor)
+        return feats, loss, pred, ncor
+
+    @staticmethod
+    def backward(ctx, _gf, g_loss, _gp, _gn):
+        d_a7, grads = ctx.saved
+        if d_a7 is None:
+            raise RuntimeError("prediction head was run without gradients")
+        return (d_a7 * g_loss, None, None) + tuple(g * g_loss for g in grads)
+
+
 class FusedLogits:
     """What `Model.forward` returns in training: a handle to the fused head's results.  The 41x41
     similarity tiles never leave shared memory; `.materialize()` re-runs the head with a logits
@@ -237,9 +286,9 @@ class Model(nn.Module):
 
     def __init__(self, params, adabn=True, train_model=True, prediction=False, glove=False, device="cuda"):
         super().__init__()
-        if prediction or glove:
-            raise NotImplementedError("--prediction / --glove modes are out of scope (broken in the "
-                                      "reference: models.py:178 vs 337, 417 vs 451)")
+        if glove:
+            raise NotImplementedError("--glove is broken in the reference (models.py:417 vs 451: the 20-dim glove row "
+                                      "is fed to Linear(256,128)); the glove tower is available through clip.ClipModel")
         self.params = params
         self.train_model = train_model
         self.adabn = adabn
@@ -288,6 +337,8 @@ class Model(nn.Module):
 
     # -- forward (models.py:112-130)
     def forward(self, EMG, GLOVE, labels):
+        if self.prediction:
+            return self._forward_prediction(EMG, labels)
         B, T = EMG.shape[0], EMG.shape[1]
         W = EMG.shape[2]
         if T != MAX_TASKS_TRAIN:
@@ -303,8 +354,36 @@ class Model(nn.Module):
             return logits
         return handle
 
+    # -- --prediction mode (models.py:113-119: features = emg_net(EMG) normalised per row; 175-196: CE + accuracy)
+    def _forward_prediction(self, EMG, labels):
+        net = self.emg_net
+        a7 = net.encode_flat(EMG)                                  # (N,512) trunk output
+        if not self.training and VOTE:
+            # the reference's own evaluation of this mode dies on `assert len(shape)==3, "wrong logit shape for val
+            # time"` (models.py:178: EMGNet.forward returns 2-D logits in prediction mode, models.py:337)
+            raise AssertionError("wrong logit shape for val time")
+        lin1, bn, lin2 = net.last[0], _bn_leaf(net.last[2]), net.last[3]
+        if self.adabn:
+            bn_mode, rm, rv = _lib.BN_BATCH, None, None
+        else:
+            bn_mode = _lib.BN_BATCH_UPDATE if self.training else _lib.BN_RUNNING
+            rm, rv = bn.running_mean, bn.running_var
+            if self.training:
+                bn.num_batches_tracked += 1
+        cfg = {"bn_mode": bn_mode, "bn_rm": rm, "bn_rv": rv, "want_grad": torch.is_grad_enabled() and self.training}
+        feats, loss, pred, ncor = _ClsHeadFn.apply(a7, labels, cfg, lin1.weight, lin1.bias, bn.weight, bn.bias, lin2.weight)
+        feats._cp_cls = (loss, pred, ncor, a7.shape[0])
+        return feats
+
     # -- loss + accuracy (+ vote) (models.py:132-208)
     def loss(self, logits, labels):
+        if self.prediction:
+            h = getattr(logits, "_cp_cls", None)
+            if h is None:
+                raise RuntimeError("prediction mode: pass the tensor Model.forward returned (the loss is fused with it)")
+            loss, pred, ncor, n = h
+            self._pending.append(("cls", ncor, n))
+            return loss
         handle = logits if isinstance(logits, FusedLogits) else getattr(logits, "_cp_handle", None)
         if handle is not None:
             loss, pred, ncor, B, W = handle.loss, handle.pred, handle.ncor, handle.B, handle.W
@@ -341,6 +420,9 @@ class Model(nn.Module):
     def _resolve(self):
         T = MAX_TASKS_TRAIN
         for kind, a, b in self._pending:
+            if kind == "cls":                    # (prediction == labels).mean()  (models.py:190-195): float64 count / n
+                self._corrects.append(float(np.float64(int(a.item())) / np.float64(b)))
+                continue
             if kind == "train":
                 counts = a.cpu().numpy().astype(np.float64)
             else:
@@ -381,6 +463,8 @@ class Model(nn.Module):
 
     def l2(self):
         """models.py:225-228: reg * sum of un-squared Frobenius norms (tiny; plain torch ops)."""
+        if self.prediction:
+            return self.emg_net.l2() * self.params['reg_emg']
         return self.glove_net.l2() * self.params['reg_glove'] + self.emg_net.l2() * self.params['reg_emg']
 
 
@@ -432,9 +516,7 @@ class EMGNet(nn.Module):
 
     def __init__(self, d_e, dp=.5, adabn=True, train=True, prediction=False, device="cuda"):
         super().__init__()
-        if prediction:
-            raise NotImplementedError("prediction head is out of scope")
-        if d_e != 16:
+        if d_e != 16 and not prediction:
             raise NotImplementedError("libcpros is built for d_e = 16 (train.py:182 des=[16])")
         self.device = torch.device(device)
         self.d_e = d_e
@@ -461,8 +543,12 @@ class EMGNet(nn.Module):
             if i >= 2:
                 blocks.append(nn.Dropout(self.dp))
         self.linear = nn.Sequential(*blocks)
-        self.bits = self.d_e
-        self.last = nn.Sequential(nn.Linear(512, self.d_e, bias=False))
+        if prediction:                       # models.py:300-309
+            self.bits = MAX_TASKS_TRAIN
+            self.last = nn.Sequential(nn.Linear(512, 128), nn.ReLU(), bn1(128), nn.Linear(128, self.bits, bias=False))
+        else:
+            self.bits = self.d_e
+            self.last = nn.Sequential(nn.Linear(512, self.d_e, bias=False))
         self.to(self.device)
 
         self.engine = _lib.ENGINE_TC         # tcgen05 GEMMs on the 3-product fp16 split (fp32-level accuracy); ENGINE_SIMT = fp32 FFMA
@@ -490,11 +576,13 @@ class EMGNet(nn.Module):
 
     def kernel_params(self):
         c, l, b = self._convs(), self._linears(), self._bns()
+        proj = None if self.prediction else self.last[0].weight        # trunk-only: the classifier head follows (cls.cuh)
         return ([c[0].weight, c[0].bias, c[1].weight, c[1].bias] + [m.weight for m in l] +
-                [m.bias for m in l] + [self.last[0].weight] + [m.weight for m in b] + [m.bias for m in b])
+                [m.bias for m in l] + [proj] + [m.weight for m in b] + [m.bias for m in b])
 
     def encode_flat(self, EMG):
-        """(B,41,W,1,12) or anything reshapeable to (-1,12) -> (N,16) embeddings, row order unchanged."""
+        """(B,41,W,1,12) or anything reshapeable to (-1,12) -> (N,16) embeddings, row order unchanged
+        (prediction mode: the (N,512) output of the 7th linear block)."""
         self.shape = EMG.shape
         x = EMG.reshape(-1, EMG_DIM)
         bns = self._bns()
@@ -518,6 +606,7 @@ class EMGNet(nn.Module):
                "dropout_step": self.dropout_step, "bn_rm": rm, "bn_rv": rv,
                "need_bwd": torch.is_grad_enabled() and self.training,
                "tap": self.debug_tap, "sync_bn": self._sync_active(), "group": self.process_group,
+               "trunk_only": self.prediction,
                "ws_alloc": getattr(self, "ws_alloc", None)}
         return _EncoderFn.apply(x, cfg, *self.kernel_params())
 
@@ -543,6 +632,9 @@ class EMGNet(nn.Module):
 
     def forward(self, EMG):
         """models.py:319-342 incl. the (B,41,W) -> (B*W,41) regrouping."""
+        if self.prediction:
+            raise RuntimeError("prediction mode: the classifier head is fused with its loss (cp_cls_forward_backward) "
+                               "and needs the labels; call Model.forward(EMG, GLOVE, labels)")
         out = self.encode_flat(EMG)
         shape = self.shape
         out = out.reshape((shape[0], shape[1], shape[2], self.bits)).transpose(1, 2)
@@ -558,17 +650,20 @@ class GLOVENet(nn.Module):
 
     def __init__(self, d_e, dp=.5, adabn=True, train=True, prediction=False, device="cuda"):
         super().__init__()
-        if prediction:
-            raise NotImplementedError("prediction head is out of scope")
         self.device = torch.device(device)
         self.d_e = d_e
         self.dp = dp
         self.prediction = prediction
         self.conv_glove = nn.Sequential(nn.Flatten())
         self.linear = nn.Sequential(nn.Flatten())
-        self.bits = self.d_e
+        self.bits = MAX_TASKS_TRAIN if prediction else self.d_e
         self.easy = nn.Sequential(nn.Linear(MAX_TASKS_TRAIN, self.d_e))
-        self.last = nn.Sequential(nn.Linear(512 // 2, self.bits, bias=False))   # unused in forward, still regularised
+        if prediction:                       # models.py:413-421 (parameters only: never called without --glove)
+            bn = AdaBatchNorm1d(128, device=device) if adabn else nn.BatchNorm1d(128)
+            self.last = nn.Sequential(nn.Linear(512 // 2, 128), nn.ReLU(), bn, nn.Dropout(self.dp),
+                                      nn.Linear(128, self.bits, bias=False))
+        else:
+            self.last = nn.Sequential(nn.Linear(512 // 2, self.bits, bias=False))   # unused in forward, still regularised
         self.to(self.device)
 
     def table_params(self):

@@ -98,6 +98,10 @@ typedef struct cp_encoder_opts {
                                    * of the same launch then draws a fresh mask when the caller bumps the counter */
     cp_allreduce_fn allreduce; /* NULL: BatchNorm statistics over this rank's rows (local BN).  Non-NULL: SyncBN, */
     void *allreduce_user;      /* statistics over the rows of every rank (global-batch parity)      */
+    int32_t trunk_only;        /* --prediction mode (models.py:300-309): stop after the 7th linear block.  `emb` of
+                                * cp_encoder_forward is then the (n,512) block output, `d_emb` of cp_encoder_backward
+                                * its gradient; proj_w is not used (may be NULL) and its gradient is not written */
+    int32_t reserved;
 } cp_encoder_opts;
 
 size_t cp_encoder_workspace_bytes(int64_t n_windows, const cp_encoder_opts *opts);
@@ -235,6 +239,27 @@ int cp_glove_forward(const cp_glove_tensors *params, const float *glove, int64_t
 int cp_glove_backward(const cp_glove_tensors *params, const float *d_emb, int64_t n,
                       const cp_glove_tensors *grads, void *workspace, size_t workspace_bytes,
                       const cp_glove_opts *opts, void *stream);
+
+/* ---------------------------------------------------------------- --prediction mode: classifier head
+ * EMGNet.last with prediction=True (models.py:300-309) on the trunk output (cp_encoder_forward, trunk_only), followed
+ * by Model.forward's row normalisation (models.py:118) and prediction_loss (models.py:175-196), in one call:
+ *   a7 (n,512) -> Linear(512->128) -> ReLU -> BN(128) -> Linear(128->41, no bias) -> z;  features = z / ||z||
+ *   loss = mean CE(features, labels);  pred = first-max argmax;  n_correct = #(pred == label)
+ * Outputs (each may be NULL): features (n,41), loss, pred (n) int32, n_correct (1) int32.  d_a7 (n,512) and grads are
+ * both NULL (forward only) or both given (every grad tensor is OVERWRITTEN; bn_rm / bn_rv of grads ignored).
+ * bn_mode as in cp_encoder_opts (stock BN: running statistics of nn.BatchNorm1d(128)). */
+#define CP_CLS_HIDDEN 128
+typedef struct cp_cls_tensors {
+    float *w1, *b1;            /* (128,512), (128)   emg_net.last.0.{weight,bias}      */
+    float *bn_w, *bn_b;        /* (128)              emg_net.last.2[.bn].{weight,bias} */
+    float *bn_rm, *bn_rv;      /* (128)              running statistics (stock BN) or NULL */
+    float *w2;                 /* (41,128)           emg_net.last.3.weight             */
+} cp_cls_tensors;
+size_t cp_cls_workspace_bytes(int64_t n);
+int cp_cls_forward_backward(const cp_cls_tensors *params, const float *a7, const int64_t *labels, int64_t n,
+                            int bn_mode, float bn_momentum, float bn_eps, float *features, float *loss,
+                            int32_t *pred, int32_t *n_correct, float *d_a7, const cp_cls_tensors *grads,
+                            void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------- K4: windowed majority vote
  * Replaces the vote loop of contrastive_loopy_loss (models.py:149-163, constants.py:74-78).

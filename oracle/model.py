@@ -25,10 +25,11 @@ def bn_prefix(adabn, seq, idx):
     return f"emg_net.{seq}.{idx}.bn" if adabn else f"emg_net.{seq}.{idx}"
 
 
-def init_state(seed=42, adabn=True, d_e=16):
+def init_state(seed=42, adabn=True, d_e=16, prediction=False):
     """Parameter init in the reference's construction order (models.py:67-85, 231-317, 353-430):
     EMGNet (conv, conv, 7 linears, projection) -> GLOVENet (easy, last) -> logit_scale, so that
-    `torch.manual_seed(seed)` consumes the CPU generator exactly as `Model(...)` does."""
+    `torch.manual_seed(seed)` consumes the CPU generator exactly as `Model(...)` does.
+    prediction=True: the classifier heads of models.py:300-309 / 413-421 instead of the projections."""
     torch.manual_seed(seed)
     sd = {}
 
@@ -50,9 +51,20 @@ def init_state(seed=42, adabn=True, d_e=16):
         put(f"emg_net.linear.{li}", nn.Linear(fan_in, 512))
         bn("linear", bi, 512, False)
         fan_in = 512
-    put("emg_net.last.0", nn.Linear(512, d_e, bias=False))
-    put("glove_net.easy.0", nn.Linear(N_TASKS, d_e))
-    put("glove_net.last.0", nn.Linear(512 // 2, d_e, bias=False))
+    if prediction:
+        put("emg_net.last.0", nn.Linear(512, 128))
+        m = nn.BatchNorm1d(128, momentum=0, track_running_stats=False) if adabn else nn.BatchNorm1d(128)
+        put("emg_net.last.2.bn" if adabn else "emg_net.last.2", m)
+        put("emg_net.last.3", nn.Linear(128, N_TASKS, bias=False))
+        put("glove_net.easy.0", nn.Linear(N_TASKS, d_e))
+        put("glove_net.last.0", nn.Linear(512 // 2, 128))
+        m = nn.BatchNorm1d(128, momentum=0, track_running_stats=False) if adabn else nn.BatchNorm1d(128)
+        put("glove_net.last.2.bn" if adabn else "glove_net.last.2", m)
+        put("glove_net.last.4", nn.Linear(128, N_TASKS, bias=False))
+    else:
+        put("emg_net.last.0", nn.Linear(512, d_e, bias=False))
+        put("glove_net.easy.0", nn.Linear(N_TASKS, d_e))
+        put("glove_net.last.0", nn.Linear(512 // 2, d_e, bias=False))
     out = {"logit_scale": torch.ones([]) * np.log(1) / 0.07}    # models.py:81  (== 0.0)
     out.update(sd)
     return out
@@ -88,7 +100,7 @@ def _relu(out, relu_masks, i):
 
 
 def encoder_forward(sd, x, adabn=True, training=True, dropout_masks=None, dp=0.0, new_stats=None,
-                    taps=None, relu_masks=None):
+                    taps=None, relu_masks=None, prediction=False):
     """EMGNet.forward up to the projection (models.py:319-323): x (N,12) -> emb (N,d_e).
 
     dropout_masks: optional list of 4 {0,1} tensors (N,512) for the dropout after linear blocks
@@ -122,7 +134,28 @@ def encoder_forward(sd, x, adabn=True, training=True, dropout_masks=None, dp=0.0
             if training and dropout_masks is not None and dp > 0:
                 out = out * dropout_masks[d].to(out.dtype) / (1.0 - dp)
             d += 1
+    if prediction:
+        # EMGNet.last with prediction=True (models.py:300-309): Linear(512,128) -> ReLU -> BN(128) -> Linear(128,41)
+        if taps is not None:
+            taps["trunk"] = out
+        out = F.relu(F.linear(out, sd["emg_net.last.0.weight"], sd["emg_net.last.0.bias"]))
+        pre = "emg_net.last.2.bn" if adabn else "emg_net.last.2"
+        out = _batch_norm(sd, pre, out, adabn, training, new_stats)
+        return F.linear(out, sd["emg_net.last.3.weight"])
     return F.linear(out, sd["emg_net.last.0.weight"])
+
+
+def prediction_step(sd, EMG, labels, adabn=True, training=True, dropout_masks=None, dp=0.0, new_stats=None):
+    """Model.forward + Model.loss with prediction=True, glove=False (models.py:113-119, 175-196) outside the (broken)
+    vote evaluation: features = z / ||z||, loss = F.cross_entropy(features, labels), accuracy = mean(argmax == labels).
+    EMG: anything reshapeable to (-1,12) with one row per label.  Returns dict(features, loss, pred, correct)."""
+    z = encoder_forward(sd, EMG.reshape(-1, EMG_DIM), adabn, training, dropout_masks, dp, new_stats, prediction=True)
+    feats = z / z.norm(dim=-1, keepdim=True)
+    labels = labels.reshape(-1).to(torch.long)
+    loss = F.cross_entropy(feats, labels)
+    pred = F.softmax(feats, dim=-1).argmax(-1)
+    correct = float((pred.detach().numpy() == labels.numpy()).mean())
+    return {"features": feats, "loss": loss, "pred": pred, "correct": correct}
 
 
 def class_table(sd):

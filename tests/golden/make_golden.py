@@ -250,6 +250,64 @@ def gen_dropout():
     print("dropout.npz", len(out), "arrays")
 
 
+def gen_prediction():
+    """--prediction mode (models.py:113-119, 175-196, 300-309): the reference's Model(prediction=True) on the CPU -- init
+    digests, one training forward / loss / backward on a fixed batch in both BN modes, and the AssertionError of its
+    vote evaluation."""
+    out = {}
+    ds = make_dataset(False)
+    tw = RU.TaskWrapper(ds)
+    for adabn in (True, False):
+        tag = "adabn" if adabn else "stockbn"
+        torch.manual_seed(42)
+        model = RM.Model(params=dict(PARAMS), adabn=adabn, prediction=True, device="cpu").to(torch.float32)
+        out[f"{tag}|keys"] = np.array(list(model.state_dict().keys()))
+        for k, v in model.state_dict().items():
+            v = v.detach().to(torch.float64).reshape(-1)
+            out[f"{tag}|init|{k}"] = np.array([v.sum().item(), v.abs().sum().item()] + v[:4].tolist())
+        tw.set_train()
+        tw.emg_rand = torch.from_numpy(fixed_perm(41, ds.D, 11))
+        tw.glove_rand = torch.from_numpy(fixed_perm(41, ds.glover.D, 12))
+        model.set_train()
+        samples = [tw[i] for i in (0, 7, 19, 3)]
+        EMG = torch.stack([s[0] for s in samples])
+        GLOVE = torch.stack([s[1] for s in samples])
+        label = torch.stack([s[2] for s in samples]).reshape(-1)
+        feats = model.forward(EMG, GLOVE, label)
+        loss = model.loss(feats, label)
+        l2 = model.l2()
+        (loss + l2).backward()
+        out[f"{tag}|EMG"] = EMG.numpy()
+        out[f"{tag}|label"] = label.numpy()
+        out[f"{tag}|features"] = feats.detach().numpy()
+        out[f"{tag}|loss"] = np.float64(loss.item())
+        out[f"{tag}|l2"] = np.float64(l2.item())
+        out[f"{tag}|correct"] = np.float64(model.corrects[-1])
+        for n, p in model.named_parameters():
+            if p.grad is not None:
+                grad_digest(n, p.grad, out, tag)
+            else:
+                out[f"{tag}|gnone|{n}"] = np.int64(1)
+        if not adabn:
+            for k, v in model.state_dict().items():
+                if "running" in k or "num_batches" in k:
+                    out[f"{tag}|after1|{k}"] = v.numpy().copy()
+        # the vote evaluation of this mode is broken in the reference itself
+        tw.set_test()
+        tw.emg_rand = torch.from_numpy(fixed_perm(41, ds.D, 13))
+        tw.glove_rand = torch.from_numpy(fixed_perm(41, ds.glover.D, 14))
+        model.set_test()
+        e, g, l = tw[0]
+        try:
+            with torch.no_grad():
+                model.loss(model.forward(e[None], g[None], l), l)
+            out[f"{tag}|eval_error"] = np.array("none")
+        except AssertionError as ex:
+            out[f"{tag}|eval_error"] = np.array(str(ex))
+    np.savez_compressed(os.path.join(HERE, "prediction.npz"), **out)
+    print("prediction.npz", len(out), "arrays")
+
+
 def copy_ref_artifacts():
     """The reference's own result artefacts = its only golden vectors."""
     dst = os.path.join(HERE, "ref_data")
@@ -312,8 +370,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
         gen_preprocess()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "prediction":
+        gen_prediction()
+        sys.exit(0)
     gen_dataset()
     gen_model()
     gen_dropout()
     gen_preprocess()
+    gen_prediction()
     copy_ref_artifacts()

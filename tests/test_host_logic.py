@@ -97,12 +97,13 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     """sizeof / offsetof of every struct in include/cpros.h, as gcc lays them out, == the ctypes mirrors."""
     fields = {"cp_encoder_tensors": ["conv1_w", "fc_w", "proj_w", "bn_w", "bn_rv"],
               "cp_encoder_opts": ["bn_mode", "engine", "bn_momentum", "bn_eps", "dropout_p", "save_for_backward",
-                                  "dropout_seed", "ext_masks", "dropout_step", "allreduce", "allreduce_user"],
+                                  "dropout_seed", "ext_masks", "dropout_step", "allreduce", "allreduce_user", "trunk_only"],
+              "cp_cls_tensors": ["w1", "b1", "bn_w", "bn_b", "bn_rm", "bn_rv", "w2"],
               "cp_glove_tensors": ["w0", "bn0_b", "w", "b", "bn_w", "bn_b", "proj_w"],
               "cp_glove_opts": ["glove_dim", "save_for_backward", "bn_eps", "dropout_p", "dropout_seed", "ext_masks",
                                 "dropout_step"]}
     mirrors = {"cp_encoder_tensors": _lib.EncoderTensors, "cp_encoder_opts": _lib.EncoderOpts,
-               "cp_glove_tensors": _lib.GloveTensors, "cp_glove_opts": _lib.GloveOpts}
+               "cp_glove_tensors": _lib.GloveTensors, "cp_glove_opts": _lib.GloveOpts, "cp_cls_tensors": _lib.ClsTensors}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "cpros.h"', 'int main(void) {']
     for st, fs in fields.items():
         lines.append(f'printf("{st} %zu\\n", sizeof({st}));')
