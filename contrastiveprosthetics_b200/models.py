@@ -253,6 +253,8 @@ class _ClsHeadFn(torch.autograd.Function):
                                              ctypes.byref(gstruct) if want_grad else None, P(ws), nbytes, _lib.stream()),
                    "cp_cls_forward_backward")
         ctx.saved = (d_a7, grads)
+        if cfg.get("tap") is not None:          # parity tap: the workspace starts with relu(linear1(a7)), (n,128) fp32
+            cfg["tap"]["relu_head"] = ws[:n * 128 * 4].view(torch.float32).reshape(n, 128).clone()
         ctx.mark_non_differentiable(feats, pred, ncor)
         return feats, loss, pred, ncor
 
@@ -370,7 +372,8 @@ class Model(nn.Module):
             rm, rv = bn.running_mean, bn.running_var
             if self.training:
                 bn.num_batches_tracked += 1
-        cfg = {"bn_mode": bn_mode, "bn_rm": rm, "bn_rv": rv, "want_grad": torch.is_grad_enabled() and self.training}
+        cfg = {"bn_mode": bn_mode, "bn_rm": rm, "bn_rv": rv, "want_grad": torch.is_grad_enabled() and self.training,
+               "tap": net.debug_tap}
         feats, loss, pred, ncor = _ClsHeadFn.apply(a7, labels, cfg, lin1.weight, lin1.bias, bn.weight, bn.bias, lin2.weight)
         feats._cp_cls = (loss, pred, ncor, a7.shape[0])
         return feats

@@ -247,7 +247,8 @@ int cp_glove_backward(const cp_glove_tensors *params, const float *d_emb, int64_
  *   loss = mean CE(features, labels);  pred = first-max argmax;  n_correct = #(pred == label)
  * Outputs (each may be NULL): features (n,41), loss, pred (n) int32, n_correct (1) int32.  d_a7 (n,512) and grads are
  * both NULL (forward only) or both given (every grad tensor is OVERWRITTEN; bn_rm / bn_rv of grads ignored).
- * bn_mode as in cp_encoder_opts (stock BN: running statistics of nn.BatchNorm1d(128)). */
+ * bn_mode as in cp_encoder_opts (stock BN: running statistics of nn.BatchNorm1d(128)).
+ * Parity tap: on return the workspace begins with relu(Linear1(a7)), (n,128) fp32. */
 #define CP_CLS_HIDDEN 128
 typedef struct cp_cls_tensors {
     float *w1, *b1;            /* (128,512), (128)   emg_net.last.0.{weight,bias}      */

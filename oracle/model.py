@@ -138,7 +138,8 @@ def encoder_forward(sd, x, adabn=True, training=True, dropout_masks=None, dp=0.0
         # EMGNet.last with prediction=True (models.py:300-309): Linear(512,128) -> ReLU -> BN(128) -> Linear(128,41)
         if taps is not None:
             taps["trunk"] = out
-        out = F.relu(F.linear(out, sd["emg_net.last.0.weight"], sd["emg_net.last.0.bias"]))
+        out = F.linear(out, sd["emg_net.last.0.weight"], sd["emg_net.last.0.bias"])
+        out = _relu(out, relu_masks, 9) if relu_masks is not None and len(relu_masks) > 9 else F.relu(out)
         pre = "emg_net.last.2.bn" if adabn else "emg_net.last.2"
         out = _batch_norm(sd, pre, out, adabn, training, new_stats)
         return F.linear(out, sd["emg_net.last.3.weight"])

@@ -48,6 +48,7 @@ def test_prediction_step_matches_reference_fixture(gp, adabn, engine):
     check_grads(gp, tag, grads, 3e-2)                 # vs the stored reference gradients: ReLU-flip noise (164 windows)
     # vs the oracle with the kernel's ReLU pattern: rounding-level agreement on every tensor
     pat = [(model.emg_net.read_activation(s, 0).cpu() > 0) for s in range(9)]
+    pat.append(model.emg_net.debug_tap["relu_head"].cpu() > 0)          # ... and the head's own ReLU
     _, ofeats, oloss, _, ograds, _ = oracle_step(gp, tag, adabn, relu_masks=pat)
     assert rel_err(feats, ofeats) < 1e-5
     for k, g in ograds.items():
@@ -90,6 +91,7 @@ def test_prediction_head_vs_oracle(n, dp):
     loss = m.loss(feats, labels.cuda())
     loss.backward()
     pat = [(m.emg_net.read_activation(s, 0).cpu() > 0) for s in range(9)]
+    pat.append(m.emg_net.debug_tap["relu_head"].cpu() > 0)
     p = {k: (v.clone().requires_grad_(True) if k in OM.trainable_keys(sd) else v.clone()) for k, v in sd.items()}
     z = OM.encoder_forward(p, x, adabn, True, masks, dp, relu_masks=pat, prediction=True)
     of = z / z.norm(dim=-1, keepdim=True)
