@@ -3,9 +3,10 @@ section 8f row 1).
 
 The reference's workflow is 150 independent `train_loop(epochs=1)` runs at `--batch_size=8` (go.sh:6): 328 windows
 per step, every kernel a few microseconds long, the GPU almost idle.  Across GPUs the folds are split per rank
-(`train.cross_validate`); WITHIN a GPU `ConcurrentFolds` advances K folds in lockstep: each fold owns its model,
-its two Adam optimizers, ONE CUDA graph of the whole step (`graph.GraphedTrainStep`) and ONE stream, so K graphs
-are in flight at a time and the SMs one fold leaves idle run the others.  The folds draw the same batches (one
+(`train.cross_validate`); WITHIN a GPU `ConcurrentFolds` advances K folds in lockstep: each fold owns its model and
+its two Adam optimizers, and the whole steps of ALL K folds are captured into ONE CUDA graph with K parallel
+branches (one capture stream per fold): a lockstep is one graph launch -- the host pays for one launch instead of
+K x ~150 kernel nodes -- and the SMs one fold leaves idle run the others.  The folds draw the same batches (one
 gather per step for all K; each fold would otherwise draw its own permutation of the same split, train.py:83-86) and
 stay statistically independent through their own initialisation-free hyper-parameters and dropout streams.
 
@@ -28,6 +29,7 @@ class ConcurrentFolds:
         self.device = dataset.device
         self.models, self.opts, self.steps, self.streams = [], [], [], []
         example = dataset.get_batch(torch.arange(batch_size))[0]
+        self.static_emg = example.clone()                     # the one input tensor of the K-fold graph
         self.label_full = torch.arange(example.shape[1], device=self.device).repeat(batch_size)
         for k, params in enumerate(params_list):
             torch.manual_seed(42 if seeds is None else seeds[k])             # models.py:12
@@ -39,10 +41,26 @@ class ConcurrentFolds:
                     optim.Adam(model.glove_net.parameters(), lr=params['lr_glove'], weight_decay=0, capturable=True, fused=True)]
             self.models.append(model)
             self.opts.append(opts)
-            self.steps.append(GraphedTrainStep(model, opts, example))
+            self.steps.append(GraphedTrainStep(model, opts, example, capture=False, static_emg=self.static_emg))
             self.streams.append(torch.cuda.Stream(device=self.device))
-        self.losses = [[] for _ in params_list]
-        self.accs = [[] for _ in params_list]
+        # ONE graph: fork a branch per fold from the capture stream, join them, stack the folds' results
+        T = example.shape[1]
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            cs = torch.cuda.current_stream(self.device)
+            outs = []
+            for step, s in zip(self.steps, self.streams):
+                s.wait_stream(cs)
+                with torch.cuda.stream(s):
+                    outs.append(step.body())
+            for s in self.streams:
+                cs.wait_stream(s)
+            self.loss_all = torch.stack([o[0] for o in outs])                         # (K,)
+            # per-batch accuracy = mean over groups of (#correct / 41)  (models.py:166-172)
+            self.acc_all = torch.stack([o[1] for o in outs]).float().mean(1) / T        # (K,)
+        for step in self.steps:
+            step.restore()
+        self._hist = []                 # per lockstep: (loss (K,), acc (K,)) clones
 
     def _eager_step(self, k, EMG):
         model, opts = self.models[k], self.opts[k]
@@ -60,37 +78,58 @@ class ConcurrentFolds:
 
     def step(self, EMG):
         """One training step of EVERY fold on the batch EMG (B, 41, 1, 1, 12)."""
+        if EMG.shape[0] == self.batch_size:
+            self.static_emg.copy_(EMG)
+            self.graph.replay()                               # the steps of all K folds: one launch
+            # the graph's static outputs are overwritten by the next replay
+            self._hist.append((self.loss_all.clone(), self.acc_all.clone()))
+            return
+        # ragged last batch of an epoch: eagerly, fold by fold on the folds' streams
         main = torch.cuda.current_stream(self.device)
         ready = main.record_event()
+        losses, accs = [], []
         for k, s in enumerate(self.streams):
             s.wait_event(ready)
             EMG.record_stream(s)
             with torch.cuda.stream(s):
-                if EMG.shape[0] == self.batch_size:
-                    loss, ncor = self.steps[k](EMG)
-                    loss = loss.clone()                       # the graph's static outputs are overwritten by the next replay
-                else:
-                    loss, ncor = self._eager_step(k, EMG)
-                self.losses[k].append(loss)
-                # per-batch accuracy = mean over groups of (#correct / 41)  (models.py:166-172)
-                self.accs[k].append(ncor.float().mean() / EMG.shape[1])
+                loss, ncor = self._eager_step(k, EMG)
+                losses.append(loss)
+                accs.append(ncor.float().mean() / EMG.shape[1])
+        self.join()
+        self._hist.append((torch.stack(losses), torch.stack(accs)))
 
     def join(self):
         main = torch.cuda.current_stream(self.device)
         for s in self.streams:
             main.wait_stream(s)
 
+    # per-fold views of the lockstep history (fold k: list of 0-d tensors, one per step since the last reset)
+    @property
+    def losses(self):
+        return [[h[0][k] for h in self._hist] for k in range(len(self.models))]
+
+    @losses.setter
+    def losses(self, _value):
+        self._hist = []
+
+    @property
+    def accs(self):
+        return [[h[1][k] for h in self._hist] for k in range(len(self.models))]
+
+    @accs.setter
+    def accs(self, _value):
+        pass
+
     def run_epoch(self, shuffle=True, generator=None):
         """One pass over the training split for all folds.  Returns the mean training loss of every fold."""
         for m in self.models:
             m.set_train()
-        self.losses = [[] for _ in self.models]
-        self.accs = [[] for _ in self.models]
+        self._hist = []
         for (EMG, _, _) in self.dataset.batches(self.batch_size, shuffle=shuffle, generator=generator):
             self.step(EMG)
         self.join()
-        return [torch.stack(l).mean().item() for l in self.losses]
+        return torch.stack([h[0] for h in self._hist]).mean(0).tolist()
 
     def train_accuracy(self):
         """Model.correct() of the epoch (mean of the per-batch accuracies, models.py:210-211) for every fold."""
-        return [torch.stack(a).mean().item() for a in self.accs]
+        return torch.stack([h[1] for h in self._hist]).mean(0).tolist()

@@ -22,14 +22,16 @@ def _opt_tensors(opt):
 
 
 class GraphedTrainStep:
-    def __init__(self, model, optimizers, example_emg, sync_grads=None, warmup=3):
+    def __init__(self, model, optimizers, example_emg, sync_grads=None, warmup=3, capture=True, static_emg=None):
         """model: models.Model (training mode); optimizers: Adam(..., capturable=True) instances;
         example_emg: a (B,41,1,1,12) CUDA batch that fixes the captured shape.  The capture runs `warmup`
         + 1 real steps on it; parameters, BatchNorm buffers and optimizer state are restored afterwards.
         sync_grads: dist.FlatGradAllReduce for sample-sharded training (one process per GPU): the gradient
         all-reduce (and, with model.emg_net.sync_bn, the BatchNorm-statistics all-reduces) are captured INSIDE the
         graph -- NCCL collectives are capturable -- so every rank replays one graph per step and the ranks' host
-        threads stop being a source of skew.  Every rank must construct and call the step in lockstep."""
+        threads stop being a source of skew.  Every rank must construct and call the step in lockstep.
+        capture=False: only the warm-up; the caller captures `body()` itself (folds.ConcurrentFolds puts the steps of
+        K folds into ONE graph) and calls `restore()` afterwards.  static_emg: share the graph's input tensor."""
         self.sync_grads = sync_grads
         if sync_grads is not None:
             import torch.distributed as dist
@@ -41,36 +43,47 @@ class GraphedTrainStep:
         self.model, self.optimizers = model, list(optimizers)
         dev = example_emg.device
         self.B = example_emg.shape[0]
-        self.static_emg = example_emg.clone()
+        self.static_emg = example_emg.clone() if static_emg is None else static_emg
         self.static_label = torch.arange(example_emg.shape[1], device=dev).repeat(self.B)
         self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         model.emg_net.dropout_step = self._step_dev
 
-        saved_model = {k: v.clone() for k, v in model.state_dict().items()}
+        self._saved_model = {k: v.clone() for k, v in model.state_dict().items()}
         # optimizer state is created lazily by the first step: snapshot it if it exists, else it is reset to zero
-        saved_opt = [[t.clone() for t in _opt_tensors(o)] if len(o.state) else None for o in self.optimizers]
+        self._saved_opt = [[t.clone() for t in _opt_tensors(o)] if len(o.state) else None for o in self.optimizers]
         stream = torch.cuda.Stream(device=dev)
         stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(stream):
             for _ in range(warmup):
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(stream)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss, self.n_correct = self._body()
-        # undo the warm-up / capture steps IN PLACE (the graph holds the addresses)
+        self.graph = None
+        self.steps = 0
+        if capture:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss, self.n_correct = self._body()
+            self.restore()
+
+    def body(self):
+        """One step on `static_emg` (what a capture records).  Returns (loss, per-group correct counts)."""
+        return self._body()
+
+    def restore(self):
+        """Undo the warm-up / capture steps IN PLACE (a graph holds the addresses)."""
         with torch.no_grad():
-            sd = model.state_dict()
-            for k, v in saved_model.items():
+            sd = self.model.state_dict()
+            for k, v in self._saved_model.items():
                 sd[k].copy_(v)
-            for o, saved in zip(self.optimizers, saved_opt):
+            for o, saved in zip(self.optimizers, self._saved_opt):
                 for i, t in enumerate(_opt_tensors(o)):
                     if saved is None:
                         t.zero_()
                     else:
                         t.copy_(saved[i])
             self._step_dev.zero_()
-        model.reset()
+        self.model.reset()
+        self._saved_model = self._saved_opt = None
         self.steps = 0
 
     def _body(self):
