@@ -137,6 +137,14 @@ class DB23(data.Dataset):
     def __len__(self):
         return self.TASKS * self.D
 
+    def subjects_of(self, idx):
+        """Subject (index into constants' 46-person axis) of every row id in `idx` -- row id = class*D + k with k
+        running over (person, repetition, window) of the current split (load.py:233-251).  Feeds the per-subject
+        AdaBN of models.EMGNet (models.py:245)."""
+        idx = torch.as_tensor(idx, device=self.device)
+        per_person = self.D // self.PEOPLE
+        return self.people_mask.to(torch.long)[(idx % self.D) // per_person]
+
     def _stats(self):
         if self.emg_stats is None:
             return None, None

@@ -338,14 +338,16 @@ class Model(nn.Module):
         return self.glove_net(GLOVE, labels)
 
     # -- forward (models.py:112-130)
-    def forward(self, EMG, GLOVE, labels):
+    def forward(self, EMG, GLOVE, labels, subjects=None):
+        """subjects (optional, beyond the reference's signature): (B,41) subject of every class row -> per-subject
+        AdaBN (EMGNet.per_subject)."""
         if self.prediction:
             return self._forward_prediction(EMG, labels)
         B, T = EMG.shape[0], EMG.shape[1]
         W = EMG.shape[2]
         if T != MAX_TASKS_TRAIN:
             raise RuntimeError(f"expected {MAX_TASKS_TRAIN} class rows per group, got {T}")
-        emb = self.emg_net.encode_flat(EMG)                       # (B*41*W, 16), order (b, class, w)
+        emb = self.emg_net.encode_flat(EMG, subjects)             # (B*41*W, 16), order (b, class, w)
         w, b = self.glove_net.table_params()
         want_grad = torch.is_grad_enabled() and self.training
         want_logits = (not self.training) or self.materialize_logits
@@ -563,6 +565,13 @@ class EMGNet(nn.Module):
         self.ext_dropout_masks = None        # (4, N, 512) uint8 keep masks injected by parity tests
         self.debug_tap = None                # set to {} to keep the workspace for read_activation()
         self.shape = None
+        # Per-subject AdaBN ("momentum = 0 and batch per subject in order to have adaptive normalization",
+        # models.py:245 -- described there, never implemented): with per_subject = True and a subject id per class
+        # row (EMG._cp_subjects from TaskWrapper(with_subjects=True), or the `subjects` argument) the batch statistics
+        # of every BatchNorm are taken over the windows of ONE subject at a time; gamma / beta stay shared.
+        self.per_subject = False
+        self.segment_streams = 4             # subject segments are independent encoder passes: run them on this many streams
+        self._seg_pool = None
 
     # ordered views of the module tree for the kernels
     def _convs(self):
@@ -583,10 +592,15 @@ class EMGNet(nn.Module):
         return ([c[0].weight, c[0].bias, c[1].weight, c[1].bias] + [m.weight for m in l] +
                 [m.bias for m in l] + [proj] + [m.weight for m in b] + [m.bias for m in b])
 
-    def encode_flat(self, EMG):
+    def encode_flat(self, EMG, subjects=None):
         """(B,41,W,1,12) or anything reshapeable to (-1,12) -> (N,16) embeddings, row order unchanged
-        (prediction mode: the (N,512) output of the 7th linear block)."""
+        (prediction mode: the (N,512) output of the 7th linear block).  subjects: see `per_subject`."""
         self.shape = EMG.shape
+        if subjects is None and self.per_subject:
+            subjects = getattr(EMG, "_cp_subjects", None)
+            if subjects is None:
+                raise RuntimeError("per-subject AdaBN needs the subject of every class row: TaskWrapper.with_subjects "
+                                   "= True, or pass subjects=")
         x = EMG.reshape(-1, EMG_DIM)
         bns = self._bns()
         if self.adabn:
@@ -611,7 +625,67 @@ class EMGNet(nn.Module):
                "tap": self.debug_tap, "sync_bn": self._sync_active(), "group": self.process_group,
                "trunk_only": self.prediction,
                "ws_alloc": getattr(self, "ws_alloc", None)}
+        if subjects is not None:
+            return self._encode_per_subject(x, subjects, cfg)
         return _EncoderFn.apply(x, cfg, *self.kernel_params())
+
+    def _encode_per_subject(self, x, subjects, cfg):
+        """Per-subject AdaBN: BatchNorm is the only coupling between the rows of a batch, so statistics per subject ==
+        one independent encoder pass per subject segment with the shared weights (autograd sums the segments' weight
+        gradients).  Rows are sorted by subject (stable), every segment runs the ordinary kernels on its contiguous
+        slice -- segments round-robin over `segment_streams` streams, they are small -- and the embeddings return in
+        the caller's row order.  One host sync per call (the segment sizes)."""
+        if not self.adabn:
+            raise RuntimeError("per-subject statistics are an AdaBN mode (batch statistics in train and eval); "
+                               "running-statistics BatchNorm has one set of statistics")
+        if cfg["sync_bn"] or cfg["tap"] is not None:
+            raise RuntimeError("per-subject AdaBN does not combine with sync_bn / debug_tap")
+        n = x.shape[0]
+        subjects = torch.as_tensor(subjects, device=x.device).to(torch.long)
+        if subjects.numel() != n:              # one id per class row (B,41) -> one per window (B,41,W)
+            if n % subjects.numel() != 0:
+                raise RuntimeError(f"{subjects.numel()} subject ids for {n} windows")
+            subjects = subjects.reshape(-1, 1).expand(-1, n // subjects.numel())
+        subjects = subjects.reshape(-1)
+        order = torch.argsort(subjects, stable=True)
+        sizes = [c for c in torch.bincount(subjects).tolist() if c > 0]
+        if min(sizes) < 2:
+            # nn.BatchNorm1d: "Expected more than 1 value per channel when training"
+            raise ValueError("per-subject AdaBN: a subject has a single window in this batch")
+        xs = x[order]
+        masks = cfg["ext_masks"][:, order] if cfg["ext_masks"] is not None else None
+        dev = x.device
+        main = torch.cuda.current_stream(dev)
+        P = max(1, min(int(self.segment_streams), len(sizes)))
+        if P > 1 and (self._seg_pool is None or len(self._seg_pool) < P):
+            self._seg_pool = [torch.cuda.Stream(device=dev) for _ in range(P)]
+        ready = main.record_event() if P > 1 else None
+        params = self.kernel_params()
+        parts, a = [], 0
+        for i, c in enumerate(sizes):
+            seg_cfg = dict(cfg)
+            seg_cfg["seed"] = (cfg["seed"] + 0x9E3779B97F4A7C15 * (i + 1)) & 0xFFFFFFFFFFFFFFFF   # own dropout stream
+            if P > 1:
+                s = self._seg_pool[i % P]
+                s.wait_event(ready)
+                with torch.cuda.stream(s):               # (the mask slice is copied on the segment's stream too)
+                    seg_cfg["ext_masks"] = masks[:, a:a + c].contiguous() if masks is not None else None
+                    out = _EncoderFn.apply(xs[a:a + c], seg_cfg, *params)
+                out.record_stream(main)
+            else:
+                seg_cfg["ext_masks"] = masks[:, a:a + c].contiguous() if masks is not None else None
+                out = _EncoderFn.apply(xs[a:a + c], seg_cfg, *params)
+            parts.append(out)
+            a += c
+        if P > 1:
+            for s in self._seg_pool[:P]:                 # every pool stream reads slices of xs / masks
+                xs.record_stream(s)
+                if masks is not None:
+                    masks.record_stream(s)
+                main.wait_stream(s)
+        inv = torch.empty_like(order)
+        inv[order] = torch.arange(n, device=dev)
+        return torch.cat(parts)[inv]
 
     def _sync_active(self):
         import torch.distributed as dist

@@ -92,6 +92,9 @@ def train_loop(dataset, params, checkpoint=False, checkpoint_dir="../checkpoints
     model = Model(params=params, train_model=True, adabn=args.no_adabn, prediction=args.prediction,
                   glove=args.glove, device=str(dataset.device)).to(torch.float32)
     model.emg_net.sync_bn = getattr(args, "sync_bn", False)      # global-batch BatchNorm statistics under torchrun
+    if getattr(args, "per_subject_adabn", False):                # models.py:245: BatchNorm statistics per subject
+        model.emg_net.per_subject = True
+        dataset.with_subjects = True
     if load is not None:
         print("Loading model")
         model.load_state_dict(torch.load(load + ".pt"))
@@ -297,6 +300,9 @@ def build_parser():
     parser.add_argument('--sync_bn', action='store_true',
                         help='under torchrun: BatchNorm statistics over the rows of every rank (global-batch parity) '
                              'instead of rank-local ones')
+    parser.add_argument('--per_subject_adabn', action='store_true',
+                        help='AdaBN statistics per subject (models.py:245 "batch per subject"): every BatchNorm '
+                             'normalises the windows of one subject at a time, in training and evaluation')
     parser.add_argument('--fused_adam', action='store_true',
                         help="torch.optim.Adam(fused=True): same update rule in one kernel per optimizer (what bench.py uses)")
     parser.add_argument('--concurrent_folds', type=int, default=1,

@@ -139,6 +139,7 @@ class TaskWrapper:
         self.__dict__["dataset"] = dataset
         self.device = dataset.device
         self.with_glove = with_glove
+        self.with_subjects = False         # True: batches carry the subject of every class row (EMG._cp_subjects)
 
     def return_rand(self, D):
         T = self.dataset.TASKS
@@ -181,6 +182,8 @@ class TaskWrapper:
         B = items.numel()
         rows = self.emg_rand[:, items].t().contiguous()                     # (B,41)
         EMG = self.dataset[rows]                                            # one launch
+        if self.with_subjects:
+            EMG._cp_subjects = self.dataset.subjects_of(rows)              # (B,41) -> per-subject AdaBN (models.py:245)
         if self.glove_rand is not None:
             grow = self.glove_rand[:, items % self.dataset.glover.D].t().contiguous()
             GLOVE = self.dataset.glover[grow]

@@ -75,9 +75,21 @@ def trainable_keys(sd):
             and k != "logit_scale"]
 
 
-def _batch_norm(sd, prefix, x, adabn, training, new_stats):
-    """models.py:17-35 (AdaBN: batch statistics in train AND eval) or stock nn.BatchNorm."""
+def _batch_norm(sd, prefix, x, adabn, training, new_stats, subjects=None):
+    """models.py:17-35 (AdaBN: batch statistics in train AND eval) or stock nn.BatchNorm.
+    subjects (N,) ints: PER-SUBJECT AdaBN -- "momentum = 0 and batch per subject in order to have adaptive
+    normalization" (models.py:245, described there and never implemented: PARITY UNPINNED): the batch statistics of
+    every feature are taken over the rows of one subject at a time; gamma / beta are shared."""
     w, b = sd[prefix + ".weight"], sd[prefix + ".bias"]
+    if adabn and subjects is not None:
+        parts, index = [], []
+        for s in torch.unique(subjects).tolist():
+            rows = torch.nonzero(subjects == s).reshape(-1)
+            parts.append(F.batch_norm(x[rows], None, None, w, b, True, 0.0, BN_EPS))
+            index.append(rows)
+        inv = torch.empty(x.shape[0], dtype=torch.long)
+        inv[torch.cat(index)] = torch.arange(x.shape[0])
+        return torch.cat(parts)[inv]
     if adabn:
         return F.batch_norm(x, None, None, w, b, True, 0.0, BN_EPS)
     rm = sd[prefix + ".running_mean"].clone()
@@ -100,13 +112,14 @@ def _relu(out, relu_masks, i):
 
 
 def encoder_forward(sd, x, adabn=True, training=True, dropout_masks=None, dp=0.0, new_stats=None,
-                    taps=None, relu_masks=None, prediction=False):
+                    taps=None, relu_masks=None, prediction=False, subjects=None):
     """EMGNet.forward up to the projection (models.py:319-323): x (N,12) -> emb (N,d_e).
 
     dropout_masks: optional list of 4 {0,1} tensors (N,512) for the dropout after linear blocks
     4..7 (models.py:282-297); applied as mask/(1-dp) in training.  None and dp==0 -> identity.
     taps: optional dict that receives intermediate activations (for layer-level parity tests).
-    relu_masks: optional list of 9 0/1 tensors (2 conv stages (N,64,1,12), 7 linear stages (N,512))."""
+    relu_masks: optional list of 9 0/1 tensors (2 conv stages (N,64,1,12), 7 linear stages (N,512)).
+    subjects: optional (N,) subject id per window -> per-subject AdaBN (see _batch_norm)."""
     out = x.reshape(-1, 1, 1, EMG_DIM)
     stage = 0
     for ci, bi in CONV_BLOCKS:
@@ -118,7 +131,7 @@ def encoder_forward(sd, x, adabn=True, training=True, dropout_masks=None, dp=0.0
         if taps is not None:
             taps[f"relu{stage}"] = out
         stage += 1
-        out = _batch_norm(sd, bn_prefix(adabn, "conv_emg", bi), out, adabn, training, new_stats)
+        out = _batch_norm(sd, bn_prefix(adabn, "conv_emg", bi), out, adabn, training, new_stats, subjects)
     out = out.flatten(1)
     d = 0
     for li, bi, has_dp in LINEAR_BLOCKS:
@@ -129,7 +142,7 @@ def encoder_forward(sd, x, adabn=True, training=True, dropout_masks=None, dp=0.0
         if taps is not None:
             taps[f"relu{stage}"] = out
         stage += 1
-        out = _batch_norm(sd, bn_prefix(adabn, "linear", bi), out, adabn, training, new_stats)
+        out = _batch_norm(sd, bn_prefix(adabn, "linear", bi), out, adabn, training, new_stats, subjects)
         if has_dp:
             if training and dropout_masks is not None and dp > 0:
                 out = out * dropout_masks[d].to(out.dtype) / (1.0 - dp)
@@ -165,13 +178,16 @@ def class_table(sd):
     return sd["glove_net.easy.0.weight"].t() + sd["glove_net.easy.0.bias"][None, :]
 
 
-def forward_logits(sd, EMG, adabn=True, training=True, dropout_masks=None, dp=0.0, new_stats=None):
+def forward_logits(sd, EMG, adabn=True, training=True, dropout_masks=None, dp=0.0, new_stats=None, subjects=None):
     """Model.forward contrastive branch (models.py:121-130) incl. the EMGNet regrouping
     (models.py:337-341) and the GLOVENet expand in eval (models.py:463-464).
 
     EMG: (B,41,W,1,12).  Returns logits (B*W,41,41): group (b,w), row = EMG class, col = class table."""
     B, T, W = EMG.shape[0], EMG.shape[1], EMG.shape[2]
-    emb = encoder_forward(sd, EMG.reshape(-1, EMG_DIM), adabn, training, dropout_masks, dp, new_stats)
+    if subjects is not None:                   # (B,41) subject of every class row -> one id per window
+        subjects = subjects.reshape(B, T, 1).expand(B, T, W).reshape(-1)
+    emb = encoder_forward(sd, EMG.reshape(-1, EMG_DIM), adabn, training, dropout_masks, dp, new_stats,
+                          subjects=subjects)
     emb = emb.reshape(B, T, W, -1).transpose(1, 2).reshape(B * W, T, -1)
     emb = emb / emb.norm(dim=-1, keepdim=True)
     tab = class_table(sd).to(emb.dtype)
@@ -261,7 +277,7 @@ def l2_penalty(sd, reg_emg, reg_glove):
 
 
 def train_step_grads(sd, EMG, adabn=True, dp=0.0, dropout_masks=None, reg_emg=0.0, reg_glove=0.0,
-                     dtype=torch.float32):
+                     dtype=torch.float32, subjects=None):
     """One train_loop iteration up to backward (train.py:95-105): returns (res, grads, new_stats)."""
     p = {}
     for k, v in sd.items():
@@ -272,7 +288,7 @@ def train_step_grads(sd, EMG, adabn=True, dp=0.0, dropout_masks=None, reg_emg=0.
         else:
             p[k] = v.clone()
     new_stats = {}
-    logits = forward_logits(p, EMG.to(dtype), adabn, True, dropout_masks, dp, new_stats)
+    logits = forward_logits(p, EMG.to(dtype), adabn, True, dropout_masks, dp, new_stats, subjects=subjects)
     res = contrastive_loss(logits, True)
     l2 = l2_penalty(p, reg_emg, reg_glove)
     total = res["loss"] + l2
