@@ -18,6 +18,7 @@
 // min(#tiles, 148); two TMEM accumulators (2 x 128 columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1; 3-stage shared-memory ring (A_hi, A_lo, B_hi, B_lo: 4 x 16 KB per stage).
 #pragma once
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -864,6 +865,151 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_cons
     if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------- CTA-pair weight gradient
+// Same math as gemm_tc_tn_kernel on a 256 (o) x 128 (c) tile owned by a pair of CTAs (cluster 2x1x1, cta_group::2
+// MMAs issued by the leader).  The single-CTA kernel streams 64 KB of operands per k-block and 128 x 128 tile --
+// 83 B/clk/SM at the tensor rate of the 3-product split, the L2 -> SM wall the K-major kernel hit before it was
+// paired.  Here each CTA stages its own 128 o-columns of G (2 MN blocks per plane) but only ONE 64-wide MN block of
+// the A planes -- the pair's tensor cores read each other's half -- so a k-block costs 48 KB per CTA (62 B/clk/SM)
+// and the ring is 4 stages deep.  Barriers as in gemm_tc_nt_pair_kernel: TMA completions of both CTAs land on the
+// leader's `full`, tcgen05.commit multicasts `empty` / `tmem_full` to both CTAs, the epilogue warps of both CTAs hand
+// the accumulator back on the leader's `tmem_empty`.  Chain cutting and the register-side running sums are unchanged.
+namespace tnp {
+constexpr int A_HALF = (BN / 2) * BK * 2;                 // 8 KB: this CTA's [64 rows r][64 halves] block of an A plane
+constexpr int STAGE = 2 * TILE_BYTES + 2 * A_HALF;        // G_hi, G_lo, A_hi/2, A_lo/2 = 48 KB
+constexpr int NSTAGES = 4;
+constexpr int SMEM = NSTAGES * STAGE + (int)sizeof(Smem); // the dynamic array is declared __align__(1024)
+static_assert(NSTAGES <= MAX_STAGES && SMEM <= 232448, "shared memory per CTA");
+}  // namespace tnp
+
+template <bool FAST>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_tc_tn_pair_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant__ CUtensorMap tm_g_lo,
+                       const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                       const TnArgs g) {
+    using namespace tnp;
+    extern __shared__ __align__(1024) uint8_t smem_tnp[];
+    uint8_t* tiles = smem_tnp;
+    Smem* sm = reinterpret_cast<Smem*>(tiles + NSTAGES * STAGE);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t rank = tc::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int o0 = (blockIdx.x / 2) * 2 * BM + (int)rank * BM;      // this CTA's 128 output rows
+    const int c0 = blockIdx.y * BN;                                 // the pair's 128 output columns
+    const int64_t r_begin = (int64_t)blockIdx.z * g.rows_per_split;
+    const int64_t r_end = min(g.R, r_begin + g.rows_per_split);
+    const int kblocks = (int)((r_end - r_begin + BK - 1) / BK);
+    const int chunks = (kblocks + CHUNK_KB - 1) / CHUNK_KB;
+
+    if (warp == 0 && tc::elect_one()) {
+        tc::prefetch_tmap(&tm_g_hi); tc::prefetch_tmap(&tm_g_lo);
+        tc::prefetch_tmap(&tm_a_hi); tc::prefetch_tmap(&tm_a_lo);
+        for (int s = 0; s < NSTAGES; ++s) { tc::mbar_init(&sm->full[s], 1); tc::mbar_init(&sm->empty[s], 1); }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(&sm->tmem_full[a], 1);
+            tc::mbar_init(&sm->tmem_empty[a], 8);        // 4 epilogue warps x 2 CTAs arrive on the leader's copy
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) {
+        tc::tmem_alloc_pair(&sm->tmem_base, TMEM_COLS);
+        tc::tmem_relinquish_pair();
+    }
+    tc::tc_fence_before();
+    tc::cluster_sync();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = sm->tmem_base;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            int s = 0; uint32_t ph = 0;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                tc::mbar_wait(&sm->empty[s], ph ^ 1);
+                uint8_t* st = tiles + s * STAGE;
+                const int r = (int)(r_begin + (int64_t)kb * BK);
+                if (leader) tc::mbar_expect_tx(&sm->full[s], FAST ? STAGE : 2 * STAGE);     // bytes of both CTAs
+                tc::tma_load_3d_pair(st, &tm_g_hi, &sm->full[s], 0, r, o0 / 64);
+                if (!FAST) tc::tma_load_3d_pair(st + TILE_BYTES, &tm_g_lo, &sm->full[s], 0, r, o0 / 64);
+                tc::tma_load_3d_pair(st + 2 * TILE_BYTES, &tm_a_hi, &sm->full[s], 0, r, c0 / 64 + (int)rank);
+                if (!FAST) tc::tma_load_3d_pair(st + 2 * TILE_BYTES + A_HALF, &tm_a_lo, &sm->full[s], 0, r, c0 / 64 + (int)rank);
+                if (++s == NSTAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && tc::elect_one()) {
+            constexpr uint32_t idesc = tc::idesc_f16(2 * BM, BN, 1, 1);
+            int s = 0; uint32_t ph = 0;
+            int kb = 0;
+            for (int ch = 0; ch < chunks; ++ch) {
+                const int acc = ch & 1;
+                tc::mbar_wait(&sm->tmem_empty[acc], ((ch >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d = tmem_base + acc * ACC_COLS;
+                const uint32_t dc = d + BN;
+                const int kb_end = min(kblocks, kb + CHUNK_KB);
+                for (bool first = true; kb < kb_end; ++kb) {
+                    tc::mbar_wait(&sm->full[s], ph);
+                    tc::tc_fence_after();
+                    const uint32_t base = tc::smem_u32(tiles + s * STAGE);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint32_t ko = k * 2048;                 // 16 rows of 128 B
+                        const uint64_t g_hi = tc::smem_desc_sw128(base + ko, MN_BLOCK, 1024);
+                        const uint64_t g_lo = tc::smem_desc_sw128(base + TILE_BYTES + ko, MN_BLOCK, 1024);
+                        const uint64_t a_hi = tc::smem_desc_sw128(base + 2 * TILE_BYTES + ko, MN_BLOCK, 1024);
+                        const uint64_t a_lo = tc::smem_desc_sw128(base + 2 * TILE_BYTES + A_HALF + ko, MN_BLOCK, 1024);
+                        const uint32_t accum = (first && k == 0) ? 0u : 1u;
+                        if (!FAST) {
+                            tc::mma_f16_pair(dc, g_lo, a_hi, idesc, accum);
+                            tc::mma_f16_pair(dc, g_hi, a_lo, idesc, 1);
+                        }
+                        tc::mma_f16_pair(d, g_hi, a_hi, idesc, accum);
+                    }
+                    first = false;
+                    tc::mma_commit_pair(&sm->empty[s]);
+                    if (++s == NSTAGES) { s = 0; ph ^= 1; }
+                }
+                tc::mma_commit_pair(&sm->tmem_full[acc]);
+            }
+        }
+    } else {
+        const int q = warp % 4;
+        float sum[BN];
+#pragma unroll
+        for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+        for (int ch = 0; ch < chunks; ++ch) {
+            const int acc = ch & 1;
+            tc::mbar_wait(&sm->tmem_full[acc], (ch >> 1) & 1);
+            tc::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                float v[32], vc[32];
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + c * 32;
+                tc::tmem_ld32(ta, v);
+                if (!FAST) tc::tmem_ld32(ta + BN, vc);
+                tc::tmem_ld_wait();
+                if (FAST) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[c * 32 + j] += v[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[c * 32 + j] += fmaf(vc[j], CP_LO_INV, v[j]);
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(tc::mapa(tc::smem_u32(&sm->tmem_empty[acc]), 0));
+        }
+        float* dst = g.P + ((int64_t)blockIdx.z * g.Mo + o0 + q * 32 + lane) * g.No + c0;
+#pragma unroll
+        for (int j = 0; j < BN; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
+    }
+    tc::tc_fence_before();
+    tc::cluster_sync();
+    if (warp == 1) tc::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+}
+
 // ---------------------------------------------------------------------------- conv2 weight gradient
 // P[z][tap*64 + c][o] = sum over the windows of slab z, positions p, of X[w, p+tap-1, c] * G[(w,p), o]
 // (the transposed weight gradient of the k = 3 convolution).  M side = conv-view of X (192 columns,
@@ -1048,12 +1194,12 @@ inline int make_tmap_2d(CUtensorMap* m, const plane_t* base, int64_t rows, int64
 
 // row-major fp16 [rows, cols] viewed as (64 cols, rows, cols/64 blocks): box {64, 64 rows, 2 blocks}
 // lands in shared memory as 2 x [64 rows][128 B], i.e. the MN-major 128B-swizzle canonical layout
-inline int make_tmap_mn(CUtensorMap* m, const plane_t* base, int64_t rows, int64_t cols, int64_t ld) {
+inline int make_tmap_mn(CUtensorMap* m, const plane_t* base, int64_t rows, int64_t cols, int64_t ld, int blocks = 2) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return CP_ERR_UNSUPPORTED;
     cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(cols / 64)};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, 128};
-    cuuint32_t box[3] = {64, 64, 2};
+    cuuint32_t box[3] = {64, 64, (cuuint32_t)blocks};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<plane_t*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1061,6 +1207,11 @@ inline int make_tmap_mn(CUtensorMap* m, const plane_t* base, int64_t rows, int64
     return r == CUDA_SUCCESS ? CP_OK : CP_ERR_ARG;
 }
 
+// CTA-pair (cta_group::2) weight-gradient kernel; CP_TN_PAIR=0 in the environment selects the single-CTA kernel (A/B runs)
+inline bool use_tn_pair() {
+    static const bool on = [] { const char* e = getenv("CP_TN_PAIR"); return !(e && e[0] == '0'); }();
+    return on;
+}
 // returns the number of splits written to P ([splits][Mo][No]) through *splits_out
 inline int launch_tn(const plane_t* G_hi, const plane_t* G_lo, int ldg, int Mo, const plane_t* A_hi, const plane_t* A_lo,
                      int lda, int No, int64_t R, float* P, size_t p_capacity_elems, int* splits_out,
@@ -1090,6 +1241,21 @@ inline int launch_tn(const plane_t* G_hi, const plane_t* G_lo, int ldg, int Mo, 
     const int64_t rps = cp_cdiv(cp_cdiv(R, S), BK) * BK;
     S = (int)cp_cdiv(R, rps);
     TnArgs g{P, Mo, No, R, rps, fast};
+    if (use_tn_pair() && Mo % (2 * BM) == 0) {
+        CUtensorMap ta_hi1, ta_lo1;                                   // A boxes of ONE 64-wide MN block: half a tile per CTA
+        if ((rc = make_tmap_mn(&ta_hi1, A_hi, R, No, lda, 1)) != CP_OK) return rc;
+        if ((rc = make_tmap_mn(&ta_lo1, A_lo, R, No, lda, 1)) != CP_OK) return rc;
+        CP_ONCE_PER_DEVICE({
+            CP_CUDA(cudaFuncSetAttribute(gemm_tc_tn_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tnp::SMEM));
+            CP_CUDA(cudaFuncSetAttribute(gemm_tc_tn_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tnp::SMEM));
+        });
+        const dim3 grid(2 * (Mo / (2 * BM)), No / BN, S);
+        if (fast) gemm_tc_tn_pair_kernel<true><<<grid, THREADS, tnp::SMEM, st>>>(tg_hi, tg_lo, ta_hi1, ta_lo1, g);
+        else gemm_tc_tn_pair_kernel<false><<<grid, THREADS, tnp::SMEM, st>>>(tg_hi, tg_lo, ta_hi1, ta_lo1, g);
+        CP_CHECK_LAUNCH();
+        *splits_out = S;
+        return CP_OK;
+    }
     if (fast) gemm_tc_tn_kernel<true><<<dim3(No / BN, Mo / BM, S), THREADS, SMEM_BYTES, st>>>(tg_hi, tg_lo, ta_hi, ta_lo, g);
     else gemm_tc_tn_kernel<false><<<dim3(No / BN, Mo / BM, S), THREADS, SMEM_BYTES, st>>>(tg_hi, tg_lo, ta_hi, ta_lo, g);
     CP_CHECK_LAUNCH();
