@@ -35,6 +35,8 @@ constexpr int F_FC = 512;
 constexpr int K_FC1 = 768;
 constexpr int WGRAD_SPLITS_MAX = 32;                       // at the largest (512x768) weight
 constexpr size_t WPART_ELEMS = (size_t)WGRAD_SPLITS_MAX * F_FC * K_FC1;
+constexpr int WS_ZERO_WORDS = 64 + 16 + 8 + 8 + 8 + 8;    // tickets, abound, wmax, l1max, rowl1, bmax: zeroed per forward call
+constexpr int N_FOLD = 3;                                 // linear layers 2..4 take their input BatchNorm folded into W
 
 struct Ws {
     float *X0, *Y1, *A1, *Y2, *A2;
@@ -67,6 +69,11 @@ struct Ws {
     unsigned int* g1max;       // [16] max |pre-activation gradient| per stage (bit pattern; zeroed with gmax, backward)
     float* coef;               // [3][512] c1, c2, c3 of the fused BN-backward epilogue (one stage at a time)
     float* gz_bound;           // [16] bound on |gz| per stage
+    // BatchNorm of linear blocks 1..3 folded into the weights of layers 2..4 (fold_bn_weights_kernel): per forward call
+    unsigned int *rowl1, *bmax;  // [8] max row L1 norm / max |bias| of the linear layers (bit patterns, zeroed with tickets)
+    plane_t *Wfh[N_FOLD], *Wfl[N_FOLD];   // planes of W_{l+1} diag(scale_l)
+    float* bias_f[N_FOLD];       // b_{l+1} + W_{l+1} shift_l
+    float* wfscale_inv;          // [N_FOLD] 1 / (power-of-two scale of those planes)
     size_t bytes;
 };
 
@@ -126,10 +133,12 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     w.m2 = c.take<float>(F_FC);
     w.totals = c.take<double>(2 * F_FC + 8);
     w.rscratch = c.take<double>((size_t)RP_SLABS * 2 * F_FC);
-    w.tickets = c.take<unsigned int>(64 + 16 + 8 + 8);
+    w.tickets = c.take<unsigned int>(WS_ZERO_WORDS);
     w.abound = w.tickets + 64;
     w.wmax = w.abound + 16;
     w.l1max = w.wmax + 8;
+    w.rowl1 = w.l1max + 8;
+    w.bmax = w.rowl1 + 8;
     w.ascale_inv = c.take<float>(16);
     w.wscale_inv = c.take<float>(8);
     w.wpart = save ? c.take<float>(WPART_ELEMS) : nullptr;
@@ -159,6 +168,13 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
             w.Wth[l] = c.take<plane_t>(we); w.Wtl[l] = c.take<plane_t>(we);
         }
     }
+    for (int f = 0; f < N_FOLD; ++f) {
+        const bool on = o->engine != CP_ENGINE_SIMT;
+        w.Wfh[f] = on ? c.take<plane_t>((size_t)F_FC * F_FC) : nullptr;
+        w.Wfl[f] = on ? c.take<plane_t>((size_t)F_FC * F_FC) : nullptr;
+        w.bias_f[f] = on ? c.take<float>(F_FC) : nullptr;
+    }
+    w.wfscale_inv = c.take<float>(8);
     w.bytes = c.off;
     return w;
 }
@@ -399,14 +415,26 @@ bool opts_ok(const cp_encoder_opts* o) {
            (o->engine == CP_ENGINE_SIMT || o->engine == CP_ENGINE_TC || o->engine == CP_ENGINE_TC_FP16);
 }
 
+// BatchNorm of linear blocks 1..3 folded into the weights of layers 2..4 (tensor-core engine, CTA-pair GEMM): forward and
+// backward of one call must agree, so both ask here.  CP_FOLD_BN=0 in the environment keeps the BN-apply passes (A/B runs)
+const bool g_fold_bn = []() { const char* e = getenv("CP_FOLD_BN"); return !(e && e[0] == '0'); }();
+bool fold_bn_active(const cp_encoder_opts* o, int64_t n) {
+    return g_fold_bn && o->engine != CP_ENGINE_SIMT && tcg::bnbwd_supported(n);
+}
+
+// the A operand of a weight gradient is the pre-BatchNorm activation of a folded stage: see wgrad_reduce_kernel
+struct FoldFix { const float *scale, *shift, *db; };
+
 // weight-gradient through the tensor-core split-K kernel + the shared re-layout / reduce kernel
 int tc_wgrad(const plane_t* Gh, const plane_t* Gl, int Mo, const plane_t* Ah, const plane_t* Al, int No, int64_t R,
              float* wpart, float* out, int mode, cudaStream_t st, const float* g_scale_inv, int fast = 0,
-             bool alone = false, const float* a_scale_inv = nullptr) {
+             bool alone = false, const float* a_scale_inv = nullptr, const FoldFix* fx = nullptr) {
     int S = 0;
     CP_TRY(tcg::launch_tn(Gh, Gl, Mo, Mo, Ah, Al, No, No, R, wpart, WPART_ELEMS, &S, st, fast, alone));
     wgrad_reduce_kernel<<<(unsigned)cp_cdiv((int64_t)Mo * No, 256), 256, 0, st>>>(wpart, S, Mo, No, out, mode, g_scale_inv,
-                                                                                  a_scale_inv);
+                                                                                  a_scale_inv, fx ? fx->scale : nullptr,
+                                                                                  fx ? fx->shift : nullptr,
+                                                                                  fx ? fx->db : nullptr);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
@@ -431,7 +459,14 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     const int64_t R12 = n * 12;
     const size_t conv_elems = (size_t)n * 12 * F_CONV, fc_elems = (size_t)n * F_FC;
 
-    CP_CUDA(cudaMemsetAsync(w.tickets, 0, (64 + 16 + 8 + 8) * sizeof(unsigned int), st));
+    CP_CUDA(cudaMemsetAsync(w.tickets, 0, WS_ZERO_WORDS * sizeof(unsigned int), st));
+    const bool fold = fold_bn_active(o, n);
+    if (fold) {
+        RowL1Args ra;
+        for (int l = 0; l < CP_N_FC; ++l) { ra.W[l] = p->fc_w[l]; ra.b[l] = p->fc_b[l]; ra.K[l] = l == 0 ? K_FC1 : F_FC; }
+        weights_row_l1_kernel<<<dim3(F_FC / 8, CP_N_FC), 256, 0, st>>>(ra, w.rowl1, w.bmax);
+        CP_CHECK_LAUNCH();
+    }
     if (tcE) {
         WmaxArgs wa;
         for (int l = 0; l < CP_N_FC; ++l) { wa.W[l] = p->fc_w[l]; wa.n[l] = F_FC * (l == 0 ? K_FC1 : F_FC); }
@@ -490,10 +525,20 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
         const float* in = l == 0 ? w.A2 : w.A[l - 1];
         const int K = l == 0 ? K_FC1 : F_FC;
         const float* W = l == 0 ? w.W1p : p->fc_w[l];
+        // BatchNorm folding (linear blocks 1..3 -> layers 2..4, no dropout in between): layer l's epilogue also writes the
+        // fp16 planes of its OUTPUT y (into the slot the BN-apply kernel would have filled), the stage's (scale, shift)
+        // go into the next layer's weights / bias, and that layer's GEMM reads the y planes: no BN-apply pass.
+        const bool in_folded = fold && l >= 1 && l <= N_FOLD;
+        const bool out_planes = fold && l < N_FOLD;
         if (tcE) {
             const plane_t* in_lo = lo_of(in, l == 0 ? conv_elems : fc_elems);
-            CP_TRY(tcg::launch_nt(hi_of(in), in_lo, n, K, K, w.Wh[l], w.Wl[l], F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb,
-                                  1, st, w.ascale_inv + 1 + l, fast, nullptr, nullptr, 1.f, w.wscale_inv + l));
+            tcg::YPlanes yp{reinterpret_cast<plane_t*>(w.A[l]), reinterpret_cast<plane_t*>(w.A[l]) + fc_elems,
+                            w.abound + 1 + l, w.rowl1 + l, w.bmax + l, w.ascale_inv + 2 + l};
+            CP_TRY(tcg::launch_nt(hi_of(in), in_lo, n, K, K, in_folded ? w.Wfh[l - 1] : w.Wh[l],
+                                  in_folded ? w.Wfl[l - 1] : w.Wl[l], F_FC, K, in_folded ? w.bias_f[l - 1] : p->fc_b[l],
+                                  w.Y[l], F_FC, w.pa, w.pb, 1, st, w.ascale_inv + 1 + l, fast, nullptr, nullptr, 1.f,
+                                  in_folded ? w.wfscale_inv + (l - 1) : w.wscale_inv + l, nullptr,
+                                  out_planes ? &yp : nullptr));
         } else {
             CP_TRY((launch_nt<128, 128, 0, false>(in, n, K, K, W, F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb, 1, st)));
         }
@@ -508,6 +553,12 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
             else
                 gen_p = o->dropout_p;              // mask drawn (and stored) inside the BN-apply kernel
             keep = w.keep[d];
+        }
+        if (out_planes) {
+            fold_bn_weights_kernel<<<F_FC, 128, 0, st>>>(p->fc_w[l + 1], p->fc_b[l + 1], w.scale[2 + l], w.shift[2 + l],
+                                                         w.wmax + l + 1, w.Wfh[l], w.Wfl[l], w.bias_f[l], w.wfscale_inv + l);
+            CP_CHECK_LAUNCH();
+            continue;
         }
         if (l + 1 < CP_N_FC) {
             CP_TRY(bn_apply<F_FC>(w.Y[l], w.A[l], tcE, n, w, 2 + l, keep, inv_keep, st, gen_p, o->dropout_seed,
@@ -556,6 +607,7 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     const size_t conv_elems = (size_t)n * 12 * F_CONV, fc_elems = (size_t)n * F_FC;
     const float inv_keep = o->dropout_p > 0.f ? 1.f / (1.f - o->dropout_p) : 1.f;
     CP_CUDA(cudaMemsetAsync(w.gmax, 0, 48 * sizeof(unsigned int), st));
+    const bool fold = fold_bn_active(o, n);
 
     const int Pp = pf::grid_for(n);          // projection weight-gradient partial rows (last_block_backward)
 
@@ -599,6 +651,9 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             const plane_t* ah = hi_of(ain);
             const plane_t* al = lo_of(ain, l == 0 ? conv_elems : fc_elems);
             const float* gsi = w.gscale_inv + 2 + l;
+            // layers 2..4 with their input BatchNorm folded: the "A planes" hold the stage's pre-BN activation
+            const FoldFix fx{w.scale[1 + l], w.shift[1 + l], gr->fc_b[l]};
+            const FoldFix* fxp = (fold && l >= 1 && l <= N_FOLD) ? &fx : nullptr;
             // The stage below (BN stage 1 + l: conv2 for l = 0) feeds this layer without dropout and statistics are
             // rank-local: its BN-backward sums follow from this layer's dW / db (bn_bwd_stats_from_wgrad_kernel), so
             // the weight gradient runs in line (its overlap with the BN backward bought nothing) and the
@@ -618,7 +673,7 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
                 // (1) dW_l, (2) the stage's BN-backward sums from dW_l / db_l
                 if (last_side) CP_CUDA(cudaStreamWaitEvent(st, last_side, 0));
                 CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, st, gsi, fast,
-                                true, w.ascale_inv + 1 + l));
+                                true, w.ascale_inv + 1 + l, fxp));
                 if (l == 0)
                     bn_bwd_stats_from_wgrad_kernel<12><<<K_FC1 / WgradStats<12>::COLS, 512, 0, st>>>(
                         p->fc_w[0], gr->fc_w[0], gr->fc_b[0], F_FC, K_FC1, n, p->bn_w[s_below], p->bn_b[s_below], w.m1, w.m2,
@@ -674,7 +729,7 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             if (algebraic) {
                 if (last_side) CP_CUDA(cudaStreamWaitEvent(st, last_side, 0));     // w.wpart is shared with the side stream
                 CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, st, gsi, fast,
-                                true, w.ascale_inv + 1 + l));
+                                true, w.ascale_inv + 1 + l, fxp));
                 const int s_below = 1 + l;             // BN stage of this layer's input
                 if (masked) {
                     // sum over the GEMM's per-tile partial rows -> w.m1 (scratch until the statistics kernel overwrites it)
@@ -704,7 +759,7 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             CP_CUDA(cudaEventRecord(g_side.ready[b], st));
             CP_CUDA(cudaStreamWaitEvent(ss, g_side.ready[b], 0));
             CP_TRY(tc_wgrad(hi_of(g1(b)), g1lo(b, fc_elems), F_FC, ah, al, K, n, w.wpart, gr->fc_w[l], l == 0 ? 1 : 0, ss, gsi, fast,
-                            false, w.ascale_inv + 1 + l));
+                            false, w.ascale_inv + 1 + l, fxp));
             CP_CUDA(cudaEventRecord(g_side.done[b], ss));
             used[b] = true;
             last_side = g_side.done[b];

@@ -997,6 +997,61 @@ weights_col_l1_kernel(const WmaxArgs a, unsigned int* __restrict__ l1max) {
     s = warp_max(s);
     if (threadIdx.x % 32 == 0 && s > 0.f && s < 3.0e38f) atomicMax(l1max + l, __float_as_uint(s));
 }
+// max over the rows j of sum_k |W_l[j, k]| (-> rowl1[l]) and max_j |b_l[j]| (-> bmax[l]) for the 7 linear layers
+// (blockIdx.y; one warp per row): |A . W^T + b| <= max|A| * rowl1 + bmax, the a-priori bound the GEMM epilogue scales
+// the fp16 planes of its OUTPUT by when the following BatchNorm is folded into the next layer (fold_bn_weights_kernel)
+struct RowL1Args { const float* W[7]; const float* b[7]; int K[7]; };
+__global__ void __launch_bounds__(256)
+weights_row_l1_kernel(const RowL1Args a, unsigned int* __restrict__ rowl1, unsigned int* __restrict__ bmax) {
+    const int l = blockIdx.y;
+    const int j = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (j >= 512) return;
+    const int K = a.K[l];
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s += fabsf(__ldg(a.W[l] + (size_t)j * K + k));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) {
+        if (s > 0.f && s < 3.0e38f) atomicMax(rowl1 + l, __float_as_uint(s));
+        const float b = fabsf(__ldg(a.b[l] + j));
+        if (b > 0.f && b < 3.0e38f) atomicMax(bmax + l, __float_as_uint(b));
+    }
+}
+
+// BatchNorm folded into the NEXT linear layer (no BN-apply pass between two linear blocks without dropout):
+//   (y * scale + shift) . W^T + b  =  y . (W diag(scale))^T + (b + W . shift)
+// One CTA per output row j: planes of W[j,k] * scale[k] * S (S = power of two from max|W| * max|scale|), folded bias
+// b'[j] = b[j] + sum_k W[j,k] * shift[k], *wscale_inv_out = 1 / S.  K = 512 (linear layers 2..4 of the encoder).
+__global__ void __launch_bounds__(128)
+fold_bn_weights_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ scale,
+                       const float* __restrict__ shift, const unsigned int* __restrict__ wmax,
+                       plane_t* __restrict__ Wh, plane_t* __restrict__ Wl, float* __restrict__ bias_out,
+                       float* __restrict__ wscale_inv_out) {
+    constexpr int K = 512;
+    __shared__ float red[4], redm[4];
+    const int j = blockIdx.x, t = threadIdx.x, lane = t % 32, wp = t / 32;
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + t);
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + t);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)j * K) + t);
+    float m = fmaxf(fmaxf(fabsf(sc.x), fabsf(sc.y)), fmaxf(fabsf(sc.z), fabsf(sc.w)));
+    float d = fmaf(w.x, sh.x, fmaf(w.y, sh.y, fmaf(w.z, sh.z, w.w * sh.w)));
+    m = warp_max(m);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+    if (lane == 0) { red[wp] = d; redm[wp] = m; }
+    __syncthreads();
+    d = (red[0] + red[1]) + (red[2] + red[3]);
+    m = fmaxf(fmaxf(redm[0], redm[1]), fmaxf(redm[2], redm[3]));
+    const float bound = __uint_as_float(__ldg(wmax)) * m;
+    const float S = (bound > 0.f && bound < 3.0e38f) ? exp2f(-ceilf(log2f(bound))) : 1.f;
+    if (t == 0) {
+        bias_out[j] = __ldg(b + j) + d;
+        if (j == 0) *wscale_inv_out = 1.f / S;
+    }
+    split_store4(make_float4(w.x * sc.x * S, w.y * sc.y * S, w.z * sc.z * S, w.w * sc.w * S), Wh + (size_t)j * K,
+                 Wl + (size_t)j * K, t);
+}
+
 // S with max|W| * S in (1/2, 1]
 __device__ __forceinline__ float weight_scale(const unsigned int* wmax_slot) {
     const float m = __uint_as_float(__ldg(wmax_slot));
@@ -1064,9 +1119,14 @@ prep_weights_tc_kernel(const PrepTcArgs a) {
 // dW = sum_z P[z]  with the inverse re-layouts.  mode 0: identity; 1: fc1 (cols p*64+c -> c*12+p);
 // 2: conv2 (cols tap*64+c -> [o][c][1][tap] of a zero-initialised (64,64,3,3) tensor);
 // 3: conv2 from the transposed tensor-core partials P[z][256][64] (row tap*64+c, column o)
+// fold_scale / fold_shift / fold_db non-null (mode 0): the A operand was the PRE-BatchNorm activation y of a stage whose BN
+// is folded into this layer (fold_bn_weights_kernel): dW[o,k] = sum_r g[r,o] (y[r,k] scale[k] + shift[k])
+//                                                             = scale[k] * (G^T y)[o,k] + shift[k] * db[o]
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ P, int S, int Mo, int No, float* __restrict__ out, int mode,
-                    const float* __restrict__ scale = nullptr, const float* __restrict__ scale2 = nullptr) {
+                    const float* __restrict__ scale = nullptr, const float* __restrict__ scale2 = nullptr,
+                    const float* __restrict__ fold_scale = nullptr, const float* __restrict__ fold_shift = nullptr,
+                    const float* __restrict__ fold_db = nullptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Mo * No) return;
     // undoes the power-of-two scales of the G planes and of the activation planes
@@ -1082,6 +1142,7 @@ wgrad_reduce_kernel(const float* __restrict__ P, int S, int Mo, int No, float* _
     for (int z = 0; z < S; ++z) s += (double)__ldg(P + (int64_t)z * Mo * No + i);
     s *= sc;
     const int o = i / No, k = i % No;
+    if (fold_scale) s = s * (double)__ldg(fold_scale + k) + (double)__ldg(fold_shift + k) * (double)__ldg(fold_db + o);
     if (mode == 0) out[i] = (float)s;
     else if (mode == 1) out[o * 768 + (k % 64) * 12 + k / 64] = (float)s;
     else out[(o * 64 + k % 64) * 9 + 3 + k / 64] = (float)s;

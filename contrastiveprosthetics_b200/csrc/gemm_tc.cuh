@@ -125,6 +125,13 @@ struct NtArgs {
     float* gscale_inv_out;
     const unsigned int* skip_flag;  // non-null: a device word; the kernel returns at once when it is zero (the conditional
                                     // plain data-gradient launch of the exact fallback, see stage_needs_exact)
+    // ---- EPI_YPLANES (pair kernel): besides C (fp32, kept for the backward pass) the epilogue writes C * S as fp16
+    // (hi, lo) planes through tm_c2 / tm_y -- the operand of the NEXT layer's GEMM when the BatchNorm between the two
+    // is folded into that layer's weights (no BN-apply pass).  S = plane_scale(in_bound * row_l1 + bias_max): an
+    // a-priori bound on |A . B^T + bias| from the bound on the input planes' values, max_j sum_k |B[j,k]| and max |bias|
+    // (bit patterns of non-negative floats); *yscale_inv_out = 1 / S.
+    const unsigned int *y_in_bound, *y_row_l1, *y_bias_max;
+    float* yscale_inv_out;
 };
 
 // warp-transposing reduction: on return v[0] of lane l = sum over the 32 lanes of their v[l]
@@ -393,7 +400,7 @@ constexpr int STAGE2 = 2 * TILE_BYTES + 2 * B_HALF;       // A_hi, A_lo, B_hi/2,
 // operand ring depth: 4 stages when the epilogue boxes leave room for them (plain epilogue: 192 + 32 KB), 3 with the
 // 64 KB of boxes of the fused BN-backward epilogue
 constexpr int MAX_STAGES2 = 4;
-__host__ __device__ constexpr int stages2(int epi) { return epi == 1 ? 3 : 4; }
+__host__ __device__ constexpr int stages2(int epi) { return epi == 0 ? 4 : 3; }
 struct Smem2 {
     uint64_t full[MAX_STAGES2], empty[MAX_STAGES2], tmem_full[2], tmem_empty[2];
     uint64_t ybar[16];              // EPI_BNBWD: arrival of the two activation boxes of each epilogue warp
@@ -409,7 +416,7 @@ constexpr int SMEM2_BNBWD = stages2(1) * STAGE2 + 8 * 2 * OUT_BOX + (int)sizeof(
 static_assert(SMEM2 <= 232448 && SMEM2_BNBWD <= 232448, "shared memory per CTA");
 }  // namespace pair
 
-constexpr int EPI_STD = 0, EPI_BNBWD = 1;
+constexpr int EPI_STD = 0, EPI_BNBWD = 1, EPI_YPLANES = 2;
 
 __device__ __forceinline__ bool nt_skip(const NtArgs& g) { return g.skip_flag && __ldg(g.skip_flag) == 0u; }
 
@@ -425,7 +432,7 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
     extern __shared__ __align__(1024) uint8_t smem_pair[];
     uint8_t* tiles = smem_pair;                  // 1024-aligned (128B-swizzled TMA boxes / UMMA descriptors)
     uint8_t* out_boxes = tiles + STAGES2 * STAGE2;                              // 8 x 4 KB (EPI_BNBWD: 8 x 8 KB), 1024-aligned
-    Smem2* sm = reinterpret_cast<Smem2*>(out_boxes + 8 * OUT_BOX * (EPI == EPI_BNBWD ? 2 : 1));
+    Smem2* sm = reinterpret_cast<Smem2*>(out_boxes + 8 * OUT_BOX * (EPI != EPI_STD ? 2 : 1));
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const uint32_t rank = tc::cluster_ctarank();
@@ -624,7 +631,13 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             gzmax = warp_max(gzmax);
             if (lane == 0 && gzmax > 0.f && g.g1max_out) atomicMax(g.g1max_out, __float_as_uint(gzmax));
             if (lane == 0) tc::tma_store_wait_read();
-        } else
+        } else {
+        float yS = 1.f;
+        if (EPI == EPI_YPLANES) {
+            yS = plane_scale(fmaf(__uint_as_float(__ldg(g.y_in_bound)), __uint_as_float(__ldg(g.y_row_l1)),
+                                  __uint_as_float(__ldg(g.y_bias_max))));
+            if (blockIdx.x == 0 && et == 0) *g.yscale_inv_out = 1.f / yS;
+        }
         for (int64_t t = cluster_id; t < n_tiles; t += n_clusters, ++it) {
             const int acc = it & 1;
             const int64_t tile_m = (t / tiles_n) * 2 + rank;            // 128-row tile index of this CTA
@@ -675,6 +688,34 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                     if (lane == 0 && mx > 0.f) atomicMax(g.gmax_bits, __float_as_uint(mx));
                 }
                 store_box_tma(&tm_c, out_boxes + (warp - 2) * OUT_BOX, v, lane, col, tile_m * BM + q * 32);
+                if (EPI == EPI_YPLANES) {
+                    // planes of C * S into the warp's second box: hi [32 rows][64 B] then lo [32 rows][64 B], no swizzle
+                    // (store_box_tma's wait covered the previous chunk's plane stores: same bulk-group thread)
+                    uint8_t* pbox = out_boxes + (8 + warp - 2) * OUT_BOX;
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        uint32_t hq[4], lq[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float a = fminf(fmaxf(v[j8 * 8 + 2 * u] * yS, -65000.f), 65000.f);
+                            const float b = fminf(fmaxf(v[j8 * 8 + 2 * u + 1] * yS, -65000.f), 65000.f);
+                            const __half2 h2 = __floats2half2_rn(a, b);
+                            const float2 hf = __half22float2(h2);
+                            const __half2 l2 = __floats2half2_rn((a - hf.x) * CP_LO_SCALE, (b - hf.y) * CP_LO_SCALE);
+                            hq[u] = *reinterpret_cast<const uint32_t*>(&h2);
+                            lq[u] = *reinterpret_cast<const uint32_t*>(&l2);
+                        }
+                        *reinterpret_cast<uint4*>(pbox + lane * 64 + j8 * 16) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+                        *reinterpret_cast<uint4*>(pbox + OUT_BOX / 2 + lane * 64 + j8 * 16) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+                    }
+                    tc::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tc::tma_store_2d(&tm_c2, pbox, col, (int)(tile_m * BM + q * 32));
+                        tc::tma_store_2d(&tm_y, pbox + OUT_BOX / 2, col, (int)(tile_m * BM + q * 32));
+                        tc::tma_store_commit();
+                    }
+                }
                 if (g.psum && g.keep) {
                     masked_col_sums(v, g, mk[c], lane);
                     cs[c] = v[0];
@@ -717,6 +758,7 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                     tc::named_bar_sync(1, EPI2);
                 }
             }
+        }
         }
         if (lane == 0) tc::tma_store_wait_read();
     }
@@ -1325,15 +1367,25 @@ inline int set_pair_attrs() {
         CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<true, EPI_STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
         CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<false, EPI_BNBWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2_BNBWD));
         CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<true, EPI_BNBWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2_BNBWD));
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<false, EPI_YPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2_BNBWD));
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<true, EPI_YPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2_BNBWD));
     });
     return CP_OK;
 }
+// plane outputs of launch_nt (EPI_YPLANES, see NtArgs)
+struct YPlanes {
+    plane_t *hi, *lo;                                       // [M][N] each
+    const unsigned int *in_bound, *row_l1, *bias_max;       // device words (bit patterns)
+    float* scale_inv_out;                                   // device scalar
+};
 inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K, int lda, const plane_t* B_hi,
                      const plane_t* B_lo, int N, int ldb, const float* bias, float* C, int ldc, float* psum,
                      float* psq, int relu, cudaStream_t st, const float* out_scale = nullptr, int fast = 0,
                      unsigned int* gmax_bits = nullptr, const uint8_t* keep = nullptr, float inv_keep = 1.f,
-                     const float* out_scale2 = nullptr, const unsigned int* skip_flag = nullptr) {
+                     const float* out_scale2 = nullptr, const unsigned int* skip_flag = nullptr,
+                     const YPlanes* yp = nullptr) {
     if (K % BK != 0 || N % BN != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldc % 4 != 0) return CP_ERR_ARG;
+    if (yp && !(g_use_pair && M > BM)) return CP_ERR_UNSUPPORTED;      // the plane epilogue exists in the pair kernel only
     if (keep && (ldc != N || ((uintptr_t)keep) % 16 != 0)) return CP_ERR_ARG;     // mask laid out like a dense [M][N] C
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_out;
     int rc;
@@ -1351,6 +1403,17 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
         if ((rc = set_pair_attrs()) != CP_OK) return rc;
         const int64_t n_tiles = cp_cdiv(M, 2 * BM) * (N / BN);
         const int clusters = (int)(n_tiles < CP_NUM_SMS / 2 ? n_tiles : CP_NUM_SMS / 2);
+        if (yp) {
+            CUtensorMap ty_hi, ty_lo;
+            if ((rc = make_tmap_plane_out(&ty_hi, yp->hi, M, N, N)) != CP_OK) return rc;
+            if ((rc = make_tmap_plane_out(&ty_lo, yp->lo, M, N, N)) != CP_OK) return rc;
+            g.y_in_bound = yp->in_bound; g.y_row_l1 = yp->row_l1; g.y_bias_max = yp->bias_max;
+            g.yscale_inv_out = yp->scale_inv_out;
+            if (fast) gemm_tc_nt_pair_kernel<true, EPI_YPLANES><<<2 * clusters, pair::THREADS2, pair::SMEM2_BNBWD, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, ty_hi, ty_lo, g);
+            else gemm_tc_nt_pair_kernel<false, EPI_YPLANES><<<2 * clusters, pair::THREADS2, pair::SMEM2_BNBWD, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, ty_hi, ty_lo, g);
+            CP_CHECK_LAUNCH();
+            return CP_OK;
+        }
         if (fast) gemm_tc_nt_pair_kernel<true, EPI_STD><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, tc_out, tc_out, g);
         else gemm_tc_nt_pair_kernel<false, EPI_STD><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, tc_out, tc_out, g);
         CP_CHECK_LAUNCH();
