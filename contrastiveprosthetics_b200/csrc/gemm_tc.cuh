@@ -400,7 +400,7 @@ constexpr int STAGE2 = 2 * TILE_BYTES + 2 * B_HALF;       // A_hi, A_lo, B_hi/2,
 // operand ring depth: 4 stages when the epilogue boxes leave room for them (plain epilogue: 192 + 32 KB), 3 with the
 // 64 KB of boxes of the fused BN-backward epilogue
 constexpr int MAX_STAGES2 = 4;
-__host__ __device__ constexpr int stages2(int epi) { return epi == 0 ? 4 : 3; }
+__host__ __device__ constexpr int stages2(int epi) { return epi == 1 ? 3 : 4; }
 struct Smem2 {
     uint64_t full[MAX_STAGES2], empty[MAX_STAGES2], tmem_full[2], tmem_empty[2];
     uint64_t ybar[16];              // EPI_BNBWD: arrival of the two activation boxes of each epilogue warp
@@ -432,7 +432,7 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
     extern __shared__ __align__(1024) uint8_t smem_pair[];
     uint8_t* tiles = smem_pair;                  // 1024-aligned (128B-swizzled TMA boxes / UMMA descriptors)
     uint8_t* out_boxes = tiles + STAGES2 * STAGE2;                              // 8 x 4 KB (EPI_BNBWD: 8 x 8 KB), 1024-aligned
-    Smem2* sm = reinterpret_cast<Smem2*>(out_boxes + 8 * OUT_BOX * (EPI != EPI_STD ? 2 : 1));
+    Smem2* sm = reinterpret_cast<Smem2*>(out_boxes + 8 * OUT_BOX * (EPI == EPI_BNBWD ? 2 : 1));
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const uint32_t rank = tc::cluster_ctarank();
@@ -688,25 +688,50 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                     if (lane == 0 && mx > 0.f) atomicMax(g.gmax_bits, __float_as_uint(mx));
                 }
                 store_box_tma(&tm_c, out_boxes + (warp - 2) * OUT_BOX, v, lane, col, tile_m * BM + q * 32);
+                if (g.psum && g.keep) {
+                    masked_col_sums(v, g, mk[c], lane);
+                    cs[c] = v[0];
+                    cq[c] = 0.f;
+                } else if (g.psum) {
+                    // column sums / sums of squares of the warp's 32 x 32 chunk, read back from the staged fp32 box (lane l
+                    // = column l; word (r, l) of the 128B-swizzled box: conflict-free) -- two register-transposing butterfly
+                    // reductions (2 x 31 shuffles + selects) cost more issue slots than the rest of the epilogue together
+                    const uint8_t* box = out_boxes + (warp - 2) * OUT_BOX;
+                    const int64_t left = g.M - (tile_m * BM + q * 32);
+                    const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+                    float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        float x = *reinterpret_cast<const float*>(box + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                        x = r < nvalid ? x : 0.f;
+                        s4[r & 3] += x;
+                        q4[r & 3] = fmaf(x, x, q4[r & 3]);
+                    }
+                    cs[c] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                    cq[c] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+                }
                 if (EPI == EPI_YPLANES) {
-                    // planes of C * S into the warp's second box: hi [32 rows][64 B] then lo [32 rows][64 B], no swizzle
-                    // (store_box_tma's wait covered the previous chunk's plane stores: same bulk-group thread)
-                    uint8_t* pbox = out_boxes + (8 + warp - 2) * OUT_BOX;
+                    // planes of C * S through the SAME box once the fp32 store has read it (a second box per warp would
+                    // cost the operand ring its 4th stage -- measured: 184 -> 277 us per launch at K = 512):
+                    // hi [32 rows][64 B] then lo [32 rows][64 B], no swizzle
+                    uint8_t* pbox = out_boxes + (warp - 2) * OUT_BOX;
+                    uint32_t hq[16], lq[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const float a = fminf(fmaxf(v[2 * u] * yS, -65000.f), 65000.f);
+                        const float b = fminf(fmaxf(v[2 * u + 1] * yS, -65000.f), 65000.f);
+                        const __half2 h2 = __floats2half2_rn(a, b);
+                        const float2 hf = __half22float2(h2);
+                        const __half2 l2 = __floats2half2_rn((a - hf.x) * CP_LO_SCALE, (b - hf.y) * CP_LO_SCALE);
+                        hq[u] = *reinterpret_cast<const uint32_t*>(&h2);
+                        lq[u] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                    if (lane == 0) tc::tma_store_wait_read();
+                    __syncwarp();
 #pragma unroll
                     for (int j8 = 0; j8 < 4; ++j8) {
-                        uint32_t hq[4], lq[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float a = fminf(fmaxf(v[j8 * 8 + 2 * u] * yS, -65000.f), 65000.f);
-                            const float b = fminf(fmaxf(v[j8 * 8 + 2 * u + 1] * yS, -65000.f), 65000.f);
-                            const __half2 h2 = __floats2half2_rn(a, b);
-                            const float2 hf = __half22float2(h2);
-                            const __half2 l2 = __floats2half2_rn((a - hf.x) * CP_LO_SCALE, (b - hf.y) * CP_LO_SCALE);
-                            hq[u] = *reinterpret_cast<const uint32_t*>(&h2);
-                            lq[u] = *reinterpret_cast<const uint32_t*>(&l2);
-                        }
-                        *reinterpret_cast<uint4*>(pbox + lane * 64 + j8 * 16) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
-                        *reinterpret_cast<uint4*>(pbox + OUT_BOX / 2 + lane * 64 + j8 * 16) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+                        *reinterpret_cast<uint4*>(pbox + lane * 64 + j8 * 16) = make_uint4(hq[4 * j8], hq[4 * j8 + 1], hq[4 * j8 + 2], hq[4 * j8 + 3]);
+                        *reinterpret_cast<uint4*>(pbox + OUT_BOX / 2 + lane * 64 + j8 * 16) = make_uint4(lq[4 * j8], lq[4 * j8 + 1], lq[4 * j8 + 2], lq[4 * j8 + 3]);
                     }
                     tc::fence_proxy_async();
                     __syncwarp();
@@ -715,22 +740,6 @@ gemm_tc_nt_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                         tc::tma_store_2d(&tm_y, pbox + OUT_BOX / 2, col, (int)(tile_m * BM + q * 32));
                         tc::tma_store_commit();
                     }
-                }
-                if (g.psum && g.keep) {
-                    masked_col_sums(v, g, mk[c], lane);
-                    cs[c] = v[0];
-                    cq[c] = 0.f;
-                } else if (g.psum) {
-                    float sq[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = row_ok ? v[j] : 0.f;
-                        sq[j] = v[j] * v[j];
-                    }
-                    warp_col_reduce32(v, lane);
-                    warp_col_reduce32(sq, lane);
-                    cs[c] = v[0];
-                    cq[c] = sq[0];
                 }
             }
             // accumulator drained -> hand it back to the leader's MMA warp
@@ -1367,8 +1376,8 @@ inline int set_pair_attrs() {
         CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<true, EPI_STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
         CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<false, EPI_BNBWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2_BNBWD));
         CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<true, EPI_BNBWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2_BNBWD));
-        CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<false, EPI_YPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2_BNBWD));
-        CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<true, EPI_YPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2_BNBWD));
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<false, EPI_YPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
+        CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_pair_kernel<true, EPI_YPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM2));
     });
     return CP_OK;
 }
@@ -1409,8 +1418,8 @@ inline int launch_nt(const plane_t* A_hi, const plane_t* A_lo, int64_t M, int K,
             if ((rc = make_tmap_plane_out(&ty_lo, yp->lo, M, N, N)) != CP_OK) return rc;
             g.y_in_bound = yp->in_bound; g.y_row_l1 = yp->row_l1; g.y_bias_max = yp->bias_max;
             g.yscale_inv_out = yp->scale_inv_out;
-            if (fast) gemm_tc_nt_pair_kernel<true, EPI_YPLANES><<<2 * clusters, pair::THREADS2, pair::SMEM2_BNBWD, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, ty_hi, ty_lo, g);
-            else gemm_tc_nt_pair_kernel<false, EPI_YPLANES><<<2 * clusters, pair::THREADS2, pair::SMEM2_BNBWD, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, ty_hi, ty_lo, g);
+            if (fast) gemm_tc_nt_pair_kernel<true, EPI_YPLANES><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, ty_hi, ty_lo, g);
+            else gemm_tc_nt_pair_kernel<false, EPI_YPLANES><<<2 * clusters, pair::THREADS2, pair::SMEM2, st>>>(ta_hi, ta_lo, tb_hi2, tb_lo2, tc_out, ty_hi, ty_lo, g);
             CP_CHECK_LAUNCH();
             return CP_OK;
         }

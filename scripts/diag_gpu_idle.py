@@ -39,6 +39,12 @@ def report(tag, prof):
     busy += cur_e - cur_s
     print(f"{tag}: kernels {len(iv)}  span {span/1e3:.3f} ms  busy {busy/1e3:.3f} ms  idle {(span-busy)/1e3:.3f} ms  "
           f"sum of durations {sum(e-s for s,e,_ in iv)/1e3:.3f} ms")
+    # context of the largest in-graph gap
+    big = sorted(((iv[i][0] - max(e for _, e, _ in iv[:i]), i) for i in range(1, len(iv))), reverse=True)[:3]
+    for gsz, i in big:
+        print(f"   gap {gsz:.1f} us before #{i}:")
+        for j in range(max(0, i - 4), min(len(iv), i + 3)):
+            print(f"      #{j} start {iv[j][0]-iv[0][0]:9.1f} dur {iv[j][1]-iv[j][0]:7.1f}  {iv[j][2][:70]}")
     gaps.sort(reverse=True)
     print("   largest gaps (us, before kernel):", [(round(g, 1), n[:40]) for g, n in gaps[:8]])
     import statistics
