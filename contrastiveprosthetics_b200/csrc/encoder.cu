@@ -36,7 +36,7 @@ constexpr int K_FC1 = 768;
 constexpr int WGRAD_SPLITS_MAX = 32;                       // at the largest (512x768) weight
 constexpr size_t WPART_ELEMS = (size_t)WGRAD_SPLITS_MAX * F_FC * K_FC1;
 constexpr int WS_ZERO_WORDS = 64 + 16 + 8 + 8 + 8 + 8;    // tickets, abound, wmax, l1max, rowl1, bmax: zeroed per forward call
-constexpr int N_FOLD = 4;                                 // linear layers 1..4 take their input BatchNorm folded into W
+constexpr int N_FOLD = 3;                                 // linear layers 2..4 take their input BatchNorm folded into W
 
 struct Ws {
     float *X0, *Y1, *A1, *Y2, *A2;
@@ -69,11 +69,10 @@ struct Ws {
     unsigned int* g1max;       // [16] max |pre-activation gradient| per stage (bit pattern; zeroed with gmax, backward)
     float* coef;               // [3][512] c1, c2, c3 of the fused BN-backward epilogue (one stage at a time)
     float* gz_bound;           // [16] bound on |gz| per stage
-    // BatchNorm of the conv2 stage and of linear blocks 1..3 folded into the weights of linear layers 1..4
-    // (fold_bn_weights[_fc1]_kernel): per forward call
-    unsigned int *rowl1, *bmax;  // [8] max row L1 norm / max |bias| of the linear layers, 7 = conv2 (bit patterns, zeroed with tickets)
-    plane_t *Wfh[N_FOLD], *Wfl[N_FOLD];   // planes of W_l diag(scale of the stage below), l = 0..3
-    float* bias_f[N_FOLD];       // b_l + W_l shift
+    // BatchNorm of linear blocks 1..3 folded into the weights of layers 2..4 (fold_bn_weights_kernel): per forward call
+    unsigned int *rowl1, *bmax;  // [8] max row L1 norm / max |bias| of the linear layers (bit patterns, zeroed with tickets)
+    plane_t *Wfh[N_FOLD], *Wfl[N_FOLD];   // planes of W_{l+1} diag(scale_l)
+    float* bias_f[N_FOLD];       // b_{l+1} + W_{l+1} shift_l
     float* wfscale_inv;          // [N_FOLD] 1 / (power-of-two scale of those planes)
     size_t bytes;
 };
@@ -171,9 +170,8 @@ Ws carve(void* base, int64_t n, const cp_encoder_opts* o) {
     }
     for (int f = 0; f < N_FOLD; ++f) {
         const bool on = o->engine != CP_ENGINE_SIMT;
-        const size_t we = (size_t)F_FC * (f == 0 ? K_FC1 : F_FC);
-        w.Wfh[f] = on ? c.take<plane_t>(we) : nullptr;
-        w.Wfl[f] = on ? c.take<plane_t>(we) : nullptr;
+        w.Wfh[f] = on ? c.take<plane_t>((size_t)F_FC * F_FC) : nullptr;
+        w.Wfl[f] = on ? c.take<plane_t>((size_t)F_FC * F_FC) : nullptr;
         w.bias_f[f] = on ? c.take<float>(F_FC) : nullptr;
     }
     w.wfscale_inv = c.take<float>(8);
@@ -425,7 +423,7 @@ bool fold_bn_active(const cp_encoder_opts* o, int64_t n) {
 }
 
 // the A operand of a weight gradient is the pre-BatchNorm activation of a folded stage: see wgrad_reduce_kernel
-struct FoldFix { const float *scale, *shift, *db; int period; };
+struct FoldFix { const float *scale, *shift, *db; };
 
 // weight-gradient through the tensor-core split-K kernel + the shared re-layout / reduce kernel
 int tc_wgrad(const plane_t* Gh, const plane_t* Gl, int Mo, const plane_t* Ah, const plane_t* Al, int No, int64_t R,
@@ -436,7 +434,7 @@ int tc_wgrad(const plane_t* Gh, const plane_t* Gl, int Mo, const plane_t* Ah, co
     wgrad_reduce_kernel<<<(unsigned)cp_cdiv((int64_t)Mo * No, 256), 256, 0, st>>>(wpart, S, Mo, No, out, mode, g_scale_inv,
                                                                                   a_scale_inv, fx ? fx->scale : nullptr,
                                                                                   fx ? fx->shift : nullptr,
-                                                                                  fx ? fx->db : nullptr, fx ? fx->period : 1);
+                                                                                  fx ? fx->db : nullptr);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
@@ -466,8 +464,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     if (fold) {
         RowL1Args ra;
         for (int l = 0; l < CP_N_FC; ++l) { ra.W[l] = p->fc_w[l]; ra.b[l] = p->fc_b[l]; ra.K[l] = l == 0 ? K_FC1 : F_FC; }
-        ra.W[7] = p->conv2_w; ra.b[7] = p->conv2_b; ra.K[7] = 192;
-        weights_row_l1_kernel<<<dim3(F_FC / 8, CP_N_FC + 1), 256, 0, st>>>(ra, w.rowl1, w.bmax);
+        weights_row_l1_kernel<<<dim3(F_FC / 8, CP_N_FC), 256, 0, st>>>(ra, w.rowl1, w.bmax);
         CP_CHECK_LAUNCH();
     }
     if (tcE) {
@@ -513,23 +510,14 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
 
     // conv2 as implicit GEMM [n*12, 192] x [64, 192]^T
     if (tcE) {
-        // fold: the epilogue also writes the fp16 planes of y2 (the operand of fc1, whose weights take the BatchNorm)
-        tcg::YPlanes yp{reinterpret_cast<plane_t*>(w.A2), reinterpret_cast<plane_t*>(w.A2) + conv_elems, w.abound + 0,
-                        w.rowl1 + 7, w.bmax + 7, w.ascale_inv + 1};
         CP_TRY(tcg::launch_conv_nt(hi_of(w.A1), lo_of(w.A1, conv_elems), n, hi_of(w.Wc2), hi_of(w.Wc2_lo), p->conv2_b,
-                                   w.Y2, w.pa, w.pb, 1, st, w.ascale_inv + 0, fast, w.wscale_inv + 7, fold ? &yp : nullptr));
+                                   w.Y2, w.pa, w.pb, 1, st, w.ascale_inv + 0, fast, w.wscale_inv + 7));
         CP_TRY(bn_finalize(w, 1, F_CONV, (int)cp_cdiv(n, tcg::CONV_WIN), R12, p, o, st));
     } else {
         CP_TRY((launch_nt<128, 64, 0, true>(w.A1, R12, 192, 64, w.Wc2, 64, 192, p->conv2_b, w.Y2, 64, w.pa, w.pb, 1, st)));
         CP_TRY(bn_finalize(w, 1, F_CONV, (int)cp_cdiv(R12, 128), R12, p, o, st));
     }
-    if (fold) {
-        fold_bn_weights_fc1_kernel<<<F_FC, 192, 0, st>>>(p->fc_w[0], p->fc_b[0], w.scale[1], w.shift[1], w.wmax + 0, w.Wfh[0],
-                                                         w.Wfl[0], w.bias_f[0], w.wfscale_inv + 0);
-        CP_CHECK_LAUNCH();
-    } else {
-        CP_TRY(bn_apply<F_CONV>(w.Y2, w.A2, tcE, R12, w, 1, nullptr, 1.f, st, 0.f, 0, 0, nullptr, fast));
-    }
+    CP_TRY(bn_apply<F_CONV>(w.Y2, w.A2, tcE, R12, w, 1, nullptr, 1.f, st, 0.f, 0, 0, nullptr, fast));
 
     // 7 x Linear -> ReLU -> BN (-> Dropout)
     const float inv_keep = o->dropout_p > 0.f ? 1.f / (1.f - o->dropout_p) : 1.f;
@@ -540,16 +528,16 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
         // BatchNorm folding (linear blocks 1..3 -> layers 2..4, no dropout in between): layer l's epilogue also writes the
         // fp16 planes of its OUTPUT y (into the slot the BN-apply kernel would have filled), the stage's (scale, shift)
         // go into the next layer's weights / bias, and that layer's GEMM reads the y planes: no BN-apply pass.
-        const bool in_folded = fold && l < N_FOLD;
-        const bool out_planes = fold && l + 1 < N_FOLD;
+        const bool in_folded = fold && l >= 1 && l <= N_FOLD;
+        const bool out_planes = fold && l < N_FOLD;
         if (tcE) {
             const plane_t* in_lo = lo_of(in, l == 0 ? conv_elems : fc_elems);
             tcg::YPlanes yp{reinterpret_cast<plane_t*>(w.A[l]), reinterpret_cast<plane_t*>(w.A[l]) + fc_elems,
                             w.abound + 1 + l, w.rowl1 + l, w.bmax + l, w.ascale_inv + 2 + l};
-            CP_TRY(tcg::launch_nt(hi_of(in), in_lo, n, K, K, in_folded ? w.Wfh[l] : w.Wh[l],
-                                  in_folded ? w.Wfl[l] : w.Wl[l], F_FC, K, in_folded ? w.bias_f[l] : p->fc_b[l],
+            CP_TRY(tcg::launch_nt(hi_of(in), in_lo, n, K, K, in_folded ? w.Wfh[l - 1] : w.Wh[l],
+                                  in_folded ? w.Wfl[l - 1] : w.Wl[l], F_FC, K, in_folded ? w.bias_f[l - 1] : p->fc_b[l],
                                   w.Y[l], F_FC, w.pa, w.pb, 1, st, w.ascale_inv + 1 + l, fast, nullptr, nullptr, 1.f,
-                                  in_folded ? w.wfscale_inv + l : w.wscale_inv + l, nullptr,
+                                  in_folded ? w.wfscale_inv + (l - 1) : w.wscale_inv + l, nullptr,
                                   out_planes ? &yp : nullptr));
         } else {
             CP_TRY((launch_nt<128, 128, 0, false>(in, n, K, K, W, F_FC, K, p->fc_b[l], w.Y[l], F_FC, w.pa, w.pb, 1, st)));
@@ -568,8 +556,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
         }
         if (out_planes) {
             fold_bn_weights_kernel<<<F_FC, 128, 0, st>>>(p->fc_w[l + 1], p->fc_b[l + 1], w.scale[2 + l], w.shift[2 + l],
-                                                         w.wmax + l + 1, w.Wfh[l + 1], w.Wfl[l + 1], w.bias_f[l + 1],
-                                                         w.wfscale_inv + l + 1);
+                                                         w.wmax + l + 1, w.Wfh[l], w.Wfl[l], w.bias_f[l], w.wfscale_inv + l);
             CP_CHECK_LAUNCH();
             continue;
         }
@@ -665,8 +652,8 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
             const plane_t* al = lo_of(ain, l == 0 ? conv_elems : fc_elems);
             const float* gsi = w.gscale_inv + 2 + l;
             // layers 2..4 with their input BatchNorm folded: the "A planes" hold the stage's pre-BN activation
-            const FoldFix fx{w.scale[1 + l], w.shift[1 + l], gr->fc_b[l], l == 0 ? F_CONV : F_FC};
-            const FoldFix* fxp = (fold && l < N_FOLD) ? &fx : nullptr;
+            const FoldFix fx{w.scale[1 + l], w.shift[1 + l], gr->fc_b[l]};
+            const FoldFix* fxp = (fold && l >= 1 && l <= N_FOLD) ? &fx : nullptr;
             // The stage below (BN stage 1 + l: conv2 for l = 0) feeds this layer without dropout and statistics are
             // rank-local: its BN-backward sums follow from this layer's dW / db (bn_bwd_stats_from_wgrad_kernel), so
             // the weight gradient runs in line (its overlap with the BN backward bought nothing) and the

@@ -1000,18 +1000,14 @@ weights_col_l1_kernel(const WmaxArgs a, unsigned int* __restrict__ l1max) {
 // max over the rows j of sum_k |W_l[j, k]| (-> rowl1[l]) and max_j |b_l[j]| (-> bmax[l]) for the 7 linear layers
 // (blockIdx.y; one warp per row): |A . W^T + b| <= max|A| * rowl1 + bmax, the a-priori bound the GEMM epilogue scales
 // the fp16 planes of its OUTPUT by when the following BatchNorm is folded into the next layer (fold_bn_weights_kernel)
-// blockIdx.y = 7: conv2 (64 output channels; only the middle row of the 3 x 3 kernels meets data: 192 of its 576 weights)
-struct RowL1Args { const float* W[8]; const float* b[8]; int K[8]; };
+struct RowL1Args { const float* W[7]; const float* b[7]; int K[7]; };
 __global__ void __launch_bounds__(256)
 weights_row_l1_kernel(const RowL1Args a, unsigned int* __restrict__ rowl1, unsigned int* __restrict__ bmax) {
     const int l = blockIdx.y;
     const int j = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
-    if (j >= (l == 7 ? 64 : 512)) return;
+    if (j >= 512) return;
     const int K = a.K[l];
     float s = 0.f;
-    if (l == 7) {
-        for (int k = lane; k < 192; k += 32) s += fabsf(__ldg(a.W[7] + ((size_t)j * 64 + k / 3) * 9 + 3 + k % 3));
-    } else
     for (int k = lane; k < K; k += 32) s += fabsf(__ldg(a.W[l] + (size_t)j * K + k));
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -1046,41 +1042,6 @@ fold_bn_weights_kernel(const float* __restrict__ W, const float* __restrict__ b,
     __syncthreads();
     d = (red[0] + red[1]) + (red[2] + red[3]);
     m = fmaxf(fmaxf(redm[0], redm[1]), fmaxf(redm[2], redm[3]));
-    const float bound = __uint_as_float(__ldg(wmax)) * m;
-    const float S = (bound > 0.f && bound < 3.0e38f) ? exp2f(-ceilf(log2f(bound))) : 1.f;
-    if (t == 0) {
-        bias_out[j] = __ldg(b + j) + d;
-        if (j == 0) *wscale_inv_out = 1.f / S;
-    }
-    split_store4(make_float4(w.x * sc.x * S, w.y * sc.y * S, w.z * sc.z * S, w.w * sc.w * S), Wh + (size_t)j * K,
-                 Wl + (size_t)j * K, t);
-}
-
-// The same for fc1 behind the conv2 stage's BatchNorm2d (64 channels): the GEMM runs on the position-major flatten, column
-// k = p*64 + c of the operand is column c*12 + p of the parameter and takes scale[c] / shift[c].  K = 768, 192 threads.
-__global__ void __launch_bounds__(192)
-fold_bn_weights_fc1_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ scale,
-                           const float* __restrict__ shift, const unsigned int* __restrict__ wmax,
-                           plane_t* __restrict__ Wh, plane_t* __restrict__ Wl, float* __restrict__ bias_out,
-                           float* __restrict__ wscale_inv_out) {
-    constexpr int K = 768;
-    __shared__ float red[6], redm[6];
-    const int j = blockIdx.x, t = threadIdx.x, lane = t % 32, wp = t / 32;
-    const int k0 = 4 * t, p = k0 / 64, c0 = k0 % 64;
-    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c0));
-    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c0));
-    const float* wr = W + (size_t)j * K + p;
-    const float4 w = make_float4(__ldg(wr + (c0 + 0) * 12), __ldg(wr + (c0 + 1) * 12), __ldg(wr + (c0 + 2) * 12),
-                                 __ldg(wr + (c0 + 3) * 12));
-    float m = fmaxf(fmaxf(fabsf(sc.x), fabsf(sc.y)), fmaxf(fabsf(sc.z), fabsf(sc.w)));
-    float d = fmaf(w.x, sh.x, fmaf(w.y, sh.y, fmaf(w.z, sh.z, w.w * sh.w)));
-    m = warp_max(m);
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-    if (lane == 0) { red[wp] = d; redm[wp] = m; }
-    __syncthreads();
-    d = ((red[0] + red[1]) + (red[2] + red[3])) + (red[4] + red[5]);
-    m = fmaxf(fmaxf(fmaxf(redm[0], redm[1]), fmaxf(redm[2], redm[3])), fmaxf(redm[4], redm[5]));
     const float bound = __uint_as_float(__ldg(wmax)) * m;
     const float S = (bound > 0.f && bound < 3.0e38f) ? exp2f(-ceilf(log2f(bound))) : 1.f;
     if (t == 0) {
@@ -1158,14 +1119,14 @@ prep_weights_tc_kernel(const PrepTcArgs a) {
 // dW = sum_z P[z]  with the inverse re-layouts.  mode 0: identity; 1: fc1 (cols p*64+c -> c*12+p);
 // 2: conv2 (cols tap*64+c -> [o][c][1][tap] of a zero-initialised (64,64,3,3) tensor);
 // 3: conv2 from the transposed tensor-core partials P[z][256][64] (row tap*64+c, column o)
-// fold_scale / fold_shift / fold_db non-null (modes 0, 1): the A operand was the PRE-BatchNorm activation y of a stage whose BN
+// fold_scale / fold_shift / fold_db non-null (mode 0): the A operand was the PRE-BatchNorm activation y of a stage whose BN
 // is folded into this layer (fold_bn_weights_kernel): dW[o,k] = sum_r g[r,o] (y[r,k] scale[k] + shift[k])
 //                                                             = scale[k] * (G^T y)[o,k] + shift[k] * db[o]
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ P, int S, int Mo, int No, float* __restrict__ out, int mode,
                     const float* __restrict__ scale = nullptr, const float* __restrict__ scale2 = nullptr,
                     const float* __restrict__ fold_scale = nullptr, const float* __restrict__ fold_shift = nullptr,
-                    const float* __restrict__ fold_db = nullptr, int fold_period = 1 << 30) {
+                    const float* __restrict__ fold_db = nullptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Mo * No) return;
     // undoes the power-of-two scales of the G planes and of the activation planes
@@ -1181,8 +1142,7 @@ wgrad_reduce_kernel(const float* __restrict__ P, int S, int Mo, int No, float* _
     for (int z = 0; z < S; ++z) s += (double)__ldg(P + (int64_t)z * Mo * No + i);
     s *= sc;
     const int o = i / No, k = i % No;
-    if (fold_scale)        // (fc1: column k = p*64 + c of the permuted operand belongs to BN channel c = k % 64)
-        s = s * (double)__ldg(fold_scale + k % fold_period) + (double)__ldg(fold_shift + k % fold_period) * (double)__ldg(fold_db + o);
+    if (fold_scale) s = s * (double)__ldg(fold_scale + k) + (double)__ldg(fold_shift + k) * (double)__ldg(fold_db + o);
     if (mode == 0) out[i] = (float)s;
     else if (mode == 1) out[o * 768 + (k % 64) * 12 + k / 64] = (float)s;
     else out[(o * 64 + k % 64) * 9 + 3 + k / 64] = (float)s;

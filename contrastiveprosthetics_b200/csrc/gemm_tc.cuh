@@ -184,8 +184,7 @@ template <int BN_, bool CONV, bool FAST>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                  const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_p_hi,
-                  const __grid_constant__ CUtensorMap tm_p_lo, const NtArgs g) {
+                  const __grid_constant__ CUtensorMap tm_c, const NtArgs g) {
     using Cfg = NtCfg<BN_>;
     constexpr int ROWS = CONV ? CONV_ROWS : BM;                 // data rows per tile
     constexpr uint32_t A_BYTES = ROWS * BK * 2;
@@ -285,14 +284,6 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         const int et = threadIdx.x - 64;             // 0..127
         const float oscale = (g.out_scale ? __ldg(g.out_scale) : 1.f) * (g.out_scale2 ? __ldg(g.out_scale2) : 1.f);
         const float cscale = CP_LO_INV * oscale;
-        // CONV with plane outputs (g.yscale_inv_out non-null; see NtArgs EPI_YPLANES): conv2's BatchNorm is folded into fc1
-        const bool yplanes = CONV && g.yscale_inv_out != nullptr;
-        float yS = 1.f;
-        if (yplanes) {
-            yS = plane_scale(fmaf(__uint_as_float(__ldg(g.y_in_bound)), __uint_as_float(__ldg(g.y_row_l1)),
-                                  __uint_as_float(__ldg(g.y_bias_max))));
-            if (blockIdx.x == 0 && et == 0) *g.yscale_inv_out = 1.f / yS;
-        }
         int it = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -352,35 +343,6 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                     }
                 } else {
                     store_box_tma(&tm_c, out_boxes + q * OUT_BOX, v, lane, col, tile_m * ROWS + q * 32);
-                }
-                if (yplanes) {
-                    // fp16 planes of C * S: [120 rows][64 B] hi at the start of the box region, lo 8 KB further, no swizzle,
-                    // once the fp32 store has read the region
-                    uint32_t hq[16], lq[16];
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        const float a = fminf(fmaxf(v[2 * u] * yS, -65000.f), 65000.f);
-                        const float b = fminf(fmaxf(v[2 * u + 1] * yS, -65000.f), 65000.f);
-                        const __half2 h2 = __floats2half2_rn(a, b);
-                        const float2 hf = __half22float2(h2);
-                        const __half2 l2 = __floats2half2_rn((a - hf.x) * CP_LO_SCALE, (b - hf.y) * CP_LO_SCALE);
-                        hq[u] = *reinterpret_cast<const uint32_t*>(&h2);
-                        lq[u] = *reinterpret_cast<const uint32_t*>(&l2);
-                    }
-                    if (et == 0) tc::tma_store_wait_read();
-                    tc::named_bar_sync(2, EPI_THREADS);
-#pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        *reinterpret_cast<uint4*>(out_boxes + rl * 64 + j8 * 16) = make_uint4(hq[4 * j8], hq[4 * j8 + 1], hq[4 * j8 + 2], hq[4 * j8 + 3]);
-                        *reinterpret_cast<uint4*>(out_boxes + 8192 + rl * 64 + j8 * 16) = make_uint4(lq[4 * j8], lq[4 * j8 + 1], lq[4 * j8 + 2], lq[4 * j8 + 3]);
-                    }
-                    tc::fence_proxy_async();
-                    tc::named_bar_sync(2, EPI_THREADS);
-                    if (et == 0) {
-                        tc::tma_store_2d(&tm_p_hi, out_boxes, col, (int)(tile_m * ROWS));
-                        tc::tma_store_2d(&tm_p_lo, out_boxes + 8192, col, (int)(tile_m * ROWS));
-                        tc::tma_store_commit();
-                    }
                 }
                 if (g.psum && g.keep) {
                     masked_col_sums(v, g, load_mask32(g, row, col, row_ok), lane);
@@ -1380,12 +1342,12 @@ inline int make_tmap_out(CUtensorMap* m, float* base, int64_t rows, int64_t cols
 }
 
 // fp16 plane output [rows, cols] (leading dimension ld halves): 32 x 32 boxes (64-byte rows), no swizzle (TMA store)
-inline int make_tmap_plane_out(CUtensorMap* m, plane_t* base, int64_t rows, int64_t cols, int64_t ld, int box_rows = 32) {
+inline int make_tmap_plane_out(CUtensorMap* m, plane_t* base, int64_t rows, int64_t cols, int64_t ld) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return CP_ERR_UNSUPPORTED;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {32, 32};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1395,15 +1357,14 @@ inline int make_tmap_plane_out(CUtensorMap* m, plane_t* base, int64_t rows, int6
 template <int BN_, bool CONV, bool FAST>
 inline int launch_nt_cfg(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
                          const CUtensorMap& tb_lo, const CUtensorMap& tc_out, const NtArgs& g, int64_t tiles_m,
-                         cudaStream_t st, const CUtensorMap* tp_hi = nullptr, const CUtensorMap* tp_lo = nullptr) {
+                         cudaStream_t st) {
     CP_ONCE_PER_DEVICE({
         CP_CUDA(cudaFuncSetAttribute(gemm_tc_nt_kernel<BN_, CONV, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      NtCfg<BN_>::SMEM));
     });
     const int64_t n_tiles = tiles_m * (g.N / BN_);
     const int grid = (int)(n_tiles < CP_NUM_SMS ? n_tiles : CP_NUM_SMS);
-    gemm_tc_nt_kernel<BN_, CONV, FAST><<<grid, THREADS, NtCfg<BN_>::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out,
-                                                                                tp_hi ? *tp_hi : tc_out, tp_lo ? *tp_lo : tc_out, g);
+    gemm_tc_nt_kernel<BN_, CONV, FAST><<<grid, THREADS, NtCfg<BN_>::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
@@ -1514,26 +1475,17 @@ inline int launch_nt_bnbwd(const plane_t* A_hi, const plane_t* A_lo, int64_t M, 
 inline int launch_conv_nt(const plane_t* X_hi, const plane_t* X_lo, int64_t windows, const plane_t* B_hi,
                           const plane_t* B_lo, const float* bias, float* C, float* psum, float* psq, int relu,
                           cudaStream_t st, const float* out_scale = nullptr, int fast = 0,
-                          const float* out_scale2 = nullptr, const YPlanes* yp = nullptr) {
-    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_out, tp_hi, tp_lo;
+                          const float* out_scale2 = nullptr) {
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tc_out;
     int rc;
     if ((rc = make_tmap_out(&tc_out, C, windows * 12, 64, 64, CONV_ROWS)) != CP_OK) return rc;
-    if (yp) {
-        if ((rc = make_tmap_plane_out(&tp_hi, yp->hi, windows * 12, 64, 64, CONV_ROWS)) != CP_OK) return rc;
-        if ((rc = make_tmap_plane_out(&tp_lo, yp->lo, windows * 12, 64, 64, CONV_ROWS)) != CP_OK) return rc;
-    }
     if ((rc = make_tmap_conv(&ta_hi, X_hi, windows, CONV_WIN)) != CP_OK) return rc;
     if ((rc = make_tmap_conv(&ta_lo, X_lo, windows, CONV_WIN)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_hi, B_hi, 64, 192, 192, 64)) != CP_OK) return rc;
     if ((rc = make_tmap_2d(&tb_lo, B_lo, 64, 192, 192, 64)) != CP_OK) return rc;
     NtArgs g{C, 64, bias, psum, psq, windows * 12, 64, 192, relu, out_scale, fast, nullptr, nullptr, 1.f, out_scale2};
-    if (yp) {
-        g.y_in_bound = yp->in_bound; g.y_row_l1 = yp->row_l1; g.y_bias_max = yp->bias_max;
-        g.yscale_inv_out = yp->scale_inv_out;
-    }
-    const CUtensorMap *ph = yp ? &tp_hi : nullptr, *pl = yp ? &tp_lo : nullptr;
-    return fast ? launch_nt_cfg<64, true, true>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st, ph, pl)
-                : launch_nt_cfg<64, true, false>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st, ph, pl);
+    return fast ? launch_nt_cfg<64, true, true>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st)
+                : launch_nt_cfg<64, true, false>(ta_hi, ta_lo, tb_hi, tb_lo, tc_out, g, cp_cdiv(windows, CONV_WIN), st);
 }
 
 // conv2 weight gradient; P capacity >= splits*256*64 floats; *splits_out = number of slabs written
