@@ -445,6 +445,10 @@ def run_cuda(args):
         hbm = hbm_kernels(dev, measured_peaks()["hbm_gbs"])
         evalp = eval_pipeline(dev)
         prep = preprocess_leg(dev)
+    c5 = None
+    if not strong:
+        torch.cuda.empty_cache()
+        c5 = c5_leg(rank, world, dev)            # config 5 at this N (every rank takes part in its collectives)
     if rank == 0:
         if world == 1:       # N = 1 only: at N > 1 the other ranks spin in the barrier on the same host cores
             cpu = cpu_reference_baseline(n_steps=10, warmup=2)
@@ -472,6 +476,7 @@ def run_cuda(args):
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e, "step_mode": e2e_mode},
             "roofline": roof, "cpu_baseline": cpu, "step_modes": modes,
             "c1_small_batch": c1, "torch_eager_gpu": eager, "hbm_kernels": hbm, "eval_pipeline": evalp, "offline_preprocess": prep,
+            "c5_clip": c5,
             "subset_eval": {"value": preds_per_s, "unit": "preds/s", "ms": ms_sub,
                             "workload": "C4: 160 items x 25 x 41 test windows x 5760 trials (144 x 40 sizes), "
                                         "rank + vote + count; trials sharded over ranks"},
@@ -483,6 +488,79 @@ def run_cuda(args):
 
 
 # ----------------------------------------------------------------------------- config 5 (CLIP) arm
+def c5_leg(rank, world, dev, B=65536, steps=5, warmup=2):
+    """Config 5 inside the default line (`c5_clip` key, every N): the batch x batch CLIP train step at GLOBAL batch B
+    sharded over the ranks (strong scaling), and the head alone on this rank's (B/world) x B strip.  Device-resident
+    inputs, CUDA events, max over ranks."""
+    import torch.distributed as dist
+    from contrastiveprosthetics_b200 import clip as C, dist as cpdist
+    from contrastiveprosthetics_b200.clip import ClipModel
+    from contrastiveprosthetics_b200.load import DB23
+    from contrastiveprosthetics_b200.utils import TaskWrapper
+    n = B // world
+    torch.manual_seed(42)
+    model = ClipModel(dict(PARAMS), glove_dim=22, device=str(dev))
+    model.train()
+    opt_e = torch.optim.Adam(model.emg_net.parameters(), lr=PARAMS['lr_emg'], weight_decay=0)
+    opt_g = torch.optim.Adam(model.glove_net.parameters(), lr=PARAMS['lr_glove'], weight_decay=0)
+    sync_grads = cpdist.FlatGradAllReduce(list(model.emg_net.parameters()) + list(model.glove_net.parameters()),
+                                          average=False)
+    ds = DB23(db2=True, device=dev)
+    ds.load_synthetic(with_glove=True, glove_dim=22)
+    tw = TaskWrapper(ds, with_glove=True)
+    tw.set_train()
+    tw.idx = torch.randperm(tw.TASKS * tw.D, generator=torch.Generator().manual_seed(5)).to(dev)   # same on every rank
+    n_batches = (tw.TASKS * tw.D) // B
+    it = {"i": 0}
+
+    def step():
+        it["i"] += 1
+        EMG, GLOVE, _ = tw.get_flat_batch((it["i"] % n_batches) * B + rank * n, n)
+        e, g = model(EMG, GLOVE)
+        total = model.loss(e, g) + model.l2()
+        opt_e.zero_grad(set_to_none=True)
+        opt_g.zero_grad(set_to_none=True)
+        total.backward()
+        sync_grads()
+        opt_e.step()
+        opt_g.step()
+
+    E = torch.randn(n, 16, device=dev, requires_grad=True)
+    G = torch.randn(n, 16, device=dev, requires_grad=True)
+
+    def head_only():
+        E.grad = G.grad = None
+        C.clip_head(E, G, 0.0)[0].backward()
+
+    def timed(fn, k, w):
+        for _ in range(w):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / k], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms = timed(step, steps, warmup)
+    ms_head = timed(head_only, steps, warmup)
+    model.n_correct.clear()
+    return {"ms_per_step": ms, "samples_per_s": B / (ms / 1e3), "global_batch": B, "samples_per_gpu": n, "scaling": "strong",
+            "head_ms": ms_head, "head_pairs_per_s": float(n) * float(B) * world / (ms_head / 1e3),
+            "workload": "C5: glove-angle (22-dim) tower + EMG tower, CLIP batch x batch loss (B x B never materialised; "
+                        "fp32 FFMA2 + MUFU sweeps), all-gather Ghat / all-reduce column sums / reduce-scatter dGhat at N > 1; "
+                        "`bench.py --workload c5` prints the full line (e2e, clocks)"}
+
+
 def run_c5(args):
     """BASELINE.json config 5: glove-angle (22-dim) tower + EMG tower, batch x batch CLIP loss, GLOBAL batch
     65,536 sharded over the ranks (strong scaling): all-gather of the glove embeddings, all-reduce of the
