@@ -17,6 +17,8 @@
 // column pass: own = Ghat (all B rows),       loop = Ehat (this rank's rows)  -> partial sums that the
 //              host all-reduces (column sums) / reduce-scatters (d Ghat) across ranks.
 // Results are deterministic (fixed-order shuffles, no float atomics).
+#include <cstdlib>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace {
@@ -234,6 +236,258 @@ __global__ void __launch_bounds__(THREADS, 1) clip_sweep_kernel(const SweepArgs 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// The same sweeps with the two contractions on the warp-level tensor cores (mma.sync m16n8k16, fp16 operands, fp32
+// accumulate) and the 3-product split of the encoder's GEMMs: x = hi + lo/2048 with hi = fp16(x), lo = fp16((x - hi)*2048);
+// a.b ~= hi_a.hi_b + (lo_a.hi_b + hi_a.lo_b)/2048 (22 significand bits per operand).  K = 16 is ONE k16 step: a 16-row x
+// 8-column similarity fragment costs 3 MMAs instead of 128 FMAs, and the gradient contraction d_own += P . Y (P = the
+// weights of the two fragments just computed, 16 x 16) takes the accumulator fragments AS its A operand -- the m16n8
+// accumulator layout is the m16k16 A layout -- so P never leaves registers.  What remains per pair is the exponent
+// (one ex2), a few FMAs and the hi/lo split of P.  (A first version on m16n8k8 tf32 MMAs, 3xTF32, was only 1.25x faster
+// than the FFMA2 kernel: the legacy tf32 path issues at ~1/16 clk per sub-partition on this chip.)
+// A warp owns 16 own rows for the whole sweep; a CTA = 8 warps = 128 own rows; the loop operand arrives in tiles of 128
+// columns and is split into fp16 planes ONCE per CTA, in the two layouts the two contractions read: pairs along k
+// (B operand of the similarity) and pairs along j (B operand of P . Y); padded rows make both fragment reads conflict-free.
+// Accumulation chains are cut per tile (the tensor core's fp32 accumulator does not round to nearest): every tile's
+// fragment is added to the running sums with ordinary fp32 adds.  Deterministic: fixed-order shuffles only.
+// Problems of one tile (n_loop <= 128) stay on the FFMA2 kernel: there the similarity of a pair and the diagonal term of
+// the loss kernel are the same fp32 FMA chain and cancel exactly (a batch of ONE has loss 0 to the last bit).
+namespace mm {
+constexpr int WARPS = 8;
+constexpr int OWN = 16 * WARPS;      // own rows per CTA
+constexpr int LOOP = 128;            // loop columns per tile
+constexpr int KS = LOOP + 8;         // words per row of the k-pair layout  [8 k-pairs][LOOP columns]
+constexpr int JS = LOOP / 2 + 4;     // words per row of the j-pair layout  [16 dims][LOOP/2 column pairs]
+constexpr int THREADS = 32 * WARPS;
+constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    const __half2 h = __halves2half2(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn((x - __half2float(hi)) * LO_SCALE);
+}
+// (a, b) -> packed hi pair, packed lo pair
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h2 = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn((a - hf.x) * LO_SCALE, (b - hf.y) * LO_SCALE);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+// D (16 x 8, fp32) += A (16 x 16 fp16, row fragment) . B (16 x 8 fp16, column fragment)
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(THREADS, 2) clip_sweep_mma_kernel(const SweepArgs g) {
+    // loop tile, fp16 planes: Kh/Kl[kp][j] = (y[2kp][j], y[2kp+1][j]);  Jh/Jl[d][jp] = (y[d][2jp], y[d][2jp+1])
+    __shared__ __align__(16) uint32_t Kh[2][D / 2][KS], Kl[2][D / 2][KS];
+    __shared__ __align__(16) uint32_t Jh[2][D][JS], Jl[2][D][JS];
+    __shared__ __align__(16) float Ls[2][LOOP];          // 1 / loop_sum of the tile (GRAD)
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const int gq = lane >> 2, t = lane & 3;              // fragment coordinates: groupID, threadID_in_group
+    const int64_t r0 = (int64_t)blockIdx.x * OWN + warp * 16;
+    const int64_t row_a = r0 + gq, row_b = r0 + gq + 8;  // the two own rows of this thread's fragments
+
+    // A operand of the similarity: the warp's 16 own rows x 16 dims (rows beyond n_own: zeros)
+    //   a0: (row_a, dims 2t, 2t+1)  a1: (row_b, 2t, 2t+1)  a2: (row_a, 2t+8, 2t+9)  a3: (row_b, 2t+8, 2t+9)
+    uint32_t ah[4], al[4];
+    {
+        const float2 z = make_float2(0.f, 0.f);
+        const float2 xa0 = row_a < g.n_own ? __ldg(reinterpret_cast<const float2*>(g.X + row_a * D + 2 * t)) : z;
+        const float2 xb0 = row_b < g.n_own ? __ldg(reinterpret_cast<const float2*>(g.X + row_b * D + 2 * t)) : z;
+        const float2 xa1 = row_a < g.n_own ? __ldg(reinterpret_cast<const float2*>(g.X + row_a * D + 2 * t + 8)) : z;
+        const float2 xb1 = row_b < g.n_own ? __ldg(reinterpret_cast<const float2*>(g.X + row_b * D + 2 * t + 8)) : z;
+        split_pair(xa0.x, xa0.y, ah[0], al[0]);
+        split_pair(xb0.x, xb0.y, ah[1], al[1]);
+        split_pair(xa1.x, xa1.y, ah[2], al[2]);
+        split_pair(xb1.x, xb1.y, ah[3], al[3]);
+    }
+    float inv_own[2] = {0.f, 0.f};
+    if (GRAD) {
+        if (row_a < g.n_own) inv_own[0] = 1.f / __ldg(g.own_sum_in + row_a);
+        if (row_b < g.n_own) inv_own[1] = 1.f / __ldg(g.own_sum_in + row_b);
+    }
+
+    const int64_t n_tiles = (g.n_loop + LOOP - 1) / LOOP;
+    // this thread's share of a tile load: dims (2 kp, 2 kp + 1) x 4 consecutive columns
+    const int kp = tid / 32;                             // 0..7
+    const int ljq = (tid % 32) * 4;
+    auto fetch = [&](int64_t tile, float4 (&v)[2], float& lsum) {
+        const int64_t j0 = tile * LOOP;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            v[q] = (j0 + ljq < g.ld_y) ? __ldg(reinterpret_cast<const float4*>(g.Yt + (int64_t)(2 * kp + q) * g.ld_y + j0 + ljq))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (GRAD && tid < LOOP) lsum = (j0 + tid < g.n_loop) ? __ldg(g.loop_sum + j0 + tid) : 0.f;
+    };
+    auto stash = [&](int buf, const float4 (&v)[2], float lsum) {
+        const float e[2][4] = {{v[0].x, v[0].y, v[0].z, v[0].w}, {v[1].x, v[1].y, v[1].z, v[1].w}};
+        __half h[2][4], l[2][4];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) split_h(e[q][c], h[q][c], l[q][c]);
+        // pairs along k: word (kp, j) = (dim 2kp, dim 2kp+1) of column j
+        *reinterpret_cast<uint4*>(&Kh[buf][kp][ljq]) =
+            make_uint4(pack_h2(h[0][0], h[1][0]), pack_h2(h[0][1], h[1][1]), pack_h2(h[0][2], h[1][2]), pack_h2(h[0][3], h[1][3]));
+        *reinterpret_cast<uint4*>(&Kl[buf][kp][ljq]) =
+            make_uint4(pack_h2(l[0][0], l[1][0]), pack_h2(l[0][1], l[1][1]), pack_h2(l[0][2], l[1][2]), pack_h2(l[0][3], l[1][3]));
+        if (GRAD) {
+            // pairs along j: word (d, jp) = columns (2jp, 2jp+1) of dim d
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                *reinterpret_cast<uint2*>(&Jh[buf][2 * kp + q][ljq / 2]) = make_uint2(pack_h2(h[q][0], h[q][1]), pack_h2(h[q][2], h[q][3]));
+                *reinterpret_cast<uint2*>(&Jl[buf][2 * kp + q][ljq / 2]) = make_uint2(pack_h2(l[q][0], l[q][1]), pack_h2(l[q][2], l[q][3]));
+            }
+            if (tid < LOOP) Ls[buf][tid] = lsum > 0.f ? 1.f / lsum : 0.f;
+        }
+    };
+
+    float acc[2] = {0.f, 0.f};                           // running row sums (rows gq, gq + 8)
+    float best[2] = {-INFINITY, -INFINITY};
+    int best_j[2] = {0x7fffffff, 0x7fffffff};
+    float dsum[2][4];                                    // running gradient fragments: [d-tile][c0..c3]
+#pragma unroll
+    for (int dt = 0; dt < 2; ++dt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dsum[dt][e] = 0.f;
+
+    {
+        float4 v[2];
+        float ls = 0.f;
+        fetch(0, v, ls);
+        stash(0, v, ls);
+    }
+    __syncthreads();
+    for (int64_t tile = 0; tile < n_tiles; ++tile) {
+        const int buf = (int)(tile & 1);
+        float4 nv[2];
+        float nls = 0.f;
+        const bool more = tile + 1 < n_tiles;
+        if (more) fetch(tile + 1, nv, nls);              // in flight while this tile is computed
+
+        const int64_t j0 = tile * LOOP;
+        float tacc[2] = {0.f, 0.f};
+        float dm[2][4], dc[2][4];                        // this tile's gradient fragments: main / correction (x 2048) terms
+        if (GRAD) {
+#pragma unroll
+            for (int dt = 0; dt < 2; ++dt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dm[dt][e] = dc[dt][e] = 0.f;
+        }
+#pragma unroll 2
+        for (int np = 0; np < LOOP / 16; ++np) {         // 16 columns = two 8-column similarity fragments
+            float ev[2][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int n0 = np * 16 + h * 8;
+                const uint32_t bh0 = Kh[buf][t][n0 + gq], bh1 = Kh[buf][t + 4][n0 + gq];
+                const uint32_t bl0 = Kl[buf][t][n0 + gq], bl1 = Kl[buf][t + 4][n0 + gq];
+                float cm[4] = {0.f, 0.f, 0.f, 0.f}, cc[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_f16(cc, al, bh0, bh1);
+                mma_f16(cc, ah, bl0, bl1);
+                mma_f16(cm, ah, bh0, bh1);
+                // c0: (row_a, col 2t), c1: (row_a, 2t+1), c2: (row_b, 2t), c3: (row_b, 2t+1)
+                const int64_t ja = j0 + n0 + 2 * t;
+                const bool ok0 = ja < g.n_loop, ok1 = ja + 1 < g.n_loop;
+                float sv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sv[e] = fmaf(cc[e], LO_INV, cm[e]);
+                ev[h][0] = ok0 ? ex2(fmaf(sv[0], g.a, -g.a)) : 0.f;
+                ev[h][1] = ok1 ? ex2(fmaf(sv[1], g.a, -g.a)) : 0.f;
+                ev[h][2] = ok0 ? ex2(fmaf(sv[2], g.a, -g.a)) : 0.f;
+                ev[h][3] = ok1 ? ex2(fmaf(sv[3], g.a, -g.a)) : 0.f;
+                if (!GRAD) {
+                    tacc[0] += ev[h][0] + ev[h][1];
+                    tacc[1] += ev[h][2] + ev[h][3];
+                    if (ok0 && sv[0] > best[0]) { best[0] = sv[0]; best_j[0] = (int)ja; }
+                    if (ok1 && sv[1] > best[0]) { best[0] = sv[1]; best_j[0] = (int)ja + 1; }
+                    if (ok0 && sv[2] > best[1]) { best[1] = sv[2]; best_j[1] = (int)ja; }
+                    if (ok1 && sv[3] > best[1]) { best[1] = sv[3]; best_j[1] = (int)ja + 1; }
+                } else {
+                    const float2 il = *reinterpret_cast<const float2*>(&Ls[buf][n0 + 2 * t]);
+                    ev[h][0] *= inv_own[0] + il.x; ev[h][1] *= inv_own[0] + il.y;
+                    ev[h][2] *= inv_own[1] + il.x; ev[h][3] *= inv_own[1] + il.y;
+                }
+            }
+            if (GRAD) {
+                // P (16 rows x 16 columns) as the A operand: a0 = (row_a, cols 2t, 2t+1) of the first fragment, a1 = row_b,
+                // a2 / a3 = the same of the second fragment (columns + 8)
+                uint32_t ph[4], pl[4];
+                split_pair(ev[0][0], ev[0][1], ph[0], pl[0]);
+                split_pair(ev[0][2], ev[0][3], ph[1], pl[1]);
+                split_pair(ev[1][0], ev[1][1], ph[2], pl[2]);
+                split_pair(ev[1][2], ev[1][3], ph[3], pl[3]);
+#pragma unroll
+                for (int dt = 0; dt < 2; ++dt) {
+                    // B: k = loop columns np*16 + (2t, 2t+1) and + 8, n = embedding dim dt*8 + gq
+                    const uint32_t yh0 = Jh[buf][dt * 8 + gq][np * 8 + t], yh1 = Jh[buf][dt * 8 + gq][np * 8 + t + 4];
+                    const uint32_t yl0 = Jl[buf][dt * 8 + gq][np * 8 + t], yl1 = Jl[buf][dt * 8 + gq][np * 8 + t + 4];
+                    mma_f16(dc[dt], pl, yh0, yh1);
+                    mma_f16(dc[dt], ph, yl0, yl1);
+                    mma_f16(dm[dt], ph, yh0, yh1);
+                }
+            }
+        }
+        if (!GRAD) {
+            acc[0] += tacc[0];
+            acc[1] += tacc[1];
+        } else {
+#pragma unroll
+            for (int dt = 0; dt < 2; ++dt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dsum[dt][e] += fmaf(dc[dt][e], LO_INV, dm[dt][e]);
+        }
+        if (more) stash(buf ^ 1, nv, nls);               // the other buffer was last read before the previous barrier
+        __syncthreads();
+    }
+
+    if (!GRAD) {
+        // the 4 threads of a group hold disjoint columns of the same two rows
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float v = acc[h], b = best[h];
+            int bj = best_j[h];
+#pragma unroll
+            for (int off = 1; off <= 2; off <<= 1) {
+                v += __shfl_xor_sync(0xffffffffu, v, off);
+                const float ob = __shfl_xor_sync(0xffffffffu, b, off);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+                if (ob > b || (ob == b && oj < bj)) { b = ob; bj = oj; }
+            }
+            const int64_t row = h ? row_b : row_a;
+            if (t == 0 && row < g.n_own) {
+                g.own_sum[row] = v;
+                if (g.own_arg) g.own_arg[row] = bj;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int dt = 0; dt < 2; ++dt) {
+            if (row_a < g.n_own)
+                *reinterpret_cast<float2*>(g.d_own + row_a * D + dt * 8 + 2 * t) =
+                    make_float2(g.coef * dsum[dt][0], g.coef * dsum[dt][1]);
+            if (row_b < g.n_own)
+                *reinterpret_cast<float2*>(g.d_own + row_b * D + dt * 8 + 2 * t) =
+                    make_float2(g.coef * dsum[dt][2], g.coef * dsum[dt][3]);
+        }
+    }
+}
+// CP_CLIP_MMA=0 in the environment keeps every size on the FFMA2 kernel above (A/B runs)
+inline bool use_mma(int64_t n_loop) {
+    static const bool on = [] { const char* e = getenv("CP_CLIP_MMA"); return !(e && e[0] == '0'); }();
+    return on && n_loop > LOOP;
+}
+}  // namespace mm
+
 // xhat = x / ||x||, inv_norm = 1 / ||x||    (models.py:123,125: no epsilon)
 __global__ void __launch_bounds__(256)
 clip_normalize_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ xhat, float* __restrict__ inv_norm) {
@@ -344,6 +598,9 @@ extern "C" int cp_clip_sums(const float* own, int64_t n_own, const float* loop_t
         !(scale > 0.f) || ((uintptr_t)loop_t % 16) != 0)
         return CP_ERR_ARG;
     SweepArgs g{own, loop_t, n_own, n_loop, ld_loop, scale * LOG2E, own_sum, own_argmax, nullptr, nullptr, 0.f, nullptr};
+    if (mm::use_mma(n_loop))
+        mm::clip_sweep_mma_kernel<false><<<(unsigned)cp_cdiv(n_own, mm::OWN), mm::THREADS, 0, (cudaStream_t)stream>>>(g);
+    else
     clip_sweep_kernel<false><<<(unsigned)cp_cdiv(n_own, OWN), THREADS, 0, (cudaStream_t)stream>>>(g);
     CP_CHECK_LAUNCH();
     return CP_OK;
@@ -356,6 +613,9 @@ extern "C" int cp_clip_grad(const float* own, int64_t n_own, const float* loop_t
         ld_loop % 4 != 0 || !(scale > 0.f) || ((uintptr_t)loop_t % 16) != 0)
         return CP_ERR_ARG;
     SweepArgs g{own, loop_t, n_own, n_loop, ld_loop, scale * LOG2E, nullptr, nullptr, own_sum, loop_sum, coef, d_own};
+    if (mm::use_mma(n_loop))
+        mm::clip_sweep_mma_kernel<true><<<(unsigned)cp_cdiv(n_own, mm::OWN), mm::THREADS, 0, (cudaStream_t)stream>>>(g);
+    else
     clip_sweep_kernel<true><<<(unsigned)cp_cdiv(n_own, OWN), THREADS, 0, (cudaStream_t)stream>>>(g);
     CP_CHECK_LAUNCH();
     return CP_OK;
