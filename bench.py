@@ -557,7 +557,7 @@ def c5_leg(rank, world, dev, B=65536, steps=5, warmup=2):
     return {"ms_per_step": ms, "samples_per_s": B / (ms / 1e3), "global_batch": B, "samples_per_gpu": n, "scaling": "strong",
             "head_ms": ms_head, "head_pairs_per_s": float(n) * float(B) * world / (ms_head / 1e3),
             "workload": "C5: glove-angle (22-dim) tower + EMG tower, CLIP batch x batch loss (B x B never materialised; "
-                        "fp32 FFMA2 + MUFU sweeps), all-gather Ghat / all-reduce column sums / reduce-scatter dGhat at N > 1; "
+                        "mma.sync m16n8k16 fp16 3-product split + MUFU sweeps), all-gather Ghat / all-reduce column sums / reduce-scatter dGhat at N > 1; "
                         "`bench.py --workload c5` prints the full line (e2e, clocks)"}
 
 
@@ -678,8 +678,8 @@ def run_c5(args):
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e},
             "clip_head": {"ms": ms_head, "pairs_per_s": pairs / (ms_head / 1e3),
                           "fp32_tflops": head_flops / (ms_head * 1e-3) / 1e12,
-                          "kernel": "clip_sweep_kernel (fp32 FFMA + MUFU.EX2; B x B never materialised)",
-                          "note": "bound by the fp32 FMA pipe, not HBM (inputs 8 MB) and not the tensor pipe (K = 16)"},
+                          "kernel": "clip_sweep_mma_kernel (mma.sync m16n8k16 fp16, 3-product hi/lo split, fp32 accumulate + MUFU.EX2; B x B never materialised)",
+                          "note": "bound by instruction issue / MUFU (one ex2 per pair), not HBM (inputs 8 MB)"},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

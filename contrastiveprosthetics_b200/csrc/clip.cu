@@ -18,6 +18,7 @@
 //              host all-reduces (column sums) / reduce-scatters (d Ghat) across ranks.
 // Results are deterministic (fixed-order shuffles, no float atomics).
 #include <cstdlib>
+#include <type_traits>
 #include <cuda_fp16.h>
 #include "common.cuh"
 
@@ -285,7 +286,7 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], u
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <bool GRAD>
+template <bool GRAD, bool ARG>
 __global__ void __launch_bounds__(THREADS, 2) clip_sweep_mma_kernel(const SweepArgs g) {
     // loop tile, fp16 planes: Kh/Kl[kp][j] = (y[2kp][j], y[2kp+1][j]);  Jh/Jl[d][jp] = (y[d][2jp], y[d][2jp+1])
     __shared__ __align__(16) uint32_t Kh[2][D / 2][KS], Kl[2][D / 2][KS];
@@ -383,6 +384,8 @@ __global__ void __launch_bounds__(THREADS, 2) clip_sweep_mma_kernel(const SweepA
 #pragma unroll
                 for (int e = 0; e < 4; ++e) dm[dt][e] = dc[dt][e] = 0.f;
         }
+        auto sweep_tile = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;     // every column of the tile is a real loop row: no predicates
 #pragma unroll 2
         for (int np = 0; np < LOOP / 16; ++np) {         // 16 columns = two 8-column similarity fragments
             float ev[2][4];
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(THREADS, 2) clip_sweep_mma_kernel(const SweepA
                 mma_f16(cm, ah, bh0, bh1);
                 // c0: (row_a, col 2t), c1: (row_a, 2t+1), c2: (row_b, 2t), c3: (row_b, 2t+1)
                 const int64_t ja = j0 + n0 + 2 * t;
-                const bool ok0 = ja < g.n_loop, ok1 = ja + 1 < g.n_loop;
+                const bool ok0 = FULL || ja < g.n_loop, ok1 = FULL || ja + 1 < g.n_loop;
                 float sv[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) sv[e] = fmaf(cc[e], LO_INV, cm[e]);
@@ -408,10 +411,12 @@ __global__ void __launch_bounds__(THREADS, 2) clip_sweep_mma_kernel(const SweepA
                 if (!GRAD) {
                     tacc[0] += ev[h][0] + ev[h][1];
                     tacc[1] += ev[h][2] + ev[h][3];
+                    if (ARG) {
                     if (ok0 && sv[0] > best[0]) { best[0] = sv[0]; best_j[0] = (int)ja; }
                     if (ok1 && sv[1] > best[0]) { best[0] = sv[1]; best_j[0] = (int)ja + 1; }
                     if (ok0 && sv[2] > best[1]) { best[1] = sv[2]; best_j[1] = (int)ja; }
                     if (ok1 && sv[3] > best[1]) { best[1] = sv[3]; best_j[1] = (int)ja + 1; }
+                    }
                 } else {
                     const float2 il = *reinterpret_cast<const float2*>(&Ls[buf][n0 + 2 * t]);
                     ev[h][0] *= inv_own[0] + il.x; ev[h][1] *= inv_own[0] + il.y;
@@ -437,6 +442,8 @@ __global__ void __launch_bounds__(THREADS, 2) clip_sweep_mma_kernel(const SweepA
                 }
             }
         }
+        };
+        if (j0 + LOOP <= g.n_loop) sweep_tile(std::true_type{}); else sweep_tile(std::false_type{});
         if (!GRAD) {
             acc[0] += tacc[0];
             acc[1] += tacc[1];
@@ -466,7 +473,7 @@ __global__ void __launch_bounds__(THREADS, 2) clip_sweep_mma_kernel(const SweepA
             const int64_t row = h ? row_b : row_a;
             if (t == 0 && row < g.n_own) {
                 g.own_sum[row] = v;
-                if (g.own_arg) g.own_arg[row] = bj;
+                if (ARG) g.own_arg[row] = bj;
             }
         }
     } else {
@@ -599,7 +606,8 @@ extern "C" int cp_clip_sums(const float* own, int64_t n_own, const float* loop_t
         return CP_ERR_ARG;
     SweepArgs g{own, loop_t, n_own, n_loop, ld_loop, scale * LOG2E, own_sum, own_argmax, nullptr, nullptr, 0.f, nullptr};
     if (mm::use_mma(n_loop))
-        mm::clip_sweep_mma_kernel<false><<<(unsigned)cp_cdiv(n_own, mm::OWN), mm::THREADS, 0, (cudaStream_t)stream>>>(g);
+        if (own_argmax) mm::clip_sweep_mma_kernel<false, true><<<(unsigned)cp_cdiv(n_own, mm::OWN), mm::THREADS, 0, (cudaStream_t)stream>>>(g);
+        else mm::clip_sweep_mma_kernel<false, false><<<(unsigned)cp_cdiv(n_own, mm::OWN), mm::THREADS, 0, (cudaStream_t)stream>>>(g);
     else
     clip_sweep_kernel<false><<<(unsigned)cp_cdiv(n_own, OWN), THREADS, 0, (cudaStream_t)stream>>>(g);
     CP_CHECK_LAUNCH();
@@ -614,7 +622,7 @@ extern "C" int cp_clip_grad(const float* own, int64_t n_own, const float* loop_t
         return CP_ERR_ARG;
     SweepArgs g{own, loop_t, n_own, n_loop, ld_loop, scale * LOG2E, nullptr, nullptr, own_sum, loop_sum, coef, d_own};
     if (mm::use_mma(n_loop))
-        mm::clip_sweep_mma_kernel<true><<<(unsigned)cp_cdiv(n_own, mm::OWN), mm::THREADS, 0, (cudaStream_t)stream>>>(g);
+        mm::clip_sweep_mma_kernel<true, false><<<(unsigned)cp_cdiv(n_own, mm::OWN), mm::THREADS, 0, (cudaStream_t)stream>>>(g);
     else
     clip_sweep_kernel<true><<<(unsigned)cp_cdiv(n_own, OWN), THREADS, 0, (cudaStream_t)stream>>>(g);
     CP_CHECK_LAUNCH();
