@@ -8,6 +8,7 @@
 //     (cp_rank_rows, uint8 order); the restricted argmax of any subset is then "first label of
 //     the ranked row that is in the subset" -- ~41/|S| byte probes.  Logits are read from HBM
 //     once for all trials (164 B/window).
+#include <cstdlib>
 #include "common.cuh"
 
 #define T CP_TASKS
@@ -146,6 +147,59 @@ subset_eval_kernel(const uint8_t* __restrict__ order, int W, const uint8_t* __re
     }
 }
 
+// Round 2: one WARP per (item, trial), one lane per window.  The thread-per-trial kernel above diverges on everything
+// (every trial of a warp has its own subset: the row loop runs over the union of 32 masks, the probe walks serialise)
+// and keeps its vote counters in shared memory; here control flow is uniform -- the warp walks the rows of ITS subset --
+// each lane probes the ranked list of its window, and the windowed majority vote is two warp instructions:
+// match.any groups the lanes by predicted label (popcount = votes), redux.max picks (votes, smallest label).
+// Shared memory holds only the item's ranked rows, windows padded to 4 x 421 bytes so that the 25 lanes hit 25 banks.
+#define SE2_WARPS 8
+#define SE2_WSTRIDE (4 * ((T * T + 3) / 4 + (((T * T + 3) / 4) % 2 == 0 ? 1 : 0)))      // 1684: odd number of words
+__global__ void __launch_bounds__(SE2_WARPS * 32)
+subset_eval_warp_kernel(const uint8_t* __restrict__ order, int W, const uint8_t* __restrict__ masks,
+                        int64_t n_trials, unsigned long long* __restrict__ correct) {
+    extern __shared__ uint8_t ord[];                       // [W][SE2_WSTRIDE]: window w, row i, rank k at w*stride + i*T + k
+    const int64_t b = blockIdx.x;
+    const uint8_t* src = order + b * (int64_t)W * T * T;
+    for (int w = 0; w < W; ++w)
+        for (int e = threadIdx.x; e < T * T; e += SE2_WARPS * 32) ord[w * SE2_WSTRIDE + e] = __ldg(src + w * T * T + e);
+    __syncthreads();
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const bool active = lane < W;
+    const unsigned wmask = W >= 32 ? 0xffffffffu : ((1u << W) - 1u);
+    const uint8_t* base = ord + (active ? lane : 0) * SE2_WSTRIDE;
+    for (int64_t t = (int64_t)blockIdx.y * SE2_WARPS + warp; t < n_trials; t += (int64_t)gridDim.y * SE2_WARPS) {
+        const unsigned lo = __ballot_sync(0xffffffffu, __ldg(masks + t * T + lane) != 0);
+        const unsigned hi = __ballot_sync(0xffffffffu, lane < T - 32 && __ldg(masks + t * T + 32 + (lane < T - 32 ? lane : 0)) != 0);
+        const unsigned long long m = (unsigned long long)lo | ((unsigned long long)hi << 32);
+        int n_ok = 0;
+        for (unsigned long long mm = m; mm; mm &= mm - 1) {
+            const int i = __ffsll((long long)mm) - 1;
+            int l = 63;                                      // idle lanes: a label no subset contains
+            if (active) {
+                // first ranked label inside the subset, four candidates per step (independent byte loads; the subset
+                // contains i, so the walk ends by rank 40 -- the look-ahead reads at most 3 bytes into the window's padding)
+                const uint8_t* row = base + i * T;
+                for (int k = 0;; k += 4) {
+                    const int l0 = row[k], l1 = row[k + 1], l2 = row[k + 2], l3 = row[k + 3];
+                    const bool h0 = (m >> l0) & 1ull, h1 = (m >> (l1 & 63)) & 1ull, h2 = (m >> (l2 & 63)) & 1ull,
+                               h3 = (m >> (l3 & 63)) & 1ull;
+                    if (h0 | h1 | h2 | h3) {
+                        l = h0 ? l0 : (h1 ? l1 : (h2 ? l2 : l3));
+                        break;
+                    }
+                }
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, l);
+            // votes of the lane's label, ties to the SMALLER label (prefix-mode rule of models.py:154)
+            unsigned key = active ? (((unsigned)__popc(peers & wmask) << 6) | (unsigned)(63 - l)) : 0u;
+            key = __reduce_max_sync(0xffffffffu, key);
+            n_ok += (63 - (int)(key & 63u)) == i;
+        }
+        if (lane == 0 && n_ok) atomicAdd(correct + t, (unsigned long long)n_ok);
+    }
+}
+
 __global__ void subset_total_kernel(const uint8_t* __restrict__ masks, int64_t n_trials, int64_t B,
                                     int64_t* __restrict__ total) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -165,6 +219,20 @@ extern "C" int cp_subset_eval(const uint8_t* order, int64_t B, int W, const uint
     subset_total_kernel<<<(unsigned)cp_cdiv(n_trials, 256), 256, 0, st>>>(masks, n_trials, B, total);
     CP_CHECK_LAUNCH();
     if (B == 0) return CP_OK;
+    static const bool warp_kernel = [] { const char* e = getenv("CP_SUBSET_WARP"); return !(e && e[0] == '0'); }();
+    if (warp_kernel) {
+        const size_t smem2 = (size_t)W * SE2_WSTRIDE;
+        CP_CUDA(cudaFuncSetAttribute(subset_eval_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        // trial chunks: ~4 resident CTAs on every SM, but at least ~8 trials per warp so that staging the item's rows pays
+        int64_t chunks2 = cp_cdiv((int64_t)CP_NUM_SMS * 4, B);
+        const int64_t most = cp_cdiv(n_trials, (int64_t)SE2_WARPS * 8);
+        if (chunks2 > most) chunks2 = most;
+        if (chunks2 < 1) chunks2 = 1;
+        subset_eval_warp_kernel<<<dim3((unsigned)B, (unsigned)chunks2), SE2_WARPS * 32, smem2, st>>>(
+            order, W, masks, n_trials, reinterpret_cast<unsigned long long*>(correct));
+        CP_CHECK_LAUNCH();
+        return CP_OK;
+    }
     const size_t smem = ((size_t)(W * T * T + 15) / 16) * 16 + (size_t)T * SE_THREADS;
     CP_CUDA(cudaFuncSetAttribute(subset_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // trial chunks: enough CTAs for >= 2 waves of 148 SMs x 4 resident CTAs when B is small

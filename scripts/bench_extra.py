@@ -196,8 +196,9 @@ def hbm_kernels(dev, hbm_gbs, scale=64):
                           "preds_per_s": n_rows * masks.shape[0] / (ms_eval * 1e-3),
                           "order_table_gbs": n_rows * 41 / (ms_eval * 1e-3) / 1e9,
                           "note": "the rank-order table (41 B per row) is read from HBM once per launch and staged in "
-                                  "shared memory per item; every trial then probes it there (~41/|S| byte probes per "
-                                  "prediction), so the kernel is bound by shared-memory byte loads, not HBM"}
+                                  "shared memory per item; one warp per (item, trial) then probes it there, one lane per window (~42 byte "
+                                  "probes per (window, trial); vote = match.any + redux.max), so the kernel is bound by "
+                                  "instruction issue, not HBM"}
     del lg
     torch.cuda.empty_cache()
     return out
