@@ -304,16 +304,19 @@ template <int F>
 int bn_backward(const float* g, const float* y, float* gz, bool planes, int64_t R, const Ws& w, int l,
                 const uint8_t* keep, float inv_keep, const float* gamma, float* d_gamma, float* d_beta,
                 float* d_bias, cudaStream_t st, const cp_encoder_opts* o, bool stats_ready = false) {
-    const int P = (int)cp_cdiv(R, ColMap<F>::ROWS);
+    // small batches (the reference's batch_size 8 = 328 windows): 64 sequential rows per thread on 3 CTAs took 26 us;
+    // 8 rows per thread on 16x the CTAs (the partial rows of w.pa stay inside partial_rows(n): 16 >= 128 / 13)
+    const int rpc = (F == 512 && R < (int64_t)ColMap<F>::ROWS * 2 * CP_NUM_SMS) ? 16 : ColMap<F>::ROWS;
+    const int P = (int)cp_cdiv(R, rpc);
     float* gz_lo = planes ? reinterpret_cast<float*>(reinterpret_cast<plane_t*>(gz) + (size_t)R * F) : nullptr;
     if (int rc = bn_bwd_sums<F>(g, y, planes, R, w, l, keep, inv_keep, d_gamma, d_beta, st, o, stats_ready)) return rc;
     if (planes)
         bn_bwd_apply_kernel<F, true><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], gamma, w.m1,
                                                         w.m2, gz, gz_lo, w.pa, nullptr, w.gmax + l, w.gscale_inv + l,
-                                                        w.g1max + l);
+                                                        w.g1max + l, rpc);
     else
         bn_bwd_apply_kernel<F, false><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], gamma, w.m1,
-                                                         w.m2, gz, nullptr, w.pa);
+                                                         w.m2, gz, nullptr, w.pa, nullptr, nullptr, nullptr, nullptr, rpc);
     CP_CHECK_LAUNCH();
     colsum_finalize_kernel<<<F / 32, 1024, 0, st>>>(w.pa, P, F, d_bias, 0);
     CP_CHECK_LAUNCH();
@@ -489,7 +492,7 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
             a.W[l] = p->fc_w[l];
             a.Wh[l] = w.Wh[l]; a.Wl[l] = w.Wl[l]; a.Wth[l] = w.Wth[l]; a.Wtl[l] = w.Wtl[l];
         }
-        prep_weights_tc_kernel<<<dim3((F_FC * K_FC1 + 255) / 256, CP_N_FC), 256, 0, st>>>(a);
+        prep_weights_tc_kernel<<<dim3(K_FC1 / 32, F_FC / 32, CP_N_FC), 256, 0, st>>>(a);
         CP_CHECK_LAUNCH();
     }
     CP_CUDA(cudaMemcpyAsync(w.X0, x, sizeof(float) * R12, cudaMemcpyDeviceToDevice, st));
