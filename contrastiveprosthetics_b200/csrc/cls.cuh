@@ -163,7 +163,7 @@ extern "C" int cp_cls_forward_backward(const cp_cls_tensors* p, const float* a7,
     CP_CHECK_LAUNCH();
     // Linear(512 -> 128) + ReLU with the BatchNorm statistics in the epilogue, BN, Linear(128 -> 41)
     CP_TRY((launch_nt<128, 128, 0, false>(a7, n, F_FC, F_FC, p->w1, CH, F_FC, p->b1, w.Y1, CH, w.pa, w.pb, 1, st)));
-    bn_finalize_kernel<<<dim3(CH / 32, bn_mode == CP_BN_RUNNING ? 1 : RP_SLABS), 1024, 0, st>>>(
+    bn_finalize_kernel<<<dim3(CH / 32, bn_mode == CP_BN_RUNNING ? 1 : rp_slabs(P)), 1024, 0, st>>>(
         w.pa, w.pb, P, CH, n, p->bn_w, p->bn_b, p->bn_rm, p->bn_rv, bn_mode, bn_momentum, bn_eps, w.mean, w.istd, w.scale,
         w.shift, w.rscratch, w.tickets);
     CP_CHECK_LAUNCH();
@@ -187,7 +187,7 @@ extern "C" int cp_cls_forward_backward(const cp_cls_tensors* p, const float* a7,
     const int Pb = (int)cp_cdiv(n, ColMap<CH>::ROWS);
     bn_bwd_reduce_kernel<CH><<<Pb, 256, 0, st>>>(w.G0, w.Y1, n, nullptr, 1.f, w.mean, w.istd, w.pa, w.pb);
     CP_CHECK_LAUNCH();
-    bn_bwd_finalize_kernel<<<dim3(CH / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, Pb, CH, n, w.m1, w.m2, gr->bn_w, gr->bn_b,
+    bn_bwd_finalize_kernel<<<dim3(CH / 32, rp_slabs(Pb)), 1024, 0, st>>>(w.pa, w.pb, Pb, CH, n, w.m1, w.m2, gr->bn_w, gr->bn_b,
                                                                      w.rscratch, w.tickets);
     CP_CHECK_LAUNCH();
     bn_bwd_apply_kernel<CH, false><<<Pb, 256, 0, st>>>(w.G0, w.Y1, n, nullptr, 1.f, w.mean, w.istd, p->bn_w, w.m1, w.m2,

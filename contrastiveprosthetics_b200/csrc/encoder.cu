@@ -232,7 +232,7 @@ int bn_finalize(const Ws& w, int l, int F, int P, int64_t R, const cp_encoder_te
                 const cp_encoder_opts* o, cudaStream_t st) {
     if (o->bn_mode != CP_BN_BATCH && (!p->bn_rm[l] || !p->bn_rv[l])) return CP_ERR_ARG;
     if (o->allreduce && o->bn_mode != CP_BN_RUNNING) {
-        bn_finalize_kernel<<<dim3(F / 32, RP_SLABS), 1024, 0, st>>>(
+        bn_finalize_kernel<<<dim3(F / 32, rp_slabs(P)), 1024, 0, st>>>(
             w.pa, w.pb, P, F, R, nullptr, nullptr, nullptr, nullptr, o->bn_mode, 0.f, 0.f, nullptr, nullptr, nullptr,
             nullptr, w.rscratch, w.tickets, w.totals);
         CP_CHECK_LAUNCH();
@@ -244,7 +244,7 @@ int bn_finalize(const Ws& w, int l, int F, int P, int64_t R, const cp_encoder_te
         CP_CHECK_LAUNCH();
         return CP_OK;
     }
-    bn_finalize_kernel<<<dim3(F / 32, o->bn_mode == CP_BN_RUNNING ? 1 : RP_SLABS), 1024, 0, st>>>(
+    bn_finalize_kernel<<<dim3(F / 32, o->bn_mode == CP_BN_RUNNING ? 1 : rp_slabs(P)), 1024, 0, st>>>(
         w.pa, w.pb, P, F, R, p->bn_w[l], p->bn_b[l], p->bn_rm[l], p->bn_rv[l], o->bn_mode, o->bn_momentum, o->bn_eps,
         w.mean[l], w.istd[l], w.scale[l], w.shift[l], w.rscratch, w.tickets, nullptr, w.abound + l);
     CP_CHECK_LAUNCH();
@@ -286,7 +286,7 @@ int bn_bwd_sums(const float* g, const float* y, bool planes, int64_t R, const Ws
                                                planes ? w.gmax + l : nullptr, run_flag);
     CP_CHECK_LAUNCH();
     const bool sync = o->allreduce != nullptr;
-    bn_bwd_finalize_kernel<<<dim3(F / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta,
+    bn_bwd_finalize_kernel<<<dim3(F / 32, rp_slabs(P)), 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta,
                                                                     w.rscratch, w.tickets, sync ? w.totals : nullptr,
                                                                     run_flag);
     CP_CHECK_LAUNCH();
@@ -390,7 +390,7 @@ int last_block_backward(const float* d_emb, float* gz, bool planes, int64_t n, c
     colsum_finalize_kernel<<<CP_EMB_DIM * F_FC / 32, 1024, 0, st>>>(w.ppart, G, CP_EMB_DIM * F_FC, gr->proj_w, 0);
     CP_CHECK_LAUNCH();
     const bool sync = o->allreduce != nullptr;
-    bn_bwd_finalize_kernel<<<dim3(F_FC / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, G, F_FC, n, w.m1, w.m2, gr->bn_w[S],
+    bn_bwd_finalize_kernel<<<dim3(F_FC / 32, rp_slabs(G)), 1024, 0, st>>>(w.pa, w.pb, G, F_FC, n, w.m1, w.m2, gr->bn_w[S],
                                                                        gr->bn_b[S], w.rscratch, w.tickets,
                                                                        sync ? w.totals : nullptr);
     CP_CHECK_LAUNCH();
@@ -820,7 +820,7 @@ extern "C" int cp_encoder_backward(const cp_encoder_tensors* p, const float* d_e
     float* c1part = w.ppart + (size_t)Pp * CP_EMB_DIM * 512;
     conv1_bn_bwd_reduce_kernel<<<P1, 256, 0, st>>>(w.G0, w.X0, n, p->conv1_w, p->conv1_b, w.mean[0], w.istd[0], w.pa, w.pb);
     CP_CHECK_LAUNCH();
-    bn_bwd_finalize_kernel<<<dim3(F_CONV / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P1, F_CONV, R12, w.m1, w.m2, gr->bn_w[0],
+    bn_bwd_finalize_kernel<<<dim3(F_CONV / 32, rp_slabs(P1)), 1024, 0, st>>>(w.pa, w.pb, P1, F_CONV, R12, w.m1, w.m2, gr->bn_w[0],
                                                                          gr->bn_b[0], w.rscratch, w.tickets,
                                                                          o->allreduce ? w.totals : nullptr);
     CP_CHECK_LAUNCH();

@@ -278,6 +278,9 @@ __device__ __forceinline__ double reduce_partials(const float* __restrict__ part
 // (atomic ticket) adds the RP_SLABS slab sums in a fixed order -> deterministic.  Returns true in the
 // threads (lane == 0, col < width) of that last CTA, with the totals in out[0..NQ).
 #define RP_SLABS 16
+// slabs (grid.y) for a list of P partial rows: one CTA per column group walks up to 64 rows by itself (32 lanes x 2) --
+// no scratch round trip, no ticket -- which is every finalize of a small batch (328 windows: 3 .. 31 partial rows)
+inline int rp_slabs(int P) { return P <= 64 ? 1 : RP_SLABS; }
 template <int NQ>
 __device__ __forceinline__ bool reduce_partials_2level(const float* const (&part)[NQ], int P, int width,
                                                        double* __restrict__ scratch, unsigned int* __restrict__ tickets,
@@ -286,7 +289,8 @@ __device__ __forceinline__ bool reduce_partials_2level(const float* const (&part
     const int cx = threadIdx.x % 32, lane = threadIdx.x / 32;
     const int col = blockIdx.x * 32 + cx;
     const int slab = blockIdx.y;
-    const int per = (P + RP_SLABS - 1) / RP_SLABS;
+    const int nslab = (int)gridDim.y;                      // RP_SLABS, or 1 for a short partial list (rp_slabs below)
+    const int per = (P + nslab - 1) / nslab;
     const int p0 = slab * per, p1 = min(P, p0 + per);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
@@ -305,7 +309,7 @@ __device__ __forceinline__ bool reduce_partials_2level(const float* const (&part
     __threadfence();
     if (threadIdx.x == 0) {
         const unsigned int t = atomicAdd(tickets + blockIdx.x, 1u);
-        is_last = (t == RP_SLABS - 1);
+        is_last = (t == (unsigned)nslab - 1u);
         if (is_last) tickets[blockIdx.x] = 0;          // re-arm for the next launch
     }
     __syncthreads();
@@ -315,7 +319,7 @@ __device__ __forceinline__ bool reduce_partials_2level(const float* const (&part
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         double t = 0.0;
-        for (int sl = 0; sl < RP_SLABS; ++sl) t += __ldcg(scratch + ((int64_t)sl * NQ + q) * width + col);
+        for (int sl = 0; sl < nslab; ++sl) t += __ldcg(scratch + ((int64_t)sl * NQ + q) * width + col);
         out[q] = t;
     }
     return true;
@@ -697,9 +701,10 @@ colsum_fold12_kernel(const float* __restrict__ part, int P, float* __restrict__ 
 // (bn_bwd_reduce_kernel / bn_bwd_finalize_kernel with run_flag) recomputes the stage's sums the long way.
 // Double accumulation in a fixed order (deterministic).  Outputs like bn_bwd_finalize_kernel.
 // With dropout between the stage and the layer only the first identity is lost (see sum_g_in below).
-#define WS_LANES 16                                   // row lanes per CTA (512 threads = 32 column slots x 16 lanes)
 template <int GROUP> struct WgradStats {
     static constexpr int COLS = GROUP == 1 ? 16 : 24;                  // columns of W per CTA (24 = 2 channels x 12 positions)
+    static constexpr int CX = GROUP == 1 ? 16 : 32;                    // column slots of the 512 threads ...
+    static constexpr int LANES = 512 / CX;                             // ... and row lanes (32 for the linear stages: every thread works)
 };
 template <int GROUP>
 __global__ void __launch_bounds__(512)
@@ -712,9 +717,10 @@ bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restr
                                double* __restrict__ cancel = nullptr /*[gridDim.x][2]: see stage_needs_exact*/,
                                unsigned int* __restrict__ cancel_ticket = nullptr /*zero on entry, re-armed*/) {
     constexpr int COLS = WgradStats<GROUP>::COLS;
+    constexpr int WS_LANES = WgradStats<GROUP>::LANES;
     __shared__ double s_a[WS_LANES][COLS], s_t[WS_LANES][COLS];
     __shared__ double s_E[COLS], s_D[COLS];
-    const int cx = threadIdx.x % 32, ky = threadIdx.x / 32;
+    const int cx = threadIdx.x % WgradStats<GROUP>::CX, ky = threadIdx.x / WgradStats<GROUP>::CX;
     const int col = blockIdx.x * COLS + cx;
     double a = 0.0, t = 0.0;
     if (cx < COLS && col < cols) {

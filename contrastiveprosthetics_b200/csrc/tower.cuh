@@ -98,7 +98,7 @@ bool glove_opts_ok(const cp_glove_opts* o) {
 
 int glove_bn_finalize(const GWs& w, int l, int P, int64_t R, const float* gamma, const float* beta,
                       const cp_glove_opts* o, cudaStream_t st) {
-    bn_finalize_kernel<<<dim3(GH / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P, GH, R, gamma, beta, nullptr, nullptr,
+    bn_finalize_kernel<<<dim3(GH / 32, rp_slabs(P)), 1024, 0, st>>>(w.pa, w.pb, P, GH, R, gamma, beta, nullptr, nullptr,
                                                                 CP_BN_BATCH, 0.f, o->bn_eps, w.mean[l], w.istd[l],
                                                                 w.scale[l], w.shift[l], w.rscratch, w.tickets);
     CP_CHECK_LAUNCH();
@@ -112,7 +112,7 @@ int glove_bn_backward(const float* g, const float* y, const float* post, float* 
     const int P = (int)cp_cdiv(R, ColMap<GH>::ROWS);
     bn_bwd_reduce_kernel<GH><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb, post);
     CP_CHECK_LAUNCH();
-    bn_bwd_finalize_kernel<<<dim3(GH / 32, RP_SLABS), 1024, 0, st>>>(w.pa, w.pb, P, GH, R, w.m1, w.m2, d_gamma, d_beta,
+    bn_bwd_finalize_kernel<<<dim3(GH / 32, rp_slabs(P)), 1024, 0, st>>>(w.pa, w.pb, P, GH, R, w.m1, w.m2, d_gamma, d_beta,
                                                                      w.rscratch, w.tickets);
     CP_CHECK_LAUNCH();
     bn_bwd_apply_kernel<GH, false><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], gamma, w.m1, w.m2,
