@@ -331,3 +331,25 @@ def test_gloo_clip_head_exchange(tmp_path):
                          env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_subjects_of_rows(emg):
+    """DB23.subjects_of (per-subject AdaBN, models.py:245): row id = class*D + k, k over (person, repetition, window) of
+    the split (load.py:233-251) -> the person's index on the 46-subject axis, in train and in the voted evaluation."""
+    ds = DB23(device="cpu", mixed=True)
+    ds.load_tensors(emg)
+    for setter, per_rep in ((ds.set_train, 100), (ds.set_test, 4)):
+        setter()
+        D, P, R = ds.D, ds.PEOPLE, ds.REPS
+        assert D == P * R * per_rep
+        rows = torch.tensor([0, per_rep * R - 1, per_rep * R, D - 1, D, 5 * D + 3 * per_rep * R + 7, 41 * D - 1])
+        k = rows % D
+        expect = ds.people_mask[k // (per_rep * R)]
+        assert torch.equal(ds.subjects_of(rows), expect)
+        # and against the data itself: the gathered row IS that person's window
+        sub = ds.EMG[ds.tasks_mask][:, ds.people_mask][:, :, ds.rep_mask][:, :, :, :100]
+        r = int(rows[5])
+        c, kk = r // D, r % D
+        p, rem = kk // (per_rep * R), kk % (per_rep * R)
+        assert int(ds.subjects_of(torch.tensor([r]))[0]) == int(ds.people_mask[p])
+        assert rem // per_rep < R and c == 5
