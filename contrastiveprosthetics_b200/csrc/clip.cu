@@ -270,6 +270,17 @@ __device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);
     lo = __float2half_rn((x - __half2float(hi)) * LO_SCALE);
 }
+// Similarity operands (unit vectors, the own rows pre-multiplied by s*log2e): the lo plane is NOT scaled -- |x| <= ~4, so
+// lo = x - hi is accurate to fp16's subnormal spacing, 6e-8 ABSOLUTE, which is what a dot product of 16 terms needs --
+// and the three products share ONE accumulator (no combine step per element).  The weights P of the gradient contraction
+// keep the scaled lo plane: they span many decades and are summed over the whole batch.
+__device__ __forceinline__ void split_pair_abs(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h2 = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
 // (a, b) -> packed hi pair, packed lo pair
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __half2 h2 = __floats2half2_rn(a, b);
@@ -306,10 +317,10 @@ __global__ void __launch_bounds__(THREADS, 2) clip_sweep_mma_kernel(const SweepA
         const float2 xb0 = row_b < g.n_own ? __ldg(reinterpret_cast<const float2*>(g.X + row_b * D + 2 * t)) : z;
         const float2 xa1 = row_a < g.n_own ? __ldg(reinterpret_cast<const float2*>(g.X + row_a * D + 2 * t + 8)) : z;
         const float2 xb1 = row_b < g.n_own ? __ldg(reinterpret_cast<const float2*>(g.X + row_b * D + 2 * t + 8)) : z;
-        split_pair(xa0.x, xa0.y, ah[0], al[0]);
-        split_pair(xb0.x, xb0.y, ah[1], al[1]);
-        split_pair(xa1.x, xa1.y, ah[2], al[2]);
-        split_pair(xb1.x, xb1.y, ah[3], al[3]);
+        split_pair_abs(xa0.x * g.a, xa0.y * g.a, ah[0], al[0]);       // pre-multiplied by s*log2(e): the MMAs return the
+        split_pair_abs(xb0.x * g.a, xb0.y * g.a, ah[1], al[1]);       // exponent's argument up to the constant -s*log2(e)
+        split_pair_abs(xa1.x * g.a, xa1.y * g.a, ah[2], al[2]);
+        split_pair_abs(xb1.x * g.a, xb1.y * g.a, ah[3], al[3]);
     }
     float inv_own[2] = {0.f, 0.f};
     if (GRAD) {
@@ -331,16 +342,19 @@ __global__ void __launch_bounds__(THREADS, 2) clip_sweep_mma_kernel(const SweepA
     };
     auto stash = [&](int buf, const float4 (&v)[2], float lsum) {
         const float e[2][4] = {{v[0].x, v[0].y, v[0].z, v[0].w}, {v[1].x, v[1].y, v[1].z, v[1].w}};
-        __half h[2][4], l[2][4];
+        __half h[2][4], l[2][4], la[2][4];
 #pragma unroll
         for (int q = 0; q < 2; ++q)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) split_h(e[q][c], h[q][c], l[q][c]);
+            for (int c = 0; c < 4; ++c) {
+                split_h(e[q][c], h[q][c], l[q][c]);
+                la[q][c] = __float2half_rn(e[q][c] - __half2float(h[q][c]));      // un-scaled lo (similarity operand)
+            }
         // pairs along k: word (kp, j) = (dim 2kp, dim 2kp+1) of column j
         *reinterpret_cast<uint4*>(&Kh[buf][kp][ljq]) =
             make_uint4(pack_h2(h[0][0], h[1][0]), pack_h2(h[0][1], h[1][1]), pack_h2(h[0][2], h[1][2]), pack_h2(h[0][3], h[1][3]));
         *reinterpret_cast<uint4*>(&Kl[buf][kp][ljq]) =
-            make_uint4(pack_h2(l[0][0], l[1][0]), pack_h2(l[0][1], l[1][1]), pack_h2(l[0][2], l[1][2]), pack_h2(l[0][3], l[1][3]));
+            make_uint4(pack_h2(la[0][0], la[1][0]), pack_h2(la[0][1], la[1][1]), pack_h2(la[0][2], la[1][2]), pack_h2(la[0][3], la[1][3]));
         if (GRAD) {
             // pairs along j: word (d, jp) = columns (2jp, 2jp+1) of dim d
 #pragma unroll
@@ -394,20 +408,17 @@ __global__ void __launch_bounds__(THREADS, 2) clip_sweep_mma_kernel(const SweepA
                 const int n0 = np * 16 + h * 8;
                 const uint32_t bh0 = Kh[buf][t][n0 + gq], bh1 = Kh[buf][t + 4][n0 + gq];
                 const uint32_t bl0 = Kl[buf][t][n0 + gq], bl1 = Kl[buf][t + 4][n0 + gq];
-                float cm[4] = {0.f, 0.f, 0.f, 0.f}, cc[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_f16(cc, al, bh0, bh1);
-                mma_f16(cc, ah, bl0, bl1);
-                mma_f16(cm, ah, bh0, bh1);
+                float sv[4] = {-g.a, -g.a, -g.a, -g.a};                 // accumulator starts at -s*log2(e): sv = a * (x.y - 1)
+                mma_f16(sv, al, bh0, bh1);
+                mma_f16(sv, ah, bl0, bl1);
+                mma_f16(sv, ah, bh0, bh1);
                 // c0: (row_a, col 2t), c1: (row_a, 2t+1), c2: (row_b, 2t), c3: (row_b, 2t+1)
                 const int64_t ja = j0 + n0 + 2 * t;
                 const bool ok0 = FULL || ja < g.n_loop, ok1 = FULL || ja + 1 < g.n_loop;
-                float sv[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) sv[e] = fmaf(cc[e], LO_INV, cm[e]);
-                ev[h][0] = ok0 ? ex2(fmaf(sv[0], g.a, -g.a)) : 0.f;
-                ev[h][1] = ok1 ? ex2(fmaf(sv[1], g.a, -g.a)) : 0.f;
-                ev[h][2] = ok0 ? ex2(fmaf(sv[2], g.a, -g.a)) : 0.f;
-                ev[h][3] = ok1 ? ex2(fmaf(sv[3], g.a, -g.a)) : 0.f;
+                ev[h][0] = ok0 ? ex2(sv[0]) : 0.f;
+                ev[h][1] = ok1 ? ex2(sv[1]) : 0.f;
+                ev[h][2] = ok0 ? ex2(sv[2]) : 0.f;
+                ev[h][3] = ok1 ? ex2(sv[3]) : 0.f;
                 if (!GRAD) {
                     tacc[0] += ev[h][0] + ev[h][1];
                     tacc[1] += ev[h][2] + ev[h][3];
