@@ -177,9 +177,39 @@ head_kernel(const float* __restrict__ emb, int64_t G, int W, const float* __rest
     }
 }
 
-// one CTA: reduce per-CTA partials (double), finish the loss and the class-table gradient
+// Per-CTA partials -> HEAD_SLICES slice sums (double), one CTA per slice; then one CTA finishes the loss and the
+// class-table gradient from the slices.  (A single CTA walking every partial -- 2.6 KB apart -- took 36 us at 592
+// partials and grew with the grid, which capped head_kernel at 8 warps per SM.)
+#define HEAD_SLICES 32
+struct HeadSlice {
+    double dC[T * D];
+    double loss;
+};
 __global__ void __launch_bounds__(704)
-head_finalize_kernel(const HeadPartial* __restrict__ partial, int n_part, int64_t G,
+head_slice_kernel(const HeadPartial* __restrict__ partial, int n_part, HeadSlice* __restrict__ slices) {
+    const int per = (n_part + HEAD_SLICES - 1) / HEAD_SLICES;
+    const int p0 = blockIdx.x * per, p1 = min(n_part, p0 + per);
+    const int tid = threadIdx.x;
+    if (tid < T * D) {
+        // 4 independent chains in a fixed order (deterministic)
+        double a[4] = {0, 0, 0, 0};
+        int p = p0;
+        for (; p + 4 <= p1; p += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] += (double)partial[p + u].dC[tid];
+        }
+        for (; p < p1; ++p) a[0] += (double)partial[p].dC[tid];
+        slices[blockIdx.x].dC[tid] = (a[0] + a[1]) + (a[2] + a[3]);
+    }
+    if (tid == T * D) {
+        double s = 0.0;
+        for (int p = p0; p < p1; ++p) s += partial[p].loss;
+        slices[blockIdx.x].loss = s;
+    }
+}
+
+__global__ void __launch_bounds__(704)
+head_finalize_kernel(const HeadSlice* __restrict__ slices, int64_t G,
                      const float* __restrict__ table_w, const float* __restrict__ table_b,
                      float* __restrict__ loss, float* __restrict__ d_table_w,
                      float* __restrict__ d_table_b) {
@@ -187,19 +217,13 @@ head_finalize_kernel(const HeadPartial* __restrict__ partial, int n_part, int64_
     __shared__ float dc[T][D];        // gradient w.r.t. the raw table rows
     const int tid = threadIdx.x;
     if (tid < T * D) {
-        // 8 independent chains (fixed order -> deterministic): the loads of a chain are 2.6 KB apart and latency-bound
-        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        int p = 0;
-        for (; p + 8 <= n_part; p += 8) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] += (double)partial[p + u].dC[tid];
-        }
-        for (; p < n_part; ++p) a[0] += (double)partial[p].dC[tid];
-        dCh[tid / D][tid % D] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+        double a = 0.0;
+        for (int p = 0; p < HEAD_SLICES; ++p) a += slices[p].dC[tid];
+        dCh[tid / D][tid % D] = a;
     }
     if (tid == T * D && loss) {
         double s = 0.0;
-        for (int p = 0; p < n_part; ++p) s += partial[p].loss;
+        for (int p = 0; p < HEAD_SLICES; ++p) s += slices[p].loss;
         *loss = (float)(s / (2.0 * (double)G * (double)T));
     }
     __syncthreads();
@@ -229,13 +253,14 @@ head_finalize_kernel(const HeadPartial* __restrict__ partial, int n_part, int64_
 }
 
 static int head_blocks(int64_t G) {
-    const int64_t cap = (int64_t)CP_NUM_SMS * 4;       // 64-thread CTAs; the finalize CTA walks this many partials
-                                                        // (x8: head 128 -> 106 us but finalize 44 -> 65 us: no gain)
+    const int64_t cap = (int64_t)CP_NUM_SMS * 16;      // 64-thread CTAs: up to 32 warps per SM (the partials are reduced
+                                                        // by HEAD_SLICES CTAs, so the grid no longer costs the finalize)
     return (int)(G < cap ? G : cap);
 }
+static size_t head_partial_bytes(int64_t G) { return cp_align(sizeof(HeadPartial) * (size_t)head_blocks(G < 1 ? 1 : G)); }
 
 extern "C" size_t cp_head_workspace_bytes(int64_t n_groups) {
-    return cp_align(sizeof(HeadPartial) * (size_t)head_blocks(n_groups < 1 ? 1 : n_groups));
+    return head_partial_bytes(n_groups) + cp_align(sizeof(HeadSlice) * HEAD_SLICES);
 }
 
 extern "C" int cp_head_forward_backward(const float* emb, int64_t B, int W, const float* table_w,
@@ -253,7 +278,10 @@ extern "C" int cp_head_forward_backward(const float* emb, int64_t B, int W, cons
     head_kernel<false><<<nb, HEAD_THREADS, 0, st>>>(emb, G, W, table_w, table_b, nullptr, d_emb, nullptr,
                                                     pred, n_correct, logits, part, need_grad);
     CP_CHECK_LAUNCH();
-    head_finalize_kernel<<<1, 704, 0, st>>>(part, nb, G, table_w, table_b, loss, d_table_w, d_table_b);
+    HeadSlice* slices = reinterpret_cast<HeadSlice*>(reinterpret_cast<char*>(workspace) + head_partial_bytes(G));
+    head_slice_kernel<<<HEAD_SLICES, 704, 0, st>>>(part, nb, slices);
+    CP_CHECK_LAUNCH();
+    head_finalize_kernel<<<1, 704, 0, st>>>(slices, G, table_w, table_b, loss, d_table_w, d_table_b);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
@@ -269,7 +297,10 @@ extern "C" int cp_logits_loss(const float* logits, int64_t G, float* loss, float
     head_kernel<true><<<nb, HEAD_THREADS, 0, st>>>(nullptr, G, 1, nullptr, nullptr, logits, nullptr, d_logits,
                                                    pred, n_correct, nullptr, part, d_logits ? 1 : 0);
     CP_CHECK_LAUNCH();
-    head_finalize_kernel<<<1, 704, 0, st>>>(part, nb, G, nullptr, nullptr, loss, nullptr, nullptr);
+    HeadSlice* slices = reinterpret_cast<HeadSlice*>(reinterpret_cast<char*>(workspace) + head_partial_bytes(G));
+    head_slice_kernel<<<HEAD_SLICES, 704, 0, st>>>(part, nb, slices);
+    CP_CHECK_LAUNCH();
+    head_finalize_kernel<<<1, 704, 0, st>>>(slices, G, nullptr, nullptr, loss, nullptr, nullptr);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }

@@ -52,7 +52,7 @@ def report(tag, prof):
     agg = collections.defaultdict(lambda: [0, 0.0])
     for s, e, n in iv:
         agg[n[:60]][0] += 1; agg[n[:60]][1] += e - s
-    for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
+    for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
         print(f"   {t/1e3:7.3f} ms n={c:3d} {n}")
 
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
