@@ -464,40 +464,26 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
 
     CP_CUDA(cudaMemsetAsync(w.tickets, 0, WS_ZERO_WORDS * sizeof(unsigned int), st));
     const bool fold = fold_bn_active(o, n);
-    // Tensor-core engine: the weight preparation (norms, plane splits: ~65 us of small launches) does not depend on the
-    // batch, the conv1 stage does not depend on it -- it runs on the device's side stream (event fork / join, capturable)
-    // next to the conv1 kernels and is joined before the first GEMM.
-    SideStream* side = tcE ? side_of_current_device() : nullptr;
-    if (tcE && !side) return CP_ERR_UNSUPPORTED;
-    std::unique_lock<std::mutex> side_guard;
-    cudaStream_t wst = st;                       // stream of the weight preparation
-    if (side) {
-        side_guard = std::unique_lock<std::mutex>(side->lock);
-        CP_TRY(side->init());
-        wst = side->stream;
-        CP_CUDA(cudaEventRecord(side->ready[0], st));             // after the memset of the norm slots
-        CP_CUDA(cudaStreamWaitEvent(wst, side->ready[0], 0));
-    }
     if (fold) {
         RowL1Args ra;
         for (int l = 0; l < CP_N_FC; ++l) { ra.W[l] = p->fc_w[l]; ra.b[l] = p->fc_b[l]; ra.K[l] = l == 0 ? K_FC1 : F_FC; }
-        weights_row_l1_kernel<<<dim3(F_FC / 8, CP_N_FC), 256, 0, wst>>>(ra, w.rowl1, w.bmax);
+        weights_row_l1_kernel<<<dim3(F_FC / 8, CP_N_FC), 256, 0, st>>>(ra, w.rowl1, w.bmax);
         CP_CHECK_LAUNCH();
     }
     if (tcE) {
         WmaxArgs wa;
         for (int l = 0; l < CP_N_FC; ++l) { wa.W[l] = p->fc_w[l]; wa.n[l] = F_FC * (l == 0 ? K_FC1 : F_FC); }
         wa.W[7] = p->conv2_w; wa.n[7] = 64 * 64 * 9;
-        weights_absmax_kernel<<<dim3(48, 8), 256, 0, wst>>>(wa, w.wmax);
+        weights_absmax_kernel<<<dim3(48, 8), 256, 0, st>>>(wa, w.wmax);
         CP_CHECK_LAUNCH();
         if (o->save_for_backward) {
-            weights_col_l1_kernel<<<dim3(K_FC1 / 256, CP_N_FC), 256, 0, wst>>>(wa, w.l1max);
+            weights_col_l1_kernel<<<dim3(K_FC1 / 256, CP_N_FC), 256, 0, st>>>(wa, w.l1max);
             CP_CHECK_LAUNCH();
         }
     }
-    prep_weights_kernel<<<(F_FC * K_FC1 + 255) / 256, 256, 0, wst>>>(p->conv2_w, p->fc_w[0], w.Wc2, w.Wc2d, w.W1p,
-                                                                     w.Wc2_lo, w.Wc2d_lo, p->conv1_w, p->conv1_b, w.c1w, w.c1b,
-                                                                     w.wmax, w.wscale_inv);
+    prep_weights_kernel<<<(F_FC * K_FC1 + 255) / 256, 256, 0, st>>>(p->conv2_w, p->fc_w[0], w.Wc2, w.Wc2d, w.W1p,
+                                                                    w.Wc2_lo, w.Wc2d_lo, p->conv1_w, p->conv1_b, w.c1w, w.c1b,
+                                                                    w.wmax, w.wscale_inv);
     CP_CHECK_LAUNCH();
     if (tcE) {
         PrepTcArgs a;
@@ -506,10 +492,9 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
             a.W[l] = p->fc_w[l];
             a.Wh[l] = w.Wh[l]; a.Wl[l] = w.Wl[l]; a.Wth[l] = w.Wth[l]; a.Wtl[l] = w.Wtl[l];
         }
-        prep_weights_tc_kernel<<<dim3(K_FC1 / 32, F_FC / 32, CP_N_FC), 256, 0, wst>>>(a);
+        prep_weights_tc_kernel<<<dim3(K_FC1 / 32, F_FC / 32, CP_N_FC), 256, 0, st>>>(a);
         CP_CHECK_LAUNCH();
     }
-    if (side) CP_CUDA(cudaEventRecord(side->done[0], wst));
     CP_CUDA(cudaMemcpyAsync(w.X0, x, sizeof(float) * R12, cudaMemcpyDeviceToDevice, st));
 
     // conv1 -> ReLU -> BN: a statistics pass and an apply pass, both recomputing the activation from x
@@ -527,7 +512,6 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
     CP_CHECK_LAUNCH();
 
     // conv2 as implicit GEMM [n*12, 192] x [64, 192]^T
-    if (side) CP_CUDA(cudaStreamWaitEvent(st, side->done[0], 0));        // weight planes / scales are ready
     if (tcE) {
         CP_TRY(tcg::launch_conv_nt(hi_of(w.A1), lo_of(w.A1, conv_elems), n, hi_of(w.Wc2), hi_of(w.Wc2_lo), p->conv2_b,
                                    w.Y2, w.pa, w.pb, 1, st, w.ascale_inv + 0, fast, w.wscale_inv + 7));
