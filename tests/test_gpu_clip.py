@@ -11,7 +11,7 @@ from gpu_util import rel_err
 pytestmark = pytest.mark.gpu
 
 LOSS_TOL = 1e-5
-GRAD_TOL = 2e-5
+GRAD_TOL = 1e-5
 
 
 def _run(n, logit_scale, seed=0):

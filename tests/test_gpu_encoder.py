@@ -25,7 +25,7 @@ FWD_TOL = 1e-5
 # ~1/sqrt(#elements) of its norm (measured: 2.4e-3 at 328 windows; the fp32 ORACLE itself is 1e-3
 # away from the fp64 oracle).  So the tight test injects the kernel's ReLU pattern into the oracle
 # (oracle.model._relu) and the un-conditioned test only bounds the flip noise.
-GRAD_TOL = 2e-5
+GRAD_TOL = 1e-5        # north_star's tolerance; measured worst case at these sizes 3.6e-6 ... 4.6e-6 (profiles/parity_r2.json)
 GRAD_TOL_UNCONDITIONED = 2e-2
 
 
