@@ -48,7 +48,7 @@ def test_glove_tower_forward_backward(glove_dim, n):
     # gradients: tight when no ReLU input of the fp64 evaluation is within fp32 noise of its kink (both sides
     # then take the same branches); otherwise only the kink-noise bound holds (DESIGN.md "ReLU kinks")
     margin = min(float(t.abs().min()) for t in taps)
-    tol = 3e-5 if margin > 2e-5 else 2e-2
+    tol = 1e-5 if margin > 2e-5 else 2e-2
     for k, p in tower.named_parameters():
         assert rel_err(p.grad, sdr["glove_net." + k].grad) < tol, (k, margin)
 
