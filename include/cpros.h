@@ -179,7 +179,9 @@ int cp_logits_loss(const float *logits, int64_t G, float *loss, float *d_logits,
  * from the per-group 41 x 41 bmm to one B x B similarity matrix with the CLIP loss the reference is
  * modelled after (models.py:65): S = scale * Ehat Ghat^T, scale = exp(logit_scale) (models.py:81,129),
  *   loss = 1/(2B) sum_i [LSE_j S_ij - S_ii] + 1/(2B) sum_j [LSE_i S_ij - S_jj].
- * The B x B matrix is never materialised.  The entry points are the pieces between which a
+ * The B x B matrix is never materialised.  cp_clip_sums / cp_clip_grad run both contractions on the warp-level
+ * tensor cores (mma.sync m16n8k16, fp16 operands with a 3-product hi/lo split, fp32 accumulate) when the loop
+ * operand has more than 128 rows, and as fp32 FMAs below that.  The entry points are the pieces between which a
  * multi-GPU caller places its collectives (all-gather of Ghat, all-reduce of the column sums,
  * reduce-scatter of d Ghat); on one GPU they are simply called in sequence:
  *   cp_clip_normalize   xhat = x/||x|| (no epsilon, models.py:123,125), inv_norm = 1/||x||
