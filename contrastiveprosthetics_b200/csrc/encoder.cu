@@ -282,10 +282,18 @@ int bn_bwd_sums(const float* g, const float* y, bool planes, int64_t R, const Ws
                 bool stats_ready) {
     const int P = (int)cp_cdiv(R, ColMap<F>::ROWS);
     const unsigned int* run_flag = stats_ready ? w.gmax + 16 + l : nullptr;
+    const bool sync = o->allreduce != nullptr;
+    if (stats_ready && !sync) {
+        // the sums were derived from the next layer's dW: reduce + finalize as ONE conditional launch (normally empty)
+        bn_bwd_reduce_finalize_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb,
+                                                            planes ? w.gmax + l : nullptr, run_flag, w.m1, w.m2, d_gamma,
+                                                            d_beta, w.tickets + 48 + l);
+        CP_CHECK_LAUNCH();
+        return CP_OK;
+    }
     bn_bwd_reduce_kernel<F><<<P, 256, 0, st>>>(g, y, R, keep, inv_keep, w.mean[l], w.istd[l], w.pa, w.pb, nullptr,
                                                planes ? w.gmax + l : nullptr, run_flag);
     CP_CHECK_LAUNCH();
-    const bool sync = o->allreduce != nullptr;
     bn_bwd_finalize_kernel<<<dim3(F / 32, rp_slabs(P)), 1024, 0, st>>>(w.pa, w.pb, P, F, R, w.m1, w.m2, d_gamma, d_beta,
                                                                     w.rscratch, w.tickets, sync ? w.totals : nullptr,
                                                                     run_flag);

@@ -485,15 +485,12 @@ bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, float* __res
 __device__ __forceinline__ bool stage_needs_exact(const unsigned int* __restrict__ flag) { return __ldg(flag) != 0u; }
 
 template <int F>
-__global__ void __launch_bounds__(256)
-bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t R,
-                     const uint8_t* __restrict__ keep, float inv_keep, const float* __restrict__ mean,
-                     const float* __restrict__ istd, float* __restrict__ p1, float* __restrict__ p2,
-                     const float* __restrict__ post = nullptr, unsigned int* __restrict__ gmax_bits = nullptr,
-                     const unsigned int* __restrict__ run_flag = nullptr) {
-    __shared__ float red[ColMap<F>::RY * F];
-    // fallback pass of the reduce-free BN backward: runs only when bn_bwd_stats_from_wgrad_kernel asked for it
-    if (run_flag && !stage_needs_exact(run_flag)) return;
+__device__ __forceinline__ void bn_bwd_reduce_body(const float* __restrict__ g, const float* __restrict__ y, int64_t R,
+                                                   const uint8_t* __restrict__ keep, float inv_keep,
+                                                   const float* __restrict__ mean, const float* __restrict__ istd,
+                                                   float* __restrict__ p1, float* __restrict__ p2,
+                                                   const float* __restrict__ post, unsigned int* __restrict__ gmax_bits,
+                                                   float* red) {
     float gmax = 0.f;                     // max |g'| (feeds the fp16 plane scale of bn_bwd_apply_kernel<.., true>)
     const int qx = threadIdx.x % ColMap<F>::QX, ry = threadIdx.x / ColMap<F>::QX;
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + qx * 4));
@@ -533,6 +530,57 @@ bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, i
         gmax = warp_max(gmax);
         // non-negative floats order like their bit patterns; NaN / Inf gradients are the caller's problem
         if (threadIdx.x % 32 == 0 && gmax > 0.f) atomicMax(gmax_bits, __float_as_uint(gmax));
+    }
+}
+
+template <int F>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t R,
+                     const uint8_t* __restrict__ keep, float inv_keep, const float* __restrict__ mean,
+                     const float* __restrict__ istd, float* __restrict__ p1, float* __restrict__ p2,
+                     const float* __restrict__ post = nullptr, unsigned int* __restrict__ gmax_bits = nullptr,
+                     const unsigned int* __restrict__ run_flag = nullptr) {
+    __shared__ float red[ColMap<F>::RY * F];
+    // fallback pass of the reduce-free BN backward: runs only when bn_bwd_stats_from_wgrad_kernel asked for it
+    if (run_flag && !stage_needs_exact(run_flag)) return;
+    bn_bwd_reduce_body<F>(g, y, R, keep, inv_keep, mean, istd, p1, p2, post, gmax_bits, red);
+}
+
+// The conditional (normally empty) fallback of the reduce-free BN backward as ONE launch: the reduce pass, then the last
+// CTA to finish (ticket, re-armed) adds the P partial rows in index order, in double, and writes what
+// bn_bwd_finalize_kernel writes.  One CTA walking every partial row is slow (~0.1 ms at 1,312 rows) -- it runs only when
+// a stage's derivation from dW was rejected -- and it saves a graph node per stage in the common case.
+template <int F>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_finalize_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t R,
+                              const uint8_t* __restrict__ keep, float inv_keep, const float* __restrict__ mean,
+                              const float* __restrict__ istd, float* __restrict__ p1, float* __restrict__ p2,
+                              unsigned int* __restrict__ gmax_bits, const unsigned int* __restrict__ run_flag,
+                              float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ d_gamma,
+                              float* __restrict__ d_beta, unsigned int* __restrict__ ticket) {
+    __shared__ float red[ColMap<F>::RY * F];
+    __shared__ bool last;
+    if (!stage_needs_exact(run_flag)) return;
+    bn_bwd_reduce_body<F>(g, y, R, keep, inv_keep, mean, istd, p1, p2, nullptr, gmax_bits, red);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        if (last) *ticket = 0;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int col = threadIdx.x; col < F; col += 256) {
+        double a = 0.0, b = 0.0;
+        for (unsigned int p = 0; p < gridDim.x; ++p) {
+            a += (double)__ldcg(p1 + (int64_t)p * F + col);
+            b += (double)__ldcg(p2 + (int64_t)p * F + col);
+        }
+        if (d_beta) d_beta[col] = (float)a;
+        if (d_gamma) d_gamma[col] = (float)b;
+        m1[col] = (float)(a / (double)R);
+        m2[col] = (float)(b / (double)R);
     }
 }
 
