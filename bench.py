@@ -381,12 +381,36 @@ def run_cuda(args):
         ms_g, clocks_g, _ = timed(graph_resident, args.steps, args.warmup)
         ms_g_e2e, _, _ = timed(graph_e2e, max(3, args.steps // 2), 2)
         modes["cuda_graph"] = {"ms_per_step": ms_g, "e2e_ms_per_step": ms_g_e2e}
+        graph_best = ("cuda_graph", ms_g, clocks_g, ms_g_e2e)
+        del gstep, model_g, opts_g, sync_g
+        # ---- the same step WITHOUT autograd / torch.optim inside the graph (step.LeanTrainStep: one prologue launch,
+        #      one Adam launch for both optimizers, the gradient bucket all-reduced in place): ~35 fewer nodes per step
+        torch.manual_seed(42)
+        model_g = Model(dict(PARAMS), adabn=True, device=str(dev))
+        model_g.emg_net.engine = model.emg_net.engine
+        model_g.emg_net.sync_bn = args.sync_bn
+        model_g.set_train()
+        opts_g = [torch.optim.Adam(model_g.emg_net.parameters(), lr=PARAMS['lr_emg'], weight_decay=0),
+                  torch.optim.Adam(model_g.glove_net.parameters(), lr=PARAMS['lr_glove'], weight_decay=0)]
+        sync_g = True if world > 1 else None
+        gstep = GraphedTrainStep(model_g, opts_g, tw.get_batch(items_ring[0])[0], sync_grads=sync_g, lean=True)
+        ms_l, clocks_l, _ = timed(graph_resident, args.steps, args.warmup)
+        ms_l_e2e, _, _ = timed(graph_e2e, max(3, args.steps // 2), 2)
+        modes["cuda_graph_lean"] = {"ms_per_step": ms_l, "e2e_ms_per_step": ms_l_e2e}
+        if ms_l < ms_g:
+            graph_best = ("cuda_graph_lean", ms_l, clocks_l, graph_best[3])
+        if ms_l_e2e < ms_g_e2e:
+            graph_best = graph_best[:3] + (ms_l_e2e,)
+            e2e_graph_name = "cuda_graph_lean"
+        else:
+            e2e_graph_name = "cuda_graph"
+        gname, ms_g, clocks_g, ms_g_e2e = graph_best
         # every rank must take the same branch: the timings are already the max over ranks
         if ms_g < ms:
-            step_mode, ms, clocks = "cuda_graph", ms_g, clocks_g
+            step_mode, ms, clocks = gname, ms_g, clocks_g
             value = N * world / (ms / 1e3)
         if ms_g_e2e < ms_e2e:
-            e2e_mode, ms_e2e = "cuda_graph", ms_g_e2e
+            e2e_mode, ms_e2e = e2e_graph_name, ms_g_e2e
         del gstep, model_g, opts_g, sync_g
     e2e_value = N * world / (ms_e2e / 1e3)
 
@@ -502,10 +526,16 @@ def run_cuda(args):
                        "engine": {0: "simt-fp32", 1: "tcgen05-3xfp16-split", 2: "tcgen05-1xfp16 (reduced precision, 1e-2 path)"}[model.emg_net.engine],
                        "step_mode": step_mode + (" (one graph launch per step, torch.optim.Adam(fused=True); gpu_launches "
                                                  "counts the kernels of the eager step, the graph replays the same ones "
-                                                 "of this library)" if step_mode == "cuda_graph" else ""),
+                                                 "of this library)" if step_mode == "cuda_graph" else
+                                                 " (one graph launch per step; the step runs without autograd / torch.optim: "
+                                                 "cp_step_prologue + the fused kernels + cp_adam_step, gradients in one flat "
+                                                 "bucket; gpu_launches counts the kernels of the eager autograd step)"
+                                                 if step_mode == "cuda_graph_lean" else ""),
                        "parallelism": f"dp{world} (sample-sharded, " + ("SyncBN" if args.sync_bn and world > 1 else "local BatchNorm")
                                       + ", one flat grad all-reduce)",
-                       "optimizer": "2 x torch.optim.Adam(fused=True) (train.py:72-73 wiring)",
+                       "optimizer": ("both Adams of train.py:72-73 in ONE cp_adam_step launch (torch.optim.Adam's update rule)"
+                                     if step_mode == "cuda_graph_lean" else
+                                     "2 x torch.optim.Adam(fused=True) (train.py:72-73 wiring)"),
                        "l2_policy": "per-step working set ~8 GB of activations >> 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(h2d),

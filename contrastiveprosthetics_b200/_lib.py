@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 # CP_LIBCPROS: another build of the same sources (A/B measurements of kernel variants); default: the in-tree library
 SO_PATH = os.environ.get("CP_LIBCPROS") or os.path.join(_PKG, "libcpros.so")
-SOURCES = ["version.cu", "gather.cu", "encoder.cu", "head.cu", "clip.cu", "vote.cu", "l2.cu", "preprocess.cu", "philox.cu"]
+SOURCES = ["version.cu", "gather.cu", "encoder.cu", "head.cu", "clip.cu", "vote.cu", "l2.cu", "step.cu", "preprocess.cu", "philox.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -152,6 +152,11 @@ def lib():
     L.cp_l2_workspace_bytes.argtypes = [_i32]
     L.cp_l2_forward.argtypes = [_vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]
     L.cp_l2_backward.argtypes = [_vp, _vp, _i32, _vp, _vp, ctypes.c_float, _vp, _vp]
+    _d = ctypes.c_double
+    L.cp_step_workspace_bytes.restype = _sz
+    L.cp_step_workspace_bytes.argtypes = [_i32]
+    L.cp_step_prologue.argtypes = [_vp, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp]
+    L.cp_adam_step.argtypes = [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _vp]
     L.cp_emg_preprocess_scratch_elems.restype = _sz
     L.cp_emg_preprocess_scratch_elems.argtypes = [_i64, _i32, _i32]
     L.cp_emg_preprocess.argtypes = [_vp, _i64, _i32, _i32, _vp, _vp, _i32, ctypes.c_float, _i32, _i32, _vp, _i32, _vp,
@@ -160,7 +165,8 @@ def lib():
                  "cp_linear_backward", "cp_head_forward_backward", "cp_logits_loss", "cp_vote_eval",
                  "cp_rank_rows", "cp_subset_eval", "cp_clip_normalize", "cp_clip_transpose", "cp_clip_sums",
                  "cp_clip_loss", "cp_clip_grad", "cp_clip_embed_backward", "cp_glove_forward", "cp_glove_backward",
-                 "cp_confusion_matrix", "cp_l2_forward", "cp_l2_backward", "cp_emg_preprocess"):
+                 "cp_confusion_matrix", "cp_l2_forward", "cp_l2_backward", "cp_emg_preprocess", "cp_step_prologue",
+                 "cp_adam_step"):
         getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L
@@ -174,7 +180,7 @@ EXPORTS = ["cp_version", "cp_launch_count", "cp_status_string", "cp_gather_norm"
            "cp_clip_grad", "cp_clip_embed_backward", "cp_glove_workspace_bytes", "cp_glove_forward",
            "cp_glove_backward", "cp_confusion_matrix", "cp_l2_workspace_bytes", "cp_l2_forward", "cp_l2_backward",
            "cp_emg_preprocess_scratch_elems", "cp_emg_preprocess", "cp_philox4x32_10", "cp_dropout_mask", "cp_cls_workspace_bytes",
-           "cp_cls_forward_backward"]
+           "cp_cls_forward_backward", "cp_step_workspace_bytes", "cp_step_prologue", "cp_adam_step"]
 
 
 def check(status, what=""):

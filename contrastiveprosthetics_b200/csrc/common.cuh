@@ -66,6 +66,30 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// sum of w[i]^2 over [lo, hi) by one 256-thread CTA, in double: four independent chains per thread (the loads of a
+// trip are in flight together), combined in a fixed order -> deterministic.  Result valid in thread 0.  Shared by
+// cp_l2_forward and cp_step_prologue, which must produce the same norms bit for bit.
+__device__ __forceinline__ double cta_sum_squares_256(const float* __restrict__ w, int64_t lo, int64_t hi,
+                                                     double* red /*[8] shared*/) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int64_t i = lo + threadIdx.x;
+    for (; i + 768 < hi; i += 1024) {
+        const double a = (double)__ldg(w + i), b = (double)__ldg(w + i + 256), c = (double)__ldg(w + i + 512),
+                     d = (double)__ldg(w + i + 768);
+        s0 += a * a; s1 += b * b; s2 += c * c; s3 += d * d;
+    }
+    for (; i < hi; i += 256) {
+        const double a = (double)__ldg(w + i);
+        s0 += a * a;
+    }
+    double s = warp_sum((s0 + s1) + (s2 + s3));
+    if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = s;
+    __syncthreads();
+    double tot = 0.0;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < 8; ++k) tot += red[k];
+    return tot;
+}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -472,20 +472,20 @@ extern "C" int cp_encoder_forward(const cp_encoder_tensors* p, const float* x, i
 
     CP_CUDA(cudaMemsetAsync(w.tickets, 0, WS_ZERO_WORDS * sizeof(unsigned int), st));
     const bool fold = fold_bn_active(o, n);
-    if (fold) {
-        RowL1Args ra;
-        for (int l = 0; l < CP_N_FC; ++l) { ra.W[l] = p->fc_w[l]; ra.b[l] = p->fc_b[l]; ra.K[l] = l == 0 ? K_FC1 : F_FC; }
-        weights_row_l1_kernel<<<dim3(F_FC / 8, CP_N_FC), 256, 0, st>>>(ra, w.rowl1, w.bmax);
-        CP_CHECK_LAUNCH();
-    }
-    if (tcE) {
-        WmaxArgs wa;
-        for (int l = 0; l < CP_N_FC; ++l) { wa.W[l] = p->fc_w[l]; wa.n[l] = F_FC * (l == 0 ? K_FC1 : F_FC); }
-        wa.W[7] = p->conv2_w; wa.n[7] = 64 * 64 * 9;
-        weights_absmax_kernel<<<dim3(48, 8), 256, 0, st>>>(wa, w.wmax);
-        CP_CHECK_LAUNCH();
-        if (o->save_for_backward) {
-            weights_col_l1_kernel<<<dim3(K_FC1 / 256, CP_N_FC), 256, 0, st>>>(wa, w.l1max);
+    {
+        WBoundsArgs ba;
+        ba.rowl1 = w.rowl1; ba.bmax = w.bmax; ba.wmax = w.wmax; ba.l1max = w.l1max;
+        for (int l = 0; l < CP_N_FC; ++l) {
+            ba.ra.W[l] = p->fc_w[l]; ba.ra.b[l] = p->fc_b[l]; ba.ra.K[l] = l == 0 ? K_FC1 : F_FC;
+            ba.wa.W[l] = p->fc_w[l]; ba.wa.n[l] = F_FC * (l == 0 ? K_FC1 : F_FC);
+        }
+        ba.wa.W[7] = p->conv2_w; ba.wa.n[7] = 64 * 64 * 9;
+        static_assert(F_FC / 8 == 64 && K_FC1 / 256 == 3, "weights_bounds_kernel's block layout");
+        ba.n_row = fold ? 64 * CP_N_FC : 0;
+        ba.n_abs = tcE ? 48 * 8 : 0;
+        ba.n_col = tcE && o->save_for_backward ? 3 * CP_N_FC : 0;
+        if (ba.n_row + ba.n_abs + ba.n_col > 0) {
+            weights_bounds_kernel<<<ba.n_row + ba.n_abs + ba.n_col, 256, 0, st>>>(ba);
             CP_CHECK_LAUNCH();
         }
     }

@@ -1027,11 +1027,10 @@ proj_bwd_weight_kernel(const float* __restrict__ d, const float* __restrict__ a,
 // max |W| of the 7 linear weights (blockIdx.y = 0..6) and of conv2's middle kernel row (7) -> wmax[8] (bit patterns,
 // zeroed per forward call): the power-of-two scales of the weight planes
 struct WmaxArgs { const float* W[8]; int n[8]; };
-__global__ void __launch_bounds__(256)
-weights_absmax_kernel(const WmaxArgs a, unsigned int* __restrict__ wmax) {
-    const int l = blockIdx.y;
+__device__ __forceinline__ void weights_absmax_body(const WmaxArgs& a, unsigned int* __restrict__ wmax, int bx, int l,
+                                                    int gx) {
     float m = 0.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n[l]; i += gridDim.x * blockDim.x) {
+    for (int i = bx * blockDim.x + threadIdx.x; i < a.n[l]; i += gx * blockDim.x) {
         // conv2: only the middle row of the 3 x 3 kernels ever meets data
         if (l == 7 && (i % 9) / 3 != 1) continue;
         m = fmaxf(m, fabsf(__ldg(a.W[l] + i)));
@@ -1039,16 +1038,20 @@ weights_absmax_kernel(const WmaxArgs a, unsigned int* __restrict__ wmax) {
     m = warp_max(m);
     if (threadIdx.x % 32 == 0 && m > 0.f && m < 3.0e38f) atomicMax(wmax + l, __float_as_uint(m));
 }
+__global__ void __launch_bounds__(256)
+weights_absmax_kernel(const WmaxArgs a, unsigned int* __restrict__ wmax) {
+    weights_absmax_body(a, wmax, blockIdx.x, blockIdx.y, gridDim.x);
+}
 // max over the columns k of sum_n |W_l[n, k]| for the 7 linear weights (blockIdx.y) -> l1max[7] (bit patterns, zeroed per
 // forward call): |G1 . W| <= max|G1| * this, the bound the fused BN-backward epilogue scales its planes by
-__global__ void __launch_bounds__(256)
-weights_col_l1_kernel(const WmaxArgs a, unsigned int* __restrict__ l1max) {
-    const int l = blockIdx.y;
+__device__ __forceinline__ void weights_col_l1_body(const WmaxArgs& a, unsigned int* __restrict__ l1max, int bx, int l) {
     const int K = a.n[l] / 512;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = bx * blockDim.x + threadIdx.x;
     float s = 0.f;
-    if (k < K)
+    if (k < K) {
+#pragma unroll 8
         for (int n = 0; n < 512; ++n) s += fabsf(__ldg(a.W[l] + (size_t)n * K + k));
+    }
     s = warp_max(s);
     if (threadIdx.x % 32 == 0 && s > 0.f && s < 3.0e38f) atomicMax(l1max + l, __float_as_uint(s));
 }
@@ -1056,10 +1059,9 @@ weights_col_l1_kernel(const WmaxArgs a, unsigned int* __restrict__ l1max) {
 // (blockIdx.y; one warp per row): |A . W^T + b| <= max|A| * rowl1 + bmax, the a-priori bound the GEMM epilogue scales
 // the fp16 planes of its OUTPUT by when the following BatchNorm is folded into the next layer (fold_bn_weights_kernel)
 struct RowL1Args { const float* W[7]; const float* b[7]; int K[7]; };
-__global__ void __launch_bounds__(256)
-weights_row_l1_kernel(const RowL1Args a, unsigned int* __restrict__ rowl1, unsigned int* __restrict__ bmax) {
-    const int l = blockIdx.y;
-    const int j = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+__device__ __forceinline__ void weights_row_l1_body(const RowL1Args& a, unsigned int* __restrict__ rowl1,
+                                                    unsigned int* __restrict__ bmax, int bx, int l) {
+    const int j = bx * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
     if (j >= 512) return;
     const int K = a.K[l];
     float s = 0.f;
@@ -1071,6 +1073,24 @@ weights_row_l1_kernel(const RowL1Args a, unsigned int* __restrict__ rowl1, unsig
         const float b = fabsf(__ldg(a.b[l] + j));
         if (b > 0.f && b < 3.0e38f) atomicMax(bmax + l, __float_as_uint(b));
     }
+}
+// The three bound passes over the weights are independent max-reductions (atomicMax: order-free, deterministic): ONE
+// launch, the block index selects the pass -- [0, n_row) row-L1 (64 x 7), [.., + n_abs) abs-max (48 x 8),
+// [.., + n_col) column-L1 (3 x 7); a pass that the configuration does not need has n_* = 0.
+struct WBoundsArgs {
+    RowL1Args ra;
+    WmaxArgs wa;
+    unsigned int *rowl1, *bmax, *wmax, *l1max;
+    int n_row, n_abs, n_col;
+};
+__global__ void __launch_bounds__(256)
+weights_bounds_kernel(const WBoundsArgs a) {
+    int b = blockIdx.x;
+    if (b < a.n_row) { weights_row_l1_body(a.ra, a.rowl1, a.bmax, b % 64, b / 64); return; }
+    b -= a.n_row;
+    if (b < a.n_abs) { weights_absmax_body(a.wa, a.wmax, b % 48, b / 48, 48); return; }
+    b -= a.n_abs;
+    weights_col_l1_body(a.wa, a.l1max, b % 3, b / 3);
 }
 
 // BatchNorm folded into the NEXT linear layer (no BN-apply pass between two linear blocks without dropout):

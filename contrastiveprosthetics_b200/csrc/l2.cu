@@ -24,19 +24,8 @@ l2_partial_kernel(const L2List L, double* __restrict__ partial /*[count][L2_CHUN
     const int64_t n = L.n[t];
     const int64_t per = (n + L2_CHUNKS - 1) / L2_CHUNKS;
     const int64_t lo = c * per, hi = min(n, lo + per);
-    double s = 0.0;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
-        const double v = (double)__ldg(w + i);
-        s += v * v;
-    }
-    s = warp_sum(s);
-    if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double tot = 0.0;
-        for (int k = 0; k < 8; ++k) tot += red[k];
-        partial[t * L2_CHUNKS + c] = tot;
-    }
+    const double tot = cta_sum_squares_256(w, lo, hi, red);
+    if (threadIdx.x == 0) partial[t * L2_CHUNKS + c] = tot;
 }
 
 __global__ void l2_finish_kernel(const double* __restrict__ partial, int count, float* __restrict__ norms,

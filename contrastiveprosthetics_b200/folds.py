@@ -21,11 +21,13 @@ from .models import Model
 
 
 class ConcurrentFolds:
-    def __init__(self, dataset, params_list, batch_size, adabn=True, seeds=None, dropout_seeds=None):
+    def __init__(self, dataset, params_list, batch_size, adabn=True, seeds=None, dropout_seeds=None, lean=True):
         """dataset: TaskWrapper in train mode; params_list: one hyper-parameter dict per fold (d_e, dp_emg, dp_glove,
         reg_emg, reg_glove, lr_emg, lr_glove); batch_size: groups per step (the captured shape, so the ragged last
-        batch of an epoch is run eagerly)."""
-        self.dataset, self.batch_size = dataset, batch_size
+        batch of an epoch is run eagerly).  lean (default): every fold steps through step.LeanTrainStep -- no
+        autograd / torch.optim nodes in the graph (~110 nodes per fold-step instead of ~145); lean=False keeps the
+        autograd + torch.optim.Adam(fused=True) step."""
+        self.dataset, self.batch_size, self.lean = dataset, batch_size, lean
         self.device = dataset.device
         self.models, self.opts, self.steps, self.streams = [], [], [], []
         example = dataset.get_batch(torch.arange(batch_size))[0]
@@ -41,7 +43,8 @@ class ConcurrentFolds:
                     optim.Adam(model.glove_net.parameters(), lr=params['lr_glove'], weight_decay=0, capturable=True, fused=True)]
             self.models.append(model)
             self.opts.append(opts)
-            self.steps.append(GraphedTrainStep(model, opts, example, capture=False, static_emg=self.static_emg))
+            self.steps.append(GraphedTrainStep(model, opts, example, capture=False, static_emg=self.static_emg,
+                                               lean=lean))
             self.streams.append(torch.cuda.Stream(device=self.device))
         # ONE graph: fork a branch per fold from the capture stream, join them, stack the folds' results
         T = example.shape[1]
@@ -64,6 +67,8 @@ class ConcurrentFolds:
 
     def _eager_step(self, k, EMG):
         model, opts = self.models[k], self.opts[k]
+        if self.lean:
+            return self.steps[k].lean.body(EMG)
         label = torch.arange(EMG.shape[1], device=self.device).repeat(EMG.shape[0])
         logits = model.forward(EMG, None, label)
         loss = model.loss(logits, label)

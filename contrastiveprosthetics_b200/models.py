@@ -144,15 +144,52 @@ class _EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_emb):
-        L = _lib.lib()
-        d_emb = d_emb.contiguous()
         grads = [torch.empty_like(p) if p is not None else None for p in ctx.params]
-        gt = _fill_tensors(_lib.EncoderTensors(), *_split(grads))
-        _lib.check(L.cp_encoder_backward(ctypes.byref(ctx.tens), _lib.ptr(d_emb), ctx.n, ctypes.byref(gt),
-                                         _lib.ptr(ctx.ws), ctx.ws.numel(), ctypes.byref(ctx.opts),
-                                         _lib.stream()), "cp_encoder_backward")
-        ctx.ws = None
+        _encoder_backward_into(ctx, d_emb, grads)
         return (None, None) + tuple(grads)
+
+
+def _encoder_backward_into(ctx, d_emb, grads):
+    """cp_encoder_backward of the forward recorded in `ctx`; the 37 parameter gradients (order of
+    EMGNet.kernel_params()) are OVERWRITTEN in the caller's tensors `grads` (autograd: fresh ones; step.LeanTrainStep:
+    views of its flat gradient bucket)."""
+    d_emb = d_emb.contiguous()
+    gt = _fill_tensors(_lib.EncoderTensors(), *_split(grads))
+    _lib.check(_lib.lib().cp_encoder_backward(ctypes.byref(ctx.tens), _lib.ptr(d_emb), ctx.n, ctypes.byref(gt),
+                                              _lib.ptr(ctx.ws), ctx.ws.numel(), ctypes.byref(ctx.opts),
+                                              _lib.stream()), "cp_encoder_backward")
+    ctx.ws = None
+
+
+class PlainCtx:
+    """Stands in for autograd's ctx when a fused op is driven without autograd (step.LeanTrainStep)."""
+
+    def mark_non_differentiable(self, *_):
+        pass
+
+
+def _head_launch(emb, table_w, table_b, B, W, want_grad, want_logits, d_w=None, d_b=None):
+    """cp_head_forward_backward.  Returns (loss, pred, ncor, logits | None, d_emb, d_w, d_b); d_w / d_b may be the
+    caller's tensors (step.LeanTrainStep: views of its gradient bucket), otherwise fresh ones."""
+    L = _lib.lib()
+    dev = emb.device
+    G = B * W
+    emb = emb.contiguous()
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    pred = torch.empty((G, MAX_TASKS_TRAIN), dtype=torch.int32, device=dev)
+    ncor = torch.empty((G,), dtype=torch.int32, device=dev)
+    logits = torch.empty((G, MAX_TASKS_TRAIN, MAX_TASKS_TRAIN), dtype=torch.float32, device=dev) \
+        if want_logits else None
+    d_emb = torch.empty_like(emb) if want_grad else None
+    if want_grad and d_w is None:
+        d_w, d_b = torch.empty_like(table_w), torch.empty_like(table_b)
+    nbytes = L.cp_head_workspace_bytes(G)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    P = _lib.ptr
+    _lib.check(L.cp_head_forward_backward(P(emb), B, W, P(table_w.contiguous()), P(table_b.contiguous()),
+                                          P(loss), P(d_emb), P(d_w), P(d_b), P(pred), P(ncor), P(logits),
+                                          P(ws), nbytes, _lib.stream()), "cp_head_forward_backward")
+    return loss, pred, ncor, logits, d_emb, d_w, d_b
 
 
 class _HeadFn(torch.autograd.Function):
@@ -161,28 +198,11 @@ class _HeadFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, emb, table_w, table_b, B, W, want_grad, want_logits):
-        L = _lib.lib()
-        dev = emb.device
-        G = B * W
-        emb = emb.contiguous()
-        loss = torch.empty((), dtype=torch.float32, device=dev)
-        pred = torch.empty((G, MAX_TASKS_TRAIN), dtype=torch.int32, device=dev)
-        ncor = torch.empty((G,), dtype=torch.int32, device=dev)
-        logits = torch.empty((G, MAX_TASKS_TRAIN, MAX_TASKS_TRAIN), dtype=torch.float32, device=dev) \
-            if want_logits else None
-        d_emb = torch.empty_like(emb) if want_grad else None
-        d_w = torch.empty_like(table_w) if want_grad else None
-        d_b = torch.empty_like(table_b) if want_grad else None
-        nbytes = L.cp_head_workspace_bytes(G)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        P = _lib.ptr
-        _lib.check(L.cp_head_forward_backward(P(emb), B, W, P(table_w.contiguous()), P(table_b.contiguous()),
-                                              P(loss), P(d_emb), P(d_w), P(d_b), P(pred), P(ncor), P(logits),
-                                              P(ws), nbytes, _lib.stream()), "cp_head_forward_backward")
+        loss, pred, ncor, logits, d_emb, d_w, d_b = _head_launch(emb, table_w, table_b, B, W, want_grad, want_logits)
         ctx.saved = (d_emb, d_w, d_b)
         ctx.mark_non_differentiable(pred, ncor)
         if logits is None:
-            logits = torch.empty(0, device=dev)
+            logits = torch.empty(0, device=emb.device)
         ctx.mark_non_differentiable(logits)
         return loss, pred, ncor, logits
 
@@ -592,7 +612,7 @@ class EMGNet(nn.Module):
         return ([c[0].weight, c[0].bias, c[1].weight, c[1].bias] + [m.weight for m in l] +
                 [m.bias for m in l] + [proj] + [m.weight for m in b] + [m.bias for m in b])
 
-    def encode_flat(self, EMG, subjects=None):
+    def encode_flat(self, EMG, subjects=None, raw=False):
         """(B,41,W,1,12) or anything reshapeable to (-1,12) -> (N,16) embeddings, row order unchanged
         (prediction mode: the (N,512) output of the 7th linear block).  subjects: see `per_subject`."""
         self.shape = EMG.shape
@@ -625,6 +645,14 @@ class EMGNet(nn.Module):
                "tap": self.debug_tap, "sync_bn": self._sync_active(), "group": self.process_group,
                "trunk_only": self.prediction,
                "ws_alloc": getattr(self, "ws_alloc", None)}
+        if raw:                                  # step.LeanTrainStep: no autograd node, the caller keeps the context
+            if subjects is not None:
+                raise NotImplementedError("per-subject AdaBN runs through autograd (one encoder pass per subject)")
+            ctx = PlainCtx()
+            cfg["need_bwd"] = True
+            with torch.no_grad():
+                emb = _EncoderFn.forward(ctx, x, cfg, *self.kernel_params())
+            return emb, ctx
         if subjects is not None:
             return self._encode_per_subject(x, subjects, cfg)
         return _EncoderFn.apply(x, cfg, *self.kernel_params())

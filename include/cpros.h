@@ -304,6 +304,29 @@ int cp_l2_forward(const float *const *tensors, const int64_t *sizes, int n_tenso
 int cp_l2_backward(const float *const *tensors, const int64_t *sizes, int n_tensors, const float *norms,
                    const float *g_total, float coef, float *const *grads, void *stream);
 
+/* ---------------------------------------------------------------- K6: step prologue + optimiser (train.py:72-73, 95-108)
+ * The two ends of the reference's loop body that it leaves to autograd and torch.optim: `+ model.l2()` /
+ * `loss.backward()`'s regulariser gradient, and `optimizer_emg.step(); optimizer_glove.step()`.
+ * cp_step_prologue: ONE launch.  norms[t] = ||W_t||_2 of the n_tensors (<= CP_STEP_MAX_TENSORS) regularised tensors
+ *   (HOST arrays of device pointers / element counts; same arithmetic as cp_l2_forward) and counters[0..n_counters)
+ *   (device int64: the dropout step of cp_encoder_opts.dropout_step, Adam's t) += 1.  The first 256 bytes of
+ *   `workspace` must be ZERO before the first call; the kernel leaves them zero (graph replays included).
+ * cp_adam_step: ONE launch over every parameter tensor of both optimisers.  params / sizes / offsets / lr_index / reg /
+ *   norm_index are HOST arrays of n_tensors entries; grads, exp_avg, exp_avg_sq are FLAT device buffers with tensor t
+ *   at element offset offsets[t]; lr is a DEVICE array of doubles (lr[lr_index[t]]: a scheduler rewrites it between
+ *   graph replays); *step (device) is Adam's t >= 1.  g = grads + (norm_index[t] >= 0 ? reg[t] * W / norms[norm_index[t]]
+ *   : 0) (the gradient of reg * ||W||_2, 0 where the norm is 0: models.py:225-228, 344-349), then torch.optim.Adam's
+ *   default update (no weight decay / amsgrad / maximize): m = b1 m + (1-b1) g, v = b2 v + (1-b2) g^2,
+ *   W -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).  params, exp_avg, exp_avg_sq are updated IN PLACE. */
+#define CP_STEP_MAX_TENSORS 48
+size_t cp_step_workspace_bytes(int n_tensors);
+int cp_step_prologue(const float *const *tensors, const int64_t *sizes, int n_tensors, float *norms,
+                     int64_t *counters, int n_counters, void *workspace, size_t workspace_bytes, void *stream);
+int cp_adam_step(float *const *params, const int64_t *sizes, const int64_t *offsets, int n_tensors,
+                 const float *grads, float *exp_avg, float *exp_avg_sq, const double *lr, const int32_t *lr_index,
+                 const float *reg, const int32_t *norm_index, const float *norms, const int64_t *step,
+                 double beta1, double beta2, double eps, void *stream);
+
 /* ---------------------------------------------------------------- offline preprocessing
  * load.py:85-101 / utils.py:134-156: per (subject, stimulus, repetition) segment raw[seg_len, n_ch] (float32, time
  * major): x = raw * gain -> IIR filter (b, a: HOST arrays of n_coef <= 17 doubles, a[0] == 1; scipy lfilter

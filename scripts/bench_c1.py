@@ -19,16 +19,16 @@ def c1_small_batch(dev, B=8, steps=200):
     tw = TaskWrapper(ds, with_glove=False)
     tw.set_train()
     out = {}
-    for mode in ("eager", "graph"):
+    for mode in ("eager", "graph", "graph_lean"):
         torch.manual_seed(42)
         model = Model(dict(params), adabn=True, device=str(dev))
         model.set_train()
-        gm = mode == "graph"            # graph mode: torch's single-kernel Adam (fused=True), 2 nodes instead of ~14
+        gm = mode != "eager"            # graph modes: torch's single-kernel Adam (fused=True), 2 nodes instead of ~14
         opts = [torch.optim.Adam(model.emg_net.parameters(), lr=1e-3, capturable=gm, fused=gm or None),
                 torch.optim.Adam(model.glove_net.parameters(), lr=1e-3, capturable=gm, fused=gm or None)]
         items = [torch.randperm(tw.D)[:B].to(dev) for _ in range(16)]
-        if mode == "graph":
-            step = GraphedTrainStep(model, opts, tw.get_batch(items[0])[0])
+        if gm:                          # graph_lean: step.LeanTrainStep inside the graph (no autograd / torch.optim nodes)
+            step = GraphedTrainStep(model, opts, tw.get_batch(items[0])[0], lean=mode == "graph_lean")
 
             def one(i):
                 step(tw.get_batch(items[i % 16])[0])
@@ -67,7 +67,7 @@ if __name__ == "__main__":
 
 def c1_concurrent_folds(dev, B=8, steps=200, ks=(1, 4, 8, 16)):
     """The reference's cross-validation workload (150 folds x 2,500 steps at batch_size 8, train.py:140-166): K folds
-    in lockstep on one GPU, one CUDA graph + one stream per fold (folds.ConcurrentFolds).  Aggregate windows/s."""
+    in lockstep on one GPU, ONE CUDA graph with K branches (folds.ConcurrentFolds, lean steps).  Aggregate windows/s."""
     from contrastiveprosthetics_b200.folds import ConcurrentFolds
     from contrastiveprosthetics_b200.load import DB23
     from contrastiveprosthetics_b200.utils import TaskWrapper
