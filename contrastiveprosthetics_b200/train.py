@@ -112,6 +112,14 @@ def train_loop(dataset, params, checkpoint=False, checkpoint_dir="../checkpoints
         scheduler_emg = optim.lr_scheduler.StepLR(optimizer_glove, step_size=5, gamma=.2)
         scheduler_glove = optim.lr_scheduler.StepLR(optimizer_glove, step_size=5, gamma=.2)
     sync_grads = cpdist.FlatGradAllReduce(list(model.emg_net.parameters()) + list(model.glove_net.parameters()))
+    # --lean_step: the loop body below without autograd / torch.optim (step.LeanTrainStep: the same kernels, the
+    # regulariser's gradient and both Adams in one launch, the gradient bucket all-reduced in place).  The torch
+    # optimizers stay as the schedulers' handle on the learning rates.
+    lean = None
+    if getattr(args, "lean_step", False) and not args.prediction and not getattr(args, "per_subject_adabn", False):
+        from . import step as cpstep
+        lean = cpstep.from_optimizers(model, [optimizer_emg, optimizer_glove], sync_grads=True)
+        optimizer_emg._opt_called = optimizer_glove._opt_called = True    # (the schedulers' "step() before optimizer.step()" check)
 
     dataset.set_train()
     model.set_train()
@@ -121,6 +129,9 @@ def train_loop(dataset, params, checkpoint=False, checkpoint_dir="../checkpoints
     for e in range(params['epochs']):
         loss_train = []
         for (EMG, GLOVE, label) in _loader(dataset, args.batch_size):
+            if lean is not None:
+                loss_train.append(lean(EMG)[0])
+                continue
             label = label.reshape(-1)
             logits = model.forward(EMG, GLOVE, label)
             loss = model.loss(logits, label)
@@ -135,6 +146,8 @@ def train_loop(dataset, params, checkpoint=False, checkpoint_dir="../checkpoints
         acc_train = model.correct()
         scheduler_emg.step()
         scheduler_glove.step()
+        if lean is not None:
+            lean.set_lr(optimizer_emg.param_groups[0]['lr'], optimizer_glove.param_groups[0]['lr'])
         loss_train = torch.stack(loss_train).mean().item()
         if cpdist.world_size() > 1:         # logging only: mean over the ranks' local shards
             t = torch.tensor([loss_train, acc_train], dtype=torch.float64, device=dataset.device)
@@ -303,6 +316,9 @@ def build_parser():
     parser.add_argument('--per_subject_adabn', action='store_true',
                         help='AdaBN statistics per subject (models.py:245 "batch per subject"): every BatchNorm '
                              'normalises the windows of one subject at a time, in training and evaluation')
+    parser.add_argument('--lean_step', action='store_true',
+                        help="train step without autograd / torch.optim (step.LeanTrainStep): same kernels and update rule, "
+                             "~35 fewer launches per step; what bench.py's cuda_graph_lean mode and --concurrent_folds use")
     parser.add_argument('--fused_adam', action='store_true',
                         help="torch.optim.Adam(fused=True): same update rule in one kernel per optimizer (what bench.py uses)")
     parser.add_argument('--concurrent_folds', type=int, default=1,

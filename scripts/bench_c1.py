@@ -65,7 +65,7 @@ if __name__ == "__main__":
     print(json.dumps(c1_small_batch(torch.device("cuda:0"))))
 
 
-def c1_concurrent_folds(dev, B=8, steps=200, ks=(1, 4, 8, 16)):
+def c1_concurrent_folds(dev, B=8, steps=200, ks=(1, 4, 8, 16, 32)):
     """The reference's cross-validation workload (150 folds x 2,500 steps at batch_size 8, train.py:140-166): K folds
     in lockstep on one GPU, ONE CUDA graph with K branches (folds.ConcurrentFolds, lean steps).  Aggregate windows/s."""
     from contrastiveprosthetics_b200.folds import ConcurrentFolds

@@ -94,6 +94,56 @@ for adabn in (True, False):
     lsum2 = ll.detach().clone(); dist.all_reduce(lsum2); lsum2 /= world
     assert abs(lsum2.item() - lf.item()) > 1e-5 * abs(lf.item())
     print("rank", rank, "adabn", adabn, "syncbn worst grad rel", worst)
+# ---- step.LeanTrainStep with the gradient bucket averaged in place == the autograd step + FlatGradAllReduce + Adam;
+#      (NCCL) its CUDA-graph capture, all-reduce inside the graph, == the eager lean step
+from contrastiveprosthetics_b200.step import LeanTrainStep
+from contrastiveprosthetics_b200.graph import GraphedTrainStep
+hp = {'d_e': 16, 'dp_emg': 0.0, 'dp_glove': 0.0, 'reg_emg': 1e-4, 'reg_glove': 1e-3}
+per = 8
+g = torch.Generator().manual_seed(9)
+steps = [(torch.randn(per * world, 41, 1, 1, 12, generator=g) + 0.5 * torch.randn(1, 41, 1, 1, 12, generator=g)).to(dev)
+         for _ in range(4)]
+mine = [b[rank * per:(rank + 1) * per].contiguous() for b in steps]
+lab = torch.arange(41, device=dev).repeat(per)
+def fresh():
+    torch.manual_seed(42)
+    m = Model(dict(hp), adabn=True, device=str(dev)); m.set_train()
+    return m
+m_ref = fresh()
+opts = [torch.optim.Adam(m_ref.emg_net.parameters(), lr=1e-3), torch.optim.Adam(m_ref.glove_net.parameters(), lr=3e-3)]
+sync = cpdist.FlatGradAllReduce(list(m_ref.emg_net.parameters()) + list(m_ref.glove_net.parameters()))
+for EMG in mine:
+    total = m_ref.loss(m_ref.forward(EMG, None, lab), lab) + m_ref.l2()
+    for o in opts: o.zero_grad(set_to_none=True)
+    total.backward(); sync()
+    for o in opts: o.step()
+m_lean = fresh()
+lean = LeanTrainStep(m_lean, 1e-3, 3e-3, sync_grads=True)
+for EMG in mine:
+    lean(EMG)
+# Adam turns rounding-level differences of single gradients (here: avg(g + l2) vs avg(g) + l2) into lr-sized differences
+# of single parameters (tests/test_gpu_step.py::test_lean_step_equals_autograd_step): compare in the mean, and the loss
+worst, n_par = 0.0, 0
+for (k, a), (_, b) in zip(m_lean.state_dict().items(), m_ref.state_dict().items()):
+    if a.dtype.is_floating_point:
+        worst += float((a - b).abs().sum()); n_par += a.numel()
+        other = a.clone(); dist.broadcast(other, src=0)
+        assert torch.equal(a, other), ("replicas diverged", k)
+worst /= n_par
+assert worst < 1e-5, worst
+with torch.no_grad():
+    l_a = m_lean.loss(m_lean.forward(mine[0], None, lab), lab).item()
+    l_b = m_ref.loss(m_ref.forward(mine[0], None, lab), lab).item()
+assert abs(l_a - l_b) < 1e-3 * abs(l_b), (l_a, l_b)
+if nccl:
+    m_g = fresh()
+    o_g = [torch.optim.Adam(m_g.emg_net.parameters(), lr=1e-3), torch.optim.Adam(m_g.glove_net.parameters(), lr=3e-3)]
+    gs = GraphedTrainStep(m_g, o_g, mine[0], sync_grads=True, lean=True)
+    for EMG in mine:
+        gs(EMG)
+    for (k, a), (_, b) in zip(m_g.state_dict().items(), m_lean.state_dict().items()):
+        assert torch.equal(a, b), ("graphed lean step != eager lean step", k)
+print("rank", rank, "lean step vs autograd + all-reduce: mean |dp|", worst, "loss", l_a, l_b)
 torch.cuda.synchronize()
 dist.barrier()
 sys.stdout.write(f"rank {rank} ok\n"); sys.stdout.flush()          # one write: the ranks share the pipe

@@ -101,11 +101,10 @@ def test_adam_step_matches_torch_adam(fused):
                                   _lib.ptr(norms), _lib.ptr(counters[1:2]), 0.9, 0.999, 1e-8, _lib.stream()))
         for p, r, l in zip(ps, ref, lrs):
             worst = max(worst, ((p - r.detach()).abs() / (r.detach().abs() + l)).max().item())
-    # |dp| relative to |p| + lr (one update is O(lr)) after 8 steps.  Measured on B200: the parameters end 1 - 3 ulp apart
-    # (3e-5 .. 9e-5 of one update) against both of torch's implementations -- a different rounding of the last subtraction
-    # here and there, nothing that accumulates.
+    # |dp| relative to |p| + lr (one update is O(lr)) after 8 steps.  Measured on B200: 1.1e-6 against torch's foreach
+    # implementation (every intermediate rounded to fp32), parameters 1 - 3 ulp apart against its single-kernel one.
     print(f"cp_adam_step vs torch.optim.Adam(fused={fused}): worst |dp| / (|p| + lr) = {worst:.3g}")
-    assert worst < 1e-6, worst
+    assert worst < 1e-5, worst
     assert counters.tolist() == [8, 8]
 
 
@@ -129,10 +128,16 @@ def _autograd_steps(model, batches, fused=True):
 
 @pytest.mark.parametrize("adabn", [True, False])
 def test_lean_step_equals_autograd_step(adabn):
+    """Against the reference's own wiring: autograd + torch.optim.Adam with its default (foreach) implementation
+    (train.py:72-73).  Adam's first updates are lr * g / (|g| + eps): an element whose gradient sits at rounding level
+    takes a different step under ANY change of rounding, and six steps amplify that -- torch's own two implementations
+    (fused=True vs default) end 6e-5 apart in the loss and 3e-3 in single weights on these batches
+    (scripts/diag_lean_vs_autograd.py), while the lean step reproduces the default one's losses digit for digit.  So:
+    losses to 2e-6, and all but a sliver of the parameters to 1e-6."""
     from contrastiveprosthetics_b200.step import LeanTrainStep
     batches = _batches(6)
     ref_model = _model(adabn=adabn)
-    ref = _autograd_steps(ref_model, batches)
+    ref = _autograd_steps(ref_model, batches, fused=False)
     model = _model(adabn=adabn)
     lean = LeanTrainStep(model, PARAMS['lr_emg'], PARAMS['lr_glove'])
     got = []
@@ -141,15 +146,17 @@ def test_lean_step_equals_autograd_step(adabn):
         got.append((loss.item(), ncor.clone()))
     assert got[0][0] == ref[0][0] and torch.equal(got[0][1], ref[0][1])        # same kernels before the first update
     for (l, n), (lr, nr) in zip(got, ref):
-        assert abs(l - lr) <= 1e-5 * abs(lr)
+        assert abs(l - lr) <= 2e-6 * abs(lr), (l, lr)
     sd, sd_ref = model.state_dict(), ref_model.state_dict()
-    worst = 0.0
+    off, total = 0, 0
     for k in sd_ref:
         if sd_ref[k].dtype.is_floating_point:
-            worst = max(worst, (sd[k] - sd_ref[k]).abs().max().item())
+            off += int(((sd[k] - sd_ref[k]).abs() > 1e-6).sum())
+            total += sd[k].numel()
         else:
             assert torch.equal(sd[k], sd_ref[k]), k
-    assert worst < 1e-6, worst                     # six updates of O(lr = 1e-3) each
+    print(f"lean vs autograd + Adam (adabn={adabn}): {off} of {total} parameters differ by more than 1e-6")
+    assert off <= 1e-3 * total, (off, total)
 
 
 def test_lean_gradients_are_the_autograd_gradients():
@@ -172,15 +179,17 @@ def test_lean_gradients_are_the_autograd_gradients():
             assert torch.equal(p.grad, q.grad), name
 
 
-@pytest.mark.parametrize("dp", [0.0, 0.5])
-def test_lean_graph_is_bit_identical_to_lean_eager(dp):
+@pytest.mark.parametrize("adabn", [True, False])
+def test_lean_graph_is_bit_identical_to_lean_eager(adabn):
+    """(Without dropout: an eager step mixes its host-side call count into the Philox key, a captured graph only the
+    device-side step counter -- same as the autograd step, tests/test_gpu_graph.py.)"""
     from contrastiveprosthetics_b200.graph import GraphedTrainStep
     from contrastiveprosthetics_b200.step import LeanTrainStep
     batches = _batches(6)
-    model = _model(dp)
+    model = _model(adabn=adabn)
     lean = LeanTrainStep(model, PARAMS['lr_emg'], PARAMS['lr_glove'])
     eager = [(l.item(), n.clone()) for l, n in (lean(EMG) for EMG in batches)]
-    model2 = _model(dp)
+    model2 = _model(adabn=adabn)
     opts = [torch.optim.Adam(model2.emg_net.parameters(), lr=PARAMS['lr_emg']),
             torch.optim.Adam(model2.glove_net.parameters(), lr=PARAMS['lr_glove'])]
     step = GraphedTrainStep(model2, opts, batches[0], lean=True)
@@ -194,15 +203,16 @@ def test_lean_graph_is_bit_identical_to_lean_eager(dp):
 
 
 def test_lean_lr_is_read_at_run_time():
-    """A scheduler's new lr reaches the captured graph (lr is a device array)."""
+    """A scheduler's new lr reaches the captured graph (lr is a device array); every replay draws a fresh dropout mask."""
     from contrastiveprosthetics_b200.graph import GraphedTrainStep
-    model = _model()
+    model = _model(dp=0.5)
     opts = [torch.optim.Adam(model.emg_net.parameters(), lr=1e-3), torch.optim.Adam(model.glove_net.parameters(), lr=1e-3)]
     EMG = _batches(1)[0]
     step = GraphedTrainStep(model, opts, EMG, lean=True)
     step.lean.set_lr(0.0, 0.0)
     before = {k: v.clone() for k, v in model.state_dict().items()}
-    step(EMG)
+    losses = [step(EMG)[0].item() for _ in range(4)]
+    assert len(set(losses)) == 4, losses            # frozen weights: only the mask can change the loss
     for k, v in model.state_dict().items():
         assert torch.equal(v, before[k]), k
     step.lean.set_lr(1e-3, 1e-3)

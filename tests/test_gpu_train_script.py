@@ -17,17 +17,17 @@ def _args(tmp_path, extra=()):
     return cptrain.build_parser().parse_args(argv + list(extra))
 
 
-@pytest.mark.parametrize("extra", [(), ("--no_adabn",)])
+@pytest.mark.parametrize("extra", [(), ("--no_adabn",), ("--lean_step",)])
 def test_main_runs_with_reference_flags(tmp_path, extra):
     args = _args(tmp_path, extra)
-    assert args.no_adabn is (len(extra) == 0)              # inverted store_false flag, as in the reference
+    assert args.no_adabn is ("--no_adabn" not in extra)    # inverted store_false flag, as in the reference
     loss, acc = cptrain.main(args)
     assert np.isfinite(loss) and 0.0 <= acc <= 1.0
     keys = np.load(f"{tmp_path}/data/cross_val_keys.npy")
     vals = np.load(f"{tmp_path}/data/cross_val_values.npy")
     assert keys.shape == (2, 7) and vals.shape == (2, 2)   # layout of data/cross_val_*.npy
     sd = torch.load(f"{tmp_path}/ckpt/contrastive.pt")
-    assert len(sd) == (41 if not extra else 68)            # reference state-dict key counts
+    assert len(sd) == (68 if "--no_adabn" in extra else 41)            # reference state-dict key counts
 
 
 def test_item_loader_path_matches_batched_path(tmp_path):
