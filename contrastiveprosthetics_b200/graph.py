@@ -79,6 +79,11 @@ class GraphedTrainStep:
                 self.loss, self.n_correct = self._body()
             self.restore()
 
+    def close(self):
+        """Drop the captured graph.  With sync_grads the graph holds NCCL collectives: release it BEFORE
+        torch.distributed.destroy_process_group(), which otherwise waits on the communicator forever."""
+        self.graph = None
+
     def body(self):
         """One step on `static_emg` (what a capture records).  Returns (loss, per-group correct counts)."""
         return self._body()

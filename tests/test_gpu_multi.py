@@ -26,6 +26,10 @@ nccl = dist.get_backend() == "nccl"
 def rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm())
 
+def mark(what):
+    torch.cuda.synchronize()
+    sys.stderr.write(f"[rank {rank}] {what}\n"); sys.stderr.flush()
+
 # ---- batch x batch CLIP head: sharded (all-gather / all-reduce / reduce-scatter) == single GPU on the whole batch
 n = 1000
 g = torch.Generator().manual_seed(0)
@@ -45,6 +49,7 @@ for logit_scale in (0.0, 1.0):
     assert rel(G.grad, Gf.grad[rank * n:(rank + 1) * n]) < 1e-5
     assert int(ncor) == int(ncor_f) and torch.equal(arg, arg_f[rank * n:(rank + 1) * n])
 
+mark("clip head ok")
 # ---- flat-bucket gradient all-reduce over NCCL: average and sum
 ps = [torch.nn.Parameter(torch.zeros(1000, 3, device=dev)), torch.nn.Parameter(torch.zeros(7, device=dev))]
 for mode, expect in ((True, (world + 1) / 2.0), (False, world * (world + 1) / 2.0)):
@@ -52,6 +57,7 @@ for mode, expect in ((True, (world + 1) / 2.0), (False, world * (world + 1) / 2.
         p.grad = torch.full_like(p, float(rank + 1))
     cpdist.FlatGradAllReduce(ps, average=mode)()
     assert all(torch.allclose(p.grad, torch.full_like(p, expect)) for p in ps)
+mark("flat all-reduce ok")
 # ---- SyncBN: world ranks x (B/world) groups with statistics over every rank's rows == one rank x B groups
 from contrastiveprosthetics_b200.models import Model
 params = {'d_e': 16, 'dp_emg': 0.0, 'dp_glove': 0.0, 'reg_emg': 0.0, 'reg_glove': 0.0}
@@ -94,6 +100,7 @@ for adabn in (True, False):
     lsum2 = ll.detach().clone(); dist.all_reduce(lsum2); lsum2 /= world
     assert abs(lsum2.item() - lf.item()) > 1e-5 * abs(lf.item())
     print("rank", rank, "adabn", adabn, "syncbn worst grad rel", worst)
+mark("syncbn ok")
 # ---- step.LeanTrainStep with the gradient bucket averaged in place == the autograd step + FlatGradAllReduce + Adam;
 #      (NCCL) its CUDA-graph capture, all-reduce inside the graph, == the eager lean step
 from contrastiveprosthetics_b200.step import LeanTrainStep
@@ -117,6 +124,7 @@ for EMG in mine:
     for o in opts: o.zero_grad(set_to_none=True)
     total.backward(); sync()
     for o in opts: o.step()
+mark("autograd reference steps ok")
 m_lean = fresh()
 lean = LeanTrainStep(m_lean, 1e-3, 3e-3, sync_grads=True)
 for EMG in mine:
@@ -135,6 +143,7 @@ with torch.no_grad():
     l_a = m_lean.loss(m_lean.forward(mine[0], None, lab), lab).item()
     l_b = m_ref.loss(m_ref.forward(mine[0], None, lab), lab).item()
 assert abs(l_a - l_b) < 1e-3 * abs(l_b), (l_a, l_b)
+mark("eager lean steps ok")
 if nccl:
     m_g = fresh()
     o_g = [torch.optim.Adam(m_g.emg_net.parameters(), lr=1e-3), torch.optim.Adam(m_g.glove_net.parameters(), lr=3e-3)]
@@ -143,11 +152,18 @@ if nccl:
         gs(EMG)
     for (k, a), (_, b) in zip(m_g.state_dict().items(), m_lean.state_dict().items()):
         assert torch.equal(a, b), ("graphed lean step != eager lean step", k)
+    # a CUDA graph that holds captured NCCL collectives must go before the communicator does (destroy_process_group
+    # otherwise waits forever -- seen on 2 x B200)
+    del gs
+    import gc; gc.collect()
 print("rank", rank, "lean step vs autograd + all-reduce: mean |dp|", worst, "loss", l_a, l_b)
 torch.cuda.synchronize()
 dist.barrier()
 sys.stdout.write(f"rank {rank} ok\n"); sys.stdout.flush()          # one write: the ranks share the pipe
+import threading
+threading.Timer(30.0, lambda: os._exit(0)).start()                  # every check has passed: never hang in teardown
 dist.destroy_process_group()
+os._exit(0)
 '''
 
 
@@ -213,7 +229,7 @@ dist.destroy_process_group()
 '''
 
 
-def _run_two_ranks(tmp_path, worker, port, timeout=900):
+def _run_two_ranks(tmp_path, worker, port, timeout=420):
     script = tmp_path / "w.py"
     script.write_text(worker)
     env = dict(os.environ, CP_ROOT=ROOT, CP_TMP=str(tmp_path))
