@@ -481,7 +481,7 @@ bn_apply_kernel(const float* __restrict__ y, float* __restrict__ a, float* __res
 // the derivation cancelled badly: that kernel collects per-CTA pairs (E^2, D^2) with E_f = (|sum W dW| +
 // |beta sum g'|) / |gamma| the magnitude of the terms and D_f = |sum g' xh| the result -- a weight-gradient error eps
 // becomes eps * E / D in d_gamma (norm-wise over the stage); beyond 8x its last CTA raises the flag too.
-#define WS_CANCEL_PARTS 32
+#define WS_CANCEL_PARTS 64
 __device__ __forceinline__ bool stage_needs_exact(const unsigned int* __restrict__ flag) { return __ldg(flag) != 0u; }
 
 template <int F>
@@ -750,9 +750,12 @@ colsum_fold12_kernel(const float* __restrict__ part, int P, float* __restrict__ 
 // Double accumulation in a fixed order (deterministic).  Outputs like bn_bwd_finalize_kernel.
 // With dropout between the stage and the layer only the first identity is lost (see sum_g_in below).
 template <int GROUP> struct WgradStats {
-    static constexpr int COLS = GROUP == 1 ? 16 : 24;                  // columns of W per CTA (24 = 2 channels x 12 positions)
-    static constexpr int CX = GROUP == 1 ? 16 : 32;                    // column slots of the 512 threads ...
-    static constexpr int LANES = 512 / CX;                             // ... and row lanes (32 for the linear stages: every thread works)
+    // linear stages: 8 columns per CTA = 64 CTAs, 64 row lanes -> 8 rows per thread, every load of a thread in flight at
+    // once (16 columns / 32 CTAs / 16 dependent trips took 9 us at any batch size: 7 such launches are 10 % of the
+    // batch_size-8 step)
+    static constexpr int COLS = GROUP == 1 ? 8 : 24;                   // columns of W per CTA (24 = 2 channels x 12 positions)
+    static constexpr int CX = GROUP == 1 ? 8 : 32;                     // column slots of the 512 threads ...
+    static constexpr int LANES = 512 / CX;                             // ... and row lanes (every thread works in the linear stages)
 };
 template <int GROUP>
 __global__ void __launch_bounds__(512)
@@ -772,7 +775,7 @@ bn_bwd_stats_from_wgrad_kernel(const float* __restrict__ W, const float* __restr
     const int col = blockIdx.x * COLS + cx;
     double a = 0.0, t = 0.0;
     if (cx < COLS && col < cols) {
-#pragma unroll 4
+#pragma unroll 8
         for (int k = ky; k < K_out; k += WS_LANES) {
             const double w = (double)__ldg(W + (size_t)k * cols + col);
             a += (double)__ldg(db + k) * w;
@@ -1030,10 +1033,19 @@ struct WmaxArgs { const float* W[8]; int n[8]; };
 __device__ __forceinline__ void weights_absmax_body(const WmaxArgs& a, unsigned int* __restrict__ wmax, int bx, int l,
                                                     int gx) {
     float m = 0.f;
-    for (int i = bx * blockDim.x + threadIdx.x; i < a.n[l]; i += gx * blockDim.x) {
-        // conv2: only the middle row of the 3 x 3 kernels ever meets data
-        if (l == 7 && (i % 9) / 3 != 1) continue;
-        m = fmaxf(m, fabsf(__ldg(a.W[l] + i)));
+    if (l != 7 && a.n[l] % 4 == 0 && (reinterpret_cast<uintptr_t>(a.W[l]) & 15) == 0) {
+        // linear weights: 16-byte loads (max is order-free: same result as the scalar walk)
+        const float4* __restrict__ w4 = reinterpret_cast<const float4*>(a.W[l]);
+        for (int i = bx * blockDim.x + threadIdx.x; i < a.n[l] / 4; i += gx * blockDim.x) {
+            const float4 v = __ldg(w4 + i);
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        }
+    } else {
+        for (int i = bx * blockDim.x + threadIdx.x; i < a.n[l]; i += gx * blockDim.x) {
+            // conv2: only the middle row of the 3 x 3 kernels ever meets data
+            if (l == 7 && (i % 9) / 3 != 1) continue;
+            m = fmaxf(m, fabsf(__ldg(a.W[l] + i)));
+        }
     }
     m = warp_max(m);
     if (threadIdx.x % 32 == 0 && m > 0.f && m < 3.0e38f) atomicMax(wmax + l, __float_as_uint(m));
