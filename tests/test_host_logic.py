@@ -78,6 +78,55 @@ def test_no_cpu_fallback(emg):
         m.forward(torch.zeros(2, 41, 1, 1, 12), torch.zeros(2, 41, 20), torch.arange(41).repeat(2))
 
 
+@pytest.mark.parametrize("adabn,n_reg", [(True, 12), (False, 21)])
+def test_lean_step_host_layout(adabn, n_reg):
+    """step.LeanTrainStep's host side (no compute call without a GPU): the regularised set is the reference's name filter
+    (models.py:344-349 / 467-472: 10 + 2 tensors with AdaBN, 19 + 2 with --no_adabn), every parameter's .grad
+    is a 512-byte-aligned view of ONE flat bucket in optimizer order, lr / reg follow the two Adams of train.py:72-73,
+    and the step itself refuses CPU tensors."""
+    from contrastiveprosthetics_b200.models import Model
+    from contrastiveprosthetics_b200.step import LeanTrainStep, from_optimizers
+    from oracle import model as OM
+    hp = {'d_e': 16, 'dp_emg': 0.5, 'dp_glove': 0., 'reg_emg': 1e-4, 'reg_glove': 1e-3}
+    torch.manual_seed(42)
+    m = Model(dict(hp), adabn=adabn, device="cpu")
+    s = LeanTrainStep(m, 1e-3, 3e-3)
+    named = [("emg_net." + k, p) for k, p in m.emg_net.named_parameters()] + \
+            [("glove_net." + k, p) for k, p in m.glove_net.named_parameters()]
+    assert [id(p) for _, p in named] == [id(p) for p in s.params]
+    assert sum(p.numel() for p in s.params) == 2_027_616          # SURVEY a12 (logit_scale untouched)
+    assert s._n_reg == n_reg
+    reg_names = {k for (k, _), ni in zip(named, s._norm_index) if ni >= 0}
+    assert reg_names == {k for k, _ in named if "bn" not in k and "bias" not in k}
+    # the oracle's penalty walks the same keys: its value changes iff a regularised tensor changes
+    sd = {k: p.detach().clone() for k, p in named}
+    base = float(OM.l2_penalty(sd, 1.0, 1.0))
+    for k in sd:
+        sd2 = dict(sd)
+        sd2[k] = sd[k] * 2 + 1
+        assert (abs(float(OM.l2_penalty(sd2, 1.0, 1.0)) - base) > 0) == (k in reg_names), k
+    off = 0
+    for (k, p), g, o, li, rg in zip(named, s.grad_views, s._offs, s._lr_index, s._reg):
+        assert o == off and o % 128 == 0 and p.grad is g and g.shape == p.shape
+        assert g.data_ptr() == s.grad_flat.data_ptr() + 4 * o
+        assert li == (0 if k.startswith("emg_net.") else 1)
+        assert rg == pytest.approx(1e-4 if k.startswith("emg_net.") else 1e-3)
+        off += (p.numel() + 127) // 128 * 128
+    assert off == s.numel == s.exp_avg.numel() == s.exp_avg_sq.numel()
+    assert m.emg_net.dropout_step.data_ptr() == s.counters.data_ptr()
+    m.set_train()
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        s(torch.zeros(2, 41, 1, 1, 12))
+    # hyper-parameters are read off the two torch optimizers; anything but train.py:72-73's plain Adam is refused
+    o_e, o_g = torch.optim.Adam(m.emg_net.parameters(), lr=2e-3), torch.optim.Adam(m.glove_net.parameters(), lr=5e-3)
+    s2 = from_optimizers(m, [o_e, o_g])
+    assert s2.lr.tolist() == [2e-3, 5e-3] and s2.betas == (0.9, 0.999) and s2.eps == 1e-8
+    with pytest.raises(RuntimeError, match="weight_decay"):
+        from_optimizers(m, [torch.optim.Adam(m.emg_net.parameters(), lr=1e-3, weight_decay=1e-2), o_g])
+    with pytest.raises(NotImplementedError):
+        LeanTrainStep(Model(dict(hp), prediction=True, device="cpu"), 1e-3, 1e-3)
+
+
 def test_cabi_exports_every_declared_symbol():
     """libcpros.so loads and exports exactly what include/cpros.h declares."""
     _lib.build()
