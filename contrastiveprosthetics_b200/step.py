@@ -22,6 +22,7 @@ import torch
 
 from . import _lib
 from . import dist as cpdist
+from .constants import MAX_TASKS_TRAIN
 from .models import _encoder_backward_into, _head_launch
 
 _ALIGN = 128            # elements: every tensor of the flat buckets starts on a 512-byte boundary, like a torch allocation
@@ -111,11 +112,13 @@ class LeanTrainStep:
         net = m.emg_net
         if not m.training:
             raise RuntimeError("LeanTrainStep: model.set_train() first")
+        if EMG.dim() != 5 or EMG.shape[1] != MAX_TASKS_TRAIN:
+            raise RuntimeError(f"expected a (B, {MAX_TASKS_TRAIN}, W, 1, 12) batch, got {tuple(EMG.shape)}")
         L = _lib.lib()
         P = _lib.ptr
         _lib.check(L.cp_step_prologue(self._reg_ptrs, self._reg_sizes, self._n_reg, P(self.norms), P(self.counters), 2,
                                       P(self._ws), self._ws.numel(), _lib.stream()), "cp_step_prologue")
-        B, T, W = EMG.shape[0], EMG.shape[1], EMG.shape[2]
+        B, W = EMG.shape[0], EMG.shape[2]
         emb, ctx = net.encode_flat(EMG, raw=True)
         w, b = m.glove_net.table_params()
         loss, pred, ncor, _, d_emb, _, _ = _head_launch(emb, w, b, B, W, True, False,

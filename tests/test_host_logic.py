@@ -117,6 +117,8 @@ def test_lean_step_host_layout(adabn, n_reg):
     m.set_train()
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         s(torch.zeros(2, 41, 1, 1, 12))
+    with pytest.raises(RuntimeError, match="expected a"):
+        s(torch.zeros(2, 40, 1, 1, 12))
     # hyper-parameters are read off the two torch optimizers; anything but train.py:72-73's plain Adam is refused
     o_e, o_g = torch.optim.Adam(m.emg_net.parameters(), lr=2e-3), torch.optim.Adam(m.glove_net.parameters(), lr=5e-3)
     s2 = from_optimizers(m, [o_e, o_g])
