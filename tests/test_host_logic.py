@@ -285,6 +285,19 @@ for i, p in enumerate(ps):
     p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
 cpdist.FlatGradAllReduce(ps)()
 assert torch.allclose(ps[0].grad, torch.full((5, 3), 1.5)) and torch.allclose(ps[1].grad, torch.full((7,), 3.0))
+# the lean step's gradient bucket is averaged IN PLACE (one all-reduce, no pack / unpack): every parameter's .grad is a
+# view of it, so each rank then sees the mean of the ranks' gradients (step.LeanTrainStep._all_reduce)
+from contrastiveprosthetics_b200.models import Model
+from contrastiveprosthetics_b200.step import LeanTrainStep
+torch.manual_seed(42)
+lean = LeanTrainStep(Model({'d_e': 16, 'dp_emg': 0.5, 'dp_glove': 0., 'reg_emg': 1e-5, 'reg_glove': 1e-5}, device="cpu"),
+                     1e-3, 1e-3, sync_grads=True)
+assert lean.sync_grads
+for i, g in enumerate(lean.grad_views):
+    g.fill_(float((rank + 1) * (i + 1)))
+lean._all_reduce()
+for i, p in enumerate(lean.params):
+    assert torch.equal(p.grad, torch.full_like(p, 1.5 * (i + 1))), i
 # trial sharding + exact integer reduction
 masks, _ = subset.make_trials(sizes=[3], trials_per_size=9, seed=1)
 lo, hi = subset.shard_trials(len(masks), rank, world)
